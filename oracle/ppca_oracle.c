@@ -1,0 +1,826 @@
+/*
+ * ppca_oracle.c — CPU restatement of the viodotcom/ppca_rs hot path.
+ *
+ * THIS IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only tests/, __graft_entry__.smoke()
+ * and bench.py's cpu_baseline / --impl reference legs may load it.  The product path
+ * (ppca_rs_b200) never links, imports or calls anything in this directory.
+ *
+ * Parity status: the Rust reference cannot be built here (no cargo/rustc), so this file
+ * restates its algorithm from the sources, in the reference's own operation order
+ * (row gather, Woodbury form with explicit inverse, ln(det) via LU, Householder QR).
+ * It is PINNED only on the two known-answer tests the reference holds for this path
+ * (ppca/src/ppca_model.rs:658-671: quadratic_form = 34.219288, covariance_log_det = -3.49328)
+ * and cross-checked against independent dense numpy formulas in tests/.  Everything
+ * else (infer, iterate, mixtures, priors, any k > 3 LU path) is "parity unpinned":
+ * the reference has no fixture for it.
+ *
+ * Third-party arithmetic that is NOT under /root/reference (nalgebra 0.32.2,
+ * Cargo.lock:181-182) is restated from its published algorithms:
+ *   try_inverse : closed form for dim <= 3, LU with partial pivoting above
+ *                 (nalgebra also has a closed form for dim 4; rounding-level difference)
+ *   determinant : closed form for dim <= 3, LU above
+ *   qr().solve  : Householder QR, Q^T b, back substitution; None on an exactly-zero pivot
+ *   svd         : restated as one-sided Jacobi (only U*S is used, sorted descending)
+ *
+ * Conventions: all matrices row-major f64.  X is N x d with non-finite entries meaning
+ * "missing" (dataset.rs:19-22 mask_non_finite).  C is d x k, mu is d, sigma is the noise
+ * STANDARD DEVIATION (ppca_model.rs:77-80).
+ *
+ * Threading: OpenMP `parallel for schedule(dynamic)` over samples stands in for rayon's
+ * work-stealing par_iter; reductions are per-thread partials summed at the end (rayon's
+ * reduce order is nondeterministic too, ppca_model.rs:148,290-293,350-358).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define LN_2PI 1.8378770664093453 /* ppca_model.rs:16 */
+
+#define EXPORT __attribute__((visibility("default")))
+
+/* ------------------------------------------------------------------------------------------
+ * small dense helpers (row-major)
+ * ---------------------------------------------------------------------------------------- */
+
+static void *xmalloc(size_t n) {
+  void *p = malloc(n ? n : 1);
+  if (!p) abort();
+  return p;
+}
+
+/* C = A^T A, A is r x k  (output_covariance.rs:57-59 inner_product) */
+static void gram(const double *A, int r, int k, double *G) {
+  memset(G, 0, sizeof(double) * k * k);
+  for (int i = 0; i < r; ++i) {
+    const double *row = A + (size_t)i * k;
+    for (int a = 0; a < k; ++a) {
+      double ra = row[a];
+      double *g = G + (size_t)a * k;
+      for (int b = 0; b < k; ++b) g[b] += ra * row[b];
+    }
+  }
+}
+
+/* out = A(m x p) * B(p x n) */
+static void matmul(const double *A, const double *B, int m, int p, int n, double *out) {
+  memset(out, 0, sizeof(double) * m * n);
+  for (int i = 0; i < m; ++i)
+    for (int l = 0; l < p; ++l) {
+      double a = A[(size_t)i * p + l];
+      const double *b = B + (size_t)l * n;
+      double *o = out + (size_t)i * n;
+      for (int j = 0; j < n; ++j) o[j] += a * b[j];
+    }
+}
+
+/* LU with partial pivoting, in place.  perm[i] = row swapped with i at step i.
+ * Mirrors nalgebra LU::new: pivot = argmax |a_ji|, j >= i; a zero pivot column is skipped. */
+static void lu_decompose(double *A, int n, int *perm, int *nswaps) {
+  *nswaps = 0;
+  for (int i = 0; i < n; ++i) {
+    int piv = i;
+    double best = fabs(A[(size_t)i * n + i]);
+    for (int j = i + 1; j < n; ++j) {
+      double v = fabs(A[(size_t)j * n + i]);
+      if (v > best) { best = v; piv = j; }
+    }
+    perm[i] = piv;
+    double diag = A[(size_t)piv * n + i];
+    if (diag == 0.0) continue; /* no non-zero entry on this column */
+    if (piv != i) {
+      for (int c = 0; c < n; ++c) {
+        double t = A[(size_t)i * n + c];
+        A[(size_t)i * n + c] = A[(size_t)piv * n + c];
+        A[(size_t)piv * n + c] = t;
+      }
+      ++*nswaps;
+    }
+    double inv = 1.0 / diag;
+    for (int j = i + 1; j < n; ++j) {
+      double f = A[(size_t)j * n + i] * inv;
+      A[(size_t)j * n + i] = f;
+      for (int c = i + 1; c < n; ++c) A[(size_t)j * n + c] -= f * A[(size_t)i * n + c];
+    }
+  }
+}
+
+/* try_inverse (output_covariance.rs:66-70).  Returns 0 on a singular matrix.  work: n*n + n ints */
+static int mat_inverse(const double *M, int n, double *inv, double *work, int *iwork) {
+  if (n == 0) return 1;
+  if (n == 1) {
+    if (M[0] == 0.0) return 0;
+    inv[0] = 1.0 / M[0];
+    return 1;
+  }
+  if (n == 2) {
+    double m11 = M[0], m12 = M[1], m21 = M[2], m22 = M[3];
+    double det = m11 * m22 - m21 * m12;
+    if (det == 0.0) return 0;
+    inv[0] = m22 / det; inv[1] = -m12 / det;
+    inv[2] = -m21 / det; inv[3] = m11 / det;
+    return 1;
+  }
+  if (n == 3) {
+    double m11 = M[0], m12 = M[1], m13 = M[2];
+    double m21 = M[3], m22 = M[4], m23 = M[5];
+    double m31 = M[6], m32 = M[7], m33 = M[8];
+    double minor_11 = m22 * m33 - m32 * m23;
+    double minor_12 = m21 * m33 - m31 * m23;
+    double minor_13 = m21 * m32 - m31 * m22;
+    double det = m11 * minor_11 - m12 * minor_12 + m13 * minor_13;
+    if (det == 0.0) return 0;
+    inv[0] = minor_11 / det;
+    inv[1] = (m13 * m32 - m33 * m12) / det;
+    inv[2] = (m12 * m23 - m22 * m13) / det;
+    inv[3] = -minor_12 / det;
+    inv[4] = (m11 * m33 - m31 * m13) / det;
+    inv[5] = (m13 * m21 - m23 * m11) / det;
+    inv[6] = minor_13 / det;
+    inv[7] = (m12 * m31 - m32 * m11) / det;
+    inv[8] = (m11 * m22 - m21 * m12) / det;
+    return 1;
+  }
+  double *LU = work;
+  memcpy(LU, M, sizeof(double) * n * n);
+  int nsw;
+  lu_decompose(LU, n, iwork, &nsw);
+  for (int i = 0; i < n; ++i)
+    if (LU[(size_t)i * n + i] == 0.0) return 0;
+  /* solve LU X = P I */
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) inv[(size_t)i * n + j] = (i == j) ? 1.0 : 0.0;
+  for (int i = 0; i < n; ++i) {
+    int p = iwork[i];
+    if (p != i)
+      for (int c = 0; c < n; ++c) {
+        double t = inv[(size_t)i * n + c];
+        inv[(size_t)i * n + c] = inv[(size_t)p * n + c];
+        inv[(size_t)p * n + c] = t;
+      }
+  }
+  for (int i = 1; i < n; ++i) /* unit lower */
+    for (int l = 0; l < i; ++l) {
+      double f = LU[(size_t)i * n + l];
+      if (f != 0.0)
+        for (int c = 0; c < n; ++c) inv[(size_t)i * n + c] -= f * inv[(size_t)l * n + c];
+    }
+  for (int i = n - 1; i >= 0; --i) { /* upper */
+    for (int l = i + 1; l < n; ++l) {
+      double f = LU[(size_t)i * n + l];
+      if (f != 0.0)
+        for (int c = 0; c < n; ++c) inv[(size_t)i * n + c] -= f * inv[(size_t)l * n + c];
+    }
+    double dinv = 1.0 / LU[(size_t)i * n + i];
+    for (int c = 0; c < n; ++c) inv[(size_t)i * n + c] *= dinv;
+  }
+  return 1;
+}
+
+/* determinant (output_covariance.rs:117) */
+static double mat_det(const double *M, int n, double *work, int *iwork) {
+  if (n == 0) return 1.0;
+  if (n == 1) return M[0];
+  if (n == 2) return M[0] * M[3] - M[2] * M[1];
+  if (n == 3) {
+    double e11 = M[0], e12 = M[1], e13 = M[2];
+    double e21 = M[3], e22 = M[4], e23 = M[5];
+    double e31 = M[6], e32 = M[7], e33 = M[8];
+    double minor_1 = e22 * e33 - e32 * e23;
+    double minor_2 = e21 * e33 - e31 * e23;
+    double minor_3 = e21 * e32 - e31 * e22;
+    return e11 * minor_1 - e12 * minor_2 + e13 * minor_3;
+  }
+  double *LU = work;
+  memcpy(LU, M, sizeof(double) * n * n);
+  int nsw;
+  lu_decompose(LU, n, iwork, &nsw);
+  double det = 1.0;
+  for (int i = 0; i < n; ++i) det *= LU[(size_t)i * n + i];
+  return (nsw & 1) ? -det : det;
+}
+
+/* Householder QR solve of A x = b (A n x n, destroyed; b overwritten with x).
+ * Returns 0 ("None") when a diagonal entry of R is exactly zero
+ * (ppca_model.rs:310-322 falls back to the old row in that case). */
+static int qr_solve(double *A, int n, double *b, double *diag) {
+  for (int i = 0; i < n; ++i) {
+    /* reflection axis from column i, rows i.. */
+    double sq = 0.0;
+    for (int r = i; r < n; ++r) sq += A[(size_t)r * n + i] * A[(size_t)r * n + i];
+    double norm = sqrt(sq);
+    double a0 = A[(size_t)i * n + i];
+    double modulus = fabs(a0);
+    double sign = (a0 < 0.0 || (a0 == 0.0 && signbit(a0))) ? -1.0 : 1.0;
+    double signed_norm = sign * norm;
+    double factor = (sq + modulus * norm) * 2.0;
+    A[(size_t)i * n + i] = a0 + signed_norm;
+    if (factor != 0.0) {
+      double s = sqrt(factor);
+      for (int r = i; r < n; ++r) A[(size_t)r * n + i] /= s;
+      diag[i] = -signed_norm;
+      /* reflect the remaining columns and b: v -= 2 (axis . v) axis */
+      for (int c = i + 1; c < n; ++c) {
+        double dot = 0.0;
+        for (int r = i; r < n; ++r) dot += A[(size_t)r * n + i] * A[(size_t)r * n + c];
+        dot *= 2.0;
+        for (int r = i; r < n; ++r) A[(size_t)r * n + c] -= dot * A[(size_t)r * n + i];
+      }
+      double dot = 0.0;
+      for (int r = i; r < n; ++r) dot += A[(size_t)r * n + i] * b[r];
+      dot *= 2.0;
+      for (int r = i; r < n; ++r) b[r] -= dot * A[(size_t)r * n + i];
+    } else {
+      diag[i] = signed_norm;
+    }
+  }
+  /* back substitution with R (strict upper part in A, diagonal in diag) */
+  for (int i = n - 1; i >= 0; --i) {
+    if (diag[i] == 0.0) return 0;
+    double v = b[i];
+    for (int c = i + 1; c < n; ++c) v -= A[(size_t)i * n + c] * b[c];
+    b[i] = v / diag[i];
+  }
+  return 1;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * per-thread scratch for the per-sample algebra
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  int d, k;
+  double *Co;    /* d x k   gathered rows (output_covariance.rs:123-131 masked) */
+  double *xs;    /* d       compressed centred sample (utils.rs:56-61) */
+  double *G, *M, *Minv, *GM, *work; /* k x k */
+  double *T;     /* k x d   estimator transform */
+  double *t;     /* k */
+  int *iwork;
+} scratch_t;
+
+static void scratch_init(scratch_t *s, int d, int k) {
+  s->d = d; s->k = k;
+  s->Co = xmalloc(sizeof(double) * d * (k ? k : 1));
+  s->xs = xmalloc(sizeof(double) * d);
+  s->G = xmalloc(sizeof(double) * k * k);
+  s->M = xmalloc(sizeof(double) * k * k);
+  s->Minv = xmalloc(sizeof(double) * k * k);
+  s->GM = xmalloc(sizeof(double) * k * k);
+  s->work = xmalloc(sizeof(double) * (k * k + k));
+  s->T = xmalloc(sizeof(double) * (k ? k : 1) * d);
+  s->t = xmalloc(sizeof(double) * (k ? k : 1));
+  s->iwork = xmalloc(sizeof(int) * (k ? k : 1));
+}
+static void scratch_free(scratch_t *s) {
+  free(s->Co); free(s->xs); free(s->G); free(s->M); free(s->Minv); free(s->GM);
+  free(s->work); free(s->T); free(s->t); free(s->iwork);
+}
+
+/* gather observed rows; returns d_obs.  Fills s->Co and s->xs (= mask(x - mu)). */
+static int gather(scratch_t *s, const double *x, const double *C, const double *mu) {
+  int d = s->d, k = s->k, r = 0;
+  for (int i = 0; i < d; ++i)
+    if (isfinite(x[i])) {
+      memcpy(s->Co + (size_t)r * k, C + (size_t)i * k, sizeof(double) * k);
+      s->xs[r] = x[i] - mu[i];
+      ++r;
+    }
+  return r;
+}
+
+/* inner_matrix = sigma^2 I + Co^T Co (output_covariance.rs:61-64); inner_inverse (:66-70) */
+static void inner_matrix(scratch_t *s, int r, double sigma) {
+  int k = s->k;
+  gram(s->Co, r, k, s->G);
+  double s2 = sigma * sigma; /* powi(2) */
+  for (int a = 0; a < k; ++a)
+    for (int b = 0; b < k; ++b) s->M[a * k + b] = ((a == b) ? s2 : 0.0) + s->G[a * k + b];
+}
+static void inner_inverse(scratch_t *s, int r, double sigma) {
+  inner_matrix(s, r, sigma);
+  if (!mat_inverse(s->M, s->k, s->Minv, s->work, s->iwork)) abort(); /* "inner matrix is always invertible" */
+}
+
+/* quadratic_form (output_covariance.rs:133-142) */
+static double quadratic_form(scratch_t *s, int r, double sigma) {
+  int k = s->k;
+  double ns = 0.0;
+  for (int i = 0; i < r; ++i) ns += s->xs[i] * s->xs[i];
+  for (int a = 0; a < k; ++a) s->t[a] = 0.0;
+  for (int i = 0; i < r; ++i)
+    for (int a = 0; a < k; ++a) s->t[a] += s->Co[(size_t)i * k + a] * s->xs[i];
+  inner_inverse(s, r, sigma);
+  /* (t^T * Minv) * t */
+  double q = 0.0;
+  for (int b = 0; b < k; ++b) {
+    double u = 0.0;
+    for (int a = 0; a < k; ++a) u += s->t[a] * s->Minv[a * k + b];
+    q += u * s->t[b];
+  }
+  return (ns - q) / (sigma * sigma);
+}
+
+/* covariance_log_det (output_covariance.rs:115-121) */
+static double covariance_log_det(scratch_t *s, int r, double sigma) {
+  inner_matrix(s, r, sigma);
+  return log(mat_det(s->M, s->k, s->work, s->iwork)) + log(sigma) * 2.0 * ((double)r - (double)s->k);
+}
+
+/* llk_one (ppca_model.rs:124-139) */
+static double llk_one(scratch_t *s, const double *x, const double *C, const double *mu, double sigma) {
+  int r = gather(s, x, C, mu);
+  if (r == 0) return 0.0;
+  double q = quadratic_form(s, r, sigma);
+  double ld = covariance_log_det(s, r, sigma);
+  return -q / 2.0 - ld / 2.0 - LN_2PI / 2.0 * (double)r;
+}
+
+/* estimator_transform (output_covariance.rs:90-94): T = (Co^T - G Minv Co^T) / sigma^2, k x r */
+static void estimator_transform(scratch_t *s, int r, double sigma) {
+  int k = s->k;
+  inner_inverse(s, r, sigma);                 /* recomputes G, M, Minv, as the reference does */
+  matmul(s->G, s->Minv, k, k, k, s->GM);      /* inner_product() * inner_inverse() */
+  double s2 = sigma * sigma;
+  for (int a = 0; a < k; ++a)
+    for (int i = 0; i < r; ++i) {
+      double acc = 0.0;
+      for (int b = 0; b < k; ++b) acc += s->GM[a * k + b] * s->Co[(size_t)i * k + b];
+      s->T[(size_t)a * r + i] = (s->Co[(size_t)i * k + a] - acc) / s2;
+    }
+}
+
+/* infer_one (ppca_model.rs:195-208): z (k), cov (k x k) */
+static void infer_one(scratch_t *s, const double *x, const double *C, const double *mu, double sigma,
+                      double *z, double *cov) {
+  int k = s->k;
+  int r = gather(s, x, C, mu);
+  if (r == 0) { /* uninferred(): zeros, identity (ppca_model.rs:98-104) */
+    for (int a = 0; a < k; ++a) z[a] = 0.0;
+    for (int a = 0; a < k; ++a)
+      for (int b = 0; b < k; ++b) cov[a * k + b] = (a == b) ? 1.0 : 0.0;
+    return;
+  }
+  estimator_transform(s, r, sigma);
+  for (int a = 0; a < k; ++a) {
+    double acc = 0.0;
+    for (int i = 0; i < r; ++i) acc += s->T[(size_t)a * r + i] * s->xs[i];
+    z[a] = acc;
+  }
+  estimator_transform(s, r, sigma);           /* estimator_covariance() calls it AGAIN (:98-101) */
+  for (int a = 0; a < k; ++a)
+    for (int b = 0; b < k; ++b) {
+      double acc = 0.0;
+      for (int i = 0; i < r; ++i) acc += s->T[(size_t)a * r + i] * s->Co[(size_t)i * k + b];
+      cov[a * k + b] = ((a == b) ? 1.0 : 0.0) - acc;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * exported API
+ * ---------------------------------------------------------------------------------------- */
+
+EXPORT int oracle_num_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+/* KAT hooks: full (unmasked) OutputCovariance of a d x k transform. */
+EXPORT double oracle_quadratic_form(int d, int k, const double *C, double sigma, const double *x) {
+  scratch_t s; scratch_init(&s, d, k);
+  memcpy(s.Co, C, sizeof(double) * d * k);
+  memcpy(s.xs, x, sizeof(double) * d);
+  double q = quadratic_form(&s, d, sigma);
+  scratch_free(&s);
+  return q;
+}
+EXPORT double oracle_covariance_log_det(int d, int k, const double *C, double sigma) {
+  scratch_t s; scratch_init(&s, d, k);
+  memcpy(s.Co, C, sizeof(double) * d * k);
+  double v = covariance_log_det(&s, d, sigma);
+  scratch_free(&s);
+  return v;
+}
+
+/* Dataset::empty_dimensions (dataset.rs:194-222): out[i] = 1 when dimension i is masked in all samples */
+EXPORT void oracle_empty_dimensions(int64_t n, int d, const double *X, uint8_t *out) {
+  for (int i = 0; i < d; ++i) out[i] = (n > 0) ? 1 : 0;
+  if (n == 0) return;
+  for (int64_t s = 0; s < n; ++s)
+    for (int i = 0; i < d; ++i)
+      if (isfinite(X[s * d + i])) out[i] = 0;
+}
+
+/* PPCAModel::llks (ppca_model.rs:152-159) */
+EXPORT void oracle_llks(int64_t n, int d, int k, const double *X, const double *C, const double *mu,
+                        double sigma, double *out) {
+#pragma omp parallel
+  {
+    scratch_t s; scratch_init(&s, d, k);
+#pragma omp for schedule(dynamic, 64)
+    for (int64_t i = 0; i < n; ++i) out[i] = llk_one(&s, X + i * d, C, mu, sigma);
+    scratch_free(&s);
+  }
+}
+
+/* PPCAModel::llk (ppca_model.rs:142-149) */
+EXPORT double oracle_llk(int64_t n, int d, int k, const double *X, const double *w, const double *C,
+                         const double *mu, double sigma) {
+  double total = 0.0;
+#pragma omp parallel reduction(+ : total)
+  {
+    scratch_t s; scratch_init(&s, d, k);
+#pragma omp for schedule(dynamic, 64)
+    for (int64_t i = 0; i < n; ++i) total += llk_one(&s, X + i * d, C, mu, sigma) * w[i];
+    scratch_free(&s);
+  }
+  return total;
+}
+
+/* PPCAModel::infer (ppca_model.rs:221-227): Z is n x k, COV is n x k x k */
+EXPORT void oracle_infer(int64_t n, int d, int k, const double *X, const double *C, const double *mu,
+                         double sigma, double *Z, double *COV) {
+#pragma omp parallel
+  {
+    scratch_t s; scratch_init(&s, d, k);
+#pragma omp for schedule(dynamic, 64)
+    for (int64_t i = 0; i < n; ++i)
+      infer_one(&s, X + i * d, C, mu, sigma, Z + i * k, COV + i * (size_t)k * k);
+    scratch_free(&s);
+  }
+}
+
+/* smoothed (ppca_model.rs:454-456) / extrapolated (:460-463, utils.rs:137-153 choose) given Z */
+static void reconstruct(int d, int k, const double *x, const double *z, const double *C, const double *mu,
+                        int extrapolate, double *out) {
+  for (int i = 0; i < d; ++i) {
+    double acc = 0.0;
+    for (int a = 0; a < k; ++a) acc += C[(size_t)i * k + a] * z[a];
+    double sm = acc + mu[i];
+    out[i] = (extrapolate && isfinite(x[i])) ? x[i] : sm;
+  }
+}
+
+/* PPCAModel::smooth (ppca_model.rs:237-244) and ::extrapolate (:254-261) */
+EXPORT void oracle_smooth(int64_t n, int d, int k, const double *X, const double *C, const double *mu,
+                          double sigma, int extrapolate, double *out) {
+#pragma omp parallel
+  {
+    scratch_t s; scratch_init(&s, d, k);
+    double *z = xmalloc(sizeof(double) * (k ? k : 1));
+    double *cov = xmalloc(sizeof(double) * (k ? k * k : 1));
+#pragma omp for schedule(dynamic, 64)
+    for (int64_t i = 0; i < n; ++i) {
+      infer_one(&s, X + i * d, C, mu, sigma, z, cov);
+      reconstruct(d, k, X + i * d, z, C, mu, extrapolate, out + i * d);
+    }
+    free(z); free(cov);
+    scratch_free(&s);
+  }
+}
+
+/* Prior (prior.rs:8-29).  has_* are flags; mean_prec is the d x d INVERSE of the mean covariance
+ * (prior.rs:36-41, computed by the caller with try_inverse semantics). */
+typedef struct {
+  int has_mean_prior;
+  const double *mean;       /* d */
+  const double *mean_prec;  /* d x d */
+  int has_noise_prior;
+  double alpha, beta;
+  double transformation_precision;
+} oracle_prior_t;
+
+/* PPCAModel::iterate_with_prior (ppca_model.rs:277-393).
+ * prior may be NULL (Prior::default()).  Returns 0 on success. */
+EXPORT int oracle_iterate(int64_t n, int d, int k, const double *X, const double *w, const double *C,
+                          const double *mu, double sigma, const oracle_prior_t *prior, double *C_out,
+                          double *mu_out, double *sigma_out) {
+  if (n <= 0) return 1;
+  size_t kk = (size_t)k * k;
+  /* :278 let inferred = self.infer(dataset)  — materialised, N (k + k^2) doubles */
+  double *Z = xmalloc(sizeof(double) * n * (k ? k : 1));
+  double *COV = xmalloc(sizeof(double) * n * (kk ? kk : 1));
+  oracle_infer(n, d, k, X, C, mu, sigma, Z, COV);
+
+  /* :281-293 total_cross_moment = sum_n w fillna(x - mu) z^T  (d x k) */
+  double *tcm = xmalloc(sizeof(double) * d * (k ? k : 1));
+  memset(tcm, 0, sizeof(double) * d * k);
+#pragma omp parallel
+  {
+    double *loc = xmalloc(sizeof(double) * d * (k ? k : 1));
+    memset(loc, 0, sizeof(double) * d * k);
+#pragma omp for schedule(dynamic, 64)
+    for (int64_t s = 0; s < n; ++s) {
+      const double *x = X + s * d;
+      const double *z = Z + s * k;
+      for (int i = 0; i < d; ++i) {
+        if (!isfinite(x[i])) continue;
+        double c = w[s] * (x[i] - mu[i]);
+        for (int a = 0; a < k; ++a) loc[(size_t)i * k + a] += c * z[a];
+      }
+    }
+#pragma omp critical
+    for (size_t j = 0; j < (size_t)d * k; ++j) tcm[j] += loc[j];
+    free(loc);
+  }
+
+  /* :294-324 per output dimension (parallel over d, serial over N) */
+  double tau = prior ? prior->transformation_precision : 0.0;
+#pragma omp parallel
+  {
+    double *S = xmalloc(sizeof(double) * (kk ? kk : 1));
+    double *tmp = xmalloc(sizeof(double) * (kk ? kk : 1));
+    double *rhs = xmalloc(sizeof(double) * (k ? k : 1));
+    double *diag = xmalloc(sizeof(double) * (k ? k : 1));
+#pragma omp for schedule(dynamic, 1)
+    for (int i = 0; i < d; ++i) {
+      memset(S, 0, sizeof(double) * kk);
+      for (int64_t s = 0; s < n; ++s) {
+        if (!isfinite(X[s * d + i])) continue;
+        const double *z = Z + s * k;
+        const double *cov = COV + s * kk;
+        /* weight * inferred.second_moment()  (:303, :437-439) */
+        for (int a = 0; a < k; ++a)
+          for (int b = 0; b < k; ++b) tmp[a * k + b] = z[a] * z[b] + cov[a * k + b];
+        double ws = w[s];
+        for (size_t j = 0; j < kk; ++j) tmp[j] *= ws;
+        for (size_t j = 0; j < kk; ++j) S[j] += tmp[j];
+      }
+      for (int a = 0; a < k; ++a) S[a * k + a] += tau; /* :307 */
+      for (int a = 0; a < k; ++a) rhs[a] = tcm[(size_t)i * k + a];
+      if (qr_solve(S, k, rhs, diag))
+        for (int a = 0; a < k; ++a) C_out[(size_t)i * k + a] = rhs[a];
+      else /* keep old row (:313-321) */
+        for (int a = 0; a < k; ++a) C_out[(size_t)i * k + a] = C[(size_t)i * k + a];
+    }
+    free(S); free(tmp); free(rhs); free(diag);
+  }
+
+  /* :328-358 noise / mean statistics over non-empty samples */
+  double square_error = 0.0, dev_sq = 0.0;
+  double *total_dev = xmalloc(sizeof(double) * d);
+  double *totals = xmalloc(sizeof(double) * d);
+  memset(total_dev, 0, sizeof(double) * d);
+  memset(totals, 0, sizeof(double) * d);
+  int64_t n_nonempty = 0;
+#pragma omp parallel reduction(+ : square_error, dev_sq, n_nonempty)
+  {
+    scratch_t sc; scratch_init(&sc, d, k);
+    double *ldev = xmalloc(sizeof(double) * d);
+    double *ltot = xmalloc(sizeof(double) * d);
+    double *CS = xmalloc(sizeof(double) * (size_t)d * (k ? k : 1));
+    memset(ldev, 0, sizeof(double) * d);
+    memset(ltot, 0, sizeof(double) * d);
+#pragma omp for schedule(dynamic, 64)
+    for (int64_t s = 0; s < n; ++s) {
+      const double *x = X + s * d;
+      int r = gather(&sc, x, C, mu); /* sub_covariance = masked(mask) (:336) */
+      if (r == 0) continue;          /* filter !is_empty (:333) */
+      ++n_nonempty;
+      const double *z = Z + s * k;
+      const double *cov = COV + s * kk;
+      /* (sub_transform * covariance).dot(sub_transform)  (:345) */
+      matmul(sc.Co, cov, r, k, k, CS);
+      double tr = 0.0;
+      for (size_t j = 0; j < (size_t)r * k; ++j) tr += CS[j] * sc.Co[j];
+      square_error += w[s] * tr;
+      /* deviation = fillna(x - C z - mu) (:338-342) */
+      double nsq = 0.0;
+      for (int i = 0; i < d; ++i) {
+        if (!isfinite(x[i])) continue;
+        double cz = 0.0;
+        for (int a = 0; a < k; ++a) cz += C[(size_t)i * k + a] * z[a];
+        double dv = x[i] - cz - mu[i];
+        nsq += dv * dv;
+        ldev[i] += w[s] * dv;
+        ltot[i] += w[s];
+      }
+      dev_sq += w[s] * nsq;
+    }
+#pragma omp critical
+    for (int i = 0; i < d; ++i) { total_dev[i] += ldev[i]; totals[i] += ltot[i]; }
+    free(ldev); free(ltot); free(CS);
+    scratch_free(&sc);
+  }
+  int rc = 0;
+  if (n_nonempty == 0) rc = 2; /* .expect("non-empty dataset") (:358) */
+
+  double tot_sum = 0.0;
+  for (int i = 0; i < d; ++i) tot_sum += totals[i];
+  double noise_sq;
+  if (prior && prior->has_noise_prior) /* :360-368 */
+    noise_sq = ((square_error + dev_sq) / 2.0 + prior->beta) / (tot_sum / 2.0 + prior->alpha + 1.0);
+  else
+    noise_sq = (square_error + dev_sq) / tot_sum; /* :370 */
+
+  for (int i = 0; i < d; ++i) /* :373-377 */
+    mu_out[i] = ((totals[i] > 0.0) ? total_dev[i] / totals[i] : 0.0) + mu[i];
+
+  if (prior && prior->has_mean_prior) { /* :379-384, prior.rs:97-110 */
+    double *P = xmalloc(sizeof(double) * (size_t)d * d);
+    double *num = xmalloc(sizeof(double) * d);
+    double *diag = xmalloc(sizeof(double) * d);
+    for (int i = 0; i < d; ++i) {
+      double acc = 0.0;
+      for (int j = 0; j < d; ++j) {
+        double prec = (i == j) ? totals[i] / noise_sq : 0.0;
+        P[(size_t)i * d + j] = prior->mean_prec[(size_t)i * d + j] + prec;
+        acc += prior->mean_prec[(size_t)i * d + j] * prior->mean[j];
+      }
+      num[i] = acc + (totals[i] / noise_sq) * mu_out[i];
+    }
+    if (!qr_solve(P, d, num, diag)) rc = 3; /* "total precision matrix is always invertible" */
+    for (int i = 0; i < d; ++i) mu_out[i] = num[i];
+    free(P); free(num); free(diag);
+  }
+  *sigma_out = sqrt(noise_sq); /* :389 */
+
+  free(Z); free(COV); free(tcm); free(total_dev); free(totals);
+  return rc;
+}
+
+/* to_canonical (ppca_model.rs:398-425): C <- U S from the SVD (singular values descending), then each
+ * column times signum(sum(column)) with signum(+0.0) = +1.  One-sided Jacobi: rotating column pairs of C
+ * until mutually orthogonal leaves exactly U S. */
+EXPORT void oracle_to_canonical(int d, int k, const double *C, double *out) {
+  memcpy(out, C, sizeof(double) * d * k);
+  if (k == 0) return;
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    double off = 0.0;
+    for (int p = 0; p < k - 1; ++p)
+      for (int q = p + 1; q < k; ++q) {
+        double app = 0, aqq = 0, apq = 0;
+        for (int i = 0; i < d; ++i) {
+          double a = out[(size_t)i * k + p], b = out[(size_t)i * k + q];
+          app += a * a; aqq += b * b; apq += a * b;
+        }
+        if (apq == 0.0) continue;
+        double rel = fabs(apq) / sqrt(app * aqq);
+        if (rel > off) off = rel;
+        if (rel < 1e-17) continue;
+        double zeta = (aqq - app) / (2.0 * apq);
+        double t = ((zeta >= 0) ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+        double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+        for (int i = 0; i < d; ++i) {
+          double a = out[(size_t)i * k + p], b = out[(size_t)i * k + q];
+          out[(size_t)i * k + p] = c * a - s * b;
+          out[(size_t)i * k + q] = s * a + c * b;
+        }
+      }
+    if (off < 1e-15) break;
+  }
+  /* sort columns by norm, descending */
+  double *nrm = xmalloc(sizeof(double) * k);
+  int *ord = xmalloc(sizeof(int) * k);
+  for (int a = 0; a < k; ++a) {
+    double s = 0;
+    for (int i = 0; i < d; ++i) s += out[(size_t)i * k + a] * out[(size_t)i * k + a];
+    nrm[a] = s; ord[a] = a;
+  }
+  for (int a = 1; a < k; ++a) { /* insertion sort, stable */
+    int o = ord[a], j = a - 1;
+    while (j >= 0 && nrm[ord[j]] < nrm[o]) { ord[j + 1] = ord[j]; --j; }
+    ord[j + 1] = o;
+  }
+  double *tmp = xmalloc(sizeof(double) * d * k);
+  memcpy(tmp, out, sizeof(double) * d * k);
+  for (int a = 0; a < k; ++a) {
+    double sum = 0;
+    for (int i = 0; i < d; ++i) sum += tmp[(size_t)i * k + ord[a]];
+    double sg = isnan(sum) ? NAN : ((sum < 0.0 || (sum == 0.0 && signbit(sum))) ? -1.0 : 1.0);
+    for (int i = 0; i < d; ++i) out[(size_t)i * k + a] = tmp[(size_t)i * k + ord[a]] * sg;
+  }
+  free(nrm); free(ord); free(tmp);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * mixtures (mix.rs)
+ * ---------------------------------------------------------------------------------------- */
+
+/* robust_log_softmax (mix.rs:14-18), in place */
+static void robust_log_softmax(double *v, int m) {
+  double mx = v[0];
+  for (int j = 1; j < m; ++j) if (v[j] > mx) mx = v[j];
+  double s = 0.0;
+  for (int j = 0; j < m; ++j) s += exp(v[j] - mx);
+  double ln = log(s);
+  for (int j = 0; j < m; ++j) v[j] = v[j] - mx - ln;
+}
+/* robust_log_softnorm (mix.rs:21-25) */
+static double robust_log_softnorm(const double *v, int m) {
+  double mx = v[0];
+  for (int j = 1; j < m; ++j) if (v[j] > mx) mx = v[j];
+  double s = 0.0;
+  for (int j = 0; j < m; ++j) s += exp(v[j] - mx);
+  return mx + log(s);
+}
+EXPORT void oracle_log_softmax(double *v, int m) { robust_log_softmax(v, m); }
+
+/* Mixture parameters are passed concatenated: models j = 0..m-1 each with state size ks[j];
+ * Cs = [C_0 | C_1 | ...] (each d x ks[j] row-major), mus = m x d, sigmas = m, logw = m (normalised). */
+static const double *mix_C(const double *Cs, const int *ks, int d, int j) {
+  size_t off = 0;
+  for (int l = 0; l < j; ++l) off += (size_t)d * ks[l];
+  return Cs + off;
+}
+
+/* llks_one per model (mix.rs:137-144) for the whole dataset: out is n x m */
+EXPORT void oracle_mix_component_llks(int64_t n, int d, int m, const int *ks, const double *X,
+                                      const double *Cs, const double *mus, const double *sigmas,
+                                      double *out) {
+  double *col = xmalloc(sizeof(double) * (n ? n : 1));
+  for (int j = 0; j < m; ++j) {
+    oracle_llks(n, d, ks[j], X, mix_C(Cs, ks, d, j), mus + (size_t)j * d, sigmas[j], col);
+    for (int64_t i = 0; i < n; ++i) out[i * m + j] = col[i];
+  }
+  free(col);
+}
+
+/* PPCAMix::llks (mix.rs:152-159) */
+EXPORT void oracle_mix_llks(int64_t n, int d, int m, const int *ks, const double *X, const double *Cs,
+                            const double *mus, const double *sigmas, const double *logw, double *out) {
+  double *L = xmalloc(sizeof(double) * (n ? n : 1) * m);
+  oracle_mix_component_llks(n, d, m, ks, X, Cs, mus, sigmas, L);
+  for (int64_t i = 0; i < n; ++i) {
+    for (int j = 0; j < m; ++j) L[i * m + j] += logw[j];
+    out[i] = robust_log_softnorm(L + i * m, m);
+  }
+  free(L);
+}
+
+/* PPCAMix::llk (mix.rs:162-174) */
+EXPORT double oracle_mix_llk(int64_t n, int d, int m, const int *ks, const double *X, const double *w,
+                             const double *Cs, const double *mus, const double *sigmas, const double *logw) {
+  if (n == 0) return 0.0;
+  double *l = xmalloc(sizeof(double) * n);
+  oracle_mix_llks(n, d, m, ks, X, Cs, mus, sigmas, logw, l);
+  double t = 0.0;
+  for (int64_t i = 0; i < n; ++i) t += w[i] * l[i];
+  free(l);
+  return t;
+}
+
+/* PPCAMix::infer_cluster (mix.rs:179-189): out n x m log-posteriors */
+EXPORT void oracle_mix_infer_cluster(int64_t n, int d, int m, const int *ks, const double *X,
+                                     const double *Cs, const double *mus, const double *sigmas,
+                                     const double *logw, double *out) {
+  oracle_mix_component_llks(n, d, m, ks, X, Cs, mus, sigmas, out);
+  for (int64_t i = 0; i < n; ++i) {
+    for (int j = 0; j < m; ++j) out[i * m + j] += logw[j];
+    robust_log_softmax(out + i * m, m);
+  }
+}
+
+/* PPCAMix::smooth / ::extrapolate (mix.rs:245-265; InferredMaskedMix::smoothed/extrapolated :397-414) */
+EXPORT void oracle_mix_smooth(int64_t n, int d, int m, const int *ks, const double *X, const double *Cs,
+                              const double *mus, const double *sigmas, const double *logw, int extrapolate,
+                              double *out) {
+  double *LP = xmalloc(sizeof(double) * (n ? n : 1) * m);
+  oracle_mix_infer_cluster(n, d, m, ks, X, Cs, mus, sigmas, logw, LP);
+  double *part = xmalloc(sizeof(double) * (n ? n : 1) * d);
+  memset(out, 0, sizeof(double) * n * d);
+  for (int j = 0; j < m; ++j) {
+    oracle_smooth(n, d, ks[j], X, mix_C(Cs, ks, d, j), mus + (size_t)j * d, sigmas[j], extrapolate, part);
+    for (int64_t i = 0; i < n; ++i) {
+      double wgt = exp(LP[i * m + j]); /* posterior() (:366-368) */
+      for (int c = 0; c < d; ++c) out[i * d + c] += wgt * part[i * d + c];
+    }
+  }
+  free(LP); free(part);
+}
+
+/* PPCAMix::iterate_with_prior (mix.rs:281-337).  All weights must be > 0 (see quirk: the reference
+ * filters w > 0 and then re-attaches by position). Outputs are laid out like the inputs. */
+EXPORT int oracle_mix_iterate(int64_t n, int d, int m, const int *ks, const double *X, const double *w,
+                              const double *Cs, const double *mus, const double *sigmas, const double *logw,
+                              const oracle_prior_t *prior, double *Cs_out, double *mus_out,
+                              double *sigmas_out, double *logw_out) {
+  if (n <= 0) return 1;
+  for (int64_t i = 0; i < n; ++i) if (!(w[i] > 0.0)) return 4;
+  double *LP = xmalloc(sizeof(double) * n * m);
+  oracle_mix_infer_cluster(n, d, m, ks, X, Cs, mus, sigmas, logw, LP); /* :283-295 */
+  double *r = xmalloc(sizeof(double) * n);
+  int rc = 0;
+  for (int j = 0; j < m; ++j) { /* :297-330 */
+    double mx = -INFINITY; int any = 0;
+    for (int64_t i = 0; i < n; ++i) {
+      r[i] = log(w[i]) + LP[i * m + j];
+      if (!isnan(r[i])) { if (!any || r[i] > mx) mx = r[i]; any = 1; }
+    }
+    if (!any) { rc = 5; break; }
+    double s = 0.0;
+    for (int64_t i = 0; i < n; ++i) { r[i] = exp(r[i] - mx); s += r[i]; }
+    logw_out[j] = log(s) + mx;
+    size_t off = (size_t)(mix_C(Cs, ks, d, j) - Cs);
+    int e = oracle_iterate(n, d, ks[j], X, r, Cs + off, mus + (size_t)j * d, sigmas[j], prior,
+                           Cs_out + off, mus_out + (size_t)j * d, sigmas_out + j);
+    if (e) { rc = e; break; }
+  }
+  if (!rc) robust_log_softmax(logw_out, m); /* :335 */
+  free(LP); free(r);
+  return rc;
+}
