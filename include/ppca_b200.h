@@ -1,0 +1,203 @@
+/*
+ * ppca_b200.h — C ABI of the B200-native PPCA / PPCA-mixture EM engine.
+ *
+ * This is the drop-in boundary for the data-parallel hot path of viodotcom/ppca_rs.  The
+ * reference has no C ABI of its own: its native surface is the Rust crate API
+ * (ppca/src/lib.rs:22-25) wrapped by pyO3 (src/python_bindings.rs:15-26).  Every entry point
+ * below names the reference symbol it replaces; a Rust `ppca` host crate would bind them 1:1
+ * (see INTEGRATION.md), and the Python package `ppca_rs_b200` binds them with ctypes.
+ *
+ * Conventions
+ *   - Plain pointers and sizes only.  All matrices are row-major f64.
+ *   - `C` is the transform, d x k; `mu` the mean, d; `sigma` the isotropic noise STANDARD
+ *     DEVIATION (ppca_model.rs:77-80).  Model parameters are tiny host arrays copied per call.
+ *   - Datasets live on the device behind an opaque handle.  Input matrices mark missing entries
+ *     with any non-finite value (dataset.rs:19-22 mask_non_finite).
+ *   - Every function returns 0 on success, non-zero on failure; the message is available from
+ *     ppca_b200_last_error() (thread-local).  Nothing throws or aborts across the boundary.
+ *   - There is NO CPU fallback: without a CUDA device every compute entry point fails.
+ *   - A context is bound to one device and one stream and is not re-entrant.
+ *   - Pointers named *_dev are DEVICE pointers (for the sharded multi-GPU path, where the caller
+ *     all-reduces the statistics buffer with NCCL between em_stats and em_finish).
+ */
+#ifndef PPCA_B200_H
+#define PPCA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
+#endif
+
+#define PPCA_B200_ABI_VERSION 1
+
+typedef struct ppca_b200_ctx ppca_b200_ctx;
+typedef struct ppca_b200_dataset ppca_b200_dataset;
+
+/* Status codes */
+enum {
+  PPCA_OK = 0,
+  PPCA_ERR_INVALID = 1,   /* bad argument / shape mismatch (the reference panics: output_covariance.rs:124) */
+  PPCA_ERR_CUDA = 2,      /* CUDA runtime error or no device */
+  PPCA_ERR_EMPTY = 3,     /* empty dataset where the reference asserts (ppca_model.rs:52,358) */
+  PPCA_ERR_NUMERIC = 4,   /* singular system where the reference `expect`s (output_covariance.rs:69, prior.rs:109) */
+  PPCA_ERR_WEIGHTS = 5    /* mixture iterate needs strictly positive weights (mix.rs:304-309,326) */
+};
+
+/* prior.rs:8-29 Prior.  mean_precision is the inverse of the prior mean covariance (prior.rs:36-41),
+ * computed by the caller.  Pointers may be NULL when the corresponding flag is 0. */
+typedef struct {
+  int32_t has_mean_prior;
+  const double *mean;            /* d */
+  const double *mean_precision;  /* d x d */
+  int32_t has_isotropic_noise_prior;
+  double isotropic_noise_alpha;
+  double isotropic_noise_beta;
+  double transformation_precision;
+} ppca_b200_prior;
+
+/* ---- library ------------------------------------------------------------------------------- */
+int32_t ppca_b200_abi_version(void);
+const char *ppca_b200_last_error(void);
+int32_t ppca_b200_device_count(int32_t *out);
+
+/* ---- context ------------------------------------------------------------------------------- */
+/* `cuda_stream` is a cudaStream_t to run on (e.g. torch's current stream) or NULL to create one. */
+int32_t ppca_b200_ctx_create(int32_t device, void *cuda_stream, ppca_b200_ctx **out);
+int32_t ppca_b200_ctx_destroy(ppca_b200_ctx *ctx);
+int32_t ppca_b200_ctx_synchronize(ppca_b200_ctx *ctx);
+/* Tuning knob: samples per E/M-step chunk (0 = automatic). */
+int32_t ppca_b200_ctx_set_chunk(ppca_b200_ctx *ctx, int64_t chunk_samples);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+int32_t ppca_b200_ctx_launch_count(ppca_b200_ctx *ctx, int64_t *out);
+/* Device time of the last iterate / em_stats call broken down per kernel family, in ms:
+ * out[0]=ksym out[1]=gram(bitgemm E) out[2]=proj out[3]=solve out[4]=moment(bitgemm M) out[5]=cross+resid
+ * out[6]=finish.  Only filled when profiling was enabled with ppca_b200_ctx_set_profiling(ctx, 1). */
+int32_t ppca_b200_ctx_set_profiling(ppca_b200_ctx *ctx, int32_t enabled);
+int32_t ppca_b200_ctx_last_profile(ppca_b200_ctx *ctx, double *out7);
+
+/* ---- datasets: Dataset / MaskedSample / Mask (dataset.rs:11-14,93-100; utils.rs:27-28) --------- */
+/* Dataset::new / new_with_weights from a host matrix (src/python_bindings.rs:32-64). weights may be NULL (all 1). */
+int32_t ppca_b200_dataset_from_host(ppca_b200_ctx *ctx, const double *x, int64_t n, int32_t d,
+                                    const double *weights, ppca_b200_dataset **out);
+/* Synthetic data generated on the device with the reference's sampler semantics
+ * (ppca_model.rs:164-191 sample_one): x = C_true xi + sigma_true eps, each entry masked with prob mask_prob.
+ * C_true[i,a] ~ Bernoulli(0.1) as in examples/big_toy_model.py:6; n_components > 1 draws each sample
+ * from one of n_components such models (PPCAMix::sample, mix.rs:124-134) with uniform mixing. */
+int32_t ppca_b200_dataset_synthetic(ppca_b200_ctx *ctx, int64_t n, int32_t d, int32_t k_true,
+                                    double sigma_true, double mask_prob, int32_t n_components,
+                                    uint64_t seed, ppca_b200_dataset **out);
+/* Dataset::with_weights (dataset.rs:171-176): shares the samples, new weights (host array of len n). */
+int32_t ppca_b200_dataset_with_weights(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds,
+                                       const double *weights, ppca_b200_dataset **out);
+/* Dataset::len / output_size (dataset.rs:179-191) */
+int32_t ppca_b200_dataset_len(const ppca_b200_dataset *ds, int64_t *out);
+int32_t ppca_b200_dataset_output_size(const ppca_b200_dataset *ds, int32_t *out);
+/* Dataset.numpy() (src/python_bindings.rs:81-92; dataset.rs:64-72 masked_vector): rows [row0,row0+nrows)
+ * into out (nrows x d), NaN at masked slots. */
+int32_t ppca_b200_dataset_to_host(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int64_t row0,
+                                  int64_t nrows, double *out);
+/* Dataset.weights() (src/python_bindings.rs:106-108) */
+int32_t ppca_b200_dataset_weights(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, double *out);
+/* Dataset::empty_dimensions (dataset.rs:194-222): out[i] = 1 if dimension i is masked in every sample. */
+int32_t ppca_b200_dataset_empty_dimensions(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, uint8_t *out);
+/* DatasetChunks::__next__ (src/python_bindings.rs:151-165): copy of rows [row0,row0+nrows) with their weights. */
+int32_t ppca_b200_dataset_slice(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int64_t row0,
+                                int64_t nrows, ppca_b200_dataset **out);
+/* Dataset.concat (src/python_bindings.rs:118-133) */
+int32_t ppca_b200_dataset_concat(ppca_b200_ctx *ctx, const ppca_b200_dataset *const *list, int32_t count,
+                                 ppca_b200_dataset **out);
+int32_t ppca_b200_dataset_destroy(ppca_b200_dataset *ds);
+
+/* ---- PPCAModel (ppca/src/ppca_model.rs) -------------------------------------------------------- */
+/* PPCAModel::llks (ppca_model.rs:152-159): out has n entries. */
+int32_t ppca_b200_llks(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int32_t k, const double *C,
+                       const double *mu, double sigma, double *out);
+/* PPCAModel::llk (ppca_model.rs:142-149): weighted sum. */
+int32_t ppca_b200_llk(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int32_t k, const double *C,
+                      const double *mu, double sigma, double *out);
+/* PPCAModel::infer (ppca_model.rs:195-227): states n x k, covariances n x k x k (nullable). */
+int32_t ppca_b200_infer(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int32_t k, const double *C,
+                        const double *mu, double sigma, double *states, double *covariances);
+/* PPCAModel::smooth (ppca_model.rs:237-244) / ::extrapolate (:254-261): new all-observed dataset,
+ * weights carried through. */
+int32_t ppca_b200_smooth(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int32_t k, const double *C,
+                         const double *mu, double sigma, ppca_b200_dataset **out);
+int32_t ppca_b200_extrapolate(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int32_t k, const double *C,
+                              const double *mu, double sigma, ppca_b200_dataset **out);
+/* PPCAModel::iterate_with_prior (ppca_model.rs:277-393); prior may be NULL (= iterate, :267-269).
+ * llk_in (nullable) receives the log-likelihood of the INPUT model on ds, which the E-step produces
+ * for free (what PPCATrainer prints each iteration, python/ppca_rs/__init__.py:51). */
+int32_t ppca_b200_iterate(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int32_t k, const double *C,
+                          const double *mu, double sigma, const ppca_b200_prior *prior, double *C_out,
+                          double *mu_out, double *sigma_out, double *llk_in);
+
+/* ---- sharded EM: one process per GPU, statistics all-reduced by the caller --------------------- */
+/* Length (in doubles) of the additive sufficient-statistics buffer for (d, k):
+ *   [ A: d x kkp | B: d x kp | tdev: d | totals: d | 8 scalars ]   kkp = roundup8(k(k+1)/2), kp = roundup8(k)
+ * scalars: 0 = sum w tr(C_o Sigma_n C_o^T) (square_error), 1 = sum w |dev|^2, 2 = sum w llk_n,
+ *          3 = sum w (all samples), 4 = number of non-empty samples, 5..7 reserved. */
+int64_t ppca_b200_em_stats_len(int32_t d, int32_t k);
+/* E-step + local M-step statistics of this shard (ppca_model.rs:278-358) into stats_dev (DEVICE memory,
+ * overwritten).  Asynchronous on the context's stream. */
+int32_t ppca_b200_em_stats(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int32_t k, const double *C,
+                           const double *mu, double sigma, double *stats_dev);
+/* M-step finish from (all-reduced) statistics: d row solves, sigma^2, mu, prior hooks
+ * (ppca_model.rs:294-324 solve part, :360-392). */
+int32_t ppca_b200_em_finish(ppca_b200_ctx *ctx, int32_t d, int32_t k, const double *C, const double *mu,
+                            double sigma, const ppca_b200_prior *prior, const double *stats_dev,
+                            double *C_out, double *mu_out, double *sigma_out, double *llk_in);
+
+/* ---- PPCAMix (ppca/src/mix.rs) ------------------------------------------------------------------ */
+/* Mixture parameters: m models; ks[j] state sizes; Cs = concatenation of the C_j (each d x ks[j]);
+ * mus = m x d; sigmas = m; log_weights = m (already normalised, mix.rs:69). */
+/* PPCAMix::llks (mix.rs:152-159) */
+int32_t ppca_b200_mix_llks(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int32_t m, const int32_t *ks,
+                           const double *Cs, const double *mus, const double *sigmas,
+                           const double *log_weights, double *out);
+/* PPCAMix::llk (mix.rs:162-174) */
+int32_t ppca_b200_mix_llk(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int32_t m, const int32_t *ks,
+                          const double *Cs, const double *mus, const double *sigmas,
+                          const double *log_weights, double *out);
+/* PPCAMix::infer_cluster (mix.rs:179-189): n x m log-posteriors. */
+int32_t ppca_b200_mix_infer_cluster(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int32_t m,
+                                    const int32_t *ks, const double *Cs, const double *mus,
+                                    const double *sigmas, const double *log_weights, double *out);
+/* PPCAMix::smooth / ::extrapolate (mix.rs:245-265): weights reset to 1. */
+int32_t ppca_b200_mix_smooth(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int32_t m, const int32_t *ks,
+                             const double *Cs, const double *mus, const double *sigmas,
+                             const double *log_weights, ppca_b200_dataset **out);
+int32_t ppca_b200_mix_extrapolate(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int32_t m,
+                                  const int32_t *ks, const double *Cs, const double *mus,
+                                  const double *sigmas, const double *log_weights, ppca_b200_dataset **out);
+/* PPCAMix::iterate_with_prior (mix.rs:281-337).  Outputs are laid out like the inputs;
+ * llk_in (nullable) receives the mixture log-likelihood of the INPUT model. */
+int32_t ppca_b200_mix_iterate(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int32_t m, const int32_t *ks,
+                              const double *Cs, const double *mus, const double *sigmas,
+                              const double *log_weights, const ppca_b200_prior *prior, double *Cs_out,
+                              double *mus_out, double *sigmas_out, double *log_weights_out, double *llk_in);
+
+/* Sharded mixture EM.  Step 1: log-posteriors of this shard into logpost_dev (n x m, DEVICE) and the
+ * per-component local maxima of ln w_n + logpost[n][j] into comp_max (host, m; -inf if the shard is empty);
+ * also the weighted mixture llk of the shard (nullable).  The caller all-reduces comp_max with MAX. */
+int32_t ppca_b200_mix_posteriors(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int32_t m,
+                                 const int32_t *ks, const double *Cs, const double *mus,
+                                 const double *sigmas, const double *log_weights, double *logpost_dev,
+                                 double *comp_max, double *llk_in);
+/* Step 2, per component j: statistics with responsibilities r_n = exp(ln w_n + logpost[n][j] - comp_max_j)
+ * as weights (mix.rs:304-326) into stats_dev (layout of ppca_b200_em_stats_len(d, ks[j])); scalar 3 of the
+ * buffer is sum_n r_n.  The caller all-reduces with SUM and calls ppca_b200_em_finish per component. */
+int32_t ppca_b200_mix_em_stats(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int32_t m, int32_t j,
+                               int32_t k, const double *C, const double *mu, double sigma,
+                               const double *logpost_dev, double comp_max_j, double *stats_dev);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* PPCA_B200_H */

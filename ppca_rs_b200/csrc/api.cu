@@ -1,0 +1,1145 @@
+// api.cu — the C ABI (include/ppca_b200.h) and the host-side orchestration of the EM engine.
+//
+// One context = one device + one stream.  The dataset stays resident on the device; per call only the
+// model parameters (d k + d + 1 doubles) cross the bus in, and the new model (or per-sample outputs) out.
+// Chunked over samples so that the E-step intermediates (packed Gram / second-moment rows) are O(chunk).
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <new>
+
+#include "common.cuh"
+
+namespace ppca {
+
+static thread_local std::string g_last_error;
+void set_error(const std::string &msg) { g_last_error = msg; }
+
+enum { FAM_KSYM = 0, FAM_GRAM, FAM_PROJ, FAM_SOLVE, FAM_MOMENT, FAM_CROSS, FAM_FINISH, FAM_COUNT };
+
+}  // namespace ppca
+
+using namespace ppca;
+
+struct ppca_b200_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int sms = 148;
+  int64_t launches = 0;
+  int64_t chunk = 0;  // 0 = automatic
+  // model staging
+  DevBuf<double> Cdense, mudense, Cpad, mupad, Ksym, logw;
+  // chunk workspaces
+  DevBuf<double> GW, YZ, WZ, nx, llk, tn, part_bg, part_cr, stats, Cnew, cov, rbuf;
+  DevBuf<int> flags;
+  // pinned staging
+  double *pinned = nullptr;
+  size_t pinned_count = 0;
+  // profiling
+  bool profiling = false;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+  struct Span { int fam; cudaEvent_t a, b; };
+  std::vector<Span> spans;
+  double last_profile[FAM_COUNT] = {0, 0, 0, 0, 0, 0, 0};
+
+  Launcher L() { return Launcher{stream, &launches, sms}; }
+  double *pin(size_t count) {
+    if (count > pinned_count) {
+      if (pinned) cudaFreeHost(pinned);
+      pinned = nullptr;
+      pinned_count = 0;
+      CUDA_CHECK(cudaMallocHost((void **)&pinned, count * sizeof(double)));
+      pinned_count = count;
+    }
+    return pinned;
+  }
+  cudaEvent_t next_event() {
+    if (ev_used == ev_pool.size()) {
+      cudaEvent_t e;
+      CUDA_CHECK(cudaEventCreate(&e));
+      ev_pool.push_back(e);
+    }
+    return ev_pool[ev_used++];
+  }
+  void span_begin(int fam) {
+    if (!profiling) return;
+    Span s{fam, next_event(), nullptr};
+    CUDA_CHECK(cudaEventRecord(s.a, stream));
+    spans.push_back(s);
+  }
+  void span_end() {
+    if (!profiling) return;
+    spans.back().b = next_event();
+    CUDA_CHECK(cudaEventRecord(spans.back().b, stream));
+  }
+  void profile_reset() {
+    spans.clear();
+    ev_used = 0;
+  }
+  void profile_collect() {
+    if (!profiling) return;
+    CUDA_CHECK(cudaStreamSynchronize(stream));
+    for (int i = 0; i < FAM_COUNT; ++i) last_profile[i] = 0.0;
+    for (auto &s : spans) {
+      float ms = 0.f;
+      CUDA_CHECK(cudaEventElapsedTime(&ms, s.a, s.b));
+      last_profile[s.fam] += ms;
+    }
+  }
+};
+
+namespace {
+
+struct DeviceGuard {
+  int prev = 0;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) CUDA_CHECK(cudaSetDevice(dev));
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+template <class F>
+int32_t guarded(F &&f) {
+  try {
+    f();
+    return PPCA_OK;
+  } catch (const Error &e) {
+    set_error(e.msg);
+    return e.code;
+  } catch (const std::bad_alloc &) {
+    set_error("out of host memory");
+    return PPCA_ERR_INVALID;
+  } catch (...) {
+    set_error("unknown error");
+    return PPCA_ERR_INVALID;
+  }
+}
+
+__global__ void fill_value_kernel(double *p, int64_t n, double v) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+std::shared_ptr<SampleStore> make_store(ppca_b200_ctx *ctx, int64_t n, int d) {
+  auto st = std::make_shared<SampleStore>();
+  st->n = n;
+  st->d = d;
+  st->ldx = (int)round_up(d > 0 ? d : 1, 4);
+  st->dw = (int)((d + 31) / 32);
+  if (st->dw == 0) st->dw = 1;
+  st->n_pad = round_up(n > 0 ? n : 1, 256);
+  st->nwT = st->n_pad / 32;
+  st->d_pad = (int)round_up(d > 0 ? d : 1, 256);
+  st->X.alloc((size_t)st->n_pad * st->ldx);
+  st->mask.alloc((size_t)st->n_pad * st->dw);
+  st->maskT.alloc((size_t)st->d_pad * st->nwT);
+  st->dn.alloc((size_t)st->n_pad);
+  CUDA_CHECK(cudaMemsetAsync(st->X.p, 0, sizeof(double) * st->n_pad * st->ldx, ctx->stream));
+  CUDA_CHECK(cudaMemsetAsync(st->mask.p, 0, sizeof(uint32_t) * st->n_pad * st->dw, ctx->stream));
+  CUDA_CHECK(cudaMemsetAsync(st->maskT.p, 0, sizeof(uint32_t) * st->d_pad * st->nwT, ctx->stream));
+  CUDA_CHECK(cudaMemsetAsync(st->dn.p, 0, sizeof(int) * st->n_pad, ctx->stream));
+  return st;
+}
+
+ppca_b200_dataset *make_dataset(ppca_b200_ctx *ctx, std::shared_ptr<SampleStore> st, const double *w_host) {
+  std::unique_ptr<ppca_b200_dataset> ds(new ppca_b200_dataset());
+  ds->store = st;
+  ds->device = ctx->device;
+  ds->w.alloc((size_t)st->n_pad);
+  CUDA_CHECK(cudaMemsetAsync(ds->w.p, 0, sizeof(double) * st->n_pad, ctx->stream));
+  if (st->n > 0) {
+    if (w_host) {
+      CUDA_CHECK(cudaMemcpyAsync(ds->w.p, w_host, sizeof(double) * st->n, cudaMemcpyHostToDevice, ctx->stream));
+      double mn = std::numeric_limits<double>::infinity();
+      for (int64_t i = 0; i < st->n; ++i) mn = w_host[i] < mn ? w_host[i] : (w_host[i] != w_host[i] ? -1.0 : mn);
+      ds->min_w = mn;
+    } else {
+      const int64_t want = (st->n + 255) / 256;
+      const int blocks = (int)(want < (int64_t)ctx->sms * 8 ? want : (int64_t)ctx->sms * 8);
+      fill_value_kernel<<<blocks, 256, 0, ctx->stream>>>(ds->w.p, st->n, 1.0);
+      CUDA_CHECK(cudaGetLastError());
+      ++ctx->launches;
+      ds->min_w = 1.0;
+    }
+  }
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  return ds.release();
+}
+
+int64_t pick_chunk(ppca_b200_ctx *ctx, int64_t n_pad, const Shape &s) {
+  int64_t chunk = ctx->chunk;
+  if (chunk <= 0) {
+    const int64_t wave = (int64_t)ctx->sms * 128;  // one full wave of 128-row tiles
+    chunk = wave * 4;
+    // keep the chunk workspace under ~8 GiB
+    const int64_t per_row = (int64_t)(s.kkp + 2 * s.kp + 4) * 8;
+    while (chunk > wave && chunk * per_row > ((int64_t)8 << 30)) chunk -= wave;
+  }
+  chunk = round_up(chunk, 256);
+  if (chunk > n_pad) chunk = n_pad;
+  return chunk;
+}
+
+// uploads (C, mu) and builds the padded model + Ksym table on the device
+DevModel stage_model(ppca_b200_ctx *ctx, int d, int k, const double *C, const double *mu, double sigma,
+                     bool need_ksym = true) {
+  REQUIRE(k >= 1, "state_size must be >= 1 (got %d)", k);
+  REQUIRE(C && mu, "null model parameters");
+  REQUIRE(sigma > 0.0 && std::isfinite(sigma), "isotropic_noise must be positive and finite");
+  Shape s(d, k);
+  ctx->Cdense.reserve((size_t)d * k);
+  ctx->mudense.reserve((size_t)d);
+  ctx->Cpad.reserve((size_t)s.d32 * s.kp);
+  ctx->mupad.reserve((size_t)s.d32);
+  ctx->Ksym.reserve((size_t)s.d32 * s.kkp);
+  double *stage = ctx->pin((size_t)d * k + d);
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));  // staging buffer may still be in flight
+  memcpy(stage, C, sizeof(double) * d * k);
+  memcpy(stage + (size_t)d * k, mu, sizeof(double) * d);
+  CUDA_CHECK(cudaMemcpyAsync(ctx->Cdense.p, stage, sizeof(double) * d * k, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_CHECK(cudaMemcpyAsync(ctx->mudense.p, stage + (size_t)d * k, sizeof(double) * d, cudaMemcpyHostToDevice,
+                             ctx->stream));
+  ctx->span_begin(FAM_KSYM);
+  launch_prepare_model(ctx->L(), ctx->Cdense.p, ctx->mudense.p, d, k, ctx->Cpad.p, ctx->mupad.p, ctx->Ksym.p);
+  ctx->span_end();
+  DevModel m;
+  m.s = s;
+  m.sigma = sigma;
+  m.C = ctx->Cpad.p;
+  m.mu = ctx->mupad.p;
+  m.Ksym = ctx->Ksym.p;
+  return m;
+}
+
+void reserve_chunk_ws(ppca_b200_ctx *ctx, int64_t chunk, const Shape &s) {
+  ctx->GW.reserve((size_t)chunk * s.kkp);
+  ctx->YZ.reserve((size_t)chunk * s.kp);
+  ctx->WZ.reserve((size_t)chunk * s.kp);
+  ctx->nx.reserve((size_t)chunk);
+  ctx->llk.reserve((size_t)chunk);
+  ctx->tn.reserve((size_t)chunk);
+}
+
+// E-step of one chunk: Gram contraction, projection, per-sample solve
+void e_step_chunk(ppca_b200_ctx *ctx, const SampleStore &st, const double *w, int64_t row0, int rows,
+                  const DevModel &m, int mode, double *llk_out, double *cov_out, double *scalars) {
+  const Launcher L = ctx->L();
+  const int rows_pad = (int)round_up(rows, 256);
+  BitGemmArgs g;
+  g.bits = st.mask.p + row0 * st.dw;
+  g.ldbits = st.dw;
+  g.Bmat = m.Ksym;
+  g.ldb = m.s.kkp;
+  g.Out = ctx->GW.p;
+  g.ldo = m.s.kkp;
+  g.M = rows;
+  g.Nq = m.s.kkp;
+  g.kblocks = m.s.d32 / 32;
+  g.accumulate = 0;
+  g.partials = nullptr;
+  g.splitk = 1;
+  ctx->span_begin(FAM_GRAM);
+  launch_bitgemm(L, g);
+  ctx->span_end();
+  ctx->span_begin(FAM_PROJ);
+  launch_proj(L, st, row0, rows, m, ctx->YZ.p, ctx->nx.p);
+  ctx->span_end();
+  SolveArgs sa;
+  sa.s = m.s;
+  sa.sigma = m.sigma;
+  sa.rows = rows;
+  sa.rows_pad = rows_pad;
+  sa.GW = ctx->GW.p;
+  sa.YZ = ctx->YZ.p;
+  sa.WZ = mode == 2 ? ctx->WZ.p : nullptr;
+  sa.nx = ctx->nx.p;
+  sa.dn = st.dn.p + row0;
+  sa.w = w ? w + row0 : nullptr;
+  sa.llk = llk_out;
+  sa.tn = mode == 2 ? ctx->tn.p : nullptr;
+  sa.cov = cov_out;
+  sa.scalars = scalars;
+  sa.mode = mode;
+  ctx->span_begin(FAM_SOLVE);
+  launch_solve(L, sa);
+  ctx->span_end();
+}
+
+// E-step + local M-step statistics of a whole (local) dataset into stats_dev
+void em_stats_impl(ppca_b200_ctx *ctx, const SampleStore &st, const double *w, const DevModel &m, double *stats_dev) {
+  const Launcher L = ctx->L();
+  const StatsLayout lay(m.s.d, m.s.k);
+  CUDA_CHECK(cudaMemsetAsync(stats_dev, 0, sizeof(double) * lay.len, ctx->stream));
+  if (st.n == 0) return;
+  const int64_t chunk = pick_chunk(ctx, st.n_pad, m.s);
+  reserve_chunk_ws(ctx, chunk, m.s);
+  const int kb_chunk = (int)(chunk / 32);
+  const int splitk = bitgemm_pick_splitk(m.s.d, m.s.kkp, kb_chunk, ctx->sms);
+  ctx->part_bg.reserve(bitgemm_partials_len(m.s.d, m.s.kkp, splitk));
+  const size_t crlen = cross_resid_partials_len(m.s.d, m.s.k, (int)chunk, ctx->sms);
+  ctx->part_cr.reserve(crlen);
+  for (int64_t row0 = 0; row0 < st.n; row0 += chunk) {
+    const int rows = (int)((st.n - row0) < chunk ? (st.n - row0) : chunk);
+    e_step_chunk(ctx, st, w, row0, rows, m, 2, ctx->llk.p, nullptr, stats_dev + lay.offScalars);
+    BitGemmArgs g;
+    g.bits = st.maskT.p + row0 / 32;
+    g.ldbits = st.nwT;
+    g.Bmat = ctx->GW.p;
+    g.ldb = m.s.kkp;
+    g.Out = stats_dev + lay.offA;
+    g.ldo = m.s.kkp;
+    g.M = m.s.d;
+    g.Nq = m.s.kkp;
+    g.kblocks = (int)(round_up(rows, 32) / 32);
+    g.accumulate = 1;
+    g.splitk = splitk < g.kblocks ? splitk : (g.kblocks > 0 ? g.kblocks : 1);
+    g.partials = g.splitk > 1 ? ctx->part_bg.p : nullptr;
+    ctx->span_begin(FAM_MOMENT);
+    launch_bitgemm(L, g);
+    ctx->span_end();
+    ctx->span_begin(FAM_CROSS);
+    launch_cross_resid(L, st, row0, rows, m, ctx->YZ.p, ctx->WZ.p, w + row0, stats_dev + lay.offB,
+                       stats_dev + lay.offTdev, stats_dev + lay.offTotals, stats_dev + lay.offScalars, ctx->part_cr.p,
+                       crlen);
+    ctx->span_end();
+  }
+}
+
+// Householder QR solve on the host (prior.rs:97-110 smooth_mean uses total_precision.qr().solve)
+bool host_qr_solve(std::vector<double> &A, int n, std::vector<double> &b) {
+  std::vector<double> diag(n);
+  for (int i = 0; i < n; ++i) {
+    double sq = 0.0;
+    for (int r = i; r < n; ++r) sq += A[(size_t)r * n + i] * A[(size_t)r * n + i];
+    const double norm = std::sqrt(sq);
+    const double a0 = A[(size_t)i * n + i];
+    const double sgn = std::signbit(a0) ? -1.0 : 1.0;
+    const double signed_norm = sgn * norm;
+    const double factor = (sq + std::fabs(a0) * norm) * 2.0;
+    A[(size_t)i * n + i] = a0 + signed_norm;
+    if (factor != 0.0) {
+      const double s = std::sqrt(factor);
+      for (int r = i; r < n; ++r) A[(size_t)r * n + i] /= s;
+      diag[i] = -signed_norm;
+      for (int c = i + 1; c < n; ++c) {
+        double dot = 0.0;
+        for (int r = i; r < n; ++r) dot += A[(size_t)r * n + i] * A[(size_t)r * n + c];
+        dot *= 2.0;
+        for (int r = i; r < n; ++r) A[(size_t)r * n + c] -= dot * A[(size_t)r * n + i];
+      }
+      double dot = 0.0;
+      for (int r = i; r < n; ++r) dot += A[(size_t)r * n + i] * b[r];
+      dot *= 2.0;
+      for (int r = i; r < n; ++r) b[r] -= dot * A[(size_t)r * n + i];
+    } else {
+      diag[i] = signed_norm;
+    }
+  }
+  for (int i = n - 1; i >= 0; --i) {
+    if (diag[i] == 0.0) return false;
+    double v = b[i];
+    for (int c = i + 1; c < n; ++c) v -= A[(size_t)i * n + c] * b[c];
+    b[i] = v / diag[i];
+  }
+  return true;
+}
+
+// M-step finish from (reduced) statistics
+void em_finish_impl(ppca_b200_ctx *ctx, int d, int k, const double *C, const double *mu, double sigma,
+                    const ppca_b200_prior *prior, const double *stats_dev, double *C_out, double *mu_out,
+                    double *sigma_out, double *llk_in, double *sumw_out) {
+  REQUIRE(C && mu && C_out && mu_out && sigma_out, "null model parameters");
+  const Shape s(d, k);
+  const StatsLayout lay(d, k);
+  // old transform, padded (fallback rows)
+  ctx->Cdense.reserve((size_t)d * k);
+  ctx->mudense.reserve((size_t)d);
+  ctx->Cpad.reserve((size_t)s.d32 * s.kp);
+  ctx->mupad.reserve((size_t)s.d32);
+  ctx->Ksym.reserve((size_t)s.d32 * s.kkp);
+  ctx->Cnew.reserve((size_t)d * k);
+  ctx->flags.reserve((size_t)d);
+  const size_t tail = (size_t)2 * d + 8;
+  double *stage = ctx->pin((size_t)d * k + tail + (size_t)d * k);
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  memcpy(stage, C, sizeof(double) * d * k);
+  CUDA_CHECK(cudaMemcpyAsync(ctx->Cdense.p, stage, sizeof(double) * d * k, cudaMemcpyHostToDevice, ctx->stream));
+  // only the padded old transform is needed on the device here (fallback rows); mu stays on the host
+  CUDA_CHECK(cudaMemsetAsync(ctx->mudense.p, 0, sizeof(double) * d, ctx->stream));
+  ctx->span_begin(FAM_FINISH);
+  launch_prepare_model(ctx->L(), ctx->Cdense.p, ctx->mudense.p, d, k, ctx->Cpad.p, ctx->mupad.p, ctx->Ksym.p);
+  const double tau = prior ? prior->transformation_precision : 0.0;
+  launch_row_solve(ctx->L(), d, k, stats_dev + lay.offA, stats_dev + lay.offB, tau, ctx->Cpad.p, ctx->Cnew.p,
+                   ctx->flags.p);
+  ctx->span_end();
+  double *h_tail = stage + (size_t)d * k;
+  double *h_C = h_tail + tail;
+  CUDA_CHECK(cudaMemcpyAsync(h_tail, stats_dev + lay.offTdev, sizeof(double) * tail, cudaMemcpyDeviceToHost,
+                             ctx->stream));
+  CUDA_CHECK(cudaMemcpyAsync(h_C, ctx->Cnew.p, sizeof(double) * d * k, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  const double *tdev = h_tail, *totals = h_tail + d, *sc = h_tail + 2 * d;
+  if (!(sc[SC_NONEMPTY] > 0.0)) PPCA_THROW(PPCA_ERR_EMPTY, "non-empty dataset required (ppca_model.rs:358)");
+  memcpy(C_out, h_C, sizeof(double) * d * k);
+  double tot_sum = 0.0;
+  for (int i = 0; i < d; ++i) tot_sum += totals[i];
+  double noise_sq;
+  if (prior && prior->has_isotropic_noise_prior)  // ppca_model.rs:360-368
+    noise_sq = ((sc[SC_SQERR] + sc[SC_DEV2]) / 2.0 + prior->isotropic_noise_beta) /
+               (tot_sum / 2.0 + prior->isotropic_noise_alpha + 1.0);
+  else
+    noise_sq = (sc[SC_SQERR] + sc[SC_DEV2]) / tot_sum;  // :370
+  for (int i = 0; i < d; ++i) mu_out[i] = (totals[i] > 0.0 ? tdev[i] / totals[i] : 0.0) + mu[i];  // :373-377
+  if (prior && prior->has_mean_prior) {  // :379-384 ; prior.rs:97-110
+    REQUIRE(prior->mean && prior->mean_precision, "mean prior needs mean and mean_precision");
+    std::vector<double> P((size_t)d * d), num(d);
+    for (int i = 0; i < d; ++i) {
+      double acc = 0.0;
+      for (int j = 0; j < d; ++j) {
+        const double pm = prior->mean_precision[(size_t)i * d + j];
+        P[(size_t)i * d + j] = pm + (i == j ? totals[i] / noise_sq : 0.0);
+        acc += pm * prior->mean[j];
+      }
+      num[i] = acc + (totals[i] / noise_sq) * mu_out[i];
+    }
+    if (!host_qr_solve(P, d, num))
+      PPCA_THROW(PPCA_ERR_NUMERIC, "total precision matrix is always invertible (prior.rs:109)");
+    for (int i = 0; i < d; ++i) mu_out[i] = num[i];
+  }
+  *sigma_out = std::sqrt(noise_sq);  // :389
+  if (llk_in) *llk_in = sc[SC_LLK];
+  if (sumw_out) *sumw_out = sc[SC_SUMW];
+}
+
+void check_ds(const ppca_b200_ctx *ctx, const ppca_b200_dataset *ds) {
+  REQUIRE(ctx != nullptr, "null context");
+  REQUIRE(ds != nullptr && ds->store, "null dataset");
+  REQUIRE(ds->device == ctx->device, "dataset lives on device %d, context on %d", ds->device, ctx->device);
+}
+
+// llks of one model for all samples into llk_dev (device, n entries, optionally strided)
+void llks_impl(ppca_b200_ctx *ctx, const SampleStore &st, const DevModel &m, double *llk_dev) {
+  if (st.n == 0) return;
+  const int64_t chunk = pick_chunk(ctx, st.n_pad, m.s);
+  reserve_chunk_ws(ctx, chunk, m.s);
+  for (int64_t row0 = 0; row0 < st.n; row0 += chunk) {
+    const int rows = (int)((st.n - row0) < chunk ? (st.n - row0) : chunk);
+    e_step_chunk(ctx, st, nullptr, row0, rows, m, 0, llk_dev + row0, nullptr, nullptr);
+  }
+}
+
+__global__ void fill_ones_mask_kernel(uint32_t *mask, int dw, int d, int64_t n, int *dn) {
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < n * dw;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int j = (int)(idx % dw);
+    const int bits = d - 32 * j;
+    mask[idx] = bits >= 32 ? 0xffffffffu : ((1u << bits) - 1u);
+    if (j == 0) dn[idx / dw] = d;
+  }
+}
+
+__global__ void strided_copy_kernel(const double *src, int64_t n, int cols, int64_t lds, double *dst, int64_t ldd) {
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < n * cols;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = idx / cols;
+    const int c = (int)(idx % cols);
+    dst[r * ldd + c] = src[r * lds + c];
+  }
+}
+
+// smooth / extrapolate into a fresh all-observed store; scale/accumulate for mixtures
+void reconstruct_impl(ppca_b200_ctx *ctx, const SampleStore &st, const DevModel &m, int extrapolate,
+                      const double *scale, int64_t scale_ld, int accumulate, SampleStore &out) {
+  if (st.n == 0) return;
+  const int64_t chunk = pick_chunk(ctx, st.n_pad, m.s);
+  reserve_chunk_ws(ctx, chunk, m.s);
+  for (int64_t row0 = 0; row0 < st.n; row0 += chunk) {
+    const int rows = (int)((st.n - row0) < chunk ? (st.n - row0) : chunk);
+    e_step_chunk(ctx, st, nullptr, row0, rows, m, 1, nullptr, nullptr, nullptr);
+    launch_reconstruct(ctx->L(), st, row0, rows, m, ctx->YZ.p, extrapolate, scale ? scale + row0 * scale_ld : nullptr,
+                       scale_ld, accumulate, out.X.p + row0 * out.ldx, out.ldx);
+  }
+}
+
+void finalize_full_store(ppca_b200_ctx *ctx, SampleStore &out) {
+  if (out.n == 0) return;
+  const int64_t total = out.n * out.dw;
+  const int blocks = (int)((total + 255) / 256 < (int64_t)ctx->sms * 8 ? (total + 255) / 256 : (int64_t)ctx->sms * 8);
+  fill_ones_mask_kernel<<<blocks, 256, 0, ctx->stream>>>(out.mask.p, out.dw, out.d, out.n, out.dn.p);
+  CUDA_CHECK(cudaGetLastError());
+  ++ctx->launches;
+  launch_transpose_mask(ctx->L(), out);
+}
+
+struct MixView {
+  int m;
+  const int32_t *ks;
+  const double *Cs, *mus, *sigmas, *logw;
+  int d;
+  const double *C(int j) const {
+    size_t off = 0;
+    for (int l = 0; l < j; ++l) off += (size_t)d * ks[l];
+    return Cs + off;
+  }
+  const double *mu(int j) const { return mus + (size_t)j * d; }
+};
+
+void check_mix(const MixView &mv) {
+  REQUIRE(mv.m >= 1, "a mixture needs at least one model (mix.rs:51)");
+  REQUIRE(mv.ks && mv.Cs && mv.mus && mv.sigmas && mv.logw, "null mixture parameters");
+}
+
+// component log-likelihoods into LP (n x m, device), then in-place log-softmax with the prior log-weights
+void mix_posteriors_impl(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, const MixView &mv, double *LP_dev,
+                         double *mix_llk_dev, double *comp_max_dev, double *llk_sum_dev) {
+  const SampleStore &st = *ds->store;
+  ctx->rbuf.reserve((size_t)st.n_pad);
+  for (int j = 0; j < mv.m; ++j) {
+    DevModel m = stage_model(ctx, st.d, mv.ks[j], mv.C(j), mv.mu(j), mv.sigmas[j]);
+    llks_impl(ctx, st, m, ctx->rbuf.p);
+    if (st.n > 0) {
+      const int64_t total = st.n;
+      const int blocks = (int)((total + 255) / 256 < (int64_t)ctx->sms * 8 ? (total + 255) / 256 : (int64_t)ctx->sms * 8);
+      strided_copy_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->rbuf.p, st.n, 1, 1, LP_dev + j, mv.m);
+      CUDA_CHECK(cudaGetLastError());
+      ++ctx->launches;
+    }
+  }
+  ctx->logw.reserve((size_t)mv.m);
+  CUDA_CHECK(cudaMemcpyAsync(ctx->logw.p, mv.logw, sizeof(double) * mv.m, cudaMemcpyHostToDevice, ctx->stream));
+  launch_log_softmax_rows(ctx->L(), LP_dev, st.n, mv.m, ctx->logw.p, ds->w.p, mix_llk_dev, comp_max_dev, llk_sum_dev);
+}
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+int32_t ppca_b200_abi_version(void) { return PPCA_B200_ABI_VERSION; }
+const char *ppca_b200_last_error(void) { return g_last_error.c_str(); }
+
+int32_t ppca_b200_device_count(int32_t *out) {
+  return guarded([&] {
+    REQUIRE(out != nullptr, "null output");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      n = 0;
+    }
+    *out = n;
+  });
+}
+
+int32_t ppca_b200_ctx_create(int32_t device, void *cuda_stream, ppca_b200_ctx **out) {
+  return guarded([&] {
+    REQUIRE(out != nullptr, "null output");
+    int n = 0;
+    CUDA_CHECK(cudaGetDeviceCount(&n));
+    REQUIRE(device >= 0 && device < n, "device %d out of range (have %d)", device, n);
+    CUDA_CHECK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+      PPCA_THROW(PPCA_ERR_CUDA, "this engine is built for sm_100a only; device %d is sm_%d%d", device, prop.major,
+                 prop.minor);
+    std::unique_ptr<ppca_b200_ctx> ctx(new ppca_b200_ctx());
+    ctx->device = device;
+    ctx->sms = prop.multiProcessorCount;
+    if (cuda_stream) {
+      ctx->stream = (cudaStream_t)cuda_stream;
+      ctx->own_stream = false;
+    } else {
+      CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+      ctx->own_stream = true;
+    }
+    *out = ctx.release();
+  });
+}
+
+int32_t ppca_b200_ctx_destroy(ppca_b200_ctx *ctx) {
+  return guarded([&] {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto e : ctx->ev_pool) cudaEventDestroy(e);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+  });
+}
+
+int32_t ppca_b200_ctx_synchronize(ppca_b200_ctx *ctx) {
+  return guarded([&] {
+    REQUIRE(ctx != nullptr, "null context");
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  });
+}
+
+int32_t ppca_b200_ctx_set_chunk(ppca_b200_ctx *ctx, int64_t chunk_samples) {
+  return guarded([&] {
+    REQUIRE(ctx != nullptr, "null context");
+    REQUIRE(chunk_samples >= 0 && chunk_samples <= ((int64_t)1 << 30), "chunk out of range");
+    ctx->chunk = chunk_samples;
+  });
+}
+
+int32_t ppca_b200_ctx_launch_count(ppca_b200_ctx *ctx, int64_t *out) {
+  return guarded([&] {
+    REQUIRE(ctx != nullptr && out != nullptr, "null argument");
+    *out = ctx->launches;
+  });
+}
+
+int32_t ppca_b200_ctx_set_profiling(ppca_b200_ctx *ctx, int32_t enabled) {
+  return guarded([&] {
+    REQUIRE(ctx != nullptr, "null context");
+    ctx->profiling = enabled != 0;
+  });
+}
+
+int32_t ppca_b200_ctx_last_profile(ppca_b200_ctx *ctx, double *out7) {
+  return guarded([&] {
+    REQUIRE(ctx != nullptr && out7 != nullptr, "null argument");
+    for (int i = 0; i < FAM_COUNT; ++i) out7[i] = ctx->last_profile[i];
+  });
+}
+
+// ---- datasets -----------------------------------------------------------------------------------
+int32_t ppca_b200_dataset_from_host(ppca_b200_ctx *ctx, const double *x, int64_t n, int32_t d, const double *weights,
+                                    ppca_b200_dataset **out) {
+  return guarded([&] {
+    REQUIRE(ctx != nullptr && out != nullptr, "null argument");
+    REQUIRE(n >= 0 && d >= 1, "bad dataset shape %lld x %d", (long long)n, d);
+    REQUIRE(n == 0 || x != nullptr, "null data");
+    DeviceGuard g(ctx->device);
+    auto st = make_store(ctx, n, d);
+    if (n > 0) {
+      const int64_t rows_per = std::max<int64_t>(1, ((int64_t)64 << 20) / ((int64_t)d * 8));
+      DevBuf<double> raw;
+      raw.alloc((size_t)std::min<int64_t>(rows_per, n) * d);
+      for (int64_t r0 = 0; r0 < n; r0 += rows_per) {
+        const int64_t rows = std::min<int64_t>(rows_per, n - r0);
+        CUDA_CHECK(cudaMemcpyAsync(raw.p, x + r0 * d, sizeof(double) * rows * d, cudaMemcpyHostToDevice, ctx->stream));
+        launch_ingest(ctx->L(), raw.p, rows, d, r0, *st);
+      }
+      launch_transpose_mask(ctx->L(), *st);
+      CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    }
+    *out = make_dataset(ctx, st, weights);
+  });
+}
+
+int32_t ppca_b200_dataset_synthetic(ppca_b200_ctx *ctx, int64_t n, int32_t d, int32_t k_true, double sigma_true,
+                                    double mask_prob, int32_t n_components, uint64_t seed, ppca_b200_dataset **out) {
+  return guarded([&] {
+    REQUIRE(ctx != nullptr && out != nullptr, "null argument");
+    REQUIRE(n >= 1 && d >= 1 && k_true >= 1 && n_components >= 1, "bad synthetic shape");
+    REQUIRE(mask_prob >= 0.0 && mask_prob <= 1.0, "invalid mask probability");
+    DeviceGuard g(ctx->device);
+    auto st = make_store(ctx, n, d);
+    launch_synthetic(ctx->L(), *st, k_true, sigma_true, mask_prob, n_components, seed);
+    launch_transpose_mask(ctx->L(), *st);
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    *out = make_dataset(ctx, st, nullptr);
+  });
+}
+
+int32_t ppca_b200_dataset_with_weights(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, const double *weights,
+                                       ppca_b200_dataset **out) {
+  return guarded([&] {
+    check_ds(ctx, ds);
+    REQUIRE(out != nullptr && (weights != nullptr || ds->store->n == 0), "null argument");
+    DeviceGuard g(ctx->device);
+    *out = make_dataset(ctx, ds->store, weights);
+  });
+}
+
+int32_t ppca_b200_dataset_len(const ppca_b200_dataset *ds, int64_t *out) {
+  return guarded([&] {
+    REQUIRE(ds != nullptr && out != nullptr, "null argument");
+    *out = ds->store->n;
+  });
+}
+
+int32_t ppca_b200_dataset_output_size(const ppca_b200_dataset *ds, int32_t *out) {
+  return guarded([&] {
+    REQUIRE(ds != nullptr && out != nullptr, "null argument");
+    *out = ds->store->d;
+  });
+}
+
+int32_t ppca_b200_dataset_to_host(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int64_t row0, int64_t nrows,
+                                  double *out) {
+  return guarded([&] {
+    check_ds(ctx, ds);
+    const SampleStore &st = *ds->store;
+    REQUIRE(row0 >= 0 && nrows >= 0 && row0 + nrows <= st.n, "row range out of bounds");
+    if (nrows == 0) return;
+    REQUIRE(out != nullptr, "null output");
+    DeviceGuard g(ctx->device);
+    const int64_t rows_per = std::max<int64_t>(1, ((int64_t)64 << 20) / ((int64_t)st.d * 8));
+    DevBuf<double> buf;
+    buf.alloc((size_t)std::min<int64_t>(rows_per, nrows) * st.d);
+    for (int64_t r0 = 0; r0 < nrows; r0 += rows_per) {
+      const int64_t rows = std::min<int64_t>(rows_per, nrows - r0);
+      launch_export(ctx->L(), st, row0 + r0, rows, buf.p);
+      CUDA_CHECK(cudaMemcpyAsync(out + r0 * st.d, buf.p, sizeof(double) * rows * st.d, cudaMemcpyDeviceToHost,
+                                 ctx->stream));
+      CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    }
+  });
+}
+
+int32_t ppca_b200_dataset_weights(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, double *out) {
+  return guarded([&] {
+    check_ds(ctx, ds);
+    if (ds->store->n == 0) return;
+    REQUIRE(out != nullptr, "null output");
+    DeviceGuard g(ctx->device);
+    CUDA_CHECK(cudaMemcpyAsync(out, ds->w.p, sizeof(double) * ds->store->n, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  });
+}
+
+int32_t ppca_b200_dataset_empty_dimensions(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, uint8_t *out) {
+  return guarded([&] {
+    check_ds(ctx, ds);
+    REQUIRE(out != nullptr, "null output");
+    const SampleStore &st = *ds->store;
+    if (st.n == 0) {  // dataset.rs:195-197: no first sample -> empty list
+      memset(out, 0, st.d);
+      return;
+    }
+    DeviceGuard g(ctx->device);
+    DevBuf<uint8_t> buf;
+    buf.alloc(st.d);
+    launch_empty_dims(ctx->L(), st, buf.p);
+    CUDA_CHECK(cudaMemcpyAsync(out, buf.p, st.d, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  });
+}
+
+int32_t ppca_b200_dataset_slice(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int64_t row0, int64_t nrows,
+                                ppca_b200_dataset **out) {
+  return guarded([&] {
+    check_ds(ctx, ds);
+    const SampleStore &src = *ds->store;
+    REQUIRE(out != nullptr, "null output");
+    REQUIRE(row0 >= 0 && nrows >= 0 && row0 + nrows <= src.n, "row range out of bounds");
+    DeviceGuard g(ctx->device);
+    auto st = make_store(ctx, nrows, src.d);
+    launch_copy_rows(ctx->L(), src, row0, nrows, *st, 0);
+    launch_transpose_mask(ctx->L(), *st);
+    std::unique_ptr<ppca_b200_dataset> nd(make_dataset(ctx, st, nullptr));
+    if (nrows > 0)
+      CUDA_CHECK(cudaMemcpyAsync(nd->w.p, ds->w.p + row0, sizeof(double) * nrows, cudaMemcpyDeviceToDevice, ctx->stream));
+    nd->min_w = ds->min_w;
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    *out = nd.release();
+  });
+}
+
+int32_t ppca_b200_dataset_concat(ppca_b200_ctx *ctx, const ppca_b200_dataset *const *list, int32_t count,
+                                 ppca_b200_dataset **out) {
+  return guarded([&] {
+    REQUIRE(ctx != nullptr && out != nullptr, "null argument");
+    REQUIRE(count >= 1 && list != nullptr, "concat needs at least one dataset");
+    int64_t total = 0;
+    const int d = list[0] && list[0]->store ? list[0]->store->d : 0;
+    for (int i = 0; i < count; ++i) {
+      check_ds(ctx, list[i]);
+      REQUIRE(list[i]->store->d == d, "output sizes differ in concat");
+      total += list[i]->store->n;
+    }
+    DeviceGuard g(ctx->device);
+    auto st = make_store(ctx, total, d);
+    std::unique_ptr<ppca_b200_dataset> nd(make_dataset(ctx, st, nullptr));
+    int64_t pos = 0;
+    double mn = std::numeric_limits<double>::infinity();
+    for (int i = 0; i < count; ++i) {
+      const SampleStore &src = *list[i]->store;
+      launch_copy_rows(ctx->L(), src, 0, src.n, *st, pos);
+      if (src.n > 0)
+        CUDA_CHECK(cudaMemcpyAsync(nd->w.p + pos, list[i]->w.p, sizeof(double) * src.n, cudaMemcpyDeviceToDevice,
+                                   ctx->stream));
+      if (src.n > 0 && list[i]->min_w < mn) mn = list[i]->min_w;
+      pos += src.n;
+    }
+    nd->min_w = mn;
+    launch_transpose_mask(ctx->L(), *st);
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    *out = nd.release();
+  });
+}
+
+int32_t ppca_b200_dataset_destroy(ppca_b200_dataset *ds) {
+  return guarded([&] {
+    if (!ds) return;
+    cudaSetDevice(ds->device);
+    delete ds;
+  });
+}
+
+// ---- PPCAModel ------------------------------------------------------------------------------------
+int32_t ppca_b200_llks(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int32_t k, const double *C, const double *mu,
+                       double sigma, double *out) {
+  return guarded([&] {
+    check_ds(ctx, ds);
+    const SampleStore &st = *ds->store;
+    if (st.n == 0) return;
+    REQUIRE(out != nullptr, "null output");
+    DeviceGuard g(ctx->device);
+    ctx->profile_reset();
+    DevModel m = stage_model(ctx, st.d, k, C, mu, sigma);
+    ctx->rbuf.reserve((size_t)st.n_pad);
+    llks_impl(ctx, st, m, ctx->rbuf.p);
+    CUDA_CHECK(cudaMemcpyAsync(out, ctx->rbuf.p, sizeof(double) * st.n, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    ctx->profile_collect();
+  });
+}
+
+int32_t ppca_b200_llk(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int32_t k, const double *C, const double *mu,
+                      double sigma, double *out) {
+  return guarded([&] {
+    check_ds(ctx, ds);
+    REQUIRE(out != nullptr, "null output");
+    const SampleStore &st = *ds->store;
+    if (st.n == 0) {
+      *out = 0.0;
+      return;
+    }
+    DeviceGuard g(ctx->device);
+    ctx->profile_reset();
+    DevModel m = stage_model(ctx, st.d, k, C, mu, sigma);
+    const int64_t chunk = pick_chunk(ctx, st.n_pad, m.s);
+    reserve_chunk_ws(ctx, chunk, m.s);
+    ctx->stats.reserve(8);
+    CUDA_CHECK(cudaMemsetAsync(ctx->stats.p, 0, sizeof(double) * 8, ctx->stream));
+    for (int64_t row0 = 0; row0 < st.n; row0 += chunk) {
+      const int rows = (int)((st.n - row0) < chunk ? (st.n - row0) : chunk);
+      e_step_chunk(ctx, st, ds->w.p, row0, rows, m, 0, ctx->llk.p, nullptr, ctx->stats.p);
+    }
+    double h[8];
+    CUDA_CHECK(cudaMemcpyAsync(h, ctx->stats.p, sizeof(double) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    *out = h[SC_LLK];
+    ctx->profile_collect();
+  });
+}
+
+int32_t ppca_b200_infer(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int32_t k, const double *C, const double *mu,
+                        double sigma, double *states, double *covariances) {
+  return guarded([&] {
+    check_ds(ctx, ds);
+    const SampleStore &st = *ds->store;
+    if (st.n == 0) return;
+    REQUIRE(states != nullptr, "null output");
+    DeviceGuard g(ctx->device);
+    DevModel m = stage_model(ctx, st.d, k, C, mu, sigma);
+    int64_t chunk = pick_chunk(ctx, st.n_pad, m.s);
+    if (covariances) {  // bound the k x k covariance staging buffer to ~1 GiB
+      const int64_t cap = round_up(std::max<int64_t>(256, ((int64_t)1 << 30) / ((int64_t)k * k * 8)), 256);
+      if (chunk > cap) chunk = cap;
+    }
+    reserve_chunk_ws(ctx, chunk, m.s);
+    if (covariances) ctx->cov.reserve((size_t)chunk * k * k);
+    ctx->rbuf.reserve((size_t)chunk * k);
+    for (int64_t row0 = 0; row0 < st.n; row0 += chunk) {
+      const int rows = (int)((st.n - row0) < chunk ? (st.n - row0) : chunk);
+      e_step_chunk(ctx, st, nullptr, row0, rows, m, 1, nullptr, covariances ? ctx->cov.p : nullptr, nullptr);
+      const int64_t total = (int64_t)rows * k;
+      const int blocks = (int)((total + 255) / 256 < (int64_t)ctx->sms * 8 ? (total + 255) / 256 : (int64_t)ctx->sms * 8);
+      strided_copy_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->YZ.p, rows, k, m.s.kp, ctx->rbuf.p, k);
+      CUDA_CHECK(cudaGetLastError());
+      ++ctx->launches;
+      CUDA_CHECK(cudaMemcpyAsync(states + row0 * k, ctx->rbuf.p, sizeof(double) * rows * k, cudaMemcpyDeviceToHost,
+                                 ctx->stream));
+      if (covariances)
+        CUDA_CHECK(cudaMemcpyAsync(covariances + row0 * k * k, ctx->cov.p, sizeof(double) * rows * k * k,
+                                   cudaMemcpyDeviceToHost, ctx->stream));
+      CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    }
+  });
+}
+
+static int32_t smooth_or_extrapolate(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int32_t k, const double *C,
+                                     const double *mu, double sigma, int extrapolate, ppca_b200_dataset **out) {
+  return guarded([&] {
+    check_ds(ctx, ds);
+    REQUIRE(out != nullptr, "null output");
+    const SampleStore &st = *ds->store;
+    DeviceGuard g(ctx->device);
+    auto ost = make_store(ctx, st.n, st.d);
+    if (st.n > 0) {
+      DevModel m = stage_model(ctx, st.d, k, C, mu, sigma);
+      reconstruct_impl(ctx, st, m, extrapolate, nullptr, 0, 0, *ost);
+      finalize_full_store(ctx, *ost);
+    }
+    std::unique_ptr<ppca_b200_dataset> nd(make_dataset(ctx, ost, nullptr));
+    if (st.n > 0)  // weights are carried through (ppca_model.rs:242,259)
+      CUDA_CHECK(cudaMemcpyAsync(nd->w.p, ds->w.p, sizeof(double) * st.n, cudaMemcpyDeviceToDevice, ctx->stream));
+    nd->min_w = ds->min_w;
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    *out = nd.release();
+  });
+}
+
+int32_t ppca_b200_smooth(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int32_t k, const double *C, const double *mu,
+                         double sigma, ppca_b200_dataset **out) {
+  return smooth_or_extrapolate(ctx, ds, k, C, mu, sigma, 0, out);
+}
+int32_t ppca_b200_extrapolate(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int32_t k, const double *C,
+                              const double *mu, double sigma, ppca_b200_dataset **out) {
+  return smooth_or_extrapolate(ctx, ds, k, C, mu, sigma, 1, out);
+}
+
+int64_t ppca_b200_em_stats_len(int32_t d, int32_t k) {
+  if (d < 1 || k < 1) return 0;
+  return StatsLayout(d, k).len;
+}
+
+int32_t ppca_b200_em_stats(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int32_t k, const double *C,
+                           const double *mu, double sigma, double *stats_dev) {
+  return guarded([&] {
+    check_ds(ctx, ds);
+    REQUIRE(stats_dev != nullptr, "null statistics buffer");
+    DeviceGuard g(ctx->device);
+    ctx->profile_reset();
+    DevModel m = stage_model(ctx, ds->store->d, k, C, mu, sigma);
+    em_stats_impl(ctx, *ds->store, ds->w.p, m, stats_dev);
+    ctx->profile_collect();
+  });
+}
+
+int32_t ppca_b200_em_finish(ppca_b200_ctx *ctx, int32_t d, int32_t k, const double *C, const double *mu, double sigma,
+                            const ppca_b200_prior *prior, const double *stats_dev, double *C_out, double *mu_out,
+                            double *sigma_out, double *llk_in) {
+  return guarded([&] {
+    REQUIRE(ctx != nullptr && stats_dev != nullptr, "null argument");
+    REQUIRE(d >= 1 && k >= 1, "bad shape");
+    DeviceGuard g(ctx->device);
+    em_finish_impl(ctx, d, k, C, mu, sigma, prior, stats_dev, C_out, mu_out, sigma_out, llk_in, nullptr);
+  });
+}
+
+int32_t ppca_b200_iterate(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int32_t k, const double *C,
+                          const double *mu, double sigma, const ppca_b200_prior *prior, double *C_out, double *mu_out,
+                          double *sigma_out, double *llk_in) {
+  return guarded([&] {
+    check_ds(ctx, ds);
+    const SampleStore &st = *ds->store;
+    if (st.n == 0) PPCA_THROW(PPCA_ERR_EMPTY, "non-empty dataset required (ppca_model.rs:358)");
+    DeviceGuard g(ctx->device);
+    ctx->profile_reset();
+    DevModel m = stage_model(ctx, st.d, k, C, mu, sigma);
+    ctx->stats.reserve((size_t)StatsLayout(st.d, k).len);
+    em_stats_impl(ctx, st, ds->w.p, m, ctx->stats.p);
+    em_finish_impl(ctx, st.d, k, C, mu, sigma, prior, ctx->stats.p, C_out, mu_out, sigma_out, llk_in, nullptr);
+    ctx->profile_collect();
+  });
+}
+
+// ---- PPCAMix --------------------------------------------------------------------------------------
+int32_t ppca_b200_mix_llks(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int32_t m, const int32_t *ks,
+                           const double *Cs, const double *mus, const double *sigmas, const double *log_weights,
+                           double *out) {
+  return guarded([&] {
+    check_ds(ctx, ds);
+    MixView mv{m, ks, Cs, mus, sigmas, log_weights, ds->store->d};
+    check_mix(mv);
+    const SampleStore &st = *ds->store;
+    if (st.n == 0) return;
+    REQUIRE(out != nullptr, "null output");
+    DeviceGuard g(ctx->device);
+    DevBuf<double> LP, ml;
+    LP.alloc((size_t)st.n * m);
+    ml.alloc((size_t)st.n);
+    mix_posteriors_impl(ctx, ds, mv, LP.p, ml.p, nullptr, nullptr);
+    CUDA_CHECK(cudaMemcpyAsync(out, ml.p, sizeof(double) * st.n, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  });
+}
+
+int32_t ppca_b200_mix_llk(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int32_t m, const int32_t *ks,
+                          const double *Cs, const double *mus, const double *sigmas, const double *log_weights,
+                          double *out) {
+  return guarded([&] {
+    check_ds(ctx, ds);
+    MixView mv{m, ks, Cs, mus, sigmas, log_weights, ds->store->d};
+    check_mix(mv);
+    REQUIRE(out != nullptr, "null output");
+    const SampleStore &st = *ds->store;
+    if (st.n == 0) {  // mix.rs:164-166
+      *out = 0.0;
+      return;
+    }
+    DeviceGuard g(ctx->device);
+    DevBuf<double> LP, ml, sum;
+    LP.alloc((size_t)st.n * m);
+    ml.alloc((size_t)st.n);
+    sum.alloc(1);
+    mix_posteriors_impl(ctx, ds, mv, LP.p, ml.p, nullptr, sum.p);
+    CUDA_CHECK(cudaMemcpyAsync(out, sum.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  });
+}
+
+int32_t ppca_b200_mix_infer_cluster(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int32_t m, const int32_t *ks,
+                                    const double *Cs, const double *mus, const double *sigmas,
+                                    const double *log_weights, double *out) {
+  return guarded([&] {
+    check_ds(ctx, ds);
+    MixView mv{m, ks, Cs, mus, sigmas, log_weights, ds->store->d};
+    check_mix(mv);
+    const SampleStore &st = *ds->store;
+    if (st.n == 0) return;
+    REQUIRE(out != nullptr, "null output");
+    DeviceGuard g(ctx->device);
+    DevBuf<double> LP;
+    LP.alloc((size_t)st.n * m);
+    mix_posteriors_impl(ctx, ds, mv, LP.p, nullptr, nullptr, nullptr);
+    CUDA_CHECK(cudaMemcpyAsync(out, LP.p, sizeof(double) * st.n * m, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  });
+}
+
+__global__ void exp_inplace_kernel(double *p, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    p[i] = exp(p[i]);
+}
+
+static int32_t mix_smooth_or_extrapolate(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int32_t m,
+                                         const int32_t *ks, const double *Cs, const double *mus, const double *sigmas,
+                                         const double *log_weights, int extrapolate, ppca_b200_dataset **out) {
+  return guarded([&] {
+    check_ds(ctx, ds);
+    MixView mv{m, ks, Cs, mus, sigmas, log_weights, ds->store->d};
+    check_mix(mv);
+    REQUIRE(out != nullptr, "null output");
+    const SampleStore &st = *ds->store;
+    DeviceGuard g(ctx->device);
+    auto ost = make_store(ctx, st.n, st.d);
+    if (st.n > 0) {
+      DevBuf<double> LP;
+      LP.alloc((size_t)st.n * m);
+      mix_posteriors_impl(ctx, ds, mv, LP.p, nullptr, nullptr, nullptr);
+      const int64_t total = st.n * m;
+      const int blocks = (int)((total + 255) / 256 < (int64_t)ctx->sms * 8 ? (total + 255) / 256 : (int64_t)ctx->sms * 8);
+      exp_inplace_kernel<<<blocks, 256, 0, ctx->stream>>>(LP.p, total);  // posterior() (mix.rs:366-368)
+      CUDA_CHECK(cudaGetLastError());
+      ++ctx->launches;
+      for (int j = 0; j < m; ++j) {  // sum_j posterior_j * (smoothed | extrapolated)_j  (mix.rs:397-414)
+        DevModel dm = stage_model(ctx, st.d, ks[j], mv.C(j), mv.mu(j), sigmas[j]);
+        reconstruct_impl(ctx, st, dm, extrapolate, LP.p + j, m, j > 0 ? 1 : 0, *ost);
+      }
+      finalize_full_store(ctx, *ost);
+    }
+    *out = make_dataset(ctx, ost, nullptr);  // weights reset to 1 (mix.rs:245-265)
+  });
+}
+
+int32_t ppca_b200_mix_smooth(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int32_t m, const int32_t *ks,
+                             const double *Cs, const double *mus, const double *sigmas, const double *log_weights,
+                             ppca_b200_dataset **out) {
+  return mix_smooth_or_extrapolate(ctx, ds, m, ks, Cs, mus, sigmas, log_weights, 0, out);
+}
+int32_t ppca_b200_mix_extrapolate(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int32_t m, const int32_t *ks,
+                                  const double *Cs, const double *mus, const double *sigmas, const double *log_weights,
+                                  ppca_b200_dataset **out) {
+  return mix_smooth_or_extrapolate(ctx, ds, m, ks, Cs, mus, sigmas, log_weights, 1, out);
+}
+
+int32_t ppca_b200_mix_posteriors(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int32_t m, const int32_t *ks,
+                                 const double *Cs, const double *mus, const double *sigmas, const double *log_weights,
+                                 double *logpost_dev, double *comp_max, double *llk_in) {
+  return guarded([&] {
+    check_ds(ctx, ds);
+    MixView mv{m, ks, Cs, mus, sigmas, log_weights, ds->store->d};
+    check_mix(mv);
+    REQUIRE(logpost_dev != nullptr && comp_max != nullptr, "null output");
+    const SampleStore &st = *ds->store;
+    if (st.n > 0 && !(ds->min_w > 0.0))
+      PPCA_THROW(PPCA_ERR_WEIGHTS, "mixture EM needs strictly positive weights (mix.rs:304-309,326)");
+    DeviceGuard g(ctx->device);
+    DevBuf<double> ml, cm, sum;
+    ml.alloc((size_t)std::max<int64_t>(st.n, 1));
+    cm.alloc((size_t)m);
+    sum.alloc(1);
+    CUDA_CHECK(cudaMemsetAsync(sum.p, 0, sizeof(double), ctx->stream));
+    mix_posteriors_impl(ctx, ds, mv, logpost_dev, ml.p, cm.p, st.n > 0 ? sum.p : nullptr);
+    double h = 0.0;
+    CUDA_CHECK(cudaMemcpyAsync(comp_max, cm.p, sizeof(double) * m, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaMemcpyAsync(&h, sum.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    if (llk_in) *llk_in = h;
+  });
+}
+
+int32_t ppca_b200_mix_em_stats(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int32_t m, int32_t j, int32_t k,
+                               const double *C, const double *mu, double sigma, const double *logpost_dev,
+                               double comp_max_j, double *stats_dev) {
+  return guarded([&] {
+    check_ds(ctx, ds);
+    REQUIRE(logpost_dev != nullptr && stats_dev != nullptr, "null argument");
+    REQUIRE(j >= 0 && j < m, "component index out of range");
+    const SampleStore &st = *ds->store;
+    DeviceGuard g(ctx->device);
+    ctx->rbuf.reserve((size_t)st.n_pad);
+    CUDA_CHECK(cudaMemsetAsync(ctx->rbuf.p, 0, sizeof(double) * st.n_pad, ctx->stream));
+    launch_responsibilities(ctx->L(), logpost_dev, st.n, m, j, ds->w.p, comp_max_j, ctx->rbuf.p);
+    DevModel dm = stage_model(ctx, st.d, k, C, mu, sigma);
+    em_stats_impl(ctx, st, ctx->rbuf.p, dm, stats_dev);
+  });
+}
+
+int32_t ppca_b200_mix_iterate(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int32_t m, const int32_t *ks,
+                              const double *Cs, const double *mus, const double *sigmas, const double *log_weights,
+                              const ppca_b200_prior *prior, double *Cs_out, double *mus_out, double *sigmas_out,
+                              double *log_weights_out, double *llk_in) {
+  return guarded([&] {
+    check_ds(ctx, ds);
+    MixView mv{m, ks, Cs, mus, sigmas, log_weights, ds->store->d};
+    check_mix(mv);
+    REQUIRE(Cs_out && mus_out && sigmas_out && log_weights_out, "null output");
+    const SampleStore &st = *ds->store;
+    if (st.n == 0) PPCA_THROW(PPCA_ERR_EMPTY, "dataset not empty (mix.rs:315)");
+    DeviceGuard g(ctx->device);
+    DevBuf<double> LP;
+    LP.alloc((size_t)st.n * m);
+    std::vector<double> cmax(m);
+    int32_t rc = ppca_b200_mix_posteriors(ctx, ds, m, ks, Cs, mus, sigmas, log_weights, LP.p, cmax.data(), llk_in);
+    if (rc) throw Error{rc, g_last_error};
+    std::vector<double> logsum(m);
+    for (int j = 0; j < m; ++j) {
+      const int kj = ks[j];
+      DevBuf<double> stats;
+      stats.alloc((size_t)StatsLayout(st.d, kj).len);
+      rc = ppca_b200_mix_em_stats(ctx, ds, m, j, kj, mv.C(j), mv.mu(j), sigmas[j], LP.p, cmax[j], stats.p);
+      if (rc) throw Error{rc, g_last_error};
+      double sumw = 0.0;
+      const size_t off = (size_t)(mv.C(j) - Cs);
+      em_finish_impl(ctx, st.d, kj, mv.C(j), mv.mu(j), sigmas[j], prior, stats.p, Cs_out + off,
+                     mus_out + (size_t)j * st.d, sigmas_out + j, nullptr, &sumw);
+      logsum[j] = std::log(sumw) + cmax[j];  // mix.rs:323-324
+    }
+    // robust_log_softmax (mix.rs:14-18, :335)
+    double mx = logsum[0];
+    for (int j = 1; j < m; ++j) mx = logsum[j] > mx ? logsum[j] : mx;
+    double s = 0.0;
+    for (int j = 0; j < m; ++j) s += std::exp(logsum[j] - mx);
+    const double ln = std::log(s);
+    for (int j = 0; j < m; ++j) log_weights_out[j] = logsum[j] - mx - ln;
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,227 @@
+// common.cuh — shared definitions for the B200 PPCA engine (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/ppca_b200.h"
+
+namespace ppca {
+
+// ---------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------
+void set_error(const std::string &msg);
+struct Error {
+  int code;
+  std::string msg;
+};
+#define PPCA_THROW(code_, ...)                               \
+  do {                                                       \
+    char buf_[512];                                          \
+    snprintf(buf_, sizeof(buf_), __VA_ARGS__);               \
+    throw ::ppca::Error{(code_), std::string(buf_)};         \
+  } while (0)
+#define CUDA_CHECK(expr)                                                                        \
+  do {                                                                                          \
+    cudaError_t e_ = (expr);                                                                    \
+    if (e_ != cudaSuccess)                                                                      \
+      PPCA_THROW(PPCA_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, \
+                 __LINE__);                                                                     \
+  } while (0)
+#define REQUIRE(cond, ...) \
+  do {                     \
+    if (!(cond)) PPCA_THROW(PPCA_ERR_INVALID, __VA_ARGS__); \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// shapes
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+__host__ __device__ inline int tri(int k) { return k * (k + 1) / 2; }
+// packed upper-by-rows index of (a, b), a <= b, in a k x k symmetric matrix
+__host__ __device__ inline int tri_row_off(int a, int k) { return a * k - (a * (a - 1)) / 2; }
+__host__ __device__ inline int tri_idx(int a, int b, int k) { return tri_row_off(a, k) + (b - a); }
+
+struct Shape {
+  int d, k;
+  int kk;    // k(k+1)/2
+  int kkp;   // kk rounded up to 8 (n8 MMA tiles, 64-byte rows)
+  int kp;    // k rounded up to 8
+  int d32;   // d rounded up to 32 (mask words)
+  __host__ __device__ Shape() {}
+  __host__ __device__ Shape(int d_, int k_) : d(d_), k(k_) {
+    kk = tri(k_);
+    kkp = (int)round_up(kk > 0 ? kk : 1, 8);
+    kp = (int)round_up(k_ > 0 ? k_ : 1, 8);
+    d32 = (int)round_up(d_, 32);
+  }
+};
+
+// statistics buffer layout (see ppca_b200_em_stats_len)
+struct StatsLayout {
+  int64_t offA, offB, offTdev, offTotals, offScalars, len;
+  StatsLayout(int d, int k) {
+    Shape s(d, k);
+    offA = 0;
+    offB = offA + (int64_t)d * s.kkp;
+    offTdev = offB + (int64_t)d * s.kp;
+    offTotals = offTdev + d;
+    offScalars = offTotals + d;
+    len = offScalars + 8;
+  }
+};
+enum { SC_SQERR = 0, SC_DEV2 = 1, SC_LLK = 2, SC_SUMW = 3, SC_NONEMPTY = 4 };
+
+// ---------------------------------------------------------------------------------------------
+// device buffers
+// ---------------------------------------------------------------------------------------------
+template <class T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t count = 0;
+  DevBuf() {}
+  DevBuf(const DevBuf &) = delete;
+  DevBuf &operator=(const DevBuf &) = delete;
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    count = 0;
+  }
+  void alloc(size_t n) {
+    release();
+    if (n == 0) n = 1;
+    CUDA_CHECK(cudaMalloc((void **)&p, n * sizeof(T)));
+    count = n;
+  }
+  // grow-only
+  void reserve(size_t n) {
+    if (n > count) alloc(n);
+  }
+};
+
+// immutable sample storage shared between datasets that differ only in weights
+struct SampleStore {
+  int64_t n = 0;       // samples
+  int d = 0;           // output size
+  int ldx = 0;         // row stride of X in doubles (multiple of 4)
+  int dw = 0;          // mask words per sample = ceil(d/32)
+  int64_t n_pad = 0;   // samples rounded up to 256 (rows of mask are allocated/zeroed up to here)
+  int64_t nwT = 0;     // words per dimension row of maskT = n_pad / 32
+  int d_pad = 0;       // rows of maskT, d rounded up to 256, zeroed
+  DevBuf<double> X;        // n_pad x ldx ; masked slots and padding hold 0.0
+  DevBuf<uint32_t> mask;   // n_pad x dw  ; bit b of word j <-> dimension 32 j + b (LSB first, like bit-vec)
+  DevBuf<uint32_t> maskT;  // d_pad x nwT ; bit b of word j <-> sample 32 j + b
+  DevBuf<int> dn;          // n_pad observed counts
+};
+
+}  // namespace ppca
+
+struct ppca_b200_dataset {
+  std::shared_ptr<ppca::SampleStore> store;
+  ppca::DevBuf<double> w;  // n_pad weights (padding 0)
+  double min_w = 1.0;      // smallest weight (mixture EM needs > 0, mix.rs:304-309)
+  int device = 0;
+};
+
+namespace ppca {
+
+// per-iteration device model
+struct DevModel {
+  Shape s;
+  double sigma;
+  const double *C;     // d32 x kp   (zero padded)
+  const double *mu;    // d32
+  const double *Ksym;  // d32 x kkp  (zero padded rows and columns)
+};
+
+struct Launcher {
+  cudaStream_t stream;
+  int64_t *launch_counter;
+  int sms;
+};
+
+// ---- kernels (host launchers) ----------------------------------------------------------------
+// ingest.cu
+void launch_ingest(const Launcher &L, const double *raw, int64_t nrows, int d, int64_t row0, SampleStore &st);
+void launch_transpose_mask(const Launcher &L, SampleStore &st);
+void launch_export(const Launcher &L, const SampleStore &st, int64_t row0, int64_t nrows, double *out_dev);
+void launch_empty_dims(const Launcher &L, const SampleStore &st, uint8_t *out_dev);
+void launch_synthetic(const Launcher &L, SampleStore &st, int k_true, double sigma_true, double mask_prob,
+                      int n_components, uint64_t seed);
+void launch_copy_rows(const Launcher &L, const SampleStore &src, int64_t src_row0, int64_t nrows, SampleStore &dst,
+                      int64_t dst_row0);
+
+// model.cu
+void launch_prepare_model(const Launcher &L, const double *C_host_layout_dev, const double *mu_dev, int d, int k,
+                          double *Cpad, double *mupad, double *Ksym);
+
+// bitgemm.cu :  Out[M x Nq] (+)= Bits[M x 32*kblocks] * Bmat[32*kblocks x Nq]
+struct BitGemmArgs {
+  const uint32_t *bits;  // row-major words, row stride ldbits; word offset already applied
+  int64_t ldbits;
+  const double *Bmat;    // row-major, row stride ldb (even)
+  int64_t ldb;
+  double *Out;           // row-major, row stride ldo (even)
+  int64_t ldo;
+  int M;                 // rows of Out (bit rows)
+  int Nq;                // columns, multiple of 8
+  int kblocks;           // number of 32-wide K blocks
+  int accumulate;        // Out += result (else Out = result)
+  double *partials;      // workspace for split-K (may be null when splitk == 1)
+  int splitk;
+};
+int bitgemm_pick_splitk(int M, int Nq, int kblocks, int sms);
+size_t bitgemm_partials_len(int M, int Nq, int splitk);
+void launch_bitgemm(const Launcher &L, const BitGemmArgs &a);
+
+// proj.cu : Y[n][a] = sum_i sel(m_ni, x_ni - mu_i) C[i][a] ; nx[n] = sum_i sel(...)^2
+void launch_proj(const Launcher &L, const SampleStore &st, int64_t row0, int rows, const DevModel &m, double *Y,
+                 double *nx);
+
+// solve.cu : per-sample k x k factorisation
+struct SolveArgs {
+  Shape s;
+  double sigma;
+  int rows;            // valid samples in the chunk
+  int rows_pad;        // rows of GW / YZ to (zero) fill, multiple of 32
+  double *GW;          // rows_pad x kkp : in G (packed upper), out W = w (z z^T + Sigma)  [mode EM]
+  double *YZ;          // rows_pad x kp  : in y, out z
+  double *WZ;          // rows_pad x kp  : out w z   (nullable)
+  const double *nx;    // rows
+  const int *dn;       // rows
+  const double *w;     // rows (nullable = 1)
+  double *llk;         // rows : out per-sample log-likelihood (nullable)
+  double *tn;          // rows : out per-sample tr(Sigma_n G_n) (nullable, mode 2)
+  double *cov;         // rows x k x k full covariances (nullable)
+  double *scalars;     // stats scalars to accumulate into (nullable; needs llk): SC_SQERR, SC_LLK, SC_SUMW, SC_NONEMPTY
+  int mode;            // 0 = llk only, 1 = infer (z, cov), 2 = EM (z, W, wz, t)
+};
+void launch_solve(const Launcher &L, const SolveArgs &a);
+
+// moments.cu : B += Xc^T (w z) ; residual statistics ; reconstruction writers
+void launch_cross_resid(const Launcher &L, const SampleStore &st, int64_t row0, int rows, const DevModel &m,
+                        const double *Z, const double *WZ, const double *w, double *statB, double *statTdev,
+                        double *statTotals, double *scalars, double *partials, size_t partials_len);
+size_t cross_resid_partials_len(int d, int k, int rows, int sms);
+// out = extrapolate ? (m ? x : C z + mu) : C z + mu ; scale != null multiplies by scale[n*scale_ld] and accumulates
+void launch_reconstruct(const Launcher &L, const SampleStore &st, int64_t row0, int rows, const DevModel &m,
+                        const double *Z, int extrapolate, const double *scale, int64_t scale_ld, int accumulate,
+                        double *outX, int64_t ldo);
+
+// finish.cu : per-dimension solves (A_i + tau I) c = B_i
+void launch_row_solve(const Launcher &L, int d, int k, const double *statA, const double *statB, double tau,
+                      const double *Cold_pad, double *Cnew /* d x k dense */, int *flags);
+
+// mix.cu
+void launch_log_softmax_rows(const Launcher &L, double *LP, int64_t n, int m, const double *logw_dev,
+                             const double *w, double *mix_llk /* n, nullable */, double *comp_max /* m */,
+                             double *llk_sum /* 1, nullable */);
+void launch_responsibilities(const Launcher &L, const double *LP, int64_t n, int m, int j, const double *w,
+                             double comp_max_j, double *r_out);
+
+}  // namespace ppca

@@ -1,0 +1,215 @@
+// ingest.cu — Dataset / MaskedSample / Mask on the device.
+//
+// Reference data model (dataset.rs:11-14,93-100; utils.rs:27-28): an array of heap vectors, each with a
+// BitVec mask where bit = is_finite(x) (dataset.rs:19-22).  Here: one row-major f64 matrix X (masked slots
+// sanitised to 0.0), a bit-packed mask with the same LSB-first u32 block layout as bit-vec, its 32x32-block
+// transpose (left operand of the M-step contraction), and the per-sample observed counts.
+#include "common.cuh"
+#include "mma.cuh"
+
+namespace ppca {
+
+// one warp per sample row: mask = isfinite, sanitise, pack with ballot, popcount
+__global__ void ingest_kernel(const double *__restrict__ raw, int64_t nrows, int d, int64_t row0, double *X, int ldx,
+                              uint32_t *mask, int dw, int *dn) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (row >= nrows) return;
+  const double *src = raw + row * d;
+  double *dst = X + (row0 + row) * ldx;
+  int count = 0;
+  for (int j = 0; j < dw; ++j) {
+    const int i = 32 * j + lane;
+    double x = (i < d) ? src[i] : __longlong_as_double(0x7ff8000000000000LL);
+    const bool fin = isfinite(x);
+    const uint32_t word = __ballot_sync(0xffffffffu, fin);
+    if (i < ldx) dst[i] = fin ? x : 0.0;
+    if (lane == 0) mask[(row0 + row) * dw + j] = word;
+    count += __popc(word);
+  }
+  if (lane == 0) dn[row0 + row] = count;
+}
+
+void launch_ingest(const Launcher &L, const double *raw, int64_t nrows, int d, int64_t row0, SampleStore &st) {
+  if (nrows <= 0) return;
+  const int threads = 256;
+  const int64_t blocks = (nrows * 32 + threads - 1) / threads;
+  ingest_kernel<<<(unsigned)blocks, threads, 0, L.stream>>>(raw, nrows, d, row0, st.X.p, st.ldx, st.mask.p, st.dw,
+                                                            st.dn.p);
+  CUDA_CHECK(cudaGetLastError());
+  ++*L.launch_counter;
+}
+
+// maskT[32 j + b][bs] bit l  =  mask[32 bs + l][j] bit b.   One warp per 32x32 bit block; 32 warps per CTA
+// cover 32 consecutive sample blocks so the transposed words leave as 128-byte rows.
+__global__ void __launch_bounds__(1024) transpose_mask_kernel(const uint32_t *__restrict__ mask, int dw, int64_t n_pad,
+                                                              uint32_t *maskT, int64_t nwT) {
+  __shared__ uint32_t tile[32][33];
+  const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+  const int j = blockIdx.y;
+  const int64_t bs = (int64_t)blockIdx.x * 32 + wi;
+  uint32_t v = 0;
+  if (bs < nwT) v = mask[(bs * 32 + lane) * dw + j];
+  uint32_t mine = 0;
+#pragma unroll
+  for (int b = 0; b < 32; ++b) {
+    const uint32_t t = __ballot_sync(0xffffffffu, (v >> b) & 1u);
+    if (lane == b) mine = t;
+  }
+  tile[lane][wi] = mine;
+  __syncthreads();
+  const int64_t col = (int64_t)blockIdx.x * 32 + lane;
+  if (col < nwT) maskT[((int64_t)32 * j + wi) * nwT + col] = tile[wi][lane];
+}
+
+void launch_transpose_mask(const Launcher &L, SampleStore &st) {
+  if (st.n == 0) return;
+  dim3 grid((unsigned)((st.nwT + 31) / 32), (unsigned)st.dw);
+  transpose_mask_kernel<<<grid, 1024, 0, L.stream>>>(st.mask.p, st.dw, st.n_pad, st.maskT.p, st.nwT);
+  CUDA_CHECK(cudaGetLastError());
+  ++*L.launch_counter;
+}
+
+// Dataset.numpy(): NaN at masked slots (dataset.rs:64-72 masked_vector)
+__global__ void export_kernel(const double *__restrict__ X, int ldx, const uint32_t *__restrict__ mask, int dw, int d,
+                              int64_t row0, int64_t nrows, double *out) {
+  const int64_t total = nrows * d;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = idx / d;
+    const int i = (int)(idx % d);
+    const uint32_t w = mask[(row0 + row) * dw + (i >> 5)];
+    out[idx] = ((w >> (i & 31)) & 1u) ? X[(row0 + row) * ldx + i] : __longlong_as_double(0x7ff8000000000000LL);
+  }
+}
+
+void launch_export(const Launcher &L, const SampleStore &st, int64_t row0, int64_t nrows, double *out_dev) {
+  if (nrows <= 0) return;
+  const int64_t total = nrows * st.d;
+  const int64_t want = (total + 255) / 256;
+  const int blocks = (int)(want < (int64_t)L.sms * 16 ? want : (int64_t)L.sms * 16);
+  export_kernel<<<blocks, 256, 0, L.stream>>>(st.X.p, st.ldx, st.mask.p, st.dw, st.d, row0, nrows, out_dev);
+  CUDA_CHECK(cudaGetLastError());
+  ++*L.launch_counter;
+}
+
+// Dataset::empty_dimensions (dataset.rs:194-222): OR of all masks; one warp per dimension over maskT
+__global__ void empty_dims_kernel(const uint32_t *__restrict__ maskT, int64_t nwT, int d, uint8_t *out) {
+  const int lane = threadIdx.x & 31;
+  const int i = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
+  if (i >= d) return;
+  uint32_t acc = 0;
+  for (int64_t j = lane; j < nwT; j += 32) acc |= maskT[(int64_t)i * nwT + j];
+  acc = __reduce_or_sync(0xffffffffu, acc);
+  if (lane == 0) out[i] = acc == 0u ? 1 : 0;
+}
+
+void launch_empty_dims(const Launcher &L, const SampleStore &st, uint8_t *out_dev) {
+  if (st.d == 0) return;
+  const int threads = 256;
+  const int blocks = (st.d * 32 + threads - 1) / threads;
+  empty_dims_kernel<<<blocks, threads, 0, L.stream>>>(st.maskT.p, st.nwT, st.d, out_dev);
+  CUDA_CHECK(cudaGetLastError());
+  ++*L.launch_counter;
+}
+
+void launch_copy_rows(const Launcher &L, const SampleStore &src, int64_t src_row0, int64_t nrows, SampleStore &dst,
+                      int64_t dst_row0) {
+  if (nrows <= 0) return;
+  CUDA_CHECK(cudaMemcpyAsync(dst.X.p + dst_row0 * dst.ldx, src.X.p + src_row0 * src.ldx,
+                             sizeof(double) * nrows * src.ldx, cudaMemcpyDeviceToDevice, L.stream));
+  CUDA_CHECK(cudaMemcpyAsync(dst.mask.p + dst_row0 * dst.dw, src.mask.p + src_row0 * src.dw,
+                             sizeof(uint32_t) * nrows * src.dw, cudaMemcpyDeviceToDevice, L.stream));
+  CUDA_CHECK(cudaMemcpyAsync(dst.dn.p + dst_row0, src.dn.p + src_row0, sizeof(int) * nrows, cudaMemcpyDeviceToDevice,
+                             L.stream));
+}
+
+// ---------------------------------------------------------------------------------------------
+// synthetic data (ppca_model.rs:164-191 sample_one semantics; mix.rs:124-134 for n_components > 1)
+// counter-based RNG: splitmix64 of (seed, stream, counter) -> uniform -> Box-Muller
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ inline uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ULL;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+  return x ^ (x >> 31);
+}
+__device__ inline uint64_t rng_u64(uint64_t seed, uint64_t stream, uint64_t ctr) {
+  return splitmix64(splitmix64(seed ^ (stream * 0xD1342543DE82EF95ULL)) + ctr);
+}
+__device__ inline double rng_uniform(uint64_t seed, uint64_t stream, uint64_t ctr) {  // (0,1)
+  return ((double)(rng_u64(seed, stream, ctr) >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+}
+__device__ inline double rng_normal(uint64_t seed, uint64_t stream, uint64_t ctr) {
+  const double u1 = rng_uniform(seed, stream, 2 * ctr), u2 = rng_uniform(seed, stream, 2 * ctr + 1);
+  return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+}
+
+// truth tables: Ct[j][i][a] ~ Bernoulli(0.1) (examples/big_toy_model.py:6), mut[j][i] = 0 for a single
+// component, ~ N(0, 1) for mixtures so that components are distinguishable
+__global__ void synth_truth_kernel(int d, int k_true, int n_components, uint64_t seed, double *Ct, double *mut) {
+  const int64_t total = (int64_t)n_components * d * k_true;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x)
+    Ct[idx] = rng_uniform(seed, 1, (uint64_t)idx) < 0.1 ? 1.0 : 0.0;
+  const int64_t totm = (int64_t)n_components * d;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < totm;
+       idx += (int64_t)gridDim.x * blockDim.x)
+    mut[idx] = n_components > 1 ? rng_normal(seed, 2, (uint64_t)idx) : 0.0;
+}
+
+// one warp per sample
+__global__ void __launch_bounds__(256) synth_kernel(int64_t n, int d, int k_true, int n_components, double sigma_true,
+                                                    double mask_prob, uint64_t seed, const double *__restrict__ Ct,
+                                                    const double *__restrict__ mut, double *X, int ldx, uint32_t *mask,
+                                                    int dw, int *dn) {
+  extern __shared__ double xi_all[];  // warps x k_true
+  const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+  const int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (row >= n) return;
+  double *xi = xi_all + wi * k_true;
+  for (int a = lane; a < k_true; a += 32) xi[a] = rng_normal(seed, 3, (uint64_t)row * k_true + a);
+  __syncwarp();
+  const int comp = n_components > 1 ? (int)(rng_u64(seed, 4, (uint64_t)row) % (uint64_t)n_components) : 0;
+  const double *Cj = Ct + (int64_t)comp * d * k_true;
+  const double *mj = mut + (int64_t)comp * d;
+  int count = 0;
+  for (int j = 0; j < dw; ++j) {
+    const int i = 32 * j + lane;
+    double x = 0.0;
+    bool obs = false;
+    if (i < d) {
+      const double *crow = Cj + (int64_t)i * k_true;
+      double acc = mj[i];
+      for (int a = 0; a < k_true; ++a) acc += crow[a] * xi[a];
+      x = acc + sigma_true * rng_normal(seed, 5, (uint64_t)row * d + i);
+      obs = !(rng_uniform(seed, 6, (uint64_t)row * d + i) < mask_prob);
+    }
+    const uint32_t word = __ballot_sync(0xffffffffu, obs);
+    if (i < ldx) X[row * ldx + i] = obs ? x : 0.0;
+    if (lane == 0) mask[row * dw + j] = word;
+    count += __popc(word);
+  }
+  if (lane == 0) dn[row] = count;
+}
+
+void launch_synthetic(const Launcher &L, SampleStore &st, int k_true, double sigma_true, double mask_prob,
+                      int n_components, uint64_t seed) {
+  DevBuf<double> Ct, mut;
+  Ct.alloc((size_t)n_components * st.d * k_true);
+  mut.alloc((size_t)n_components * st.d);
+  synth_truth_kernel<<<L.sms * 4, 256, 0, L.stream>>>(st.d, k_true, n_components, seed, Ct.p, mut.p);
+  CUDA_CHECK(cudaGetLastError());
+  ++*L.launch_counter;
+  const int threads = 256;
+  const int64_t blocks = (st.n * 32 + threads - 1) / threads;
+  const size_t smem = sizeof(double) * (threads / 32) * k_true;
+  synth_kernel<<<(unsigned)blocks, threads, smem, L.stream>>>(st.n, st.d, k_true, n_components, sigma_true, mask_prob,
+                                                              seed, Ct.p, mut.p, st.X.p, st.ldx, st.mask.p, st.dw,
+                                                              st.dn.p);
+  CUDA_CHECK(cudaGetLastError());
+  ++*L.launch_counter;
+  CUDA_CHECK(cudaStreamSynchronize(L.stream));  // Ct / mut are freed on return
+}
+
+}  // namespace ppca

@@ -1,0 +1,456 @@
+// moments.cu — the sample-matrix side of the M-step and the reconstruction writers.
+//
+// cross_resid_kernel (one pass over X per EM iteration):
+//   B      += Xc^T (w .* Z)                  total_cross_moment            (ppca_model.rs:281-293)
+//   R       = m .* (Xc - Z C^T)              deviation, OLD C and OLD mu   (ppca_model.rs:338-342)
+//   dev2   += sum_n w_n |R_n|^2              deviations_square_sum         (:346)
+//   tdev_i += sum_n w_n R_ni                 total_deviation               (:347)
+//   tot_i  += sum_n w_n m_ni                 totals                        (:348)
+// Both contractions run on DMMA from one centred shared-memory tile of X: the cross moment with
+// (M,N,K) = (dims, k, samples) and the reconstruction with (samples, dims, k).
+// Empty samples have all bits clear and contribute nothing, matching the reference's filter (:333).
+//
+// reconstruct_kernel: smoothed = C z + mu (ppca_model.rs:454-456); extrapolated = mask.choose(x, smoothed)
+// (:460-463, utils.rs:137-153) — observed slots are copied, never recomputed.
+#include "common.cuh"
+#include "mma.cuh"
+
+namespace ppca {
+
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gmem_src, int src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(smem_u32(smem_dst)), "l"(gmem_src),
+               "r"(src_bytes));
+}
+
+template <int KT, int BS>
+struct CrCfg {
+  static constexpr int BD = 64, LDX = 68;
+  static constexpr int KPP = 8 * KT;
+  static constexpr int LDZ = KPP + ((20 - KPP % 16) % 16);
+  static constexpr int STAGE = BS * LDX + 2 * BS * LDZ + BS + BS;  // X, Z, WZ, w, mask words (2 u32 per row)
+  static constexpr int FIXED = BD * LDZ + BD;                      // C block, mu
+  static constexpr size_t SMEM = (size_t)(FIXED + 2 * STAGE) * sizeof(double);
+  static constexpr int MI = BS / 32;  // phase-B m8 tiles per warp
+};
+
+struct CrArgs {
+  const double *X;
+  int ldx;
+  const uint32_t *mask;
+  int dw;
+  int64_t row0;
+  int rows;
+  const double *Cpad;
+  int kp;
+  int d32;
+  const double *mupad;
+  const double *Z, *WZ;  // chunk-local, row pitch kp
+  const double *w;       // chunk-local weights
+  int d64;               // dblocks * 64
+  double *pB, *pT, *pO, *pD;
+};
+
+template <int KT, int BS>
+__global__ void __launch_bounds__(256, 1) cross_resid_kernel(CrArgs a) {
+  using Cfg = CrCfg<KT, BS>;
+  constexpr int LDX = Cfg::LDX, LDZ = Cfg::LDZ, KPP = Cfg::KPP, MI = Cfg::MI, NI = 4;
+  extern __shared__ __align__(16) double smem[];
+  double *sC = smem;
+  double *sMu = sC + 64 * LDZ;
+  double *stage0 = sMu + 64;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int r = lane >> 2, c = lane & 3;
+  const int xb = blockIdx.x;  // dimension block
+  const int ntiles = (a.rows + BS - 1) / BS;
+
+  auto load_tile = [&](int st, int t) {
+    double *sX = stage0 + st * Cfg::STAGE;
+    double *sZ = sX + BS * LDX;
+    double *sWZ = sZ + BS * LDZ;
+    double *sW = sWZ + BS * LDZ;
+    uint32_t *sM = reinterpret_cast<uint32_t *>(sW + BS);
+    const int base = t * BS;
+    for (int idx = tid; idx < BS * 32; idx += 256) {
+      const int row = idx >> 5, col = (idx & 31) * 2;
+      const int gcol = 64 * xb + col;
+      const bool ok = gcol < a.ldx;
+      const double *src = ok ? a.X + (a.row0 + base + row) * a.ldx + gcol : a.X;
+      cp_async16(sX + row * LDX + col, src, ok ? 16 : 0);
+    }
+    for (int idx = tid; idx < BS * (KPP / 2); idx += 256) {
+      const int row = idx / (KPP / 2), col = (idx % (KPP / 2)) * 2;
+      const bool ok = col < a.kp;
+      const int64_t off = (int64_t)(base + row) * a.kp + col;
+      cp_async16(sZ + row * LDZ + col, ok ? a.Z + off : a.Z, ok ? 16 : 0);
+      cp_async16(sWZ + row * LDZ + col, ok ? a.WZ + off : a.WZ, ok ? 16 : 0);
+    }
+    for (int idx = tid; idx < BS; idx += 256) cp_async8(sW + idx, a.w + base + idx, 8);
+    for (int idx = tid; idx < BS * 2; idx += 256) {
+      const int row = idx >> 1, j = idx & 1;
+      const int wj = 2 * xb + j;
+      const bool ok = wj < a.dw;
+      cp_async4(sM + idx, ok ? a.mask + (a.row0 + base + row) * a.dw + wj : a.mask, ok ? 4 : 0);
+    }
+  };
+
+  // fixed operands: C rows of this dimension block (zero beyond d), mu
+  for (int idx = tid; idx < 64 * KPP; idx += 256) {
+    const int row = idx / KPP, col = idx % KPP;
+    const int gi = 64 * xb + row;
+    sC[row * LDZ + col] = (gi < a.d32 && col < a.kp) ? a.Cpad[(int64_t)gi * a.kp + col] : 0.0;
+  }
+  if (tid < 64) sMu[tid] = (64 * xb + tid < a.d32) ? a.mupad[64 * xb + tid] : 0.0;
+
+  // persistent accumulators
+  double accB[KT][2];
+#pragma unroll
+  for (int ni = 0; ni < KT; ++ni) accB[ni][0] = accB[ni][1] = 0.0;
+  double tdev[NI][2], tot[NI][2], dev2 = 0.0;
+#pragma unroll
+  for (int ni = 0; ni < NI; ++ni) tdev[ni][0] = tdev[ni][1] = tot[ni][0] = tot[ni][1] = 0.0;
+
+  const int mt0 = MI * (warp & 3), nt0 = NI * (warp >> 2);
+
+  int t = blockIdx.y;
+  if (t < ntiles) load_tile(0, t);
+  cp_async_commit();
+  int st = 0;
+  for (; t < ntiles; t += gridDim.y, st ^= 1) {
+    const int tn = t + gridDim.y;
+    if (tn < ntiles) load_tile(st ^ 1, tn);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    double *sX = stage0 + st * Cfg::STAGE;
+    const double *sZ = sX + BS * LDX;
+    const double *sWZ = sZ + BS * LDZ;
+    const double *sW = sWZ + BS * LDZ;
+    const uint32_t *sM = reinterpret_cast<const uint32_t *>(sW + BS);
+
+    // centre + select (utils.rs:118-127 fillna semantics: select, never multiply)
+#pragma unroll
+    for (int it = 0; it < BS * 64 / 256; ++it) {
+      const int idx = tid + 256 * it;
+      const int row = idx >> 6, col = idx & 63;
+      const uint32_t wbits = sM[row * 2 + (col >> 5)];
+      double *p = sX + row * LDX + col;
+      *p = ((wbits >> (col & 31)) & 1u) ? (*p - sMu[col]) : 0.0;
+    }
+    __syncthreads();
+
+    // phase A: accB[dims 8*warp.., k] += Xc^T (w z)
+    {
+      const double *pa = sX + c * LDX + 8 * warp + r;
+      const double *pb = sWZ + c * LDZ + r;
+#pragma unroll 4
+      for (int s = 0; s < BS / 4; ++s) {
+        const double av = pa[(4 * s) * LDX];
+#pragma unroll
+        for (int ni = 0; ni < KT; ++ni) dmma884(accB[ni][0], accB[ni][1], av, pb[(4 * s) * LDZ + 8 * ni]);
+      }
+    }
+
+    // phase B: R = Xc - Z C^T on this warp's (MI x NI) tiles
+    {
+      double acc[MI][NI][2];
+#pragma unroll
+      for (int mi = 0; mi < MI; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < NI; ++ni) {
+          const double2 xv =
+              *reinterpret_cast<const double2 *>(sX + (8 * (mt0 + mi) + r) * LDX + 8 * (nt0 + ni) + 2 * c);
+          acc[mi][ni][0] = -xv.x;
+          acc[mi][ni][1] = -xv.y;
+        }
+      const double *pa = sZ + (8 * mt0 + r) * LDZ + c;
+      const double *pb = sC + (8 * nt0 + r) * LDZ + c;
+#pragma unroll
+      for (int s = 0; s < 2 * KT; ++s) {
+        double av[MI], bv[NI];
+#pragma unroll
+        for (int mi = 0; mi < MI; ++mi) av[mi] = pa[(8 * mi) * LDZ + 4 * s];
+#pragma unroll
+        for (int ni = 0; ni < NI; ++ni) bv[ni] = pb[(8 * ni) * LDZ + 4 * s];
+#pragma unroll
+        for (int mi = 0; mi < MI; ++mi)
+#pragma unroll
+          for (int ni = 0; ni < NI; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], av[mi], bv[ni]);
+      }
+      // acc = Z C^T - Xc = -R on observed slots
+#pragma unroll
+      for (int mi = 0; mi < MI; ++mi) {
+        const int row = 8 * (mt0 + mi) + r;
+        const double wn = sW[row];
+#pragma unroll
+        for (int ni = 0; ni < NI; ++ni) {
+          const int col = 8 * (nt0 + ni) + 2 * c;
+          const uint32_t wbits = sM[row * 2 + (col >> 5)] >> (col & 31);
+          const double r0 = (wbits & 1u) ? -acc[mi][ni][0] : 0.0;
+          const double r1 = (wbits & 2u) ? -acc[mi][ni][1] : 0.0;
+          dev2 = fma(wn * r0, r0, dev2);
+          dev2 = fma(wn * r1, r1, dev2);
+          tdev[ni][0] = fma(wn, r0, tdev[ni][0]);
+          tdev[ni][1] = fma(wn, r1, tdev[ni][1]);
+          tot[ni][0] += (wbits & 1u) ? wn : 0.0;
+          tot[ni][1] += (wbits & 2u) ? wn : 0.0;
+        }
+      }
+    }
+    __syncthreads();  // all reads of this stage done before it is refilled two iterations later
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+
+  // ---- write this CTA's partials ----
+  const int64_t slab = blockIdx.y;
+  {
+    double *pB = a.pB + (slab * a.d64 + 64 * xb + 8 * warp + r) * a.kp;
+#pragma unroll
+    for (int ni = 0; ni < KT; ++ni) {
+      const int col = 8 * ni + 2 * c;
+      if (col < a.kp) *reinterpret_cast<double2 *>(pB + col) = make_double2(accB[ni][0], accB[ni][1]);
+    }
+  }
+  double *red = stage0;  // [2][4][64] scratch
+#pragma unroll
+  for (int ni = 0; ni < NI; ++ni)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      double v = tdev[ni][j], o = tot[ni][j];
+#pragma unroll
+      for (int sh = 4; sh < 32; sh <<= 1) {
+        v += __shfl_xor_sync(0xffffffffu, v, sh);
+        o += __shfl_xor_sync(0xffffffffu, o, sh);
+      }
+      if (r == 0) {
+        const int col = 8 * (nt0 + ni) + 2 * c + j;
+        red[(warp & 3) * 64 + col] = v;
+        red[256 + (warp & 3) * 64 + col] = o;
+      }
+    }
+  dev2 = warp_sum(dev2);
+  if (lane == 0) red[512 + warp] = dev2;
+  __syncthreads();
+  if (tid < 64) {
+    const double v = red[tid] + red[64 + tid] + red[128 + tid] + red[192 + tid];
+    const double o = red[256 + tid] + red[320 + tid] + red[384 + tid] + red[448 + tid];
+    a.pT[slab * a.d64 + 64 * xb + tid] = v;
+    a.pO[slab * a.d64 + 64 * xb + tid] = o;
+  }
+  if (tid == 0) {
+    double s = 0.0;
+    for (int i = 0; i < 8; ++i) s += red[512 + i];
+    a.pD[slab * gridDim.x + xb] = s;
+  }
+}
+
+// fixed-order reduction of the per-slab partials into the statistics buffer (accumulating across chunks)
+__global__ void cross_resid_reduce_kernel(int slabs, int dblocks, int d64, int d, int kp, const double *pB,
+                                          const double *pT, const double *pO, const double *pD, double *statB,
+                                          double *statTdev, double *statTotals, double *scalars) {
+  const int64_t totalB = (int64_t)d * kp;
+  const int64_t gtid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, gsz = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t idx = gtid; idx < totalB; idx += gsz) {
+    double s = 0.0;
+    for (int z = 0; z < slabs; ++z) s += pB[(int64_t)z * d64 * kp + idx];
+    statB[idx] += s;
+  }
+  for (int64_t idx = gtid; idx < d; idx += gsz) {
+    double s = 0.0, o = 0.0;
+    for (int z = 0; z < slabs; ++z) {
+      s += pT[(int64_t)z * d64 + idx];
+      o += pO[(int64_t)z * d64 + idx];
+    }
+    statTdev[idx] += s;
+    statTotals[idx] += o;
+  }
+  if (gtid == 0) {
+    double s = 0.0;
+    for (int z = 0; z < slabs * dblocks; ++z) s += pD[z];
+    scalars[SC_DEV2] += s;
+  }
+}
+
+static int cr_slabs(int d, int rows, int bs, int sms) {
+  const int dblocks = (d + 63) / 64;
+  const int ntiles = (rows + bs - 1) / bs;
+  int slabs = sms / dblocks;
+  if (slabs < 1) slabs = 1;
+  if (slabs > ntiles) slabs = ntiles;
+  return slabs < 1 ? 1 : slabs;
+}
+static int cr_bs(int kp) { return kp <= 32 ? 64 : 32; }
+
+size_t cross_resid_partials_len(int d, int k, int rows, int sms) {
+  Shape s(d, k);
+  const int dblocks = (d + 63) / 64, d64 = dblocks * 64;
+  const int slabs = cr_slabs(d, rows, cr_bs(s.kp), sms);
+  return (size_t)slabs * ((size_t)d64 * s.kp + 2 * (size_t)d64 + dblocks);
+}
+
+template <int KT, int BS>
+static void launch_cr(const Launcher &L, CrArgs a, int dblocks, int slabs) {
+  using Cfg = CrCfg<KT, BS>;
+  static bool configured = false;
+  if (!configured) {
+    CUDA_CHECK(cudaFuncSetAttribute(cross_resid_kernel<KT, BS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)Cfg::SMEM));
+    configured = true;
+  }
+  cross_resid_kernel<KT, BS><<<dim3(dblocks, slabs), 256, Cfg::SMEM, L.stream>>>(a);
+  CUDA_CHECK(cudaGetLastError());
+  ++*L.launch_counter;
+}
+
+void launch_cross_resid(const Launcher &L, const SampleStore &st, int64_t row0, int rows, const DevModel &m,
+                        const double *Z, const double *WZ, const double *w, double *statB, double *statTdev,
+                        double *statTotals, double *scalars, double *partials, size_t partials_len) {
+  if (rows <= 0) return;
+  const int d = m.s.d, kp = m.s.kp;
+  REQUIRE(kp <= 128, "state_size %d > 128 is not supported by the cross-moment kernel", m.s.k);
+  const int dblocks = (d + 63) / 64, d64 = dblocks * 64;
+  const int bs = cr_bs(kp);
+  const int slabs = cr_slabs(d, rows, bs, L.sms);
+  REQUIRE(partials_len >= (size_t)slabs * ((size_t)d64 * kp + 2 * (size_t)d64 + dblocks), "cross_resid workspace too small");
+  CrArgs a;
+  a.X = st.X.p; a.ldx = st.ldx; a.mask = st.mask.p; a.dw = st.dw; a.row0 = row0; a.rows = rows;
+  a.Cpad = m.C; a.kp = kp; a.d32 = m.s.d32; a.mupad = m.mu; a.Z = Z; a.WZ = WZ; a.w = w; a.d64 = d64;
+  a.pB = partials;
+  a.pT = a.pB + (size_t)slabs * d64 * kp;
+  a.pO = a.pT + (size_t)slabs * d64;
+  a.pD = a.pO + (size_t)slabs * d64;
+  const int kt = kp / 8;
+  if (kt <= 1) launch_cr<1, 64>(L, a, dblocks, slabs);
+  else if (kt <= 2) launch_cr<2, 64>(L, a, dblocks, slabs);
+  else if (kt <= 4) launch_cr<4, 64>(L, a, dblocks, slabs);
+  else if (kt <= 8) launch_cr<8, 32>(L, a, dblocks, slabs);
+  else launch_cr<16, 32>(L, a, dblocks, slabs);
+  const int64_t total = (int64_t)d * kp;
+  const int blocks = (int)((total + 255) / 256 < 2 * L.sms ? (total + 255) / 256 : 2 * L.sms);
+  cross_resid_reduce_kernel<<<blocks, 256, 0, L.stream>>>(slabs, dblocks, d64, d, kp, a.pB, a.pT, a.pO, a.pD, statB,
+                                                          statTdev, statTotals, scalars);
+  CUDA_CHECK(cudaGetLastError());
+  ++*L.launch_counter;
+}
+
+// ---------------------------------------------------------------------------------------------
+// reconstruction writer: 64 samples x 64 dims per CTA, K = k
+// ---------------------------------------------------------------------------------------------
+struct RecArgs {
+  const double *X;
+  int ldx;
+  const uint32_t *mask;
+  int dw;
+  int64_t row0;
+  int rows;
+  int d;
+  const double *Cpad;
+  int kp;
+  int d32;
+  const double *mupad;
+  const double *Z;
+  int extrapolate;
+  const double *scale;
+  int64_t scale_ld;
+  int accumulate;
+  double *out;
+  int64_t ldo;
+};
+
+template <int KT>
+__global__ void __launch_bounds__(256) reconstruct_kernel(RecArgs a) {
+  constexpr int KPP = 8 * KT;
+  constexpr int LDZ = KPP + ((20 - KPP % 16) % 16);
+  extern __shared__ __align__(16) double smem[];
+  double *sZ = smem;
+  double *sC = smem + 64 * LDZ;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int r = lane >> 2, c = lane & 3;
+  const int xb = blockIdx.x, base = blockIdx.y * 64;
+  for (int idx = tid; idx < 64 * KPP; idx += 256) {
+    const int row = idx / KPP, col = idx % KPP;
+    const int gi = 64 * xb + row;
+    sC[row * LDZ + col] = (gi < a.d32 && col < a.kp) ? a.Cpad[(int64_t)gi * a.kp + col] : 0.0;
+    sZ[row * LDZ + col] = (base + row < a.rows && col < a.kp) ? a.Z[(int64_t)(base + row) * a.kp + col] : 0.0;
+  }
+  __syncthreads();
+  const int mt0 = 2 * (warp & 3), nt0 = 4 * (warp >> 2);
+  double acc[2][4][2];
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+  const double *pa = sZ + (8 * mt0 + r) * LDZ + c;
+  const double *pb = sC + (8 * nt0 + r) * LDZ + c;
+#pragma unroll
+  for (int s = 0; s < 2 * KT; ++s) {
+    double av[2], bv[4];
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi) av[mi] = pa[(8 * mi) * LDZ + 4 * s];
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) bv[ni] = pb[(8 * ni) * LDZ + 4 * s];
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], av[mi], bv[ni]);
+  }
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi) {
+    const int row = base + 8 * (mt0 + mi) + r;
+    if (row >= a.rows) continue;
+    const int64_t grow = a.row0 + row;
+    const double sc = a.scale ? a.scale[(int64_t)row * a.scale_ld] : 1.0;
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int col = 64 * xb + 8 * (nt0 + ni) + 2 * c + j;
+        if (col >= a.d) continue;
+        double v = acc[mi][ni][j] + a.mupad[col];
+        if (a.extrapolate) {
+          const uint32_t wbits = a.mask[grow * a.dw + (col >> 5)];
+          if ((wbits >> (col & 31)) & 1u) v = a.X[grow * a.ldx + col];
+        }
+        if (a.scale) v *= sc;
+        double *o = a.out + (int64_t)row * a.ldo + col;
+        *o = a.accumulate ? (*o + v) : v;
+      }
+    }
+  }
+}
+
+template <int KT>
+static void launch_rec(const Launcher &L, const RecArgs &a, dim3 grid) {
+  constexpr int KPP = 8 * KT;
+  constexpr int LDZ = KPP + ((20 - KPP % 16) % 16);
+  constexpr size_t SMEM = 2 * 64 * LDZ * sizeof(double);
+  static bool configured = false;
+  if (!configured) {
+    CUDA_CHECK(cudaFuncSetAttribute(reconstruct_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+    configured = true;
+  }
+  reconstruct_kernel<KT><<<grid, 256, SMEM, L.stream>>>(a);
+}
+
+void launch_reconstruct(const Launcher &L, const SampleStore &st, int64_t row0, int rows, const DevModel &m,
+                        const double *Z, int extrapolate, const double *scale, int64_t scale_ld, int accumulate,
+                        double *outX, int64_t ldo) {
+  if (rows <= 0) return;
+  REQUIRE(m.s.kp <= 128, "state_size %d > 128 is not supported by the reconstruction kernel", m.s.k);
+  RecArgs a;
+  a.X = st.X.p; a.ldx = st.ldx; a.mask = st.mask.p; a.dw = st.dw; a.row0 = row0; a.rows = rows; a.d = m.s.d;
+  a.Cpad = m.C; a.kp = m.s.kp; a.d32 = m.s.d32; a.mupad = m.mu; a.Z = Z; a.extrapolate = extrapolate;
+  a.scale = scale; a.scale_ld = scale_ld; a.accumulate = accumulate; a.out = outX; a.ldo = ldo;
+  dim3 grid((m.s.d + 63) / 64, (rows + 63) / 64);
+  const int kt = m.s.kp / 8;
+  if (kt <= 1) launch_rec<1>(L, a, grid);
+  else if (kt <= 2) launch_rec<2>(L, a, grid);
+  else if (kt <= 4) launch_rec<4>(L, a, grid);
+  else if (kt <= 8) launch_rec<8>(L, a, grid);
+  else launch_rec<16>(L, a, grid);
+  CUDA_CHECK(cudaGetLastError());
+  ++*L.launch_counter;
+}
+
+}  // namespace ppca

@@ -1,0 +1,235 @@
+// solve.cu — per-sample k x k posterior algebra, one warp per sample.
+//
+// Input per sample: G_n = C_o^T C_o (packed upper, from the masked-Gram contraction), y_n = C_o^T x~_n,
+// nx_n = |x~_n|^2, d_n = #observed.  With M_n = sigma^2 I + G_n = L L^T (output_covariance.rs:61-64):
+//   z_n     = M_n^{-1} y_n            == estimator_transform * x~   (output_covariance.rs:90-94, ppca_model.rs:205)
+//   Sigma_n = sigma^2 M_n^{-1}        == I - T C_o                  (output_covariance.rs:98-101, ppca_model.rs:206)
+//   llk_n   = -(nx - y^T M^{-1} y)/(2 sigma^2) - (ln det M + 2 ln sigma (d_n - k))/2 - ln(2 pi) d_n / 2
+//                                                                   (ppca_model.rs:131-138, output_covariance.rs:115-142)
+//   W_n     = w_n (z z^T + Sigma_n)   second moment                 (ppca_model.rs:303, :437-439)
+//   t_n     = tr(Sigma_n G_n)         == (C_o Sigma_n).dot(C_o)     (ppca_model.rs:345)
+// The reference uses an LU inverse and ln(det) by LU; M_n is SPD so the Cholesky route agrees to rounding
+// and cannot overflow the determinant.  Empty samples: z = 0, Sigma = I, llk = 0 (ppca_model.rs:98-104,125-129).
+//
+// This is the generic (any k) shared-memory kernel: the (k+1) x k augmented matrix [M ; y^T] lives in shared
+// memory, one per warp; L^{-1} is built in the unused strict upper triangle.
+#include "common.cuh"
+#include "mma.cuh"
+
+namespace ppca {
+
+#define LN_2PI 1.8378770664093453
+
+struct SolveSmem {
+  int ldk;      // odd pitch
+  int per_warp; // doubles per warp
+  __host__ __device__ SolveSmem(int k) {
+    ldk = (k | 1);
+    per_warp = (k + 1) * ldk + 2 * (k > 0 ? k : 1);
+    per_warp = (per_warp + 1) & ~1;
+  }
+};
+
+__global__ void __launch_bounds__(256) solve_kernel(SolveArgs a) {
+  extern __shared__ double smem_solve[];
+  const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5, warps = blockDim.x >> 5;
+  const int k = a.s.k, kk = a.s.kk, kkp = a.s.kkp, kp = a.s.kp;
+  const SolveSmem lay(k);
+  const int ldk = lay.ldk;
+  double *M = smem_solve + (size_t)wi * lay.per_warp;  // (k+1) x ldk ; row k = y^T
+  double *dinv = M + (k + 1) * ldk;                    // 1 / L_pp
+  double *zv = dinv + k;
+  const double s2 = a.sigma * a.sigma;
+  const double ln_sigma = log(a.sigma);
+
+  for (int row = blockIdx.x * warps + wi; row < a.rows_pad; row += gridDim.x * warps) {
+    double *G = a.GW ? a.GW + (int64_t)row * kkp : nullptr;
+    double *y = a.YZ + (int64_t)row * kp;
+    const int dn = row < a.rows ? a.dn[row] : 0;
+    if (dn == 0) {  // padding row or empty sample
+      if (a.mode == 2) {
+        for (int q = lane; q < kkp; q += 32) G[q] = 0.0;
+        if (a.WZ)
+          for (int q = lane; q < kp; q += 32) a.WZ[(int64_t)row * kp + q] = 0.0;
+      }
+      for (int q = lane; q < kp; q += 32) y[q] = 0.0;
+      if (row < a.rows) {
+        if (a.llk && lane == 0) a.llk[row] = 0.0;
+        if (a.tn && lane == 0) a.tn[row] = 0.0;
+        if (a.cov)
+          for (int q = lane; q < k * k; q += 32) a.cov[(int64_t)row * k * k + q] = (q / k == q % k) ? 1.0 : 0.0;
+      }
+      continue;
+    }
+    const double w = a.w ? a.w[row] : 1.0;
+
+    // 1. unpack [M ; y]
+    for (int p = 0; p < k; ++p) {
+      const int off = tri_row_off(p, k) - p;
+      for (int b = p + lane; b < k; b += 32) M[b * ldk + p] = G[off + b] + (b == p ? s2 : 0.0);
+    }
+    for (int q = lane; q < k; q += 32) M[k * ldk + q] = y[q];
+    __syncwarp();
+
+    // 2. Cholesky of the augmented matrix: rows 0..k-1 -> L, row k -> u = L^{-1} y
+    double logdet = 0.0;
+    for (int p = 0; p < k; ++p) {
+      const double dpp = M[p * ldk + p];
+      const double inv = rsqrt(dpp);
+      logdet += log(dpp);
+      __syncwarp();
+      for (int rr = p + 1 + lane; rr <= k; rr += 32) M[rr * ldk + p] *= inv;
+      if (lane == 0) dinv[p] = inv;
+      __syncwarp();
+      for (int cc = p + 1; cc < k; ++cc) {
+        const double lcp = M[cc * ldk + p];
+        for (int rr = cc + lane; rr <= k; rr += 32) M[rr * ldk + cc] = fma(-M[rr * ldk + p], lcp, M[rr * ldk + cc]);
+      }
+      __syncwarp();
+    }
+    double quad = 0.0;  // y^T M^{-1} y = |u|^2
+    for (int q = lane; q < k; q += 32) {
+      const double u = M[k * ldk + q];
+      quad = fma(u, u, quad);
+    }
+    quad = warp_sum(quad);
+    if (a.llk) {
+      const double llk = -0.5 * (a.nx[row] - quad) / s2 - 0.5 * (logdet + 2.0 * ln_sigma * (double)(dn - k)) -
+                         0.5 * LN_2PI * (double)dn;
+      if (lane == 0) a.llk[row] = llk;
+    }
+    if (a.mode == 0) {
+      __syncwarp();
+      continue;
+    }
+
+    // 3. X = L^{-1} into the strict upper triangle: X[r][j] (r > j) at M[j][r]; X[j][j] = dinv[j]
+    for (int j = lane; j < ((k + 31) & ~31); j += 32) {
+      const bool live = j < k;
+      const double xjj = live ? dinv[j] : 0.0;
+      for (int rr = 1; rr < k; ++rr) {
+        double s = 0.0;
+        for (int cc = 0; cc < rr; ++cc) {
+          const double lrc = M[rr * ldk + cc];
+          double x = 0.0;
+          if (live && cc >= j) x = (cc == j) ? xjj : M[j * ldk + cc];
+          s = fma(lrc, x, s);
+        }
+        if (live && rr > j) M[j * ldk + rr] = -s * dinv[rr];
+      }
+    }
+    __syncwarp();
+
+    // 4. z = X^T u
+    for (int q = lane; q < k; q += 32) {
+      double s = dinv[q] * M[k * ldk + q];
+      for (int rr = q + 1; rr < k; ++rr) s = fma(M[q * ldk + rr], M[k * ldk + rr], s);
+      zv[q] = s;
+    }
+    __syncwarp();
+    for (int q = lane; q < kp; q += 32) {
+      const double z = q < k ? zv[q] : 0.0;
+      y[q] = z;
+      if (a.WZ) a.WZ[(int64_t)row * kp + q] = w * z;
+    }
+
+    // 5. M^{-1} = X^T X (packed), W, t, optional full covariance
+    if (a.mode == 2 || a.cov) {
+      double tpart = 0.0;
+      for (int p = 0; p < k; ++p) {
+        const int off = tri_row_off(p, k) - p;
+        const double zp = zv[p];
+        for (int b0 = p; b0 < k; b0 += 32) {
+          const int b = b0 + lane;
+          const bool live = b < k;
+          double s = 0.0;
+          if (live) s = (b == p) ? dinv[p] * dinv[p] : M[p * ldk + b] * dinv[b];
+          for (int rr = b0 + 1; rr < k; ++rr) {
+            const double xp = M[p * ldk + rr];
+            if (live && rr > b) s = fma(xp, M[b * ldk + rr], s);
+          }
+          if (live) {
+            if (a.mode == 2) {
+              const double g = G[off + b];
+              tpart = fma((b == p ? 1.0 : 2.0) * s, g, tpart);
+              G[off + b] = w * fma(zp, zv[b], s2 * s);
+            }
+            if (a.cov) {
+              a.cov[(int64_t)row * k * k + p * k + b] = s2 * s;
+              a.cov[(int64_t)row * k * k + b * k + p] = s2 * s;
+            }
+          }
+        }
+      }
+      if (a.mode == 2) {
+        for (int q = kk + lane; q < kkp; q += 32) G[q] = 0.0;
+        tpart = warp_sum(tpart);
+        if (a.tn && lane == 0) a.tn[row] = s2 * tpart;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// fixed-order reduction of the per-sample scalars of one chunk into the statistics scalars
+__global__ void __launch_bounds__(1024) solve_reduce_kernel(int rows, const double *__restrict__ llk,
+                                                            const double *__restrict__ tn, const int *__restrict__ dn,
+                                                            const double *__restrict__ w, double *scalars) {
+  __shared__ double sh[4][32];
+  double v[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int i = threadIdx.x; i < rows; i += 1024) {
+    const double wi = w ? w[i] : 1.0;
+    if (tn) v[0] = fma(wi, tn[i], v[0]);
+    if (llk) v[1] = fma(wi, llk[i], v[1]);
+    v[2] += wi;
+    v[3] += dn[i] > 0 ? 1.0 : 0.0;
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    v[j] = warp_sum(v[j]);
+    if (lane == 0) sh[j][wid] = v[j];
+  }
+  __syncthreads();
+  if (wid == 0) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      double s = warp_sum(sh[j][lane]);
+      if (lane == 0) {
+        const int slot = j == 0 ? SC_SQERR : j == 1 ? SC_LLK : j == 2 ? SC_SUMW : SC_NONEMPTY;
+        scalars[slot] += s;
+      }
+    }
+  }
+}
+
+void launch_solve(const Launcher &L, const SolveArgs &a) {
+  if (a.rows_pad <= 0) return;
+  const SolveSmem lay(a.s.k);
+  const size_t per_warp = (size_t)lay.per_warp * sizeof(double);
+  int warps = 8;
+  while (warps > 1 && per_warp * warps > 200 * 1024) warps >>= 1;
+  REQUIRE(per_warp * warps <= 227 * 1024, "state_size %d too large for the per-sample solve kernel", a.s.k);
+  const size_t smem = per_warp * warps;
+  static bool configured = false;
+  if (!configured) {
+    CUDA_CHECK(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
+  }
+  int ctas_per_sm = (int)((220 * 1024) / (smem + 1024));
+  if (ctas_per_sm < 1) ctas_per_sm = 1;
+  if (ctas_per_sm * warps > 48) ctas_per_sm = 48 / warps > 0 ? 48 / warps : 1;
+  int64_t blocks = (a.rows_pad + warps - 1) / warps;
+  const int64_t cap = (int64_t)L.sms * ctas_per_sm;
+  if (blocks > cap) blocks = cap;
+  solve_kernel<<<(unsigned)blocks, warps * 32, smem, L.stream>>>(a);
+  CUDA_CHECK(cudaGetLastError());
+  ++*L.launch_counter;
+  if (a.scalars) {
+    solve_reduce_kernel<<<1, 1024, 0, L.stream>>>(a.rows, a.llk, a.tn, a.dn, a.w, a.scalars);
+    CUDA_CHECK(cudaGetLastError());
+    ++*L.launch_counter;
+  }
+}
+
+}  // namespace ppca

@@ -1,0 +1,804 @@
+"""Host-side mirror of the reference's Python extension module (`ppca_rs.ppca_rs`, src/python_bindings.rs).
+
+Same class names, method names, argument meaning and error behaviour; the data-parallel work (E-step,
+M-step statistics, log-likelihoods, reconstruction) runs in the CUDA engine through the C ABI
+(include/ppca_b200.h).  Model parameters live on the host as numpy arrays (d k + d + 1 doubles), the
+dataset lives on the device behind an opaque handle — exactly the split the reference has between Python
+and its Rust side (Dataset is an opaque wrapper there too, src/python_bindings.rs:28-30).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Iterator, List, Optional, Sequence
+
+import numpy as np
+
+from . import _native as nat
+from . import bincode
+
+
+def _as_vector(x, what: str) -> np.ndarray:
+    """src/utils.rs:10-23 to_nalgebra_vector: accepts 1 x n or n x 1 (1-D accepted as a convenience)."""
+    a = np.asarray(x, dtype=np.float64)
+    if a.ndim == 1:
+        return np.ascontiguousarray(a)
+    if a.ndim == 2 and (a.shape[0] == 1 or a.shape[1] == 1):
+        return np.ascontiguousarray(a.reshape(-1))
+    raise ValueError(f"Expected column- or row- vector for {what}; got {'x'.join(map(str, a.shape))} matrix")
+
+
+def _as_matrix(x, what: str) -> np.ndarray:
+    a = np.asarray(x, dtype=np.float64)
+    if a.ndim != 2:
+        raise TypeError(f"{what} must be a 2-D float64 array")
+    return np.ascontiguousarray(a)
+
+
+# =================================================================================================
+# Dataset  (src/python_bindings.rs:28-166 ; ppca/src/dataset.rs)
+# =================================================================================================
+class Dataset:
+    """A dataset of samples with potentially missing values, resident on the GPU.
+
+    `Dataset(ndarray, weights=None)`: `ndarray` is (n_samples, n_features) float64; every non-finite entry
+    (NaN, +-inf) is a missing value (dataset.rs:19-22).
+    """
+
+    def __init__(self, ndarray, weights=None, *, _handle=None, _ctx=None):
+        self._ctx = _ctx or nat.get_context()
+        if _handle is not None:
+            self._h = _handle
+            return
+        x = _as_matrix(ndarray, "ndarray")
+        n, d = x.shape
+        w = None
+        if weights is not None:
+            w = nat.f64(np.asarray(weights, dtype=np.float64).reshape(-1))
+            if w.shape[0] != n:  # dataset.rs:163 assert_eq!(data.len(), weights.len())
+                raise ValueError(f"weights has {w.shape[0]} entries for {n} samples")
+        if d < 1:
+            raise ValueError("dataset needs at least one output dimension")
+        h = nat.c_ds_p()
+        nat.check(nat.lib().ppca_b200_dataset_from_host(self._ctx.handle, nat.dptr(x), n, d, nat.dptr(w), C.byref(h)))
+        self._h = h
+
+    # -- construction helpers --------------------------------------------------------------------
+    @classmethod
+    def _wrap(cls, handle, ctx) -> "Dataset":
+        return cls(None, _handle=handle, _ctx=ctx)
+
+    @classmethod
+    def synthetic(cls, n: int, d: int, k_true: int, sigma_true: float = 0.1, mask_prob: float = 0.2,
+                  n_components: int = 1, seed: int = 20240531, ctx: Optional[nat.Context] = None) -> "Dataset":
+        """Device-generated data with the reference sampler's semantics (ppca_model.rs:164-191)."""
+        ctx = ctx or nat.get_context()
+        h = nat.c_ds_p()
+        nat.check(nat.lib().ppca_b200_dataset_synthetic(ctx.handle, int(n), int(d), int(k_true), float(sigma_true),
+                                                        float(mask_prob), int(n_components), int(seed), C.byref(h)))
+        return cls._wrap(h, ctx)
+
+    def __del__(self):  # pragma: no cover
+        try:
+            if getattr(self, "_h", None):
+                nat.lib().ppca_b200_dataset_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    # -- reference API ---------------------------------------------------------------------------
+    @staticmethod
+    def load(data: bytes) -> "Dataset":
+        try:
+            x, w = bincode.load_dataset(bytes(data))
+        except ValueError as e:
+            raise Exception(str(e))
+        if x.shape[0] == 0:
+            raise Exception("cannot load an empty dataset (output size unknown)")
+        return Dataset(x, w)
+
+    def dump(self) -> bytes:
+        return bincode.dump_dataset(self.numpy(), self.weights())
+
+    def numpy(self) -> np.ndarray:
+        n, d = len(self), self._output_size()
+        out = np.empty((n, d), dtype=np.float64)
+        nat.check(nat.lib().ppca_b200_dataset_to_host(self._ctx.handle, self._h, 0, n, nat.dptr(out)))
+        return out
+
+    def __len__(self) -> int:
+        out = C.c_int64(0)
+        nat.check(nat.lib().ppca_b200_dataset_len(self._h, C.byref(out)))
+        return out.value
+
+    def _output_size(self) -> int:
+        out = C.c_int32(0)
+        nat.check(nat.lib().ppca_b200_dataset_output_size(self._h, C.byref(out)))
+        return out.value
+
+    def output_size(self) -> Optional[int]:
+        """dataset.rs:189-191: None for an empty dataset."""
+        return self._output_size() if len(self) > 0 else None
+
+    def empty_dimensions(self) -> List[int]:
+        d = self._output_size()
+        out = np.zeros(d, dtype=np.uint8)
+        nat.check(nat.lib().ppca_b200_dataset_empty_dimensions(self._ctx.handle, self._h,
+                                                               out.ctypes.data_as(C.POINTER(C.c_uint8))))
+        return [int(i) for i in np.nonzero(out)[0]]
+
+    def weights(self) -> np.ndarray:
+        out = np.empty(len(self), dtype=np.float64)
+        nat.check(nat.lib().ppca_b200_dataset_weights(self._ctx.handle, self._h, nat.dptr(out)))
+        return out
+
+    def with_weights(self, weights) -> "Dataset":
+        """dataset.rs:171-176: same samples (shared on the device), new weights."""
+        w = nat.f64(np.asarray(weights, dtype=np.float64).reshape(-1))
+        if w.shape[0] != len(self):
+            raise ValueError("weights length does not match dataset length")
+        h = nat.c_ds_p()
+        nat.check(nat.lib().ppca_b200_dataset_with_weights(self._ctx.handle, self._h, nat.dptr(w), C.byref(h)))
+        return Dataset._wrap(h, self._ctx)
+
+    def _slice(self, row0: int, nrows: int) -> "Dataset":
+        h = nat.c_ds_p()
+        nat.check(nat.lib().ppca_b200_dataset_slice(self._ctx.handle, self._h, int(row0), int(nrows), C.byref(h)))
+        return Dataset._wrap(h, self._ctx)
+
+    def chunks(self, chunks: int) -> "DatasetChunks":
+        return DatasetChunks(self, chunks)
+
+    @staticmethod
+    def concat(list: Sequence["Dataset"]) -> "Dataset":
+        items = [d for d in list]
+        if not items:
+            raise ValueError("cannot concatenate an empty list of datasets (output size unknown)")
+        ctx = items[0]._ctx
+        arr = (nat.c_ds_p * len(items))(*[d._h for d in items])
+        h = nat.c_ds_p()
+        nat.check(nat.lib().ppca_b200_dataset_concat(ctx.handle, arr, len(items), C.byref(h)))
+        return Dataset._wrap(h, ctx)
+
+    # pickling (the reference pickles through dump/load)
+    def __getstate__(self):
+        return self.dump()
+
+    def __setstate__(self, state):
+        other = Dataset.load(state)
+        self._ctx = other._ctx
+        self._h = other._h
+        other._h = None
+
+    def __reduce__(self):
+        return (_load_dataset, (self.dump(),))
+
+
+def _load_dataset(data: bytes) -> Dataset:
+    return Dataset.load(data)
+
+
+class DatasetChunks:
+    """src/python_bindings.rs:136-166: stride = ceil(len / chunks), yields copies in order."""
+
+    def __init__(self, dataset: Dataset, chunks: int):
+        self.length = len(dataset)
+        self.stride = int(math.ceil(self.length / float(chunks))) if chunks > 0 else 0
+        self.position = 0
+        self.dataset = dataset
+
+    def __iter__(self) -> Iterator[Dataset]:
+        return self
+
+    def __next__(self) -> Dataset:
+        if self.position < self.length and self.stride > 0:
+            end = min(self.length, self.position + self.stride)
+            out = self.dataset._slice(self.position, end - self.position)
+            self.position += self.stride
+            return out
+        raise StopIteration
+
+
+# =================================================================================================
+# Prior  (src/python_bindings.rs:168-201 ; ppca/src/prior.rs)
+# =================================================================================================
+class Prior:
+    """A prior for the PPCA model (mean N(mu0, S0), inverse-gamma noise, ridge on the transform rows)."""
+
+    def __init__(self):
+        self.mean: Optional[np.ndarray] = None
+        self.mean_covariance: Optional[np.ndarray] = None
+        self.mean_precision: Optional[np.ndarray] = None
+        self.isotropic_noise_alpha: Optional[float] = None
+        self.isotropic_noise_beta: Optional[float] = None
+        self.transformation_precision: float = 0.0
+
+    def _clone(self) -> "Prior":
+        p = Prior()
+        p.__dict__.update(self.__dict__)
+        return p
+
+    def with_mean_prior(self, mean, mean_covariance) -> "Prior":
+        m = _as_vector(mean, "mean")
+        cov = _as_matrix(mean_covariance, "mean_covariance")
+        if cov.shape != (m.shape[0], m.shape[0]):  # prior.rs:33-34
+            raise ValueError("mean covariance shape does not match mean length")
+        try:
+            prec = np.linalg.inv(cov)  # prior.rs:36-41 try_inverse().expect(...)
+        except np.linalg.LinAlgError:
+            raise ValueError("mean covariance should be invertible")
+        p = self._clone()
+        p.mean, p.mean_covariance, p.mean_precision = m, cov, np.ascontiguousarray(prec)
+        return p
+
+    def with_isotropic_noise_prior(self, alpha: float, beta: float) -> "Prior":
+        if not (alpha >= 0.0 and beta >= 0.0):  # prior.rs:50-51
+            raise ValueError("alpha and beta must be non-negative")
+        p = self._clone()
+        p.isotropic_noise_alpha, p.isotropic_noise_beta = float(alpha), float(beta)
+        return p
+
+    def with_transformation_precision(self, precision: float) -> "Prior":
+        if not precision >= 0.0:  # prior.rs:61
+            raise ValueError("precision must be non-negative")
+        p = self._clone()
+        p.transformation_precision = float(precision)
+        return p
+
+    def _c(self, d: int):
+        """Returns (CPrior, keepalive)."""
+        pr = nat.CPrior()
+        keep = []
+        pr.has_mean_prior = 0
+        if self.mean is not None:
+            if self.mean.shape[0] != d:
+                raise ValueError("mean prior length does not match the model output size")
+            keep = [self.mean, self.mean_precision]
+            pr.has_mean_prior = 1
+            pr.mean = nat.dptr(self.mean)
+            pr.mean_precision = nat.dptr(self.mean_precision)
+        pr.has_isotropic_noise_prior = int(self.isotropic_noise_alpha is not None)
+        pr.isotropic_noise_alpha = float(self.isotropic_noise_alpha or 0.0)
+        pr.isotropic_noise_beta = float(self.isotropic_noise_beta or 0.0)
+        pr.transformation_precision = float(self.transformation_precision)
+        return pr, keep
+
+
+# =================================================================================================
+# PPCAModel  (src/python_bindings.rs:367-533 ; ppca/src/ppca_model.rs)
+# =================================================================================================
+class PPCAModel:
+    """x ~ N(0, I_k);  y = C x + mu + noise;  noise ~ N(0, sigma^2 I_d)   (ppca_model.rs:24-38)."""
+
+    def __init__(self, isotropic_noise: float, transform, mean):
+        self._sigma = float(isotropic_noise)
+        self._C = _as_matrix(transform, "transform")
+        self._mu = _as_vector(mean, "mean")
+        if self._mu.shape[0] != self._C.shape[0]:
+            raise ValueError("mean length does not match the number of rows of transform")
+
+    # -- getters ---------------------------------------------------------------------------------
+    @property
+    def output_size(self) -> int:
+        return int(self._C.shape[0])
+
+    @property
+    def state_size(self) -> int:
+        return int(self._C.shape[1])
+
+    @property
+    def n_parameters(self) -> int:
+        return 1 + self.state_size * self.output_size + self._mu.shape[0]  # ppca_model.rs:107-109
+
+    @property
+    def singular_values(self) -> np.ndarray:
+        return np.sqrt(np.linalg.norm(self._C, axis=0))  # ppca_model.rs:113-121: sqrt of the column NORM
+
+    @property
+    def transform(self) -> np.ndarray:
+        return self._C.copy()
+
+    @property
+    def isotropic_noise(self) -> float:
+        return self._sigma
+
+    @property
+    def mean(self) -> np.ndarray:
+        return self._mu.copy()
+
+    # -- construction ----------------------------------------------------------------------------
+    @staticmethod
+    def init(state_size: int, dataset: Dataset, seed: Optional[int] = None) -> "PPCAModel":
+        """ppca_model.rs:51-70: sigma = 1, mu = 0, C ~ N(0, 1) with the rows of empty dimensions zeroed."""
+        if len(dataset) == 0:
+            raise ValueError("dataset must not be empty")
+        d = dataset.output_size()
+        rng = np.random.default_rng(seed)
+        C0 = rng.standard_normal((d, int(state_size)))
+        for i in dataset.empty_dimensions():
+            C0[i, :] = 0.0
+        return PPCAModel(1.0, C0, np.zeros(d))
+
+    @staticmethod
+    def load(data: bytes) -> "PPCAModel":
+        try:
+            sigma, transform, mean = bincode.load_model(bytes(data))
+        except ValueError as e:
+            raise Exception(str(e))
+        return PPCAModel(sigma, transform, mean)
+
+    def dump(self) -> bytes:
+        return bincode.dump_model(self._sigma, self._C, self._mu)
+
+    def __repr__(self) -> str:
+        return (f"PPCAModel(isotropic_noise={self._sigma}, transform=array({self._C}, dtype=\"float32\"), "
+                f"mean=narray({self._mu}, dtype=\"float32\"))")
+
+    # -- hot path --------------------------------------------------------------------------------
+    def _check(self, dataset: Dataset) -> None:
+        if len(dataset) > 0 and dataset._output_size() != self.output_size:  # output_covariance.rs:124
+            raise ValueError(f"dataset output size {dataset._output_size()} != model output size {self.output_size}")
+        if self.state_size < 1:
+            raise ValueError("state_size 0 is not supported by the B200 engine")
+
+    def llk(self, dataset: Dataset) -> float:
+        self._check(dataset)
+        out = C.c_double(0.0)
+        nat.check(nat.lib().ppca_b200_llk(dataset._ctx.handle, dataset._h, self.state_size, nat.dptr(self._C),
+                                          nat.dptr(self._mu), self._sigma, C.byref(out)))
+        return out.value
+
+    def llks(self, dataset: Dataset) -> np.ndarray:
+        self._check(dataset)
+        out = np.empty(len(dataset))
+        nat.check(nat.lib().ppca_b200_llks(dataset._ctx.handle, dataset._h, self.state_size, nat.dptr(self._C),
+                                           nat.dptr(self._mu), self._sigma, nat.dptr(out)))
+        return out
+
+    def sample(self, dataset_size: int, mask_prob: float) -> Dataset:
+        """ppca_model.rs:164-191 (unseeded, like the reference)."""
+        if not 0.0 <= mask_prob <= 1.0:
+            raise ValueError("invalid mask probability")
+        rng = np.random.default_rng()
+        n, d, k = int(dataset_size), self.output_size, self.state_size
+        x = rng.standard_normal((n, k)) @ self._C.T + self._mu + self._sigma * rng.standard_normal((n, d))
+        x[rng.random((n, d)) < mask_prob] = np.nan
+        return Dataset(x)
+
+    def infer(self, dataset: Dataset) -> "InferredMasked":
+        self._check(dataset)
+        n, k = len(dataset), self.state_size
+        states = np.empty((n, k))
+        covs = np.empty((n, k, k))
+        nat.check(nat.lib().ppca_b200_infer(dataset._ctx.handle, dataset._h, k, nat.dptr(self._C), nat.dptr(self._mu),
+                                            self._sigma, nat.dptr(states), nat.dptr(covs)))
+        return InferredMasked(states, covs)
+
+    def _recon(self, dataset: Dataset, fn) -> Dataset:
+        self._check(dataset)
+        h = nat.c_ds_p()
+        nat.check(fn(dataset._ctx.handle, dataset._h, self.state_size, nat.dptr(self._C), nat.dptr(self._mu),
+                     self._sigma, C.byref(h)))
+        return Dataset._wrap(h, dataset._ctx)
+
+    def smooth(self, dataset: Dataset) -> Dataset:
+        return self._recon(dataset, nat.lib().ppca_b200_smooth)
+
+    # readme.md:62 calls `smooth` filter_extrapolate
+    filter_extrapolate = smooth
+
+    def extrapolate(self, dataset: Dataset) -> Dataset:
+        return self._recon(dataset, nat.lib().ppca_b200_extrapolate)
+
+    def _iterate(self, dataset: Dataset, prior: Optional[Prior]):
+        """Returns (new model, llk of THIS model on dataset) — the E-step yields the latter for free."""
+        self._check(dataset)
+        d, k = self.output_size, self.state_size
+        C_out = np.empty((d, k))
+        mu_out = np.empty(d)
+        s_out = C.c_double(0.0)
+        llk = C.c_double(0.0)
+        pr_ref, keep = None, None
+        if prior is not None:
+            pr, keep = prior._c(d)
+            pr_ref = C.byref(pr)
+        nat.check(nat.lib().ppca_b200_iterate(dataset._ctx.handle, dataset._h, k, nat.dptr(self._C), nat.dptr(self._mu),
+                                              self._sigma, pr_ref, nat.dptr(C_out), nat.dptr(mu_out), C.byref(s_out),
+                                              C.byref(llk)))
+        return PPCAModel(s_out.value, C_out, mu_out), llk.value
+
+    def iterate_with_prior(self, dataset: Dataset, prior: Prior) -> "PPCAModel":
+        return self._iterate(dataset, prior)[0]
+
+    def iterate(self, dataset: Dataset) -> "PPCAModel":
+        return self._iterate(dataset, None)[0]
+
+    def to_canonical(self) -> "PPCAModel":
+        """ppca_model.rs:398-425: C <- U S (singular values descending), columns times signum(sum(column))."""
+        if self.state_size == 0:
+            return PPCAModel(self._sigma, self._C, self._mu)
+        u, s, _ = np.linalg.svd(self._C, full_matrices=False)
+        new_c = u * s
+        sums = new_c.sum(axis=0)
+        sign = np.where(np.signbit(sums), -1.0, 1.0)  # f64::signum: signum(+0.0) = 1, signum(-0.0) = -1
+        sign = np.where(np.isnan(sums), np.nan, sign)
+        return PPCAModel(self._sigma, new_c * sign, self._mu)
+
+    # -- pickling (src/python_bindings.rs:513-532) -------------------------------------------------
+    def __getstate__(self):
+        return self.dump()
+
+    def __setstate__(self, state):
+        self._sigma, self._C, self._mu = bincode.load_model(bytes(state))
+
+    def __getnewargs__(self):
+        return (self._sigma, self._C.copy(), self._mu.copy())
+
+
+# =================================================================================================
+# InferredMasked  (src/python_bindings.rs:203-365 ; ppca_model.rs:428-626)
+# Per-sample convenience algebra on the inferred posteriors.  Host numpy: SURVEY.md §8(f) rank 1 ("next").
+# =================================================================================================
+class InferredMasked:
+    def __init__(self, states: np.ndarray, covariances: np.ndarray):
+        self._states = states
+        self._covs = covariances
+
+    def __len__(self) -> int:
+        return self._states.shape[0]
+
+    def states(self) -> np.ndarray:
+        if len(self) == 0:
+            return np.zeros((0, 0))
+        return self._states.copy()
+
+    def covariances(self) -> List[np.ndarray]:
+        return [c.copy() for c in self._covs]
+
+    def smoothed(self, ppca: PPCAModel) -> Dataset:
+        return Dataset(self._states @ ppca._C.T + ppca._mu)  # ppca_model.rs:454-456
+
+    def extrapolated(self, ppca: PPCAModel, dataset: Dataset) -> Dataset:
+        x = dataset.numpy()
+        sm = self._states @ ppca._C.T + ppca._mu
+        return Dataset(np.where(np.isfinite(x), x, sm))  # ppca_model.rs:460-463
+
+    def smoothed_covariances(self, ppca: PPCAModel) -> List[np.ndarray]:
+        d = ppca.output_size
+        eye = np.eye(d) * ppca._sigma ** 2
+        return [eye + ppca._C @ c @ ppca._C.T for c in self._covs]  # ppca_model.rs:471-477
+
+    def _smoothed_cov_diag(self, ppca: PPCAModel) -> np.ndarray:
+        tc = np.einsum("ia,nab->nib", ppca._C, self._covs)
+        return np.einsum("nib,ib->ni", tc, ppca._C) + ppca._sigma ** 2  # ppca_model.rs:485-508
+
+    def smoothed_covariances_diagonal(self, ppca: PPCAModel) -> Dataset:
+        return Dataset(self._smoothed_cov_diag(ppca))
+
+    def extrapolated_covariances(self, ppca: PPCAModel, dataset: Dataset) -> List[np.ndarray]:
+        x = dataset.numpy()
+        out = []
+        full = self.smoothed_covariances(ppca)
+        for i in range(len(self)):
+            neg = ~np.isfinite(x[i])  # ppca_model.rs:517-534
+            m = np.zeros_like(full[i])
+            if neg.any():
+                m[np.ix_(neg, neg)] = full[i][np.ix_(neg, neg)]
+            out.append(m)
+        return out
+
+    def extrapolated_covariances_diagonal(self, ppca: PPCAModel, dataset: Dataset) -> Dataset:
+        x = dataset.numpy()
+        diag = self._smoothed_cov_diag(ppca)
+        return Dataset(np.where(np.isfinite(x), 0.0, diag))  # ppca_model.rs:542-577
+
+    def posterior_sampler(self) -> "PosteriorSampler":
+        return PosteriorSampler(self._states, np.linalg.cholesky(self._covs))  # ppca_model.rs:581-592
+
+
+class PosteriorSampler:
+    """ppca_model.rs:595-626; needs the model to map states to outputs, as in the reference struct."""
+
+    def __init__(self, states: np.ndarray, chol: np.ndarray, model: Optional[PPCAModel] = None):
+        self._states, self._chol, self._model = states, chol, model
+
+    def sample(self, model: Optional[PPCAModel] = None) -> Dataset:
+        model = model or self._model
+        if model is None:
+            raise ValueError("a PPCAModel is needed to sample outputs")
+        rng = np.random.default_rng()
+        n, k = self._states.shape
+        z = self._states + np.einsum("nab,nb->na", self._chol, rng.standard_normal((n, k)))
+        noise = model._sigma * rng.standard_normal((n, model.output_size))
+        return Dataset(noise + model._mu + z @ model._C.T)
+
+
+# =================================================================================================
+# PPCAMix  (src/python_bindings.rs:535-711 ; ppca/src/mix.rs)
+# =================================================================================================
+def _log_softmax(v: np.ndarray) -> np.ndarray:
+    """mix.rs:14-18 robust_log_softmax."""
+    mx = np.max(v)
+    return v - mx - np.log(np.sum(np.exp(v - mx)))
+
+
+class PPCAMix:
+    def __init__(self, models: Sequence[PPCAModel], log_weights):
+        models = list(models)
+        lw = np.asarray(log_weights, dtype=np.float64).reshape(-1)
+        if len(models) == 0:  # mix.rs:51
+            raise ValueError("a PPCA mixture needs at least one model")
+        if len(models) != lw.shape[0]:  # mix.rs:52
+            raise ValueError("models and log_weights have different lengths")
+        sizes = [m.output_size for m in models]
+        if len(set(sizes)) != 1:  # mix.rs:58-64
+            raise ValueError(f"Model output sizes are not the same: {sizes}")
+        self._models = models
+        self._logw = _log_softmax(lw)  # mix.rs:69
+
+    @staticmethod
+    def init(n_models: int, state_size: int, dataset: Dataset) -> "PPCAMix":
+        return PPCAMix([PPCAModel.init(state_size, dataset) for _ in range(n_models)], np.zeros(n_models))
+
+    @staticmethod
+    def load(data: bytes) -> "PPCAMix":
+        try:
+            _, models, lw = bincode.load_mix(bytes(data))
+        except ValueError as e:
+            raise Exception(str(e))
+        mix = PPCAMix.__new__(PPCAMix)
+        mix._models = [PPCAModel(s, c, m) for s, c, m in models]
+        mix._logw = np.asarray(lw, dtype=np.float64)  # stored already normalised
+        return mix
+
+    def dump(self) -> bytes:
+        return bincode.dump_mix(self.output_size, [(m._sigma, m._C, m._mu) for m in self._models], self._logw)
+
+    @property
+    def output_size(self) -> int:
+        return self._models[0].output_size
+
+    @property
+    def state_sizes(self) -> List[int]:
+        return [m.state_size for m in self._models]
+
+    @property
+    def n_parameters(self) -> int:
+        return sum(m.n_parameters for m in self._models) + len(self._models) - 1  # mix.rs:96-104
+
+    @property
+    def models(self) -> List[PPCAModel]:
+        return list(self._models)
+
+    @property
+    def log_weights(self) -> np.ndarray:
+        return self._logw.copy()
+
+    @property
+    def weights(self) -> np.ndarray:
+        return np.exp(self._logw)
+
+    def __repr__(self) -> str:
+        return f"PPCAMix(models={self._models!r}, log_weights={self._logw!r})"
+
+    # -- packing for the C ABI -------------------------------------------------------------------
+    def _pack(self):
+        ks = np.array(self.state_sizes, dtype=np.int32)
+        if (ks < 1).any():
+            raise ValueError("state_size 0 is not supported by the B200 engine")
+        Cs = np.ascontiguousarray(np.concatenate([m._C.reshape(-1) for m in self._models]))
+        mus = np.ascontiguousarray(np.stack([m._mu for m in self._models]))
+        sig = np.array([m._sigma for m in self._models], dtype=np.float64)
+        return ks, Cs, mus, sig, np.ascontiguousarray(self._logw)
+
+    def _check(self, dataset: Dataset) -> None:
+        if len(dataset) > 0 and dataset._output_size() != self.output_size:
+            raise ValueError("dataset output size does not match the mixture output size")
+
+    def _call(self, fn, dataset: Dataset, *tail):
+        self._check(dataset)
+        ks, Cs, mus, sig, lw = self._pack()
+        nat.check(fn(dataset._ctx.handle, dataset._h, len(self._models), ks.ctypes.data_as(nat.c_ip), nat.dptr(Cs),
+                     nat.dptr(mus), nat.dptr(sig), nat.dptr(lw), *tail))
+
+    def llks(self, dataset: Dataset) -> np.ndarray:
+        out = np.empty(len(dataset))
+        self._call(nat.lib().ppca_b200_mix_llks, dataset, nat.dptr(out))
+        return out
+
+    def llk(self, dataset: Dataset) -> float:
+        out = C.c_double(0.0)
+        self._call(nat.lib().ppca_b200_mix_llk, dataset, C.byref(out))
+        return out.value
+
+    def sample(self, dataset_size: int, mask_probability: float) -> Dataset:
+        """mix.rs:124-134 (unseeded)."""
+        rng = np.random.default_rng()
+        comp = rng.choice(len(self._models), size=int(dataset_size), p=self.weights / self.weights.sum())
+        d = self.output_size
+        x = np.empty((int(dataset_size), d))
+        for j, m in enumerate(self._models):
+            idx = np.nonzero(comp == j)[0]
+            if idx.size:
+                x[idx] = (rng.standard_normal((idx.size, m.state_size)) @ m._C.T + m._mu
+                          + m._sigma * rng.standard_normal((idx.size, d)))
+        x[rng.random(x.shape) < mask_probability] = np.nan
+        return Dataset(x)
+
+    def infer_cluster(self, dataset: Dataset) -> np.ndarray:
+        out = np.empty((len(dataset), len(self._models)))
+        self._call(nat.lib().ppca_b200_mix_infer_cluster, dataset, nat.dptr(out))
+        return out
+
+    def infer(self, dataset: Dataset) -> "InferredMaskedMix":
+        log_post = self.infer_cluster(dataset)
+        return InferredMaskedMix(log_post, [m.infer(dataset) for m in self._models])
+
+    def smooth(self, dataset: Dataset) -> Dataset:
+        h = nat.c_ds_p()
+        self._call(nat.lib().ppca_b200_mix_smooth, dataset, C.byref(h))
+        return Dataset._wrap(h, dataset._ctx)
+
+    filter_extrapolate = smooth
+
+    def extrapolate(self, dataset: Dataset) -> Dataset:
+        h = nat.c_ds_p()
+        self._call(nat.lib().ppca_b200_mix_extrapolate, dataset, C.byref(h))
+        return Dataset._wrap(h, dataset._ctx)
+
+    def _iterate(self, dataset: Dataset, prior: Optional[Prior]):
+        self._check(dataset)
+        ks, Cs, mus, sig, lw = self._pack()
+        Cs_o, mus_o, sig_o, lw_o = np.empty_like(Cs), np.empty_like(mus), np.empty_like(sig), np.empty_like(lw)
+        llk = C.c_double(0.0)
+        pr_ref, keep = None, None
+        if prior is not None:
+            pr, keep = prior._c(self.output_size)
+            pr_ref = C.byref(pr)
+        nat.check(nat.lib().ppca_b200_mix_iterate(dataset._ctx.handle, dataset._h, len(self._models),
+                                                  ks.ctypes.data_as(nat.c_ip), nat.dptr(Cs), nat.dptr(mus),
+                                                  nat.dptr(sig), nat.dptr(lw), pr_ref, nat.dptr(Cs_o), nat.dptr(mus_o),
+                                                  nat.dptr(sig_o), nat.dptr(lw_o), C.byref(llk)))
+        d = self.output_size
+        models, off = [], 0
+        for j, k in enumerate(ks):
+            models.append(PPCAModel(float(sig_o[j]), Cs_o[off:off + d * k].reshape(d, k).copy(), mus_o[j].copy()))
+            off += d * k
+        mix = PPCAMix.__new__(PPCAMix)
+        mix._models = models
+        mix._logw = lw_o
+        return mix, llk.value
+
+    def iterate_with_prior(self, dataset: Dataset, prior: Prior) -> "PPCAMix":
+        return self._iterate(dataset, prior)[0]
+
+    def iterate(self, dataset: Dataset) -> "PPCAMix":
+        return self._iterate(dataset, None)[0]
+
+    def to_canonical(self) -> "PPCAMix":
+        mix = PPCAMix.__new__(PPCAMix)
+        mix._models = [m.to_canonical() for m in self._models]
+        mix._logw = self._logw.copy()
+        return mix
+
+    def __getstate__(self):
+        return self.dump()
+
+    def __setstate__(self, state):
+        other = PPCAMix.load(state)
+        self._models, self._logw = other._models, other._logw
+
+    def __getnewargs__(self):
+        return (self.models, self.log_weights)
+
+
+# =================================================================================================
+# InferredMaskedMix  (src/python_bindings.rs:713-905 ; mix.rs:357-532).  Host numpy ("next").
+# =================================================================================================
+class InferredMaskedMix:
+    def __init__(self, log_posteriors: np.ndarray, inferred: List[InferredMasked]):
+        self._lp = log_posteriors
+        self._inf = inferred
+
+    def __len__(self) -> int:
+        return self._lp.shape[0]
+
+    def log_posteriors(self) -> np.ndarray:
+        return self._lp.copy() if len(self) else np.zeros((0, 0))
+
+    def posteriors(self) -> np.ndarray:
+        return np.exp(self._lp) if len(self) else np.zeros((0, 0))
+
+    def states(self) -> np.ndarray:
+        """mix.rs:374-380 weighs the sub-states by the LOG-posterior (reference quirk, reproduced)."""
+        if len(self) == 0:
+            return np.zeros((0, 0))
+        return sum(self._lp[:, j:j + 1] * inf._states for j, inf in enumerate(self._inf))
+
+    def covariances(self) -> List[np.ndarray]:
+        mean = self.states()
+        post = np.exp(self._lp)
+        out = np.zeros_like(self._inf[0]._covs)
+        for j, inf in enumerate(self._inf):  # mix.rs:383-394
+            dlt = inf._states - mean
+            out += post[:, j, None, None] * (inf._covs + np.einsum("na,nb->nab", dlt, dlt))
+        return [c for c in out]
+
+    def _parts(self, mix: PPCAMix, dataset: Optional[Dataset]):
+        post = np.exp(self._lp)
+        x = dataset.numpy() if dataset is not None else None
+        parts = []
+        for inf, m in zip(self._inf, mix._models):
+            sm = inf._states @ m._C.T + m._mu
+            parts.append(np.where(np.isfinite(x), x, sm) if x is not None else sm)
+        return post, parts
+
+    def smoothed(self, mix: PPCAMix) -> Dataset:
+        post, parts = self._parts(mix, None)
+        return Dataset(sum(post[:, j:j + 1] * p for j, p in enumerate(parts)))  # mix.rs:397-404
+
+    def extrapolated(self, mix: PPCAMix, dataset: Dataset) -> Dataset:
+        post, parts = self._parts(mix, dataset)
+        return Dataset(sum(post[:, j:j + 1] * p for j, p in enumerate(parts)))  # mix.rs:407-414
+
+    def smoothed_covariances(self, mix: PPCAMix) -> List[np.ndarray]:
+        post, parts = self._parts(mix, None)
+        mean = sum(post[:, j:j + 1] * p for j, p in enumerate(parts))
+        out = []
+        covs = [inf.smoothed_covariances(m) for inf, m in zip(self._inf, mix._models)]
+        for n in range(len(self)):  # mix.rs:422-437
+            acc = 0.0
+            for j in range(len(self._inf)):
+                dlt = parts[j][n] - mean[n]
+                acc = acc + post[n, j] * (covs[j][n] + np.outer(dlt, dlt))
+            out.append(acc)
+        return out
+
+    def smoothed_covariances_diagonal(self, mix: PPCAMix) -> Dataset:
+        post, parts = self._parts(mix, None)
+        mean = sum(post[:, j:j + 1] * p for j, p in enumerate(parts))
+        acc = 0.0
+        for j, (inf, m) in enumerate(zip(self._inf, mix._models)):  # mix.rs:445-458
+            acc = acc + post[:, j:j + 1] * (inf._smoothed_cov_diag(m) + (parts[j] - mean) ** 2)
+        return Dataset(acc)
+
+    def extrapolated_covariances(self, mix: PPCAMix, dataset: Dataset) -> List[np.ndarray]:
+        post, parts = self._parts(mix, dataset)
+        mean = sum(post[:, j:j + 1] * p for j, p in enumerate(parts))
+        covs = [inf.smoothed_covariances(m) for inf, m in zip(self._inf, mix._models)]  # mix.rs:474 (smoothed!)
+        out = []
+        for n in range(len(self)):
+            acc = 0.0
+            for j in range(len(self._inf)):
+                dlt = parts[j][n] - mean[n]
+                acc = acc + post[n, j] * (covs[j][n] + np.outer(dlt, dlt))
+            out.append(acc)
+        return out
+
+    def extrapolated_covariances_diagonal(self, mix: PPCAMix, dataset: Dataset) -> Dataset:
+        post, parts = self._parts(mix, dataset)
+        mean = sum(post[:, j:j + 1] * p for j, p in enumerate(parts))
+        x = dataset.numpy()
+        acc = 0.0
+        for j, (inf, m) in enumerate(zip(self._inf, mix._models)):  # mix.rs:485-501
+            diag = np.where(np.isfinite(x), 0.0, inf._smoothed_cov_diag(m))
+            acc = acc + post[:, j:j + 1] * (diag + (parts[j] - mean) ** 2)
+        return Dataset(acc)
+
+    def posterior_sampler(self) -> "PosteriorSamplerMix":
+        return PosteriorSamplerMix(np.exp(self._lp), [inf.posterior_sampler() for inf in self._inf])
+
+
+class PosteriorSamplerMix:
+    """mix.rs:519-532."""
+
+    def __init__(self, posteriors: np.ndarray, samplers: List[PosteriorSampler]):
+        self._post, self._samplers = posteriors, samplers
+
+    def sample(self, mix: PPCAMix) -> Dataset:
+        rng = np.random.default_rng()
+        n = self._post.shape[0]
+        p = self._post / self._post.sum(axis=1, keepdims=True)
+        choice = np.array([rng.choice(p.shape[1], p=p[i]) for i in range(n)])
+        outs = [s.sample(m).numpy() for s, m in zip(self._samplers, mix._models)]
+        return Dataset(np.stack([outs[choice[i]][i] for i in range(n)]))

@@ -1,0 +1,232 @@
+"""GPU parity: the CUDA engine (through the C ABI / ppca_rs_b200 front end) against the CPU oracle.
+
+Tolerance: BASELINE.json north_star — 1e-9 relative for the FP64 path (per-iteration llk, C, mu, sigma^2),
+identical masks and bit-identical observed slots for extrapolate.
+"""
+import numpy as np
+import pytest
+
+from helpers import init_model, make_data, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-9
+
+SHAPES = [
+    # n, d, k, p_missing
+    (100, 3, 2, 0.2),      # config 1: examples/toy_model.py
+    (777, 37, 5, 0.3),     # ragged everything
+    (3000, 200, 16, 0.2),  # config 2 shape, small n
+    (1500, 70, 10, 0.25),
+    (1200, 150, 32, 0.25), # config 4 state size
+    (600, 130, 48, 0.3),   # config 5 state size
+    (500, 260, 64, 0.3),   # config 3 state size
+    (300, 20, 1, 0.1),
+]
+
+
+@pytest.fixture(scope="module")
+def pk():
+    import ppca_rs_b200 as pk
+    return pk
+
+
+@pytest.fixture(scope="module")
+def orc():
+    from oracle import oracle
+    return oracle
+
+
+def _case(n, d, k, p, seed=0, **kw):
+    X = make_data(n, d, k, p, seed=seed, **kw)
+    C0, mu0, s0 = init_model(d, k, empty_dims=kw.get("empty_dims", ()))
+    return X, C0, mu0, s0
+
+
+def test_dataset_roundtrip(pk, orc):
+    X = make_data(1000, 45, 4, 0.3, seed=3, empty_rows=(5, 17), empty_dims=(7, 44))
+    X[3, 2] = np.inf
+    X[4, 1] = -np.inf
+    w = np.random.default_rng(1).random(1000) + 0.5
+    ds = pk.Dataset(X, w)
+    assert len(ds) == 1000 and ds.output_size() == 45
+    back = ds.numpy()
+    fin = np.isfinite(X)
+    assert np.array_equal(np.isfinite(back), fin)            # identical masks
+    assert np.array_equal(back[fin], X[fin])                  # bit-identical observed values
+    assert np.isnan(back[~fin]).all()                         # masked_vector: NaN (also where the input was inf)
+    assert np.array_equal(ds.weights(), w)
+    assert ds.empty_dimensions() == orc.empty_dimensions(X) == [7, 44]
+    # chunks / concat (src/python_bindings.rs:110-133,151-165)
+    parts = list(ds.chunks(3))
+    assert [len(p) for p in parts] == [334, 334, 332]
+    cat = pk.Dataset.concat(parts)
+    assert np.array_equal(np.isnan(cat.numpy()), np.isnan(back))
+    assert np.array_equal(cat.numpy()[fin], X[fin])
+    assert np.array_equal(cat.weights(), w)
+    # bincode round trip
+    again = pk.Dataset.load(ds.dump())
+    assert np.array_equal(again.numpy()[fin], X[fin]) and np.array_equal(again.weights(), w)
+
+
+@pytest.mark.parametrize("n,d,k,p", SHAPES)
+def test_llks_and_llk(pk, orc, n, d, k, p):
+    X, C0, mu0, s0 = _case(n, d, k, p, empty_rows=(1,))
+    w = np.random.default_rng(7).random(n) + 0.25
+    ds = pk.Dataset(X, w)
+    for sigma in (1.0, 0.3):
+        model = pk.PPCAModel(sigma, C0, mu0.reshape(1, -1))
+        got = model.llks(ds)
+        want = orc.llks(X, C0, mu0, sigma)
+        assert got[1] == 0.0                                   # empty sample (ppca_model.rs:125-129)
+        assert rel_err(got, want) < TOL
+        assert abs(model.llk(ds) - orc.llk(X, w, C0, mu0, sigma)) <= TOL * abs(orc.llk(X, w, C0, mu0, sigma))
+
+
+@pytest.mark.parametrize("n,d,k,p", SHAPES)
+def test_infer(pk, orc, n, d, k, p):
+    X, C0, mu0, s0 = _case(n, d, k, p, empty_rows=(0, 9))
+    ds = pk.Dataset(X)
+    model = pk.PPCAModel(0.5, C0, mu0.reshape(-1, 1))
+    inf = model.infer(ds)
+    Z, COV = orc.infer(X, C0, mu0, 0.5)
+    assert rel_err(inf.states(), Z) < TOL
+    assert rel_err(np.stack(inf.covariances()), COV) < TOL
+    assert np.array_equal(inf.states()[0], np.zeros(k))       # uninferred (ppca_model.rs:98-104)
+    assert np.array_equal(inf.covariances()[9], np.eye(k))
+
+
+@pytest.mark.parametrize("n,d,k,p", SHAPES)
+def test_smooth_extrapolate(pk, orc, n, d, k, p):
+    X, C0, mu0, s0 = _case(n, d, k, p, empty_rows=(2,))
+    w = np.random.default_rng(3).random(n) + 0.1
+    ds = pk.Dataset(X, w)
+    model = pk.PPCAModel(0.7, C0, mu0)
+    sm = model.smooth(ds)
+    ex = model.extrapolate(ds)
+    want_sm = orc.smooth(X, C0, mu0, 0.7)
+    want_ex = orc.extrapolate(X, C0, mu0, 0.7)
+    got_sm, got_ex = sm.numpy(), ex.numpy()
+    assert np.isfinite(got_sm).all() and np.isfinite(got_ex).all()   # outputs are unmasked datasets
+    fin = np.isfinite(X)
+    assert np.array_equal(got_ex[fin], X[fin])                        # observed slots bit-identical
+    scale = np.max(np.abs(want_sm))
+    assert np.max(np.abs(got_sm - want_sm)) < TOL * scale
+    assert np.max(np.abs(got_ex - want_ex)) < TOL * scale
+    assert np.array_equal(sm.weights(), w) and np.array_equal(ex.weights(), w)  # weights carried (:242,259)
+    assert np.array_equal(model.filter_extrapolate(ds).numpy(), got_sm)
+
+
+@pytest.mark.parametrize("n,d,k,p", SHAPES)
+def test_iterate_trajectory(pk, orc, n, d, k, p):
+    """Per-iteration llk, C, mu, sigma^2 over 6 EM iterations, each step started from the oracle's model."""
+    X, C0, mu0, s0 = _case(n, d, k, p, empty_rows=(4,), empty_dims=(d - 1,) if d > 3 else ())
+    w = np.random.default_rng(11).random(n) + 0.5
+    ds = pk.Dataset(X, w)
+    C, mu, s = C0, mu0, s0
+    for it in range(6):
+        model = pk.PPCAModel(s, C, mu)
+        new, llk = model._iterate(ds, None)
+        Cw, muw, sw = orc.iterate(X, w, C, mu, s)
+        llkw = orc.llk(X, w, C, mu, s)
+        assert abs(llk - llkw) <= TOL * abs(llkw), f"llk iteration {it}"
+        assert rel_err(new.transform, Cw) < TOL, f"C iteration {it}"
+        assert rel_err(new.mean, muw) < TOL, f"mu iteration {it}"
+        assert abs(new.isotropic_noise ** 2 - sw ** 2) <= TOL * sw ** 2, f"sigma^2 iteration {it}"
+        if d > 3:  # empty dimension keeps its (zeroed) row and mean (ppca_model.rs:313-321,376)
+            assert np.array_equal(new.transform[d - 1], C[d - 1])
+        C, mu, s = Cw, muw, sw
+
+
+def test_iterate_free_running(pk, orc):
+    """10 iterations without re-synchronising; llk must not decrease (ppca_model.rs:263-265)."""
+    X, C0, mu0, s0 = _case(2000, 60, 8, 0.2, seed=5)
+    ds = pk.Dataset(X)
+    model = pk.PPCAModel(s0, C0, mu0)
+    C, mu, s = C0, mu0, s0
+    last = -np.inf
+    for it in range(10):
+        llk = model.llk(ds)
+        assert llk >= last - 1e-9 * abs(llk)
+        last = llk
+        model = model.iterate(ds)
+        C, mu, s = orc.iterate(X, None, C, mu, s)
+    assert rel_err(model.transform, C) < 1e-7 and rel_err(model.mean, mu) < 1e-7
+    assert abs(model.isotropic_noise - s) < 1e-7 * s
+    canon = model.to_canonical()
+    assert abs(canon.llk(ds) - model.llk(ds)) < 1e-9 * abs(model.llk(ds))  # ppca_model.rs:395-397
+
+
+def test_priors(pk, orc):
+    X, C0, mu0, s0 = _case(800, 12, 3, 0.25, seed=9)
+    ds = pk.Dataset(X)
+    rng = np.random.default_rng(2)
+    A = rng.standard_normal((12, 12))
+    cov = A @ A.T / 12 + np.eye(12)
+    m0 = rng.standard_normal(12)
+    prior = (pk.Prior().with_mean_prior(m0.reshape(1, -1), cov).with_isotropic_noise_prior(3.0, 2.0)
+             .with_transformation_precision(0.5))
+    oprior = orc.Prior(mean=m0, mean_covariance=cov, isotropic_noise_alpha=3.0, isotropic_noise_beta=2.0,
+                       transformation_precision=0.5)
+    C, mu, s = C0, mu0, s0
+    for it in range(4):
+        new = pk.PPCAModel(s, C, mu).iterate_with_prior(ds, prior)
+        C, mu, s = orc.iterate(X, None, C, mu, s, oprior)
+        assert rel_err(new.transform, C) < TOL and rel_err(new.mean, mu) < TOL
+        assert abs(new.isotropic_noise - s) < TOL * s
+
+
+def _mix_case(pk, n, d, ks, seed=0):
+    rng = np.random.default_rng(seed)
+    X = np.concatenate([make_data(n // len(ks), d, k, 0.2, seed=seed + j, mean_scale=2.0) for j, k in enumerate(ks)])
+    rng.shuffle(X, axis=0)
+    models = []
+    for j, k in enumerate(ks):
+        C0, mu0, s0 = init_model(d, k, seed=1000 + j)
+        models.append((C0, mu0 + 0.1 * j, 1.0 + 0.1 * j))
+    logw = np.log(np.arange(1, len(ks) + 1) / np.sum(np.arange(1, len(ks) + 1)))
+    return X, models, logw
+
+
+@pytest.mark.parametrize("ks", [(2, 2), (4, 4, 4), (3, 5, 2, 8)])
+def test_mixture(pk, orc, ks):
+    n, d = 900, 24
+    X, models, logw = _mix_case(pk, n, d, ks)
+    w = np.random.default_rng(5).random(X.shape[0]) + 0.5
+    ds = pk.Dataset(X, w)
+    mix = pk.PPCAMix([pk.PPCAModel(s, C, mu) for C, mu, s in models], logw)
+    assert rel_err(mix.llks(ds), orc.mix_llks(X, models, logw)) < TOL
+    want_llk = orc.mix_llk(X, w, models, logw)
+    assert abs(mix.llk(ds) - want_llk) < TOL * abs(want_llk)
+    assert np.max(np.abs(mix.infer_cluster(ds) - orc.mix_infer_cluster(X, models, logw))) < 1e-9
+    sm, ex = mix.smooth(ds).numpy(), mix.extrapolate(ds).numpy()
+    want_sm, want_ex = orc.mix_smooth(X, models, logw), orc.mix_smooth(X, models, logw, extrapolate=True)
+    assert np.max(np.abs(sm - want_sm)) < TOL * np.max(np.abs(want_sm))
+    assert np.max(np.abs(ex - want_ex)) < TOL * np.max(np.abs(want_ex))
+    assert np.array_equal(mix.smooth(ds).weights(), np.ones(X.shape[0]))     # weights reset (mix.rs:245-265)
+    cur_models, cur_logw = models, logw
+    for it in range(3):
+        m = pk.PPCAMix([pk.PPCAModel(s, C, mu) for C, mu, s in cur_models], cur_logw)
+        new, llk = m._iterate(ds, None)
+        want_models, want_logw = orc.mix_iterate(X, w, cur_models, cur_logw)
+        assert abs(llk - orc.mix_llk(X, w, cur_models, cur_logw)) < TOL * abs(llk)
+        assert np.max(np.abs(new.log_weights - want_logw)) < 1e-9
+        for got, (Cw, muw, sw) in zip(new.models, want_models):
+            assert rel_err(got.transform, Cw) < TOL and rel_err(got.mean, muw) < TOL
+            assert abs(got.isotropic_noise - sw) < TOL * sw
+        cur_models, cur_logw = want_models, want_logw
+
+
+def test_trainer_and_pickle(pk, capsys):
+    import pickle
+    X = make_data(500, 10, 3, 0.2, seed=4)
+    ds = pk.Dataset(X)
+    model = pk.PPCATrainer(ds).train(state_size=3, n_iters=5)
+    out = capsys.readouterr().out
+    assert out.count("Masked PPCA iteration") == 5 and "aic=" in out
+    again = pickle.loads(pickle.dumps(model))
+    assert np.array_equal(again.transform, model.transform) and again.isotropic_noise == model.isotropic_noise
+    assert pk.PPCAModel.load(model.dump()).llk(ds) == model.llk(ds)
+    mix = pk.PPCAMixTrainer(ds).train(n_models=2, state_size=2, n_iters=3, quiet=True)
+    assert pickle.loads(pickle.dumps(mix)).llk(ds) == mix.llk(ds)
+    assert mix.n_parameters == sum(m.n_parameters for m in mix.models) + 1
