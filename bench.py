@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""bench.py — EM samples*iterations/s of the B200 PPCA engine (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3|c4|...]
+
+A "step" is what the reference trainer does per loop (python/ppca_rs/__init__.py:49-65): the log-likelihood
+of the current model plus one EM `iterate` over the whole (per-GPU resident) dataset.  The engine returns the
+log-likelihood as a by-product of the E-step, so one step is one pass.
+
+N > 1 is launched by the driver with torch.distributed.run, one rank per GPU.  Samples are sharded across
+ranks (weak scaling: every rank holds the same number of rows); each step every rank accumulates its local
+statistics buffer, ONE NCCL all-reduce sums it, and every rank finishes the M-step.
+
+`--impl reference` times the CPU restatement of the reference's algorithm (oracle/, kind "port": the Rust crate
+cannot be built in this image) on the host cores, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# name -> dict(n per GPU, d, k, p_missing, components, k_true)
+WORKLOADS = {
+    # configs[0] examples/toy_model.py
+    "c1": dict(n=100, d=3, k=2, p=0.2, m=1, k_true=2, desc="toy d=3 k=2 N=100"),
+    # configs[1] examples/big_toy_model.py scale, the single-GPU headline
+    "c2": dict(n=1_000_000, d=200, k=16, p=0.2, m=1, k_true=16, desc="N=1M d=200 k=16 20% missing"),
+    # configs[2] large PPCA: N=100M does not fit (1.64 TB); per-GPU resident shard of 4M rows (65.5 GB)
+    "c3": dict(n=4_000_000, d=2048, k=64, p=0.3, m=1, k_true=64, desc="d=2048 k=64 30% missing, 4M-row shard per GPU of the N=100M job"),
+    "c3s": dict(n=500_000, d=2048, k=64, p=0.3, m=1, k_true=64, desc="d=2048 k=64 30% missing, 0.5M-row shard"),
+    # configs[3] PPCAMix, 32 components
+    "c4": dict(n=2_000_000, d=512, k=32, p=0.25, m=32, k_true=32, desc="PPCAMix M=32 d=512 k=32 25% missing, 2M-row shard per GPU"),
+    "c4s": dict(n=200_000, d=512, k=32, p=0.25, m=4, k_true=32, desc="PPCAMix M=4 d=512 k=32 25% missing, 0.2M rows"),
+}
+SEED = 20240531
+
+
+def flops_per_sample_iter(d, k):
+    """F_iter = 2 d k (k+1) + 6 d k + k^3 (symmetric k x k counted once)."""
+    return 2 * d * k * (k + 1) + 6 * d * k + k ** 3
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.samples = []
+        self._stop = threading.Event()
+        self._t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        self._t.join(timeout=6)
+        return False
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples)
+        reasons = []
+        for name, col in (("hw_slowdown", 2), ("hw_thermal_slowdown", 3), ("sw_thermal_slowdown", 4), ("sw_power_cap", 5)):
+            if any(s[col].lower().startswith("active") for s in self.samples):
+                reasons.append(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+def fp64_peak():
+    """FP64 tensor (DMMA) peak for the roofline.  MEASURED_PEAKS.json only has HBM GB/s and bf16 TFLOP/s and
+    tcgen05 has no f64 kind, so the denominator is our own register-resident DMMA microbenchmark
+    (tools/fp64_peak.cu), run on this box when the binary is present, else the committed round-1 measurement."""
+    exe = os.path.join(ROOT, "build", "fp64_peak")
+    try:
+        if os.path.exists(exe):
+            out = subprocess.run([exe], capture_output=True, text=True, timeout=120).stdout.strip().splitlines()[-1]
+            j = json.loads(out)
+            return j["dmma_tflops"], j.get("dmma_tflops_sustained"), "tools/fp64_peak.cu on this box (burst)"
+    except Exception:
+        pass
+    with open(os.path.join(ROOT, "profiles", "r01_fp64_peak.json")) as f:
+        j = json.load(f)
+    return j["dmma_tflops"], j.get("dmma_tflops_sustained"), "profiles/r01_fp64_peak.json (tools/fp64_peak.cu, round 1)"
+
+
+def init_params(d, k, seed):
+    rng = np.random.default_rng(seed)
+    return rng.standard_normal((d, k)), np.zeros(d), 1.0
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm: CPU restatement on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_sample_rows(wl):
+    # about 10-30 s of CPU work per step at ~2e3 samples*iters/s/core for c2-like shapes
+    cost = flops_per_sample_iter(wl["d"], wl["k"]) * max(1, wl["m"])
+    return int(max(2_000, min(200_000, 2.5e10 / cost)))
+
+
+def host_sample(wl, rows, seed):
+    """Same generator semantics as the device one (ppca_model.rs:164-191), numpy on the host."""
+    rng = np.random.default_rng(seed)
+    d, kt = wl["d"], wl["k_true"]
+    Ct = (rng.random((d, kt)) < 0.1).astype(np.float64)
+    X = rng.standard_normal((rows, kt)) @ Ct.T + 0.1 * rng.standard_normal((rows, d))
+    X[rng.random((rows, d)) < wl["p"]] = np.nan
+    return X
+
+
+def cpu_step_time(wl, X, steps, warmup):
+    from oracle import oracle as orc  # bench.py's cpu_baseline / reference leg only
+    d, k, m = wl["d"], wl["k"], wl["m"]
+    times = []
+    if m == 1:
+        C, mu, s = init_params(d, k, SEED + 1000)
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            orc.llk(X, None, C, mu, s)            # python/ppca_rs/__init__.py:51
+            C, mu, s = orc.iterate(X, None, C, mu, s)  # :61-65
+            if it >= warmup:
+                times.append(time.perf_counter() - t0)
+    else:
+        models = [init_params(d, k, SEED + 1000 + j) for j in range(m)]
+        logw = np.full(m, -np.log(m))
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            orc.mix_llk(X, None, models, logw)
+            models, logw = orc.mix_iterate(X, None, models, logw)
+            if it >= warmup:
+                times.append(time.perf_counter() - t0)
+    return times, orc.num_threads()
+
+
+def run_reference(args, wl, rank):
+    if rank != 0:
+        return
+    rows = cpu_sample_rows(wl)
+    X = host_sample(wl, rows, SEED)
+    steps, warmup = max(1, min(args.steps, 3)), min(args.warmup, 1)
+    times, cores = cpu_step_time(wl, X, steps, warmup)
+    total = float(sum(times))
+    value = rows * len(times) / total
+    line = {
+        "impl": "reference", "metric": "EM samples*iters/sec", "value": value, "unit": "samples*iters/s",
+        "n_gpus": args.gpus, "steps": len(times), "warmup": warmup, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {wl['desc']}", "sample_rows": rows},
+        "cpu_baseline": {"value": value, "unit": "samples*iters/s", "cores": cores, "kind": "port",
+                         "sample": f"{rows} rows of the workload, {len(times)} step(s) of llk + iterate "
+                                   "(oracle/ppca_oracle.c, OpenMP, restatement of the reference's CPU algorithm; "
+                                   "the Rust crate cannot be built in this image)"},
+        "e2e": {"value": value, "unit": "samples*iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, wl, rank, world, local_rank):
+    import torch
+    import ppca_rs_b200 as pk
+    from ppca_rs_b200 import _native as nat
+    from ppca_rs_b200 import distributed as pdist
+
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    stream = torch.cuda.Stream(device=local_rank)  # the default stream's handle is NULL; use a real one
+    torch.cuda.set_stream(stream)
+    ctx = pk.Context(local_rank, stream.cuda_stream)
+    pk.set_context(ctx)
+    if args.chunk:
+        ctx.set_chunk(args.chunk)
+
+    n, d, k, m = wl["n"], wl["d"], wl["k"], wl["m"]
+    if args.rows:
+        n = args.rows
+    ds = pk.Dataset.synthetic(n, d, wl["k_true"], 0.1, wl["p"], n_components=max(1, m), seed=SEED + rank, ctx=ctx)
+
+    if m == 1:
+        C, mu, s = init_params(d, k, SEED + 1000)
+        state = pdist.ShardedPPCA(ctx, ds, pk.PPCAModel(s, C, mu), group=dist)
+    else:
+        models = [pk.PPCAModel(sg, Cj, muj) for Cj, muj, sg in (init_params(d, k, SEED + 1000 + j) for j in range(m))]
+        state = pdist.ShardedPPCAMix(ctx, ds, pk.PPCAMix(models, np.zeros(m)), group=dist)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        state.step()
+    ctx.set_profiling(True)
+    fam = {}
+    sync_all()
+    launches0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        e0.record(stream)
+        for _ in range(args.steps):
+            state.step()
+            for name, ms in ctx.last_profile().items():
+                fam[name] = fam.get(name, 0.0) + ms
+        e1.record(stream)
+        sync_all()
+    ms_total = e0.elapsed_time(e1)
+    launches = ctx.launch_count() - launches0
+    ctx.set_profiling(False)
+    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    n_total = n * world
+    value = n_total * args.steps / (ms_total * 1e-3)
+
+    # ---- end to end through the public API with host model buffers each step -------------------
+    # The reference API keeps the Dataset behind an opaque handle on the native side
+    # (src/python_bindings.rs:28-30); per step only the model crosses the boundary.
+    if m == 1:
+        C0, mu0, s0 = init_params(d, k, SEED + 1000)
+        model = pk.PPCAModel(s0, C0, mu0)
+        h2d = (d * k + d) * 8
+        d2h = (d * k + 2 * d + 8) * 8
+    else:
+        model = pk.PPCAMix([pk.PPCAModel(sg, Cj, muj) for Cj, muj, sg in (init_params(d, k, SEED + 1000 + j) for j in range(m))], np.zeros(m))
+        h2d = m * (d * k + d) * 8 * 2
+        d2h = m * (d * k + 2 * d + 8) * 8
+    e2e = None
+    if world == 1:
+        for _ in range(min(args.warmup, 3)):
+            model, _ = model._iterate(ds, None)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            model, llk = model._iterate(ds, None)
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        e2e = {"value": n * args.steps / e2e_s, "unit": "samples*iters/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h,
+               "note": "public API PPCAModel.iterate(dataset) with host numpy model in/out every step; the Dataset "
+                       "stays behind its handle as in the reference (src/python_bindings.rs:28-30); wall clock"}
+    else:
+        e2e = {"value": value, "unit": "samples*iters/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "note": "sharded step: host model in/out every step on every rank; same timed region as value"}
+
+    if rank != 0:
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel family: the masked-Gram contraction (bitgemm E + M) ------
+    peak, peak_sustained, peak_src = fp64_peak()
+    kk = k * (k + 1) // 2
+    bit_ms = fam.get("gram", 0.0) + fam.get("moment", 0.0)
+    if m > 1:
+        # E-step runs twice per component (posterior pass + weighted pass), M-step once
+        flops_bit = (3 * 2 * d * kk) * n * m * args.steps
+    else:
+        flops_bit = (2 * 2 * d * kk) * n * args.steps
+    achieved = flops_bit / (bit_ms * 1e-3) / 1e12 if bit_ms > 0 else None
+    roofline = {
+        "bound": "tensor", "kernel": "bitgemm_kernel (gram + moment launches)", "achieved": achieved, "peak": peak,
+        "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None, "traffic": None,
+        "peak_source": peak_src, "peak_sustained": peak_sustained,
+        "share_of_step": bit_ms / ms_total if ms_total else None,
+        "family_ms_per_step": {kname: v / args.steps for kname, v in fam.items()},
+        "whole_step_frac": flops_per_sample_iter(d, k) * max(1, m) * n * args.steps / (ms_total * 1e-3) / 1e12 / peak,
+    }
+
+    # ---- CPU baseline on a bounded sample of the same workload (rank 0, N=1 only) ----------------
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        rows = min(cpu_sample_rows(wl), n)
+        X = np.empty((rows, d))
+        nat.check(nat.lib().ppca_b200_dataset_to_host(ctx.handle, ds._h, 0, rows, nat.dptr(X)))
+        times, cores = cpu_step_time(wl, X, 1, 0)
+        cpu = {"value": rows / times[0], "unit": "samples*iters/s", "cores": cores, "kind": "port",
+               "sample": f"first {rows} rows of the GPU workload, 1 step of llk + iterate with the CPU restatement "
+                         "of the reference's algorithm (oracle/ppca_oracle.c, OpenMP); Rust crate not buildable here"}
+
+    line = {
+        "metric": "EM samples*iters/sec", "value": value, "unit": "samples*iters/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {wl['desc']}", "rows_per_gpu": n, "d": d, "k": k,
+                   "components": m, "parallelism": f"sample-sharded x{world}, one NCCL all-reduce of the statistics per step",
+                   "l2": "inputs larger than L2 (resident X per GPU = %.2f GB)" % (n * d * 8 / 1e9)},
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+        "clocks": clocks.summary(),
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--rows", type=int, default=0, help="override rows per GPU")
+    ap.add_argument("--chunk", type=int, default=0, help="samples per chunk (0 = automatic)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, wl, rank)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+    run_ours(args, wl, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

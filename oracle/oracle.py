@@ -94,6 +94,18 @@ class Prior:
         return pr, keep
 
 
+class stable:
+    """Context manager: run the oracle with the cancellation-free posterior formulas (see ppca_oracle.c)."""
+
+    def __enter__(self):
+        lib().oracle_set_stable(1)
+        return self
+
+    def __exit__(self, *exc):
+        lib().oracle_set_stable(0)
+        return False
+
+
 def num_threads() -> int:
     return lib().oracle_num_threads()
 

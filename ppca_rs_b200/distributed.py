@@ -1,0 +1,154 @@
+"""Sample-sharded EM: one process per GPU, one all-reduce of the additive statistics per iteration.
+
+Every statistic of the EM iteration is a sum over independent samples (ppca_model.rs:290-293,303-306,350-358;
+mix.rs:173,312-325), so the dataset is split into contiguous row blocks, one per rank, the model is replicated,
+and per iteration each rank
+    1. accumulates its local statistics buffer on the device       (ppca_b200_em_stats)
+    2. joins ONE all-reduce(SUM) over that buffer                   (torch.distributed, NCCL over NVLink)
+    3. finishes the M-step from the reduced buffer                  (ppca_b200_em_finish; replicated, O(d k^3))
+Mixtures add one all-reduce(MAX) of m doubles for the per-component responsibility maxima (mix.rs:312-318).
+
+The arithmetic is behind a small engine protocol so the host logic (sharding, buffer layout, reduction,
+replicated finish) can be exercised with world_size-2 gloo tests on CPU tensors; the product engine is
+`CudaEngine`, which has no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _native as nat
+from .model import Dataset, PPCAMix, PPCAModel, Prior
+
+
+def shard_bounds(n: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous row block [lo, hi) of rank `rank` out of `world`: sizes differ by at most one row."""
+    base, rem = divmod(int(n), int(world))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def stats_len(d: int, k: int) -> int:
+    """[A: d x kkp | B: d x kp | tdev: d | totals: d | 8 scalars] — ppca_b200_em_stats_len, restated."""
+    kk = k * (k + 1) // 2
+    kkp = (max(kk, 1) + 7) // 8 * 8
+    kp = (max(k, 1) + 7) // 8 * 8
+    return d * kkp + d * kp + 2 * d + 8
+
+
+class CudaEngine:
+    """The product engine: statistics on the device through the C ABI."""
+
+    def __init__(self, ctx: nat.Context):
+        import torch  # plumbing only: device buffers that NCCL can reduce
+        self.torch = torch
+        self.ctx = ctx
+        self.device = torch.device("cuda", ctx.device)
+
+    def new_stats(self, d: int, k: int):
+        n = nat.lib().ppca_b200_em_stats_len(d, k)
+        assert n == stats_len(d, k)
+        return self.torch.zeros(n, dtype=self.torch.float64, device=self.device)
+
+    def em_stats(self, ds: Dataset, model: PPCAModel, stats) -> None:
+        nat.check(nat.lib().ppca_b200_em_stats(self.ctx.handle, ds._h, model.state_size, nat.dptr(model._C),
+                                               nat.dptr(model._mu), model._sigma, C.c_void_p(stats.data_ptr())))
+
+    def em_finish(self, model: PPCAModel, prior: Optional[Prior], stats) -> Tuple[PPCAModel, float]:
+        d, k = model.output_size, model.state_size
+        C_out, mu_out = np.empty((d, k)), np.empty(d)
+        s_out, llk = C.c_double(0.0), C.c_double(0.0)
+        pr_ref, keep = None, None
+        if prior is not None:
+            pr, keep = prior._c(d)
+            pr_ref = C.byref(pr)
+        nat.check(nat.lib().ppca_b200_em_finish(self.ctx.handle, d, k, nat.dptr(model._C), nat.dptr(model._mu),
+                                                model._sigma, pr_ref, C.c_void_p(stats.data_ptr()), nat.dptr(C_out),
+                                                nat.dptr(mu_out), C.byref(s_out), C.byref(llk)))
+        return PPCAModel(s_out.value, C_out, mu_out), llk.value
+
+    # mixtures
+    def new_logpost(self, n: int, m: int):
+        return self.torch.empty(max(n, 1) * m, dtype=self.torch.float64, device=self.device)
+
+    def mix_posteriors(self, ds: Dataset, mix: PPCAMix, logpost) -> Tuple[np.ndarray, float]:
+        ks, Cs, mus, sig, lw = mix._pack()
+        cmax = np.empty(len(ks))
+        llk = C.c_double(0.0)
+        nat.check(nat.lib().ppca_b200_mix_posteriors(self.ctx.handle, ds._h, len(ks), ks.ctypes.data_as(nat.c_ip),
+                                                     nat.dptr(Cs), nat.dptr(mus), nat.dptr(sig), nat.dptr(lw),
+                                                     C.c_void_p(logpost.data_ptr()), nat.dptr(cmax), C.byref(llk)))
+        return cmax, llk.value
+
+    def mix_em_stats(self, ds: Dataset, mix: PPCAMix, j: int, logpost, cmax_j: float, stats) -> None:
+        mj = mix._models[j]
+        nat.check(nat.lib().ppca_b200_mix_em_stats(self.ctx.handle, ds._h, len(mix._models), j, mj.state_size,
+                                                   nat.dptr(mj._C), nat.dptr(mj._mu), mj._sigma,
+                                                   C.c_void_p(logpost.data_ptr()), float(cmax_j),
+                                                   C.c_void_p(stats.data_ptr())))
+
+    def to_tensor(self, a: np.ndarray):
+        return self.torch.from_numpy(np.ascontiguousarray(a)).to(self.device)
+
+    def scalar_sumw(self, stats, d: int, k: int) -> float:
+        return float(stats[stats_len(d, k) - 8 + 3].item())
+
+
+class ShardedPPCA:
+    """EM for one PPCAModel over a dataset sharded across the ranks of `group` (None = single process)."""
+
+    def __init__(self, ctx, dataset, model: PPCAModel, group=None, prior: Optional[Prior] = None, engine=None):
+        self.engine = engine or CudaEngine(ctx)
+        self.dataset, self.model, self.prior, self.group = dataset, model, prior, group
+        self.stats = self.engine.new_stats(model.output_size, model.state_size)
+        self.last_llk = float("nan")
+
+    def step(self) -> float:
+        """One EM iteration; returns the (global) log-likelihood of the model the step started from."""
+        self.engine.em_stats(self.dataset, self.model, self.stats)
+        if self.group is not None:
+            self.group.all_reduce(self.stats)  # SUM
+        self.model, self.last_llk = self.engine.em_finish(self.model, self.prior, self.stats)
+        return self.last_llk
+
+
+class ShardedPPCAMix:
+    """EM for a PPCAMix over a sharded dataset (mix.rs:281-337)."""
+
+    def __init__(self, ctx, dataset, mix: PPCAMix, group=None, prior: Optional[Prior] = None, engine=None):
+        self.engine = engine or CudaEngine(ctx)
+        self.dataset, self.mix, self.prior, self.group = dataset, mix, prior, group
+        d = mix.output_size
+        self.stats = [self.engine.new_stats(d, k) for k in mix.state_sizes]
+        self.logpost = self.engine.new_logpost(len(dataset), len(mix._models))
+        self.last_llk = float("nan")
+
+    def step(self) -> float:
+        eng, mix = self.engine, self.mix
+        m, d = len(mix._models), mix.output_size
+        cmax, llk = eng.mix_posteriors(self.dataset, mix, self.logpost)
+        if self.group is not None:
+            t = eng.to_tensor(np.concatenate([cmax, [llk]]))
+            tmax = t[:m].clone()
+            self.group.all_reduce(tmax, op=self.group.ReduceOp.MAX)
+            tsum = t[m:].clone()
+            self.group.all_reduce(tsum)
+            cmax, llk = tmax.cpu().numpy(), float(tsum.item())
+        for j in range(m):
+            eng.mix_em_stats(self.dataset, mix, j, self.logpost, float(cmax[j]), self.stats[j])
+        if self.group is not None:
+            for st in self.stats:
+                self.group.all_reduce(st)
+        models, logsum = [], np.empty(m)
+        for j, mj in enumerate(mix._models):
+            new, _ = eng.em_finish(mj, self.prior, self.stats[j])
+            models.append(new)
+            logsum[j] = np.log(eng.scalar_sumw(self.stats[j], d, mj.state_size)) + cmax[j]  # mix.rs:323-324
+        new_mix = PPCAMix.__new__(PPCAMix)
+        new_mix._models = models
+        mx = logsum.max()
+        new_mix._logw = logsum - mx - np.log(np.sum(np.exp(logsum - mx)))  # mix.rs:335
+        self.mix, self.last_llk = new_mix, llk
+        return llk

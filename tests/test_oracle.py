@@ -137,3 +137,26 @@ def test_mixture_against_definitions():
 def test_empty_dimensions():
     X = np.array([[1.0, 1.0, np.nan], [1.0, 1.0, np.nan]])  # examples/empty_dimensions.py
     assert orc.empty_dimensions(X) == [2]
+
+
+def test_reference_noise_floor_is_documented():
+    """The reference's posterior formulas cancel (I - T C_o); its own error versus 50-digit arithmetic grows
+    like eps (|G|/sigma^2)^2.  The stable oracle variant stays at rounding level.  This is why the GPU parity
+    tests compare against both variants (see tests/test_gpu_parity.py::assert_close)."""
+    import mpmath as mp
+    X = make_data(10, 30, 4, 0.2, seed=1)
+    C0, mu0, _ = init_model(30, 4)
+    mp.mp.dps = 50
+    x = X[0]; m = np.isfinite(x)
+    Co = mp.matrix(C0[m].tolist())
+    errs = {}
+    for sigma in (1.0, 0.01):
+        Minv = (Co.T * Co + mp.eye(4) * mp.mpf(sigma) ** 2) ** -1
+        truth = np.array([[float(Minv[i, j] * mp.mpf(sigma) ** 2) for j in range(4)] for i in range(4)])
+        _, cov_f = orc.infer(X[:1], C0, mu0, sigma)
+        with orc.stable():
+            _, cov_s = orc.infer(X[:1], C0, mu0, sigma)
+        errs[sigma] = (rel_err(cov_f[0], truth), rel_err(cov_s[0], truth))
+    assert errs[1.0][0] < 1e-11 and errs[1.0][1] < 1e-13
+    assert errs[0.01][0] > 1e-9          # the reference's own noise floor is above the parity tolerance here
+    assert errs[0.01][1] < 1e-13         # the cancellation-free form is not
