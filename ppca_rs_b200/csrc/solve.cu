@@ -171,6 +171,298 @@ __global__ void __launch_bounds__(256) solve_kernel(SolveArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Register-resident variant for k <= 32: KP (8/16/32) lanes per sample, lane i owns row i of the symmetric
+// matrix in registers.  M_n is inverted by an in-place Gauss-Jordan elimination without row scaling:
+//   pivot p:  m_i = T[i][p] / d_p ;  T[i][j] -= m_i T[p][j] (j != p) ;  T[i][p] = -m_i ;  T[p][p] = 1
+// and a final row scaling by 1/d_i.  The pivot ROW is never broadcast from one lane: by symmetry of the
+// Schur complement T[p][j] = T[j][p] for unpivoted j and T[p][j] = -T[j][p] / d_j for pivoted j, so every
+// lane contributes its own element through one conflict-free shared-memory store per pivot.  The pivots are
+// the Cholesky pivots squared, so ln det M = sum ln d_p (no determinant overflow).
+// ---------------------------------------------------------------------------------------------
+template <int KP>
+__global__ void __launch_bounds__(256, (KP == 32 ? 2 : (KP == 16 ? 3 : 4))) solve_reg_kernel(SolveArgs a) {
+  constexpr int SPW = 32 / KP;
+  extern __shared__ __align__(16) double smem_reg[];
+  const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5, warps = blockDim.x >> 5;
+  const int sub = lane / KP, li = lane % KP;
+  const int k = a.s.k, kkp = a.s.kkp, kp = a.s.kp;
+  const int per_warp = SPW * kkp + 128;
+  double *stage = smem_reg + (size_t)wi * per_warp;  // SPW packed rows
+  double *col = stage + SPW * kkp;                   // [2][32] pivot-column exchange
+  double *yb = col + 64;                             // [32]
+  double *zb = yb + 32;                              // [32]
+  const double s2 = a.sigma * a.sigma;
+  const double ln_sigma = log(a.sigma);
+  const int groups = (a.rows_pad + SPW - 1) / SPW;
+
+  for (int g = blockIdx.x * warps + wi; g < groups; g += gridDim.x * warps) {
+    const int row0 = g * SPW;
+    const int row = row0 + sub;
+    double *gsrc = a.GW + (int64_t)row0 * kkp;
+    for (int q = lane * 2; q < SPW * kkp; q += 64)
+      *reinterpret_cast<double2 *>(stage + q) = *reinterpret_cast<const double2 *>(gsrc + q);
+    yb[lane] = (li < kp) ? a.YZ[(int64_t)row * kp + li] : 0.0;
+    const int dn = row < a.rows ? a.dn[row] : 0;
+    const bool empty = dn == 0;
+    const double w = (a.w && row < a.rows) ? a.w[row] : (row < a.rows ? 1.0 : 0.0);
+    __syncwarp();
+
+    const double *st = stage + sub * kkp;
+    const bool live = li < k && !empty;
+    double A[KP];
+#pragma unroll
+    for (int j = 0; j < KP; ++j) {
+      double v = (j == li) ? 1.0 : 0.0;
+      if (live && j < k) {
+        const int lo = li < j ? li : j, hi = li < j ? j : li;
+        v = st[tri_row_off(lo, k) + hi - lo] + (j == li ? s2 : 0.0);
+      }
+      A[j] = v;
+    }
+
+    double mypiv = 1.0, myinv = 1.0;
+#pragma unroll
+    for (int p = 0; p < KP; ++p) {
+      double *cb = col + (p & 1) * 32;
+      cb[lane] = (li < p) ? -A[p] * myinv : A[p];
+      __syncwarp();
+      const double *cs = cb + sub * KP;
+      const double dpp = cs[p];
+      const double inv = 1.0 / dpp;
+      if (li == p) {
+        mypiv = dpp;
+        myinv = inv;
+      }
+      const double f = (li == p) ? 0.0 : A[p] * inv;
+#pragma unroll
+      for (int j = 0; j < KP; ++j)
+        if (j != p) A[j] = fma(-f, cs[j], A[j]);
+      A[p] = (li == p) ? 1.0 : -f;
+    }
+#pragma unroll
+    for (int j = 0; j < KP; ++j) A[j] *= myinv;  // A[j] = M^{-1}[li][j]
+
+    // z = M^{-1} y ; quad = y^T z ; ln det
+    double zi = 0.0;
+    {
+      const double *ys = yb + sub * KP;
+#pragma unroll
+      for (int j = 0; j < KP; ++j) zi = fma(A[j], ys[j], zi);
+    }
+    if (!live) zi = 0.0;
+    double quad = yb[lane] * zi;
+    double logdet = live ? log(mypiv) : 0.0;
+#pragma unroll
+    for (int o = KP / 2; o > 0; o >>= 1) {
+      quad += __shfl_xor_sync(0xffffffffu, quad, o);
+      logdet += __shfl_xor_sync(0xffffffffu, logdet, o);
+    }
+    if (a.llk && li == 0 && row < a.rows) {
+      double llk = 0.0;
+      if (!empty)
+        llk = -0.5 * (a.nx[row] - quad) / s2 - 0.5 * (logdet + 2.0 * ln_sigma * (double)(dn - k)) -
+              0.5 * LN_2PI * (double)dn;
+      a.llk[row] = llk;
+    }
+    if (a.mode == 0) {
+      __syncwarp();
+      continue;
+    }
+    zb[lane] = zi;
+    if (li < kp) {
+      a.YZ[(int64_t)row * kp + li] = zi;
+      if (a.WZ) a.WZ[(int64_t)row * kp + li] = w * zi;
+    }
+    if (a.cov && row < a.rows && li < k) {
+      double *cv = a.cov + (int64_t)row * k * k + (int64_t)li * k;
+#pragma unroll
+      for (int j = 0; j < KP; ++j)
+        if (j < k) cv[j] = empty ? (j == li ? 1.0 : 0.0) : s2 * A[j];
+    }
+    if (a.mode == 2) {
+      // t = tr(Sigma G) = sigma^2 sum_ij M^{-1}_ij G_ij  (G still in the staging buffer)
+      double tpart = 0.0;
+      if (live) {
+#pragma unroll
+        for (int j = 0; j < KP; ++j)
+          if (j < k) {
+            const int lo = li < j ? li : j, hi = li < j ? j : li;
+            tpart = fma(A[j], st[tri_row_off(lo, k) + hi - lo], tpart);
+          }
+      }
+#pragma unroll
+      for (int o = KP / 2; o > 0; o >>= 1) tpart += __shfl_xor_sync(0xffffffffu, tpart, o);
+      if (a.tn && li == 0 && row < a.rows) a.tn[row] = empty ? 0.0 : s2 * tpart;
+      __syncwarp();  // everyone is done reading G and zb is visible
+      // W = w (z z^T + sigma^2 M^{-1}), upper triangle of row li, packed in place
+      if (li < k) {
+        double *so = stage + sub * kkp + tri_row_off(li, k) - li;
+        const double *zs = zb + sub * KP;
+#pragma unroll
+        for (int j = 0; j < KP; ++j)
+          if (j >= li && j < k) so[j] = empty ? 0.0 : w * fma(zi, zs[j], s2 * A[j]);
+      }
+      __syncwarp();
+      for (int q = lane * 2; q < SPW * kkp; q += 64)
+        *reinterpret_cast<double2 *>(gsrc + q) = *reinterpret_cast<const double2 *>(stage + q);
+    }
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 32 < k <= 64: the same elimination with 64 lanes (two warps) per sample; the pivot-column exchange and the
+// reductions go through shared memory with a 64-thread named barrier per sample.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pair_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+
+__global__ void __launch_bounds__(256, 1) solve_reg64_kernel(SolveArgs a) {
+  constexpr int KP = 64;
+  extern __shared__ __align__(16) double smem_reg[];
+  const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+  const int pair = wi >> 1, li = (wi & 1) * 32 + lane;
+  const int bar_id = pair + 1;
+  const int k = a.s.k, kkp = a.s.kkp, kp = a.s.kp;
+  const int per_pair = kkp + 5 * 64;
+  double *stage = smem_reg + (size_t)pair * per_pair;  // one packed row
+  double *col = stage + kkp;                           // [2][64]
+  double *yb = col + 128;                              // [64]
+  double *zb = yb + 64;                                // [64]
+  double *red = zb + 64;                               // [64] scratch for reductions
+  const double s2 = a.sigma * a.sigma;
+  const double ln_sigma = log(a.sigma);
+
+  for (int row = blockIdx.x * 4 + pair; row < a.rows_pad; row += gridDim.x * 4) {
+    double *gsrc = a.GW + (int64_t)row * kkp;
+    for (int q = li * 2; q < kkp; q += 128)
+      *reinterpret_cast<double2 *>(stage + q) = *reinterpret_cast<const double2 *>(gsrc + q);
+    yb[li] = (li < kp) ? a.YZ[(int64_t)row * kp + li] : 0.0;
+    const int dn = row < a.rows ? a.dn[row] : 0;
+    const bool empty = dn == 0;
+    const double w = (a.w && row < a.rows) ? a.w[row] : (row < a.rows ? 1.0 : 0.0);
+    pair_sync(bar_id);
+
+    const bool live = li < k && !empty;
+    double A[KP];
+#pragma unroll
+    for (int j = 0; j < KP; ++j) {
+      double v = (j == li) ? 1.0 : 0.0;
+      if (live && j < k) {
+        const int lo = li < j ? li : j, hi = li < j ? j : li;
+        v = stage[tri_row_off(lo, k) + hi - lo] + (j == li ? s2 : 0.0);
+      }
+      A[j] = v;
+    }
+
+    double mypiv = 1.0, myinv = 1.0;
+#pragma unroll
+    for (int p = 0; p < KP; ++p) {
+      double *cb = col + (p & 1) * 64;
+      cb[li] = (li < p) ? -A[p] * myinv : A[p];
+      pair_sync(bar_id);
+      const double dpp = cb[p];
+      const double inv = 1.0 / dpp;
+      if (li == p) {
+        mypiv = dpp;
+        myinv = inv;
+      }
+      const double f = (li == p) ? 0.0 : A[p] * inv;
+#pragma unroll
+      for (int j = 0; j < KP; ++j)
+        if (j != p) A[j] = fma(-f, cb[j], A[j]);
+      A[p] = (li == p) ? 1.0 : -f;
+    }
+#pragma unroll
+    for (int j = 0; j < KP; ++j) A[j] *= myinv;
+
+    double zi = 0.0;
+#pragma unroll
+    for (int j = 0; j < KP; ++j) zi = fma(A[j], yb[j], zi);
+    if (!live) zi = 0.0;
+    double quad = warp_sum(yb[li] * zi);
+    double logdet = warp_sum(live ? log(mypiv) : 0.0);
+    if (lane == 0) {
+      red[(wi & 1) * 2] = quad;
+      red[(wi & 1) * 2 + 1] = logdet;
+    }
+    zb[li] = zi;
+    pair_sync(bar_id);
+    if (a.llk && li == 0 && row < a.rows) {
+      double llk = 0.0;
+      if (!empty)
+        llk = -0.5 * (a.nx[row] - (red[0] + red[2])) / s2 -
+              0.5 * ((red[1] + red[3]) + 2.0 * ln_sigma * (double)(dn - k)) - 0.5 * LN_2PI * (double)dn;
+      a.llk[row] = llk;
+    }
+    if (a.mode != 0) {
+      if (li < kp) {
+        a.YZ[(int64_t)row * kp + li] = zi;
+        if (a.WZ) a.WZ[(int64_t)row * kp + li] = w * zi;
+      }
+      if (a.cov && row < a.rows && li < k) {
+        double *cv = a.cov + (int64_t)row * k * k + (int64_t)li * k;
+#pragma unroll
+        for (int j = 0; j < KP; ++j)
+          if (j < k) cv[j] = empty ? (j == li ? 1.0 : 0.0) : s2 * A[j];
+      }
+    }
+    if (a.mode == 2) {
+      double tpart = 0.0;
+      if (live) {
+#pragma unroll
+        for (int j = 0; j < KP; ++j)
+          if (j < k) {
+            const int lo = li < j ? li : j, hi = li < j ? j : li;
+            tpart = fma(A[j], stage[tri_row_off(lo, k) + hi - lo], tpart);
+          }
+      }
+      tpart = warp_sum(tpart);
+      if (lane == 0) red[4 + (wi & 1)] = tpart;
+      pair_sync(bar_id);  // all reads of G done, partial traces visible
+      if (a.tn && li == 0 && row < a.rows) a.tn[row] = empty ? 0.0 : s2 * (red[4] + red[5]);
+      if (li < k) {
+        double *so = stage + tri_row_off(li, k) - li;
+#pragma unroll
+        for (int j = 0; j < KP; ++j)
+          if (j >= li && j < k) so[j] = empty ? 0.0 : w * fma(zi, zb[j], s2 * A[j]);
+      }
+      pair_sync(bar_id);
+      for (int q = li * 2; q < kkp; q += 128)
+        *reinterpret_cast<double2 *>(gsrc + q) = *reinterpret_cast<const double2 *>(stage + q);
+    }
+    pair_sync(bar_id);
+  }
+}
+
+static void launch_solve_reg64(const Launcher &L, const SolveArgs &a) {
+  const size_t smem = (size_t)4 * (a.s.kkp + 5 * 64) * sizeof(double);
+  static bool configured = false;
+  if (!configured) {
+    CUDA_CHECK(cudaFuncSetAttribute(solve_reg64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    configured = true;
+  }
+  int64_t blocks = (a.rows_pad + 3) / 4;
+  if (blocks > L.sms) blocks = L.sms;
+  solve_reg64_kernel<<<(unsigned)blocks, 256, smem, L.stream>>>(a);
+  CUDA_CHECK(cudaGetLastError());
+  ++*L.launch_counter;
+}
+
+template <int KP>
+static void launch_solve_reg(const Launcher &L, const SolveArgs &a) {
+  constexpr int SPW = 32 / KP;
+  const int warps = 8;
+  const size_t smem = (size_t)warps * (SPW * a.s.kkp + 128) * sizeof(double);
+  const int groups = (a.rows_pad + SPW - 1) / SPW;
+  int64_t blocks = (groups + warps - 1) / warps;
+  const int64_t cap = (int64_t)L.sms * 8;
+  if (blocks > cap) blocks = cap;
+  solve_reg_kernel<KP><<<(unsigned)blocks, warps * 32, smem, L.stream>>>(a);
+  CUDA_CHECK(cudaGetLastError());
+  ++*L.launch_counter;
+}
+
 // fixed-order reduction of the per-sample scalars of one chunk into the statistics scalars
 __global__ void __launch_bounds__(1024) solve_reduce_kernel(int rows, const double *__restrict__ llk,
                                                             const double *__restrict__ tn, const int *__restrict__ dn,
@@ -203,8 +495,7 @@ __global__ void __launch_bounds__(1024) solve_reduce_kernel(int rows, const doub
   }
 }
 
-void launch_solve(const Launcher &L, const SolveArgs &a) {
-  if (a.rows_pad <= 0) return;
+static void launch_solve_generic(const Launcher &L, const SolveArgs &a) {
   const SolveSmem lay(a.s.k);
   const size_t per_warp = (size_t)lay.per_warp * sizeof(double);
   int warps = 8;
@@ -225,6 +516,16 @@ void launch_solve(const Launcher &L, const SolveArgs &a) {
   solve_kernel<<<(unsigned)blocks, warps * 32, smem, L.stream>>>(a);
   CUDA_CHECK(cudaGetLastError());
   ++*L.launch_counter;
+}
+
+void launch_solve(const Launcher &L, const SolveArgs &a) {
+  if (a.rows_pad <= 0) return;
+  REQUIRE(a.mode == 0 || a.GW != nullptr, "solve: missing Gram buffer");
+  if (a.s.k <= 8) launch_solve_reg<8>(L, a);
+  else if (a.s.k <= 16) launch_solve_reg<16>(L, a);
+  else if (a.s.k <= 32) launch_solve_reg<32>(L, a);
+  else if (a.s.k <= 64) launch_solve_reg64(L, a);
+  else launch_solve_generic(L, a);
   if (a.scalars) {
     solve_reduce_kernel<<<1, 1024, 0, L.stream>>>(a.rows, a.llk, a.tn, a.dn, a.w, a.scalars);
     CUDA_CHECK(cudaGetLastError());
