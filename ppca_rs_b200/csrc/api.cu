@@ -32,7 +32,7 @@ struct ppca_b200_ctx {
   // model staging
   DevBuf<double> Cdense, mudense, Cpad, mupad, Ksym, logw;
   // chunk workspaces
-  DevBuf<double> GW, YZ, WZ, nx, llk, tn, part_bg, part_cr, stats, Cnew, cov, rbuf;
+  DevBuf<double> GW, YZ, WZ, nx, llk, tn, part_bg, part_cr, part_solve, stats, Cnew, cov, rbuf;
   DevBuf<int> flags;
   // pinned staging
   double *pinned = nullptr;
@@ -75,14 +75,15 @@ struct ppca_b200_ctx {
     spans.back().b = next_event();
     CUDA_CHECK(cudaEventRecord(spans.back().b, stream));
   }
-  void profile_reset() {
+  void profile_reset(bool zero = true) {
     spans.clear();
     ev_used = 0;
+    if (zero)
+      for (int i = 0; i < FAM_COUNT; ++i) last_profile[i] = 0.0;
   }
   void profile_collect() {
     if (!profiling) return;
     CUDA_CHECK(cudaStreamSynchronize(stream));
-    for (int i = 0; i < FAM_COUNT; ++i) last_profile[i] = 0.0;
     for (auto &s : spans) {
       float ms = 0.f;
       CUDA_CHECK(cudaEventElapsedTime(&ms, s.a, s.b));
@@ -228,7 +229,7 @@ void reserve_chunk_ws(ppca_b200_ctx *ctx, int64_t chunk, const Shape &s) {
 
 // E-step of one chunk: Gram contraction, projection, per-sample solve
 void e_step_chunk(ppca_b200_ctx *ctx, const SampleStore &st, const double *w, int64_t row0, int rows,
-                  const DevModel &m, int mode, double *llk_out, double *cov_out, double *scalars) {
+                  const DevModel &m, int mode, double *llk_out, double *cov_out, double *solve_part) {
   const Launcher L = ctx->L();
   const int rows_pad = (int)round_up(rows, 256);
   BitGemmArgs g;
@@ -241,9 +242,11 @@ void e_step_chunk(ppca_b200_ctx *ctx, const SampleStore &st, const double *w, in
   g.M = rows;
   g.Nq = m.s.kkp;
   g.kblocks = m.s.d32 / 32;
+  g.kcols = m.s.d;
   g.accumulate = 0;
   g.partials = nullptr;
   g.splitk = 1;
+  g.defer_reduce = 0;
   ctx->span_begin(FAM_GRAM);
   launch_bitgemm(L, g);
   ctx->span_end();
@@ -264,7 +267,7 @@ void e_step_chunk(ppca_b200_ctx *ctx, const SampleStore &st, const double *w, in
   sa.llk = llk_out;
   sa.tn = mode == 2 ? ctx->tn.p : nullptr;
   sa.cov = cov_out;
-  sa.scalars = scalars;
+  sa.part = solve_part;
   sa.mode = mode;
   ctx->span_begin(FAM_SOLVE);
   launch_solve(L, sa);
@@ -281,12 +284,19 @@ void em_stats_impl(ppca_b200_ctx *ctx, const SampleStore &st, const double *w, c
   reserve_chunk_ws(ctx, chunk, m.s);
   const int kb_chunk = (int)(chunk / 32);
   const int splitk = bitgemm_pick_splitk(m.s.d, m.s.kkp, kb_chunk, ctx->sms);
-  ctx->part_bg.reserve(bitgemm_partials_len(m.s.d, m.s.kkp, splitk));
-  const size_t crlen = cross_resid_partials_len(m.s.d, m.s.k, (int)chunk, ctx->sms);
+  const size_t bglen = bitgemm_partials_len(m.s.d, m.s.kkp, splitk);
+  ctx->part_bg.reserve(bglen);
+  const int slabs = cross_resid_slabs(m.s.d, m.s.k, (int)chunk, ctx->sms);
+  const size_t crlen = cross_resid_partials_len(m.s.d, m.s.k, slabs);
   ctx->part_cr.reserve(crlen);
+  ctx->part_solve.reserve((size_t)SOLVE_SLOTS * 4);
+  // partial slots are owned by fixed CTAs and accumulated across chunks; one fixed-order reduction at the end
+  if (bglen) CUDA_CHECK(cudaMemsetAsync(ctx->part_bg.p, 0, sizeof(double) * bglen, ctx->stream));
+  CUDA_CHECK(cudaMemsetAsync(ctx->part_cr.p, 0, sizeof(double) * crlen, ctx->stream));
+  CUDA_CHECK(cudaMemsetAsync(ctx->part_solve.p, 0, sizeof(double) * SOLVE_SLOTS * 4, ctx->stream));
   for (int64_t row0 = 0; row0 < st.n; row0 += chunk) {
     const int rows = (int)((st.n - row0) < chunk ? (st.n - row0) : chunk);
-    e_step_chunk(ctx, st, w, row0, rows, m, 2, ctx->llk.p, nullptr, stats_dev + lay.offScalars);
+    e_step_chunk(ctx, st, w, row0, rows, m, 2, ctx->llk.p, nullptr, ctx->part_solve.p);
     BitGemmArgs g;
     g.bits = st.maskT.p + row0 / 32;
     g.ldbits = st.nwT;
@@ -297,18 +307,33 @@ void em_stats_impl(ppca_b200_ctx *ctx, const SampleStore &st, const double *w, c
     g.M = m.s.d;
     g.Nq = m.s.kkp;
     g.kblocks = (int)(round_up(rows, 32) / 32);
+    g.kcols = 32 * g.kblocks;
     g.accumulate = 1;
     g.splitk = splitk < g.kblocks ? splitk : (g.kblocks > 0 ? g.kblocks : 1);
-    g.partials = g.splitk > 1 ? ctx->part_bg.p : nullptr;
+    if (splitk > 1 && g.splitk < 2) g.splitk = 2 <= g.kblocks ? 2 : 1;
+    g.partials = splitk > 1 ? ctx->part_bg.p : nullptr;
+    g.defer_reduce = 1;
+    if (splitk > 1 && g.splitk == 1) {  // degenerate last chunk: accumulate straight into the statistics
+      g.partials = nullptr;
+      g.defer_reduce = 0;
+    }
     ctx->span_begin(FAM_MOMENT);
     launch_bitgemm(L, g);
     ctx->span_end();
     ctx->span_begin(FAM_CROSS);
-    launch_cross_resid(L, st, row0, rows, m, ctx->YZ.p, ctx->WZ.p, w + row0, stats_dev + lay.offB,
-                       stats_dev + lay.offTdev, stats_dev + lay.offTotals, stats_dev + lay.offScalars, ctx->part_cr.p,
-                       crlen);
+    launch_cross_resid(L, st, row0, rows, m, ctx->YZ.p, ctx->WZ.p, w + row0, ctx->part_cr.p, slabs);
     ctx->span_end();
   }
+  ctx->span_begin(FAM_SOLVE);
+  launch_solve_finish(L, ctx->part_solve.p, stats_dev + lay.offScalars);
+  ctx->span_end();
+  ctx->span_begin(FAM_MOMENT);
+  launch_bitgemm_reduce(L, ctx->part_bg.p, splitk, m.s.d, m.s.kkp, stats_dev + lay.offA, m.s.kkp, 1);
+  ctx->span_end();
+  ctx->span_begin(FAM_CROSS);
+  launch_cross_resid_finish(L, m.s.d, m.s.k, ctx->part_cr.p, slabs, stats_dev + lay.offB, stats_dev + lay.offTdev,
+                            stats_dev + lay.offTotals, stats_dev + lay.offScalars);
+  ctx->span_end();
 }
 
 // Householder QR solve on the host (prior.rs:97-110 smooth_mean uses total_precision.qr().solve)
@@ -824,11 +849,14 @@ int32_t ppca_b200_llk(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int32_t k
     const int64_t chunk = pick_chunk(ctx, st.n_pad, m.s);
     reserve_chunk_ws(ctx, chunk, m.s);
     ctx->stats.reserve(8);
+    ctx->part_solve.reserve((size_t)SOLVE_SLOTS * 4);
     CUDA_CHECK(cudaMemsetAsync(ctx->stats.p, 0, sizeof(double) * 8, ctx->stream));
+    CUDA_CHECK(cudaMemsetAsync(ctx->part_solve.p, 0, sizeof(double) * SOLVE_SLOTS * 4, ctx->stream));
     for (int64_t row0 = 0; row0 < st.n; row0 += chunk) {
       const int rows = (int)((st.n - row0) < chunk ? (st.n - row0) : chunk);
-      e_step_chunk(ctx, st, ds->w.p, row0, rows, m, 0, ctx->llk.p, nullptr, ctx->stats.p);
+      e_step_chunk(ctx, st, ds->w.p, row0, rows, m, 0, ctx->llk.p, nullptr, ctx->part_solve.p);
     }
+    launch_solve_finish(ctx->L(), ctx->part_solve.p, ctx->stats.p);
     double h[8];
     CUDA_CHECK(cudaMemcpyAsync(h, ctx->stats.p, sizeof(double) * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
@@ -928,7 +956,10 @@ int32_t ppca_b200_em_finish(ppca_b200_ctx *ctx, int32_t d, int32_t k, const doub
     REQUIRE(ctx != nullptr && stats_dev != nullptr, "null argument");
     REQUIRE(d >= 1 && k >= 1, "bad shape");
     DeviceGuard g(ctx->device);
+    ctx->profile_reset(false);
     em_finish_impl(ctx, d, k, C, mu, sigma, prior, stats_dev, C_out, mu_out, sigma_out, llk_in, nullptr);
+    ctx->profile_collect();
+    ctx->profile_reset(false);
   });
 }
 

@@ -101,8 +101,10 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) bitgemm_kernel(BitGemmArgs a)
     uint32_t wsh[MI];
 #pragma unroll
     for (int mi = 0; mi < MI; ++mi) wsh[mi] = wcur[mi] >> c;
+    const int smax = min(8, (a.kcols - 32 * (kb_begin + it) + 3) >> 2);  // trims the ragged last K block
 #pragma unroll
     for (int s = 0; s < 8; ++s) {
+      if (s >= smax) break;
       double b[NI];
 #pragma unroll
       for (int ni = 0; ni < NI; ++ni) b[ni] = sB[(4 * s) * LDB + 8 * ni];
@@ -126,7 +128,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) bitgemm_kernel(BitGemmArgs a)
   if (a.splitk > 1) {
     out = a.partials + (int64_t)blockIdx.z * a.M * a.Nq;
     ldo = a.Nq;
-    accumulate = false;
+    accumulate = a.defer_reduce != 0;
   } else {
     out = a.Out;
     ldo = a.ldo;
@@ -210,9 +212,23 @@ static int pick_cfg(int Nq) {
 int bitgemm_pick_splitk(int M, int Nq, int kblocks, int sms) {
   const CfgInfo &c = kCfgs[pick_cfg(Nq)];
   const int64_t tiles = round_up(M, c.BM) / c.BM * (round_up(Nq, c.BN) / c.BN);
-  if (tiles >= sms) return 1;
-  int64_t s = sms / tiles;
   const int64_t max_s = kblocks / 8 > 0 ? kblocks / 8 : 1;  // at least 8 K-blocks (256 rows) per slab
+  if (tiles >= sms) {
+    // one CTA per SM: pick the smallest split that keeps the last wave >= 95% full
+    int best = 1;
+    double best_eff = 0.0;
+    for (int s = 1; s <= 8 && s <= max_s; ++s) {
+      const int64_t ctas = tiles * s;
+      const double eff = (double)ctas / (double)(round_up(ctas, sms));
+      if (eff > best_eff + 1e-9) {
+        best_eff = eff;
+        best = s;
+      }
+      if (eff >= 0.95) return s;
+    }
+    return best;
+  }
+  int64_t s = sms / tiles;
   if (s > max_s) s = max_s;
   return (int)(s < 1 ? 1 : s);
 }
@@ -247,13 +263,18 @@ void launch_bitgemm(const Launcher &L, const BitGemmArgs &a) {
     case 5: launch_cfg<Cfg16>(L, a); break;
     default: launch_cfg<Cfg8>(L, a); break;
   }
-  if (a.splitk > 1) {
-    const int64_t total = (int64_t)a.M * (a.Nq / 2);
-    const int blocks = (int)((total + 255) / 256 < 4 * L.sms ? (total + 255) / 256 : 4 * L.sms);
-    bitgemm_reduce_kernel<<<blocks, 256, 0, L.stream>>>(a.partials, a.splitk, a.M, a.Nq, a.Out, a.ldo, a.accumulate);
-    CUDA_CHECK(cudaGetLastError());
-    ++*L.launch_counter;
-  }
+  if (a.splitk > 1 && !a.defer_reduce)
+    launch_bitgemm_reduce(L, a.partials, a.splitk, a.M, a.Nq, a.Out, a.ldo, a.accumulate);
+}
+
+void launch_bitgemm_reduce(const Launcher &L, const double *partials, int splitk, int M, int Nq, double *Out,
+                           int64_t ldo, int accumulate) {
+  if (splitk <= 1 || M <= 0 || Nq <= 0) return;
+  const int64_t total = (int64_t)M * (Nq / 2);
+  const int blocks = (int)((total + 255) / 256 < 4 * L.sms ? (total + 255) / 256 : 4 * L.sms);
+  bitgemm_reduce_kernel<<<blocks, 256, 0, L.stream>>>(partials, splitk, M, Nq, Out, ldo, accumulate);
+  CUDA_CHECK(cudaGetLastError());
+  ++*L.launch_counter;
 }
 
 }  // namespace ppca

@@ -171,13 +171,18 @@ struct BitGemmArgs {
   int M;                 // rows of Out (bit rows)
   int Nq;                // columns, multiple of 8
   int kblocks;           // number of 32-wide K blocks
+  int kcols;             // valid K columns (<= 32 * kblocks); MMA steps past it are skipped
   int accumulate;        // Out += result (else Out = result)
   double *partials;      // workspace for split-K (may be null when splitk == 1)
   int splitk;
+  int defer_reduce;      // split-K only: partials += result (caller zeroed them) and no reduction is launched;
+                         // the caller runs launch_bitgemm_reduce once after the last chunk
 };
 int bitgemm_pick_splitk(int M, int Nq, int kblocks, int sms);
 size_t bitgemm_partials_len(int M, int Nq, int splitk);
 void launch_bitgemm(const Launcher &L, const BitGemmArgs &a);
+void launch_bitgemm_reduce(const Launcher &L, const double *partials, int splitk, int M, int Nq, double *Out,
+                           int64_t ldo, int accumulate);
 
 // proj.cu : Y[n][a] = sum_i sel(m_ni, x_ni - mu_i) C[i][a] ; nx[n] = sum_i sel(...)^2
 void launch_proj(const Launcher &L, const SampleStore &st, int64_t row0, int rows, const DevModel &m, double *Y,
@@ -198,16 +203,23 @@ struct SolveArgs {
   double *llk;         // rows : out per-sample log-likelihood (nullable)
   double *tn;          // rows : out per-sample tr(Sigma_n G_n) (nullable, mode 2)
   double *cov;         // rows x k x k full covariances (nullable)
-  double *scalars;     // stats scalars to accumulate into (nullable; needs llk): SC_SQERR, SC_LLK, SC_SUMW, SC_NONEMPTY
+  double *part;        // SOLVE_SLOTS x 4 partial sums to accumulate into (nullable; needs llk): w t, w llk, w, #non-empty
   int mode;            // 0 = llk only, 1 = infer (z, cov), 2 = EM (z, W, wz, t)
 };
+enum { SOLVE_SLOTS = 128 };
 void launch_solve(const Launcher &L, const SolveArgs &a);
+// sums the partial slots (fixed order) into scalars[SC_SQERR, SC_LLK, SC_SUMW, SC_NONEMPTY]
+void launch_solve_finish(const Launcher &L, const double *part, double *scalars);
 
 // moments.cu : B += Xc^T (w z) ; residual statistics ; reconstruction writers
+// accumulates into per-(slab, dimension block) partial slots (zeroed by the caller before the first chunk);
+// launch_cross_resid_finish reduces them once, in fixed order, into the statistics buffer
 void launch_cross_resid(const Launcher &L, const SampleStore &st, int64_t row0, int rows, const DevModel &m,
-                        const double *Z, const double *WZ, const double *w, double *statB, double *statTdev,
-                        double *statTotals, double *scalars, double *partials, size_t partials_len);
-size_t cross_resid_partials_len(int d, int k, int rows, int sms);
+                        const double *Z, const double *WZ, const double *w, double *partials, int slabs_alloc);
+void launch_cross_resid_finish(const Launcher &L, int d, int k, const double *partials, int slabs_alloc, double *statB,
+                               double *statTdev, double *statTotals, double *scalars);
+int cross_resid_slabs(int d, int k, int rows, int sms);
+size_t cross_resid_partials_len(int d, int k, int slabs_alloc);
 // out = extrapolate ? (m ? x : C z + mu) : C z + mu ; scale != null multiplies by scale[n*scale_ld] and accumulates
 void launch_reconstruct(const Launcher &L, const SampleStore &st, int64_t row0, int rows, const DevModel &m,
                         const double *Z, int extrapolate, const double *scale, int64_t scale_ld, int accumulate,

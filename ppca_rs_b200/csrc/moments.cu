@@ -47,11 +47,11 @@ struct CrArgs {
   const double *Z, *WZ;  // chunk-local, row pitch kp
   const double *w;       // chunk-local weights
   int d64;               // dblocks * 64
-  double *pB, *pT, *pO, *pD;
+  double *pB, *pT, *pO, *pD;  // per-slab partial slots, accumulated (+=) across chunks
 };
 
 template <int KT, int BS>
-__global__ void __launch_bounds__(256, 1) cross_resid_kernel(CrArgs a) {
+__global__ void __launch_bounds__(256, (KT <= 4 ? 2 : 1)) cross_resid_kernel(CrArgs a) {
   using Cfg = CrCfg<KT, BS>;
   constexpr int LDX = Cfg::LDX, LDZ = Cfg::LDZ, KPP = Cfg::KPP, MI = Cfg::MI, NI = 4;
   extern __shared__ __align__(16) double smem[];
@@ -103,9 +103,9 @@ __global__ void __launch_bounds__(256, 1) cross_resid_kernel(CrArgs a) {
   if (tid < 64) sMu[tid] = (64 * xb + tid < a.d32) ? a.mupad[64 * xb + tid] : 0.0;
 
   // persistent accumulators
-  double accB[KT][2];
+  double accB[2][KT][2];  // two independent accumulator sets (even / odd K steps) to shorten the DMMA chains
 #pragma unroll
-  for (int ni = 0; ni < KT; ++ni) accB[ni][0] = accB[ni][1] = 0.0;
+  for (int ni = 0; ni < KT; ++ni) accB[0][ni][0] = accB[0][ni][1] = accB[1][ni][0] = accB[1][ni][1] = 0.0;
   double tdev[NI][2], tot[NI][2], dev2 = 0.0;
 #pragma unroll
   for (int ni = 0; ni < NI; ++ni) tdev[ni][0] = tdev[ni][1] = tot[ni][0] = tot[ni][1] = 0.0;
@@ -143,11 +143,12 @@ __global__ void __launch_bounds__(256, 1) cross_resid_kernel(CrArgs a) {
     {
       const double *pa = sX + c * LDX + 8 * warp + r;
       const double *pb = sWZ + c * LDZ + r;
-#pragma unroll 4
+#pragma unroll
       for (int s = 0; s < BS / 4; ++s) {
         const double av = pa[(4 * s) * LDX];
 #pragma unroll
-        for (int ni = 0; ni < KT; ++ni) dmma884(accB[ni][0], accB[ni][1], av, pb[(4 * s) * LDZ + 8 * ni]);
+        for (int ni = 0; ni < KT; ++ni)
+          dmma884(accB[s & 1][ni][0], accB[s & 1][ni][1], av, pb[(4 * s) * LDZ + 8 * ni]);
       }
     }
 
@@ -209,7 +210,11 @@ __global__ void __launch_bounds__(256, 1) cross_resid_kernel(CrArgs a) {
 #pragma unroll
     for (int ni = 0; ni < KT; ++ni) {
       const int col = 8 * ni + 2 * c;
-      if (col < a.kp) *reinterpret_cast<double2 *>(pB + col) = make_double2(accB[ni][0], accB[ni][1]);
+      if (col < a.kp) {
+        double2 *o = reinterpret_cast<double2 *>(pB + col);
+        const double2 prev = *o;
+        *o = make_double2(prev.x + (accB[0][ni][0] + accB[1][ni][0]), prev.y + (accB[0][ni][1] + accB[1][ni][1]));
+      }
     }
   }
   double *red = stage0;  // [2][4][64] scratch
@@ -235,13 +240,13 @@ __global__ void __launch_bounds__(256, 1) cross_resid_kernel(CrArgs a) {
   if (tid < 64) {
     const double v = red[tid] + red[64 + tid] + red[128 + tid] + red[192 + tid];
     const double o = red[256 + tid] + red[320 + tid] + red[384 + tid] + red[448 + tid];
-    a.pT[slab * a.d64 + 64 * xb + tid] = v;
-    a.pO[slab * a.d64 + 64 * xb + tid] = o;
+    a.pT[slab * a.d64 + 64 * xb + tid] += v;
+    a.pO[slab * a.d64 + 64 * xb + tid] += o;
   }
   if (tid == 0) {
     double s = 0.0;
     for (int i = 0; i < 8; ++i) s += red[512 + i];
-    a.pD[slab * gridDim.x + xb] = s;
+    a.pD[slab * gridDim.x + xb] += s;
   }
 }
 
@@ -265,28 +270,31 @@ __global__ void cross_resid_reduce_kernel(int slabs, int dblocks, int d64, int d
     statTdev[idx] += s;
     statTotals[idx] += o;
   }
-  if (gtid == 0) {
+  if (blockIdx.x == 0 && threadIdx.x < 32) {  // fixed-order: lane-strided partial sums, then a shuffle tree
     double s = 0.0;
-    for (int z = 0; z < slabs * dblocks; ++z) s += pD[z];
-    scalars[SC_DEV2] += s;
+    for (int z = threadIdx.x; z < slabs * dblocks; z += 32) s += pD[z];
+    s = warp_sum(s);
+    if (threadIdx.x == 0) scalars[SC_DEV2] += s;
   }
 }
 
-static int cr_slabs(int d, int rows, int bs, int sms) {
+static int cr_bs(int kp) { (void)kp; return 32; }
+static int cr_ctas_per_sm(int kp) { return kp <= 32 ? 2 : 1; }
+
+int cross_resid_slabs(int d, int k, int rows, int sms) {
+  Shape s(d, k);
   const int dblocks = (d + 63) / 64;
-  const int ntiles = (rows + bs - 1) / bs;
-  int slabs = sms / dblocks;
+  const int ntiles = (rows + cr_bs(s.kp) - 1) / cr_bs(s.kp);
+  int slabs = sms * cr_ctas_per_sm(s.kp) / dblocks;
   if (slabs < 1) slabs = 1;
   if (slabs > ntiles) slabs = ntiles;
   return slabs < 1 ? 1 : slabs;
 }
-static int cr_bs(int kp) { return kp <= 32 ? 64 : 32; }
 
-size_t cross_resid_partials_len(int d, int k, int rows, int sms) {
+size_t cross_resid_partials_len(int d, int k, int slabs_alloc) {
   Shape s(d, k);
   const int dblocks = (d + 63) / 64, d64 = dblocks * 64;
-  const int slabs = cr_slabs(d, rows, cr_bs(s.kp), sms);
-  return (size_t)slabs * ((size_t)d64 * s.kp + 2 * (size_t)d64 + dblocks);
+  return (size_t)slabs_alloc * ((size_t)d64 * s.kp + 2 * (size_t)d64 + dblocks);
 }
 
 template <int KT, int BS>
@@ -304,31 +312,40 @@ static void launch_cr(const Launcher &L, CrArgs a, int dblocks, int slabs) {
 }
 
 void launch_cross_resid(const Launcher &L, const SampleStore &st, int64_t row0, int rows, const DevModel &m,
-                        const double *Z, const double *WZ, const double *w, double *statB, double *statTdev,
-                        double *statTotals, double *scalars, double *partials, size_t partials_len) {
+                        const double *Z, const double *WZ, const double *w, double *partials, int slabs_alloc) {
   if (rows <= 0) return;
   const int d = m.s.d, kp = m.s.kp;
   REQUIRE(kp <= 128, "state_size %d > 128 is not supported by the cross-moment kernel", m.s.k);
   const int dblocks = (d + 63) / 64, d64 = dblocks * 64;
-  const int bs = cr_bs(kp);
-  const int slabs = cr_slabs(d, rows, bs, L.sms);
-  REQUIRE(partials_len >= (size_t)slabs * ((size_t)d64 * kp + 2 * (size_t)d64 + dblocks), "cross_resid workspace too small");
+  int slabs = cross_resid_slabs(d, m.s.k, rows, L.sms);
+  if (slabs > slabs_alloc) slabs = slabs_alloc;
   CrArgs a;
   a.X = st.X.p; a.ldx = st.ldx; a.mask = st.mask.p; a.dw = st.dw; a.row0 = row0; a.rows = rows;
   a.Cpad = m.C; a.kp = kp; a.d32 = m.s.d32; a.mupad = m.mu; a.Z = Z; a.WZ = WZ; a.w = w; a.d64 = d64;
   a.pB = partials;
-  a.pT = a.pB + (size_t)slabs * d64 * kp;
-  a.pO = a.pT + (size_t)slabs * d64;
-  a.pD = a.pO + (size_t)slabs * d64;
+  a.pT = a.pB + (size_t)slabs_alloc * d64 * kp;
+  a.pO = a.pT + (size_t)slabs_alloc * d64;
+  a.pD = a.pO + (size_t)slabs_alloc * d64;
   const int kt = kp / 8;
-  if (kt <= 1) launch_cr<1, 64>(L, a, dblocks, slabs);
-  else if (kt <= 2) launch_cr<2, 64>(L, a, dblocks, slabs);
-  else if (kt <= 4) launch_cr<4, 64>(L, a, dblocks, slabs);
+  if (kt <= 1) launch_cr<1, 32>(L, a, dblocks, slabs);
+  else if (kt <= 2) launch_cr<2, 32>(L, a, dblocks, slabs);
+  else if (kt <= 4) launch_cr<4, 32>(L, a, dblocks, slabs);
   else if (kt <= 8) launch_cr<8, 32>(L, a, dblocks, slabs);
   else launch_cr<16, 32>(L, a, dblocks, slabs);
+}
+
+void launch_cross_resid_finish(const Launcher &L, int d, int k, const double *partials, int slabs_alloc, double *statB,
+                               double *statTdev, double *statTotals, double *scalars) {
+  Shape s(d, k);
+  const int kp = s.kp;
+  const int dblocks = (d + 63) / 64, d64 = dblocks * 64;
+  const double *pB = partials;
+  const double *pT = pB + (size_t)slabs_alloc * d64 * kp;
+  const double *pO = pT + (size_t)slabs_alloc * d64;
+  const double *pD = pO + (size_t)slabs_alloc * d64;
   const int64_t total = (int64_t)d * kp;
   const int blocks = (int)((total + 255) / 256 < 2 * L.sms ? (total + 255) / 256 : 2 * L.sms);
-  cross_resid_reduce_kernel<<<blocks, 256, 0, L.stream>>>(slabs, dblocks, d64, d, kp, a.pB, a.pT, a.pO, a.pD, statB,
+  cross_resid_reduce_kernel<<<blocks, 256, 0, L.stream>>>(slabs_alloc, dblocks, d64, d, kp, pB, pT, pO, pD, statB,
                                                           statTdev, statTotals, scalars);
   CUDA_CHECK(cudaGetLastError());
   ++*L.launch_counter;

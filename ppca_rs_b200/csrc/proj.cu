@@ -11,7 +11,7 @@ namespace ppca {
 
 template <int NI>
 struct ProjCfg {
-  static constexpr int BM = 128, LDA = 36, STAGES = 3, THREADS = 256;
+  static constexpr int BM = 128, LDA = 36, STAGES = 2, THREADS = 256;
   static constexpr int BN = 8 * NI;
   static constexpr int LDC = BN + ((20 - BN % 16) % 16);
   static constexpr int X_STAGE = BM * LDA, C_STAGE = 32 * LDC;
@@ -19,10 +19,10 @@ struct ProjCfg {
 };
 
 template <int NI>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(256, 2)
     proj_kernel(const double *__restrict__ X, int ldx, const uint32_t *__restrict__ mask, int dw, int64_t row0,
-                const double *__restrict__ Cpad, int kp, const double *__restrict__ mupad, int nkb, double *Y,
-                double *nx) {
+                const double *__restrict__ Cpad, int kp, const double *__restrict__ mupad, int nkb, int d,
+                double *Y, double *nx) {
   using Cfg = ProjCfg<NI>;
   constexpr int BM = Cfg::BM, LDA = Cfg::LDA, LDC = Cfg::LDC, STAGES = Cfg::STAGES, BN = Cfg::BN;
   extern __shared__ __align__(16) double smem[];
@@ -95,8 +95,10 @@ __global__ void __launch_bounds__(256, 1)
     __syncwarp();
     const double *sA = sX + (16 * warp + r) * LDA + c;
     const double *sB = sC + c * LDC + r;
+    const int smax = min(8, (d - 32 * kb + 3) >> 2);
 #pragma unroll
     for (int s = 0; s < 8; ++s) {
+      if (s >= smax) break;
       double a[2], b[NI];
       a[0] = sA[4 * s];
       a[1] = sA[8 * LDA + 4 * s];
@@ -139,7 +141,7 @@ static void launch_proj_ni(const Launcher &L, const SampleStore &st, int64_t row
   }
   dim3 grid((unsigned)((rows + Cfg::BM - 1) / Cfg::BM), (unsigned)((m.s.kp + Cfg::BN - 1) / Cfg::BN));
   proj_kernel<NI><<<grid, 256, Cfg::SMEM, L.stream>>>(st.X.p, st.ldx, st.mask.p, st.dw, row0, m.C, m.s.kp, m.mu,
-                                                      m.s.d32 / 32, Y, nx);
+                                                      m.s.d32 / 32, m.s.d, Y, nx);
   CUDA_CHECK(cudaGetLastError());
   ++*L.launch_counter;
 }

@@ -20,6 +20,19 @@ namespace ppca {
 
 #define LN_2PI 1.8378770664093453
 
+// 1 / x for a positive normal double: hardware seed (about 2^-20) and two Newton steps with a final fused
+// residual correction; relative error at rounding level, no special-case branches.
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  return fma(r, e, r);
+}
+
 struct SolveSmem {
   int ldk;      // odd pitch
   int per_warp; // doubles per warp
@@ -210,15 +223,17 @@ __global__ void __launch_bounds__(256, (KP == 32 ? 2 : (KP == 16 ? 3 : 4))) solv
 
     const double *st = stage + sub * kkp;
     const bool live = li < k && !empty;
+    // row li of the packed symmetric matrix: (li, j >= li) sits at up + j, (j < li, li) at j (2k - j - 1) / 2 + li
+    const int up = tri_row_off(li, k) - li;
     double A[KP];
 #pragma unroll
-    for (int j = 0; j < KP; ++j) {
-      double v = (j == li) ? 1.0 : 0.0;
-      if (live && j < k) {
-        const int lo = li < j ? li : j, hi = li < j ? j : li;
-        v = st[tri_row_off(lo, k) + hi - lo] + (j == li ? s2 : 0.0);
-      }
-      A[j] = v;
+    for (int j = 0; j < KP; ++j) {  // branch-free: clamped index, unconditional load, select
+      int idx = (j >= li) ? up + j : ((j * (2 * k - j - 1)) >> 1) + li;
+      const bool use = live && j < k;
+      idx = use ? idx : 0;
+      const double g = st[idx];
+      const double unit = (j == li) ? 1.0 : 0.0;
+      A[j] = use ? fma(unit, s2, g) : unit;
     }
 
     double mypiv = 1.0, myinv = 1.0;
@@ -229,7 +244,7 @@ __global__ void __launch_bounds__(256, (KP == 32 ? 2 : (KP == 16 ? 3 : 4))) solv
       __syncwarp();
       const double *cs = cb + sub * KP;
       const double dpp = cs[p];
-      const double inv = 1.0 / dpp;
+      const double inv = fast_rcp(dpp);
       if (li == p) {
         mypiv = dpp;
         myinv = inv;
@@ -281,15 +296,14 @@ __global__ void __launch_bounds__(256, (KP == 32 ? 2 : (KP == 16 ? 3 : 4))) solv
         if (j < k) cv[j] = empty ? (j == li ? 1.0 : 0.0) : s2 * A[j];
     }
     if (a.mode == 2) {
-      // t = tr(Sigma G) = sigma^2 sum_ij M^{-1}_ij G_ij  (G still in the staging buffer)
+      // t = tr(Sigma G) = sigma^2 tr(M^{-1} (M - sigma^2 I)) = sigma^2 sum_i (1 - sigma^2 M^{-1}_ii)
       double tpart = 0.0;
-      if (live) {
+      {
+        double diag = 0.0;
 #pragma unroll
         for (int j = 0; j < KP; ++j)
-          if (j < k) {
-            const int lo = li < j ? li : j, hi = li < j ? j : li;
-            tpart = fma(A[j], st[tri_row_off(lo, k) + hi - lo], tpart);
-          }
+          if (j == li) diag = A[j];
+        if (live) tpart = fma(-s2, diag, 1.0);
       }
 #pragma unroll
       for (int o = KP / 2; o > 0; o >>= 1) tpart += __shfl_xor_sync(0xffffffffu, tpart, o);
@@ -297,11 +311,12 @@ __global__ void __launch_bounds__(256, (KP == 32 ? 2 : (KP == 16 ? 3 : 4))) solv
       __syncwarp();  // everyone is done reading G and zb is visible
       // W = w (z z^T + sigma^2 M^{-1}), upper triangle of row li, packed in place
       if (li < k) {
-        double *so = stage + sub * kkp + tri_row_off(li, k) - li;
+        double *so = stage + sub * kkp + up;
         const double *zs = zb + sub * KP;
+        const double ws2 = empty ? 0.0 : w * s2, wzi = empty ? 0.0 : w * zi;
 #pragma unroll
         for (int j = 0; j < KP; ++j)
-          if (j >= li && j < k) so[j] = empty ? 0.0 : w * fma(zi, zs[j], s2 * A[j]);
+          if (j >= li && j < k) so[j] = fma(wzi, zs[j], ws2 * A[j]);
       }
       __syncwarp();
       for (int q = lane * 2; q < SPW * kkp; q += 64)
@@ -344,15 +359,16 @@ __global__ void __launch_bounds__(256, 1) solve_reg64_kernel(SolveArgs a) {
     pair_sync(bar_id);
 
     const bool live = li < k && !empty;
+    const int up = tri_row_off(li, k) - li;
     double A[KP];
 #pragma unroll
-    for (int j = 0; j < KP; ++j) {
-      double v = (j == li) ? 1.0 : 0.0;
-      if (live && j < k) {
-        const int lo = li < j ? li : j, hi = li < j ? j : li;
-        v = stage[tri_row_off(lo, k) + hi - lo] + (j == li ? s2 : 0.0);
-      }
-      A[j] = v;
+    for (int j = 0; j < KP; ++j) {  // branch-free: clamped index, unconditional load, select
+      int idx = (j >= li) ? up + j : ((j * (2 * k - j - 1)) >> 1) + li;
+      const bool use = live && j < k;
+      idx = use ? idx : 0;
+      const double g = stage[idx];
+      const double unit = (j == li) ? 1.0 : 0.0;
+      A[j] = use ? fma(unit, s2, g) : unit;
     }
 
     double mypiv = 1.0, myinv = 1.0;
@@ -362,7 +378,7 @@ __global__ void __launch_bounds__(256, 1) solve_reg64_kernel(SolveArgs a) {
       cb[li] = (li < p) ? -A[p] * myinv : A[p];
       pair_sync(bar_id);
       const double dpp = cb[p];
-      const double inv = 1.0 / dpp;
+      const double inv = fast_rcp(dpp);
       if (li == p) {
         mypiv = dpp;
         myinv = inv;
@@ -409,23 +425,23 @@ __global__ void __launch_bounds__(256, 1) solve_reg64_kernel(SolveArgs a) {
     }
     if (a.mode == 2) {
       double tpart = 0.0;
-      if (live) {
+      {
+        double diag = 0.0;
 #pragma unroll
         for (int j = 0; j < KP; ++j)
-          if (j < k) {
-            const int lo = li < j ? li : j, hi = li < j ? j : li;
-            tpart = fma(A[j], stage[tri_row_off(lo, k) + hi - lo], tpart);
-          }
+          if (j == li) diag = A[j];
+        if (live) tpart = fma(-s2, diag, 1.0);
       }
       tpart = warp_sum(tpart);
       if (lane == 0) red[4 + (wi & 1)] = tpart;
       pair_sync(bar_id);  // all reads of G done, partial traces visible
       if (a.tn && li == 0 && row < a.rows) a.tn[row] = empty ? 0.0 : s2 * (red[4] + red[5]);
       if (li < k) {
-        double *so = stage + tri_row_off(li, k) - li;
+        double *so = stage + up;
+        const double ws2 = empty ? 0.0 : w * s2, wzi = empty ? 0.0 : w * zi;
 #pragma unroll
         for (int j = 0; j < KP; ++j)
-          if (j >= li && j < k) so[j] = empty ? 0.0 : w * fma(zi, zb[j], s2 * A[j]);
+          if (j >= li && j < k) so[j] = fma(wzi, zb[j], ws2 * A[j]);
       }
       pair_sync(bar_id);
       for (int q = li * 2; q < kkp; q += 128)
@@ -463,13 +479,16 @@ static void launch_solve_reg(const Launcher &L, const SolveArgs &a) {
   ++*L.launch_counter;
 }
 
-// fixed-order reduction of the per-sample scalars of one chunk into the statistics scalars
-__global__ void __launch_bounds__(1024) solve_reduce_kernel(int rows, const double *__restrict__ llk,
-                                                            const double *__restrict__ tn, const int *__restrict__ dn,
-                                                            const double *__restrict__ w, double *scalars) {
-  __shared__ double sh[4][32];
+// Per-sample scalars of one chunk -> SOLVE_SLOTS partial slots (block b always owns slot b and rows
+// [b R, (b+1) R) of the chunk, so the summation order is fixed run to run); launch_solve_finish sums the slots.
+__global__ void __launch_bounds__(256) solve_reduce_kernel(int rows, const double *__restrict__ llk,
+                                                           const double *__restrict__ tn, const int *__restrict__ dn,
+                                                           const double *__restrict__ w, double *part) {
+  __shared__ double sh[4][8];
+  const int per = (rows + gridDim.x - 1) / gridDim.x;
+  const int lo = blockIdx.x * per, hi = min(rows, lo + per);
   double v[4] = {0.0, 0.0, 0.0, 0.0};
-  for (int i = threadIdx.x; i < rows; i += 1024) {
+  for (int i = lo + threadIdx.x; i < hi; i += 256) {
     const double wi = w ? w[i] : 1.0;
     if (tn) v[0] = fma(wi, tn[i], v[0]);
     if (llk) v[1] = fma(wi, llk[i], v[1]);
@@ -483,16 +502,27 @@ __global__ void __launch_bounds__(1024) solve_reduce_kernel(int rows, const doub
     if (lane == 0) sh[j][wid] = v[j];
   }
   __syncthreads();
-  if (wid == 0) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      double s = warp_sum(sh[j][lane]);
-      if (lane == 0) {
-        const int slot = j == 0 ? SC_SQERR : j == 1 ? SC_LLK : j == 2 ? SC_SUMW : SC_NONEMPTY;
-        scalars[slot] += s;
-      }
-    }
+  if (threadIdx.x < 4) {
+    double s = 0.0;
+    for (int i = 0; i < 8; ++i) s += sh[threadIdx.x][i];
+    part[blockIdx.x * 4 + threadIdx.x] += s;
   }
+}
+
+__global__ void solve_finish_kernel(const double *__restrict__ part, double *scalars) {
+  if (threadIdx.x < 4) {
+    double s = 0.0;
+    for (int b = 0; b < SOLVE_SLOTS; ++b) s += part[b * 4 + threadIdx.x];
+    const int j = threadIdx.x;
+    const int slot = j == 0 ? SC_SQERR : j == 1 ? SC_LLK : j == 2 ? SC_SUMW : SC_NONEMPTY;
+    scalars[slot] += s;
+  }
+}
+
+void launch_solve_finish(const Launcher &L, const double *part, double *scalars) {
+  solve_finish_kernel<<<1, 32, 0, L.stream>>>(part, scalars);
+  CUDA_CHECK(cudaGetLastError());
+  ++*L.launch_counter;
 }
 
 static void launch_solve_generic(const Launcher &L, const SolveArgs &a) {
@@ -526,8 +556,8 @@ void launch_solve(const Launcher &L, const SolveArgs &a) {
   else if (a.s.k <= 32) launch_solve_reg<32>(L, a);
   else if (a.s.k <= 64) launch_solve_reg64(L, a);
   else launch_solve_generic(L, a);
-  if (a.scalars) {
-    solve_reduce_kernel<<<1, 1024, 0, L.stream>>>(a.rows, a.llk, a.tn, a.dn, a.w, a.scalars);
+  if (a.part) {
+    solve_reduce_kernel<<<SOLVE_SLOTS, 256, 0, L.stream>>>(a.rows, a.llk, a.tn, a.dn, a.w, a.part);
     CUDA_CHECK(cudaGetLastError());
     ++*L.launch_counter;
   }
