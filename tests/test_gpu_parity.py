@@ -253,3 +253,98 @@ def test_trainer_and_pickle(pk, capsys):
     mix = pk.PPCAMixTrainer(ds).train(n_models=2, state_size=2, n_iters=3, quiet=True)
     assert pickle.loads(pickle.dumps(mix)).llk(ds) == mix.llk(ds)
     assert mix.n_parameters == sum(m.n_parameters for m in mix.models) + 1
+
+
+# ---- committed golden vectors (tests/golden, made by tests/golden/make_golden.py) -----------------------
+@pytest.mark.parametrize("name", ["toy_d3_k2", "ragged_d37_k5", "c2shape_d200_k16"])
+def test_golden_single(pk, name):
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+    X, w = g["X"], g["w"]
+    ds = pk.Dataset(X, w)
+    model = pk.PPCAModel(float(g["s0"]), g["C0"], g["mu0"])
+    assert rel_err(model.llks(ds), g["llks0"]) < TOL
+    inf = model.infer(ds)
+    assert rel_err(inf.states(), g["Z0"]) < TOL and rel_err(np.stack(inf.covariances()), g["COV0"]) < TOL
+    ex = model.extrapolate(ds).numpy()
+    fin = np.isfinite(X)
+    assert np.array_equal(ex[fin], X[fin]) and rel_err(ex, g["extrapolate0"]) < TOL
+    C, mu, s = g["C0"], g["mu0"], float(g["s0"])
+    for it in range(g["C_traj"].shape[0]):
+        new, llk = pk.PPCAModel(s, C, mu)._iterate(ds, None)
+        assert abs(llk - float(g["llk_traj"][it])) < TOL * abs(llk)
+        # the golden trajectory carries the reference's own cancellation noise (see assert_close); at these
+        # sigma values it stays below ~3e-9
+        assert rel_err(new.transform, g["C_traj"][it]) < 5e-9 and rel_err(new.mean, g["mu_traj"][it]) < 5e-9
+        assert abs(new.isotropic_noise - float(g["s_traj"][it])) < 5e-9 * new.isotropic_noise
+        C, mu, s = g["C_traj"][it], g["mu_traj"][it], float(g["s_traj"][it])
+
+
+def test_golden_mixture(pk):
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mix_d12_k232.npz"))
+    ds = pk.Dataset(g["X"], g["w"])
+    m = len(g["ks"])
+    mix = pk.PPCAMix([pk.PPCAModel(float(g[f"s0_{j}"]), g[f"C0_{j}"], g[f"mu0_{j}"]) for j in range(m)], g["logw0"])
+    assert rel_err(mix.llks(ds), g["llks0"]) < TOL
+    assert np.max(np.abs(mix.infer_cluster(ds) - g["logpost0"])) < 1e-9
+    assert rel_err(mix.extrapolate(ds).numpy(), g["extrapolate0"]) < TOL
+    new, llk = mix._iterate(ds, None)
+    assert abs(llk - float(g["llk_0"])) < TOL * abs(llk)
+    assert np.max(np.abs(new.log_weights - g["logw_0"])) < 1e-9
+    for j, got in enumerate(new.models):
+        assert rel_err(got.transform, g[f"C_0_{j}"]) < 5e-9
+
+
+# ---- the sharded path through the C ABI: virtual shards on one GPU --------------------------------------
+def test_virtual_shards_equal_single_pass(pk, orc):
+    """ppca_b200_em_stats on R row blocks, buffers summed in rank order (what the NCCL all-reduce does),
+    then ppca_b200_em_finish == one ppca_b200_iterate on the whole dataset."""
+    import torch
+    from ppca_rs_b200.distributed import CudaEngine, shard_bounds
+    n, d, k = 5000, 90, 12
+    X, C0, mu0, s0 = _case(n, d, k, 0.25, seed=21)
+    w = np.random.default_rng(2).random(n) + 0.5
+    model = pk.PPCAModel(s0, C0, mu0)
+    whole = pk.Dataset(X, w)
+    want, want_llk = model._iterate(whole, None)
+    eng = CudaEngine(pk.get_context())
+    for world in (2, 3):
+        total = None
+        for r in range(world):
+            lo, hi = shard_bounds(n, world, r)
+            st = eng.new_stats(d, k)
+            eng.em_stats(pk.Dataset(X[lo:hi], w[lo:hi]), model, st)
+            torch.cuda.synchronize()
+            total = st.clone() if total is None else total + st
+        got, llk = eng.em_finish(model, None, total)
+        assert rel_err(got.transform, want.transform) < 1e-12 and rel_err(got.mean, want.mean) < 1e-12
+        assert abs(got.isotropic_noise - want.isotropic_noise) < 1e-12 * want.isotropic_noise
+        assert abs(llk - want_llk) < 1e-12 * abs(want_llk)
+
+
+# ---- full-size properties (BASELINE configs[1]: N=1M, d=200, k=16, 20% missing) ---------------------------
+def test_full_size_properties(pk):
+    n, d, k = 1_000_000, 200, 16
+    ds = pk.Dataset.synthetic(n, d, k, 0.1, 0.2, seed=20240531)
+    assert len(ds) == n and ds.output_size() == d and ds.empty_dimensions() == []
+    rng = np.random.default_rng(1)
+    model = pk.PPCAModel(1.0, rng.standard_normal((d, k)), np.zeros(d))
+    llks = []
+    for _ in range(4):
+        model, llk = model._iterate(ds, None)
+        llks.append(llk)
+    assert all(b >= a for a, b in zip(llks, llks[1:]))                  # EM never decreases the llk (:263-265)
+    assert abs(model.llk(ds) - float(np.sum(model.llks(ds)))) < 1e-9 * abs(llks[-1])   # llk == sum of llks
+    canon = model.to_canonical()
+    assert abs(canon.llk(ds) - model.llk(ds)) < 1e-9 * abs(llks[-1])   # :395-397
+    head = ds._slice(0, 4096)
+    x = head.numpy()
+    ex = model.extrapolate(head).numpy()
+    fin = np.isfinite(x)
+    assert 0.78 < fin.mean() < 0.82                                     # Bernoulli(0.8) mask
+    assert np.array_equal(ex[fin], x[fin]) and np.isfinite(ex).all()    # observed slots untouched (:246-247)
+    sm = model.smooth(head).numpy()
+    assert np.array_equal(ex[~fin], sm[~fin])                           # extrapolate = choose(x, smoothed)
+    # idempotence: smoothing a fully observed reconstruction of rank k with tiny noise moves it very little
+    assert np.sqrt(np.mean((sm[fin] - x[fin]) ** 2)) < 5 * model.isotropic_noise

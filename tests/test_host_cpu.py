@@ -1,0 +1,207 @@
+"""CPU tests (no GPU): C ABI surface, host-side mirror logic, serialisation, sharding plumbing over gloo."""
+import ctypes
+import os
+import re
+import socket
+import struct
+
+import numpy as np
+import pytest
+
+from helpers import init_model, make_data, rel_err
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ---- the C ABI -----------------------------------------------------------------------------------
+def _header_symbols():
+    text = open(os.path.join(ROOT, "include", "ppca_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ppca_b200_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from ppca_rs_b200 import _native as nat
+    lib = ctypes.CDLL(nat.LIB_PATH)
+    syms = _header_symbols()
+    assert len(syms) >= 38
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/ppca_b200.h but not exported"
+    assert sorted(nat._PROTOTYPES) == syms            # the ctypes binding covers the whole header
+    assert nat.lib().ppca_b200_abi_version() == 1
+
+
+def test_stats_len_matches_python_layout():
+    from ppca_rs_b200 import _native as nat
+    from ppca_rs_b200.distributed import stats_len
+    for d, k in [(3, 2), (200, 16), (2048, 64), (37, 5), (512, 32), (1024, 48)]:
+        assert nat.lib().ppca_b200_em_stats_len(d, k) == stats_len(d, k)
+    assert nat.lib().ppca_b200_em_stats_len(0, 4) == 0
+
+
+def test_no_cpu_fallback():
+    """Without a device every compute entry point fails loudly (never routes to a CPU path)."""
+    import ppca_rs_b200 as pk
+    if pk.device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(pk.NativeError):
+        pk.Dataset(np.zeros((4, 3)))
+    with pytest.raises(pk.NativeError):
+        pk.Context(0)
+
+
+def test_product_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "ppca_rs_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                assert "oracle" not in open(os.path.join(dirpath, f)).read().replace("test oracle", ""), f
+
+
+# ---- host-side model logic ------------------------------------------------------------------------
+def test_model_constructor_and_getters():
+    import ppca_rs_b200 as pk
+    C = np.arange(6.0).reshape(3, 2)
+    m = pk.PPCAModel(isotropic_noise=0.1, transform=C, mean=np.array([[0.0], [1.0], [0.0]]))  # examples/toy_model.py
+    assert m.output_size == 3 and m.state_size == 2 and m.n_parameters == 1 + 6 + 3   # ppca_model.rs:107-109
+    assert m.mean.shape == (3,) and np.array_equal(m.mean, [0, 1, 0])
+    assert np.array_equal(pk.PPCAModel(0.1, C, np.array([[0.0, 1.0, 0.0]])).mean, [0, 1, 0])  # 1 x n accepted
+    with pytest.raises(ValueError):
+        pk.PPCAModel(0.1, C, np.zeros((3, 3)))       # src/utils.rs:17-21 panics on a non-vector
+    assert np.allclose(m.singular_values, np.sqrt(np.linalg.norm(C, axis=0)))  # ppca_model.rs:113-121 quirk
+    assert "PPCAModel(isotropic_noise=0.1" in repr(m)
+
+
+def test_to_canonical_matches_oracle_and_reference_rules():
+    import ppca_rs_b200 as pk
+    from oracle import oracle as orc
+    rng = np.random.default_rng(0)
+    C = rng.standard_normal((30, 5))
+    canon = pk.PPCAModel(0.3, C, np.zeros(30)).to_canonical()
+    assert rel_err(canon.transform, orc.to_canonical(C)) < 1e-10
+    assert np.all(canon.transform.sum(axis=0) >= 0)
+    assert canon.isotropic_noise == 0.3
+
+
+def test_prior_validation():
+    import ppca_rs_b200 as pk
+    p = pk.Prior()
+    with pytest.raises(ValueError):
+        p.with_isotropic_noise_prior(-1.0, 1.0)      # prior.rs:50
+    with pytest.raises(ValueError):
+        p.with_transformation_precision(-0.1)        # prior.rs:61
+    with pytest.raises(ValueError):
+        p.with_mean_prior(np.zeros(3), np.eye(4))    # prior.rs:33-34
+    q = p.with_mean_prior(np.zeros((1, 3)), 2.0 * np.eye(3)).with_transformation_precision(0.5)
+    assert p.mean is None and q.transformation_precision == 0.5   # builder returns new objects
+    assert np.allclose(q.mean_precision, 0.5 * np.eye(3))
+
+
+def test_mix_constructor():
+    import ppca_rs_b200 as pk
+    m1 = pk.PPCAModel(1.0, np.ones((4, 2)), np.zeros(4))
+    m2 = pk.PPCAModel(1.0, np.ones((4, 3)), np.zeros(4))
+    mix = pk.PPCAMix([m1, m2], np.log([1.0, 3.0]))
+    assert np.allclose(mix.weights, [0.25, 0.75])                 # mix.rs:69 log-softmax normalisation
+    assert mix.state_sizes == [2, 3] and mix.output_size == 4
+    assert mix.n_parameters == m1.n_parameters + m2.n_parameters + 1   # mix.rs:96-104
+    with pytest.raises(ValueError):
+        pk.PPCAMix([], [])
+    with pytest.raises(ValueError):
+        pk.PPCAMix([m1, pk.PPCAModel(1.0, np.ones((5, 2)), np.zeros(5))], [0.0, 0.0])
+
+
+# ---- bincode layouts (src/python_bindings.rs:66-79,388-401,571-584) --------------------------------
+def test_bincode_model_layout_and_roundtrip():
+    import pickle
+    import ppca_rs_b200 as pk
+    C = np.array([[1.0, 2.0], [3.0, 4.0], [5.0, 6.0]])
+    m = pk.PPCAModel(0.5, C, np.array([7.0, 8.0, 9.0]))
+    raw = m.dump()
+    # f64 sigma | DMatrix: u64 len, column-major data, u64 nrows, u64 ncols | DVector: u64 len, data, u64 nrows
+    expect = struct.pack("<d", 0.5) + struct.pack("<Q", 6) + struct.pack("<6d", 1, 3, 5, 2, 4, 6) + struct.pack("<QQ", 3, 2)
+    expect += struct.pack("<Q", 3) + struct.pack("<3d", 7, 8, 9) + struct.pack("<Q", 3)
+    assert raw == expect
+    back = pk.PPCAModel.load(raw)
+    assert np.array_equal(back.transform, C) and back.isotropic_noise == 0.5 and np.array_equal(back.mean, m.mean)
+    assert np.array_equal(pickle.loads(pickle.dumps(m)).transform, C)
+    with pytest.raises(Exception):
+        pk.PPCAModel.load(raw[:-3])
+    mix = pk.PPCAMix([m, m], [0.0, 0.0])
+    again = pk.PPCAMix.load(mix.dump())
+    assert np.allclose(again.log_weights, mix.log_weights) and np.array_equal(again.models[1].transform, C)
+    assert mix.dump()[:16] == struct.pack("<QQ", 3, 2)            # output_size, number of models
+
+
+def test_bincode_dataset_layout():
+    from ppca_rs_b200 import bincode
+    X = np.array([[1.0, np.nan, 3.0], [np.nan, np.nan, 6.0]])
+    raw = bincode.dump_dataset(X, np.array([1.0, 2.0]))
+    # Vec len | per sample: DVector (len, data, nrows) + BitVec (n blocks, u32 blocks LSB-first, nbits) | weights
+    assert raw[:8] == struct.pack("<Q", 2)
+    first_mask = raw[8 + 8 + 24 + 8:8 + 8 + 24 + 8 + 8 + 4 + 8]
+    assert first_mask == struct.pack("<Q", 1) + struct.pack("<I", 0b101) + struct.pack("<Q", 3)
+    x2, w2 = bincode.load_dataset(raw)
+    assert np.array_equal(np.isnan(x2), np.isnan(X)) and np.array_equal(x2[np.isfinite(X)], X[np.isfinite(X)])
+    assert np.array_equal(w2, [1.0, 2.0])
+
+
+# ---- sharding plumbing ------------------------------------------------------------------------------
+def test_shard_bounds_cover_everything():
+    from ppca_rs_b200.distributed import shard_bounds
+    for n in (0, 1, 7, 100, 1_000_003):
+        for world in (1, 2, 3, 8):
+            bounds = [shard_bounds(n, world, r) for r in range(world)]
+            assert bounds[0][0] == 0 and bounds[-1][1] == n
+            assert all(bounds[i][1] == bounds[i + 1][0] for i in range(world - 1))
+            sizes = [hi - lo for lo, hi in bounds]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _gloo_worker(rank, world, port, X, w, C0, mu0, s0, iters, out):
+    import torch.distributed as dist
+    from numpy_engine import HostShard, NumpyEngine
+    from ppca_rs_b200.distributed import ShardedPPCA, shard_bounds
+    from ppca_rs_b200.model import PPCAModel
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, hi = shard_bounds(X.shape[0], world, rank)
+    state = ShardedPPCA(None, HostShard(X[lo:hi], w[lo:hi]), PPCAModel(s0, C0, mu0), group=dist, engine=NumpyEngine())
+    llks = [state.step() for _ in range(iters)]
+    if rank == 0:
+        np.savez(out, C=state.model.transform, mu=state.model.mean, s=state.model.isotropic_noise, llk=np.array(llks))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_em_world_size_2_gloo(tmp_path):
+    """Two gloo ranks, each with half of the rows: local statistics -> all-reduce(SUM) -> replicated finish must
+    equal the single-process EM on the whole dataset (every statistic is additive over samples)."""
+    import torch.multiprocessing as mp
+    from oracle import oracle as orc
+    n, d, k, iters = 301, 14, 3, 3
+    X = make_data(n, d, k, 0.25, seed=12, empty_rows=(5,))
+    w = np.random.default_rng(1).random(n) + 0.5
+    C0, mu0, s0 = init_model(d, k)
+    out = str(tmp_path / "rank0.npz")
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    mp.spawn(_gloo_worker, args=(2, _free_port(), X, w, C0, mu0, s0, iters, out), nprocs=2, join=True)
+    got = np.load(out)
+    C, mu, s = C0, mu0, s0
+    llks = []
+    with orc.stable():
+        for _ in range(iters):
+            llks.append(orc.llk(X, w, C, mu, s))
+            C, mu, s = orc.iterate(X, w, C, mu, s)
+    assert rel_err(got["C"], C) < 1e-9 and rel_err(got["mu"], mu) < 1e-9
+    assert abs(float(got["s"]) - s) < 1e-9 * s
+    assert rel_err(got["llk"], np.array(llks)) < 1e-10
