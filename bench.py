@@ -121,9 +121,9 @@ def init_params(d, k, seed):
 # reference arm: CPU restatement on the host cores
 # ------------------------------------------------------------------------------------------------
 def cpu_sample_rows(wl):
-    # about 10-30 s of CPU work per step at ~2e3 samples*iters/s/core for c2-like shapes
+    # about 10 s of CPU work per step on ~16-24 host cores (measured ~1.6e5 samples*iters/s at c2)
     cost = flops_per_sample_iter(wl["d"], wl["k"]) * max(1, wl["m"])
-    return int(max(2_000, min(200_000, 2.5e10 / cost)))
+    return int(max(2_000, min(wl["n"], 2.0e11 / cost)))
 
 
 def host_sample(wl, rows, seed):
