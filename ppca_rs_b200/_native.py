@@ -52,6 +52,7 @@ _PROTOTYPES = {
     "ppca_b200_ctx_destroy": (C.c_int32, [c_ctx_p]),
     "ppca_b200_ctx_synchronize": (C.c_int32, [c_ctx_p]),
     "ppca_b200_ctx_set_chunk": (C.c_int32, [c_ctx_p, C.c_int64]),
+    "ppca_b200_ctx_set_gemm": (C.c_int32, [c_ctx_p, C.c_int32, C.c_int32]),
     "ppca_b200_ctx_launch_count": (C.c_int32, [c_ctx_p, C.POINTER(C.c_int64)]),
     "ppca_b200_ctx_set_profiling": (C.c_int32, [c_ctx_p, C.c_int32]),
     "ppca_b200_ctx_last_profile": (C.c_int32, [c_ctx_p, c_dp]),
@@ -162,6 +163,10 @@ class Context:
 
     def set_chunk(self, chunk: int) -> None:
         check(lib().ppca_b200_ctx_set_chunk(self._h, int(chunk)))
+
+    def set_gemm(self, mode: str, slices: int = 7) -> None:
+        """'dmma' (FP64 tensor cores) or 'int8' (exact int8-sliced evaluation, see include/ppca_b200.h)."""
+        check(lib().ppca_b200_ctx_set_gemm(self._h, {"dmma": 0, "int8": 1}[mode], int(slices)))
 
     def launch_count(self) -> int:
         out = C.c_int64(0)

@@ -5,6 +5,7 @@
 // Chunked over samples so that the E-step intermediates (packed Gram / second-moment rows) are O(chunk).
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <new>
@@ -29,6 +30,11 @@ struct ppca_b200_ctx {
   int sms = 148;
   int64_t launches = 0;
   int64_t chunk = 0;  // 0 = automatic
+  int gemm_mode = 0;  // 0 = DMMA, 1 = int8-sliced (ibitgemm.cu)
+  int slices = 7;
+  DevBuf<int8_t> KsymQ, WQ;
+  DevBuf<double> KsymScale, WScale;
+  DevBuf<unsigned long long> colmax;
   // model staging
   DevBuf<double> Cdense, mudense, Cpad, mupad, Ksym, logw;
   // chunk workspaces
@@ -208,6 +214,14 @@ DevModel stage_model(ppca_b200_ctx *ctx, int d, int k, const double *C, const do
                              ctx->stream));
   ctx->span_begin(FAM_KSYM);
   launch_prepare_model(ctx->L(), ctx->Cdense.p, ctx->mudense.p, d, k, ctx->Cpad.p, ctx->mupad.p, ctx->Ksym.p);
+  if (ctx->gemm_mode == 1) {
+    const int kblocks = s.d32 / 32;
+    ctx->KsymQ.reserve(sliced_bytes(kblocks, s.kkp, ctx->slices));
+    ctx->KsymScale.reserve((size_t)s.kkp);
+    ctx->colmax.reserve((size_t)s.kkp);
+    launch_slice(ctx->L(), ctx->Ksym.p, s.kkp, d, s.kkp, kblocks, ctx->slices, ctx->KsymQ.p, ctx->KsymScale.p,
+                 ctx->colmax.p);
+  }
   ctx->span_end();
   DevModel m;
   m.s = s;
@@ -232,23 +246,42 @@ void e_step_chunk(ppca_b200_ctx *ctx, const SampleStore &st, const double *w, in
                   const DevModel &m, int mode, double *llk_out, double *cov_out, double *solve_part) {
   const Launcher L = ctx->L();
   const int rows_pad = (int)round_up(rows, 256);
-  BitGemmArgs g;
-  g.bits = st.mask.p + row0 * st.dw;
-  g.ldbits = st.dw;
-  g.Bmat = m.Ksym;
-  g.ldb = m.s.kkp;
-  g.Out = ctx->GW.p;
-  g.ldo = m.s.kkp;
-  g.M = rows;
-  g.Nq = m.s.kkp;
-  g.kblocks = m.s.d32 / 32;
-  g.kcols = m.s.d;
-  g.accumulate = 0;
-  g.partials = nullptr;
-  g.splitk = 1;
-  g.defer_reduce = 0;
   ctx->span_begin(FAM_GRAM);
-  launch_bitgemm(L, g);
+  if (ctx->gemm_mode == 1) {
+    IBitGemmArgs g;
+    g.bits = st.mask.p + row0 * st.dw;
+    g.ldbits = st.dw;
+    g.Bq = ctx->KsymQ.p;
+    g.scale = ctx->KsymScale.p;
+    g.T = ctx->slices;
+    g.Out = ctx->GW.p;
+    g.ldo = m.s.kkp;
+    g.M = rows;
+    g.Nq = m.s.kkp;
+    g.kblocks = m.s.d32 / 32;
+    g.accumulate = 0;
+    g.partials = nullptr;
+    g.splitk = 1;
+    g.defer_reduce = 0;
+    launch_ibitgemm(L, g);
+  } else {
+    BitGemmArgs g;
+    g.bits = st.mask.p + row0 * st.dw;
+    g.ldbits = st.dw;
+    g.Bmat = m.Ksym;
+    g.ldb = m.s.kkp;
+    g.Out = ctx->GW.p;
+    g.ldo = m.s.kkp;
+    g.M = rows;
+    g.Nq = m.s.kkp;
+    g.kblocks = m.s.d32 / 32;
+    g.kcols = m.s.d;
+    g.accumulate = 0;
+    g.partials = nullptr;
+    g.splitk = 1;
+    g.defer_reduce = 0;
+    launch_bitgemm(L, g);
+  }
   ctx->span_end();
   ctx->span_begin(FAM_PROJ);
   launch_proj(L, st, row0, rows, m, ctx->YZ.p, ctx->nx.p);
@@ -283,8 +316,14 @@ void em_stats_impl(ppca_b200_ctx *ctx, const SampleStore &st, const double *w, c
   const int64_t chunk = pick_chunk(ctx, st.n_pad, m.s);
   reserve_chunk_ws(ctx, chunk, m.s);
   const int kb_chunk = (int)(chunk / 32);
-  const int splitk = bitgemm_pick_splitk(m.s.d, m.s.kkp, kb_chunk, ctx->sms);
+  const int splitk = ctx->gemm_mode == 1 ? ibitgemm_pick_splitk(m.s.d, m.s.kkp, kb_chunk, ctx->sms)
+                                         : bitgemm_pick_splitk(m.s.d, m.s.kkp, kb_chunk, ctx->sms);
   const size_t bglen = bitgemm_partials_len(m.s.d, m.s.kkp, splitk);
+  if (ctx->gemm_mode == 1) {
+    ctx->WQ.reserve(sliced_bytes(kb_chunk, m.s.kkp, ctx->slices));
+    ctx->WScale.reserve((size_t)m.s.kkp);
+    ctx->colmax.reserve((size_t)m.s.kkp);
+  }
   ctx->part_bg.reserve(bglen);
   const int slabs = cross_resid_slabs(m.s.d, m.s.k, (int)chunk, ctx->sms);
   const size_t crlen = cross_resid_partials_len(m.s.d, m.s.k, slabs);
@@ -297,28 +336,47 @@ void em_stats_impl(ppca_b200_ctx *ctx, const SampleStore &st, const double *w, c
   for (int64_t row0 = 0; row0 < st.n; row0 += chunk) {
     const int rows = (int)((st.n - row0) < chunk ? (st.n - row0) : chunk);
     e_step_chunk(ctx, st, w, row0, rows, m, 2, ctx->llk.p, nullptr, ctx->part_solve.p);
-    BitGemmArgs g;
-    g.bits = st.maskT.p + row0 / 32;
-    g.ldbits = st.nwT;
-    g.Bmat = ctx->GW.p;
-    g.ldb = m.s.kkp;
-    g.Out = stats_dev + lay.offA;
-    g.ldo = m.s.kkp;
-    g.M = m.s.d;
-    g.Nq = m.s.kkp;
-    g.kblocks = (int)(round_up(rows, 32) / 32);
-    g.kcols = 32 * g.kblocks;
-    g.accumulate = 1;
-    g.splitk = splitk < g.kblocks ? splitk : (g.kblocks > 0 ? g.kblocks : 1);
-    if (splitk > 1 && g.splitk < 2) g.splitk = 2 <= g.kblocks ? 2 : 1;
-    g.partials = splitk > 1 ? ctx->part_bg.p : nullptr;
-    g.defer_reduce = 1;
-    if (splitk > 1 && g.splitk == 1) {  // degenerate last chunk: accumulate straight into the statistics
-      g.partials = nullptr;
-      g.defer_reduce = 0;
-    }
+    const int kblocks = (int)(round_up(rows, 32) / 32);
+    int sk = splitk < kblocks ? splitk : (kblocks > 0 ? kblocks : 1);
+    if (splitk > 1 && sk < 2) sk = 2 <= kblocks ? 2 : 1;
+    const bool direct = splitk > 1 && sk == 1;  // degenerate last chunk: accumulate straight into the statistics
     ctx->span_begin(FAM_MOMENT);
-    launch_bitgemm(L, g);
+    if (ctx->gemm_mode == 1) {
+      launch_slice(L, ctx->GW.p, m.s.kkp, rows, m.s.kkp, kblocks, ctx->slices, ctx->WQ.p, ctx->WScale.p, ctx->colmax.p);
+      IBitGemmArgs g;
+      g.bits = st.maskT.p + row0 / 32;
+      g.ldbits = st.nwT;
+      g.Bq = ctx->WQ.p;
+      g.scale = ctx->WScale.p;
+      g.T = ctx->slices;
+      g.Out = stats_dev + lay.offA;
+      g.ldo = m.s.kkp;
+      g.M = m.s.d;
+      g.Nq = m.s.kkp;
+      g.kblocks = kblocks;
+      g.accumulate = 1;
+      g.splitk = sk;
+      g.partials = (splitk > 1 && !direct) ? ctx->part_bg.p : nullptr;
+      g.defer_reduce = direct ? 0 : 1;
+      launch_ibitgemm(L, g);
+    } else {
+      BitGemmArgs g;
+      g.bits = st.maskT.p + row0 / 32;
+      g.ldbits = st.nwT;
+      g.Bmat = ctx->GW.p;
+      g.ldb = m.s.kkp;
+      g.Out = stats_dev + lay.offA;
+      g.ldo = m.s.kkp;
+      g.M = m.s.d;
+      g.Nq = m.s.kkp;
+      g.kblocks = kblocks;
+      g.kcols = 32 * kblocks;
+      g.accumulate = 1;
+      g.splitk = sk;
+      g.partials = (splitk > 1 && !direct) ? ctx->part_bg.p : nullptr;
+      g.defer_reduce = direct ? 0 : 1;
+      launch_bitgemm(L, g);
+    }
     ctx->span_end();
     ctx->span_begin(FAM_CROSS);
     launch_cross_resid(L, st, row0, rows, m, ctx->YZ.p, ctx->WZ.p, w + row0, ctx->part_cr.p, slabs);
@@ -579,6 +637,11 @@ int32_t ppca_b200_ctx_create(int32_t device, void *cuda_stream, ppca_b200_ctx **
     std::unique_ptr<ppca_b200_ctx> ctx(new ppca_b200_ctx());
     ctx->device = device;
     ctx->sms = prop.multiProcessorCount;
+    if (const char *e = getenv("PPCA_B200_GEMM")) ctx->gemm_mode = (strcmp(e, "int8") == 0) ? 1 : 0;
+    if (const char *e = getenv("PPCA_B200_SLICES")) {
+      const int t = atoi(e);
+      if (t >= 6 && t <= 8) ctx->slices = t;
+    }
     if (cuda_stream) {
       ctx->stream = (cudaStream_t)cuda_stream;
       ctx->own_stream = false;
@@ -614,6 +677,16 @@ int32_t ppca_b200_ctx_set_chunk(ppca_b200_ctx *ctx, int64_t chunk_samples) {
     REQUIRE(ctx != nullptr, "null context");
     REQUIRE(chunk_samples >= 0 && chunk_samples <= ((int64_t)1 << 30), "chunk out of range");
     ctx->chunk = chunk_samples;
+  });
+}
+
+int32_t ppca_b200_ctx_set_gemm(ppca_b200_ctx *ctx, int32_t mode, int32_t slices) {
+  return guarded([&] {
+    REQUIRE(ctx != nullptr, "null context");
+    REQUIRE(mode == 0 || mode == 1, "gemm mode must be 0 (dmma) or 1 (int8)");
+    REQUIRE(slices >= 6 && slices <= 8, "slices must be 6, 7 or 8");
+    ctx->gemm_mode = mode;
+    ctx->slices = slices;
   });
 }
 

@@ -237,3 +237,34 @@ void launch_responsibilities(const Launcher &L, const double *LP, int64_t n, int
                              double comp_max_j, double *r_out);
 
 }  // namespace ppca
+
+// ---- ibitgemm.cu : the same masked contraction evaluated exactly on the int8 tensor path ---------------
+// Out[M x Nq] (+)= Bits[M x K] * Bmat[K x Nq] with Bmat pre-split into T signed 7-bit slices per column
+// (column scale 2^e): every partial sum is an exact int32, slices are recombined in FP64 in the epilogue.
+namespace ppca {
+struct SlicedB {
+  int8_t *q = nullptr;      // [kblocks][T][Nq][32]  (32 K-bytes permuted for the IMMA B fragment)
+  double *scale = nullptr;  // [Nq] column scale s = 2^e >= max |column|
+  int T = 0;
+};
+size_t sliced_bytes(int kblocks, int Nq, int T);
+// colmax over rows [0,K) of Bmat, then digits; rows in [K, 32*kblocks) are treated as zero
+void launch_slice(const Launcher &L, const double *Bmat, int64_t ldb, int K, int Nq, int kblocks, int T, int8_t *q,
+                  double *scale, unsigned long long *colmax_scratch);
+struct IBitGemmArgs {
+  const uint32_t *bits;
+  int64_t ldbits;
+  const int8_t *Bq;
+  const double *scale;
+  int T;
+  double *Out;
+  int64_t ldo;
+  int M, Nq, kblocks;
+  int accumulate;
+  double *partials;
+  int splitk;
+  int defer_reduce;
+};
+int ibitgemm_pick_splitk(int M, int Nq, int kblocks, int sms);
+void launch_ibitgemm(const Launcher &L, const IBitGemmArgs &a);
+}  // namespace ppca

@@ -348,3 +348,53 @@ def test_full_size_properties(pk):
     assert np.array_equal(ex[~fin], sm[~fin])                           # extrapolate = choose(x, smoothed)
     # idempotence: smoothing a fully observed reconstruction of rank k with tiny noise moves it very little
     assert np.sqrt(np.mean((sm[fin] - x[fin]) ** 2)) < 5 * model.isotropic_noise
+
+
+# ---- the exact int8-sliced evaluation of the two masked-Gram contractions (csrc/ibitgemm.cu) -----------------
+@pytest.fixture
+def int8_ctx(pk):
+    ctx = pk.get_context()
+    yield ctx
+    ctx.set_gemm("dmma")
+
+
+@pytest.mark.parametrize("slices", [7, 8])
+@pytest.mark.parametrize("n,d,k,p", [(100, 3, 2, 0.2), (777, 37, 5, 0.3), (3000, 200, 16, 0.2), (1200, 150, 32, 0.25),
+                                     (500, 260, 64, 0.3)])
+def test_int8_sliced_iterate(pk, orc, int8_ctx, slices, n, d, k, p):
+    int8_ctx.set_gemm("int8", slices)
+    X, C0, mu0, s0 = _case(n, d, k, p, empty_rows=(4,), empty_dims=(d - 1,) if d > 3 else ())
+    w = np.random.default_rng(11).random(n) + 0.5
+    ds = pk.Dataset(X, w)
+    model = pk.PPCAModel(0.4, C0, mu0)
+    assert rel_err(model.llks(ds), orc.llks(X, C0, mu0, 0.4)) < TOL
+    (Z, COV), (Zs, COVs) = both(orc, orc.infer, X, C0, mu0, 0.4)
+    inf = model.infer(ds)
+    assert_close(inf.states(), Z, Zs, "states")
+    assert_close(np.stack(inf.covariances()), COV, COVs, "covariances")
+    C, mu, s = C0, mu0, s0
+    for it in range(5):
+        new, llk = pk.PPCAModel(s, C, mu)._iterate(ds, None)
+        (Cw, muw, sw), (Cs, mus, ss) = both(orc, orc.iterate, X, w, C, mu, s)
+        llkw = orc.llk(X, w, C, mu, s)
+        assert abs(llk - llkw) <= TOL * abs(llkw), f"llk iteration {it}"
+        assert_close(new.transform, Cw, Cs, f"C iteration {it}")
+        assert_close(new.mean, muw, mus, f"mu iteration {it}")
+        assert_close(new.isotropic_noise ** 2, sw ** 2, ss ** 2, f"sigma^2 iteration {it}")
+        C, mu, s = Cw, muw, sw
+
+
+def test_int8_sliced_matches_dmma_closely(pk, int8_ctx):
+    """Same inputs through both arithmetic paths: the int8-sliced statistics agree with DMMA to ~1e-13."""
+    n, d, k = 20000, 200, 16
+    ds = pk.Dataset.synthetic(n, d, k, 0.1, 0.2, seed=5)
+    rng = np.random.default_rng(2)
+    model = pk.PPCAModel(1.0, rng.standard_normal((d, k)), np.zeros(d))
+    int8_ctx.set_gemm("dmma")
+    a, llk_a = model._iterate(ds, None)
+    for slices, tol in ((8, 5e-13), (7, 5e-13), (6, 5e-11)):
+        int8_ctx.set_gemm("int8", slices)
+        b, llk_b = model._iterate(ds, None)
+        assert rel_err(b.transform, a.transform) < tol and rel_err(b.mean, a.mean) < tol, slices
+        assert abs(b.isotropic_noise - a.isotropic_noise) < tol * a.isotropic_noise
+        assert abs(llk_b - llk_a) < tol * abs(llk_a)
