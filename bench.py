@@ -341,7 +341,7 @@ def main():
     ap.add_argument("--rows", type=int, default=0, help="override rows per GPU")
     ap.add_argument("--chunk", type=int, default=0, help="samples per chunk (0 = automatic)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--gemm", default=os.environ.get("PPCA_B200_GEMM", "dmma"), choices=["dmma", "int8"],
+    ap.add_argument("--gemm", default=os.environ.get("PPCA_B200_GEMM", "dmma"), choices=["dmma", "int8", "tc"],
                     help="arithmetic path of the masked-Gram contractions (see include/ppca_b200.h)")
     ap.add_argument("--slices", type=int, default=int(os.environ.get("PPCA_B200_SLICES", "7")))
     args = ap.parse_args()

@@ -75,8 +75,9 @@ int32_t ppca_b200_ctx_set_chunk(ppca_b200_ctx *ctx, int64_t chunk_samples);
  *   mode 0 = FP64 tensor cores (mma.sync DMMA);
  *   mode 1 = exact int8-sliced evaluation on the int8 tensor path: the {0,1} mask times `slices` signed 7-bit
  *            digit planes of the FP64 operand, int32 accumulation (exact), FP64 recombination.  slices in {6,7,8};
- *            7 keeps every term to 2^-49 of its column scale (below FP64 dot-product rounding).
- * The default comes from the environment: PPCA_B200_GEMM=dmma|int8, PPCA_B200_SLICES=6|7|8. */
+ *            7 keeps every term to 2^-49 of its column scale (below FP64 dot-product rounding).  mma.sync IMMA.
+ *   mode 2 = the same arithmetic on tcgen05.mma.kind::i8 with the accumulators in tensor memory.
+ * The default comes from the environment: PPCA_B200_GEMM=dmma|int8|tc, PPCA_B200_SLICES=6|7|8. */
 int32_t ppca_b200_ctx_set_gemm(ppca_b200_ctx *ctx, int32_t mode, int32_t slices);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 int32_t ppca_b200_ctx_launch_count(ppca_b200_ctx *ctx, int64_t *out);

@@ -165,8 +165,9 @@ class Context:
         check(lib().ppca_b200_ctx_set_chunk(self._h, int(chunk)))
 
     def set_gemm(self, mode: str, slices: int = 7) -> None:
-        """'dmma' (FP64 tensor cores) or 'int8' (exact int8-sliced evaluation, see include/ppca_b200.h)."""
-        check(lib().ppca_b200_ctx_set_gemm(self._h, {"dmma": 0, "int8": 1}[mode], int(slices)))
+        """'dmma' (FP64 tensor cores), 'int8' (exact int8-sliced evaluation on mma.sync) or 'tc' (the same on
+        tcgen05 with TMEM accumulators); see include/ppca_b200.h."""
+        check(lib().ppca_b200_ctx_set_gemm(self._h, {"dmma": 0, "int8": 1, "tc": 2}[mode], int(slices)))
 
     def launch_count(self) -> int:
         out = C.c_int64(0)

@@ -30,7 +30,7 @@ struct ppca_b200_ctx {
   int sms = 148;
   int64_t launches = 0;
   int64_t chunk = 0;  // 0 = automatic
-  int gemm_mode = 0;  // 0 = DMMA, 1 = int8-sliced (ibitgemm.cu)
+  int gemm_mode = 0;  // 0 = DMMA, 1 = int8-sliced on mma.sync (ibitgemm.cu), 2 = int8-sliced on tcgen05 (tbitgemm.cu)
   int slices = 7;
   DevBuf<int8_t> KsymQ, WQ;
   DevBuf<double> KsymScale, WScale;
@@ -214,7 +214,14 @@ DevModel stage_model(ppca_b200_ctx *ctx, int d, int k, const double *C, const do
                              ctx->stream));
   ctx->span_begin(FAM_KSYM);
   launch_prepare_model(ctx->L(), ctx->Cdense.p, ctx->mudense.p, d, k, ctx->Cpad.p, ctx->mupad.p, ctx->Ksym.p);
-  if (ctx->gemm_mode == 1) {
+  if (ctx->gemm_mode == 2) {
+    const int kblocks = s.d32 / 32;
+    ctx->KsymQ.reserve(sliced_tc_bytes(kblocks, s.kkp, ctx->slices));
+    ctx->KsymScale.reserve((size_t)s.kkp);
+    ctx->colmax.reserve((size_t)s.kkp);
+    launch_slice_tc(ctx->L(), ctx->Ksym.p, s.kkp, d, s.kkp, kblocks, ctx->slices, ctx->KsymQ.p, ctx->KsymScale.p,
+                    ctx->colmax.p);
+  } else if (ctx->gemm_mode == 1) {
     const int kblocks = s.d32 / 32;
     ctx->KsymQ.reserve(sliced_bytes(kblocks, s.kkp, ctx->slices));
     ctx->KsymScale.reserve((size_t)s.kkp);
@@ -247,7 +254,10 @@ void e_step_chunk(ppca_b200_ctx *ctx, const SampleStore &st, const double *w, in
   const Launcher L = ctx->L();
   const int rows_pad = (int)round_up(rows, 256);
   ctx->span_begin(FAM_GRAM);
-  if (ctx->gemm_mode == 1) {
+  if (ctx->gemm_mode == 2) {
+    launch_tbitgemm(L, st.mask.p + row0 * st.dw, st.dw, st.dw, ctx->KsymQ.p, ctx->KsymScale.p, ctx->slices, ctx->GW.p,
+                    m.s.kkp, rows, m.s.kkp, (m.s.d32 / 32 + 3) / 4, 0, nullptr, 1, 0);
+  } else if (ctx->gemm_mode == 1) {
     IBitGemmArgs g;
     g.bits = st.mask.p + row0 * st.dw;
     g.ldbits = st.dw;
@@ -316,10 +326,15 @@ void em_stats_impl(ppca_b200_ctx *ctx, const SampleStore &st, const double *w, c
   const int64_t chunk = pick_chunk(ctx, st.n_pad, m.s);
   reserve_chunk_ws(ctx, chunk, m.s);
   const int kb_chunk = (int)(chunk / 32);
-  const int splitk = ctx->gemm_mode == 1 ? ibitgemm_pick_splitk(m.s.d, m.s.kkp, kb_chunk, ctx->sms)
-                                         : bitgemm_pick_splitk(m.s.d, m.s.kkp, kb_chunk, ctx->sms);
+  const int splitk = ctx->gemm_mode == 2   ? tbitgemm_pick_splitk(m.s.d, m.s.kkp, kb_chunk / 4, ctx->sms)
+                     : ctx->gemm_mode == 1 ? ibitgemm_pick_splitk(m.s.d, m.s.kkp, kb_chunk, ctx->sms)
+                                           : bitgemm_pick_splitk(m.s.d, m.s.kkp, kb_chunk, ctx->sms);
   const size_t bglen = bitgemm_partials_len(m.s.d, m.s.kkp, splitk);
-  if (ctx->gemm_mode == 1) {
+  if (ctx->gemm_mode == 2) {
+    ctx->WQ.reserve(sliced_tc_bytes(kb_chunk, m.s.kkp, ctx->slices));
+    ctx->WScale.reserve((size_t)m.s.kkp);
+    ctx->colmax.reserve((size_t)m.s.kkp);
+  } else if (ctx->gemm_mode == 1) {
     ctx->WQ.reserve(sliced_bytes(kb_chunk, m.s.kkp, ctx->slices));
     ctx->WScale.reserve((size_t)m.s.kkp);
     ctx->colmax.reserve((size_t)m.s.kkp);
@@ -341,7 +356,21 @@ void em_stats_impl(ppca_b200_ctx *ctx, const SampleStore &st, const double *w, c
     if (splitk > 1 && sk < 2) sk = 2 <= kblocks ? 2 : 1;
     const bool direct = splitk > 1 && sk == 1;  // degenerate last chunk: accumulate straight into the statistics
     ctx->span_begin(FAM_MOMENT);
-    if (ctx->gemm_mode == 1) {
+    if (ctx->gemm_mode == 2) {
+      launch_slice_tc(L, ctx->GW.p, m.s.kkp, rows, m.s.kkp, kblocks, ctx->slices, ctx->WQ.p, ctx->WScale.p,
+                      ctx->colmax.p);
+      const int ksteps = (kblocks + 3) / 4;
+      int skt = splitk < ksteps ? splitk : ksteps;
+      if (skt < 1) skt = 1;
+      {  // no empty slabs
+        const int per = (ksteps + skt - 1) / skt;
+        skt = (ksteps + per - 1) / per;
+      }
+      const bool to_partials = splitk > 1 && skt > 1;
+      launch_tbitgemm(L, st.maskT.p + row0 / 32, st.nwT, 4 * ksteps, ctx->WQ.p, ctx->WScale.p, ctx->slices,
+                      stats_dev + lay.offA, m.s.kkp, m.s.d, m.s.kkp, ksteps, 1, to_partials ? ctx->part_bg.p : nullptr,
+                      skt, to_partials ? 1 : 0);
+    } else if (ctx->gemm_mode == 1) {
       launch_slice(L, ctx->GW.p, m.s.kkp, rows, m.s.kkp, kblocks, ctx->slices, ctx->WQ.p, ctx->WScale.p, ctx->colmax.p);
       IBitGemmArgs g;
       g.bits = st.maskT.p + row0 / 32;
@@ -637,7 +666,8 @@ int32_t ppca_b200_ctx_create(int32_t device, void *cuda_stream, ppca_b200_ctx **
     std::unique_ptr<ppca_b200_ctx> ctx(new ppca_b200_ctx());
     ctx->device = device;
     ctx->sms = prop.multiProcessorCount;
-    if (const char *e = getenv("PPCA_B200_GEMM")) ctx->gemm_mode = (strcmp(e, "int8") == 0) ? 1 : 0;
+    if (const char *e = getenv("PPCA_B200_GEMM"))
+      ctx->gemm_mode = (strcmp(e, "int8") == 0) ? 1 : (strcmp(e, "tc") == 0 ? 2 : 0);
     if (const char *e = getenv("PPCA_B200_SLICES")) {
       const int t = atoi(e);
       if (t >= 6 && t <= 8) ctx->slices = t;
@@ -683,7 +713,7 @@ int32_t ppca_b200_ctx_set_chunk(ppca_b200_ctx *ctx, int64_t chunk_samples) {
 int32_t ppca_b200_ctx_set_gemm(ppca_b200_ctx *ctx, int32_t mode, int32_t slices) {
   return guarded([&] {
     REQUIRE(ctx != nullptr, "null context");
-    REQUIRE(mode == 0 || mode == 1, "gemm mode must be 0 (dmma) or 1 (int8)");
+    REQUIRE(mode >= 0 && mode <= 2, "gemm mode must be 0 (dmma), 1 (int8 on mma.sync) or 2 (int8 on tcgen05)");
     REQUIRE(slices >= 6 && slices <= 8, "slices must be 6, 7 or 8");
     ctx->gemm_mode = mode;
     ctx->slices = slices;

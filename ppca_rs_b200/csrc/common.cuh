@@ -267,4 +267,13 @@ struct IBitGemmArgs {
 };
 int ibitgemm_pick_splitk(int M, int Nq, int kblocks, int sms);
 void launch_ibitgemm(const Launcher &L, const IBitGemmArgs &a);
+
+// ---- tbitgemm.cu : the int8-sliced contraction on tcgen05 (TMEM accumulators) ----------------------------
+size_t sliced_tc_bytes(int kblocks32, int Nq, int T);
+void launch_slice_tc(const Launcher &L, const double *Bmat, int64_t ldb, int K, int Nq, int kblocks32, int T, int8_t *q,
+                     double *scale, unsigned long long *colmax_scratch);
+int tbitgemm_pick_splitk(int M, int Nq, int ksteps, int sms);
+void launch_tbitgemm(const Launcher &L, const uint32_t *bits, int64_t ldbits, int nwords, const int8_t *Bq,
+                     const double *scale, int T, double *Out, int64_t ldo, int M, int Nq, int ksteps, int accumulate,
+                     double *partials, int splitk, int defer_reduce);
 }  // namespace ppca

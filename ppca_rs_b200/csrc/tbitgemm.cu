@@ -1,0 +1,423 @@
+// tbitgemm.cu — the exact int8-sliced masked-Gram contraction on the 5th-generation tensor cores (tcgen05).
+//
+//   Out[M x Nq] (+)= Bits[M x K] * Bmat[K x Nq],   Bmat pre-split into T signed 7-bit digit planes (ibitgemm.cu)
+//
+// Same arithmetic as ibitgemm.cu (exact int32 partial sums, FP64 Horner recombination), but the MMAs are
+// tcgen05.mma.kind::i8 issued by one thread, with the accumulators of all T planes of a 128 x 32 output tile in
+// tensor memory (N = 32 T columns, double buffered).  Warp-specialised persistent kernel, one CTA per SM:
+//   warps 0-3  producers: expand the bit-packed mask rows to int8 {0,1} straight into the SWIZZLE_128B K-major
+//              shared-memory layout the MMA reads (the mask never exists as bytes in HBM), and cp.async the
+//              digit-plane tile into the same layout; fence.proxy.async; arrive on the stage's "full" mbarrier
+//   warp  4    MMA issuer: tcgen05.mma M=128, N=32T, K=32, four per 128-byte K step; tcgen05.commit frees the
+//              stage ("empty" mbarrier) and, after the last K step, publishes the accumulator ("tmem_full")
+//   warps 5-8  epilogue: tcgen05.ld the T planes of 8 columns at a time, recombine in FP64, scale, store
+// References as in bitgemm.cu: E-step Gs = Mask Ksym (output_covariance.rs:57-59 after :123-131),
+// M-step A += Mask^T W (ppca_model.rs:297-306).
+#include <cstdio>
+
+#include "common.cuh"
+#include "mma.cuh"
+
+namespace ppca {
+
+namespace tb {
+
+constexpr int BM = 128, NQ = 32, BKB = 128, STAGES = 4;
+constexpr int PRODUCERS = 128, THREADS = 288;
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_i8(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
+      "}" ::"r"(tmem_c),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld8(uint32_t taddr, int (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): 8-row groups of 1024 bytes
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// byte offset of 16-byte chunk c of row r in the swizzled tile
+__device__ __forceinline__ uint32_t sw128_off(int r, int c) {
+  return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
+}
+__device__ __forceinline__ uint32_t nib4(uint32_t b, int shift) {
+  return (((b >> shift) & 0xFu) * 0x00204081u) & 0x01010101u;
+}
+
+}  // namespace tb
+
+struct TBitGemmArgs {
+  const uint32_t *bits;
+  int64_t ldbits;     // words per bit row
+  int nwords;         // valid words per bit row (reads at or beyond return 0)
+  const int8_t *Bq;   // [ksteps][qtiles][T*32][128]
+  const double *scale;
+  double *Out;
+  int64_t ldo;
+  int M, Nq;
+  int ksteps;         // 128-bit K steps
+  int accumulate;
+  double *partials;
+  int splitk;
+  int defer_reduce;
+};
+
+template <int T>
+__global__ void __launch_bounds__(tb::THREADS, 1) tbitgemm_kernel(TBitGemmArgs a) {
+  using namespace tb;
+  constexpr int N = T * NQ;
+  constexpr uint32_t A_BYTES = BM * BKB, B_BYTES = N * BKB, STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+  extern __shared__ unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * STAGES + 4];
+  __shared__ uint32_t tmem_base_slot;
+
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int b) { return bar0 + 8u * (2 * STAGES + b); };
+  auto tempty_bar = [&](int b) { return bar0 + 8u * (2 * STAGES + 2 + b); };
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), PRODUCERS);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull_bar(b), 1);
+      mbar_init(tempty_bar(b), 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                 "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  const int mtiles = (a.M + BM - 1) / BM, qtiles = (a.Nq + NQ - 1) / NQ;
+  const int ntiles = mtiles * qtiles * a.splitk;
+  const int ks_per = (a.ksteps + a.splitk - 1) / a.splitk;
+
+  if (warp < 4) {
+    // ===================== producers =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    const int r = tid;  // row of the tile handled by this thread
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int z = tile / (mtiles * qtiles), rem = tile % (mtiles * qtiles);
+      const int qt = rem / mtiles, mt = rem % mtiles;
+      const int ks_begin = z * ks_per, ks_end = min(a.ksteps, ks_begin + ks_per);
+      const int row = mt * BM + r;
+      const bool row_ok = row < a.M;
+      const uint32_t *wrow = a.bits + (int64_t)(row_ok ? row : 0) * a.ldbits;
+      for (int ks = ks_begin; ks < ks_end; ++ks) {
+        // this K step's four mask words (issued before waiting for the slot)
+        uint32_t w[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int wi = 4 * ks + j;
+          w[j] = (row_ok && wi < a.nwords) ? __ldg(wrow + wi) : 0u;
+        }
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        const uint32_t sA = smem_base + stage * STAGE_BYTES, sB = sA + A_BYTES;
+        // digit planes: N rows x 128 bytes, contiguous in global memory
+        const int8_t *src = a.Bq + ((int64_t)ks * qtiles + qt) * (int64_t)B_BYTES;
+#pragma unroll
+        for (int j = 0; j < (N * 8) / PRODUCERS; ++j) {
+          const int idx = tid + PRODUCERS * j;
+          const int n = idx >> 3, c = idx & 7;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sB + sw128_off(n, c)), "l"(src + idx * 16));
+        }
+        asm volatile("cp.async.commit_group;" ::);
+        // mask bits -> int8 {0,1}, 16 bytes per chunk
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint32_t b = (w[c >> 1] >> ((c & 1) * 16)) & 0xFFFFu;
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sA + sw128_off(r, c)), "r"(nib4(b, 0)),
+                       "r"(nib4(b, 4)), "r"(nib4(b, 8)), "r"(nib4(b, 12))
+                       : "memory");
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        fence_proxy_async();
+        mbar_arrive(full_bar(stage));
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp == 4) {
+    // ===================== MMA issuer =====================
+    int stage = 0, buf = 0;
+    uint32_t phase = 0, tphase = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int z = tile / (mtiles * qtiles);
+      const int ks_begin = z * ks_per, ks_end = min(a.ksteps, ks_begin + ks_per);
+      mbar_wait(tempty_bar(buf), tphase ^ 1u);
+      tc_fence_after();
+      const uint32_t tmem_c = tmem_base + (uint32_t)(buf * N);
+      if (ks_begin >= ks_end) {  // empty K slab (never produced by the host-side split): publish immediately
+        if (lane == 0) tc_commit(tfull_bar(buf));
+        __syncwarp();
+      }
+      for (int ks = ks_begin; ks < ks_end; ++ks) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sA = smem_base + stage * STAGE_BYTES, sB = sA + A_BYTES;
+          const uint64_t adesc = smem_desc_sw128(sA), bdesc = smem_desc_sw128(sB);
+#pragma unroll
+          for (int k = 0; k < BKB / 32; ++k)
+            tc_mma_i8(tmem_c, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC,
+                      (ks > ks_begin || k > 0) ? 1u : 0u);
+          tc_commit(empty_bar(stage));
+          if (ks == ks_end - 1) tc_commit(tfull_bar(buf));
+        }
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+      if (++buf == 2) {
+        buf = 0;
+        tphase ^= 1u;
+      }
+    }
+  } else {
+    // ===================== epilogue =====================
+    int buf = 0;
+    uint32_t tphase = 0;
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int z = tile / (mtiles * qtiles), rem = tile % (mtiles * qtiles);
+      const int qt = rem / mtiles, mt = rem % mtiles;
+      const int row = mt * BM + quarter * 32 + lane;
+      const bool empty_slab = z * ks_per >= min(a.ksteps, z * ks_per + ks_per);
+      double *out;
+      int64_t ldo;
+      bool accumulate;
+      if (a.splitk > 1) {
+        out = a.partials + (int64_t)z * a.M * a.Nq;
+        ldo = a.Nq;
+        accumulate = a.defer_reduce != 0;
+      } else {
+        out = a.Out;
+        ldo = a.ldo;
+        accumulate = a.accumulate != 0;
+      }
+      mbar_wait(tfull_bar(buf), tphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * N);
+#pragma unroll 1
+      for (int qc = 0; qc < NQ / 8; ++qc) {
+        int rg[T][8];
+#pragma unroll
+        for (int t = 0; t < T; ++t) tc_ld8(taddr + (uint32_t)(t * NQ + 8 * qc), rg[t]);
+        tc_wait_ld();
+        const int q = qt * NQ + 8 * qc;
+        if (row < a.M && q < a.Nq) {
+          double v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            double acc = (double)rg[T - 1][j];
+#pragma unroll
+            for (int t = T - 2; t >= 0; --t) acc = fma(acc, 1.0 / 128.0, (double)rg[t][j]);
+            v[j] = empty_slab ? 0.0 : acc * (a.scale[q + j] * (1.0 / 64.0));
+          }
+          double2 *p = reinterpret_cast<double2 *>(out + (int64_t)row * ldo + q);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            double2 val = make_double2(v[2 * j], v[2 * j + 1]);
+            if (accumulate) {
+              const double2 o = p[j];
+              val.x += o.x;
+              val.y += o.y;
+            }
+            p[j] = val;
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(buf));
+      if (++buf == 2) {
+        buf = 0;
+        tphase ^= 1u;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// digit planes in the layout above: [kstep][qtile][t * 32 + qi][128 bytes], natural byte order
+// ---------------------------------------------------------------------------------------------
+template <int T>
+__global__ void __launch_bounds__(128) slice_tc_kernel(const double *__restrict__ B, int64_t ldb, int K, int Nq,
+                                                       const unsigned long long *__restrict__ cm, int8_t *out,
+                                                       double *scale) {
+  const int q = blockIdx.x * 128 + threadIdx.x;
+  const int kb = blockIdx.y;  // 32-row block
+  if (q >= Nq) return;
+  const int qtiles = (Nq + 31) / 32;
+  const double m = __longlong_as_double((long long)cm[q]);
+  int ex = 0;
+  if (m > 0.0) frexp(m, &ex);
+  if (kb == 0) scale[q] = ldexp(1.0, ex);
+  const double inv = ldexp(64.0, -ex);
+  uint32_t words[T][8];
+#pragma unroll
+  for (int t = 0; t < T; ++t)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) words[t][j] = 0u;
+#pragma unroll
+  for (int r = 0; r < 32; ++r) {
+    const int row = kb * 32 + r;
+    double xs = (row < K) ? B[(int64_t)row * ldb + q] * inv : 0.0;
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      const double dg = rint(xs);
+      xs = (xs - dg) * 128.0;
+      words[t][r >> 2] |= ((uint32_t)((int)dg & 0xff)) << (8 * (r & 3));
+    }
+  }
+  const int ks = kb >> 2, qt = q >> 5, qi = q & 31;
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    uint4 *dst = reinterpret_cast<uint4 *>(out + ((((int64_t)ks * qtiles + qt) * T + t) * 32 + qi) * 128 + (kb & 3) * 32);
+    dst[0] = make_uint4(words[t][0], words[t][1], words[t][2], words[t][3]);
+    dst[1] = make_uint4(words[t][4], words[t][5], words[t][6], words[t][7]);
+  }
+}
+
+__global__ void colmax_kernel_tc(const double *__restrict__ B, int64_t ldb, int K, int Nq, unsigned long long *cm) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= Nq) return;
+  const int per = (K + gridDim.y - 1) / gridDim.y;
+  const int lo = blockIdx.y * per, hi = min(K, lo + per);
+  double m = 0.0;
+  for (int r = lo; r < hi; ++r) m = fmax(m, fabs(B[(int64_t)r * ldb + q]));
+  if (m > 0.0) atomicMax(cm + q, (unsigned long long)__double_as_longlong(m));
+}
+
+size_t sliced_tc_bytes(int kblocks32, int Nq, int T) {
+  const int64_t ks = (kblocks32 + 3) / 4, qt = (Nq + 31) / 32;
+  return (size_t)(ks * qt * T * 32 * 128);
+}
+
+void launch_slice_tc(const Launcher &L, const double *Bmat, int64_t ldb, int K, int Nq, int kblocks32, int T, int8_t *q,
+                     double *scale, unsigned long long *cm) {
+  if (Nq <= 0 || kblocks32 <= 0) return;
+  CUDA_CHECK(cudaMemsetAsync(cm, 0, sizeof(unsigned long long) * Nq, L.stream));
+  int slabs = K / 256;
+  if (slabs < 1) slabs = 1;
+  if (slabs > 8 * L.sms) slabs = 8 * L.sms;
+  colmax_kernel_tc<<<dim3((Nq + 127) / 128, slabs), 128, 0, L.stream>>>(Bmat, ldb, K, Nq, cm);
+  CUDA_CHECK(cudaGetLastError());
+  ++*L.launch_counter;
+  dim3 grid((Nq + 127) / 128, kblocks32);
+  if (T == 6) slice_tc_kernel<6><<<grid, 128, 0, L.stream>>>(Bmat, ldb, K, Nq, cm, q, scale);
+  else if (T == 7) slice_tc_kernel<7><<<grid, 128, 0, L.stream>>>(Bmat, ldb, K, Nq, cm, q, scale);
+  else if (T == 8) slice_tc_kernel<8><<<grid, 128, 0, L.stream>>>(Bmat, ldb, K, Nq, cm, q, scale);
+  else PPCA_THROW(PPCA_ERR_INVALID, "int8 path: T must be 6, 7 or 8 (got %d)", T);
+  CUDA_CHECK(cudaGetLastError());
+  ++*L.launch_counter;
+}
+
+int tbitgemm_pick_splitk(int M, int Nq, int ksteps, int sms) {
+  const int64_t tiles = round_up(M, tb::BM) / tb::BM * (round_up(Nq, tb::NQ) / tb::NQ);
+  const int64_t max_s = ksteps / 8 > 0 ? ksteps / 8 : 1;  // at least 8 K steps (1024 rows) per slab
+  if (tiles >= 2 * sms) return 1;  // persistent kernel: enough tiles to balance
+  int64_t s = (2 * sms + tiles - 1) / tiles;
+  if (s > max_s) s = max_s;
+  return (int)(s < 1 ? 1 : s);
+}
+
+template <int T>
+static void launch_tb(const Launcher &L, const TBitGemmArgs &a) {
+  constexpr size_t SMEM = (size_t)tb::STAGES * (tb::BM * tb::BKB + T * tb::NQ * tb::BKB) + 1024;
+  static bool configured = false;
+  if (!configured) {
+    CUDA_CHECK(cudaFuncSetAttribute(tbitgemm_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+    configured = true;
+  }
+  const int64_t tiles = round_up(a.M, tb::BM) / tb::BM * (round_up(a.Nq, tb::NQ) / tb::NQ) * a.splitk;
+  const int grid = (int)(tiles < L.sms ? tiles : L.sms);
+  tbitgemm_kernel<T><<<grid, tb::THREADS, SMEM, L.stream>>>(a);
+  CUDA_CHECK(cudaGetLastError());
+  ++*L.launch_counter;
+}
+
+void launch_tbitgemm(const Launcher &L, const uint32_t *bits, int64_t ldbits, int nwords, const int8_t *Bq,
+                     const double *scale, int T, double *Out, int64_t ldo, int M, int Nq, int ksteps, int accumulate,
+                     double *partials, int splitk, int defer_reduce) {
+  REQUIRE(Nq % 8 == 0 && ldo % 2 == 0, "tbitgemm: Nq must be a multiple of 8, output pitch even");
+  REQUIRE(splitk >= 1 && splitk <= (ksteps > 0 ? ksteps : 1), "tbitgemm: bad split-K");
+  {  // every K slab must be non-empty
+    const int per = (ksteps + splitk - 1) / splitk;
+    REQUIRE((splitk - 1) * per < ksteps || splitk == 1, "tbitgemm: split-K leaves an empty slab");
+  }
+  REQUIRE(splitk == 1 || partials != nullptr, "tbitgemm: split-K needs a partials workspace");
+  if (M <= 0 || Nq <= 0 || ksteps <= 0) return;
+  TBitGemmArgs a;
+  a.bits = bits; a.ldbits = ldbits; a.nwords = nwords; a.Bq = Bq; a.scale = scale; a.Out = Out; a.ldo = ldo;
+  a.M = M; a.Nq = Nq; a.ksteps = ksteps; a.accumulate = accumulate; a.partials = partials; a.splitk = splitk;
+  a.defer_reduce = defer_reduce;
+  if (T == 6) launch_tb<6>(L, a);
+  else if (T == 7) launch_tb<7>(L, a);
+  else if (T == 8) launch_tb<8>(L, a);
+  else PPCA_THROW(PPCA_ERR_INVALID, "int8 path: T must be 6, 7 or 8 (got %d)", T);
+  if (splitk > 1 && !defer_reduce) launch_bitgemm_reduce(L, partials, splitk, M, Nq, Out, ldo, accumulate);
+}
+
+}  // namespace ppca
