@@ -112,6 +112,27 @@ def fp64_peak():
     return j["dmma_tflops"], j.get("dmma_tflops_sustained"), "profiles/r01_fp64_peak.json (tools/fp64_peak.cu, round 1)"
 
 
+def measured_bf16_peak():
+    """Dense bf16 TFLOP/s from the driver-written MEASURED_PEAKS.json, else the profiling guide's fallback."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["bf16_tflops"]), "MEASURED_PEAKS.json"
+    except Exception:
+        return 1590.0, "B200_PROFILING.md fallback (MEASURED_PEAKS.json absent)"
+
+
+def ctx_chunk(ctx, n, d, k):
+    """Samples per chunk the engine picks automatically (mirrors pick_chunk in csrc/api.cu)."""
+    wave = 148 * 128
+    chunk = wave * 4
+    kk = k * (k + 1) // 2
+    per_row = ((kk + 7) // 8 * 8 + 2 * ((k + 7) // 8 * 8) + 4) * 8
+    while chunk > wave and chunk * per_row > (8 << 30):
+        chunk -= wave
+    n_pad = (n + 255) // 256 * 256
+    return min(chunk, n_pad)
+
+
 def init_params(d, k, seed):
     rng = np.random.default_rng(seed)
     return rng.standard_normal((d, k)), np.zeros(d), 1.0
@@ -285,24 +306,43 @@ def run_ours(args, wl, rank, world, local_rank):
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel family: the masked-Gram contraction (bitgemm E + M) ------
-    peak, peak_sustained, peak_src = fp64_peak()
+    # ---- roofline of the dominant kernel family: the masked-Gram contraction (E-step + M-step launches) ------
+    peak64, peak64_sustained, peak64_src = fp64_peak()
     kk = k * (k + 1) // 2
     bit_ms = fam.get("gram", 0.0) + fam.get("moment", 0.0)
-    if m > 1:
-        # E-step runs twice per component (posterior pass + weighted pass), M-step once
-        flops_bit = (3 * 2 * d * kk) * n * m * args.steps
-    else:
-        flops_bit = (2 * 2 * d * kk) * n * args.steps
-    achieved = flops_bit / (bit_ms * 1e-3) / 1e12 if bit_ms > 0 else None
-    roofline = {
-        "bound": "tensor", "kernel": "bitgemm_kernel (gram + moment launches)", "achieved": achieved, "peak": peak,
-        "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None, "traffic": None,
-        "peak_source": peak_src, "peak_sustained": peak_sustained,
-        "share_of_step": bit_ms / ms_total if ms_total else None,
+    # E-step runs twice per mixture component (posterior pass + weighted pass), M-step once
+    contractions = (3 if m > 1 else 2) * max(1, m)
+    flops_bit = contractions * (2 * d * kk) * n * args.steps          # algorithmic FP64 flops
+    fp64_equiv = flops_bit / (bit_ms * 1e-3) / 1e12 if bit_ms > 0 else None
+    launches_bit = contractions * args.steps * max(1, -(-n // max(1, ctx_chunk(ctx, n, d, k))))
+    common = {
+        "bound": "tensor", "traffic": None, "share_of_step": bit_ms / ms_total if ms_total else None,
+        "avg_launch_ms": bit_ms / launches_bit if launches_bit else None,
         "family_ms_per_step": {kname: v / args.steps for kname, v in fam.items()},
-        "whole_step_frac": flops_per_sample_iter(d, k) * max(1, m) * n * args.steps / (ms_total * 1e-3) / 1e12 / peak,
+        "fp64_equivalent_tflops": fp64_equiv, "fp64_dmma_peak_tflops": peak64, "fp64_peak_source": peak64_src,
+        "fp64_equivalent_frac": (fp64_equiv / peak64) if fp64_equiv else None,
+        "whole_step_fp64_equivalent_frac":
+            flops_per_sample_iter(d, k) * max(1, m) * n * args.steps / (ms_total * 1e-3) / 1e12 / peak64,
     }
+    if args.gemm == "dmma":
+        roofline = dict(common, kernel="bitgemm_kernel (mma.sync DMMA; E-step + M-step launches)", achieved=fp64_equiv,
+                        peak=peak64, unit="TFLOP/s", frac=common["fp64_equivalent_frac"], peak_source=peak64_src,
+                        peak_sustained=peak64_sustained)
+    else:
+        tops = flops_bit * args.slices / (bit_ms * 1e-3) / 1e12 if bit_ms > 0 else None   # int8 ops = T digit planes
+        if args.gemm == "tc":
+            bf16, src = measured_bf16_peak()
+            peak, psrc = 2.0 * bf16, f"2 x bf16_tflops of {src} (int8 dense tcgen05 rate = 2 x bf16; no measured int8 figure)"
+            kern = f"tbitgemm_kernel<{args.slices}> (tcgen05.mma.kind::i8, TMEM accumulators; E-step + M-step launches)"
+        else:
+            with open(os.path.join(ROOT, "profiles", "r01_imma_peak.json")) as f:
+                peak = json.load(f)["imma_s8_tops"]
+            psrc = "profiles/r01_imma_peak.json (tools/imma_peak.cu, mma.sync.m16n8k32.s8, round 1)"
+            kern = f"ibitgemm_kernel<{args.slices}> (mma.sync IMMA; E-step + M-step launches)"
+        roofline = dict(common, kernel=kern, achieved=tops, peak=peak, unit="TOP/s", frac=(tops / peak) if tops else None,
+                        peak_source=psrc,
+                        note=f"exact int8-sliced evaluation: {args.slices} signed 7-bit digit planes per FP64 operand, "
+                             "int32 accumulation, FP64 recombination; achieved counts 2*rows*d*kk*slices int8 ops per launch")
 
     # ---- CPU baseline on a bounded sample of the same workload (rank 0, N=1 only) ----------------
     cpu = None
@@ -341,7 +381,7 @@ def main():
     ap.add_argument("--rows", type=int, default=0, help="override rows per GPU")
     ap.add_argument("--chunk", type=int, default=0, help="samples per chunk (0 = automatic)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--gemm", default=os.environ.get("PPCA_B200_GEMM", "dmma"), choices=["dmma", "int8", "tc"],
+    ap.add_argument("--gemm", default=os.environ.get("PPCA_B200_GEMM", "tc"), choices=["dmma", "int8", "tc"],
                     help="arithmetic path of the masked-Gram contractions (see include/ppca_b200.h)")
     ap.add_argument("--slices", type=int, default=int(os.environ.get("PPCA_B200_SLICES", "7")))
     args = ap.parse_args()

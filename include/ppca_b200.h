@@ -77,15 +77,16 @@ int32_t ppca_b200_ctx_set_chunk(ppca_b200_ctx *ctx, int64_t chunk_samples);
  *            digit planes of the FP64 operand, int32 accumulation (exact), FP64 recombination.  slices in {6,7,8};
  *            7 keeps every term to 2^-49 of its column scale (below FP64 dot-product rounding).  mma.sync IMMA.
  *   mode 2 = the same arithmetic on tcgen05.mma.kind::i8 with the accumulators in tensor memory.
- * The default comes from the environment: PPCA_B200_GEMM=dmma|int8|tc, PPCA_B200_SLICES=6|7|8. */
+ * Default: mode 2 with 7 slices; the environment overrides it: PPCA_B200_GEMM=dmma|int8|tc, PPCA_B200_SLICES=6|7|8. */
 int32_t ppca_b200_ctx_set_gemm(ppca_b200_ctx *ctx, int32_t mode, int32_t slices);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 int32_t ppca_b200_ctx_launch_count(ppca_b200_ctx *ctx, int64_t *out);
 /* Device time of the last iterate / em_stats call broken down per kernel family, in ms:
- * out[0]=ksym out[1]=gram(bitgemm E) out[2]=proj out[3]=solve out[4]=moment(bitgemm M) out[5]=cross+resid
- * out[6]=finish.  Only filled when profiling was enabled with ppca_b200_ctx_set_profiling(ctx, 1). */
+ * out[0]=model staging (Ksym, digit planes) out[1]=gram (masked contraction, E-step) out[2]=proj out[3]=solve
+ * out[4]=moment (masked contraction, M-step) out[5]=cross+resid out[6]=finish out[7]=digit-plane slicing of W.
+ * Only filled when profiling was enabled with ppca_b200_ctx_set_profiling(ctx, 1). */
 int32_t ppca_b200_ctx_set_profiling(ppca_b200_ctx *ctx, int32_t enabled);
-int32_t ppca_b200_ctx_last_profile(ppca_b200_ctx *ctx, double *out7);
+int32_t ppca_b200_ctx_last_profile(ppca_b200_ctx *ctx, double *out8);
 
 /* ---- datasets: Dataset / MaskedSample / Mask (dataset.rs:11-14,93-100; utils.rs:27-28) --------- */
 /* Dataset::new / new_with_weights from a host matrix (src/python_bindings.rs:32-64). weights may be NULL (all 1). */

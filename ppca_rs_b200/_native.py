@@ -178,9 +178,9 @@ class Context:
         check(lib().ppca_b200_ctx_set_profiling(self._h, int(bool(enabled))))
 
     def last_profile(self) -> Dict[str, float]:
-        out = np.zeros(7)
+        out = np.zeros(8)
         check(lib().ppca_b200_ctx_last_profile(self._h, dptr(out)))
-        names = ["ksym", "gram", "proj", "solve", "moment", "cross_resid", "finish"]
+        names = ["ksym", "gram", "proj", "solve", "moment", "cross_resid", "finish", "slice"]
         return dict(zip(names, out.tolist()))
 
     def close(self) -> None:

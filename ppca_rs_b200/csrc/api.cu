@@ -17,7 +17,7 @@ namespace ppca {
 static thread_local std::string g_last_error;
 void set_error(const std::string &msg) { g_last_error = msg; }
 
-enum { FAM_KSYM = 0, FAM_GRAM, FAM_PROJ, FAM_SOLVE, FAM_MOMENT, FAM_CROSS, FAM_FINISH, FAM_COUNT };
+enum { FAM_KSYM = 0, FAM_GRAM, FAM_PROJ, FAM_SOLVE, FAM_MOMENT, FAM_CROSS, FAM_FINISH, FAM_SLICE, FAM_COUNT };
 
 }  // namespace ppca
 
@@ -30,7 +30,7 @@ struct ppca_b200_ctx {
   int sms = 148;
   int64_t launches = 0;
   int64_t chunk = 0;  // 0 = automatic
-  int gemm_mode = 0;  // 0 = DMMA, 1 = int8-sliced on mma.sync (ibitgemm.cu), 2 = int8-sliced on tcgen05 (tbitgemm.cu)
+  int gemm_mode = 2;  // 0 = DMMA, 1 = int8-sliced on mma.sync (ibitgemm.cu), 2 = int8-sliced on tcgen05 (tbitgemm.cu)
   int slices = 7;
   DevBuf<int8_t> KsymQ, WQ;
   DevBuf<double> KsymScale, WScale;
@@ -49,7 +49,7 @@ struct ppca_b200_ctx {
   size_t ev_used = 0;
   struct Span { int fam; cudaEvent_t a, b; };
   std::vector<Span> spans;
-  double last_profile[FAM_COUNT] = {0, 0, 0, 0, 0, 0, 0};
+  double last_profile[FAM_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0};
 
   Launcher L() { return Launcher{stream, &launches, sms}; }
   double *pin(size_t count) {
@@ -355,10 +355,18 @@ void em_stats_impl(ppca_b200_ctx *ctx, const SampleStore &st, const double *w, c
     int sk = splitk < kblocks ? splitk : (kblocks > 0 ? kblocks : 1);
     if (splitk > 1 && sk < 2) sk = 2 <= kblocks ? 2 : 1;
     const bool direct = splitk > 1 && sk == 1;  // degenerate last chunk: accumulate straight into the statistics
-    ctx->span_begin(FAM_MOMENT);
     if (ctx->gemm_mode == 2) {
+      ctx->span_begin(FAM_SLICE);
       launch_slice_tc(L, ctx->GW.p, m.s.kkp, rows, m.s.kkp, kblocks, ctx->slices, ctx->WQ.p, ctx->WScale.p,
                       ctx->colmax.p);
+      ctx->span_end();
+    } else if (ctx->gemm_mode == 1) {
+      ctx->span_begin(FAM_SLICE);
+      launch_slice(L, ctx->GW.p, m.s.kkp, rows, m.s.kkp, kblocks, ctx->slices, ctx->WQ.p, ctx->WScale.p, ctx->colmax.p);
+      ctx->span_end();
+    }
+    ctx->span_begin(FAM_MOMENT);
+    if (ctx->gemm_mode == 2) {
       const int ksteps = (kblocks + 3) / 4;
       int skt = splitk < ksteps ? splitk : ksteps;
       if (skt < 1) skt = 1;
@@ -371,7 +379,6 @@ void em_stats_impl(ppca_b200_ctx *ctx, const SampleStore &st, const double *w, c
                       stats_dev + lay.offA, m.s.kkp, m.s.d, m.s.kkp, ksteps, 1, to_partials ? ctx->part_bg.p : nullptr,
                       skt, to_partials ? 1 : 0);
     } else if (ctx->gemm_mode == 1) {
-      launch_slice(L, ctx->GW.p, m.s.kkp, rows, m.s.kkp, kblocks, ctx->slices, ctx->WQ.p, ctx->WScale.p, ctx->colmax.p);
       IBitGemmArgs g;
       g.bits = st.maskT.p + row0 / 32;
       g.ldbits = st.nwT;
@@ -667,7 +674,7 @@ int32_t ppca_b200_ctx_create(int32_t device, void *cuda_stream, ppca_b200_ctx **
     ctx->device = device;
     ctx->sms = prop.multiProcessorCount;
     if (const char *e = getenv("PPCA_B200_GEMM"))
-      ctx->gemm_mode = (strcmp(e, "int8") == 0) ? 1 : (strcmp(e, "tc") == 0 ? 2 : 0);
+      ctx->gemm_mode = (strcmp(e, "int8") == 0) ? 1 : (strcmp(e, "dmma") == 0 ? 0 : 2);
     if (const char *e = getenv("PPCA_B200_SLICES")) {
       const int t = atoi(e);
       if (t >= 6 && t <= 8) ctx->slices = t;
@@ -734,10 +741,10 @@ int32_t ppca_b200_ctx_set_profiling(ppca_b200_ctx *ctx, int32_t enabled) {
   });
 }
 
-int32_t ppca_b200_ctx_last_profile(ppca_b200_ctx *ctx, double *out7) {
+int32_t ppca_b200_ctx_last_profile(ppca_b200_ctx *ctx, double *out8) {
   return guarded([&] {
-    REQUIRE(ctx != nullptr && out7 != nullptr, "null argument");
-    for (int i = 0; i < FAM_COUNT; ++i) out7[i] = ctx->last_profile[i];
+    REQUIRE(ctx != nullptr && out8 != nullptr, "null argument");
+    for (int i = 0; i < FAM_COUNT; ++i) out8[i] = ctx->last_profile[i];
   });
 }
 

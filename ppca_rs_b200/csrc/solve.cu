@@ -20,14 +20,12 @@ namespace ppca {
 
 #define LN_2PI 1.8378770664093453
 
-// 1 / x for a positive normal double: hardware seed (about 2^-20) and two Newton steps with a final fused
-// residual correction; relative error at rounding level, no special-case branches.
+// 1 / x for a positive normal double: hardware seed (relative error <= 2^-23) and two Newton steps
+// (2^-46, then rounding level); no special-case branches.
 __device__ __forceinline__ double fast_rcp(double x) {
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
   double e = fma(-x, r, 1.0);
-  r = fma(r, e, r);
-  e = fma(-x, r, 1.0);
   r = fma(r, e, r);
   e = fma(-x, r, 1.0);
   return fma(r, e, r);
@@ -250,9 +248,13 @@ __global__ void __launch_bounds__(256, (KP == 32 ? 2 : (KP == 16 ? 3 : 4))) solv
         myinv = inv;
       }
       const double f = (li == p) ? 0.0 : A[p] * inv;
+      const double2 *cs2 = reinterpret_cast<const double2 *>(cs);
 #pragma unroll
-      for (int j = 0; j < KP; ++j)
-        if (j != p) A[j] = fma(-f, cs[j], A[j]);
+      for (int j = 0; j < KP; j += 2) {
+        const double2 cv = cs2[j >> 1];
+        if (j != p) A[j] = fma(-f, cv.x, A[j]);
+        if (j + 1 != p) A[j + 1] = fma(-f, cv.y, A[j + 1]);
+      }
       A[p] = (li == p) ? 1.0 : -f;
     }
 #pragma unroll
@@ -384,9 +386,13 @@ __global__ void __launch_bounds__(256, 1) solve_reg64_kernel(SolveArgs a) {
         myinv = inv;
       }
       const double f = (li == p) ? 0.0 : A[p] * inv;
+      const double2 *cb2 = reinterpret_cast<const double2 *>(cb);
 #pragma unroll
-      for (int j = 0; j < KP; ++j)
-        if (j != p) A[j] = fma(-f, cb[j], A[j]);
+      for (int j = 0; j < KP; j += 2) {
+        const double2 cv = cb2[j >> 1];
+        if (j != p) A[j] = fma(-f, cv.x, A[j]);
+        if (j + 1 != p) A[j + 1] = fma(-f, cv.y, A[j + 1]);
+      }
       A[p] = (li == p) ? 1.0 : -f;
     }
 #pragma unroll

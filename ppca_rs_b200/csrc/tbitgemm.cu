@@ -304,12 +304,14 @@ __global__ void __launch_bounds__(tb::THREADS, 1) tbitgemm_kernel(TBitGemmArgs a
 // ---------------------------------------------------------------------------------------------
 template <int T>
 __global__ void __launch_bounds__(128) slice_tc_kernel(const double *__restrict__ B, int64_t ldb, int K, int Nq,
-                                                       const unsigned long long *__restrict__ cm, int8_t *out,
-                                                       double *scale) {
-  const int q = blockIdx.x * 128 + threadIdx.x;
-  const int kb = blockIdx.y;  // 32-row block
-  if (q >= Nq) return;
-  const int qtiles = (Nq + 31) / 32;
+                                                       int kblocks32, const unsigned long long *__restrict__ cm,
+                                                       int8_t *out, double *scale) {
+  // block = 32 columns (one q tile) x 4 consecutive 32-row blocks (one 128-byte K step)
+  const int qt = blockIdx.x, qi = threadIdx.x & 31;
+  const int q = qt * 32 + qi;
+  const int ks = blockIdx.y, kb = ks * 4 + (threadIdx.x >> 5);
+  if (q >= Nq || kb >= kblocks32) return;
+  const int qtiles = gridDim.x;
   const double m = __longlong_as_double((long long)cm[q]);
   int ex = 0;
   if (m > 0.0) frexp(m, &ex);
@@ -331,7 +333,6 @@ __global__ void __launch_bounds__(128) slice_tc_kernel(const double *__restrict_
       words[t][r >> 2] |= ((uint32_t)((int)dg & 0xff)) << (8 * (r & 3));
     }
   }
-  const int ks = kb >> 2, qt = q >> 5, qi = q & 31;
 #pragma unroll
   for (int t = 0; t < T; ++t) {
     uint4 *dst = reinterpret_cast<uint4 *>(out + ((((int64_t)ks * qtiles + qt) * T + t) * 32 + qi) * 128 + (kb & 3) * 32);
@@ -340,14 +341,33 @@ __global__ void __launch_bounds__(128) slice_tc_kernel(const double *__restrict_
   }
 }
 
-__global__ void colmax_kernel_tc(const double *__restrict__ B, int64_t ldb, int K, int Nq, unsigned long long *cm) {
-  const int q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= Nq) return;
+// column maxima of |B|: 32 columns x 8 row lanes per block, coalesced along columns, 4 independent loads in flight
+__global__ void __launch_bounds__(256) colmax_kernel_tc(const double *__restrict__ B, int64_t ldb, int K, int Nq,
+                                                        unsigned long long *cm) {
+  __shared__ double red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int q = blockIdx.x * 32 + tx;
   const int per = (K + gridDim.y - 1) / gridDim.y;
   const int lo = blockIdx.y * per, hi = min(K, lo + per);
-  double m = 0.0;
-  for (int r = lo; r < hi; ++r) m = fmax(m, fabs(B[(int64_t)r * ldb + q]));
-  if (m > 0.0) atomicMax(cm + q, (unsigned long long)__double_as_longlong(m));
+  double m0 = 0.0, m1 = 0.0, m2 = 0.0, m3 = 0.0;
+  if (q < Nq) {
+    int r = lo + ty;
+    for (; r + 24 < hi; r += 32) {
+      m0 = fmax(m0, fabs(B[(int64_t)r * ldb + q]));
+      m1 = fmax(m1, fabs(B[(int64_t)(r + 8) * ldb + q]));
+      m2 = fmax(m2, fabs(B[(int64_t)(r + 16) * ldb + q]));
+      m3 = fmax(m3, fabs(B[(int64_t)(r + 24) * ldb + q]));
+    }
+    for (; r < hi; r += 8) m0 = fmax(m0, fabs(B[(int64_t)r * ldb + q]));
+  }
+  red[ty][tx] = fmax(fmax(m0, m1), fmax(m2, m3));
+  __syncthreads();
+  if (ty == 0 && q < Nq) {
+    double m = red[0][tx];
+#pragma unroll
+    for (int j = 1; j < 8; ++j) m = fmax(m, red[j][tx]);
+    if (m > 0.0) atomicMax(cm + q, (unsigned long long)__double_as_longlong(m));  // order-independent
+  }
 }
 
 size_t sliced_tc_bytes(int kblocks32, int Nq, int T) {
@@ -359,16 +379,17 @@ void launch_slice_tc(const Launcher &L, const double *Bmat, int64_t ldb, int K, 
                      double *scale, unsigned long long *cm) {
   if (Nq <= 0 || kblocks32 <= 0) return;
   CUDA_CHECK(cudaMemsetAsync(cm, 0, sizeof(unsigned long long) * Nq, L.stream));
-  int slabs = K / 256;
+  const int qtiles = (Nq + 31) / 32;
+  int slabs = (4 * L.sms + qtiles - 1) / qtiles;
+  if (slabs > (K + 63) / 64) slabs = (K + 63) / 64;
   if (slabs < 1) slabs = 1;
-  if (slabs > 8 * L.sms) slabs = 8 * L.sms;
-  colmax_kernel_tc<<<dim3((Nq + 127) / 128, slabs), 128, 0, L.stream>>>(Bmat, ldb, K, Nq, cm);
+  colmax_kernel_tc<<<dim3(qtiles, slabs), 256, 0, L.stream>>>(Bmat, ldb, K, Nq, cm);
   CUDA_CHECK(cudaGetLastError());
   ++*L.launch_counter;
-  dim3 grid((Nq + 127) / 128, kblocks32);
-  if (T == 6) slice_tc_kernel<6><<<grid, 128, 0, L.stream>>>(Bmat, ldb, K, Nq, cm, q, scale);
-  else if (T == 7) slice_tc_kernel<7><<<grid, 128, 0, L.stream>>>(Bmat, ldb, K, Nq, cm, q, scale);
-  else if (T == 8) slice_tc_kernel<8><<<grid, 128, 0, L.stream>>>(Bmat, ldb, K, Nq, cm, q, scale);
+  dim3 grid(qtiles, (kblocks32 + 3) / 4);
+  if (T == 6) slice_tc_kernel<6><<<grid, 128, 0, L.stream>>>(Bmat, ldb, K, Nq, kblocks32, cm, q, scale);
+  else if (T == 7) slice_tc_kernel<7><<<grid, 128, 0, L.stream>>>(Bmat, ldb, K, Nq, kblocks32, cm, q, scale);
+  else if (T == 8) slice_tc_kernel<8><<<grid, 128, 0, L.stream>>>(Bmat, ldb, K, Nq, kblocks32, cm, q, scale);
   else PPCA_THROW(PPCA_ERR_INVALID, "int8 path: T must be 6, 7 or 8 (got %d)", T);
   CUDA_CHECK(cudaGetLastError());
   ++*L.launch_counter;
@@ -376,11 +397,24 @@ void launch_slice_tc(const Launcher &L, const double *Bmat, int64_t ldb, int K, 
 
 int tbitgemm_pick_splitk(int M, int Nq, int ksteps, int sms) {
   const int64_t tiles = round_up(M, tb::BM) / tb::BM * (round_up(Nq, tb::NQ) / tb::NQ);
-  const int64_t max_s = ksteps / 8 > 0 ? ksteps / 8 : 1;  // at least 8 K steps (1024 rows) per slab
-  if (tiles >= 2 * sms) return 1;  // persistent kernel: enough tiles to balance
-  int64_t s = (2 * sms + tiles - 1) / tiles;
-  if (s > max_s) s = max_s;
-  return (int)(s < 1 ? 1 : s);
+  if (tiles >= 4 * sms) return 1;  // persistent kernel: enough tiles to balance
+  // fewest K slabs (>= 4 K steps = 512 rows each) that keep every persistent CTA busy in the last round
+  const int64_t max_s = ksteps / 4 > 0 ? ksteps / 4 : 1;
+  int best = 1;
+  double best_eff = 0.0;
+  for (int64_t s = 1; s <= max_s; ++s) {
+    const int64_t per = (ksteps + s - 1) / s;
+    if ((s - 1) * per >= ksteps) continue;  // would leave an empty slab
+    const int64_t ctas = tiles * s;
+    if (ctas < sms && s < max_s) continue;
+    const double eff = (double)ctas / (double)round_up(ctas, sms);
+    if (eff > best_eff + 1e-9) {
+      best_eff = eff;
+      best = (int)s;
+    }
+    if (eff >= 0.97) break;
+  }
+  return best;
 }
 
 template <int T>

@@ -355,14 +355,15 @@ def test_full_size_properties(pk):
 def int8_ctx(pk):
     ctx = pk.get_context()
     yield ctx
-    ctx.set_gemm("dmma")
+    ctx.set_gemm("tc", 7)  # the engine default
 
 
+@pytest.mark.parametrize("mode", ["dmma", "int8", "tc"])
 @pytest.mark.parametrize("slices", [7, 8])
 @pytest.mark.parametrize("n,d,k,p", [(100, 3, 2, 0.2), (777, 37, 5, 0.3), (3000, 200, 16, 0.2), (1200, 150, 32, 0.25),
-                                     (500, 260, 64, 0.3)])
-def test_int8_sliced_iterate(pk, orc, int8_ctx, slices, n, d, k, p):
-    int8_ctx.set_gemm("int8", slices)
+                                     (500, 260, 64, 0.3), (300, 20, 1, 0.1), (20000, 70, 10, 0.25)])
+def test_int8_sliced_iterate(pk, orc, int8_ctx, mode, slices, n, d, k, p):
+    int8_ctx.set_gemm(mode, slices)
     X, C0, mu0, s0 = _case(n, d, k, p, empty_rows=(4,), empty_dims=(d - 1,) if d > 3 else ())
     w = np.random.default_rng(11).random(n) + 0.5
     ds = pk.Dataset(X, w)
@@ -392,9 +393,28 @@ def test_int8_sliced_matches_dmma_closely(pk, int8_ctx):
     model = pk.PPCAModel(1.0, rng.standard_normal((d, k)), np.zeros(d))
     int8_ctx.set_gemm("dmma")
     a, llk_a = model._iterate(ds, None)
-    for slices, tol in ((8, 5e-13), (7, 5e-13), (6, 5e-11)):
-        int8_ctx.set_gemm("int8", slices)
+    for mode, slices, tol in (("int8", 8, 5e-13), ("int8", 7, 5e-13), ("int8", 6, 5e-11),
+                              ("tc", 8, 5e-13), ("tc", 7, 5e-13), ("tc", 6, 5e-11)):
+        int8_ctx.set_gemm(mode, slices)
         b, llk_b = model._iterate(ds, None)
-        assert rel_err(b.transform, a.transform) < tol and rel_err(b.mean, a.mean) < tol, slices
+        assert rel_err(b.transform, a.transform) < tol and rel_err(b.mean, a.mean) < tol, (mode, slices)
         assert abs(b.isotropic_noise - a.isotropic_noise) < tol * a.isotropic_noise
         assert abs(llk_b - llk_a) < tol * abs(llk_a)
+
+
+def test_dmma_mixture_and_inference(pk, orc, int8_ctx):
+    """Mixture EM and extrapolate with the FP64 DMMA contraction (the other tests run the tcgen05 default)."""
+    int8_ctx.set_gemm("dmma")
+    X, models, logw = _mix_case(pk, 900, 24, (3, 5, 2, 8))
+    w = np.random.default_rng(5).random(X.shape[0]) + 0.5
+    ds = pk.Dataset(X, w)
+    mix = pk.PPCAMix([pk.PPCAModel(s, C, mu) for C, mu, s in models], logw)
+    assert rel_err(mix.llks(ds), orc.mix_llks(X, models, logw)) < TOL
+    want_ex, want_ex_s = both(orc, orc.mix_smooth, X, models, logw, extrapolate=True)
+    assert_close(mix.extrapolate(ds).numpy(), want_ex, want_ex_s, "mix extrapolate")
+    new, llk = mix._iterate(ds, None)
+    (want_models, want_logw), (st_models, _) = both(orc, orc.mix_iterate, X, w, models, logw)
+    assert np.max(np.abs(new.log_weights - want_logw)) < 1e-9
+    for got, (Cw, muw, sw), (Cs, mus, ss) in zip(new.models, want_models, st_models):
+        assert_close(got.transform, Cw, Cs, "mix C")
+        assert_close(got.isotropic_noise, sw, ss, "mix sigma")
