@@ -144,52 +144,73 @@ __global__ void __launch_bounds__(tb::THREADS, 1) tbitgemm_kernel(TBitGemmArgs a
 
   if (warp < 4) {
     // ===================== producers =====================
+    // The (tile, K step) jobs of this CTA form one sequence.  Each thread publishes its part of a job with
+    // cp.async.mbarrier.arrive.noinc: the arrival on the stage's "full" barrier fires when the thread's cp.async
+    // copies have landed, so the producers never block on memory and up to STAGES jobs are in flight.
+    const int r = tid;  // row of the tile handled by this thread
+    int tiles_left = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    int tile_i = blockIdx.x, ks_i = 0, ks_end_i = 0, qt_i = 0;
+    const uint32_t *wrow = a.bits;
+    bool row_ok = false;
+    auto open_tile = [&]() {
+      const int z = tile_i / (mtiles * qtiles), rem = tile_i % (mtiles * qtiles);
+      qt_i = rem / mtiles;
+      const int mt = rem % mtiles;
+      ks_i = z * ks_per;
+      ks_end_i = min(a.ksteps, ks_i + ks_per);
+      const int row = mt * BM + r;
+      row_ok = row < a.M;
+      wrow = a.bits + (int64_t)(row_ok ? row : 0) * a.ldbits;
+    };
+    if (tiles_left > 0) open_tile();
+    while (tiles_left > 0 && ks_i >= ks_end_i) {  // skip empty K slabs
+      tile_i += gridDim.x;
+      if (--tiles_left > 0) open_tile();
+    }
+    auto load_words = [&](uint32_t (&w)[4]) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int wi = 4 * ks_i + j;
+        w[j] = (row_ok && wi < a.nwords) ? __ldg(wrow + wi) : 0u;
+      }
+    };
+    uint32_t w[4] = {0u, 0u, 0u, 0u};
+    if (tiles_left > 0) load_words(w);
     int stage = 0;
     uint32_t phase = 0;
-    const int r = tid;  // row of the tile handled by this thread
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const int z = tile / (mtiles * qtiles), rem = tile % (mtiles * qtiles);
-      const int qt = rem / mtiles, mt = rem % mtiles;
-      const int ks_begin = z * ks_per, ks_end = min(a.ksteps, ks_begin + ks_per);
-      const int row = mt * BM + r;
-      const bool row_ok = row < a.M;
-      const uint32_t *wrow = a.bits + (int64_t)(row_ok ? row : 0) * a.ldbits;
-      for (int ks = ks_begin; ks < ks_end; ++ks) {
-        // this K step's four mask words (issued before waiting for the slot)
-        uint32_t w[4];
+    while (tiles_left > 0) {
+      mbar_wait(empty_bar(stage), phase ^ 1u);
+      const uint32_t sA = smem_base + stage * STAGE_BYTES, sB = sA + A_BYTES;
+      const int8_t *src = a.Bq + ((int64_t)ks_i * qtiles + qt_i) * (int64_t)B_BYTES;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int wi = 4 * ks + j;
-          w[j] = (row_ok && wi < a.nwords) ? __ldg(wrow + wi) : 0u;
-        }
-        mbar_wait(empty_bar(stage), phase ^ 1u);
-        const uint32_t sA = smem_base + stage * STAGE_BYTES, sB = sA + A_BYTES;
-        // digit planes: N rows x 128 bytes, contiguous in global memory
-        const int8_t *src = a.Bq + ((int64_t)ks * qtiles + qt) * (int64_t)B_BYTES;
+      for (int j = 0; j < (N * 8) / PRODUCERS; ++j) {
+        const int idx = tid + PRODUCERS * j;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sB + sw128_off(idx >> 3, idx & 7)),
+                     "l"(src + idx * 16));
+      }
+      const uint32_t wc[4] = {w[0], w[1], w[2], w[3]};
+      // advance the cursor and prefetch the next job's mask words before expanding this job's
+      ++ks_i;
+      while (tiles_left > 0 && ks_i >= ks_end_i) {
+        tile_i += gridDim.x;
+        if (--tiles_left > 0) open_tile();
+      }
+      if (tiles_left > 0) load_words(w);
 #pragma unroll
-        for (int j = 0; j < (N * 8) / PRODUCERS; ++j) {
-          const int idx = tid + PRODUCERS * j;
-          const int n = idx >> 3, c = idx & 7;
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sB + sw128_off(n, c)), "l"(src + idx * 16));
-        }
-        asm volatile("cp.async.commit_group;" ::);
-        // mask bits -> int8 {0,1}, 16 bytes per chunk
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const uint32_t b = (w[c >> 1] >> ((c & 1) * 16)) & 0xFFFFu;
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sA + sw128_off(r, c)), "r"(nib4(b, 0)),
-                       "r"(nib4(b, 4)), "r"(nib4(b, 8)), "r"(nib4(b, 12))
-                       : "memory");
-        }
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        fence_proxy_async();
-        mbar_arrive(full_bar(stage));
-        if (++stage == STAGES) {
-          stage = 0;
-          phase ^= 1u;
-        }
+      for (int c = 0; c < 8; ++c) {
+        const uint32_t b = (wc[c >> 1] >> ((c & 1) * 16)) & 0xFFFFu;
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sA + sw128_off(r, c)), "r"(nib4(b, 0)),
+                     "r"(nib4(b, 4)), "r"(nib4(b, 8)), "r"(nib4(b, 12))
+                     : "memory");
+      }
+      fence_proxy_async();  // the st.shared tile above must be visible to the tensor core (async proxy)
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(full_bar(stage)) : "memory");
+      if (++stage == STAGES) {
+        stage = 0;
+        phase ^= 1u;
       }
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");
   } else if (warp == 4) {
     // ===================== MMA issuer =====================
     int stage = 0, buf = 0;
