@@ -6,8 +6,8 @@
 // tcgen05.mma.kind::i8 issued by one thread, with the accumulators of all T planes of a 128 x 32 output tile in
 // tensor memory (N = 32 T columns, double buffered).  Warp-specialised persistent kernel, one CTA per SM:
 //   warps 0-3  producers: expand the bit-packed mask rows to int8 {0,1} straight into the SWIZZLE_128B K-major
-//              shared-memory layout the MMA reads (the mask never exists as bytes in HBM), and cp.async the
-//              digit-plane tile into the same layout; fence.proxy.async; arrive on the stage's "full" mbarrier
+//              shared-memory layout the MMA reads (the mask never exists as bytes in HBM); the digit-plane tile,
+//              stored pre-swizzled, arrives by one cp.async.bulk per stage (mbarrier complete_tx)
 //   warp  4    MMA issuer: tcgen05.mma M=128, N=32T, K=32, four per 128-byte K step; tcgen05.commit frees the
 //              stage ("empty" mbarrier) and, after the last K step, publishes the accumulator ("tmem_full")
 //   warps 5-8  epilogue: tcgen05.ld the T planes of 8 columns at a time, recombine in FP64, scale, store
@@ -22,7 +22,8 @@ namespace ppca {
 
 namespace tb {
 
-constexpr int BM = 128, NQ = 32, BKB = 128, STAGES = 4;
+constexpr int MH = 1;             // 128-row MMA halves per tile (MH = 2 with NQ = 16 measured slower: producer bound)
+constexpr int BM = 128 * MH, NQ = 32, BKB = 128, STAGES = 4;
 constexpr int PRODUCERS = 128, THREADS = 288;
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -87,7 +88,7 @@ struct TBitGemmArgs {
   const uint32_t *bits;
   int64_t ldbits;     // words per bit row
   int nwords;         // valid words per bit row (reads at or beyond return 0)
-  const int8_t *Bq;   // [ksteps][qtiles][T*32][128]
+  const int8_t *Bq;   // [ksteps][qtiles][T*NQ][128]
   const double *scale;
   double *Out;
   int64_t ldo;
@@ -104,7 +105,10 @@ __global__ void __launch_bounds__(tb::THREADS, 1) tbitgemm_kernel(TBitGemmArgs a
   using namespace tb;
   constexpr int N = T * NQ;
   constexpr uint32_t A_BYTES = BM * BKB, B_BYTES = N * BKB, STAGE_BYTES = A_BYTES + B_BYTES;
-  constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+  constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  constexpr int TCOLS = MH * N;  // TMEM columns per accumulator buffer
+  static_assert(MH == 1 && (STAGES & (STAGES - 1)) == 0, "producer groups assume one 128-row half and 2^n stages");
+  static_assert(2 * TCOLS <= 512, "two accumulator buffers must fit the 512 TMEM columns");
   extern __shared__ unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * STAGES + 4];
   __shared__ uint32_t tmem_base_slot;
@@ -119,7 +123,7 @@ __global__ void __launch_bounds__(tb::THREADS, 1) tbitgemm_kernel(TBitGemmArgs a
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar(s), PRODUCERS);
+      mbar_init(full_bar(s), 64 + 1);  // the 64 mask expanders of the group that owns the job + its bulk-copy issue
       mbar_init(empty_bar(s), 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -144,73 +148,95 @@ __global__ void __launch_bounds__(tb::THREADS, 1) tbitgemm_kernel(TBitGemmArgs a
 
   if (warp < 4) {
     // ===================== producers =====================
-    // The (tile, K step) jobs of this CTA form one sequence.  Each thread publishes its part of a job with
-    // cp.async.mbarrier.arrive.noinc: the arrival on the stage's "full" barrier fires when the thread's cp.async
-    // copies have landed, so the producers never block on memory and up to STAGES jobs are in flight.
-    const int r = tid;  // row of the tile handled by this thread
+    // The (tile, K step) jobs of this CTA form one sequence.  The four producer warps work as two groups of 64
+    // threads that take alternate jobs, so each group has two MMA periods per job and its mask-word loads (issued
+    // one own job ahead) are covered.  Per job: one thread issues ONE cp.async.bulk of the pre-swizzled digit-plane
+    // tile (completion counted in bytes on the stage's "full" mbarrier); every thread of the group expands two
+    // mask rows into the A tile, fences the generic->async proxy and arrives.
+    const int grp = warp >> 1, gt = tid & 63;  // group, thread within group: rows gt and gt + 64
     int tiles_left = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     int tile_i = blockIdx.x, ks_i = 0, ks_end_i = 0, qt_i = 0;
-    const uint32_t *wrow = a.bits;
-    bool row_ok = false;
+    const uint32_t *wrow[2] = {a.bits, a.bits};
+    bool row_ok[2] = {false, false};
     auto open_tile = [&]() {
       const int z = tile_i / (mtiles * qtiles), rem = tile_i % (mtiles * qtiles);
       qt_i = rem / mtiles;
       const int mt = rem % mtiles;
       ks_i = z * ks_per;
       ks_end_i = min(a.ksteps, ks_i + ks_per);
-      const int row = mt * BM + r;
-      row_ok = row < a.M;
-      wrow = a.bits + (int64_t)(row_ok ? row : 0) * a.ldbits;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int row = mt * BM + 64 * h + gt;
+        row_ok[h] = row < a.M;
+        wrow[h] = a.bits + (int64_t)(row_ok[h] ? row : 0) * a.ldbits;
+      }
+    };
+    auto advance = [&]() {  // to the next job of the sequence
+      ++ks_i;
+      while (tiles_left > 0 && ks_i >= ks_end_i) {
+        tile_i += gridDim.x;
+        if (--tiles_left > 0) open_tile();
+      }
     };
     if (tiles_left > 0) open_tile();
     while (tiles_left > 0 && ks_i >= ks_end_i) {  // skip empty K slabs
       tile_i += gridDim.x;
       if (--tiles_left > 0) open_tile();
     }
-    auto load_words = [&](uint32_t (&w)[4]) {
+    auto load_words = [&](uint32_t (&w)[2][4]) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int wi = 4 * ks_i + j;
-        w[j] = (row_ok && wi < a.nwords) ? __ldg(wrow + wi) : 0u;
-      }
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int wi = 4 * ks_i + j;
+          w[h][j] = (row_ok[h] && wi < a.nwords) ? __ldg(wrow[h] + wi) : 0u;
+        }
     };
-    uint32_t w[4] = {0u, 0u, 0u, 0u};
+    int job = 0;
+    if (grp == 1 && tiles_left > 0) {  // group 1 starts at job 1
+      advance();
+      job = 1;
+    }
+    uint32_t w[2][4];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) w[h][0] = w[h][1] = w[h][2] = w[h][3] = 0u;
     if (tiles_left > 0) load_words(w);
-    int stage = 0;
-    uint32_t phase = 0;
     while (tiles_left > 0) {
+      const int stage = job & (STAGES - 1);
+      const uint32_t phase = (uint32_t)(job / STAGES) & 1u;
       mbar_wait(empty_bar(stage), phase ^ 1u);
       const uint32_t sA = smem_base + stage * STAGE_BYTES, sB = sA + A_BYTES;
-      const int8_t *src = a.Bq + ((int64_t)ks_i * qtiles + qt_i) * (int64_t)B_BYTES;
+      if (gt == 0) {
+        const int8_t *src = a.Bq + ((int64_t)ks_i * qtiles + qt_i) * (int64_t)B_BYTES;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full_bar(stage)), "r"(B_BYTES)
+                     : "memory");
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sB),
+            "l"(src), "r"(B_BYTES), "r"(full_bar(stage))
+            : "memory");
+      }
+      uint32_t wc[2][4];
 #pragma unroll
-      for (int j = 0; j < (N * 8) / PRODUCERS; ++j) {
-        const int idx = tid + PRODUCERS * j;
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sB + sw128_off(idx >> 3, idx & 7)),
-                     "l"(src + idx * 16));
-      }
-      const uint32_t wc[4] = {w[0], w[1], w[2], w[3]};
-      // advance the cursor and prefetch the next job's mask words before expanding this job's
-      ++ks_i;
-      while (tiles_left > 0 && ks_i >= ks_end_i) {
-        tile_i += gridDim.x;
-        if (--tiles_left > 0) open_tile();
-      }
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) wc[h][j] = w[h][j];
+      // move the cursor two jobs on (the other group owns the next one) and fetch that job's mask words now
+      advance();
+      if (tiles_left > 0) advance();
+      job += 2;
       if (tiles_left > 0) load_words(w);
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const uint32_t b = (wc[c >> 1] >> ((c & 1) * 16)) & 0xFFFFu;
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sA + sw128_off(r, c)), "r"(nib4(b, 0)),
-                     "r"(nib4(b, 4)), "r"(nib4(b, 8)), "r"(nib4(b, 12))
-                     : "memory");
-      }
-      fence_proxy_async();  // the st.shared tile above must be visible to the tensor core (async proxy)
-      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(full_bar(stage)) : "memory");
-      if (++stage == STAGES) {
-        stage = 0;
-        phase ^= 1u;
-      }
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint32_t b = (wc[h][c >> 1] >> ((c & 1) * 16)) & 0xFFFFu;
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sA + sw128_off(64 * h + gt, c)),
+                       "r"(nib4(b, 0)), "r"(nib4(b, 4)), "r"(nib4(b, 8)), "r"(nib4(b, 12))
+                       : "memory");
+        }
+      fence_proxy_async();  // the st.shared rows above must be visible to the tensor core (async proxy)
+      mbar_arrive(full_bar(stage));
     }
-    asm volatile("cp.async.wait_all;" ::: "memory");
   } else if (warp == 4) {
     // ===================== MMA issuer =====================
     int stage = 0, buf = 0;
@@ -220,7 +246,7 @@ __global__ void __launch_bounds__(tb::THREADS, 1) tbitgemm_kernel(TBitGemmArgs a
       const int ks_begin = z * ks_per, ks_end = min(a.ksteps, ks_begin + ks_per);
       mbar_wait(tempty_bar(buf), tphase ^ 1u);
       tc_fence_after();
-      const uint32_t tmem_c = tmem_base + (uint32_t)(buf * N);
+      const uint32_t tmem_c = tmem_base + (uint32_t)(buf * TCOLS);
       if (ks_begin >= ks_end) {  // empty K slab (never produced by the host-side split): publish immediately
         if (lane == 0) tc_commit(tfull_bar(buf));
         __syncwarp();
@@ -230,11 +256,13 @@ __global__ void __launch_bounds__(tb::THREADS, 1) tbitgemm_kernel(TBitGemmArgs a
         tc_fence_after();
         if (lane == 0) {
           const uint32_t sA = smem_base + stage * STAGE_BYTES, sB = sA + A_BYTES;
-          const uint64_t adesc = smem_desc_sw128(sA), bdesc = smem_desc_sw128(sB);
+          const uint64_t bdesc = smem_desc_sw128(sB);
 #pragma unroll
           for (int k = 0; k < BKB / 32; ++k)
-            tc_mma_i8(tmem_c, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC,
-                      (ks > ks_begin || k > 0) ? 1u : 0u);
+#pragma unroll
+            for (int h = 0; h < MH; ++h)
+              tc_mma_i8(tmem_c + (uint32_t)(h * N), smem_desc_sw128(sA + h * (128 * BKB)) + (uint64_t)(2 * k),
+                        bdesc + (uint64_t)(2 * k), IDESC, (ks > ks_begin || k > 0) ? 1u : 0u);
           tc_commit(empty_bar(stage));
           if (ks == ks_end - 1) tc_commit(tfull_bar(buf));
         }
@@ -257,7 +285,6 @@ __global__ void __launch_bounds__(tb::THREADS, 1) tbitgemm_kernel(TBitGemmArgs a
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int z = tile / (mtiles * qtiles), rem = tile % (mtiles * qtiles);
       const int qt = rem / mtiles, mt = rem % mtiles;
-      const int row = mt * BM + quarter * 32 + lane;
       const bool empty_slab = z * ks_per >= min(a.ksteps, z * ks_per + ks_per);
       double *out;
       int64_t ldo;
@@ -273,33 +300,37 @@ __global__ void __launch_bounds__(tb::THREADS, 1) tbitgemm_kernel(TBitGemmArgs a
       }
       mbar_wait(tfull_bar(buf), tphase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * N);
 #pragma unroll 1
-      for (int qc = 0; qc < NQ / 8; ++qc) {
-        int rg[T][8];
+      for (int h = 0; h < MH; ++h) {
+        const int row = mt * BM + 128 * h + quarter * 32 + lane;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * TCOLS + h * N);
+#pragma unroll 1
+        for (int qc = 0; qc < NQ / 8; ++qc) {
+          int rg[T][8];
 #pragma unroll
-        for (int t = 0; t < T; ++t) tc_ld8(taddr + (uint32_t)(t * NQ + 8 * qc), rg[t]);
-        tc_wait_ld();
-        const int q = qt * NQ + 8 * qc;
-        if (row < a.M && q < a.Nq) {
-          double v[8];
+          for (int t = 0; t < T; ++t) tc_ld8(taddr + (uint32_t)(t * NQ + 8 * qc), rg[t]);
+          tc_wait_ld();
+          const int q = qt * NQ + 8 * qc;
+          if (row < a.M && q < a.Nq) {
+            double v[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            double acc = (double)rg[T - 1][j];
+            for (int j = 0; j < 8; ++j) {
+              double acc = (double)rg[T - 1][j];
 #pragma unroll
-            for (int t = T - 2; t >= 0; --t) acc = fma(acc, 1.0 / 128.0, (double)rg[t][j]);
-            v[j] = empty_slab ? 0.0 : acc * (a.scale[q + j] * (1.0 / 64.0));
-          }
-          double2 *p = reinterpret_cast<double2 *>(out + (int64_t)row * ldo + q);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            double2 val = make_double2(v[2 * j], v[2 * j + 1]);
-            if (accumulate) {
-              const double2 o = p[j];
-              val.x += o.x;
-              val.y += o.y;
+              for (int t = T - 2; t >= 0; --t) acc = fma(acc, 1.0 / 128.0, (double)rg[t][j]);
+              v[j] = empty_slab ? 0.0 : acc * (a.scale[q + j] * (1.0 / 64.0));
             }
-            p[j] = val;
+            double2 *p = reinterpret_cast<double2 *>(out + (int64_t)row * ldo + q);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              double2 val = make_double2(v[2 * j], v[2 * j + 1]);
+              if (accumulate) {
+                const double2 o = p[j];
+                val.x += o.x;
+                val.y += o.y;
+              }
+              p[j] = val;
+            }
           }
         }
       }
@@ -321,18 +352,18 @@ __global__ void __launch_bounds__(tb::THREADS, 1) tbitgemm_kernel(TBitGemmArgs a
 }
 
 // ---------------------------------------------------------------------------------------------
-// digit planes in the layout above: [kstep][qtile][t * 32 + qi][128 bytes], natural byte order
+// digit planes: [kstep][qtile] tiles, each the exact SWIZZLE_128B shared-memory image of (T NQ rows) x 128 bytes
 // ---------------------------------------------------------------------------------------------
 template <int T>
 __global__ void __launch_bounds__(128) slice_tc_kernel(const double *__restrict__ B, int64_t ldb, int K, int Nq,
                                                        int kblocks32, const unsigned long long *__restrict__ cm,
                                                        int8_t *out, double *scale) {
-  // block = 32 columns (one q tile) x 4 consecutive 32-row blocks (one 128-byte K step)
-  const int qt = blockIdx.x, qi = threadIdx.x & 31;
-  const int q = qt * 32 + qi;
+  // block = 32 columns x 4 consecutive 32-row blocks (one 128-byte K step)
+  const int q = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int qt = q / tb::NQ, qi = q % tb::NQ;
   const int ks = blockIdx.y, kb = ks * 4 + (threadIdx.x >> 5);
   if (q >= Nq || kb >= kblocks32) return;
-  const int qtiles = gridDim.x;
+  const int qtiles = (Nq + tb::NQ - 1) / tb::NQ;
   const double m = __longlong_as_double((long long)cm[q]);
   int ex = 0;
   if (m > 0.0) frexp(m, &ex);
@@ -356,9 +387,14 @@ __global__ void __launch_bounds__(128) slice_tc_kernel(const double *__restrict_
   }
 #pragma unroll
   for (int t = 0; t < T; ++t) {
-    uint4 *dst = reinterpret_cast<uint4 *>(out + ((((int64_t)ks * qtiles + qt) * T + t) * 32 + qi) * 128 + (kb & 3) * 32);
-    dst[0] = make_uint4(words[t][0], words[t][1], words[t][2], words[t][3]);
-    dst[1] = make_uint4(words[t][4], words[t][5], words[t][6], words[t][7]);
+    // shared-memory image of the SWIZZLE_128B K-major tile: row n = t NQ + qi, 16-byte chunks 2 (kb & 3) and + 1
+    int8_t *tile = out + ((int64_t)ks * qtiles + qt) * (int64_t)(T * tb::NQ * 128);
+    const int n = t * tb::NQ + qi, c0 = 2 * (kb & 3);
+    const int base = (n >> 3) * 1024 + (n & 7) * 128;
+    *reinterpret_cast<uint4 *>(tile + base + (((c0) ^ (n & 7)) << 4)) =
+        make_uint4(words[t][0], words[t][1], words[t][2], words[t][3]);
+    *reinterpret_cast<uint4 *>(tile + base + (((c0 + 1) ^ (n & 7)) << 4)) =
+        make_uint4(words[t][4], words[t][5], words[t][6], words[t][7]);
   }
 }
 
@@ -392,15 +428,15 @@ __global__ void __launch_bounds__(256) colmax_kernel_tc(const double *__restrict
 }
 
 size_t sliced_tc_bytes(int kblocks32, int Nq, int T) {
-  const int64_t ks = (kblocks32 + 3) / 4, qt = (Nq + 31) / 32;
-  return (size_t)(ks * qt * T * 32 * 128);
+  const int64_t ks = (kblocks32 + 3) / 4, qt = (Nq + tb::NQ - 1) / tb::NQ;
+  return (size_t)(ks * qt * T * tb::NQ * 128);
 }
 
 void launch_slice_tc(const Launcher &L, const double *Bmat, int64_t ldb, int K, int Nq, int kblocks32, int T, int8_t *q,
                      double *scale, unsigned long long *cm) {
   if (Nq <= 0 || kblocks32 <= 0) return;
   CUDA_CHECK(cudaMemsetAsync(cm, 0, sizeof(unsigned long long) * Nq, L.stream));
-  const int qtiles = (Nq + 31) / 32;
+  const int qtiles = (Nq + 31) / 32;  // 32-column thread blocks (independent of the MMA tile width)
   int slabs = (4 * L.sms + qtiles - 1) / qtiles;
   if (slabs > (K + 63) / 64) slabs = (K + 63) / 64;
   if (slabs < 1) slabs = 1;
