@@ -13,6 +13,8 @@
 //
 // This is the generic (any k) shared-memory kernel: the (k+1) x k augmented matrix [M ; y^T] lives in shared
 // memory, one per warp; L^{-1} is built in the unused strict upper triangle.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "mma.cuh"
 
@@ -457,6 +459,163 @@ __global__ void __launch_bounds__(256, 1) solve_reg64_kernel(SolveArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// 32 < k <= 64, second variant: 128 threads per sample.  Thread (i, h) owns columns [32 h, 32 h + 32) of row i,
+// so the per-pivot dependent chain is 32 FMAs instead of 64, registers halve (two CTAs of two samples per SM)
+// and twice as many warps hide the exchange / reciprocal latency.  Same elimination as above; the column
+// exchange carries both the symmetric-transformed value (pivot row) and the raw value (this row's multiplier).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void quad_sync(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+
+__global__ void __launch_bounds__(256, 2) solve_split64_kernel(SolveArgs a) {
+  constexpr int KP = 64, CW = 32;
+  extern __shared__ __align__(16) double smem_reg[];
+  const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+  const int smp = wi >> 2;                       // sample slot in the CTA (0, 1)
+  const int ws = wi & 3;                         // warp within the sample
+  const int li = (ws & 1) * 32 + lane;           // row
+  const int h = ws >> 1;                         // column half
+  const int c0 = CW * h;
+  const int bar_id = smp + 1;
+  const int k = a.s.k, kkp = a.s.kkp, kp = a.s.kp;
+  const int per_smp = kkp + 2 * 128 + 64 + 128 + 16;
+  double *stage = smem_reg + (size_t)smp * per_smp;  // one packed row
+  double *col = stage + kkp;                         // [2][64 transformed | 64 raw]
+  double *yb = col + 256;                            // [64]
+  double *zpart = yb + 64;                           // [2][64] partial z per column half
+  double *red = zpart + 128;                         // [16]
+  const double s2 = a.sigma * a.sigma;
+  const double ln_sigma = log(a.sigma);
+
+  for (int row = blockIdx.x * 2 + smp; row < a.rows_pad; row += gridDim.x * 2) {
+    double *gsrc = a.GW + (int64_t)row * kkp;
+    const int ts = ws * 32 + lane;  // 0..127
+    for (int q = ts * 2; q < kkp; q += 256)
+      *reinterpret_cast<double2 *>(stage + q) = *reinterpret_cast<const double2 *>(gsrc + q);
+    if (h == 0) yb[li] = (li < kp) ? a.YZ[(int64_t)row * kp + li] : 0.0;
+    const int dn = row < a.rows ? a.dn[row] : 0;
+    const bool empty = dn == 0;
+    const double w = (a.w && row < a.rows) ? a.w[row] : (row < a.rows ? 1.0 : 0.0);
+    quad_sync(bar_id);
+
+    const bool live = li < k && !empty;
+    const int up = tri_row_off(li, k) - li;
+    double A[CW];
+#pragma unroll
+    for (int jj = 0; jj < CW; ++jj) {
+      const int j = c0 + jj;
+      int idx = (j >= li) ? up + j : ((j * (2 * k - j - 1)) >> 1) + li;
+      const bool use = live && j < k;
+      idx = use ? idx : 0;
+      const double g = stage[idx];
+      const double unit = (j == li) ? 1.0 : 0.0;
+      A[jj] = use ? fma(unit, s2, g) : unit;
+    }
+
+    double mypiv = 1.0, myinv = 1.0;
+#pragma unroll
+    for (int p = 0; p < KP; ++p) {
+      double *cb = col + (p & 1) * 128;  // [0,64) transformed column, [64,128) raw column
+      if (h == (p >> 5)) {
+        const double v = A[p & 31];
+        cb[li] = (li < p) ? -v * myinv : v;
+        cb[64 + li] = v;
+      }
+      quad_sync(bar_id);
+      const double dpp = cb[p];
+      const double inv = fast_rcp(dpp);
+      if (li == p) {
+        mypiv = dpp;
+        myinv = inv;
+      }
+      const double f = (li == p) ? 0.0 : cb[64 + li] * inv;
+      const double2 *cb2 = reinterpret_cast<const double2 *>(cb + c0);
+#pragma unroll
+      for (int jj = 0; jj < CW; jj += 2) {
+        const double2 cv = cb2[jj >> 1];
+        A[jj] = fma(-f, cv.x, A[jj]);
+        A[jj + 1] = fma(-f, cv.y, A[jj + 1]);
+      }
+      if (h == (p >> 5)) A[p & 31] = (li == p) ? 1.0 : -f;
+    }
+#pragma unroll
+    for (int jj = 0; jj < CW; ++jj) A[jj] *= myinv;  // A[jj] = M^{-1}[li][c0 + jj]
+
+    double zp = 0.0;
+#pragma unroll
+    for (int jj = 0; jj < CW; ++jj) zp = fma(A[jj], yb[c0 + jj], zp);
+    zpart[h * 64 + li] = live ? zp : 0.0;
+    double ld = warp_sum((live && h == 0) ? log(mypiv) : 0.0);
+    if (lane == 0) red[ws] = ld;
+    quad_sync(bar_id);
+    const double zi = zpart[li] + zpart[64 + li];
+    double quad = warp_sum(h == 0 ? yb[li] * zi : 0.0);
+    if (lane == 0) red[4 + ws] = quad;
+    double tpart = 0.0;
+    if (a.mode == 2) {  // t = sigma^2 sum_i (1 - sigma^2 M^{-1}_ii): the diagonal lives in half h = i / 32
+      double diag = 0.0;
+#pragma unroll
+      for (int jj = 0; jj < CW; ++jj)
+        if (c0 + jj == li) diag = A[jj];
+      tpart = warp_sum((live && h == (li >> 5)) ? fma(-s2, diag, 1.0) : 0.0);
+      if (lane == 0) red[8 + ws] = tpart;
+    }
+    quad_sync(bar_id);
+    if (ts == 0 && row < a.rows) {
+      if (a.llk) {
+        double llk = 0.0;
+        if (!empty)
+          llk = -0.5 * (a.nx[row] - (red[4] + red[5])) / s2 -
+                0.5 * ((red[0] + red[1]) + 2.0 * ln_sigma * (double)(dn - k)) - 0.5 * LN_2PI * (double)dn;
+        a.llk[row] = llk;
+      }
+      if (a.mode == 2 && a.tn) a.tn[row] = empty ? 0.0 : s2 * (red[8] + red[9] + red[10] + red[11]);
+    }
+    if (a.mode != 0) {
+      if (h == 0 && li < kp) {
+        a.YZ[(int64_t)row * kp + li] = zi;
+        if (a.WZ) a.WZ[(int64_t)row * kp + li] = w * zi;
+      }
+      if (a.cov && row < a.rows && li < k) {
+        double *cv = a.cov + (int64_t)row * k * k + (int64_t)li * k;
+#pragma unroll
+        for (int jj = 0; jj < CW; ++jj)
+          if (c0 + jj < k) cv[c0 + jj] = empty ? (c0 + jj == li ? 1.0 : 0.0) : s2 * A[jj];
+      }
+    }
+    if (a.mode == 2) {
+      // all reads of G are done (gather happened before the elimination barriers); W overwrites it in place
+      if (li < k) {
+        double *so = stage + up;
+        const double ws2 = empty ? 0.0 : w * s2, wzi = empty ? 0.0 : w * zi;
+#pragma unroll
+        for (int jj = 0; jj < CW; ++jj) {
+          const int j = c0 + jj;
+          if (j >= li && j < k) so[j] = fma(wzi, zpart[j] + zpart[64 + j], ws2 * A[jj]);
+        }
+      }
+      quad_sync(bar_id);
+      for (int q = ts * 2; q < kkp; q += 256)
+        *reinterpret_cast<double2 *>(gsrc + q) = *reinterpret_cast<const double2 *>(stage + q);
+    }
+    quad_sync(bar_id);
+  }
+}
+
+static void launch_solve_split64(const Launcher &L, const SolveArgs &a) {
+  const size_t smem = (size_t)2 * (a.s.kkp + 2 * 128 + 64 + 128 + 16) * sizeof(double);
+  static bool configured = false;
+  if (!configured) {
+    CUDA_CHECK(cudaFuncSetAttribute(solve_split64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    configured = true;
+  }
+  int64_t blocks = (a.rows_pad + 1) / 2;
+  if (blocks > 2 * (int64_t)L.sms) blocks = 2 * (int64_t)L.sms;
+  solve_split64_kernel<<<(unsigned)blocks, 256, smem, L.stream>>>(a);
+  CUDA_CHECK(cudaGetLastError());
+  ++*L.launch_counter;
+}
+
 static void launch_solve_reg64(const Launcher &L, const SolveArgs &a) {
   const size_t smem = (size_t)4 * (a.s.kkp + 5 * 64) * sizeof(double);
   static bool configured = false;
@@ -560,7 +719,11 @@ void launch_solve(const Launcher &L, const SolveArgs &a) {
   if (a.s.k <= 8) launch_solve_reg<8>(L, a);
   else if (a.s.k <= 16) launch_solve_reg<16>(L, a);
   else if (a.s.k <= 32) launch_solve_reg<32>(L, a);
-  else if (a.s.k <= 64) launch_solve_reg64(L, a);
+  else if (a.s.k <= 64) {
+    static const bool use_pair = getenv("PPCA_B200_SOLVE64") && atoi(getenv("PPCA_B200_SOLVE64")) == 1;
+    if (use_pair) launch_solve_reg64(L, a);
+    else launch_solve_split64(L, a);
+  }
   else launch_solve_generic(L, a);
   if (a.part) {
     solve_reduce_kernel<<<SOLVE_SLOTS, 256, 0, L.stream>>>(a.rows, a.llk, a.tn, a.dn, a.w, a.part);
