@@ -341,7 +341,7 @@ def run_ours(args, wl, rank, world, local_rank):
             kern = f"ibitgemm_kernel<{args.slices}> (mma.sync IMMA; E-step + M-step launches)"
         roofline = dict(common, kernel=kern, achieved=tops, peak=peak, unit="TOP/s", frac=(tops / peak) if tops else None,
                         peak_source=psrc,
-                        note=f"exact int8-sliced evaluation: {args.slices} signed 7-bit digit planes per FP64 operand, "
+                        note=f"exact int8-sliced evaluation: {args.slices} balanced base-256 digit planes (int8) per FP64 operand, "
                              "int32 accumulation, FP64 recombination; achieved counts 2*rows*d*kk*slices int8 ops per launch")
 
     # ---- CPU baseline on a bounded sample of the same workload (rank 0, N=1 only) ----------------
@@ -383,7 +383,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--gemm", default=os.environ.get("PPCA_B200_GEMM", "tc"), choices=["dmma", "int8", "tc"],
                     help="arithmetic path of the masked-Gram contractions (see include/ppca_b200.h)")
-    ap.add_argument("--slices", type=int, default=int(os.environ.get("PPCA_B200_SLICES", "7")))
+    ap.add_argument("--slices", type=int, default=int(os.environ.get("PPCA_B200_SLICES", "6")))
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))

@@ -73,11 +73,12 @@ int32_t ppca_b200_ctx_synchronize(ppca_b200_ctx *ctx);
 int32_t ppca_b200_ctx_set_chunk(ppca_b200_ctx *ctx, int64_t chunk_samples);
 /* Arithmetic path of the two masked-Gram contractions (E-step Gram matrices, M-step second moments):
  *   mode 0 = FP64 tensor cores (mma.sync DMMA);
- *   mode 1 = exact int8-sliced evaluation on the int8 tensor path: the {0,1} mask times `slices` signed 7-bit
- *            digit planes of the FP64 operand, int32 accumulation (exact), FP64 recombination.  slices in {6,7,8};
- *            7 keeps every term to 2^-49 of its column scale (below FP64 dot-product rounding).  mma.sync IMMA.
+ *   mode 1 = exact int8-sliced evaluation on the int8 tensor path: the {0,1} mask times `slices` balanced base-256
+ *            digit planes (int8) of the FP64 operand, int32 accumulation (exact), FP64 recombination.  slices in
+ *            {6,7,8} keep every term to 46 / 54 / 62 bits below its column scale (6: below FP64 dot-product
+ *            rounding; 7: every FP64 input exactly).  mma.sync IMMA.
  *   mode 2 = the same arithmetic on tcgen05.mma.kind::i8 with the accumulators in tensor memory.
- * Default: mode 2 with 7 slices; the environment overrides it: PPCA_B200_GEMM=dmma|int8|tc, PPCA_B200_SLICES=6|7|8. */
+ * Default: mode 2 with 6 slices; the environment overrides it: PPCA_B200_GEMM=dmma|int8|tc, PPCA_B200_SLICES=6|7|8. */
 int32_t ppca_b200_ctx_set_gemm(ppca_b200_ctx *ctx, int32_t mode, int32_t slices);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 int32_t ppca_b200_ctx_launch_count(ppca_b200_ctx *ctx, int64_t *out);

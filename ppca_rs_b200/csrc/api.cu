@@ -31,7 +31,7 @@ struct ppca_b200_ctx {
   int64_t launches = 0;
   int64_t chunk = 0;  // 0 = automatic
   int gemm_mode = 2;  // 0 = DMMA, 1 = int8-sliced on mma.sync (ibitgemm.cu), 2 = int8-sliced on tcgen05 (tbitgemm.cu)
-  int slices = 7;
+  int slices = 6;
   DevBuf<int8_t> KsymQ, WQ;
   DevBuf<double> KsymScale, WScale;
   DevBuf<unsigned long long> colmax;

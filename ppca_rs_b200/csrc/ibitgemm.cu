@@ -3,11 +3,12 @@
 //   Out[M x Nq] (+)= Bits[M x K] * Bmat[K x Nq]
 //
 // The left operand is a {0,1} bit matrix, so every output is a plain sum of selected FP64 numbers.  Each column
-// of Bmat is scaled by a power of two s_q >= max|column| and split into T signed 7-bit digits (base 128,
-// digits in [-64, 64]):  x / s_q * 64 = sum_t digit_t * 128^-t  + r,  |r| <= 0.5 * 128^-(T-1).
-// One int8 x int8 -> int32 tensor MMA per digit plane accumulates sum_k bit * digit EXACTLY (|sum| <= 64 K < 2^31),
-// and the epilogue recombines the T planes in FP64 by Horner.  With T = 7 the only error is the 2^-49 s_q
-// truncation of each term (below the rounding error of an FP64 dot product); there is no accumulation error.
+// of Bmat is scaled by a power of two s_q > max|column| and split into T balanced base-256 digits
+// (int8, [-128, 127]; the leading digit stays within +-65):  v = rint(x / s_q * 2^(8T-2)) = sum_t digit_t 256^(T-1-t),
+// i.e. x is kept to 8T-2 bits below its column scale (46 bits for T = 6, 54 for T = 7).
+// One int8 x int8 -> int32 tensor MMA per digit plane accumulates sum_k bit * digit EXACTLY (|sum| <= 128 K < 2^31),
+// and the epilogue recombines the T planes in FP64 by Horner.  The only error is that 2^-(8T-1) s_q rounding of each
+// term (below the rounding error of an FP64 dot product for T >= 6); there is no accumulation error.
 // B200: legacy mma.sync.m16n8k32.s8 runs at 1144 TOP/s (profiles/r01_imma_peak.json), i.e. 163 TFLOP/s
 // FP64-equivalent at T = 7 against 37 TFLOP/s for DMMA.  Same operands, same references as bitgemm.cu:
 //   E-step Gs = Mask * Ksym (output_covariance.rs:57-59 after :123-131), M-step A += Mask^T W (ppca_model.rs:297-306).
@@ -34,6 +35,14 @@ __global__ void colmax_kernel(const double *__restrict__ B, int64_t ldb, int K, 
 // position of K-row r (0..31) inside the 32-byte group: thread t of a quad reads bytes [8t, 8t+8) as (b0, b1)
 __host__ __device__ constexpr int perm32(int r) { return ((r & 15) >> 2) * 8 + (r >> 4) * 4 + (r & 3); }
 
+// rint(xs) as T balanced base-256 digits packed little-endian (byte t = digit of weight 256^t); |xs| <= 2^(8T-2)
+template <int T>
+__device__ __forceinline__ unsigned long long digit_bytes(double xs) {
+  constexpr unsigned long long BIAS = 0x0080808080808080ull & ((1ull << (8 * (T - 1))) - 1ull);  // +128 below the top digit
+  const long long v = __double2ll_rn(xs) + (long long)BIAS;
+  return (unsigned long long)v ^ BIAS;  // low digits: byte - 128 == byte ^ 0x80 as int8; top digit: signed as is
+}
+
 template <int T>
 __global__ void __launch_bounds__(128) slice_kernel(const double *__restrict__ B, int64_t ldb, int K, int Nq,
                                                     const unsigned long long *__restrict__ cm, int8_t *out,
@@ -46,7 +55,7 @@ __global__ void __launch_bounds__(128) slice_kernel(const double *__restrict__ B
   if (m > 0.0) frexp(m, &ex);  // m = f 2^ex, f in [0.5, 1)  =>  |x| < 2^ex
   const double s = ldexp(1.0, ex);
   if (kb == 0) scale[q] = s;
-  const double inv = ldexp(64.0, -ex);
+  const double inv = ldexp(1.0, 8 * T - 2 - ex);
   uint32_t words[T][8];
 #pragma unroll
   for (int t = 0; t < T; ++t)
@@ -55,15 +64,12 @@ __global__ void __launch_bounds__(128) slice_kernel(const double *__restrict__ B
 #pragma unroll
   for (int r = 0; r < 32; ++r) {
     const int row = kb * 32 + r;
-    double xs = (row < K) ? B[(int64_t)row * ldb + q] * inv : 0.0;
+    const double x = (row < K) ? B[(int64_t)row * ldb + q] : 0.0;
     const int p = perm32(r);
+    const unsigned long long v = digit_bytes<T>(x * inv);
 #pragma unroll
-    for (int t = 0; t < T; ++t) {
-      const double dg = rint(xs);
-      xs = (xs - dg) * 128.0;
-      const int di = (int)dg;
-      words[t][p >> 2] |= ((uint32_t)(di & 0xff)) << (8 * (p & 3));
-    }
+    for (int t = 0; t < T; ++t)  // plane 0 = most significant digit
+      words[t][p >> 2] |= (uint32_t)((v >> (8 * (T - 1 - t))) & 0xffull) << (8 * (p & 3));
   }
 #pragma unroll
   for (int t = 0; t < T; ++t) {
@@ -251,8 +257,8 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) ibitgemm_kernel(IBitGemmArgs 
         double v0 = (double)acc[mi][ni][T - 1][2 * h], v1 = (double)acc[mi][ni][T - 1][2 * h + 1];
 #pragma unroll
         for (int t = T - 2; t >= 0; --t) {
-          v0 = fma(v0, 1.0 / 128.0, (double)acc[mi][ni][t][2 * h]);
-          v1 = fma(v1, 1.0 / 128.0, (double)acc[mi][ni][t][2 * h + 1]);
+          v0 = fma(v0, 1.0 / 256.0, (double)acc[mi][ni][t][2 * h]);
+          v1 = fma(v1, 1.0 / 256.0, (double)acc[mi][ni][t][2 * h + 1]);
         }
         double2 v = make_double2(v0 * sc0, v1 * sc1);
         double2 *p = reinterpret_cast<double2 *>(out + (int64_t)row * ldo + col);

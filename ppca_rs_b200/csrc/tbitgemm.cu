@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(tb::THREADS, 1) tbitgemm_kernel(TBitGemmArgs a
             for (int j = 0; j < 8; ++j) {
               double acc = (double)rg[T - 1][j];
 #pragma unroll
-              for (int t = T - 2; t >= 0; --t) acc = fma(acc, 1.0 / 128.0, (double)rg[t][j]);
+              for (int t = T - 2; t >= 0; --t) acc = fma(acc, 1.0 / 256.0, (double)rg[t][j]);
               v[j] = empty_slab ? 0.0 : acc * (a.scale[q + j] * (1.0 / 64.0));
             }
             double2 *p = reinterpret_cast<double2 *>(out + (int64_t)row * ldo + q);
@@ -368,7 +368,7 @@ __global__ void __launch_bounds__(128) slice_tc_kernel(const double *__restrict_
   int ex = 0;
   if (m > 0.0) frexp(m, &ex);
   if (kb == 0) scale[q] = ldexp(1.0, ex);
-  const double inv = ldexp(64.0, -ex);
+  const double inv = ldexp(1.0, 8 * T - 2 - ex);
   uint32_t words[T][8];
 #pragma unroll
   for (int t = 0; t < T; ++t)
@@ -377,13 +377,13 @@ __global__ void __launch_bounds__(128) slice_tc_kernel(const double *__restrict_
 #pragma unroll
   for (int r = 0; r < 32; ++r) {
     const int row = kb * 32 + r;
-    double xs = (row < K) ? B[(int64_t)row * ldb + q] * inv : 0.0;
+    const double x = (row < K) ? B[(int64_t)row * ldb + q] : 0.0;
+    // rint(x / s 2^(8T-2)) as T balanced base-256 digits (see ibitgemm.cu): +128 below the top digit, then ^ 0x80
+    constexpr unsigned long long BIAS = 0x0080808080808080ull & ((1ull << (8 * (T - 1))) - 1ull);
+    const unsigned long long v = (unsigned long long)(__double2ll_rn(x * inv) + (long long)BIAS) ^ BIAS;
 #pragma unroll
-    for (int t = 0; t < T; ++t) {
-      const double dg = rint(xs);
-      xs = (xs - dg) * 128.0;
-      words[t][r >> 2] |= ((uint32_t)((int)dg & 0xff)) << (8 * (r & 3));
-    }
+    for (int t = 0; t < T; ++t)  // plane 0 = most significant digit
+      words[t][r >> 2] |= (uint32_t)((v >> (8 * (T - 1 - t))) & 0xffull) << (8 * (r & 3));
   }
 #pragma unroll
   for (int t = 0; t < T; ++t) {
