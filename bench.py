@@ -256,10 +256,9 @@ def run_ours(args, wl, rank, world, local_rank):
         e0.record(stream)
         for _ in range(args.steps):
             state.step()
-            for name, ms in ctx.last_profile().items():
-                fam[name] = fam.get(name, 0.0) + ms
         e1.record(stream)
         sync_all()
+    fam = ctx.last_profile()  # CUDA-event spans recorded on the launching stream during the timed steps
     ms_total = e0.elapsed_time(e1)
     launches = ctx.launch_count() - launches0
     ctx.set_profiling(False)
@@ -355,6 +354,22 @@ def run_ours(args, wl, rank, world, local_rank):
                "sample": f"first {rows} rows of the GPU workload, 1 step of llk + iterate with the CPU restatement "
                          "of the reference's algorithm (oracle/ppca_oracle.c, OpenMP); Rust crate not buildable here"}
 
+    # ---- one-off ingest cost of the public Dataset(ndarray) constructor (host -> device, mask build) ----------
+    ingest = None
+    if world == 1:
+        rows_i = min(n, max(1, int(4e8 // (8 * d))))
+        Xh = np.empty((rows_i, d))
+        nat.check(nat.lib().ppca_b200_dataset_to_host(ctx.handle, ds._h, 0, rows_i, nat.dptr(Xh)))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ds_h = pk.Dataset(Xh)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        ingest = {"rows": rows_i, "seconds": dt, "gb_per_s": rows_i * d * 8 / dt / 1e9,
+                  "note": "pk.Dataset(ndarray) from pageable host memory: H2D copy + mask/transpose kernels; paid once "
+                          "per dataset, like the reference's own numpy -> Rust copy (src/python_bindings.rs:41-54)"}
+        del ds_h
+
     line = {
         "metric": "EM samples*iters/sec", "value": value, "unit": "samples*iters/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
@@ -362,7 +377,7 @@ def run_ours(args, wl, rank, world, local_rank):
         "config": {"workload": f"{args.workload}: {wl['desc']}", "rows_per_gpu": n, "d": d, "k": k,
                    "components": m, "parallelism": f"sample-sharded x{world}, one NCCL all-reduce of the statistics per step",
                    "l2": "inputs larger than L2 (resident X per GPU = %.2f GB)" % (n * d * 8 / 1e9)},
-        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "ingest": ingest, "gpu_launches": int(launches),
         "clocks": clocks.summary(),
     }
     print(json.dumps(line), flush=True)

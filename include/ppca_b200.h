@@ -82,10 +82,11 @@ int32_t ppca_b200_ctx_set_chunk(ppca_b200_ctx *ctx, int64_t chunk_samples);
 int32_t ppca_b200_ctx_set_gemm(ppca_b200_ctx *ctx, int32_t mode, int32_t slices);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 int32_t ppca_b200_ctx_launch_count(ppca_b200_ctx *ctx, int64_t *out);
-/* Device time of the last iterate / em_stats call broken down per kernel family, in ms:
+/* Device time accumulated since profiling was enabled (ppca_b200_ctx_set_profiling(ctx, 1) resets it), broken
+ * down per kernel family, in ms; reading it synchronises the stream once, the profiled calls never do:
  * out[0]=model staging (Ksym, digit planes) out[1]=gram (masked contraction, E-step) out[2]=proj out[3]=solve
  * out[4]=moment (masked contraction, M-step) out[5]=cross+resid out[6]=finish out[7]=digit-plane slicing of W.
- * Only filled when profiling was enabled with ppca_b200_ctx_set_profiling(ctx, 1). */
+ * Measured with CUDA events recorded on the context's stream around each family's launches. */
 int32_t ppca_b200_ctx_set_profiling(ppca_b200_ctx *ctx, int32_t enabled);
 int32_t ppca_b200_ctx_last_profile(ppca_b200_ctx *ctx, double *out8);
 

@@ -87,15 +87,6 @@ struct ppca_b200_ctx {
     if (zero)
       for (int i = 0; i < FAM_COUNT; ++i) last_profile[i] = 0.0;
   }
-  void profile_collect() {
-    if (!profiling) return;
-    CUDA_CHECK(cudaStreamSynchronize(stream));
-    for (auto &s : spans) {
-      float ms = 0.f;
-      CUDA_CHECK(cudaEventElapsedTime(&ms, s.a, s.b));
-      last_profile[s.fam] += ms;
-    }
-  }
 };
 
 namespace {
@@ -738,12 +729,24 @@ int32_t ppca_b200_ctx_set_profiling(ppca_b200_ctx *ctx, int32_t enabled) {
   return guarded([&] {
     REQUIRE(ctx != nullptr, "null context");
     ctx->profiling = enabled != 0;
+    ctx->profile_reset(true);  // spans accumulate from here until ppca_b200_ctx_last_profile reads them
   });
 }
 
 int32_t ppca_b200_ctx_last_profile(ppca_b200_ctx *ctx, double *out8) {
   return guarded([&] {
     REQUIRE(ctx != nullptr && out8 != nullptr, "null argument");
+    DeviceGuard g(ctx->device);
+    if (ctx->profiling) {  // one synchronisation here, none inside the profiled calls
+      CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+      for (auto &sp : ctx->spans) {
+        float ms = 0.f;
+        CUDA_CHECK(cudaEventElapsedTime(&ms, sp.a, sp.b));
+        ctx->last_profile[sp.fam] += ms;
+      }
+      ctx->spans.clear();
+      ctx->ev_used = 0;
+    }
     for (int i = 0; i < FAM_COUNT; ++i) out8[i] = ctx->last_profile[i];
   });
 }
@@ -933,13 +936,11 @@ int32_t ppca_b200_llks(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int32_t 
     if (st.n == 0) return;
     REQUIRE(out != nullptr, "null output");
     DeviceGuard g(ctx->device);
-    ctx->profile_reset();
     DevModel m = stage_model(ctx, st.d, k, C, mu, sigma);
     ctx->rbuf.reserve((size_t)st.n_pad);
     llks_impl(ctx, st, m, ctx->rbuf.p);
     CUDA_CHECK(cudaMemcpyAsync(out, ctx->rbuf.p, sizeof(double) * st.n, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-    ctx->profile_collect();
   });
 }
 
@@ -954,7 +955,6 @@ int32_t ppca_b200_llk(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int32_t k
       return;
     }
     DeviceGuard g(ctx->device);
-    ctx->profile_reset();
     DevModel m = stage_model(ctx, st.d, k, C, mu, sigma);
     const int64_t chunk = pick_chunk(ctx, st.n_pad, m.s);
     reserve_chunk_ws(ctx, chunk, m.s);
@@ -971,7 +971,6 @@ int32_t ppca_b200_llk(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int32_t k
     CUDA_CHECK(cudaMemcpyAsync(h, ctx->stats.p, sizeof(double) * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     *out = h[SC_LLK];
-    ctx->profile_collect();
   });
 }
 
@@ -1052,10 +1051,8 @@ int32_t ppca_b200_em_stats(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int3
     check_ds(ctx, ds);
     REQUIRE(stats_dev != nullptr, "null statistics buffer");
     DeviceGuard g(ctx->device);
-    ctx->profile_reset();
     DevModel m = stage_model(ctx, ds->store->d, k, C, mu, sigma);
     em_stats_impl(ctx, *ds->store, ds->w.p, m, stats_dev);
-    ctx->profile_collect();
   });
 }
 
@@ -1066,10 +1063,7 @@ int32_t ppca_b200_em_finish(ppca_b200_ctx *ctx, int32_t d, int32_t k, const doub
     REQUIRE(ctx != nullptr && stats_dev != nullptr, "null argument");
     REQUIRE(d >= 1 && k >= 1, "bad shape");
     DeviceGuard g(ctx->device);
-    ctx->profile_reset(false);
     em_finish_impl(ctx, d, k, C, mu, sigma, prior, stats_dev, C_out, mu_out, sigma_out, llk_in, nullptr);
-    ctx->profile_collect();
-    ctx->profile_reset(false);
   });
 }
 
@@ -1081,12 +1075,10 @@ int32_t ppca_b200_iterate(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int32
     const SampleStore &st = *ds->store;
     if (st.n == 0) PPCA_THROW(PPCA_ERR_EMPTY, "non-empty dataset required (ppca_model.rs:358)");
     DeviceGuard g(ctx->device);
-    ctx->profile_reset();
     DevModel m = stage_model(ctx, st.d, k, C, mu, sigma);
     ctx->stats.reserve((size_t)StatsLayout(st.d, k).len);
     em_stats_impl(ctx, st, ds->w.p, m, ctx->stats.p);
     em_finish_impl(ctx, st.d, k, C, mu, sigma, prior, ctx->stats.p, C_out, mu_out, sigma_out, llk_in, nullptr);
-    ctx->profile_collect();
   });
 }
 
