@@ -9,6 +9,7 @@
 #include <cstring>
 #include <limits>
 #include <new>
+#include <thread>
 
 #include "common.cuh"
 
@@ -43,6 +44,9 @@ struct ppca_b200_ctx {
   // pinned staging
   double *pinned = nullptr;
   size_t pinned_count = 0;
+  double *upload_pin[2] = {nullptr, nullptr};  // double-buffered dataset upload (kept for the context's lifetime)
+  size_t upload_count = 0;
+  DevBuf<double> upload_raw[2];
   // profiling
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;
@@ -688,6 +692,8 @@ int32_t ppca_b200_ctx_destroy(ppca_b200_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    for (int b = 0; b < 2; ++b)
+      if (ctx->upload_pin[b]) cudaFreeHost(ctx->upload_pin[b]);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
   });
@@ -761,16 +767,62 @@ int32_t ppca_b200_dataset_from_host(ppca_b200_ctx *ctx, const double *x, int64_t
     DeviceGuard g(ctx->device);
     auto st = make_store(ctx, n, d);
     if (n > 0) {
-      const int64_t rows_per = std::max<int64_t>(1, ((int64_t)64 << 20) / ((int64_t)d * 8));
-      DevBuf<double> raw;
-      raw.alloc((size_t)std::min<int64_t>(rows_per, n) * d);
-      for (int64_t r0 = 0; r0 < n; r0 += rows_per) {
-        const int64_t rows = std::min<int64_t>(rows_per, n - r0);
-        CUDA_CHECK(cudaMemcpyAsync(raw.p, x + r0 * d, sizeof(double) * rows * d, cudaMemcpyHostToDevice, ctx->stream));
-        launch_ingest(ctx->L(), raw.p, rows, d, r0, *st);
+      // Double-buffered upload: a few host threads copy the next block of rows into pinned memory while the
+      // previous block is on the bus (pageable cudaMemcpy alone tops out near 6 GB/s).
+      const int64_t rows_per = std::max<int64_t>(1, ((int64_t)32 << 20) / ((int64_t)d * 8));
+      const size_t blk = (size_t)rows_per * d;
+      if (ctx->upload_count < blk) {
+        for (int b = 0; b < 2; ++b) {
+          if (ctx->upload_pin[b]) cudaFreeHost(ctx->upload_pin[b]);
+          ctx->upload_pin[b] = nullptr;
+        }
+        ctx->upload_count = 0;
+        for (int b = 0; b < 2; ++b) CUDA_CHECK(cudaMallocHost((void **)&ctx->upload_pin[b], blk * sizeof(double)));
+        ctx->upload_count = blk;
       }
-      launch_transpose_mask(ctx->L(), *st);
-      CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+      DevBuf<double> *raw = ctx->upload_raw;
+      double **pin = ctx->upload_pin;
+      cudaEvent_t done[2];
+      for (int b = 0; b < 2; ++b) {
+        raw[b].reserve(blk);
+        CUDA_CHECK(cudaEventCreateWithFlags(&done[b], cudaEventDisableTiming));
+      }
+      auto cleanup = [&] {
+        for (int b = 0; b < 2; ++b) cudaEventDestroy(done[b]);
+      };
+      try {
+        int i = 0;
+        for (int64_t r0 = 0; r0 < n; r0 += rows_per, ++i) {
+          const int b = i & 1;
+          const int64_t rows = std::min<int64_t>(rows_per, n - r0);
+          if (i >= 2) CUDA_CHECK(cudaEventSynchronize(done[b]));  // the H2D that last used this pinned block
+          const size_t bytes = (size_t)rows * d * sizeof(double);
+          const char *src = reinterpret_cast<const char *>(x + r0 * d);
+          char *dst = reinterpret_cast<char *>(pin[b]);
+          const int nthr = bytes >= ((size_t)4 << 20) ? 4 : 1;
+          if (nthr == 1) {
+            memcpy(dst, src, bytes);
+          } else {
+            std::vector<std::thread> th;
+            const size_t per = (bytes / nthr + 63) & ~(size_t)63;
+            for (int t = 0; t < nthr; ++t) {
+              const size_t lo = std::min(bytes, per * t), hi = std::min(bytes, per * (t + 1));
+              if (hi > lo) th.emplace_back([=] { memcpy(dst + lo, src + lo, hi - lo); });
+            }
+            for (auto &t : th) t.join();
+          }
+          CUDA_CHECK(cudaMemcpyAsync(raw[b].p, pin[b], bytes, cudaMemcpyHostToDevice, ctx->stream));
+          CUDA_CHECK(cudaEventRecord(done[b], ctx->stream));
+          launch_ingest(ctx->L(), raw[b].p, rows, d, r0, *st);
+        }
+        launch_transpose_mask(ctx->L(), *st);
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+      } catch (...) {
+        cudaStreamSynchronize(ctx->stream);
+        cleanup();
+        throw;
+      }
+      cleanup();
     }
     *out = make_dataset(ctx, st, weights);
   });
