@@ -40,6 +40,7 @@ struct ppca_b200_ctx {
   DevBuf<double> Cdense, mudense, Cpad, mupad, Ksym, logw;
   // chunk workspaces
   DevBuf<double> GW, YZ, WZ, nx, llk, tn, part_bg, part_cr, part_solve, stats, Cnew, cov, rbuf;
+  DevBuf<double> mixLP, mixLlk, mixMax, mixSum, mixStats;  // mixture workspaces (grow-only, no per-call cudaMalloc)
   DevBuf<int> flags;
   // pinned staging
   double *pinned = nullptr;
@@ -1146,9 +1147,9 @@ int32_t ppca_b200_mix_llks(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int3
     if (st.n == 0) return;
     REQUIRE(out != nullptr, "null output");
     DeviceGuard g(ctx->device);
-    DevBuf<double> LP, ml;
-    LP.alloc((size_t)st.n * m);
-    ml.alloc((size_t)st.n);
+    DevBuf<double> &LP = ctx->mixLP, &ml = ctx->mixLlk;
+    LP.reserve((size_t)st.n * m);
+    ml.reserve((size_t)st.n);
     mix_posteriors_impl(ctx, ds, mv, LP.p, ml.p, nullptr, nullptr);
     CUDA_CHECK(cudaMemcpyAsync(out, ml.p, sizeof(double) * st.n, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
@@ -1169,10 +1170,10 @@ int32_t ppca_b200_mix_llk(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int32
       return;
     }
     DeviceGuard g(ctx->device);
-    DevBuf<double> LP, ml, sum;
-    LP.alloc((size_t)st.n * m);
-    ml.alloc((size_t)st.n);
-    sum.alloc(1);
+    DevBuf<double> &LP = ctx->mixLP, &ml = ctx->mixLlk, &sum = ctx->mixSum;
+    LP.reserve((size_t)st.n * m);
+    ml.reserve((size_t)st.n);
+    sum.reserve(1);
     mix_posteriors_impl(ctx, ds, mv, LP.p, ml.p, nullptr, sum.p);
     CUDA_CHECK(cudaMemcpyAsync(out, sum.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
@@ -1190,8 +1191,8 @@ int32_t ppca_b200_mix_infer_cluster(ppca_b200_ctx *ctx, const ppca_b200_dataset 
     if (st.n == 0) return;
     REQUIRE(out != nullptr, "null output");
     DeviceGuard g(ctx->device);
-    DevBuf<double> LP;
-    LP.alloc((size_t)st.n * m);
+    DevBuf<double> &LP = ctx->mixLP;
+    LP.reserve((size_t)st.n * m);
     mix_posteriors_impl(ctx, ds, mv, LP.p, nullptr, nullptr, nullptr);
     CUDA_CHECK(cudaMemcpyAsync(out, LP.p, sizeof(double) * st.n * m, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
@@ -1215,8 +1216,8 @@ static int32_t mix_smooth_or_extrapolate(ppca_b200_ctx *ctx, const ppca_b200_dat
     DeviceGuard g(ctx->device);
     auto ost = make_store(ctx, st.n, st.d);
     if (st.n > 0) {
-      DevBuf<double> LP;
-      LP.alloc((size_t)st.n * m);
+      DevBuf<double> &LP = ctx->mixLP;
+      LP.reserve((size_t)st.n * m);
       mix_posteriors_impl(ctx, ds, mv, LP.p, nullptr, nullptr, nullptr);
       const int64_t total = st.n * m;
       const int blocks = (int)((total + 255) / 256 < (int64_t)ctx->sms * 8 ? (total + 255) / 256 : (int64_t)ctx->sms * 8);
@@ -1256,10 +1257,10 @@ int32_t ppca_b200_mix_posteriors(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds
     if (st.n > 0 && !(ds->min_w > 0.0))
       PPCA_THROW(PPCA_ERR_WEIGHTS, "mixture EM needs strictly positive weights (mix.rs:304-309,326)");
     DeviceGuard g(ctx->device);
-    DevBuf<double> ml, cm, sum;
-    ml.alloc((size_t)std::max<int64_t>(st.n, 1));
-    cm.alloc((size_t)m);
-    sum.alloc(1);
+    DevBuf<double> &ml = ctx->mixLlk, &cm = ctx->mixMax, &sum = ctx->mixSum;
+    ml.reserve((size_t)std::max<int64_t>(st.n, 1));
+    cm.reserve((size_t)m);
+    sum.reserve(1);
     CUDA_CHECK(cudaMemsetAsync(sum.p, 0, sizeof(double), ctx->stream));
     mix_posteriors_impl(ctx, ds, mv, logpost_dev, ml.p, cm.p, st.n > 0 ? sum.p : nullptr);
     double h = 0.0;
@@ -1299,16 +1300,16 @@ int32_t ppca_b200_mix_iterate(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, i
     const SampleStore &st = *ds->store;
     if (st.n == 0) PPCA_THROW(PPCA_ERR_EMPTY, "dataset not empty (mix.rs:315)");
     DeviceGuard g(ctx->device);
-    DevBuf<double> LP;
-    LP.alloc((size_t)st.n * m);
+    DevBuf<double> &LP = ctx->mixLP;
+    LP.reserve((size_t)st.n * m);
     std::vector<double> cmax(m);
     int32_t rc = ppca_b200_mix_posteriors(ctx, ds, m, ks, Cs, mus, sigmas, log_weights, LP.p, cmax.data(), llk_in);
     if (rc) throw Error{rc, g_last_error};
     std::vector<double> logsum(m);
     for (int j = 0; j < m; ++j) {
       const int kj = ks[j];
-      DevBuf<double> stats;
-      stats.alloc((size_t)StatsLayout(st.d, kj).len);
+      DevBuf<double> &stats = ctx->mixStats;
+      stats.reserve((size_t)StatsLayout(st.d, kj).len);
       rc = ppca_b200_mix_em_stats(ctx, ds, m, j, kj, mv.C(j), mv.mu(j), sigmas[j], LP.p, cmax[j], stats.p);
       if (rc) throw Error{rc, g_last_error};
       double sumw = 0.0;

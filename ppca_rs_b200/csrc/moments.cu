@@ -379,9 +379,11 @@ template <int KT>
 __global__ void __launch_bounds__(256) reconstruct_kernel(RecArgs a) {
   constexpr int KPP = 8 * KT;
   constexpr int LDZ = KPP + ((20 - KPP % 16) % 16);
+  constexpr int LDO = 66;  // staging pitch of the 64 x 64 output tile
   extern __shared__ __align__(16) double smem[];
   double *sZ = smem;
   double *sC = smem + 64 * LDZ;
+  double *sO = smem;  // Z and C tiles are dead after the MMA phase (the launch sizes smem for whichever is larger)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int r = lane >> 2, c = lane & 3;
   const int xb = blockIdx.x, base = blockIdx.y * 64;
@@ -412,27 +414,33 @@ __global__ void __launch_bounds__(256) reconstruct_kernel(RecArgs a) {
 #pragma unroll
       for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], av[mi], bv[ni]);
   }
+  __syncthreads();  // all fragment reads of sZ / sC are done: reuse sZ as the output staging tile
 #pragma unroll
-  for (int mi = 0; mi < 2; ++mi) {
-    const int row = base + 8 * (mt0 + mi) + r;
-    if (row >= a.rows) continue;
-    const int64_t grow = a.row0 + row;
-    const double sc = a.scale ? a.scale[(int64_t)row * a.scale_ld] : 1.0;
+  for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-    for (int ni = 0; ni < 4; ++ni) {
+    for (int ni = 0; ni < 4; ++ni)
+      *reinterpret_cast<double2 *>(sO + (8 * (mt0 + mi) + r) * LDO + 8 * (nt0 + ni) + 2 * c) =
+          make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+  __syncthreads();
+  // coalesced pass: warp w handles rows w, w + 8, ...; lanes walk the 64 columns of the dimension block
+  for (int row = warp; row < 64; row += 8) {
+    if (base + row >= a.rows) break;
+    const int64_t grow = a.row0 + base + row;
+    const double sc = a.scale ? a.scale[(int64_t)(base + row) * a.scale_ld] : 1.0;
+    uint32_t w0 = 0u, w1 = 0u;
+    if (a.extrapolate) {
+      if (2 * xb < a.dw) w0 = a.mask[grow * a.dw + 2 * xb];
+      if (2 * xb + 1 < a.dw) w1 = a.mask[grow * a.dw + 2 * xb + 1];
+    }
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int col = 64 * xb + 8 * (nt0 + ni) + 2 * c + j;
-        if (col >= a.d) continue;
-        double v = acc[mi][ni][j] + a.mupad[col];
-        if (a.extrapolate) {
-          const uint32_t wbits = a.mask[grow * a.dw + (col >> 5)];
-          if ((wbits >> (col & 31)) & 1u) v = a.X[grow * a.ldx + col];
-        }
-        if (a.scale) v *= sc;
-        double *o = a.out + (int64_t)row * a.ldo + col;
-        *o = a.accumulate ? (*o + v) : v;
-      }
+    for (int hh = 0; hh < 2; ++hh) {
+      const int col = 64 * xb + 32 * hh + lane;
+      if (col >= a.d) continue;
+      double v = sO[row * LDO + 32 * hh + lane] + a.mupad[col];
+      if (a.extrapolate && (((hh ? w1 : w0) >> lane) & 1u)) v = a.X[grow * a.ldx + col];  // observed: copy, never recompute
+      if (a.scale) v *= sc;
+      double *o = a.out + (int64_t)(base + row) * a.ldo + col;
+      *o = a.accumulate ? (*o + v) : v;
     }
   }
 }
@@ -441,7 +449,7 @@ template <int KT>
 static void launch_rec(const Launcher &L, const RecArgs &a, dim3 grid) {
   constexpr int KPP = 8 * KT;
   constexpr int LDZ = KPP + ((20 - KPP % 16) % 16);
-  constexpr size_t SMEM = 2 * 64 * LDZ * sizeof(double);
+  constexpr size_t SMEM = (2 * 64 * LDZ > 64 * 66 ? 2 * 64 * LDZ : 64 * 66) * sizeof(double);
   static bool configured = false;
   if (!configured) {
     CUDA_CHECK(cudaFuncSetAttribute(reconstruct_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
