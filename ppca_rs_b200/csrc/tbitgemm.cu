@@ -14,6 +14,7 @@
 // References as in bitgemm.cu: E-step Gs = Mask Ksym (output_covariance.rs:57-59 after :123-131),
 // M-step A += Mask^T W (ppca_model.rs:297-306).
 #include <cstdio>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "mma.cuh"
@@ -24,7 +25,7 @@ namespace tb {
 
 constexpr int MH = 1;             // 128-row MMA halves per tile (MH = 2 with NQ = 16 measured slower: producer bound)
 constexpr int BM = 128 * MH, NQ = 32, BKB = 128, STAGES = 4;
-constexpr int PRODUCERS = 128, THREADS = 288;
+constexpr int PRODUCERS = 128, THREADS = 288, THREADS_ATM = 448;
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
@@ -44,6 +45,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "}" ::"r"(bar),
       "r"(parity)
       : "memory");
+}
+// Whole-warp wait with a single polling lane: 32 lanes spinning on one mbarrier serialise in the shared-memory
+// pipe (ncu counted them as ~4e8 bank conflicts per launch), so lane 0 polls and __syncwarp() releases the rest.
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
+  if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
+  __syncwarp();
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -68,6 +75,29 @@ __device__ __forceinline__ void tc_ld8(uint32_t taddr, int (&r)[8]) {
                : "r"(taddr));
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// A operand from tensor memory (lane = row, 4 K-bytes per 32-bit column), B from shared memory
+__device__ __forceinline__ void tc_mma_i8_ts(uint32_t tmem_c, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t"
+      "}" ::"r"(tmem_c),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+      "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]),
+      "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),
+      "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
 
 // K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): 8-row groups of 1024 bytes
 __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
@@ -204,7 +234,7 @@ __global__ void __launch_bounds__(tb::THREADS, 1) tbitgemm_kernel(TBitGemmArgs a
     while (tiles_left > 0) {
       const int stage = job & (STAGES - 1);
       const uint32_t phase = (uint32_t)(job / STAGES) & 1u;
-      mbar_wait(empty_bar(stage), phase ^ 1u);
+      mbar_wait_warp(empty_bar(stage), phase ^ 1u);
       const uint32_t sA = smem_base + stage * STAGE_BYTES, sB = sA + A_BYTES;
       if (gt == 0) {
         const int8_t *src = a.Bq + ((int64_t)ks_i * qtiles + qt_i) * (int64_t)B_BYTES;
@@ -244,7 +274,7 @@ __global__ void __launch_bounds__(tb::THREADS, 1) tbitgemm_kernel(TBitGemmArgs a
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int z = tile / (mtiles * qtiles);
       const int ks_begin = z * ks_per, ks_end = min(a.ksteps, ks_begin + ks_per);
-      mbar_wait(tempty_bar(buf), tphase ^ 1u);
+      mbar_wait_warp(tempty_bar(buf), tphase ^ 1u);
       tc_fence_after();
       const uint32_t tmem_c = tmem_base + (uint32_t)(buf * TCOLS);
       if (ks_begin >= ks_end) {  // empty K slab (never produced by the host-side split): publish immediately
@@ -252,7 +282,7 @@ __global__ void __launch_bounds__(tb::THREADS, 1) tbitgemm_kernel(TBitGemmArgs a
         __syncwarp();
       }
       for (int ks = ks_begin; ks < ks_end; ++ks) {
-        mbar_wait(full_bar(stage), phase);
+        mbar_wait_warp(full_bar(stage), phase);
         tc_fence_after();
         if (lane == 0) {
           const uint32_t sA = smem_base + stage * STAGE_BYTES, sB = sA + A_BYTES;
@@ -298,7 +328,7 @@ __global__ void __launch_bounds__(tb::THREADS, 1) tbitgemm_kernel(TBitGemmArgs a
         ldo = a.ldo;
         accumulate = a.accumulate != 0;
       }
-      mbar_wait(tfull_bar(buf), tphase);
+      mbar_wait_warp(tfull_bar(buf), tphase);
       tc_fence_after();
 #pragma unroll 1
       for (int h = 0; h < MH; ++h) {
@@ -346,6 +376,294 @@ __global__ void __launch_bounds__(tb::THREADS, 1) tbitgemm_kernel(TBitGemmArgs a
   tc_fence_before();
   __syncthreads();
   if (warp == 4) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+  }
+}
+
+template <int T>
+__global__ void __launch_bounds__(tb::THREADS_ATM, 1) tbitgemm_atm_kernel(TBitGemmArgs a) {
+  using namespace tb;
+  constexpr int N = T * NQ;
+  // the A tile never touches shared memory here: producers write it to tensor memory (tcgen05.st), the MMA
+  // reads it from there, so shared memory only carries the digit-plane tile (write once, read once per K step)
+  constexpr uint32_t B_BYTES = N * BKB, STAGE_BYTES = B_BYTES;
+  constexpr int ACOL = 2 * MH * N;  // first TMEM column of the A stages (32 columns = 128 K-bytes each)
+  static_assert(ACOL + 32 * STAGES <= 512, "A stages + two accumulator buffers must fit the 512 TMEM columns");
+  constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  constexpr int TCOLS = MH * N;  // TMEM columns per accumulator buffer
+  static_assert(MH == 1 && (STAGES & (STAGES - 1)) == 0, "producer groups assume one 128-row half and 2^n stages");
+  static_assert(2 * TCOLS <= 512, "two accumulator buffers must fit the 512 TMEM columns");
+  extern __shared__ unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * STAGES + 4];
+  __shared__ uint32_t tmem_base_slot;
+
+  // warps 0-3 / 4-7: two producer groups (alternate jobs; warp w writes TMEM lane quarter w & 3), warp 8: MMA issuer,
+  // warps 9-12: epilogue (quarters 1,2,3,0), warp 13: digit-plane loader
+  constexpr int MMA_WARP = 8, EPI_WARP0 = 9, LOAD_WARP = 13;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int b) { return bar0 + 8u * (2 * STAGES + b); };
+  auto tempty_bar = [&](int b) { return bar0 + 8u * (2 * STAGES + 2 + b); };
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), PRODUCERS + 1);  // 128 mask expanders + the bulk-copy issue
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull_bar(b), 1);
+      mbar_init(tempty_bar(b), 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == MMA_WARP) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                 "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  const int mtiles = (a.M + BM - 1) / BM, qtiles = (a.Nq + NQ - 1) / NQ;
+  const int ntiles = mtiles * qtiles * a.splitk;
+  const int ks_per = (a.ksteps + a.splitk - 1) / a.splitk;
+
+  if (warp < 8) {
+    // ===================== producers =====================
+    // The (tile, K step) jobs of this CTA form one sequence; producer group g = warp / 4 takes jobs j = g (mod 2).
+    // Per job every thread of the group expands its mask row (row = 32 (warp & 3) + lane = TMEM lane) to int8
+    // {0,1} in registers and writes the 128 bytes to the stage's tensor-memory columns with one tcgen05.st;
+    // tcgen05.wait::st, fence, arrive.  The 16 bytes of mask a thread needs per job are fetched DEPTH own jobs
+    // ahead with cp.async into a private shared-memory ring (mask rows are strided: latency, not bandwidth).
+    constexpr int DEPTH = 3, RING = 4;
+    const int grp = warp >> 2, gt = tid & 127;  // group, thread within the group = row of the tile
+    uint32_t *ring = reinterpret_cast<uint32_t *>(smem_raw + (smem_base - smem_u32(smem_raw)) + STAGES * STAGE_BYTES) +
+                     grp * (RING * 128 * 4);
+    struct Cursor {
+      int tiles_left, tile, ks, ks_end;
+      const uint32_t *wrow;
+      bool row_ok;
+    };
+    auto open_tile = [&](Cursor &c) {
+      const int z = c.tile / (mtiles * qtiles), rem = c.tile % (mtiles * qtiles);
+      const int mt = rem % mtiles;
+      c.ks = z * ks_per;
+      c.ks_end = min(a.ksteps, c.ks + ks_per);
+      const int row = mt * BM + gt;
+      c.row_ok = row < a.M;
+      c.wrow = a.bits + (int64_t)(c.row_ok ? row : 0) * a.ldbits;
+    };
+    auto settle = [&](Cursor &c) {
+      while (c.tiles_left > 0 && c.ks >= c.ks_end) {
+        c.tile += gridDim.x;
+        if (--c.tiles_left > 0) open_tile(c);
+      }
+    };
+    auto step = [&](Cursor &c) {  // to the next job of the sequence
+      if (c.tiles_left > 0) {
+        ++c.ks;
+        settle(c);
+      }
+    };
+    auto start = [&](Cursor &c) {
+      c.tiles_left = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+      c.tile = blockIdx.x;
+      c.ks = c.ks_end = 0;
+      c.wrow = a.bits;
+      c.row_ok = false;
+      if (c.tiles_left > 0) open_tile(c);
+      settle(c);
+      if (grp == 1) step(c);  // group 1 starts at job 1
+    };
+    auto fetch_words = [&](const Cursor &c, int slot) {  // 4 x 4-byte cp.async (mask rows are only 4-byte aligned)
+      const uint32_t dst = smem_u32(ring + (slot * 128 + gt) * 4);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int wi = 4 * c.ks + j;
+        const bool ok = c.tiles_left > 0 && c.row_ok && wi < a.nwords;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + 4 * j), "l"(ok ? c.wrow + wi : a.bits),
+                     "r"(ok ? 4 : 0));
+      }
+      asm volatile("cp.async.commit_group;" ::);
+    };
+    Cursor cp, cf;  // processing cursor, fetch cursor (DEPTH own jobs ahead)
+    start(cp);
+    start(cf);
+    int nf = 0;
+    for (; nf < DEPTH; ++nf) {
+      fetch_words(cf, nf % RING);
+      step(cf);
+      step(cf);
+    }
+    int job = grp, own = 0;
+    while (cp.tiles_left > 0) {
+      fetch_words(cf, nf % RING);
+      ++nf;
+      step(cf);
+      step(cf);
+      const int stage = job & (STAGES - 1);
+      const uint32_t phase = (uint32_t)(job / STAGES) & 1u;
+      mbar_wait_warp(empty_bar(stage), phase ^ 1u);
+      tc_fence_after();
+      asm volatile("cp.async.wait_group %0;" ::"n"(DEPTH) : "memory");  // this job's own mask words have landed
+      const uint4 wq = *reinterpret_cast<const uint4 *>(ring + ((own % RING) * 128 + gt) * 4);
+      const uint32_t wc[4] = {wq.x, wq.y, wq.z, wq.w};
+      uint32_t v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = nib4(wc[j >> 3], 4 * (j & 7));
+      tc_st32(tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(ACOL + 32 * stage), v);
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(full_bar(stage));
+      step(cp);
+      step(cp);
+      job += 2;
+      ++own;
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+  } else if (warp == LOAD_WARP) {
+    // ===================== digit-plane loader =====================
+    // one thread streams the pre-swizzled digit-plane tiles with cp.async.bulk as soon as a stage is free,
+    // independently of the mask expansion (completion counted in bytes on the stage's "full" mbarrier)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int z = tile / (mtiles * qtiles), rem = tile % (mtiles * qtiles);
+        const int qt = rem / mtiles;
+        const int ks_begin = z * ks_per, ks_end = min(a.ksteps, ks_begin + ks_per);
+        for (int ks = ks_begin; ks < ks_end; ++ks) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sB = smem_base + stage * STAGE_BYTES;
+          const int8_t *src = a.Bq + ((int64_t)ks * qtiles + qt) * (int64_t)B_BYTES;
+          const uint32_t nbytes = B_BYTES;
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full_bar(stage)), "r"(nbytes)
+                       : "memory");
+          asm volatile(
+              "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sB),
+              "l"(src), "r"(nbytes), "r"(full_bar(stage))
+              : "memory");
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == MMA_WARP) {
+    // ===================== MMA issuer =====================
+    int stage = 0, buf = 0;
+    uint32_t phase = 0, tphase = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int z = tile / (mtiles * qtiles);
+      const int ks_begin = z * ks_per, ks_end = min(a.ksteps, ks_begin + ks_per);
+      mbar_wait_warp(tempty_bar(buf), tphase ^ 1u);
+      tc_fence_after();
+      const uint32_t tmem_c = tmem_base + (uint32_t)(buf * TCOLS);
+      if (ks_begin >= ks_end) {  // empty K slab (never produced by the host-side split): publish immediately
+        if (lane == 0) tc_commit(tfull_bar(buf));
+        __syncwarp();
+      }
+      for (int ks = ks_begin; ks < ks_end; ++ks) {
+        mbar_wait_warp(full_bar(stage), phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sB = smem_base + stage * STAGE_BYTES;
+          const uint64_t bdesc = smem_desc_sw128(sB);
+          const uint32_t tmem_a = tmem_base + (uint32_t)(ACOL + 32 * stage);
+#pragma unroll
+          for (int k = 0; k < BKB / 32; ++k)
+            tc_mma_i8_ts(tmem_c, tmem_a + (uint32_t)(8 * k), bdesc + (uint64_t)(2 * k), IDESC,
+                         (ks > ks_begin || k > 0) ? 1u : 0u);
+          tc_commit(empty_bar(stage));
+          if (ks == ks_end - 1) tc_commit(tfull_bar(buf));
+        }
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+      if (++buf == 2) {
+        buf = 0;
+        tphase ^= 1u;
+      }
+    }
+  } else {
+    // ===================== epilogue =====================
+    int buf = 0;
+    uint32_t tphase = 0;
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access (warps 9..12 -> 1,2,3,0)
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int z = tile / (mtiles * qtiles), rem = tile % (mtiles * qtiles);
+      const int qt = rem / mtiles, mt = rem % mtiles;
+      const bool empty_slab = z * ks_per >= min(a.ksteps, z * ks_per + ks_per);
+      double *out;
+      int64_t ldo;
+      bool accumulate;
+      if (a.splitk > 1) {
+        out = a.partials + (int64_t)z * a.M * a.Nq;
+        ldo = a.Nq;
+        accumulate = a.defer_reduce != 0;
+      } else {
+        out = a.Out;
+        ldo = a.ldo;
+        accumulate = a.accumulate != 0;
+      }
+      mbar_wait_warp(tfull_bar(buf), tphase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int h = 0; h < MH; ++h) {
+        const int row = mt * BM + 128 * h + quarter * 32 + lane;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * TCOLS + h * N);
+#pragma unroll 1
+        for (int qc = 0; qc < NQ / 8; ++qc) {
+          int rg[T][8];
+#pragma unroll
+          for (int t = 0; t < T; ++t) tc_ld8(taddr + (uint32_t)(t * NQ + 8 * qc), rg[t]);
+          tc_wait_ld();
+          const int q = qt * NQ + 8 * qc;
+          if (row < a.M && q < a.Nq) {
+            double v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              double acc = (double)rg[T - 1][j];
+#pragma unroll
+              for (int t = T - 2; t >= 0; --t) acc = fma(acc, 1.0 / 256.0, (double)rg[t][j]);
+              v[j] = empty_slab ? 0.0 : acc * (a.scale[q + j] * (1.0 / 64.0));
+            }
+            double2 *p = reinterpret_cast<double2 *>(out + (int64_t)row * ldo + q);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              double2 val = make_double2(v[2 * j], v[2 * j + 1]);
+              if (accumulate) {
+                const double2 o = p[j];
+                val.x += o.x;
+                val.y += o.y;
+              }
+              p[j] = val;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(buf));
+      if (++buf == 2) {
+        buf = 0;
+        tphase ^= 1u;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
   }
@@ -476,14 +794,29 @@ int tbitgemm_pick_splitk(int M, int Nq, int ksteps, int sms) {
 
 template <int T>
 static void launch_tb(const Launcher &L, const TBitGemmArgs &a) {
+  const int64_t tiles = round_up(a.M, tb::BM) / tb::BM * (round_up(a.Nq, tb::NQ) / tb::NQ) * a.splitk;
+  const int grid = (int)(tiles < L.sms ? tiles : L.sms);
+  if constexpr (2 * T * tb::NQ + 32 * tb::STAGES <= 512) {
+    static const bool smem_a = getenv("PPCA_B200_TC_SMEM_A") && atoi(getenv("PPCA_B200_TC_SMEM_A")) == 1;
+    if (!smem_a) {  // A operand in tensor memory: shared memory carries only the digit planes
+      constexpr size_t SMEM_ATM = (size_t)tb::STAGES * (T * tb::NQ * tb::BKB) + 1024 + 2 * 4 * 128 * 16;
+      static bool configured_atm = false;
+      if (!configured_atm) {
+        CUDA_CHECK(cudaFuncSetAttribute(tbitgemm_atm_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_ATM));
+        configured_atm = true;
+      }
+      tbitgemm_atm_kernel<T><<<grid, tb::THREADS_ATM, SMEM_ATM, L.stream>>>(a);
+      CUDA_CHECK(cudaGetLastError());
+      ++*L.launch_counter;
+      return;
+    }
+  }
   constexpr size_t SMEM = (size_t)tb::STAGES * (tb::BM * tb::BKB + T * tb::NQ * tb::BKB) + 1024;
   static bool configured = false;
   if (!configured) {
     CUDA_CHECK(cudaFuncSetAttribute(tbitgemm_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
     configured = true;
   }
-  const int64_t tiles = round_up(a.M, tb::BM) / tb::BM * (round_up(a.Nq, tb::NQ) / tb::NQ) * a.splitk;
-  const int grid = (int)(tiles < L.sms ? tiles : L.sms);
   tbitgemm_kernel<T><<<grid, tb::THREADS, SMEM, L.stream>>>(a);
   CUDA_CHECK(cudaGetLastError());
   ++*L.launch_counter;
