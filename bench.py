@@ -121,6 +121,21 @@ def measured_bf16_peak():
         return 1590.0, "B200_PROFILING.md fallback (MEASURED_PEAKS.json absent)"
 
 
+def int8_tc_peak():
+    """Dense int8 tcgen05 peak for the roofline of the default contraction path.  MEASURED_PEAKS.json has no int8
+    figure, so the denominator is our own issue-rate probe (tools/utc_peak.cu: back-to-back tcgen05.mma.kind::i8,
+    M=128 N=192 K=32, one CTA per SM), run on this box when the binary is present, else the committed measurement."""
+    exe = os.path.join(ROOT, "build", "utc_peak")
+    try:
+        if os.path.exists(exe):
+            out = subprocess.run([exe], capture_output=True, text=True, timeout=120).stdout.strip().splitlines()[-1]
+            return float(json.loads(out)["utcimma_ts_n192_tops"]), "tools/utc_peak.cu on this box (tcgen05.mma.kind::i8 M128 N192 K32)"
+    except Exception:
+        pass
+    with open(os.path.join(ROOT, "profiles", "r01_utc_i8_peak.json")) as f:
+        return float(json.load(f)["utcimma_ts_n192_tops"]), "profiles/r01_utc_i8_peak.json (tools/utc_peak.cu, round 1)"
+
+
 def measured_hbm_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -338,8 +353,9 @@ def run_ours(args, wl, rank, world, local_rank):
     else:
         tops = flops_bit * args.slices / (bit_ms * 1e-3) / 1e12 if bit_ms > 0 else None   # int8 ops = T digit planes
         if args.gemm == "tc":
+            peak, psrc = int8_tc_peak()
             bf16, src = measured_bf16_peak()
-            peak, psrc = 2.0 * bf16, f"2 x bf16_tflops of {src} (int8 dense tcgen05 rate = 2 x bf16; no measured int8 figure)"
+            psrc += f"; for scale: 2 x bf16_tflops of {src} = {2.0 * bf16:.0f}"
             kern = f"tbitgemm_kernel<{args.slices}> (tcgen05.mma.kind::i8, TMEM accumulators; E-step + M-step launches)"
         else:
             with open(os.path.join(ROOT, "profiles", "r01_imma_peak.json")) as f:
