@@ -146,6 +146,25 @@ int32_t ppca_b200_iterate(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int32
                           const double *mu, double sigma, const ppca_b200_prior *prior, double *C_out,
                           double *mu_out, double *sigma_out, double *llk_in);
 
+/* ---- out-of-core EM step: the samples stay in HOST memory ---------------------------------------- */
+/* Same result as ppca_b200_dataset_from_host + ppca_b200_iterate (ppca_model.rs:277-393; the numpy -> Rust copy of
+ * src/python_bindings.rs:41-54 happens per step instead of once), for datasets that do not fit the device or are
+ * visited once: `x` (n x d row-major f64, non-finite = missing) and `weights` (n, nullable = 1) are streamed block
+ * by block, the H2D copy of block i+1 on a second stream overlapping the ingest + E/M-step kernels of block i.
+ * Page-lock the buffers first (ppca_b200_host_register, or cudaHostAlloc) for full PCIe bandwidth; pageable
+ * memory works but copies synchronously through the driver's staging buffer. */
+int32_t ppca_b200_iterate_host(ppca_b200_ctx *ctx, const double *x, int64_t n, int32_t d, const double *weights,
+                               int32_t k, const double *C, const double *mu, double sigma,
+                               const ppca_b200_prior *prior, double *C_out, double *mu_out, double *sigma_out,
+                               double *llk_in);
+/* The sharded form of the same: this rank's host-resident rows into stats_dev (DEVICE, layout of
+ * ppca_b200_em_stats_len), to be all-reduced by the caller and finished with ppca_b200_em_finish. */
+int32_t ppca_b200_em_stats_host(ppca_b200_ctx *ctx, const double *x, int64_t n, int32_t d, const double *weights,
+                                int32_t k, const double *C, const double *mu, double sigma, double *stats_dev);
+/* cudaHostRegister / cudaHostUnregister of a caller-owned host range (e.g. a numpy array). */
+int32_t ppca_b200_host_register(const void *p, uint64_t bytes);
+int32_t ppca_b200_host_unregister(const void *p);
+
 /* ---- sharded EM: one process per GPU, statistics all-reduced by the caller --------------------- */
 /* Length (in doubles) of the additive sufficient-statistics buffer for (d, k):
  *   [ A: d x kkp | B: d x kp | tdev: d | totals: d | 8 scalars ]   kkp = roundup8(k(k+1)/2), kp = roundup8(k)

@@ -15,6 +15,7 @@ from ._native import Context, NativeError, device_count, get_context, set_contex
 from .model import (
     Dataset,
     DatasetChunks,
+    HostDataset,
     InferredMasked,
     InferredMaskedMix,
     PosteriorSampler,
@@ -27,7 +28,7 @@ from .model import (
 __version__ = "0.1.0"
 
 __all__ = [
-    "Dataset", "DatasetChunks", "InferredMasked", "InferredMaskedMix", "PosteriorSampler", "PosteriorSamplerMix",
+    "Dataset", "DatasetChunks", "HostDataset", "InferredMasked", "InferredMaskedMix", "PosteriorSampler", "PosteriorSamplerMix",
     "PPCAMix", "PPCAModel", "Prior", "PPCATrainer", "PPCAMixTrainer", "TrainMetrics", "Context", "NativeError",
     "device_count", "get_context", "set_context",
 ]

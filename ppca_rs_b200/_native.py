@@ -79,6 +79,15 @@ _PROTOTYPES = {
         C.c_int32,
         [c_ctx_p, c_ds_p, C.c_int32, c_dp, c_dp, C.c_double, C.POINTER(CPrior), c_dp, c_dp, c_dp, c_dp],
     ),
+    "ppca_b200_iterate_host": (
+        C.c_int32,
+        [c_ctx_p, c_dp, C.c_int64, C.c_int32, c_dp, C.c_int32, c_dp, c_dp, C.c_double, C.POINTER(CPrior), c_dp, c_dp,
+         c_dp, c_dp],
+    ),
+    "ppca_b200_em_stats_host": (
+        C.c_int32, [c_ctx_p, c_dp, C.c_int64, C.c_int32, c_dp, C.c_int32, c_dp, c_dp, C.c_double, C.c_void_p]),
+    "ppca_b200_host_register": (C.c_int32, [C.c_void_p, C.c_uint64]),
+    "ppca_b200_host_unregister": (C.c_int32, [C.c_void_p]),
     "ppca_b200_em_stats_len": (C.c_int64, [C.c_int32, C.c_int32]),
     "ppca_b200_em_stats": (C.c_int32, [c_ctx_p, c_ds_p, C.c_int32, c_dp, c_dp, C.c_double, C.c_void_p]),
     "ppca_b200_em_finish": (

@@ -48,6 +48,11 @@ struct ppca_b200_ctx {
   double *upload_pin[2] = {nullptr, nullptr};  // double-buffered dataset upload (kept for the context's lifetime)
   size_t upload_count = 0;
   DevBuf<double> upload_raw[2];
+  // out-of-core streaming (ppca_b200_iterate_host): copy stream, raw block buffers, block stores
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+  DevBuf<double> s_raw[2], s_wraw[2], s_w;
+  std::shared_ptr<SampleStore> s_store, s_tail;
   // profiling
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;
@@ -313,19 +318,28 @@ void e_step_chunk(ppca_b200_ctx *ctx, const SampleStore &st, const double *w, in
   ctx->span_end();
 }
 
-// E-step + local M-step statistics of a whole (local) dataset into stats_dev
-void em_stats_impl(ppca_b200_ctx *ctx, const SampleStore &st, const double *w, const DevModel &m, double *stats_dev) {
-  const Launcher L = ctx->L();
+// E-step + local M-step statistics, chunk by chunk.  em_begin zeroes the statistics and the partial slots (owned by
+// fixed CTAs and accumulated across chunks), em_chunk runs one chunk of `rows` samples starting at row0 of `st`,
+// em_end reduces the partial slots once, in fixed order.  The resident path (em_stats_impl) walks one store; the
+// out-of-core path (ppca_b200_iterate_host) feeds it one freshly uploaded block store after another.
+struct EmPlan {
+  int64_t chunk = 0;
+  int splitk = 1;
+  size_t bglen = 0, crlen = 0;
+  int slabs = 1;
+};
+
+EmPlan em_begin(ppca_b200_ctx *ctx, int64_t n_pad, const DevModel &m, double *stats_dev) {
   const StatsLayout lay(m.s.d, m.s.k);
   CUDA_CHECK(cudaMemsetAsync(stats_dev, 0, sizeof(double) * lay.len, ctx->stream));
-  if (st.n == 0) return;
-  const int64_t chunk = pick_chunk(ctx, st.n_pad, m.s);
-  reserve_chunk_ws(ctx, chunk, m.s);
-  const int kb_chunk = (int)(chunk / 32);
-  const int splitk = ctx->gemm_mode == 2   ? tbitgemm_pick_splitk(m.s.d, m.s.kkp, kb_chunk / 4, ctx->sms)
-                     : ctx->gemm_mode == 1 ? ibitgemm_pick_splitk(m.s.d, m.s.kkp, kb_chunk, ctx->sms)
-                                           : bitgemm_pick_splitk(m.s.d, m.s.kkp, kb_chunk, ctx->sms);
-  const size_t bglen = bitgemm_partials_len(m.s.d, m.s.kkp, splitk);
+  EmPlan p;
+  p.chunk = pick_chunk(ctx, n_pad, m.s);
+  reserve_chunk_ws(ctx, p.chunk, m.s);
+  const int kb_chunk = (int)(p.chunk / 32);
+  p.splitk = ctx->gemm_mode == 2   ? tbitgemm_pick_splitk(m.s.d, m.s.kkp, kb_chunk / 4, ctx->sms)
+             : ctx->gemm_mode == 1 ? ibitgemm_pick_splitk(m.s.d, m.s.kkp, kb_chunk, ctx->sms)
+                                   : bitgemm_pick_splitk(m.s.d, m.s.kkp, kb_chunk, ctx->sms);
+  p.bglen = bitgemm_partials_len(m.s.d, m.s.kkp, p.splitk);
   if (ctx->gemm_mode == 2) {
     ctx->WQ.reserve(sliced_tc_bytes(kb_chunk, m.s.kkp, ctx->slices));
     ctx->WScale.reserve((size_t)m.s.kkp);
@@ -335,95 +349,118 @@ void em_stats_impl(ppca_b200_ctx *ctx, const SampleStore &st, const double *w, c
     ctx->WScale.reserve((size_t)m.s.kkp);
     ctx->colmax.reserve((size_t)m.s.kkp);
   }
-  ctx->part_bg.reserve(bglen);
-  const int slabs = cross_resid_slabs(m.s.d, m.s.k, (int)chunk, ctx->sms);
-  const size_t crlen = cross_resid_partials_len(m.s.d, m.s.k, slabs);
-  ctx->part_cr.reserve(crlen);
+  ctx->part_bg.reserve(p.bglen);
+  p.slabs = cross_resid_slabs(m.s.d, m.s.k, (int)p.chunk, ctx->sms);
+  p.crlen = cross_resid_partials_len(m.s.d, m.s.k, p.slabs);
+  ctx->part_cr.reserve(p.crlen);
   ctx->part_solve.reserve((size_t)SOLVE_SLOTS * 4);
-  // partial slots are owned by fixed CTAs and accumulated across chunks; one fixed-order reduction at the end
-  if (bglen) CUDA_CHECK(cudaMemsetAsync(ctx->part_bg.p, 0, sizeof(double) * bglen, ctx->stream));
-  CUDA_CHECK(cudaMemsetAsync(ctx->part_cr.p, 0, sizeof(double) * crlen, ctx->stream));
+  if (p.bglen) CUDA_CHECK(cudaMemsetAsync(ctx->part_bg.p, 0, sizeof(double) * p.bglen, ctx->stream));
+  CUDA_CHECK(cudaMemsetAsync(ctx->part_cr.p, 0, sizeof(double) * p.crlen, ctx->stream));
   CUDA_CHECK(cudaMemsetAsync(ctx->part_solve.p, 0, sizeof(double) * SOLVE_SLOTS * 4, ctx->stream));
-  for (int64_t row0 = 0; row0 < st.n; row0 += chunk) {
-    const int rows = (int)((st.n - row0) < chunk ? (st.n - row0) : chunk);
-    e_step_chunk(ctx, st, w, row0, rows, m, 2, ctx->llk.p, nullptr, ctx->part_solve.p);
-    const int kblocks = (int)(round_up(rows, 32) / 32);
-    int sk = splitk < kblocks ? splitk : (kblocks > 0 ? kblocks : 1);
-    if (splitk > 1 && sk < 2) sk = 2 <= kblocks ? 2 : 1;
-    const bool direct = splitk > 1 && sk == 1;  // degenerate last chunk: accumulate straight into the statistics
-    if (ctx->gemm_mode == 2) {
-      ctx->span_begin(FAM_SLICE);
-      launch_slice_tc(L, ctx->GW.p, m.s.kkp, rows, m.s.kkp, kblocks, ctx->slices, ctx->WQ.p, ctx->WScale.p,
-                      ctx->colmax.p);
-      ctx->span_end();
-    } else if (ctx->gemm_mode == 1) {
-      ctx->span_begin(FAM_SLICE);
-      launch_slice(L, ctx->GW.p, m.s.kkp, rows, m.s.kkp, kblocks, ctx->slices, ctx->WQ.p, ctx->WScale.p, ctx->colmax.p);
-      ctx->span_end();
-    }
-    ctx->span_begin(FAM_MOMENT);
-    if (ctx->gemm_mode == 2) {
-      const int ksteps = (kblocks + 3) / 4;
-      int skt = splitk < ksteps ? splitk : ksteps;
-      if (skt < 1) skt = 1;
-      {  // no empty slabs
-        const int per = (ksteps + skt - 1) / skt;
-        skt = (ksteps + per - 1) / per;
-      }
-      const bool to_partials = splitk > 1 && skt > 1;
-      launch_tbitgemm(L, st.maskT.p + row0 / 32, st.nwT, 4 * ksteps, ctx->WQ.p, ctx->WScale.p, ctx->slices,
-                      stats_dev + lay.offA, m.s.kkp, m.s.d, m.s.kkp, ksteps, 1, to_partials ? ctx->part_bg.p : nullptr,
-                      skt, to_partials ? 1 : 0);
-    } else if (ctx->gemm_mode == 1) {
-      IBitGemmArgs g;
-      g.bits = st.maskT.p + row0 / 32;
-      g.ldbits = st.nwT;
-      g.Bq = ctx->WQ.p;
-      g.scale = ctx->WScale.p;
-      g.T = ctx->slices;
-      g.Out = stats_dev + lay.offA;
-      g.ldo = m.s.kkp;
-      g.M = m.s.d;
-      g.Nq = m.s.kkp;
-      g.kblocks = kblocks;
-      g.accumulate = 1;
-      g.splitk = sk;
-      g.partials = (splitk > 1 && !direct) ? ctx->part_bg.p : nullptr;
-      g.defer_reduce = direct ? 0 : 1;
-      launch_ibitgemm(L, g);
-    } else {
-      BitGemmArgs g;
-      g.bits = st.maskT.p + row0 / 32;
-      g.ldbits = st.nwT;
-      g.Bmat = ctx->GW.p;
-      g.ldb = m.s.kkp;
-      g.Out = stats_dev + lay.offA;
-      g.ldo = m.s.kkp;
-      g.M = m.s.d;
-      g.Nq = m.s.kkp;
-      g.kblocks = kblocks;
-      g.kcols = 32 * kblocks;
-      g.accumulate = 1;
-      g.splitk = sk;
-      g.partials = (splitk > 1 && !direct) ? ctx->part_bg.p : nullptr;
-      g.defer_reduce = direct ? 0 : 1;
-      launch_bitgemm(L, g);
-    }
+  return p;
+}
+
+void em_chunk(ppca_b200_ctx *ctx, const SampleStore &st, const double *w, int64_t row0, int rows, const DevModel &m,
+              double *stats_dev, const EmPlan &p) {
+  const Launcher L = ctx->L();
+  const StatsLayout lay(m.s.d, m.s.k);
+  const int splitk = p.splitk;
+  e_step_chunk(ctx, st, w, row0, rows, m, 2, ctx->llk.p, nullptr, ctx->part_solve.p);
+  const int kblocks = (int)(round_up(rows, 32) / 32);
+  int sk = splitk < kblocks ? splitk : (kblocks > 0 ? kblocks : 1);
+  if (splitk > 1 && sk < 2) sk = 2 <= kblocks ? 2 : 1;
+  const bool direct = splitk > 1 && sk == 1;  // degenerate last chunk: accumulate straight into the statistics
+  if (ctx->gemm_mode == 2) {
+    ctx->span_begin(FAM_SLICE);
+    launch_slice_tc(L, ctx->GW.p, m.s.kkp, rows, m.s.kkp, kblocks, ctx->slices, ctx->WQ.p, ctx->WScale.p,
+                    ctx->colmax.p);
     ctx->span_end();
-    ctx->span_begin(FAM_CROSS);
-    launch_cross_resid(L, st, row0, rows, m, ctx->YZ.p, ctx->WZ.p, w + row0, ctx->part_cr.p, slabs);
+  } else if (ctx->gemm_mode == 1) {
+    ctx->span_begin(FAM_SLICE);
+    launch_slice(L, ctx->GW.p, m.s.kkp, rows, m.s.kkp, kblocks, ctx->slices, ctx->WQ.p, ctx->WScale.p, ctx->colmax.p);
     ctx->span_end();
   }
+  ctx->span_begin(FAM_MOMENT);
+  if (ctx->gemm_mode == 2) {
+    const int ksteps = (kblocks + 3) / 4;
+    int skt = splitk < ksteps ? splitk : ksteps;
+    if (skt < 1) skt = 1;
+    {  // no empty slabs
+      const int per = (ksteps + skt - 1) / skt;
+      skt = (ksteps + per - 1) / per;
+    }
+    const bool to_partials = splitk > 1 && skt > 1;
+    launch_tbitgemm(L, st.maskT.p + row0 / 32, st.nwT, 4 * ksteps, ctx->WQ.p, ctx->WScale.p, ctx->slices,
+                    stats_dev + lay.offA, m.s.kkp, m.s.d, m.s.kkp, ksteps, 1, to_partials ? ctx->part_bg.p : nullptr,
+                    skt, to_partials ? 1 : 0);
+  } else if (ctx->gemm_mode == 1) {
+    IBitGemmArgs g;
+    g.bits = st.maskT.p + row0 / 32;
+    g.ldbits = st.nwT;
+    g.Bq = ctx->WQ.p;
+    g.scale = ctx->WScale.p;
+    g.T = ctx->slices;
+    g.Out = stats_dev + lay.offA;
+    g.ldo = m.s.kkp;
+    g.M = m.s.d;
+    g.Nq = m.s.kkp;
+    g.kblocks = kblocks;
+    g.accumulate = 1;
+    g.splitk = sk;
+    g.partials = (splitk > 1 && !direct) ? ctx->part_bg.p : nullptr;
+    g.defer_reduce = direct ? 0 : 1;
+    launch_ibitgemm(L, g);
+  } else {
+    BitGemmArgs g;
+    g.bits = st.maskT.p + row0 / 32;
+    g.ldbits = st.nwT;
+    g.Bmat = ctx->GW.p;
+    g.ldb = m.s.kkp;
+    g.Out = stats_dev + lay.offA;
+    g.ldo = m.s.kkp;
+    g.M = m.s.d;
+    g.Nq = m.s.kkp;
+    g.kblocks = kblocks;
+    g.kcols = 32 * kblocks;
+    g.accumulate = 1;
+    g.splitk = sk;
+    g.partials = (splitk > 1 && !direct) ? ctx->part_bg.p : nullptr;
+    g.defer_reduce = direct ? 0 : 1;
+    launch_bitgemm(L, g);
+  }
+  ctx->span_end();
+  ctx->span_begin(FAM_CROSS);
+  launch_cross_resid(L, st, row0, rows, m, ctx->YZ.p, ctx->WZ.p, w + row0, ctx->part_cr.p, p.slabs);
+  ctx->span_end();
+}
+
+void em_end(ppca_b200_ctx *ctx, const DevModel &m, double *stats_dev, const EmPlan &p) {
+  const Launcher L = ctx->L();
+  const StatsLayout lay(m.s.d, m.s.k);
   ctx->span_begin(FAM_SOLVE);
   launch_solve_finish(L, ctx->part_solve.p, stats_dev + lay.offScalars);
   ctx->span_end();
   ctx->span_begin(FAM_MOMENT);
-  launch_bitgemm_reduce(L, ctx->part_bg.p, splitk, m.s.d, m.s.kkp, stats_dev + lay.offA, m.s.kkp, 1);
+  launch_bitgemm_reduce(L, ctx->part_bg.p, p.splitk, m.s.d, m.s.kkp, stats_dev + lay.offA, m.s.kkp, 1);
   ctx->span_end();
   ctx->span_begin(FAM_CROSS);
-  launch_cross_resid_finish(L, m.s.d, m.s.k, ctx->part_cr.p, slabs, stats_dev + lay.offB, stats_dev + lay.offTdev,
+  launch_cross_resid_finish(L, m.s.d, m.s.k, ctx->part_cr.p, p.slabs, stats_dev + lay.offB, stats_dev + lay.offTdev,
                             stats_dev + lay.offTotals, stats_dev + lay.offScalars);
   ctx->span_end();
+}
+
+// E-step + local M-step statistics of a whole (local, resident) dataset into stats_dev
+void em_stats_impl(ppca_b200_ctx *ctx, const SampleStore &st, const double *w, const DevModel &m, double *stats_dev) {
+  if (st.n == 0) {
+    CUDA_CHECK(cudaMemsetAsync(stats_dev, 0, sizeof(double) * StatsLayout(m.s.d, m.s.k).len, ctx->stream));
+    return;
+  }
+  const EmPlan p = em_begin(ctx, st.n_pad, m, stats_dev);
+  for (int64_t row0 = 0; row0 < st.n; row0 += p.chunk) {
+    const int rows = (int)((st.n - row0) < p.chunk ? (st.n - row0) : p.chunk);
+    em_chunk(ctx, st, w, row0, rows, m, stats_dev, p);
+  }
+  em_end(ctx, m, stats_dev, p);
 }
 
 // Householder QR solve on the host (prior.rs:97-110 smooth_mean uses total_precision.qr().solve)
@@ -695,6 +732,11 @@ int32_t ppca_b200_ctx_destroy(ppca_b200_ctx *ctx) {
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     for (int b = 0; b < 2; ++b)
       if (ctx->upload_pin[b]) cudaFreeHost(ctx->upload_pin[b]);
+    for (int b = 0; b < 2; ++b) {
+      if (ctx->ev_copied[b]) cudaEventDestroy(ctx->ev_copied[b]);
+      if (ctx->ev_free[b]) cudaEventDestroy(ctx->ev_free[b]);
+    }
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
   });
@@ -1132,6 +1174,118 @@ int32_t ppca_b200_iterate(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int32
     ctx->stats.reserve((size_t)StatsLayout(st.d, k).len);
     em_stats_impl(ctx, st, ds->w.p, m, ctx->stats.p);
     em_finish_impl(ctx, st.d, k, C, mu, sigma, prior, ctx->stats.p, C_out, mu_out, sigma_out, llk_in, nullptr);
+  });
+}
+
+// ---- out-of-core EM step: samples stay in host memory -------------------------------------------------
+int32_t ppca_b200_host_register(const void *p, uint64_t bytes) {
+  return guarded([&] {
+    REQUIRE(p != nullptr && bytes > 0, "null host range");
+    CUDA_CHECK(cudaHostRegister(const_cast<void *>(p), (size_t)bytes, cudaHostRegisterPortable));
+  });
+}
+
+int32_t ppca_b200_host_unregister(const void *p) {
+  return guarded([&] {
+    REQUIRE(p != nullptr, "null host range");
+    CUDA_CHECK(cudaHostUnregister(const_cast<void *>(p)));
+  });
+}
+
+}  // extern "C"
+
+namespace {
+// streams x (host) through the device block by block and accumulates the statistics into stats_dev
+void em_stats_host_impl(ppca_b200_ctx *ctx, const double *x, int64_t n, int d, const double *weights, const DevModel &m,
+                        double *stats_dev) {
+  if (!ctx->copy_stream) {
+    CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; ++b) {
+      CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_copied[b], cudaEventDisableTiming));
+      CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_free[b], cudaEventDisableTiming));
+    }
+  }
+  const EmPlan p = em_begin(ctx, round_up(n, 256), m, stats_dev);
+  const int64_t blk = p.chunk;  // one uploaded block = one E/M-step chunk
+  const int64_t tail = n % blk;
+  if (n >= blk && (!ctx->s_store || ctx->s_store->n != blk || ctx->s_store->d != d)) ctx->s_store = make_store(ctx, blk, d);
+  if (tail && (!ctx->s_tail || ctx->s_tail->n != tail || ctx->s_tail->d != d)) ctx->s_tail = make_store(ctx, tail, d);
+  const int64_t brows = n < blk ? n : blk;
+  for (int b = 0; b < 2; ++b) {
+    ctx->s_raw[b].reserve((size_t)brows * d);
+    if (weights) ctx->s_wraw[b].reserve((size_t)brows);
+  }
+  ctx->s_w.reserve((size_t)round_up(brows, 256));
+  // the copy stream must not run ahead of work already queued on the compute stream that still reads the raw blocks
+  CUDA_CHECK(cudaEventRecord(ctx->ev_free[0], ctx->stream));
+  CUDA_CHECK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_free[0], 0));
+  const Launcher L = ctx->L();
+  int i = 0;
+  for (int64_t r0 = 0; r0 < n; r0 += blk, ++i) {
+    const int b = i & 1;
+    const int64_t rows = (n - r0) < blk ? (n - r0) : blk;
+    SampleStore &st = rows == blk ? *ctx->s_store : *ctx->s_tail;
+    // H2D of block i on the copy stream, overlapped with the kernels of block i-1 on the compute stream
+    if (i >= 2) CUDA_CHECK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_free[b], 0));
+    CUDA_CHECK(cudaMemcpyAsync(ctx->s_raw[b].p, x + r0 * d, sizeof(double) * rows * d, cudaMemcpyHostToDevice,
+                               ctx->copy_stream));
+    if (weights)
+      CUDA_CHECK(cudaMemcpyAsync(ctx->s_wraw[b].p, weights + r0, sizeof(double) * rows, cudaMemcpyHostToDevice,
+                                 ctx->copy_stream));
+    CUDA_CHECK(cudaEventRecord(ctx->ev_copied[b], ctx->copy_stream));
+    CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[b], 0));
+    launch_ingest(L, ctx->s_raw[b].p, rows, d, 0, st);
+    CUDA_CHECK(cudaMemsetAsync(ctx->s_w.p, 0, sizeof(double) * st.n_pad, ctx->stream));
+    if (weights) {
+      CUDA_CHECK(cudaMemcpyAsync(ctx->s_w.p, ctx->s_wraw[b].p, sizeof(double) * rows, cudaMemcpyDeviceToDevice,
+                                 ctx->stream));
+    } else {
+      const int64_t want = (rows + 255) / 256;
+      const int blocks = (int)(want < (int64_t)ctx->sms * 8 ? want : (int64_t)ctx->sms * 8);
+      fill_value_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->s_w.p, rows, 1.0);
+      CUDA_CHECK(cudaGetLastError());
+      ++ctx->launches;
+    }
+    CUDA_CHECK(cudaEventRecord(ctx->ev_free[b], ctx->stream));
+    launch_transpose_mask(L, st);
+    em_chunk(ctx, st, ctx->s_w.p, 0, (int)rows, m, stats_dev, p);
+  }
+  em_end(ctx, m, stats_dev, p);
+}
+}  // namespace
+
+extern "C" {
+
+int32_t ppca_b200_em_stats_host(ppca_b200_ctx *ctx, const double *x, int64_t n, int32_t d, const double *weights,
+                                int32_t k, const double *C, const double *mu, double sigma, double *stats_dev) {
+  return guarded([&] {
+    REQUIRE(ctx != nullptr && stats_dev != nullptr, "null argument");
+    REQUIRE(n >= 0 && d >= 1, "bad dataset shape %lld x %d", (long long)n, d);
+    REQUIRE(n == 0 || x != nullptr, "null data");
+    DeviceGuard g(ctx->device);
+    DevModel m = stage_model(ctx, d, k, C, mu, sigma);
+    if (n == 0) {
+      CUDA_CHECK(cudaMemsetAsync(stats_dev, 0, sizeof(double) * StatsLayout(d, k).len, ctx->stream));
+      return;
+    }
+    em_stats_host_impl(ctx, x, n, d, weights, m, stats_dev);
+  });
+}
+
+int32_t ppca_b200_iterate_host(ppca_b200_ctx *ctx, const double *x, int64_t n, int32_t d, const double *weights,
+                               int32_t k, const double *C, const double *mu, double sigma,
+                               const ppca_b200_prior *prior, double *C_out, double *mu_out, double *sigma_out,
+                               double *llk_in) {
+  return guarded([&] {
+    REQUIRE(ctx != nullptr, "null context");
+    REQUIRE(n >= 0 && d >= 1, "bad dataset shape %lld x %d", (long long)n, d);
+    if (n == 0) PPCA_THROW(PPCA_ERR_EMPTY, "non-empty dataset required (ppca_model.rs:358)");
+    REQUIRE(x != nullptr, "null data");
+    DeviceGuard g(ctx->device);
+    DevModel m = stage_model(ctx, d, k, C, mu, sigma);
+    ctx->stats.reserve((size_t)StatsLayout(d, k).len);
+    em_stats_host_impl(ctx, x, n, d, weights, m, ctx->stats.p);
+    em_finish_impl(ctx, d, k, C, mu, sigma, prior, ctx->stats.p, C_out, mu_out, sigma_out, llk_in, nullptr);
   });
 }
 

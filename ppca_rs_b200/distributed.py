@@ -20,7 +20,7 @@ from typing import List, Optional, Sequence, Tuple
 import numpy as np
 
 from . import _native as nat
-from .model import Dataset, PPCAMix, PPCAModel, Prior
+from .model import Dataset, HostDataset, PPCAMix, PPCAModel, Prior
 
 
 def shard_bounds(n: int, world: int, rank: int) -> Tuple[int, int]:
@@ -52,7 +52,13 @@ class CudaEngine:
         assert n == stats_len(d, k)
         return self.torch.zeros(n, dtype=self.torch.float64, device=self.device)
 
-    def em_stats(self, ds: Dataset, model: PPCAModel, stats) -> None:
+    def em_stats(self, ds, model: PPCAModel, stats) -> None:
+        if isinstance(ds, HostDataset):  # this rank's rows stay in host memory and are streamed every step
+            nat.check(nat.lib().ppca_b200_em_stats_host(self.ctx.handle, nat.dptr(ds._x), len(ds), ds._output_size(),
+                                                        nat.dptr(ds._w), model.state_size, nat.dptr(model._C),
+                                                        nat.dptr(model._mu), model._sigma,
+                                                        C.c_void_p(stats.data_ptr())))
+            return
         nat.check(nat.lib().ppca_b200_em_stats(self.ctx.handle, ds._h, model.state_size, nat.dptr(model._C),
                                                nat.dptr(model._mu), model._sigma, C.c_void_p(stats.data_ptr())))
 

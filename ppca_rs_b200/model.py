@@ -178,6 +178,66 @@ def _load_dataset(data: bytes) -> Dataset:
     return Dataset.load(data)
 
 
+class HostDataset:
+    """Out-of-core dataset: the samples stay in (page-locked) HOST memory and are streamed through the GPU block by
+    block on every EM step (`ppca_b200_iterate_host`), the H2D copy of one block overlapping the kernels of the
+    previous one.  For data that does not fit the device (BASELINE config 3 is 1.64 TB) or is visited once.
+    Accepted by `PPCAModel.iterate / iterate_with_prior` and `PPCATrainer`; same numbers as `Dataset`."""
+
+    def __init__(self, ndarray, weights=None, *, pin: bool = True, ctx: Optional[nat.Context] = None):
+        self._ctx = ctx or nat.get_context()
+        self._x = _as_matrix(ndarray, "ndarray")
+        n, d = self._x.shape
+        if d < 1:
+            raise ValueError("dataset needs at least one output dimension")
+        self._w = None
+        if weights is not None:
+            self._w = nat.f64(np.asarray(weights, dtype=np.float64).reshape(-1))
+            if self._w.shape[0] != n:  # dataset.rs:163
+                raise ValueError(f"weights has {self._w.shape[0]} entries for {n} samples")
+        self._pinned = []
+        if pin and n > 0:
+            for a in (self._x, self._w):
+                if a is not None and a.nbytes > 0:
+                    nat.check(nat.lib().ppca_b200_host_register(C.c_void_p(a.ctypes.data), a.nbytes))
+                    self._pinned.append(a.ctypes.data)
+
+    def __del__(self):  # pragma: no cover
+        try:
+            for ptr in getattr(self, "_pinned", []):
+                nat.lib().ppca_b200_host_unregister(C.c_void_p(ptr))
+            self._pinned = []
+        except Exception:
+            pass
+
+    def __len__(self) -> int:
+        return int(self._x.shape[0])
+
+    def _output_size(self) -> int:
+        return int(self._x.shape[1])
+
+    def output_size(self) -> Optional[int]:
+        return self._output_size() if len(self) > 0 else None
+
+    def numpy(self) -> np.ndarray:
+        out = self._x.copy()
+        out[~np.isfinite(out)] = np.nan
+        return out
+
+    def weights(self) -> np.ndarray:
+        return np.ones(len(self)) if self._w is None else self._w.copy()
+
+    def empty_dimensions(self) -> List[int]:
+        """dataset.rs:194-222 (host side: the data is here)."""
+        if len(self) == 0:
+            return []
+        return [int(i) for i in np.nonzero(~np.isfinite(self._x).any(axis=0))[0]]
+
+    def resident(self) -> Dataset:
+        """Uploads once and returns the device-resident Dataset."""
+        return Dataset(self._x, self._w)
+
+
 class DatasetChunks:
     """src/python_bindings.rs:136-166: stride = ceil(len / chunks), yields copies in order."""
 
@@ -402,6 +462,12 @@ class PPCAModel:
         if prior is not None:
             pr, keep = prior._c(d)
             pr_ref = C.byref(pr)
+        if isinstance(dataset, HostDataset):
+            nat.check(nat.lib().ppca_b200_iterate_host(dataset._ctx.handle, nat.dptr(dataset._x), len(dataset), d,
+                                                       nat.dptr(dataset._w), k, nat.dptr(self._C), nat.dptr(self._mu),
+                                                       self._sigma, pr_ref, nat.dptr(C_out), nat.dptr(mu_out),
+                                                       C.byref(s_out), C.byref(llk)))
+            return PPCAModel(s_out.value, C_out, mu_out), llk.value
         nat.check(nat.lib().ppca_b200_iterate(dataset._ctx.handle, dataset._h, k, nat.dptr(self._C), nat.dptr(self._mu),
                                               self._sigma, pr_ref, nat.dptr(C_out), nat.dptr(mu_out), C.byref(s_out),
                                               C.byref(llk)))

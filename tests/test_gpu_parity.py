@@ -323,6 +323,50 @@ def test_virtual_shards_equal_single_pass(pk, orc):
         assert abs(llk - want_llk) < 1e-12 * abs(want_llk)
 
 
+# ---- out-of-core path: samples streamed from host memory every step ---------------------------------------
+@pytest.mark.parametrize("n,d,k,chunk,weighted,pin", [
+    (5000, 90, 12, 0, True, True),       # one (tail) block
+    (5000, 90, 12, 1024, False, True),   # 4 full blocks + tail, double-buffered H2D
+    (4096, 33, 7, 1024, True, False),    # exact multiple of the block, pageable memory
+    (700, 200, 16, 256, False, True),
+])
+def test_iterate_host_streaming_equals_resident(pk, orc, n, d, k, chunk, weighted, pin):
+    """ppca_b200_iterate_host (HostDataset) == ppca_b200_dataset_from_host + ppca_b200_iterate, and == oracle."""
+    X, C0, mu0, s0 = _case(n, d, k, 0.25, seed=31)
+    X[5, :] = np.nan                                   # an empty sample
+    w = (np.random.default_rng(3).random(n) + 0.5) if weighted else None
+    ctx = pk.Context(0)
+    try:
+        ctx.set_chunk(chunk)
+        model = pk.PPCAModel(s0, C0, mu0)
+        host = pk.HostDataset(X, w, pin=pin, ctx=ctx)
+        assert len(host) == n and host.output_size() == d
+        prior = pk.Prior().with_transformation_precision(0.5)
+        for pr in (None, prior):
+            want, want_llk = model._iterate(pk.Dataset(X, w, _ctx=ctx), pr)
+            for _ in range(2):                         # second call reuses the cached block stores
+                got, llk = model._iterate(host, pr)
+                assert rel_err(got.transform, want.transform) < 1e-12 and rel_err(got.mean, want.mean) < 1e-12
+                assert abs(got.isotropic_noise - want.isotropic_noise) < 1e-12 * want.isotropic_noise
+                assert abs(llk - want_llk) < 1e-12 * abs(want_llk)
+        (Cw, muw, sw), (Cs, mus, ss) = both(orc, orc.iterate, X, w, C0, mu0, s0)
+        got, llk = model._iterate(host, None)
+        assert_close(got.transform, Cw, Cs, "C")
+        assert_close(got.mean, muw, mus, "mu")
+        assert_close(got.isotropic_noise ** 2, sw ** 2, ss ** 2, "sigma^2")
+        del host
+    finally:
+        ctx.close()
+
+
+def test_trainer_on_host_dataset(pk):
+    X, C0, mu0, s0 = _case(3000, 40, 4, 0.2, seed=5)
+    start = pk.PPCAModel(s0, C0, mu0)
+    a = pk.PPCATrainer(pk.Dataset(X)).train(start=start, state_size=4, n_iters=5, quiet=True)
+    b = pk.PPCATrainer(pk.HostDataset(X)).train(start=start, state_size=4, n_iters=5, quiet=True)
+    assert rel_err(b.transform, a.transform) < 1e-10 and abs(b.isotropic_noise - a.isotropic_noise) < 1e-10
+
+
 # ---- full-size properties (BASELINE configs[1]: N=1M, d=200, k=16, 20% missing) ---------------------------
 def test_full_size_properties(pk):
     n, d, k = 1_000_000, 200, 16
