@@ -251,7 +251,8 @@ void reserve_chunk_ws(ppca_b200_ctx *ctx, int64_t chunk, const Shape &s) {
 
 // E-step of one chunk: Gram contraction, projection, per-sample solve
 void e_step_chunk(ppca_b200_ctx *ctx, const SampleStore &st, const double *w, int64_t row0, int rows,
-                  const DevModel &m, int mode, double *llk_out, double *cov_out, double *solve_part) {
+                  const DevModel &m, int mode, double *llk_out, double *cov_out, double *solve_part,
+                  unsigned long long *w_colmax = nullptr) {
   const Launcher L = ctx->L();
   const int rows_pad = (int)round_up(rows, 256);
   ctx->span_begin(FAM_GRAM);
@@ -313,6 +314,8 @@ void e_step_chunk(ppca_b200_ctx *ctx, const SampleStore &st, const double *w, in
   sa.cov = cov_out;
   sa.part = solve_part;
   sa.mode = mode;
+  sa.colmax = w_colmax;
+  if (w_colmax) CUDA_CHECK(cudaMemsetAsync(w_colmax, 0, sizeof(unsigned long long) * m.s.kkp, ctx->stream));
   ctx->span_begin(FAM_SOLVE);
   launch_solve(L, sa);
   ctx->span_end();
@@ -365,7 +368,10 @@ void em_chunk(ppca_b200_ctx *ctx, const SampleStore &st, const double *w, int64_
   const Launcher L = ctx->L();
   const StatsLayout lay(m.s.d, m.s.k);
   const int splitk = p.splitk;
-  e_step_chunk(ctx, st, w, row0, rows, m, 2, ctx->llk.p, nullptr, ctx->part_solve.p);
+  // the solve kernels (state_size <= 64) leave the column maxima of W behind for the tcgen05 digit planes
+  const bool fused_colmax = ctx->gemm_mode == 2 && m.s.k <= 64;
+  e_step_chunk(ctx, st, w, row0, rows, m, 2, ctx->llk.p, nullptr, ctx->part_solve.p,
+               fused_colmax ? ctx->colmax.p : nullptr);
   const int kblocks = (int)(round_up(rows, 32) / 32);
   int sk = splitk < kblocks ? splitk : (kblocks > 0 ? kblocks : 1);
   if (splitk > 1 && sk < 2) sk = 2 <= kblocks ? 2 : 1;
@@ -373,7 +379,7 @@ void em_chunk(ppca_b200_ctx *ctx, const SampleStore &st, const double *w, int64_
   if (ctx->gemm_mode == 2) {
     ctx->span_begin(FAM_SLICE);
     launch_slice_tc(L, ctx->GW.p, m.s.kkp, rows, m.s.kkp, kblocks, ctx->slices, ctx->WQ.p, ctx->WScale.p,
-                    ctx->colmax.p);
+                    ctx->colmax.p, fused_colmax);
     ctx->span_end();
   } else if (ctx->gemm_mode == 1) {
     ctx->span_begin(FAM_SLICE);

@@ -205,6 +205,8 @@ struct SolveArgs {
   double *cov;         // rows x k x k full covariances (nullable)
   double *part;        // SOLVE_SLOTS x 4 partial sums to accumulate into (nullable; needs llk): w t, w llk, w, #non-empty
   int mode;            // 0 = llk only, 1 = infer (z, cov), 2 = EM (z, W, wz, t)
+  unsigned long long *colmax;  // kkp (nullable, mode 2, k <= 64; zeroed by the caller): atomicMax of the bit patterns
+                               // of max_n |W[n][q]| — the column scales of the M-step digit planes, fused here
 };
 enum { SOLVE_SLOTS = 128 };
 void launch_solve(const Launcher &L, const SolveArgs &a);
@@ -270,8 +272,9 @@ void launch_ibitgemm(const Launcher &L, const IBitGemmArgs &a);
 
 // ---- tbitgemm.cu : the int8-sliced contraction on tcgen05 (TMEM accumulators) ----------------------------
 size_t sliced_tc_bytes(int kblocks32, int Nq, int T);
+// have_colmax: colmax_scratch already holds the column maxima (produced by the solve kernel); skip that pass
 void launch_slice_tc(const Launcher &L, const double *Bmat, int64_t ldb, int K, int Nq, int kblocks32, int T, int8_t *q,
-                     double *scale, unsigned long long *colmax_scratch);
+                     double *scale, unsigned long long *colmax_scratch, bool have_colmax = false);
 int tbitgemm_pick_splitk(int M, int Nq, int ksteps, int sms);
 void launch_tbitgemm(const Launcher &L, const uint32_t *bits, int64_t ldbits, int nwords, const int8_t *Bq,
                      const double *scale, int T, double *Out, int64_t ldo, int M, int Nq, int ksteps, int accumulate,

@@ -205,6 +205,11 @@ __global__ void __launch_bounds__(256, (KP == 32 ? 2 : (KP == 16 ? 3 : 4))) solv
   double *col = stage + SPW * kkp;                   // [2][32] pivot-column exchange
   double *yb = col + 64;                             // [32]
   double *zb = yb + 32;                              // [32]
+  // running max |W| per staged slot of this warp (column maxima for the int8 digit planes, fused here so the
+  // M-step slicing does not need its own pass over W)
+  double *cmw = smem_reg + (size_t)warps * per_warp + (size_t)wi * (SPW * kkp);
+  if (a.colmax)
+    for (int q = lane; q < SPW * kkp; q += 32) cmw[q] = 0.0;
   const double s2 = a.sigma * a.sigma;
   const double ln_sigma = log(a.sigma);
   const int groups = (a.rows_pad + SPW - 1) / SPW;
@@ -323,10 +328,27 @@ __global__ void __launch_bounds__(256, (KP == 32 ? 2 : (KP == 16 ? 3 : 4))) solv
           if (j >= li && j < k) so[j] = fma(wzi, zs[j], ws2 * A[j]);
       }
       __syncwarp();
-      for (int q = lane * 2; q < SPW * kkp; q += 64)
-        *reinterpret_cast<double2 *>(gsrc + q) = *reinterpret_cast<const double2 *>(stage + q);
+      for (int q = lane * 2; q < SPW * kkp; q += 64) {
+        const double2 v = *reinterpret_cast<const double2 *>(stage + q);
+        *reinterpret_cast<double2 *>(gsrc + q) = v;
+        if (a.colmax) {
+          double2 m = *reinterpret_cast<const double2 *>(cmw + q);
+          m.x = fmax(m.x, fabs(v.x));
+          m.y = fmax(m.y, fabs(v.y));
+          *reinterpret_cast<double2 *>(cmw + q) = m;
+        }
+      }
     }
     __syncwarp();
+  }
+  if (a.colmax) {
+    __syncthreads();
+    const double *all = smem_reg + (size_t)warps * per_warp;
+    for (int c = threadIdx.x; c < kkp; c += blockDim.x) {
+      double m = 0.0;
+      for (int j = 0; j < warps * SPW; ++j) m = fmax(m, all[(size_t)j * kkp + c]);
+      if (m > 0.0) atomicMax(a.colmax + c, (unsigned long long)__double_as_longlong(m));
+    }
   }
 }
 
@@ -349,6 +371,9 @@ __global__ void __launch_bounds__(256, 1) solve_reg64_kernel(SolveArgs a) {
   double *yb = col + 128;                              // [64]
   double *zb = yb + 64;                                // [64]
   double *red = zb + 64;                               // [64] scratch for reductions
+  double *cmw = smem_reg + (size_t)4 * per_pair + (size_t)pair * kkp;  // running max |W| of this pair's samples
+  if (a.colmax)
+    for (int q = li; q < kkp; q += 64) cmw[q] = 0.0;
   const double s2 = a.sigma * a.sigma;
   const double ln_sigma = log(a.sigma);
 
@@ -452,10 +477,26 @@ __global__ void __launch_bounds__(256, 1) solve_reg64_kernel(SolveArgs a) {
           if (j >= li && j < k) so[j] = fma(wzi, zb[j], ws2 * A[j]);
       }
       pair_sync(bar_id);
-      for (int q = li * 2; q < kkp; q += 128)
-        *reinterpret_cast<double2 *>(gsrc + q) = *reinterpret_cast<const double2 *>(stage + q);
+      for (int q = li * 2; q < kkp; q += 128) {
+        const double2 v = *reinterpret_cast<const double2 *>(stage + q);
+        *reinterpret_cast<double2 *>(gsrc + q) = v;
+        if (a.colmax) {
+          double2 m = *reinterpret_cast<const double2 *>(cmw + q);
+          m.x = fmax(m.x, fabs(v.x));
+          m.y = fmax(m.y, fabs(v.y));
+          *reinterpret_cast<double2 *>(cmw + q) = m;
+        }
+      }
     }
     pair_sync(bar_id);
+  }
+  if (a.colmax) {
+    __syncthreads();
+    const double *all = smem_reg + (size_t)4 * per_pair;
+    for (int c = threadIdx.x; c < kkp; c += blockDim.x) {
+      const double m = fmax(fmax(all[c], all[kkp + c]), fmax(all[2 * kkp + c], all[3 * kkp + c]));
+      if (m > 0.0) atomicMax(a.colmax + c, (unsigned long long)__double_as_longlong(m));
+    }
   }
 }
 
@@ -484,6 +525,9 @@ __global__ void __launch_bounds__(256, 2) solve_split64_kernel(SolveArgs a) {
   double *yb = col + 256;                            // [64]
   double *zpart = yb + 64;                           // [2][64] partial z per column half
   double *red = zpart + 128;                         // [16]
+  double *cmw = smem_reg + (size_t)2 * per_smp + (size_t)smp * kkp;  // running max |W| of this slot's samples
+  if (a.colmax)
+    for (int q = ws * 32 + lane; q < kkp; q += 128) cmw[q] = 0.0;
   const double s2 = a.sigma * a.sigma;
   const double ln_sigma = log(a.sigma);
 
@@ -595,15 +639,31 @@ __global__ void __launch_bounds__(256, 2) solve_split64_kernel(SolveArgs a) {
         }
       }
       quad_sync(bar_id);
-      for (int q = ts * 2; q < kkp; q += 256)
-        *reinterpret_cast<double2 *>(gsrc + q) = *reinterpret_cast<const double2 *>(stage + q);
+      for (int q = ts * 2; q < kkp; q += 256) {
+        const double2 v = *reinterpret_cast<const double2 *>(stage + q);
+        *reinterpret_cast<double2 *>(gsrc + q) = v;
+        if (a.colmax) {
+          double2 m = *reinterpret_cast<const double2 *>(cmw + q);
+          m.x = fmax(m.x, fabs(v.x));
+          m.y = fmax(m.y, fabs(v.y));
+          *reinterpret_cast<double2 *>(cmw + q) = m;
+        }
+      }
     }
     quad_sync(bar_id);
+  }
+  if (a.colmax) {
+    __syncthreads();
+    const double *all = smem_reg + (size_t)2 * per_smp;
+    for (int c = threadIdx.x; c < kkp; c += blockDim.x) {
+      const double m = fmax(all[c], all[kkp + c]);
+      if (m > 0.0) atomicMax(a.colmax + c, (unsigned long long)__double_as_longlong(m));
+    }
   }
 }
 
 static void launch_solve_split64(const Launcher &L, const SolveArgs &a) {
-  const size_t smem = (size_t)2 * (a.s.kkp + 2 * 128 + 64 + 128 + 16) * sizeof(double);
+  const size_t smem = (size_t)2 * (a.s.kkp + 2 * 128 + 64 + 128 + 16 + (a.colmax ? a.s.kkp : 0)) * sizeof(double);
   static bool configured = false;
   if (!configured) {
     CUDA_CHECK(cudaFuncSetAttribute(solve_split64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
@@ -617,10 +677,10 @@ static void launch_solve_split64(const Launcher &L, const SolveArgs &a) {
 }
 
 static void launch_solve_reg64(const Launcher &L, const SolveArgs &a) {
-  const size_t smem = (size_t)4 * (a.s.kkp + 5 * 64) * sizeof(double);
+  const size_t smem = (size_t)4 * (a.s.kkp + 5 * 64 + (a.colmax ? a.s.kkp : 0)) * sizeof(double);
   static bool configured = false;
   if (!configured) {
-    CUDA_CHECK(cudaFuncSetAttribute(solve_reg64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CUDA_CHECK(cudaFuncSetAttribute(solve_reg64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     configured = true;
   }
   int64_t blocks = (a.rows_pad + 3) / 4;
@@ -634,7 +694,12 @@ template <int KP>
 static void launch_solve_reg(const Launcher &L, const SolveArgs &a) {
   constexpr int SPW = 32 / KP;
   const int warps = 8;
-  const size_t smem = (size_t)warps * (SPW * a.s.kkp + 128) * sizeof(double);
+  const size_t smem = (size_t)warps * (SPW * a.s.kkp + 128 + (a.colmax ? SPW * a.s.kkp : 0)) * sizeof(double);
+  static bool configured = false;
+  if (!configured) {
+    CUDA_CHECK(cudaFuncSetAttribute(solve_reg_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    configured = true;
+  }
   const int groups = (a.rows_pad + SPW - 1) / SPW;
   int64_t blocks = (groups + warps - 1) / warps;
   const int64_t cap = (int64_t)L.sms * 8;
@@ -724,7 +789,10 @@ void launch_solve(const Launcher &L, const SolveArgs &a) {
     if (use_pair) launch_solve_reg64(L, a);
     else launch_solve_split64(L, a);
   }
-  else launch_solve_generic(L, a);
+  else {
+    REQUIRE(a.colmax == nullptr, "solve: the generic kernel (state_size > 64) does not produce column maxima");
+    launch_solve_generic(L, a);
+  }
   if (a.part) {
     solve_reduce_kernel<<<SOLVE_SLOTS, 256, 0, L.stream>>>(a.rows, a.llk, a.tn, a.dn, a.w, a.part);
     CUDA_CHECK(cudaGetLastError());

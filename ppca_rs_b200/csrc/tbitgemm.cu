@@ -112,6 +112,35 @@ __device__ __forceinline__ uint32_t nib4(uint32_t b, int shift) {
   return (((b >> shift) & 0xFu) * 0x00204081u) & 0x01010101u;
 }
 
+
+// Recombination of the T digit-plane sums d_t (exact int32) of one output: value = sum_t d_t 256^(T-1-t).
+// The planes are first merged in exact 64-bit integer arithmetic in groups of three (|group| < 2^48 for the
+// three-plane groups), so an output costs ceil(T/3) int64->double conversions and ceil(T/3)-1 FMAs instead of T
+// conversions and T-1 FMAs: the FP64 conversion unit was the epilogue's narrowest pipe.  Returns the value itself;
+// combine_scale<T>() carries the 2^(-8 (T-1)) normalisation and the 1/64 of the digit scale.
+template <int T>
+__device__ __forceinline__ double combine_planes(const int (&d)[T]) {
+  constexpr int NG = (T + 2) / 3, FIRST = T - 3 * (NG - 1);  // planes in the leading group
+  long long g = 0;
+#pragma unroll
+  for (int t = 0; t < FIRST; ++t) g = g * 256 + (long long)d[t];
+  double acc = (double)g;
+#pragma unroll
+  for (int j = 1; j < NG; ++j) {
+    const int t0 = FIRST + 3 * (j - 1);
+    const long long gj = ((long long)d[t0] * 256 + (long long)d[t0 + 1]) * 256 + (long long)d[t0 + 2];
+    acc = fma(acc, 16777216.0, (double)gj);
+  }
+  return acc;
+}
+template <int T>
+__device__ __forceinline__ constexpr double combine_scale() {
+  // the old Horner form returned value / 256^(T-1); keep that normalisation: 2^(-8 (T-1)) / 64
+  double s = 1.0 / 64.0;
+  for (int i = 0; i < T - 1; ++i) s *= 1.0 / 256.0;
+  return s;
+}
+
 }  // namespace tb
 
 struct TBitGemmArgs {
@@ -345,10 +374,10 @@ __global__ void __launch_bounds__(tb::THREADS, 1) tbitgemm_kernel(TBitGemmArgs a
             double v[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              double acc = (double)rg[T - 1][j];
+              int d[T];
 #pragma unroll
-              for (int t = T - 2; t >= 0; --t) acc = fma(acc, 1.0 / 256.0, (double)rg[t][j]);
-              v[j] = empty_slab ? 0.0 : acc * (a.scale[q + j] * (1.0 / 64.0));
+              for (int t = 0; t < T; ++t) d[t] = rg[t][j];
+              v[j] = empty_slab ? 0.0 : combine_planes<T>(d) * (a.scale[q + j] * combine_scale<T>());
             }
             double2 *p = reinterpret_cast<double2 *>(out + (int64_t)row * ldo + q);
 #pragma unroll
@@ -633,10 +662,10 @@ __global__ void __launch_bounds__(tb::THREADS_ATM, 1) tbitgemm_atm_kernel(TBitGe
             double v[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              double acc = (double)rg[T - 1][j];
+              int d[T];
 #pragma unroll
-              for (int t = T - 2; t >= 0; --t) acc = fma(acc, 1.0 / 256.0, (double)rg[t][j]);
-              v[j] = empty_slab ? 0.0 : acc * (a.scale[q + j] * (1.0 / 64.0));
+              for (int t = 0; t < T; ++t) d[t] = rg[t][j];
+              v[j] = empty_slab ? 0.0 : combine_planes<T>(d) * (a.scale[q + j] * combine_scale<T>());
             }
             double2 *p = reinterpret_cast<double2 *>(out + (int64_t)row * ldo + q);
 #pragma unroll
@@ -751,16 +780,18 @@ size_t sliced_tc_bytes(int kblocks32, int Nq, int T) {
 }
 
 void launch_slice_tc(const Launcher &L, const double *Bmat, int64_t ldb, int K, int Nq, int kblocks32, int T, int8_t *q,
-                     double *scale, unsigned long long *cm) {
+                     double *scale, unsigned long long *cm, bool have_colmax) {
   if (Nq <= 0 || kblocks32 <= 0) return;
-  CUDA_CHECK(cudaMemsetAsync(cm, 0, sizeof(unsigned long long) * Nq, L.stream));
   const int qtiles = (Nq + 31) / 32;  // 32-column thread blocks (independent of the MMA tile width)
-  int slabs = (4 * L.sms + qtiles - 1) / qtiles;
-  if (slabs > (K + 63) / 64) slabs = (K + 63) / 64;
-  if (slabs < 1) slabs = 1;
-  colmax_kernel_tc<<<dim3(qtiles, slabs), 256, 0, L.stream>>>(Bmat, ldb, K, Nq, cm);
-  CUDA_CHECK(cudaGetLastError());
-  ++*L.launch_counter;
+  if (!have_colmax) {
+    CUDA_CHECK(cudaMemsetAsync(cm, 0, sizeof(unsigned long long) * Nq, L.stream));
+    int slabs = (4 * L.sms + qtiles - 1) / qtiles;
+    if (slabs > (K + 63) / 64) slabs = (K + 63) / 64;
+    if (slabs < 1) slabs = 1;
+    colmax_kernel_tc<<<dim3(qtiles, slabs), 256, 0, L.stream>>>(Bmat, ldb, K, Nq, cm);
+    CUDA_CHECK(cudaGetLastError());
+    ++*L.launch_counter;
+  }
   dim3 grid(qtiles, (kblocks32 + 3) / 4);
   if (T == 6) slice_tc_kernel<6><<<grid, 128, 0, L.stream>>>(Bmat, ldb, K, Nq, kblocks32, cm, q, scale);
   else if (T == 7) slice_tc_kernel<7><<<grid, 128, 0, L.stream>>>(Bmat, ldb, K, Nq, kblocks32, cm, q, scale);
