@@ -335,7 +335,7 @@ def run_ours(args, wl, rank, world, local_rank):
                 "ShardedPPCA.step over HostDataset shards -> ppca_b200_em_stats_host + NCCL all-reduce + ppca_b200_em_finish")
     else:
         mix0 = pk.PPCAMix([pk.PPCAModel(sg, Cj, muj) for Cj, muj, sg in (init_params(d, k, SEED + 1000 + j) for j in range(m))], np.zeros(m))
-        host = None
+        host = pk.HostDataset(Xh, pin=True, ctx=ctx)            # page-locks Xh; Dataset(Xh) below DMAs from it directly
         box = {"mix": mix0}
         h2d = n_e2e * d * 8 + m * (d * k + d) * 8 * 2
         d2h = m * (d * k + 2 * d + 8) * 8

@@ -839,6 +839,13 @@ int32_t ppca_b200_dataset_from_host(ppca_b200_ctx *ctx, const double *x, int64_t
       auto cleanup = [&] {
         for (int b = 0; b < 2; ++b) cudaEventDestroy(done[b]);
       };
+      // caller memory that is already page-locked (cudaHostRegister / cudaHostAlloc) is DMA-ed directly
+      bool src_pinned = false;
+      {
+        cudaPointerAttributes pa;
+        if (cudaPointerGetAttributes(&pa, x) == cudaSuccess) src_pinned = pa.type == cudaMemoryTypeHost;
+        else cudaGetLastError();
+      }
       try {
         int i = 0;
         for (int64_t r0 = 0; r0 < n; r0 += rows_per, ++i) {
@@ -847,6 +854,12 @@ int32_t ppca_b200_dataset_from_host(ppca_b200_ctx *ctx, const double *x, int64_t
           if (i >= 2) CUDA_CHECK(cudaEventSynchronize(done[b]));  // the H2D that last used this pinned block
           const size_t bytes = (size_t)rows * d * sizeof(double);
           const char *src = reinterpret_cast<const char *>(x + r0 * d);
+          if (src_pinned) {
+            CUDA_CHECK(cudaMemcpyAsync(raw[b].p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+            CUDA_CHECK(cudaEventRecord(done[b], ctx->stream));
+            launch_ingest(ctx->L(), raw[b].p, rows, d, r0, *st);
+            continue;
+          }
           char *dst = reinterpret_cast<char *>(pin[b]);
           const int nthr = bytes >= ((size_t)4 << 20) ? 4 : 1;
           if (nthr == 1) {

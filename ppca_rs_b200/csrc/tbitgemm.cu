@@ -410,8 +410,13 @@ __global__ void __launch_bounds__(tb::THREADS, 1) tbitgemm_kernel(TBitGemmArgs a
   }
 }
 
-template <int T>
+// NGRP producer groups (128 threads each, taking jobs round-robin) and NEPI sets of four epilogue warps (each set
+// owns NQ / NEPI of the tile's columns); NGRP + NEPI = 3 keeps the CTA at 14 warps.  <2, 1> feeds long K loops
+// (mask expansion is the scarce resource), <1, 2> drains short ones (d <= 512: a tile is only a few K steps, the
+// FP64 recombination of its 32 x T accumulator columns is what bounds it; ncu: producers idle, epilogue warps busy).
+template <int T, int NGRP, int NEPI>
 __global__ void __launch_bounds__(tb::THREADS_ATM, 1) tbitgemm_atm_kernel(TBitGemmArgs a) {
+  static_assert(32 * (4 * NGRP + 2 + 4 * NEPI) == tb::THREADS_ATM, "role split must add up to the CTA size");
   using namespace tb;
   constexpr int N = T * NQ;
   // the A tile never touches shared memory here: producers write it to tensor memory (tcgen05.st), the MMA
@@ -429,7 +434,7 @@ __global__ void __launch_bounds__(tb::THREADS_ATM, 1) tbitgemm_atm_kernel(TBitGe
 
   // warps 0-3 / 4-7: two producer groups (alternate jobs; warp w writes TMEM lane quarter w & 3), warp 8: MMA issuer,
   // warps 9-12: epilogue (quarters 1,2,3,0), warp 13: digit-plane loader
-  constexpr int MMA_WARP = 8, EPI_WARP0 = 9, LOAD_WARP = 13;
+  constexpr int MMA_WARP = 4 * NGRP, EPI_WARP0 = MMA_WARP + 1, LOAD_WARP = EPI_WARP0 + 4 * NEPI;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t bar0 = smem_u32(bars);
@@ -445,7 +450,7 @@ __global__ void __launch_bounds__(tb::THREADS_ATM, 1) tbitgemm_atm_kernel(TBitGe
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull_bar(b), 1);
-      mbar_init(tempty_bar(b), 128);
+      mbar_init(tempty_bar(b), 128 * NEPI);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -463,9 +468,9 @@ __global__ void __launch_bounds__(tb::THREADS_ATM, 1) tbitgemm_atm_kernel(TBitGe
   const int ntiles = mtiles * qtiles * a.splitk;
   const int ks_per = (a.ksteps + a.splitk - 1) / a.splitk;
 
-  if (warp < 8) {
+  if (warp < 4 * NGRP) {
     // ===================== producers =====================
-    // The (tile, K step) jobs of this CTA form one sequence; producer group g = warp / 4 takes jobs j = g (mod 2).
+    // The (tile, K step) jobs of this CTA form one sequence; producer group g = warp / 4 takes jobs j = g (mod NGRP).
     // Per job every thread of the group expands its mask row (row = 32 (warp & 3) + lane = TMEM lane) to int8
     // {0,1} in registers and writes the 128 bytes to the stage's tensor-memory columns with one tcgen05.st;
     // tcgen05.wait::st, fence, arrive.  The 16 bytes of mask a thread needs per job are fetched DEPTH own jobs
@@ -494,11 +499,15 @@ __global__ void __launch_bounds__(tb::THREADS_ATM, 1) tbitgemm_atm_kernel(TBitGe
         if (--c.tiles_left > 0) open_tile(c);
       }
     };
-    auto step = [&](Cursor &c) {  // to the next job of the sequence
+    auto step1 = [&](Cursor &c) {  // to the next job of the sequence
       if (c.tiles_left > 0) {
         ++c.ks;
         settle(c);
       }
+    };
+    auto step = [&](Cursor &c) {  // to this group's next job
+#pragma unroll
+      for (int g = 0; g < NGRP; ++g) step1(c);
     };
     auto start = [&](Cursor &c) {
       c.tiles_left = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
@@ -508,7 +517,7 @@ __global__ void __launch_bounds__(tb::THREADS_ATM, 1) tbitgemm_atm_kernel(TBitGe
       c.row_ok = false;
       if (c.tiles_left > 0) open_tile(c);
       settle(c);
-      if (grp == 1) step(c);  // group 1 starts at job 1
+      if (grp == 1) step1(c);  // group 1 starts at job 1
     };
     auto fetch_words = [&](const Cursor &c, int slot) {  // 4 x 4-byte cp.async (mask rows are only 4-byte aligned)
       const uint32_t dst = smem_u32(ring + (slot * 128 + gt) * 4);
@@ -528,13 +537,11 @@ __global__ void __launch_bounds__(tb::THREADS_ATM, 1) tbitgemm_atm_kernel(TBitGe
     for (; nf < DEPTH; ++nf) {
       fetch_words(cf, nf % RING);
       step(cf);
-      step(cf);
     }
     int job = grp, own = 0;
     while (cp.tiles_left > 0) {
       fetch_words(cf, nf % RING);
       ++nf;
-      step(cf);
       step(cf);
       const int stage = job & (STAGES - 1);
       const uint32_t phase = (uint32_t)(job / STAGES) & 1u;
@@ -551,8 +558,7 @@ __global__ void __launch_bounds__(tb::THREADS_ATM, 1) tbitgemm_atm_kernel(TBitGe
       tc_fence_before();
       mbar_arrive(full_bar(stage));
       step(cp);
-      step(cp);
-      job += 2;
+      job += NGRP;
       ++own;
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
@@ -628,7 +634,8 @@ __global__ void __launch_bounds__(tb::THREADS_ATM, 1) tbitgemm_atm_kernel(TBitGe
     // ===================== epilogue =====================
     int buf = 0;
     uint32_t tphase = 0;
-    const int quarter = warp & 3;  // TMEM lane quarter this warp may access (warps 9..12 -> 1,2,3,0)
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access (hardware rule: warp id mod 4)
+    const int cset = (warp - EPI_WARP0) >> 2;  // which NQ / NEPI column set of the tile this warp drains
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int z = tile / (mtiles * qtiles), rem = tile % (mtiles * qtiles);
       const int qt = rem / mtiles, mt = rem % mtiles;
@@ -652,7 +659,7 @@ __global__ void __launch_bounds__(tb::THREADS_ATM, 1) tbitgemm_atm_kernel(TBitGe
         const int row = mt * BM + 128 * h + quarter * 32 + lane;
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * TCOLS + h * N);
 #pragma unroll 1
-        for (int qc = 0; qc < NQ / 8; ++qc) {
+        for (int qc = cset * (NQ / 8 / NEPI); qc < (cset + 1) * (NQ / 8 / NEPI); ++qc) {
           int rg[T][8];
 #pragma unroll
           for (int t = 0; t < T; ++t) tc_ld8(taddr + (uint32_t)(t * NQ + 8 * qc), rg[t]);
@@ -722,15 +729,23 @@ __global__ void __launch_bounds__(128) slice_tc_kernel(const double *__restrict_
 #pragma unroll
     for (int j = 0; j < 8; ++j) words[t][j] = 0u;
 #pragma unroll
-  for (int r = 0; r < 32; ++r) {
-    const int row = kb * 32 + r;
-    const double x = (row < K) ? B[(int64_t)row * ldb + q] : 0.0;
-    // rint(x / s 2^(8T-2)) as T balanced base-256 digits (see ibitgemm.cu): +128 below the top digit, then ^ 0x80
-    constexpr unsigned long long BIAS = 0x0080808080808080ull & ((1ull << (8 * (T - 1))) - 1ull);
-    const unsigned long long v = (unsigned long long)(__double2ll_rn(x * inv) + (long long)BIAS) ^ BIAS;
+  for (int half = 0; half < 2; ++half) {
+    double xs[16];  // 16 independent loads in flight per thread before the first conversion
 #pragma unroll
-    for (int t = 0; t < T; ++t)  // plane 0 = most significant digit
-      words[t][r >> 2] |= (uint32_t)((v >> (8 * (T - 1 - t))) & 0xffull) << (8 * (r & 3));
+    for (int r = 0; r < 16; ++r) {
+      const int row = kb * 32 + 16 * half + r;
+      xs[r] = (row < K) ? __ldg(B + (int64_t)row * ldb + q) : 0.0;
+    }
+#pragma unroll
+    for (int rr = 0; rr < 16; ++rr) {
+      const int r = 16 * half + rr;
+      // rint(x / s 2^(8T-2)) as T balanced base-256 digits (see ibitgemm.cu): +128 below the top digit, then ^ 0x80
+      constexpr unsigned long long BIAS = 0x0080808080808080ull & ((1ull << (8 * (T - 1))) - 1ull);
+      const unsigned long long v = (unsigned long long)(__double2ll_rn(xs[rr] * inv) + (long long)BIAS) ^ BIAS;
+#pragma unroll
+      for (int t = 0; t < T; ++t)  // plane 0 = most significant digit
+        words[t][r >> 2] |= (uint32_t)((v >> (8 * (T - 1 - t))) & 0xffull) << (8 * (r & 3));
+    }
   }
 #pragma unroll
   for (int t = 0; t < T; ++t) {
@@ -833,10 +848,15 @@ static void launch_tb(const Launcher &L, const TBitGemmArgs &a) {
       constexpr size_t SMEM_ATM = (size_t)tb::STAGES * (T * tb::NQ * tb::BKB) + 1024 + 2 * 4 * 128 * 16;
       static bool configured_atm = false;
       if (!configured_atm) {
-        CUDA_CHECK(cudaFuncSetAttribute(tbitgemm_atm_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_ATM));
+        CUDA_CHECK(cudaFuncSetAttribute(tbitgemm_atm_kernel<T, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_ATM));
+        CUDA_CHECK(cudaFuncSetAttribute(tbitgemm_atm_kernel<T, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_ATM));
         configured_atm = true;
       }
-      tbitgemm_atm_kernel<T><<<grid, tb::THREADS_ATM, SMEM_ATM, L.stream>>>(a);
+      static const int force = getenv("PPCA_B200_TC_ROLES") ? atoi(getenv("PPCA_B200_TC_ROLES")) : 0;
+      const int ks_per = (a.ksteps + a.splitk - 1) / a.splitk;
+      const bool drain = force ? force == 2 : ks_per <= 4;  // short K loops: epilogue-bound
+      if (drain) tbitgemm_atm_kernel<T, 1, 2><<<grid, tb::THREADS_ATM, SMEM_ATM, L.stream>>>(a);
+      else tbitgemm_atm_kernel<T, 2, 1><<<grid, tb::THREADS_ATM, SMEM_ATM, L.stream>>>(a);
       CUDA_CHECK(cudaGetLastError());
       ++*L.launch_counter;
       return;
