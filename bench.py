@@ -160,6 +160,21 @@ def int8_tc_peak():
         return float(json.load(f)["utcimma_ts_n192_tops"]), "profiles/r01_utc_i8_peak.json (tools/utc_peak.cu, round 1)"
 
 
+def measured_traffic(workload, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed ncu --set full capture
+    of one chunk of this workload (profiles/r01_traffic.json); None when that workload was not captured."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            t = json.load(f)
+        wl = {"c3": "c3s"}.get(workload, workload)
+        for name, v in t[wl]["kernels"].items():
+            if name.startswith(kernel):
+                return v["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    return None
+
+
 def measured_hbm_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -398,8 +413,15 @@ def run_ours(args, wl, rank, world, local_rank):
     flops_bit = contractions * (2 * d * kk) * n * args.steps          # algorithmic FP64 flops
     fp64_equiv = flops_bit / (bit_ms * 1e-3) / 1e12 if bit_ms > 0 else None
     launches_bit = contractions * args.steps * max(1, -(-n // max(1, ctx_chunk(ctx, n, d, k))))
+    n_chunk = min(ctx_chunk(ctx, n, d, k), n)
+    # one launch = one chunk: the packed mask in, G (E-step, 8 B per entry) or the W digit planes (M-step, `slices` B)
+    alg_bytes_launch = n_chunk * ((d + 31) // 32) * 4 + n_chunk * ((kk + 7) // 8 * 8) * (8 + args.slices) / 2.0
     common = {
-        "bound": "tensor", "traffic": None, "share_of_step": bit_ms / ms_total if ms_total else None,
+        "bound": "tensor", "traffic": measured_traffic(args.workload, "tbitgemm_atm_kernel") if args.gemm == "tc" else None,
+        "traffic_note": "DRAM bytes per launch (E- and M-step launches averaged) from profiles/r01_traffic.json; below the "
+                        "algorithmic bytes because the 126 MB L2 absorbs most of the chunk's G / W round trip",
+        "algorithmic_bytes_per_launch": alg_bytes_launch,
+        "share_of_step": bit_ms / ms_total if ms_total else None,
         "avg_launch_ms": bit_ms / launches_bit if launches_bit else None,
         "family_ms_per_step": {kname: v / args.steps for kname, v in fam.items()},
         "fp64_equivalent_tflops": fp64_equiv, "fp64_dmma_peak_tflops": peak64, "fp64_peak_source": peak64_src,
