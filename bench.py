@@ -221,6 +221,8 @@ def host_sample(wl, rows, seed):
 
 def cpu_step_time(wl, X, steps, warmup):
     from oracle import oracle as orc  # bench.py's cpu_baseline / reference leg only
+    # the reference fans out on rayon's global pool = every host core; torchrun exports OMP_NUM_THREADS=1, undo that
+    orc.set_num_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     d, k, m = wl["d"], wl["k"], wl["m"]
     times = []
     if m == 1:
@@ -458,7 +460,7 @@ def run_ours(args, wl, rank, world, local_rank):
     fam_bytes = {                                           # algorithmic bytes per sample (per component)
         "proj": 8 * d + d / 8 + 8 * kp,                                   # read x + mask, write y
         "solve": 8 * (2 * kkp + 3 * kp + 4),                              # read G, y; write W, z, w z, scalars
-        "slice": (8 + 8 + args.slices) * kkp if args.gemm != "dmma" else 0,  # read W twice, write T digit planes
+        "slice": (8 + args.slices) * kkp if args.gemm != "dmma" else 0,      # read W once, write T digit planes
         "cross_resid": 8 * d + d / 8 + 16 * kp,                           # read x + mask, z, w z
     }
     fam_mult = {"proj": passes, "solve": passes, "slice": comps, "cross_resid": comps}

@@ -106,6 +106,13 @@ class stable:
         return False
 
 
+def set_num_threads(n: int) -> None:
+    """rayon's global pool uses every core regardless of OMP_NUM_THREADS (which torchrun sets to 1)."""
+    lib().oracle_set_num_threads.argtypes = [C.c_int]
+    lib().oracle_set_num_threads.restype = None
+    lib().oracle_set_num_threads(int(n))
+
+
 def num_threads() -> int:
     return lib().oracle_num_threads()
 

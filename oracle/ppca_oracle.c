@@ -403,6 +403,10 @@ static void infer_one(scratch_t *s, const double *x, const double *C, const doub
  * exported API
  * ---------------------------------------------------------------------------------------- */
 
+EXPORT void oracle_set_num_threads(int n) {
+  if (n > 0) omp_set_num_threads(n);
+}
+
 EXPORT int oracle_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();
