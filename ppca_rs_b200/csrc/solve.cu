@@ -14,6 +14,7 @@
 // This is the generic (any k) shared-memory kernel: the (k+1) x k augmented matrix [M ; y^T] lives in shared
 // memory, one per warp; L^{-1} is built in the unused strict upper triangle.
 #include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 #include "mma.cuh"
@@ -662,6 +663,263 @@ __global__ void __launch_bounds__(256, 2) solve_split64_kernel(SolveArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Blocked Gauss-Jordan on the FP64 tensor cores (k <= 64).  M_n is held as 8 x 8 tiles in the accumulator layout
+// of mma.sync.m8n8k4.f64: warp i of the sample owns block row i (NT tiles, 2 doubles per lane each).  Per pivot
+// block b (in place, no pivoting: every pivot block is an SPD Schur complement):
+//     A_bb <- P^-1 ;  A_bj <- P^-1 A_bj ;  A_ib <- -A_ib P^-1 ;  A_ij <- A_ij - (A_ib P^-1) A_bj
+// Warp b publishes its raw row block to shared memory, inverts the 8 x 8 pivot block in registers (scalar
+// Gauss-Jordan over warp shuffles: the only serial part) and publishes P^-1; after ONE barrier every warp updates its
+// block row with 2 NT DMMAs, taking the B operands (A_bj, P^-1) from shared memory and converting its own panel tile
+// from accumulator to A-operand layout with two shuffles per half.  Against the scalar kernels above this issues
+// k^3 / 256 DMMAs instead of k^3 / 32 DFMAs plus a 2 k-byte pivot-row broadcast per pivot, so the FP64 pipe, not the
+// issue slots and shared-memory latency, is what bounds it.  ln det M = sum_b ln det P_b.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double acc_to_aop(double x0, double x1, int h, int lane) {
+  // accumulator layout (r, 2c / 2c+1) -> A operand of K half h: lane (r, c) needs X[r][4h + c]
+  const int c = lane & 3, src = (lane & ~3) | (2 * h + (c >> 1));
+  const double t0 = __shfl_sync(0xffffffffu, x0, src), t1 = __shfl_sync(0xffffffffu, x1, src);
+  return (c & 1) ? t1 : t0;
+}
+
+__device__ __forceinline__ void inv8_acc(double &x0, double &x1, double &det, int lane) {
+  const int r = lane >> 2, c = lane & 3;
+  det = 1.0;
+#pragma unroll
+  for (int p = 0; p < 8; ++p) {
+    const double xs = (p & 1) ? x1 : x0;
+    const double d = __shfl_sync(0xffffffffu, xs, 4 * p + (p >> 1));            // P[p][p]
+    const double f = __shfl_sync(0xffffffffu, xs, (lane & ~3) + (p >> 1));      // P[r][p]
+    const double row0 = __shfl_sync(0xffffffffu, x0, 4 * p + c);                // P[p][2c]
+    const double row1 = __shfl_sync(0xffffffffu, x1, 4 * p + c);                // P[p][2c+1]
+    const double inv = fast_rcp(d);
+    det *= d;
+    const double n0 = row0 * inv, n1 = row1 * inv, fi = -f * inv;
+    const bool isp = r == p, c0p = 2 * c == p, c1p = 2 * c + 1 == p;
+    x0 = isp ? (c0p ? inv : n0) : (c0p ? fi : fma(-f, n0, x0));
+    x1 = isp ? (c1p ? inv : n1) : (c1p ? fi : fma(-f, n1, x1));
+  }
+}
+
+template <int NT>
+struct BlkCfg {
+  static constexpr int KP = 8 * NT, TPS = 32 * NT, SPC = 256 / TPS, LDR = KP + 8;
+  __host__ __device__ static int per_slot(int kkp, bool colmax) {
+    return kkp + 2 * 8 * LDR + 2 * 64 + 2 * KP + 32 + (colmax ? kkp : 0);
+  }
+};
+
+template <int NT>
+__global__ void __launch_bounds__(256, (NT == 8 ? 3 : 4)) solve_blk_kernel(SolveArgs a) {
+  using Cfg = BlkCfg<NT>;
+  constexpr int KP = Cfg::KP, TPS = Cfg::TPS, SPC = Cfg::SPC, LDR = Cfg::LDR;
+  extern __shared__ __align__(16) double smem_reg[];
+  const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+  const int slot = wi / NT, wb = wi % NT, ts = threadIdx.x % TPS;
+  const int r = lane >> 2, c = lane & 3;
+  const int k = a.s.k, kk = a.s.kk, kkp = a.s.kkp, kp = a.s.kp;
+  const int per_slot = Cfg::per_slot(kkp, a.colmax != nullptr);
+  double *stage = smem_reg + (size_t)slot * per_slot;  // packed G in, packed W out
+  double *rowbuf = stage + kkp;                        // [2][8][LDR] raw pivot row block
+  double *pinv = rowbuf + 2 * 8 * LDR;                 // [2][8][8]
+  double *yb = pinv + 128;                             // [KP]
+  double *zb = yb + KP;                                // [KP]
+  double *red = zb + KP;                               // [32]: quad[0..8) logdet[8..16) trace[16..24)
+  double *cmw = red + 32;                              // [kkp] running max |W| (optional)
+  const int bar_id = slot + 1;
+  auto sample_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(TPS) : "memory"); };
+  if (a.colmax)
+    for (int q = ts; q < kkp; q += TPS) cmw[q] = 0.0;
+  const double s2 = a.sigma * a.sigma;
+  const double ln_sigma = log(a.sigma);
+  const int gr = 8 * wb + r;  // this lane's matrix row
+
+  for (int row = blockIdx.x * SPC + slot; row < a.rows_pad; row += gridDim.x * SPC) {
+    double *gsrc = a.GW + (int64_t)row * kkp;
+    for (int q = ts * 2; q < kkp; q += 2 * TPS)
+      *reinterpret_cast<double2 *>(stage + q) = *reinterpret_cast<const double2 *>(gsrc + q);
+    if (ts < KP) yb[ts] = (ts < kp) ? a.YZ[(int64_t)row * kp + ts] : 0.0;
+    const int dn = row < a.rows ? a.dn[row] : 0;
+    const bool empty = dn == 0;
+    const double w = (a.w && row < a.rows) ? a.w[row] : (row < a.rows ? 1.0 : 0.0);
+    sample_sync();
+
+    // block row wb of M = sigma^2 I + G (identity where padded or empty)
+    double x[NT][2];
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const int gc = 8 * j + 2 * c + s;
+        const bool use = !empty && gr < k && gc < k;
+        const int lo = min(gr, gc), hi = max(gr, gc);
+        const double g = stage[use ? tri_idx(lo, hi, k) : 0];
+        const double unit = (gr == gc) ? 1.0 : 0.0;
+        x[j][s] = use ? fma(unit, s2, g) : unit;
+      }
+
+    double logdet = 0.0;
+#pragma unroll
+    for (int b = 0; b < NT; ++b) {
+      double *rb = rowbuf + (b & 1) * (8 * LDR);
+      double *pb = pinv + (b & 1) * 64;
+      if (wb == b) {
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+          *reinterpret_cast<double2 *>(rb + r * LDR + 8 * j + 2 * c) = make_double2(x[j][0], x[j][1]);
+        double det;
+        inv8_acc(x[b][0], x[b][1], det, lane);
+        logdet += log(det);
+        *reinterpret_cast<double2 *>(pb + r * 8 + 2 * c) = make_double2(x[b][0], x[b][1]);
+      }
+      sample_sync();
+      if (wb == b) {
+        const double a0 = acc_to_aop(x[b][0], x[b][1], 0, lane), a1 = acc_to_aop(x[b][0], x[b][1], 1, lane);
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+          if (j == b) continue;
+          double c0 = 0.0, c1 = 0.0;
+          dmma884(c0, c1, a0, rb[c * LDR + 8 * j + r]);
+          dmma884(c0, c1, a1, rb[(4 + c) * LDR + 8 * j + r]);
+          x[j][0] = c0;
+          x[j][1] = c1;
+        }
+      } else {
+        double l0 = 0.0, l1 = 0.0;  // L = A_ib P^-1
+        dmma884(l0, l1, acc_to_aop(x[b][0], x[b][1], 0, lane), pb[c * 8 + r]);
+        dmma884(l0, l1, acc_to_aop(x[b][0], x[b][1], 1, lane), pb[(4 + c) * 8 + r]);
+        l0 = -l0;
+        l1 = -l1;
+        const double a0 = acc_to_aop(l0, l1, 0, lane), a1 = acc_to_aop(l0, l1, 1, lane);
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+          if (j == b) continue;
+          dmma884(x[j][0], x[j][1], a0, rb[c * LDR + 8 * j + r]);
+          dmma884(x[j][0], x[j][1], a1, rb[(4 + c) * LDR + 8 * j + r]);
+        }
+        x[b][0] = l0;
+        x[b][1] = l1;
+      }
+    }
+    // x = block row wb of M^-1
+
+    // z = M^-1 y, quad = y^T z, trace term
+    double zp = 0.0;
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      const double2 yv = *reinterpret_cast<const double2 *>(yb + 8 * j + 2 * c);
+      zp = fma(x[j][0], yv.x, zp);
+      zp = fma(x[j][1], yv.y, zp);
+    }
+    zp += __shfl_xor_sync(0xffffffffu, zp, 1);
+    zp += __shfl_xor_sync(0xffffffffu, zp, 2);
+    const bool live = !empty && gr < k;
+    const double zi = live ? zp : 0.0;
+    if (c == 0) zb[gr] = zi;
+    const double quad = warp_sum(c == 0 ? yb[gr] * zi : 0.0);
+    double tr = 0.0;
+    if (a.mode == 2) {  // t = sigma^2 sum_i (1 - sigma^2 M^-1_ii)
+      double diag = 0.0;
+#pragma unroll
+      for (int j = 0; j < NT; ++j)
+        if (j == wb) diag = (r & 1) ? x[j][1] : x[j][0];
+      tr = warp_sum((live && c == (r >> 1)) ? fma(-s2, diag, 1.0) : 0.0);
+    }
+    if (lane == 0) {
+      red[wb] = quad;
+      red[8 + wb] = empty ? 0.0 : logdet;
+      red[16 + wb] = tr;
+    }
+    sample_sync();
+    if (ts == 0 && row < a.rows) {
+      double sq = 0.0, sl = 0.0, st = 0.0;
+#pragma unroll
+      for (int i = 0; i < NT; ++i) {
+        sq += red[i];
+        sl += red[8 + i];
+        st += red[16 + i];
+      }
+      if (a.llk) {
+        double llk = 0.0;
+        if (!empty)
+          llk = -0.5 * (a.nx[row] - sq) / s2 - 0.5 * (sl + 2.0 * ln_sigma * (double)(dn - k)) -
+                0.5 * LN_2PI * (double)dn;
+        a.llk[row] = llk;
+      }
+      if (a.mode == 2 && a.tn) a.tn[row] = empty ? 0.0 : s2 * st;
+    }
+    if (a.mode != 0) {
+      if (ts < kp) {
+        const double zv = zb[ts];
+        a.YZ[(int64_t)row * kp + ts] = zv;
+        if (a.WZ) a.WZ[(int64_t)row * kp + ts] = w * zv;
+      }
+      if (a.cov && row < a.rows && gr < k) {
+        double *cv = a.cov + (int64_t)row * k * k + (int64_t)gr * k;
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+#pragma unroll
+          for (int s = 0; s < 2; ++s) {
+            const int gc = 8 * j + 2 * c + s;
+            if (gc < k) cv[gc] = empty ? (gc == gr ? 1.0 : 0.0) : s2 * x[j][s];
+          }
+      }
+    }
+    if (a.mode == 2) {
+      // W = w (z z^T + sigma^2 M^-1), packed upper, in place of G (all reads of G happened before the elimination)
+      const double ws2 = empty ? 0.0 : w * s2, wzi = empty ? 0.0 : w * zi;
+      if (gr < k) {
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+#pragma unroll
+          for (int s = 0; s < 2; ++s) {
+            const int gc = 8 * j + 2 * c + s;
+            if (gc >= gr && gc < k) stage[tri_idx(gr, gc, k)] = fma(wzi, zb[gc], ws2 * x[j][s]);
+          }
+      }
+      for (int q = kk + ts; q < kkp; q += TPS) stage[q] = 0.0;
+      sample_sync();
+      for (int q = ts * 2; q < kkp; q += 2 * TPS) {
+        const double2 v = *reinterpret_cast<const double2 *>(stage + q);
+        *reinterpret_cast<double2 *>(gsrc + q) = v;
+        if (a.colmax) {
+          double2 m = *reinterpret_cast<const double2 *>(cmw + q);
+          m.x = fmax(m.x, fabs(v.x));
+          m.y = fmax(m.y, fabs(v.y));
+          *reinterpret_cast<double2 *>(cmw + q) = m;
+        }
+      }
+    }
+    sample_sync();
+  }
+  if (a.colmax) {
+    __syncthreads();
+    for (int q = threadIdx.x; q < kkp; q += blockDim.x) {
+      double m = 0.0;
+#pragma unroll
+      for (int sl = 0; sl < SPC; ++sl) m = fmax(m, smem_reg[(size_t)sl * per_slot + (cmw - stage) + q]);
+      if (m > 0.0) atomicMax(a.colmax + q, (unsigned long long)__double_as_longlong(m));
+    }
+  }
+}
+
+template <int NT>
+static void launch_solve_blk(const Launcher &L, const SolveArgs &a) {
+  using Cfg = BlkCfg<NT>;
+  const size_t smem = (size_t)Cfg::SPC * Cfg::per_slot(a.s.kkp, a.colmax != nullptr) * sizeof(double);
+  static bool configured = false;
+  if (!configured) {
+    CUDA_CHECK(cudaFuncSetAttribute(solve_blk_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    configured = true;
+  }
+  int64_t blocks = (a.rows_pad + Cfg::SPC - 1) / Cfg::SPC;
+  const int64_t cap = (int64_t)L.sms * (NT == 8 ? 3 : 4);
+  if (blocks > cap) blocks = cap;
+  solve_blk_kernel<NT><<<(unsigned)blocks, 256, smem, L.stream>>>(a);
+  CUDA_CHECK(cudaGetLastError());
+  ++*L.launch_counter;
+}
+
 static void launch_solve_split64(const Launcher &L, const SolveArgs &a) {
   const size_t smem = (size_t)2 * (a.s.kkp + 2 * 128 + 64 + 128 + 16 + (a.colmax ? a.s.kkp : 0)) * sizeof(double);
   static bool configured = false;
@@ -781,7 +1039,20 @@ static void launch_solve_generic(const Launcher &L, const SolveArgs &a) {
 void launch_solve(const Launcher &L, const SolveArgs &a) {
   if (a.rows_pad <= 0) return;
   REQUIRE(a.mode == 0 || a.GW != nullptr, "solve: missing Gram buffer");
-  if (a.s.k <= 8) launch_solve_reg<8>(L, a);
+  // PPCA_B200_SOLVE: unset / "scalar" (default) = the register-resident scalar kernels; "blk" = the DMMA-blocked
+  // kernel for 16 < k <= 64, "blk16" = also for 8 < k <= 16.  Measured on B200 (profiles/r01_solve_blk_ncu.txt): the
+  // blocked kernel issues 3x fewer instructions but only 3 samples fit an SM and 7 of a sample's 8 warps wait at the
+  // barrier while the 8 x 8 pivot block is inverted (a chain of 8 dependent reciprocals), so it ties at k = 64
+  // (28.1 vs 27.7 ms per 0.5 M samples) and loses at k = 32 (16.8 vs 9.9 ms) and k = 16 (3.3 vs 1.6 ms).
+  static const int blk_mode = [] {
+    const char *e = getenv("PPCA_B200_SOLVE");
+    if (!e) return 0;
+    return strcmp(e, "blk") == 0 ? 1 : (strcmp(e, "blk16") == 0 ? 2 : 0);
+  }();
+  if (blk_mode >= 1 && a.s.k > 32 && a.s.k <= 64) launch_solve_blk<8>(L, a);
+  else if (blk_mode >= 1 && a.s.k > 16 && a.s.k <= 32) launch_solve_blk<4>(L, a);
+  else if (blk_mode == 2 && a.s.k > 8 && a.s.k <= 16) launch_solve_blk<2>(L, a);
+  else if (a.s.k <= 8) launch_solve_reg<8>(L, a);
   else if (a.s.k <= 16) launch_solve_reg<16>(L, a);
   else if (a.s.k <= 32) launch_solve_reg<32>(L, a);
   else if (a.s.k <= 64) {
