@@ -161,6 +161,13 @@ int32_t ppca_b200_iterate_host(ppca_b200_ctx *ctx, const double *x, int64_t n, i
  * ppca_b200_em_stats_len), to be all-reduced by the caller and finished with ppca_b200_em_finish. */
 int32_t ppca_b200_em_stats_host(ppca_b200_ctx *ctx, const double *x, int64_t n, int32_t d, const double *weights,
                                 int32_t k, const double *C, const double *mu, double sigma, double *stats_dev);
+/* Out-of-core inference: PPCAModel::smooth (extrapolate = 0) / ::extrapolate (= 1) (ppca_model.rs:237-261) and
+ * ::llks (:152-159) over host-resident samples, streamed like ppca_b200_iterate_host; three streams overlap the H2D
+ * of block i+1, the kernels of block i and the D2H of block i-1.  `out` (n x d, nullable) receives the
+ * reconstruction (observed slots of extrapolate are bit copies of x), `llks` (n, nullable) the log-likelihoods. */
+int32_t ppca_b200_reconstruct_host(ppca_b200_ctx *ctx, const double *x, int64_t n, int32_t d, int32_t k,
+                                   const double *C, const double *mu, double sigma, int32_t extrapolate, double *out,
+                                   double *llks);
 /* cudaHostRegister / cudaHostUnregister of a caller-owned host range (e.g. a numpy array). */
 int32_t ppca_b200_host_register(const void *p, uint64_t bytes);
 int32_t ppca_b200_host_unregister(const void *p);

@@ -12,6 +12,7 @@ from typing import Literal, Optional
 import numpy as np
 
 from ._native import Context, NativeError, device_count, get_context, set_context
+from .adapter import DataFrameAdapter, DataFrameAdapterDescription
 from .model import (
     Dataset,
     DatasetChunks,
@@ -29,7 +30,8 @@ __version__ = "0.1.0"
 
 __all__ = [
     "Dataset", "DatasetChunks", "HostDataset", "InferredMasked", "InferredMaskedMix", "PosteriorSampler", "PosteriorSamplerMix",
-    "PPCAMix", "PPCAModel", "Prior", "PPCATrainer", "PPCAMixTrainer", "TrainMetrics", "Context", "NativeError",
+    "PPCAMix", "PPCAModel", "Prior", "PPCATrainer", "PPCAMixTrainer", "TrainMetrics", "DataFrameAdapter",
+    "DataFrameAdapterDescription", "Context", "NativeError",
     "device_count", "get_context", "set_context",
 ]
 

@@ -86,6 +86,8 @@ _PROTOTYPES = {
     ),
     "ppca_b200_em_stats_host": (
         C.c_int32, [c_ctx_p, c_dp, C.c_int64, C.c_int32, c_dp, C.c_int32, c_dp, c_dp, C.c_double, C.c_void_p]),
+    "ppca_b200_reconstruct_host": (
+        C.c_int32, [c_ctx_p, c_dp, C.c_int64, C.c_int32, C.c_int32, c_dp, c_dp, C.c_double, C.c_int32, c_dp, c_dp]),
     "ppca_b200_host_register": (C.c_int32, [C.c_void_p, C.c_uint64]),
     "ppca_b200_host_unregister": (C.c_int32, [C.c_void_p]),
     "ppca_b200_em_stats_len": (C.c_int64, [C.c_int32, C.c_int32]),

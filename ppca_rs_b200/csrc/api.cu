@@ -53,6 +53,10 @@ struct ppca_b200_ctx {
   cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
   DevBuf<double> s_raw[2], s_wraw[2], s_w;
   std::shared_ptr<SampleStore> s_store, s_tail;
+  // out-of-core inference (ppca_b200_reconstruct_host): D2H stream and double-buffered outputs
+  cudaStream_t out_stream = nullptr;
+  cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_outfree[2] = {nullptr, nullptr};
+  DevBuf<double> s_out[2], s_llk[2];
   // profiling
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;
@@ -742,6 +746,11 @@ int32_t ppca_b200_ctx_destroy(ppca_b200_ctx *ctx) {
       if (ctx->ev_copied[b]) cudaEventDestroy(ctx->ev_copied[b]);
       if (ctx->ev_free[b]) cudaEventDestroy(ctx->ev_free[b]);
     }
+    for (int b = 0; b < 2; ++b) {
+      if (ctx->ev_done[b]) cudaEventDestroy(ctx->ev_done[b]);
+      if (ctx->ev_outfree[b]) cudaEventDestroy(ctx->ev_outfree[b]);
+    }
+    if (ctx->out_stream) cudaStreamDestroy(ctx->out_stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -1305,6 +1314,79 @@ int32_t ppca_b200_iterate_host(ppca_b200_ctx *ctx, const double *x, int64_t n, i
     ctx->stats.reserve((size_t)StatsLayout(d, k).len);
     em_stats_host_impl(ctx, x, n, d, weights, m, ctx->stats.p);
     em_finish_impl(ctx, d, k, C, mu, sigma, prior, ctx->stats.p, C_out, mu_out, sigma_out, llk_in, nullptr);
+  });
+}
+
+// ---- out-of-core inference: smooth / extrapolate / llks over samples that stay in host memory ------------
+int32_t ppca_b200_reconstruct_host(ppca_b200_ctx *ctx, const double *x, int64_t n, int32_t d, int32_t k,
+                                   const double *C, const double *mu, double sigma, int32_t extrapolate, double *out,
+                                   double *llks) {
+  return guarded([&] {
+    REQUIRE(ctx != nullptr, "null context");
+    REQUIRE(n >= 0 && d >= 1, "bad dataset shape %lld x %d", (long long)n, d);
+    REQUIRE(out != nullptr || llks != nullptr, "nothing to compute: both outputs are null");
+    if (n == 0) return;
+    REQUIRE(x != nullptr, "null data");
+    DeviceGuard g(ctx->device);
+    if (!ctx->copy_stream) {
+      CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+      for (int b = 0; b < 2; ++b) {
+        CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_copied[b], cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_free[b], cudaEventDisableTiming));
+      }
+    }
+    if (!ctx->out_stream) {
+      CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->out_stream, cudaStreamNonBlocking));
+      for (int b = 0; b < 2; ++b) {
+        CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_done[b], cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_outfree[b], cudaEventDisableTiming));
+      }
+    }
+    DevModel m = stage_model(ctx, d, k, C, mu, sigma);
+    const int64_t blk = pick_chunk(ctx, round_up(n, 256), m.s);
+    reserve_chunk_ws(ctx, blk, m.s);
+    const int64_t tail = n % blk;
+    if (n >= blk && (!ctx->s_store || ctx->s_store->n != blk || ctx->s_store->d != d)) ctx->s_store = make_store(ctx, blk, d);
+    if (tail && (!ctx->s_tail || ctx->s_tail->n != tail || ctx->s_tail->d != d)) ctx->s_tail = make_store(ctx, tail, d);
+    const int64_t brows = n < blk ? n : blk;
+    for (int b = 0; b < 2; ++b) {
+      ctx->s_raw[b].reserve((size_t)brows * d);
+      if (out) ctx->s_out[b].reserve((size_t)brows * d);
+      if (llks) ctx->s_llk[b].reserve((size_t)round_up(brows, 256));
+    }
+    CUDA_CHECK(cudaEventRecord(ctx->ev_free[0], ctx->stream));  // neither side stream may run ahead of queued work
+    CUDA_CHECK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_free[0], 0));
+    CUDA_CHECK(cudaStreamWaitEvent(ctx->out_stream, ctx->ev_free[0], 0));
+    const Launcher L = ctx->L();
+    int i = 0;
+    for (int64_t r0 = 0; r0 < n; r0 += blk, ++i) {
+      const int b = i & 1;
+      const int64_t rows = (n - r0) < blk ? (n - r0) : blk;
+      SampleStore &st = rows == blk ? *ctx->s_store : *ctx->s_tail;
+      // H2D of block i (copy stream) || kernels of block i-1 (compute stream) || D2H of block i-2 (out stream)
+      if (i >= 2) CUDA_CHECK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_free[b], 0));
+      CUDA_CHECK(cudaMemcpyAsync(ctx->s_raw[b].p, x + r0 * d, sizeof(double) * rows * d, cudaMemcpyHostToDevice,
+                                 ctx->copy_stream));
+      CUDA_CHECK(cudaEventRecord(ctx->ev_copied[b], ctx->copy_stream));
+      CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[b], 0));
+      launch_ingest(L, ctx->s_raw[b].p, rows, d, 0, st);
+      CUDA_CHECK(cudaEventRecord(ctx->ev_free[b], ctx->stream));
+      if (i >= 2) CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->ev_outfree[b], 0));  // outputs of block i-2 left
+      e_step_chunk(ctx, st, nullptr, 0, (int)rows, m, out ? 1 : 0, llks ? ctx->s_llk[b].p : nullptr, nullptr, nullptr);
+      if (out)
+        launch_reconstruct(L, st, 0, (int)rows, m, ctx->YZ.p, extrapolate, nullptr, 0, 0, ctx->s_out[b].p, d);
+      CUDA_CHECK(cudaEventRecord(ctx->ev_done[b], ctx->stream));
+      CUDA_CHECK(cudaStreamWaitEvent(ctx->out_stream, ctx->ev_done[b], 0));
+      if (out)
+        CUDA_CHECK(cudaMemcpyAsync(out + r0 * d, ctx->s_out[b].p, sizeof(double) * rows * d, cudaMemcpyDeviceToHost,
+                                   ctx->out_stream));
+      if (llks)
+        CUDA_CHECK(cudaMemcpyAsync(llks + r0, ctx->s_llk[b].p, sizeof(double) * rows, cudaMemcpyDeviceToHost,
+                                   ctx->out_stream));
+      CUDA_CHECK(cudaEventRecord(ctx->ev_outfree[b], ctx->out_stream));
+    }
+    CUDA_CHECK(cudaStreamSynchronize(ctx->out_stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
   });
 }
 

@@ -403,13 +403,31 @@ class PPCAModel:
 
     def llk(self, dataset: Dataset) -> float:
         self._check(dataset)
+        if isinstance(dataset, HostDataset):
+            return float(np.dot(self._host_pass(dataset, None, True)[1], dataset.weights())) if len(dataset) else 0.0
         out = C.c_double(0.0)
         nat.check(nat.lib().ppca_b200_llk(dataset._ctx.handle, dataset._h, self.state_size, nat.dptr(self._C),
                                           nat.dptr(self._mu), self._sigma, C.byref(out)))
         return out.value
 
+    def _host_pass(self, dataset: "HostDataset", extrapolate: Optional[bool], want_llks: bool):
+        """Streams a HostDataset through ppca_b200_reconstruct_host; returns (HostDataset | None, llks | None)."""
+        n, d = len(dataset), self.output_size
+        out = None
+        if extrapolate is not None:
+            out = HostDataset(np.empty((n, d)), None if dataset._w is None else dataset._w.copy(),
+                              pin=bool(dataset._pinned), ctx=dataset._ctx)
+        llks = np.empty(n) if want_llks else None
+        nat.check(nat.lib().ppca_b200_reconstruct_host(dataset._ctx.handle, nat.dptr(dataset._x), n, d, self.state_size,
+                                                       nat.dptr(self._C), nat.dptr(self._mu), self._sigma,
+                                                       int(bool(extrapolate)), nat.dptr(out._x) if out else None,
+                                                       nat.dptr(llks)))
+        return out, llks
+
     def llks(self, dataset: Dataset) -> np.ndarray:
         self._check(dataset)
+        if isinstance(dataset, HostDataset):
+            return self._host_pass(dataset, None, True)[1]
         out = np.empty(len(dataset))
         nat.check(nat.lib().ppca_b200_llks(dataset._ctx.handle, dataset._h, self.state_size, nat.dptr(self._C),
                                            nat.dptr(self._mu), self._sigma, nat.dptr(out)))
@@ -436,6 +454,8 @@ class PPCAModel:
 
     def _recon(self, dataset: Dataset, fn) -> Dataset:
         self._check(dataset)
+        if isinstance(dataset, HostDataset):  # host in, host out, streamed
+            return self._host_pass(dataset, fn is nat.lib().ppca_b200_extrapolate, False)[0]
         h = nat.c_ds_p()
         nat.check(fn(dataset._ctx.handle, dataset._h, self.state_size, nat.dptr(self._C), nat.dptr(self._mu),
                      self._sigma, C.byref(h)))

@@ -367,6 +367,52 @@ def test_trainer_on_host_dataset(pk):
     assert rel_err(b.transform, a.transform) < 1e-10 and abs(b.isotropic_noise - a.isotropic_noise) < 1e-10
 
 
+@pytest.mark.parametrize("n,d,k,chunk,pin", [(5000, 90, 12, 1024, True), (3000, 130, 48, 0, True), (2048, 33, 7, 512, False)])
+def test_host_streamed_inference_equals_resident(pk, orc, n, d, k, chunk, pin):
+    """ppca_b200_reconstruct_host (smooth / extrapolate / llks on a HostDataset) == the resident entry points."""
+    X, C0, mu0, s0 = _case(n, d, k, 0.3, seed=41)
+    X[7, :] = np.nan
+    w = np.random.default_rng(5).random(n) + 0.5
+    ctx = pk.Context(0)
+    try:
+        ctx.set_chunk(chunk)
+        model = pk.PPCAModel(0.3, C0, mu0)
+        res, host = pk.Dataset(X, w, _ctx=ctx), pk.HostDataset(X, w, pin=pin, ctx=ctx)
+        for _ in range(2):
+            ex = model.extrapolate(host)
+            assert isinstance(ex, pk.HostDataset) and np.array_equal(ex.weights(), w)
+            got, want = ex.numpy(), model.extrapolate(res).numpy()
+            fin = np.isfinite(X)
+            assert np.array_equal(got[fin], X[fin])                       # observed slots: bit copies
+            assert rel_err(got, want) < 1e-13
+            assert rel_err(model.smooth(host).numpy(), model.smooth(res).numpy()) < 1e-13
+            assert rel_err(model.llks(host), model.llks(res)) < 1e-13
+            assert abs(model.llk(host) - model.llk(res)) < 1e-12 * abs(model.llk(res))
+        assert rel_err(model.extrapolate(host).numpy(), orc.extrapolate(X, C0, mu0, 0.3)) < 1e-9
+    finally:
+        ctx.close()
+
+
+def test_dataframe_adapter_roundtrip_on_device(pk):
+    pd = pytest.importorskip("pandas")
+    rng = np.random.default_rng(0)
+    rows = [{"unit": u, "t": t, "sensor": f"s{j}", "value": float(np.sin(0.1 * t * (j + 1)) + 0.01 * rng.standard_normal())}
+            for u in range(6) for t in range(40) for j in range(5) if rng.random() > 0.25]
+    df = pd.DataFrame(rows)
+    ad = pk.DataFrameAdapter.from_pandas(df, keys=["unit", "t"], dimensions=["sensor"], metric="value")
+    assert isinstance(ad.dataset, pk.Dataset) and ad.dataset.output_size() == 5
+    model = pk.PPCATrainer(ad.dataset).train(state_size=2, n_iters=8, quiet=True)
+    long = ad.convert_datasets({"value_hat": model.extrapolate(ad.dataset), "value_in": ad.dataset})
+    assert len(long) == len(ad.sample_idx) * 5 and not long["value_hat"].isna().any()
+    merged = long.merge(df, on=["unit", "t", "sensor"], how="left")
+    obs = ~merged["value"].isna()
+    assert np.array_equal(merged.loc[obs, "value_hat"].to_numpy(), merged.loc[obs, "value"].to_numpy())
+    assert merged.loc[~obs, "value_in"].isna().all()
+    host = pk.DataFrameAdapter.from_pandas(df, keys=["unit", "t"], dimensions=["sensor"], metric="value",
+                                           dataset_factory=pk.HostDataset)
+    assert np.allclose(host.dataset.numpy(), ad.dataset.numpy(), equal_nan=True)
+
+
 # ---- full-size properties (BASELINE configs[1]: N=1M, d=200, k=16, 20% missing) ---------------------------
 def test_full_size_properties(pk):
     n, d, k = 1_000_000, 200, 16

@@ -205,3 +205,77 @@ def test_sharded_em_world_size_2_gloo(tmp_path):
     assert rel_err(got["C"], C) < 1e-9 and rel_err(got["mu"], mu) < 1e-9
     assert abs(float(got["s"]) - s) < 1e-9 * s
     assert rel_err(got["llk"], np.array(llks)) < 1e-10
+
+
+# ---- DataFrameAdapter (python/ppca_rs/__init__.py:121-433): host logic, no GPU (dataset_factory injected) ----------
+class _FakeDataset:
+    def __init__(self, x):
+        self.x = np.array(x, dtype=np.float64)
+
+    def numpy(self):
+        return self.x
+
+
+def _adapter_frame(seed=0, n_keys=40, n_dims=7):
+    import pandas as pd
+    rng = np.random.default_rng(seed)
+    rows = []
+    for day in range(n_keys // 4):
+        for shop in "abcd":
+            for dim in range(n_dims):
+                if rng.random() < 0.3:
+                    continue                                   # a missing combination -> NaN in the dataset
+                rows.append({"day": day, "shop": shop, "product": f"p{dim % 3}", "size": dim // 3,
+                             "sales": float(rng.standard_normal())})
+    df = pd.DataFrame(rows)
+    return df.sample(frac=1.0, random_state=1).reset_index(drop=True)   # row order must not matter
+
+
+def test_dataframe_adapter_matches_reference_semantics():
+    pytest.importorskip("pandas")
+    from ppca_rs_b200.adapter import DataFrameAdapter, DataFrameAdapterDescription
+    df = _adapter_frame()
+    ad = DataFrameAdapter.from_pandas(df, keys=["day", "shop"], dimensions=["product", "size"], metric="sales",
+                                      dataset_factory=_FakeDataset)
+    # the reference's construction, restated: sorted distinct dimension tuples, groupby(keys) order, scatter per group
+    dims = sorted(set(zip(df["product"], df["size"])))
+    assert [tuple(r) for r in ad.dimension_idx[["product", "size"]].itertuples(index=False)] == dims
+    assert list(ad.dimension_idx["__dim_idx"]) == list(range(len(dims)))
+    groups = sorted(set(zip(df["day"], df["shop"])))
+    assert [tuple(r) for r in ad.sample_idx[["day", "shop"]].itertuples(index=False)] == groups
+    want = np.full((len(groups), len(dims)), np.nan)
+    for _, row in df.iterrows():
+        want[groups.index((row["day"], row["shop"])), dims.index((row["product"], row["size"]))] = row["sales"]
+    got = ad.dataset.numpy()
+    assert got.shape == want.shape and np.array_equal(np.isnan(got), np.isnan(want))
+    assert np.array_equal(got[~np.isnan(got)], want[~np.isnan(want)])
+
+    # description round trip (to_json / from_json) re-adapts new data onto the SAME dimension numbering
+    desc = DataFrameAdapterDescription.from_json(ad.description().to_json())
+    assert desc.dimension_idx == [list(t) for t in dims] and desc.keys == ["day", "shop"] and desc.metric == "sales"
+    sub = df[df["day"] < 3]
+    ad2 = desc.adapt_pandas(sub, dataset_factory=_FakeDataset)
+    assert ad2.dimensions == ["product", "size"] and ad2.dataset.numpy().shape[1] == len(dims)
+    assert np.allclose(ad2.dataset.numpy(), want[: len(set(zip(sub["day"], sub["shop"])))], equal_nan=True)
+
+    # back to the long format: every (sample, dimension) pair, keys and dimensions attached
+    long = ad.convert_datasets({"sales_hat": _FakeDataset(np.nan_to_num(want, nan=-1.0)), "raw": ad.dataset})
+    assert list(long.columns) == ["day", "shop", "product", "size", "sales_hat", "raw"]
+    assert len(long) == want.size
+    merged = long.merge(df, on=["day", "shop", "product", "size"], how="left")
+    obs = ~merged["sales"].isna()
+    assert np.allclose(merged.loc[obs, "sales_hat"], merged.loc[obs, "sales"])
+    assert np.all(merged.loc[~obs, "sales_hat"] == -1.0) and merged.loc[~obs, "raw"].isna().all()
+    one = ad.convert_dataset(ad.dataset, column_name="x")
+    assert list(one.columns) == ["day", "shop", "product", "size", "x"]
+
+
+def test_dataframe_adapter_unknown_dimensions_are_dropped():
+    pytest.importorskip("pandas")
+    import pandas as pd
+    from ppca_rs_b200.adapter import DataFrameAdapter
+    df = pd.DataFrame({"k": [0, 0, 1, 1], "dim": ["a", "b", "a", "zzz"], "v": [1.0, 2.0, 3.0, 4.0]})
+    idx = pd.DataFrame({"__dim_idx": [0, 1], "dim": ["a", "b"]})
+    ad = DataFrameAdapter.from_pandas(df, keys=["k"], dimension_idx=idx, metric="v", dataset_factory=_FakeDataset)
+    assert ad.dimensions == ["dim"]
+    assert np.allclose(ad.dataset.numpy(), [[1.0, 2.0], [3.0, np.nan]], equal_nan=True)
