@@ -1,0 +1,102 @@
+#!/usr/bin/env python
+"""Regenerates profiles/r01_summary.md from the committed bench JSON lines (profiles/r01_bench_*.json)."""
+import json
+import os
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+P = os.path.join(ROOT, "profiles")
+
+
+def L(name):
+    with open(os.path.join(P, name)) as f:
+        return json.loads(f.read().strip().splitlines()[-1])
+
+
+def famrow(j):
+    f = j["roofline"]["families"]
+    return " | ".join(f"{f[k]['ms_per_step']:.2f}" for k in ("gram", "proj", "solve", "slice", "moment", "cross_resid", "finish"))
+
+
+def roofrow(j):
+    f = j["roofline"]["families"]
+    out = []
+    for k in ("gram", "moment", "proj", "solve", "slice", "cross_resid"):
+        e = f[k]
+        out.append(f"{100 * e['frac']:.0f} % {e['bound']}" if "frac" in e else "—")
+    return " | ".join(out)
+
+
+def main():
+    c2, c3s, c3, c4, ref, c5 = (L("r01_bench_c2.json"), L("r01_bench_c3s.json"), L("r01_bench_c3_4Mrows.json"),
+                                L("r01_bench_c4s.json"), L("r01_bench_c2_reference_arm.json"), L("r01_bench_c5.json"))
+    r = lambda j: j["roofline"]
+    txt = f"""# Round 1 — measured results (one B200, sm_100a, SM clock 1965 MHz, no throttle reasons)
+
+All numbers come from `bench.py` on a fresh `gpurun` box; the JSON lines are committed next to this file
+(`r01_bench_*.json`).  ncu evidence: `r01_c2_step_ncu_full_summary.txt`, `r01_c3s_step_ncu_full_summary.txt`
+(`--set full`, one chunk), `r01_launches_c2_v4.csv` (launch list of the bench command), `r01_traffic.json` (DRAM bytes
+per launch), `r01_tbitgemm_*` / `r01_bitgemm_*` (contraction kernels), `r01_solve_blk_ncu.txt` (the blocked solve
+experiment); peaks: `r01_fp64_peak.json` (DMMA 37.1 TFLOP/s = DFMA rate), `r01_utc_i8_peak.json` (tcgen05 int8
+4.3 POP/s), `r01_imma_peak.json`, `MEASURED_PEAKS.json` (HBM 6551 GB/s).
+
+## Headline (BASELINE metric: EM samples·iterations/s; one iteration = llk of the current model + `iterate`)
+
+| workload | rows/GPU | ms/step | value (dataset resident) | e2e (host samples cross the bus every step) | CPU arm |
+|---|---|---|---|---|---|
+| c2: d=200 k=16 20 % missing | 1 000 000 | {c2['ms_per_step']:.2f} | {c2['value']/1e6:.1f} M/s | {c2['e2e']['value']/1e6:.1f} M/s at {c2['e2e']['h2d_gb_per_s']:.1f} GB/s H2D | {ref['value']/1e3:.0f} K/s ({ref['cpu_baseline']['cores']} cores, oracle port) |
+| c3 shard: d=2048 k=64 30 % missing | 4 000 000 (65.5 GB) | {c3['ms_per_step']:.0f} | {c3['value']/1e6:.2f} M/s | {c3['e2e']['value']/1e6:.2f} M/s at {c3['e2e']['h2d_gb_per_s']:.1f} GB/s | — |
+| c3 shard, small | 500 000 | {c3s['ms_per_step']:.1f} | {c3s['value']/1e6:.2f} M/s | {c3s['e2e']['value']/1e6:.2f} M/s | — |
+| c4 small: PPCAMix M=4 d=512 k=32 | 200 000 | {c4['ms_per_step']:.1f} | {c4['value']/1e6:.2f} M/s | {c4['e2e']['value']/1e6:.2f} M/s | — |
+| c5 inference (extrapolate + llks) d=1024 k=48 | 2 000 000 | {c5['ms_per_step']:.0f} | {c5['value']/1e6:.2f} M samples/s | {c5['e2e']['value']/1e6:.2f} M samples/s (host in, host out) | — |
+
+c2 resident is {c2['value']/ref['value']:.0f}x the CPU arm and end to end {c2['e2e']['value']/ref['value']:.0f}x; the end-to-end step is PCIe-bound (the
+kernels, {c2['ms_per_step']:.1f} ms, hide behind the 1.6 GB H2D copy, 29.6 ms).  2 GPUs (`gpurun --gpus 2`, torchrun, NCCL): c2 e2e 67.6 M/s.
+
+## Kernel families, ms per step (CUDA events on the launching stream, inside the timed region)
+
+| workload | gram (E) | proj | solve | slice | moment (M) | cross+resid | finish |
+|---|---|---|---|---|---|---|---|
+| c2 | {famrow(c2)} |
+| c3 (4M rows) | {famrow(c3)} |
+| c3s | {famrow(c3s)} |
+| c4s | {famrow(c4)} |
+
+Fraction of the nearer roof per family (tensor = tcgen05 int8 peak for gram/moment, FP64 37.1 TFLOP/s for the others;
+hbm = 6551 GB/s):
+
+| workload | gram | moment | proj | solve | slice | cross+resid |
+|---|---|---|---|---|---|---|
+| c2 | {roofrow(c2)} |
+| c3 (4M rows) | {roofrow(c3)} |
+| c4s | {roofrow(c4)} |
+
+## Roofline of the masked-Gram contraction (`tbitgemm_atm_kernel<6>`, tcgen05.mma.kind::i8, E- and M-step launches)
+
+| workload | int8 TOP/s achieved | of measured tcgen05 int8 peak | FP64-equivalent TFLOP/s | vs FP64 DMMA peak (37.1) |
+|---|---|---|---|---|
+| c2 | {r(c2)['achieved']:.0f} | {100*r(c2)['frac']:.1f} % | {r(c2)['fp64_equivalent_tflops']:.0f} | {r(c2)['fp64_equivalent_frac']:.2f}x |
+| c3 (4M rows) | {r(c3)['achieved']:.0f} | {100*r(c3)['frac']:.1f} % | {r(c3)['fp64_equivalent_tflops']:.0f} | {r(c3)['fp64_equivalent_frac']:.2f}x |
+| c4s | {r(c4)['achieved']:.0f} | {100*r(c4)['frac']:.1f} % | {r(c4)['fp64_equivalent_tflops']:.0f} | {r(c4)['fp64_equivalent_frac']:.2f}x |
+
+c2 (k=16, d=200) is not tensor-bound: a tile is two K steps and 136 output columns, so the contraction is bounded by
+the FP64 recombination epilogue and the G write (DESIGN.md §3.1); the tensor fraction is meaningful at c3 (north star:
+>= 50 % of the FP64 tensor roofline on the masked-Gram contraction — the FP64 DMMA path `bitgemm_kernel` measures 84 %
+DMMA-pipe active, `r01_bitgemm_c3s_ncu_details.txt`; the default int8-sliced path does {r(c3)['fp64_equivalent_frac']:.1f}x that roofline in
+FP64-equivalent work).  Whole-step FP64-equivalent throughput (SURVEY §8d F_iter) against the DMMA peak:
+c2 {100*r(c2)['whole_step_fp64_equivalent_frac']:.0f} %, c3 {100*r(c3)['whole_step_fp64_equivalent_frac']:.0f} %, c4s {100*r(c4)['whole_step_fp64_equivalent_frac']:.0f} %.
+
+## What bounds the step now (next round)
+
+* Per-sample solve: 30 % (c2) to 36 % (c3) of the step, ~25 % of the FP64 peak; latency-bound chain of dependent
+  reciprocals per pivot with the register file limiting the samples in flight (4 per SM at k=64).
+* Cross-moment / residual pass: FP64 DMMA-bound at k >= 16 (4dk flop per 8d bytes), 31-53 % of the DMMA peak.
+* Contractions at the c3 shape: 38 % (E) / 51 % (M) of the int8 peak; stage round-trip latency (4 stages) and the
+  mask expansion issue rate bound the main loop.
+"""
+    with open(os.path.join(P, "r01_summary.md"), "w") as f:
+        f.write(txt)
+    print(txt)
+
+
+if __name__ == "__main__":
+    main()
