@@ -186,16 +186,16 @@ def measured_hbm_peak():
         return 6650.0, "B200_PROFILING.md fallback (MEASURED_PEAKS.json absent)"
 
 
-def ctx_chunk(ctx, n, d, k):
+def ctx_chunk(ctx, n, d, k, slices=6):
     """Samples per chunk the engine picks automatically (mirrors pick_chunk in csrc/api.cu)."""
-    wave = 148 * 128
-    chunk = wave * 4
     kk = k * (k + 1) // 2
-    per_row = ((kk + 7) // 8 * 8 + 2 * ((k + 7) // 8 * 8) + 4) * 8
-    while chunk > wave and chunk * per_row > (8 << 30):
-        chunk -= wave
+    kkp, kp = (kk + 7) // 8 * 8, (k + 7) // 8 * 8
+    per_row = (kkp + 2 * kp + 4) * 8 + kkp * slices
+    cap = max(148 * 128, min((8 << 30) // per_row, 2 << 20))
     n_pad = (n + 255) // 256 * 256
-    return min(chunk, n_pad)
+    nchunks = -(-n_pad // cap)
+    chunk = -(-n_pad // nchunks)
+    return min((chunk + 255) // 256 * 256, n_pad)
 
 
 def init_params(d, k, seed):

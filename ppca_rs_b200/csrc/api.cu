@@ -184,18 +184,34 @@ ppca_b200_dataset *make_dataset(ppca_b200_ctx *ctx, std::shared_ptr<SampleStore>
   return ds.release();
 }
 
+// Samples per E/M-step chunk.  Measured on B200 (profiles/r01_summary.md, chunk sweep): bigger is better all the way to
+// one chunk per dataset (c2: 5.47 ms at 4 waves of 128-row tiles, 4.17 ms with the whole 1 M rows in one chunk) — the
+// per-launch tails and the split-K/slab reductions outweigh any L2 residency of a small chunk.  So: as many rows as
+// 8 GiB of chunk workspace holds, at most 2 M (grid.y limits of the 64-row reconstruction tiles; int32-exact digit
+// sums need K < 2^24 rows per split-K slab), split evenly over the dataset.
 int64_t pick_chunk(ppca_b200_ctx *ctx, int64_t n_pad, const Shape &s) {
   int64_t chunk = ctx->chunk;
   if (chunk <= 0) {
+    const int64_t per_row = (int64_t)(s.kkp + 2 * s.kp + 4) * 8 + (int64_t)s.kkp * ctx->slices;
+    int64_t cap = ((int64_t)8 << 30) / per_row;
+    if (cap > ((int64_t)2 << 20)) cap = (int64_t)2 << 20;
     const int64_t wave = (int64_t)ctx->sms * 128;  // one full wave of 128-row tiles
-    chunk = wave * 4;
-    // keep the chunk workspace under ~8 GiB
-    const int64_t per_row = (int64_t)(s.kkp + 2 * s.kp + 4) * 8;
-    while (chunk > wave && chunk * per_row > ((int64_t)8 << 30)) chunk -= wave;
+    if (cap < wave) cap = wave;
+    const int64_t nchunks = (n_pad + cap - 1) / cap;
+    chunk = (n_pad + nchunks - 1) / nchunks;
   }
   chunk = round_up(chunk, 256);
   if (chunk > n_pad) chunk = n_pad;
   return chunk;
+}
+
+// Rows per uploaded block of the out-of-core paths: small enough that the first H2D and the last block's kernels
+// (the parts that cannot overlap) are a small fraction of the pass, large enough to keep the kernels efficient.
+int64_t pick_stream_block(ppca_b200_ctx *ctx, int64_t n_pad, const Shape &s) {
+  int64_t blk = pick_chunk(ctx, n_pad, s);
+  const int64_t four_waves = (int64_t)ctx->sms * 128 * 4;
+  if (ctx->chunk <= 0 && blk > four_waves) blk = four_waves;
+  return blk;
 }
 
 // uploads (C, mu) and builds the padded model + Ksym table on the device
@@ -336,11 +352,11 @@ struct EmPlan {
   int slabs = 1;
 };
 
-EmPlan em_begin(ppca_b200_ctx *ctx, int64_t n_pad, const DevModel &m, double *stats_dev) {
+EmPlan em_begin(ppca_b200_ctx *ctx, int64_t chunk, const DevModel &m, double *stats_dev) {
   const StatsLayout lay(m.s.d, m.s.k);
   CUDA_CHECK(cudaMemsetAsync(stats_dev, 0, sizeof(double) * lay.len, ctx->stream));
   EmPlan p;
-  p.chunk = pick_chunk(ctx, n_pad, m.s);
+  p.chunk = chunk;
   reserve_chunk_ws(ctx, p.chunk, m.s);
   const int kb_chunk = (int)(p.chunk / 32);
   p.splitk = ctx->gemm_mode == 2   ? tbitgemm_pick_splitk(m.s.d, m.s.kkp, kb_chunk / 4, ctx->sms)
@@ -465,7 +481,7 @@ void em_stats_impl(ppca_b200_ctx *ctx, const SampleStore &st, const double *w, c
     CUDA_CHECK(cudaMemsetAsync(stats_dev, 0, sizeof(double) * StatsLayout(m.s.d, m.s.k).len, ctx->stream));
     return;
   }
-  const EmPlan p = em_begin(ctx, st.n_pad, m, stats_dev);
+  const EmPlan p = em_begin(ctx, pick_chunk(ctx, st.n_pad, m.s), m, stats_dev);
   for (int64_t row0 = 0; row0 < st.n; row0 += p.chunk) {
     const int rows = (int)((st.n - row0) < p.chunk ? (st.n - row0) : p.chunk);
     em_chunk(ctx, st, w, row0, rows, m, stats_dev, p);
@@ -1233,7 +1249,7 @@ void em_stats_host_impl(ppca_b200_ctx *ctx, const double *x, int64_t n, int d, c
       CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_free[b], cudaEventDisableTiming));
     }
   }
-  const EmPlan p = em_begin(ctx, round_up(n, 256), m, stats_dev);
+  const EmPlan p = em_begin(ctx, pick_stream_block(ctx, round_up(n, 256), m.s), m, stats_dev);
   const int64_t blk = p.chunk;  // one uploaded block = one E/M-step chunk
   const int64_t tail = n % blk;
   if (n >= blk && (!ctx->s_store || ctx->s_store->n != blk || ctx->s_store->d != d)) ctx->s_store = make_store(ctx, blk, d);
@@ -1343,7 +1359,7 @@ int32_t ppca_b200_reconstruct_host(ppca_b200_ctx *ctx, const double *x, int64_t 
       }
     }
     DevModel m = stage_model(ctx, d, k, C, mu, sigma);
-    const int64_t blk = pick_chunk(ctx, round_up(n, 256), m.s);
+    const int64_t blk = pick_stream_block(ctx, round_up(n, 256), m.s);
     reserve_chunk_ws(ctx, blk, m.s);
     const int64_t tail = n % blk;
     if (n >= blk && (!ctx->s_store || ctx->s_store->n != blk || ctx->s_store->d != d)) ctx->s_store = make_store(ctx, blk, d);

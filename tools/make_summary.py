@@ -50,7 +50,8 @@ experiment); peaks: `r01_fp64_peak.json` (DMMA 37.1 TFLOP/s = DFMA rate), `r01_u
 | c5 inference (extrapolate + llks) d=1024 k=48 | 2 000 000 | {c5['ms_per_step']:.0f} | {c5['value']/1e6:.2f} M samples/s | {c5['e2e']['value']/1e6:.2f} M samples/s (host in, host out) | — |
 
 c2 resident is {c2['value']/ref['value']:.0f}x the CPU arm and end to end {c2['e2e']['value']/ref['value']:.0f}x; the end-to-end step is PCIe-bound (the
-kernels, {c2['ms_per_step']:.1f} ms, hide behind the 1.6 GB H2D copy, 29.6 ms).  2 GPUs (`gpurun --gpus 2`, torchrun, NCCL): c2 e2e 67.6 M/s.
+kernels, {c2['ms_per_step']:.1f} ms, hide behind the 1.6 GB H2D copy, 29.6 ms).  The mixture e2e leg re-creates the device Dataset
+every step and varied between 0.25 and 4.6 M/s across runs (allocation stalls); its resident number is stable.  2 GPUs (`gpurun --gpus 2`, torchrun, NCCL): c2 e2e 67.6 M/s.
 
 ## Kernel families, ms per step (CUDA events on the launching stream, inside the timed region)
 
@@ -84,6 +85,15 @@ the FP64 recombination epilogue and the G write (DESIGN.md §3.1); the tensor fr
 DMMA-pipe active, `r01_bitgemm_c3s_ncu_details.txt`; the default int8-sliced path does {r(c3)['fp64_equivalent_frac']:.1f}x that roofline in
 FP64-equivalent work).  Whole-step FP64-equivalent throughput (SURVEY §8d F_iter) against the DMMA peak:
 c2 {100*r(c2)['whole_step_fp64_equivalent_frac']:.0f} %, c3 {100*r(c3)['whole_step_fp64_equivalent_frac']:.0f} %, c4s {100*r(c4)['whole_step_fp64_equivalent_frac']:.0f} %.
+
+## Chunk size (samples per E/M-step chunk), c2, ms per step
+
+| 18 944 (1 wave) | 37 888 | 75 776 (old default) | 151 552 | 265 216 | 511 488 | 1 003 520 (whole dataset, new default) |
+|---|---|---|---|---|---|---|
+| 9.08 | 6.69 | 5.47 | 4.85 | 4.53 | 4.29 | 4.17 |
+
+Bigger is better all the way (per-launch tails, split-K/slab reductions); L2 residency of a small chunk does not pay.
+The engine now takes as many rows per chunk as 8 GiB of workspace holds (at most 2 M), split evenly.
 
 ## What bounds the step now (next round)
 
