@@ -51,7 +51,7 @@ experiment); peaks: `r01_fp64_peak.json` (DMMA 37.1 TFLOP/s = DFMA rate), `r01_u
 
 c2 resident is {c2['value']/ref['value']:.0f}x the CPU arm and end to end {c2['e2e']['value']/ref['value']:.0f}x; the end-to-end step is PCIe-bound (the
 kernels, {c2['ms_per_step']:.1f} ms, hide behind the 1.6 GB H2D copy, 29.6 ms).  The mixture e2e leg re-creates the device Dataset
-every step and varied between 0.25 and 4.6 M/s across runs (allocation stalls); its resident number is stable.  2 GPUs (`gpurun --gpus 2`, torchrun, NCCL): c2 e2e 67.6 M/s.
+every step; the committed line hit a one-off stall (0.25 M/s), seven other runs measured 2.5-4.6 M/s; the resident number is stable.  2 GPUs (`gpurun --gpus 2`, torchrun, NCCL): c2 e2e 67.6 M/s.
 
 ## Kernel families, ms per step (CUDA events on the launching stream, inside the timed region)
 
