@@ -101,6 +101,11 @@ int32_t ppca_b200_dataset_from_host(ppca_b200_ctx *ctx, const double *x, int64_t
 int32_t ppca_b200_dataset_synthetic(ppca_b200_ctx *ctx, int64_t n, int32_t d, int32_t k_true,
                                     double sigma_true, double mask_prob, int32_t n_components,
                                     uint64_t seed, ppca_b200_dataset **out);
+/* PPCAModel::sample (ppca_model.rs:164-191): n draws x = C xi + mu + sigma eps from the given model, each entry masked
+ * with probability mask_prob, generated on the device with a counter-based RNG keyed by `seed` (the reference is
+ * unseeded: only the distribution can agree). */
+int32_t ppca_b200_model_sample(ppca_b200_ctx *ctx, int64_t n, int32_t d, int32_t k, const double *C, const double *mu,
+                               double sigma, double mask_prob, uint64_t seed, ppca_b200_dataset **out);
 /* Dataset::with_weights (dataset.rs:171-176): shares the samples, new weights (host array of len n). */
 int32_t ppca_b200_dataset_with_weights(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds,
                                        const double *weights, ppca_b200_dataset **out);

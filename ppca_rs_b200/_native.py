@@ -61,6 +61,10 @@ _PROTOTYPES = {
         C.c_int32,
         [c_ctx_p, C.c_int64, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_uint64, C.POINTER(c_ds_p)],
     ),
+    "ppca_b200_model_sample": (
+        C.c_int32,
+        [c_ctx_p, C.c_int64, C.c_int32, C.c_int32, c_dp, c_dp, C.c_double, C.c_double, C.c_uint64, C.POINTER(c_ds_p)],
+    ),
     "ppca_b200_dataset_with_weights": (C.c_int32, [c_ctx_p, c_ds_p, c_dp, C.POINTER(c_ds_p)]),
     "ppca_b200_dataset_len": (C.c_int32, [c_ds_p, C.POINTER(C.c_int64)]),
     "ppca_b200_dataset_output_size": (C.c_int32, [c_ds_p, c_ip]),

@@ -930,6 +930,33 @@ int32_t ppca_b200_dataset_synthetic(ppca_b200_ctx *ctx, int64_t n, int32_t d, in
   });
 }
 
+int32_t ppca_b200_model_sample(ppca_b200_ctx *ctx, int64_t n, int32_t d, int32_t k, const double *C, const double *mu,
+                                double sigma, double mask_prob, uint64_t seed, ppca_b200_dataset **out) {
+  return guarded([&] {
+    REQUIRE(ctx != nullptr && out != nullptr && C != nullptr && mu != nullptr, "null argument");
+    REQUIRE(n >= 0 && d >= 1 && k >= 1, "bad sample shape");
+    REQUIRE(mask_prob >= 0.0 && mask_prob <= 1.0, "invalid mask probability");  // ppca_model.rs:165
+    REQUIRE(sigma >= 0.0 && std::isfinite(sigma), "isotropic_noise must be finite and non-negative");
+    DeviceGuard g(ctx->device);
+    auto st = make_store(ctx, n, d);
+    if (n > 0) {
+      ctx->Cdense.reserve((size_t)d * k);
+      ctx->mudense.reserve((size_t)d);
+      double *stage = ctx->pin((size_t)d * k + d);
+      CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+      memcpy(stage, C, sizeof(double) * d * k);
+      memcpy(stage + (size_t)d * k, mu, sizeof(double) * d);
+      CUDA_CHECK(cudaMemcpyAsync(ctx->Cdense.p, stage, sizeof(double) * d * k, cudaMemcpyHostToDevice, ctx->stream));
+      CUDA_CHECK(cudaMemcpyAsync(ctx->mudense.p, stage + (size_t)d * k, sizeof(double) * d, cudaMemcpyHostToDevice,
+                                 ctx->stream));
+      launch_model_sample(ctx->L(), *st, k, ctx->Cdense.p, ctx->mudense.p, sigma, mask_prob, seed);
+      launch_transpose_mask(ctx->L(), *st);
+    }
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    *out = make_dataset(ctx, st, nullptr);
+  });
+}
+
 int32_t ppca_b200_dataset_with_weights(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, const double *weights,
                                        ppca_b200_dataset **out) {
   return guarded([&] {

@@ -153,6 +153,8 @@ void launch_export(const Launcher &L, const SampleStore &st, int64_t row0, int64
 void launch_empty_dims(const Launcher &L, const SampleStore &st, uint8_t *out_dev);
 void launch_synthetic(const Launcher &L, SampleStore &st, int k_true, double sigma_true, double mask_prob,
                       int n_components, uint64_t seed);
+void launch_model_sample(const Launcher &L, SampleStore &st, int k, const double *C_dev, const double *mu_dev,
+                         double sigma, double mask_prob, uint64_t seed);
 void launch_copy_rows(const Launcher &L, const SampleStore &src, int64_t src_row0, int64_t nrows, SampleStore &dst,
                       int64_t dst_row0);
 

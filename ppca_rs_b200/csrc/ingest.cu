@@ -212,4 +212,18 @@ void launch_synthetic(const Launcher &L, SampleStore &st, int k_true, double sig
   CUDA_CHECK(cudaStreamSynchronize(L.stream));  // Ct / mut are freed on return
 }
 
+
+// PPCAModel::sample (ppca_model.rs:164-191) with a caller-supplied model: x = C xi + mu + sigma eps, masked with
+// probability mask_prob; C_dev is the dense d x k transform, mu_dev the mean (both on the device).
+void launch_model_sample(const Launcher &L, SampleStore &st, int k, const double *C_dev, const double *mu_dev,
+                         double sigma, double mask_prob, uint64_t seed) {
+  const int threads = 256;
+  const int64_t blocks = (st.n * 32 + threads - 1) / threads;
+  const size_t smem = sizeof(double) * (threads / 32) * k;
+  synth_kernel<<<(unsigned)blocks, threads, smem, L.stream>>>(st.n, st.d, k, 1, sigma, mask_prob, seed, C_dev, mu_dev,
+                                                              st.X.p, st.ldx, st.mask.p, st.dw, st.dn.p);
+  CUDA_CHECK(cudaGetLastError());
+  ++*L.launch_counter;
+}
+
 }  // namespace ppca

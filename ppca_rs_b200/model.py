@@ -433,15 +433,21 @@ class PPCAModel:
                                            nat.dptr(self._mu), self._sigma, nat.dptr(out)))
         return out
 
-    def sample(self, dataset_size: int, mask_prob: float) -> Dataset:
-        """ppca_model.rs:164-191 (unseeded, like the reference)."""
+    def sample(self, dataset_size: int, mask_prob: float, seed: Optional[int] = None) -> Dataset:
+        """ppca_model.rs:164-191, generated on the device (counter-based RNG).  Unseeded like the reference unless
+        `seed` is given (extension)."""
         if not 0.0 <= mask_prob <= 1.0:
             raise ValueError("invalid mask probability")
-        rng = np.random.default_rng()
-        n, d, k = int(dataset_size), self.output_size, self.state_size
-        x = rng.standard_normal((n, k)) @ self._C.T + self._mu + self._sigma * rng.standard_normal((n, d))
-        x[rng.random((n, d)) < mask_prob] = np.nan
-        return Dataset(x)
+        if self.state_size < 1:
+            raise ValueError("state_size 0 is not supported by the B200 engine")
+        if seed is None:
+            seed = int(np.random.default_rng().integers(0, 2 ** 63))
+        ctx = nat.get_context()
+        h = nat.c_ds_p()
+        nat.check(nat.lib().ppca_b200_model_sample(ctx.handle, int(dataset_size), self.output_size, self.state_size,
+                                                   nat.dptr(self._C), nat.dptr(self._mu), self._sigma, float(mask_prob),
+                                                   int(seed), C.byref(h)))
+        return Dataset._wrap(h, ctx)
 
     def infer(self, dataset: Dataset) -> "InferredMasked":
         self._check(dataset)

@@ -413,6 +413,31 @@ def test_dataframe_adapter_roundtrip_on_device(pk):
     assert np.allclose(host.dataset.numpy(), ad.dataset.numpy(), equal_nan=True)
 
 
+def test_model_sample_on_device_has_the_model_distribution(pk):
+    """PPCAModel.sample (ppca_model.rs:164-191): x ~ N(mu, C C^T + sigma^2 I), entries masked i.i.d. with prob p.
+    The reference is unseeded, so parity is distributional; a given seed reproduces."""
+    rng = np.random.default_rng(3)
+    d, k, n, p = 12, 3, 400_000, 0.3
+    C0, mu0, s0 = rng.standard_normal((d, k)), rng.standard_normal(d), 0.5
+    model = pk.PPCAModel(s0, C0, mu0)
+    a = model.sample(n, p, seed=11).numpy()
+    assert a.shape == (n, d)
+    fin = np.isfinite(a)
+    assert abs(fin.mean() - (1 - p)) < 5e-3
+    cov_true = C0 @ C0.T + s0 ** 2 * np.eye(d)
+    mean = np.nanmean(a, axis=0)
+    assert np.max(np.abs(mean - mu0)) < 6 * np.sqrt(np.max(np.diag(cov_true)) / (n * (1 - p)))
+    xc = np.where(fin, a - mu0, 0.0)
+    pair = fin.astype(np.float64).T @ fin.astype(np.float64)
+    cov = (xc.T @ xc) / pair                              # pairwise-complete covariance
+    assert np.max(np.abs(cov - cov_true)) < 0.05 * np.max(np.abs(cov_true))
+    assert np.array_equal(model.sample(1000, p, seed=11).numpy(), a[:1000], equal_nan=True)   # counter-based RNG
+    assert not np.array_equal(model.sample(1000, p, seed=12).numpy(), a[:1000], equal_nan=True)
+    assert len(model.sample(0, p)) == 0
+    fitted = pk.PPCATrainer(model.sample(50_000, 0.2, seed=5)).train(state_size=k, n_iters=30, quiet=True)
+    assert abs(fitted.isotropic_noise - s0) < 0.02 and np.max(np.abs(fitted.mean - mu0)) < 0.05
+
+
 # ---- full-size properties (BASELINE configs[1]: N=1M, d=200, k=16, 20% missing) ---------------------------
 def test_full_size_properties(pk):
     n, d, k = 1_000_000, 200, 16
