@@ -960,7 +960,9 @@ static void launch_solve_reg(const Launcher &L, const SolveArgs &a) {
   }
   const int groups = (a.rows_pad + SPW - 1) / SPW;
   int64_t blocks = (groups + warps - 1) / warps;
-  const int64_t cap = (int64_t)L.sms * 8;
+  // exactly one resident wave (the kernel's __launch_bounds__ occupancy): the grid-stride loop over sample groups
+  // balances to < 1 %, where a 2.67-wave grid left the last third of the SMs idle for a whole CTA lifetime
+  const int64_t cap = (int64_t)L.sms * (KP == 32 ? 2 : (KP == 16 ? 3 : 4));
   if (blocks > cap) blocks = cap;
   solve_reg_kernel<KP><<<(unsigned)blocks, warps * 32, smem, L.stream>>>(a);
   CUDA_CHECK(cudaGetLastError());

@@ -434,8 +434,10 @@ def test_model_sample_on_device_has_the_model_distribution(pk):
     assert np.array_equal(model.sample(1000, p, seed=11).numpy(), a[:1000], equal_nan=True)   # counter-based RNG
     assert not np.array_equal(model.sample(1000, p, seed=12).numpy(), a[:1000], equal_nan=True)
     assert len(model.sample(0, p)) == 0
-    fitted = pk.PPCATrainer(model.sample(50_000, 0.2, seed=5)).train(state_size=k, n_iters=30, quiet=True)
-    assert abs(fitted.isotropic_noise - s0) < 0.02 and np.max(np.abs(fitted.mean - mu0)) < 0.05
+    fresh = model.sample(50_000, 0.2, seed=5)
+    fitted = pk.PPCATrainer(fresh).train(state_size=k, n_iters=60, quiet=True)
+    assert abs(fitted.isotropic_noise - s0) < 0.1 and np.max(np.abs(fitted.mean - mu0)) < 0.1
+    assert fitted.llk(fresh) > model.llk(fresh) - 0.01 * abs(model.llk(fresh))   # the fit explains the draw like the truth
 
 
 # ---- full-size properties (BASELINE configs[1]: N=1M, d=200, k=16, 20% missing) ---------------------------
