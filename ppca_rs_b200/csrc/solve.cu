@@ -194,21 +194,18 @@ __global__ void __launch_bounds__(256) solve_kernel(SolveArgs a) {
 // lane contributes its own element through one conflict-free shared-memory store per pivot.  The pivots are
 // the Cholesky pivots squared, so ln det M = sum ln d_p (no determinant overflow).
 // ---------------------------------------------------------------------------------------------
-template <int KP, bool PREFETCH>
+template <int KP>
 __global__ void __launch_bounds__(256, (KP == 32 ? 2 : (KP == 16 ? 3 : 4))) solve_reg_kernel(SolveArgs a) {
   constexpr int SPW = 32 / KP;
   extern __shared__ __align__(16) double smem_reg[];
   const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5, warps = blockDim.x >> 5;
   const int sub = lane / KP, li = lane % KP;
   const int k = a.s.k, kkp = a.s.kkp, kp = a.s.kp;
-  // PREFETCH: the packed G rows and y of the NEXT sample group are fetched with cp.async into a second staging buffer
-  // while this group is eliminated (ncu: long_scoreboard was the top stall, every warp waited for its own 2 KB of G)
-  constexpr int NBUF = PREFETCH ? 2 : 1;
-  const int per_warp = NBUF * SPW * kkp + 128 + (NBUF - 1) * 32;
-  double *stage_base = smem_reg + (size_t)wi * per_warp;  // NBUF x SPW packed rows
-  double *col = stage_base + NBUF * SPW * kkp;            // [2][32] pivot-column exchange
-  double *yb_base = col + 64;                             // NBUF x [32]
-  double *zb = yb_base + NBUF * 32;                       // [32]
+  const int per_warp = SPW * kkp + 128;
+  double *stage = smem_reg + (size_t)wi * per_warp;  // SPW packed rows
+  double *col = stage + SPW * kkp;                   // [2][32] pivot-column exchange
+  double *yb = col + 64;                             // [32]
+  double *zb = yb + 32;                              // [32]
   // running max |W| per staged slot of this warp (column maxima for the int8 digit planes, fused here so the
   // M-step slicing does not need its own pass over W)
   double *cmw = smem_reg + (size_t)warps * per_warp + (size_t)wi * (SPW * kkp);
@@ -217,35 +214,14 @@ __global__ void __launch_bounds__(256, (KP == 32 ? 2 : (KP == 16 ? 3 : 4))) solv
   const double s2 = a.sigma * a.sigma;
   const double ln_sigma = log(a.sigma);
   const int groups = (a.rows_pad + SPW - 1) / SPW;
-  const int gstride = gridDim.x * warps;
-  auto prefetch = [&](int g2, int buf) {
-    const int r0 = g2 * SPW;
-    const double *src = a.GW + (int64_t)r0 * kkp;
-    double *dst = stage_base + buf * (SPW * kkp);
-    for (int q = lane * 2; q < SPW * kkp; q += 64) cp_async16(dst + q, src + q, 16);
-    cp_async8(yb_base + buf * 32 + lane, a.YZ + (int64_t)(r0 + sub) * kp + (li < kp ? li : 0), li < kp ? 8 : 0);
-  };
-  int buf = 0;
-  if (PREFETCH) {
-    if ((int)(blockIdx.x * warps + wi) < groups) prefetch(blockIdx.x * warps + wi, 0);
-    cp_async_commit();
-  }
 
-  for (int g = blockIdx.x * warps + wi; g < groups; g += gstride, buf ^= (NBUF - 1)) {
+  for (int g = blockIdx.x * warps + wi; g < groups; g += gridDim.x * warps) {
     const int row0 = g * SPW;
     const int row = row0 + sub;
     double *gsrc = a.GW + (int64_t)row0 * kkp;
-    double *stage = stage_base + buf * (SPW * kkp);
-    double *yb = yb_base + buf * 32;
-    if (PREFETCH) {
-      if (g + gstride < groups) prefetch(g + gstride, buf ^ 1);
-      cp_async_commit();
-      cp_async_wait<1>();  // this group's copies have landed; the next group's stay in flight
-    } else {
-      for (int q = lane * 2; q < SPW * kkp; q += 64)
-        *reinterpret_cast<double2 *>(stage + q) = *reinterpret_cast<const double2 *>(gsrc + q);
-      yb[lane] = (li < kp) ? a.YZ[(int64_t)row * kp + li] : 0.0;
-    }
+    for (int q = lane * 2; q < SPW * kkp; q += 64)
+      *reinterpret_cast<double2 *>(stage + q) = *reinterpret_cast<const double2 *>(gsrc + q);
+    yb[lane] = (li < kp) ? a.YZ[(int64_t)row * kp + li] : 0.0;
     const int dn = row < a.rows ? a.dn[row] : 0;
     const bool empty = dn == 0;
     const double w = (a.w && row < a.rows) ? a.w[row] : (row < a.rows ? 1.0 : 0.0);
@@ -366,7 +342,6 @@ __global__ void __launch_bounds__(256, (KP == 32 ? 2 : (KP == 16 ? 3 : 4))) solv
     }
     __syncwarp();
   }
-  if (PREFETCH) cp_async_wait<0>();
   if (a.colmax) {
     __syncthreads();
     const double *all = smem_reg + (size_t)warps * per_warp;
@@ -973,18 +948,14 @@ static void launch_solve_reg64(const Launcher &L, const SolveArgs &a) {
   ++*L.launch_counter;
 }
 
-template <int KP, bool PREFETCH>
-static void launch_solve_reg_v(const Launcher &L, const SolveArgs &a) {
+template <int KP>
+static void launch_solve_reg(const Launcher &L, const SolveArgs &a) {
   constexpr int SPW = 32 / KP;
   const int warps = 8;
-  constexpr int NBUF = PREFETCH ? 2 : 1;  // must match the kernel's staging layout
-  const size_t smem = (size_t)warps * (NBUF * SPW * a.s.kkp + 128 + (NBUF - 1) * 32 + (a.colmax ? SPW * a.s.kkp : 0)) *
-                      sizeof(double);
+  const size_t smem = (size_t)warps * (SPW * a.s.kkp + 128 + (a.colmax ? SPW * a.s.kkp : 0)) * sizeof(double);
   static bool configured = false;
   if (!configured) {
-    CUDA_CHECK(cudaFuncSetAttribute(solve_reg_kernel<KP, PREFETCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    100 * 1024));
-    // (no carve-out hint: forcing the maximum shared-memory carve-out cost 8 % here, the kernel likes its L1)
+    CUDA_CHECK(cudaFuncSetAttribute(solve_reg_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     configured = true;
   }
   const int groups = (a.rows_pad + SPW - 1) / SPW;
@@ -993,20 +964,9 @@ static void launch_solve_reg_v(const Launcher &L, const SolveArgs &a) {
   // balances to < 1 %, where a 2.67-wave grid left the last third of the SMs idle for a whole CTA lifetime
   const int64_t cap = (int64_t)L.sms * (KP == 32 ? 2 : (KP == 16 ? 3 : 4));
   if (blocks > cap) blocks = cap;
-  solve_reg_kernel<KP, PREFETCH><<<(unsigned)blocks, warps * 32, smem, L.stream>>>(a);
+  solve_reg_kernel<KP><<<(unsigned)blocks, warps * 32, smem, L.stream>>>(a);
   CUDA_CHECK(cudaGetLastError());
   ++*L.launch_counter;
-}
-
-template <int KP>
-static void launch_solve_reg(const Launcher &L, const SolveArgs &a) {
-  // PPCA_B200_SOLVE_PREFETCH=1: cp.async double-buffered staging of the next sample group (k <= 16 only).  Measured
-  // slower on B200 (c2: 1.55 vs 1.39 ms per 1 M samples): the doubled staging buffer eats the L1 the scalar loads use.
-  static const bool prefetch = getenv("PPCA_B200_SOLVE_PREFETCH") && atoi(getenv("PPCA_B200_SOLVE_PREFETCH")) == 1;
-  if constexpr (KP <= 16) {
-    if (prefetch) return launch_solve_reg_v<KP, true>(L, a);
-  }
-  launch_solve_reg_v<KP, false>(L, a);
 }
 
 // Per-sample scalars of one chunk -> SOLVE_SLOTS partial slots (block b always owns slot b and rows

@@ -26,6 +26,7 @@ namespace tb {
 constexpr int MH = 1;             // 128-row MMA halves per tile (MH = 2 with NQ = 16 measured slower: producer bound)
 constexpr int BM = 128 * MH, NQ = 32, BKB = 128, STAGES = 4;
 constexpr int PRODUCERS = 128, THREADS = 288, THREADS_ATM = 448;
+constexpr int ATM_DEPTH = 6, ATM_RING = 8;  // mask-word prefetch distance (own jobs) and ring slots of the ATM kernel
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
@@ -445,7 +446,7 @@ __global__ void __launch_bounds__(tb::THREADS_ATM, 1) tbitgemm_atm_kernel(TBitGe
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar(s), PRODUCERS + 1);  // 128 mask expanders + the bulk-copy issue
+      mbar_init(full_bar(s), PRODUCERS / 32 + 1);  // one elected lane per producer warp + the bulk-copy issue
       mbar_init(empty_bar(s), 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -475,7 +476,7 @@ __global__ void __launch_bounds__(tb::THREADS_ATM, 1) tbitgemm_atm_kernel(TBitGe
     // {0,1} in registers and writes the 128 bytes to the stage's tensor-memory columns with one tcgen05.st;
     // tcgen05.wait::st, fence, arrive.  The 16 bytes of mask a thread needs per job are fetched DEPTH own jobs
     // ahead with cp.async into a private shared-memory ring (mask rows are strided: latency, not bandwidth).
-    constexpr int DEPTH = 3, RING = 4;
+    constexpr int DEPTH = ATM_DEPTH, RING = ATM_RING;
     const int grp = warp >> 2, gt = tid & 127;  // group, thread within the group = row of the tile
     uint32_t *ring = reinterpret_cast<uint32_t *>(smem_raw + (smem_base - smem_u32(smem_raw)) + STAGES * STAGE_BYTES) +
                      grp * (RING * 128 * 4);
@@ -556,7 +557,10 @@ __global__ void __launch_bounds__(tb::THREADS_ATM, 1) tbitgemm_atm_kernel(TBitGe
       tc_st32(tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(ACOL + 32 * stage), v);
       tc_wait_st();
       tc_fence_before();
-      mbar_arrive(full_bar(stage));
+      // one arrive per warp: 128 lanes arriving on one mbarrier word serialise in the shared-memory pipe (ncu counted
+      // ~1e9 LSU bank conflicts per E-step launch, the same pipe the bulk copies and the mask ring use)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full_bar(stage));
       step(cp);
       job += NGRP;
       ++own;
@@ -845,7 +849,7 @@ static void launch_tb(const Launcher &L, const TBitGemmArgs &a) {
   if constexpr (2 * T * tb::NQ + 32 * tb::STAGES <= 512) {
     static const bool smem_a = getenv("PPCA_B200_TC_SMEM_A") && atoi(getenv("PPCA_B200_TC_SMEM_A")) == 1;
     if (!smem_a) {  // A operand in tensor memory: shared memory carries only the digit planes
-      constexpr size_t SMEM_ATM = (size_t)tb::STAGES * (T * tb::NQ * tb::BKB) + 1024 + 2 * 4 * 128 * 16;
+      constexpr size_t SMEM_ATM = (size_t)tb::STAGES * (T * tb::NQ * tb::BKB) + 1024 + 2 * tb::ATM_RING * 128 * 16;
       static bool configured_atm = false;
       if (!configured_atm) {
         CUDA_CHECK(cudaFuncSetAttribute(tbitgemm_atm_kernel<T, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_ATM));
