@@ -194,8 +194,8 @@ __global__ void __launch_bounds__(256) solve_kernel(SolveArgs a) {
 // lane contributes its own element through one conflict-free shared-memory store per pivot.  The pivots are
 // the Cholesky pivots squared, so ln det M = sum ln d_p (no determinant overflow).
 // ---------------------------------------------------------------------------------------------
-template <int KP>
-__global__ void __launch_bounds__(256, (KP == 32 ? 2 : (KP == 16 ? 3 : 4))) solve_reg_kernel(SolveArgs a) {
+template <int KP, int MINB>
+__global__ void __launch_bounds__(256, MINB) solve_reg_kernel(SolveArgs a) {
   constexpr int SPW = 32 / KP;
   extern __shared__ __align__(16) double smem_reg[];
   const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5, warps = blockDim.x >> 5;
@@ -948,25 +948,38 @@ static void launch_solve_reg64(const Launcher &L, const SolveArgs &a) {
   ++*L.launch_counter;
 }
 
-template <int KP>
-static void launch_solve_reg(const Launcher &L, const SolveArgs &a) {
+template <int KP, int MINB>
+static void launch_solve_reg_b(const Launcher &L, const SolveArgs &a) {
   constexpr int SPW = 32 / KP;
   const int warps = 8;
   const size_t smem = (size_t)warps * (SPW * a.s.kkp + 128 + (a.colmax ? SPW * a.s.kkp : 0)) * sizeof(double);
   static bool configured = false;
   if (!configured) {
-    CUDA_CHECK(cudaFuncSetAttribute(solve_reg_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CUDA_CHECK(cudaFuncSetAttribute(solve_reg_kernel<KP, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     configured = true;
   }
   const int groups = (a.rows_pad + SPW - 1) / SPW;
   int64_t blocks = (groups + warps - 1) / warps;
   // exactly one resident wave (the kernel's __launch_bounds__ occupancy): the grid-stride loop over sample groups
   // balances to < 1 %, where a 2.67-wave grid left the last third of the SMs idle for a whole CTA lifetime
-  const int64_t cap = (int64_t)L.sms * (KP == 32 ? 2 : (KP == 16 ? 3 : 4));
+  const int64_t cap = (int64_t)L.sms * MINB;
   if (blocks > cap) blocks = cap;
-  solve_reg_kernel<KP><<<(unsigned)blocks, warps * 32, smem, L.stream>>>(a);
+  solve_reg_kernel<KP, MINB><<<(unsigned)blocks, warps * 32, smem, L.stream>>>(a);
   CUDA_CHECK(cudaGetLastError());
   ++*L.launch_counter;
+}
+
+template <int KP>
+static void launch_solve_reg(const Launcher &L, const SolveArgs &a) {
+  // resident CTAs per SM the kernel is compiled for (register budget 65536 / (256 MINB)); PPCA_B200_SOLVE_MINB
+  // overrides the default for k <= 16 (experiments)
+  static const int minb16 = getenv("PPCA_B200_SOLVE_MINB") ? atoi(getenv("PPCA_B200_SOLVE_MINB")) : 3;
+  if constexpr (KP == 32) launch_solve_reg_b<32, 2>(L, a);
+  else if constexpr (KP == 16) {
+    if (minb16 == 2) launch_solve_reg_b<16, 2>(L, a);
+    else if (minb16 == 4) launch_solve_reg_b<16, 4>(L, a);
+    else launch_solve_reg_b<16, 3>(L, a);
+  } else launch_solve_reg_b<8, 4>(L, a);
 }
 
 // Per-sample scalars of one chunk -> SOLVE_SLOTS partial slots (block b always owns slot b and rows
