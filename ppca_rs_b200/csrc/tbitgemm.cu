@@ -114,6 +114,14 @@ __device__ __forceinline__ uint32_t nib4(uint32_t b, int shift) {
 }
 
 
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256); the address must be 32-byte aligned
+__device__ __forceinline__ void st_global_256(double *p, double a, double b, double c, double d) {
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+__device__ __forceinline__ void ld_global_256(const double *p, double &a, double &b, double &c, double &d) {
+  asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p) : "memory");
+}
+
 // Recombination of the T digit-plane sums d_t (exact int32) of one output: value = sum_t d_t 256^(T-1-t).
 // The planes are first merged in exact 64-bit integer arithmetic in groups of three (|group| < 2^48 for the
 // three-plane groups), so an output costs ceil(T/3) int64->double conversions and ceil(T/3)-1 FMAs instead of T
@@ -380,16 +388,19 @@ __global__ void __launch_bounds__(tb::THREADS, 1) tbitgemm_kernel(TBitGemmArgs a
               for (int t = 0; t < T; ++t) d[t] = rg[t][j];
               v[j] = empty_slab ? 0.0 : combine_planes<T>(d) * (a.scale[q + j] * combine_scale<T>());
             }
-            double2 *p = reinterpret_cast<double2 *>(out + (int64_t)row * ldo + q);
+            // 32-byte accesses: a lane's 8 outputs are two full L2 sectors (16-byte stores wrote every sector twice)
+            double *p = out + (int64_t)row * ldo + q;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              double2 val = make_double2(v[2 * j], v[2 * j + 1]);
+            for (int j = 0; j < 2; ++j) {
               if (accumulate) {
-                const double2 o = p[j];
-                val.x += o.x;
-                val.y += o.y;
+                double o0, o1, o2, o3;
+                ld_global_256(p + 4 * j, o0, o1, o2, o3);
+                v[4 * j] += o0;
+                v[4 * j + 1] += o1;
+                v[4 * j + 2] += o2;
+                v[4 * j + 3] += o3;
               }
-              p[j] = val;
+              st_global_256(p + 4 * j, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
             }
           }
         }
@@ -678,16 +689,19 @@ __global__ void __launch_bounds__(tb::THREADS_ATM, 1) tbitgemm_atm_kernel(TBitGe
               for (int t = 0; t < T; ++t) d[t] = rg[t][j];
               v[j] = empty_slab ? 0.0 : combine_planes<T>(d) * (a.scale[q + j] * combine_scale<T>());
             }
-            double2 *p = reinterpret_cast<double2 *>(out + (int64_t)row * ldo + q);
+            // 32-byte accesses: a lane's 8 outputs are two full L2 sectors (16-byte stores wrote every sector twice)
+            double *p = out + (int64_t)row * ldo + q;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              double2 val = make_double2(v[2 * j], v[2 * j + 1]);
+            for (int j = 0; j < 2; ++j) {
               if (accumulate) {
-                const double2 o = p[j];
-                val.x += o.x;
-                val.y += o.y;
+                double o0, o1, o2, o3;
+                ld_global_256(p + 4 * j, o0, o1, o2, o3);
+                v[4 * j] += o0;
+                v[4 * j + 1] += o1;
+                v[4 * j + 2] += o2;
+                v[4 * j + 3] += o3;
               }
-              p[j] = val;
+              st_global_256(p + 4 * j, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
             }
           }
         }
@@ -757,10 +771,17 @@ __global__ void __launch_bounds__(128) slice_tc_kernel(const double *__restrict_
     int8_t *tile = out + ((int64_t)ks * qtiles + qt) * (int64_t)(T * tb::NQ * 128);
     const int n = t * tb::NQ + qi, c0 = 2 * (kb & 3);
     const int base = (n >> 3) * 1024 + (n & 7) * 128;
-    *reinterpret_cast<uint4 *>(tile + base + (((c0) ^ (n & 7)) << 4)) =
-        make_uint4(words[t][0], words[t][1], words[t][2], words[t][3]);
-    *reinterpret_cast<uint4 *>(tile + base + (((c0 + 1) ^ (n & 7)) << 4)) =
-        make_uint4(words[t][4], words[t][5], words[t][6], words[t][7]);
+    // chunks c0 and c0 + 1 (c0 even) swizzle to the two halves of ONE aligned 32-byte sector, swapped when n is odd:
+    // one 256-bit store instead of two half-sector stores
+    const int sw = n & 7, lo = ((c0 ^ sw) & ~1) << 4;
+    const bool swap = sw & 1;
+    const uint32_t a0 = swap ? words[t][4] : words[t][0], a1 = swap ? words[t][5] : words[t][1];
+    const uint32_t a2 = swap ? words[t][6] : words[t][2], a3 = swap ? words[t][7] : words[t][3];
+    const uint32_t b0 = swap ? words[t][0] : words[t][4], b1 = swap ? words[t][1] : words[t][5];
+    const uint32_t b2 = swap ? words[t][2] : words[t][6], b3 = swap ? words[t][3] : words[t][7];
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(tile + base + lo), "r"(a0), "r"(a1), "r"(a2),
+                 "r"(a3), "r"(b0), "r"(b1), "r"(b2), "r"(b3)
+                 : "memory");
   }
 }
 
@@ -880,7 +901,9 @@ static void launch_tb(const Launcher &L, const TBitGemmArgs &a) {
 void launch_tbitgemm(const Launcher &L, const uint32_t *bits, int64_t ldbits, int nwords, const int8_t *Bq,
                      const double *scale, int T, double *Out, int64_t ldo, int M, int Nq, int ksteps, int accumulate,
                      double *partials, int splitk, int defer_reduce) {
-  REQUIRE(Nq % 8 == 0 && ldo % 2 == 0, "tbitgemm: Nq must be a multiple of 8, output pitch even");
+  REQUIRE(Nq % 8 == 0 && ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(Out) & 31) == 0 &&
+              (partials == nullptr || (reinterpret_cast<uintptr_t>(partials) & 31) == 0),
+          "tbitgemm: Nq must be a multiple of 8, output pitch a multiple of 4, outputs 32-byte aligned");
   REQUIRE(splitk >= 1 && splitk <= (ksteps > 0 ? ksteps : 1), "tbitgemm: bad split-K");
   {  // every K slab must be non-empty
     const int per = (ksteps + splitk - 1) / splitk;
