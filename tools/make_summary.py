@@ -34,7 +34,7 @@ def main():
 
 All numbers come from `bench.py` on a fresh `gpurun` box; the JSON lines are committed next to this file
 (`r01_bench_*.json`).  ncu evidence: `r01_c2_step_ncu_full_summary.txt`, `r01_c3s_step_ncu_full_summary.txt`
-(`--set full`, one chunk), `r01_launches_c2_v4.csv` (launch list of the bench command), `r01_traffic.json` (DRAM bytes
+(`--set full`, one chunk), `r01_launches_c2_v6.csv` (launch list of the bench command), `r01_traffic.json` (DRAM bytes
 per launch), `r01_tbitgemm_*` / `r01_bitgemm_*` (contraction kernels), `r01_solve_blk_ncu.txt` (the blocked solve
 experiment); peaks: `r01_fp64_peak.json` (DMMA 37.1 TFLOP/s = DFMA rate), `r01_utc_i8_peak.json` (tcgen05 int8
 4.3 POP/s), `r01_imma_peak.json`, `MEASURED_PEAKS.json` (HBM 6551 GB/s).
@@ -51,7 +51,9 @@ experiment); peaks: `r01_fp64_peak.json` (DMMA 37.1 TFLOP/s = DFMA rate), `r01_u
 
 c2 resident is {c2['value']/ref['value']:.0f}x the CPU arm and end to end {c2['e2e']['value']/ref['value']:.0f}x; the end-to-end step is PCIe-bound (the
 kernels, {c2['ms_per_step']:.1f} ms, hide behind the 1.6 GB H2D copy, 29.6 ms).  The mixture e2e leg re-creates the device Dataset
-every step; the committed line hit a one-off stall (0.25 M/s), seven other runs measured 2.5-4.6 M/s; the resident number is stable.  2 GPUs (`gpurun --gpus 2`, torchrun, NCCL): c2 e2e 67.6 M/s.
+every step (cudaMalloc/cudaFree of ~1 GB inside the timed region) and varies run to run (2.1-4.6 M/s, one 0.25 M/s outlier); the resident number is stable.  2 GPUs (`gpurun --gpus 2`, torchrun, NCCL, `r01_bench_c2_2gpu.json`):
+c2 481 M/s resident (4.16 ms/step, 98 % of 2x), e2e 67.6 M/s.  The c5 resident figure allocates its 16 GB output Dataset every step
+and varied 298-484 ms across runs; its streamed (host in / host out) figure is stable.
 
 ## Kernel families, ms per step (CUDA events on the launching stream, inside the timed region)
 
@@ -90,7 +92,7 @@ c2 {100*r(c2)['whole_step_fp64_equivalent_frac']:.0f} %, c3 {100*r(c3)['whole_st
 
 | 18 944 (1 wave) | 37 888 | 75 776 (old default) | 151 552 | 265 216 | 511 488 | 1 003 520 (whole dataset, new default) |
 |---|---|---|---|---|---|---|
-| 9.08 | 6.69 | 5.47 | 4.85 | 4.53 | 4.29 | 4.17 |
+| 9.08 | 6.69 | 5.47 | 4.85 | 4.53 | 4.29 | 4.17 (4.00 after the 256-bit stores) |
 
 Bigger is better all the way (per-launch tails, split-K/slab reductions); L2 residency of a small chunk does not pay.
 The engine now takes as many rows per chunk as 8 GiB of workspace holds (at most 2 M), split evenly.
@@ -100,8 +102,8 @@ The engine now takes as many rows per chunk as 8 GiB of workspace holds (at most
 * Per-sample solve: 30 % (c2) to 36 % (c3) of the step, ~25 % of the FP64 peak; latency-bound chain of dependent
   reciprocals per pivot with the register file limiting the samples in flight (4 per SM at k=64).
 * Cross-moment / residual pass: FP64 DMMA-bound at k >= 16 (4dk flop per 8d bytes), 31-53 % of the DMMA peak.
-* Contractions at the c3 shape: 38 % (E) / 51 % (M) of the int8 peak; stage round-trip latency (4 stages) and the
-  mask expansion issue rate bound the main loop.
+* Contractions at the c3 shape: 43 % (E) / 53 % (M) of the int8 peak; stage round-trip latency (4 stages) and the
+  mask expansion issue rate bound the main loop.  Full-sector (256-bit) epilogue stores were worth 9-21 % of the E-step.
 """
     with open(os.path.join(P, "r01_summary.md"), "w") as f:
         f.write(txt)
