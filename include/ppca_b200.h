@@ -138,6 +138,14 @@ int32_t ppca_b200_llk(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int32_t k
 /* PPCAModel::infer (ppca_model.rs:195-227): states n x k, covariances n x k x k (nullable). */
 int32_t ppca_b200_infer(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int32_t k, const double *C,
                         const double *mu, double sigma, double *states, double *covariances);
+/* InferredMasked::smoothed_covariance_diagonal (ppca_model.rs:485-508) and ::extrapolated_covariance_diagonal
+ * (:542-577), batched as in src/python_bindings.rs:282-333: out[n][i] = sigma^2 + c_i^T Sigma_n c_i, evaluated as
+ * the dense FP64 GEMM (packed Sigma_n) x (row-wise symmetric Kronecker table of C)^T on the tensor cores.
+ * `covariances` is the host n x k x k array ppca_b200_infer returned.  With `masked_by` (nullable) the slots that
+ * dataset observed are 0, as in the extrapolated variant.  Result: an all-observed dataset, weights 1. */
+int32_t ppca_b200_covariance_diagonal(ppca_b200_ctx *ctx, int64_t n, int32_t d, int32_t k, const double *C, double sigma,
+                                      const double *covariances, const ppca_b200_dataset *masked_by,
+                                      ppca_b200_dataset **out);
 /* PPCAModel::smooth (ppca_model.rs:237-244) / ::extrapolate (:254-261): new all-observed dataset,
  * weights carried through. */
 int32_t ppca_b200_smooth(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int32_t k, const double *C,

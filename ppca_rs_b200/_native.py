@@ -77,6 +77,10 @@ _PROTOTYPES = {
     "ppca_b200_llks": (C.c_int32, [c_ctx_p, c_ds_p, C.c_int32, c_dp, c_dp, C.c_double, c_dp]),
     "ppca_b200_llk": (C.c_int32, [c_ctx_p, c_ds_p, C.c_int32, c_dp, c_dp, C.c_double, c_dp]),
     "ppca_b200_infer": (C.c_int32, [c_ctx_p, c_ds_p, C.c_int32, c_dp, c_dp, C.c_double, c_dp, c_dp]),
+    "ppca_b200_covariance_diagonal": (
+        C.c_int32,
+        [c_ctx_p, C.c_int64, C.c_int32, C.c_int32, c_dp, C.c_double, c_dp, c_ds_p, C.POINTER(c_ds_p)],
+    ),
     "ppca_b200_smooth": (C.c_int32, [c_ctx_p, c_ds_p, C.c_int32, c_dp, c_dp, C.c_double, C.POINTER(c_ds_p)]),
     "ppca_b200_extrapolate": (C.c_int32, [c_ctx_p, c_ds_p, C.c_int32, c_dp, c_dp, C.c_double, C.POINTER(c_ds_p)]),
     "ppca_b200_iterate": (

@@ -655,6 +655,49 @@ void finalize_full_store(ppca_b200_ctx *ctx, SampleStore &out) {
   launch_transpose_mask(ctx->L(), out);
 }
 
+
+// ---- covariance diagonals (InferredMasked::smoothed_ / extrapolated_covariance_diagonal) ----------------------------
+// S2[n][q(a,b)] = (a == b ? 1 : 2) Sigma_n[a][b] (packed upper, zero padded): diag_i = sigma^2 + sum_q S2[n][q] Ksym[i][q]
+__global__ void pack_cov_kernel(const double *__restrict__ cov, int64_t rows, int64_t rows_pad, int k, int kk, int kkp,
+                                double *S2) {
+  const int64_t total = rows_pad * kkp;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = idx / kkp;
+    const int q = (int)(idx % kkp);
+    double v = 0.0;
+    if (n < rows && q < kk) {
+      int a = 0, off = q;  // q -> (a, b) of the packed upper triangle by rows
+      while (off >= k - a) {
+        off -= k - a;
+        ++a;
+      }
+      const int b = a + off;
+      v = cov[n * k * k + (int64_t)a * k + b] * (a == b ? 1.0 : 2.0);
+    }
+    S2[idx] = v;
+  }
+}
+
+// KT[q][i] = Ksym[i][q] for i < d, q < kk (zero elsewhere): kq32 x d8
+__global__ void transpose_ksym_kernel(const double *__restrict__ Ksym, int d, int kk, int kkp, int kq32, int d8, double *KT) {
+  const int64_t total = (int64_t)kq32 * d8;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int q = (int)(idx / d8), i = (int)(idx % d8);
+    KT[idx] = (i < d && q < kk) ? Ksym[(int64_t)i * kkp + q] : 0.0;
+  }
+}
+
+__global__ void cov_diag_finish_kernel(const double *__restrict__ Y, int d8, int64_t rows, int d, double s2,
+                                       const uint32_t *__restrict__ mask, int dw, int64_t mrow0, double *outX, int ldx) {
+  const int64_t total = rows * d;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = idx / d;
+    const int i = (int)(idx % d);
+    const bool observed = mask && ((mask[(mrow0 + n) * dw + (i >> 5)] >> (i & 31)) & 1u);
+    outX[n * ldx + i] = observed ? 0.0 : Y[n * d8 + i] + s2;  // expand() leaves observed slots at 0 (ppca_model.rs:576)
+  }
+}
+
 struct MixView {
   int m;
   const int32_t *ks;
@@ -1430,6 +1473,68 @@ int32_t ppca_b200_reconstruct_host(ppca_b200_ctx *ctx, const double *x, int64_t 
     }
     CUDA_CHECK(cudaStreamSynchronize(ctx->out_stream));
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  });
+}
+
+// ---- covariance diagonals ------------------------------------------------------------------------------------------
+int32_t ppca_b200_covariance_diagonal(ppca_b200_ctx *ctx, int64_t n, int32_t d, int32_t k, const double *C, double sigma,
+                                      const double *covariances, const ppca_b200_dataset *masked_by,
+                                      ppca_b200_dataset **out) {
+  return guarded([&] {
+    REQUIRE(ctx != nullptr && out != nullptr && C != nullptr, "null argument");
+    REQUIRE(n >= 0 && d >= 1 && k >= 1, "bad shape");
+    REQUIRE(n == 0 || covariances != nullptr, "null covariances");
+    if (masked_by) {
+      check_ds(ctx, masked_by);
+      REQUIRE(masked_by->store->n == n && masked_by->store->d == d, "dataset shape does not match the inferred batch");
+    }
+    DeviceGuard g(ctx->device);
+    auto ost = make_store(ctx, n, d);
+    if (n > 0) {
+      std::vector<double> zero_mu((size_t)d, 0.0);
+      DevModel m = stage_model(ctx, d, k, C, zero_mu.data(), sigma > 0.0 ? sigma : 1.0, true);
+      const int kk = m.s.kk, kkp = m.s.kkp, kq32 = (int)round_up(kkp, 32), d8 = (int)round_up(d, 8);
+      DevBuf<double> KT, zeros, S2, Y, nxs, covd;
+      DevBuf<uint32_t> ones;
+      KT.alloc((size_t)kq32 * d8);
+      zeros.alloc((size_t)kq32);
+      ones.alloc((size_t)kq32 / 32);
+      CUDA_CHECK(cudaMemsetAsync(zeros.p, 0, sizeof(double) * kq32, ctx->stream));
+      CUDA_CHECK(cudaMemsetAsync(ones.p, 0xff, sizeof(uint32_t) * (kq32 / 32), ctx->stream));
+      const int tb = (int)std::min<int64_t>((int64_t)ctx->sms * 8, ((int64_t)kq32 * d8 + 255) / 256);
+      transpose_ksym_kernel<<<tb, 256, 0, ctx->stream>>>(m.Ksym, d, kk, kkp, kq32, d8, KT.p);
+      CUDA_CHECK(cudaGetLastError());
+      ++ctx->launches;
+      // rows per pass: covariance staging <= 256 MiB, result staging <= 512 MiB
+      int64_t rows_per = std::min<int64_t>(((int64_t)256 << 20) / ((int64_t)k * k * 8), ((int64_t)512 << 20) / ((int64_t)d8 * 8));
+      rows_per = std::max<int64_t>(128, rows_per / 128 * 128);
+      if (rows_per > round_up(n, 128)) rows_per = round_up(n, 128);
+      covd.alloc((size_t)rows_per * k * k);
+      S2.alloc((size_t)rows_per * kkp);
+      Y.alloc((size_t)rows_per * d8);
+      nxs.alloc((size_t)rows_per);
+      for (int64_t r0 = 0; r0 < n; r0 += rows_per) {
+        const int64_t rows = std::min<int64_t>(rows_per, n - r0), rows_pad = round_up(rows, 128);
+        CUDA_CHECK(cudaMemcpyAsync(covd.p, covariances + r0 * k * k, sizeof(double) * rows * k * k, cudaMemcpyHostToDevice,
+                                   ctx->stream));
+        const int pb = (int)std::min<int64_t>((int64_t)ctx->sms * 16, (rows_pad * kkp + 255) / 256);
+        pack_cov_kernel<<<pb, 256, 0, ctx->stream>>>(covd.p, rows, rows_pad, k, kk, kkp, S2.p);
+        CUDA_CHECK(cudaGetLastError());
+        ++ctx->launches;
+        launch_rowgemm(ctx->L(), S2.p, kkp, (int)rows_pad, kkp, KT.p, d8, ones.p, zeros.p, Y.p, nxs.p);
+        const int fb = (int)std::min<int64_t>((int64_t)ctx->sms * 16, (rows * d + 255) / 256);
+        cov_diag_finish_kernel<<<fb, 256, 0, ctx->stream>>>(Y.p, d8, rows, d, sigma * sigma,
+                                                            masked_by ? masked_by->store->mask.p : nullptr,
+                                                            masked_by ? masked_by->store->dw : 0, r0,
+                                                            ost->X.p + r0 * ost->ldx, ost->ldx);
+        CUDA_CHECK(cudaGetLastError());
+        ++ctx->launches;
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));  // covd / S2 / Y are reused by the next pass
+      }
+      finalize_full_store(ctx, *ost);
+    }
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    *out = make_dataset(ctx, ost, nullptr);
   });
 }
 

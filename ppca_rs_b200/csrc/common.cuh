@@ -190,6 +190,10 @@ void launch_bitgemm_reduce(const Launcher &L, const double *partials, int splitk
 void launch_proj(const Launcher &L, const SampleStore &st, int64_t row0, int rows, const DevModel &m, double *Y,
                  double *nx);
 
+// dense FP64 row GEMM on the projection kernel (covariance diagonals): Y = A * Bt, see proj.cu
+void launch_rowgemm(const Launcher &L, const double *A, int lda, int rows_pad, int K, const double *Bt, int n8,
+                    const uint32_t *ones, const double *zeros, double *Y, double *nx_scratch);
+
 // solve.cu : per-sample k x k factorisation
 struct SolveArgs {
   Shape s;

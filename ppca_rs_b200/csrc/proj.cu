@@ -157,4 +157,33 @@ void launch_proj(const Launcher &L, const SampleStore &st, int64_t row0, int row
   else launch_proj_ni<8>(L, st, row0, rows, m, Y, nx);
 }
 
+
+// Dense FP64 row GEMM on the same kernel:  Y[rows_pad x n8] = A[rows_pad x K] * Bt[K32 x n8]  (no masking, no centring).
+// `ones` must hold K32 / 32 words of 0xffffffff (every row reads the same words: mask pitch 0), `zeros` K32 doubles of 0.
+template <int NI>
+static void launch_rowgemm_ni(const Launcher &L, const double *A, int lda, int rows_pad, int K, const double *Bt, int n8,
+                              const uint32_t *ones, const double *zeros, double *Y, double *nx_scratch) {
+  using Cfg = ProjCfg<NI>;
+  static bool configured = false;
+  if (!configured) {
+    CUDA_CHECK(cudaFuncSetAttribute(proj_kernel<NI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+    configured = true;
+  }
+  dim3 grid((unsigned)(rows_pad / Cfg::BM), (unsigned)((n8 + Cfg::BN - 1) / Cfg::BN));
+  proj_kernel<NI><<<grid, 256, Cfg::SMEM, L.stream>>>(A, lda, ones, 0, 0, Bt, n8, zeros, (K + 31) / 32, K, Y, nx_scratch);
+  CUDA_CHECK(cudaGetLastError());
+  ++*L.launch_counter;
+}
+
+void launch_rowgemm(const Launcher &L, const double *A, int lda, int rows_pad, int K, const double *Bt, int n8,
+                    const uint32_t *ones, const double *zeros, double *Y, double *nx_scratch) {
+  REQUIRE(rows_pad % 128 == 0 && n8 % 8 == 0 && lda % 2 == 0, "rowgemm: rows must be padded to 128, columns to 8");
+  if (rows_pad <= 0) return;
+  const int nt = n8 / 8;
+  if (nt <= 1) launch_rowgemm_ni<1>(L, A, lda, rows_pad, K, Bt, n8, ones, zeros, Y, nx_scratch);
+  else if (nt <= 2) launch_rowgemm_ni<2>(L, A, lda, rows_pad, K, Bt, n8, ones, zeros, Y, nx_scratch);
+  else if (nt <= 4) launch_rowgemm_ni<4>(L, A, lda, rows_pad, K, Bt, n8, ones, zeros, Y, nx_scratch);
+  else launch_rowgemm_ni<8>(L, A, lda, rows_pad, K, Bt, n8, ones, zeros, Y, nx_scratch);
+}
+
 }  // namespace ppca

@@ -560,12 +560,23 @@ class InferredMasked:
         eye = np.eye(d) * ppca._sigma ** 2
         return [eye + ppca._C @ c @ ppca._C.T for c in self._covs]  # ppca_model.rs:471-477
 
+    def _cov_diag_dataset(self, ppca: PPCAModel, dataset: Optional[Dataset]) -> Dataset:
+        """sigma^2 + c_i^T Sigma_n c_i for every (sample, dimension), on the device (ppca_b200_covariance_diagonal);
+        slots `dataset` observed are 0 when it is given (ppca_model.rs:485-508, 542-577)."""
+        n, k = self._states.shape[0], ppca.state_size
+        ctx = dataset._ctx if dataset is not None else nat.get_context()
+        covs = nat.f64(self._covs)
+        h = nat.c_ds_p()
+        nat.check(nat.lib().ppca_b200_covariance_diagonal(ctx.handle, n, ppca.output_size, k, nat.dptr(ppca._C),
+                                                          ppca._sigma, nat.dptr(covs),
+                                                          dataset._h if dataset is not None else None, C.byref(h)))
+        return Dataset._wrap(h, ctx)
+
     def _smoothed_cov_diag(self, ppca: PPCAModel) -> np.ndarray:
-        tc = np.einsum("ia,nab->nib", ppca._C, self._covs)
-        return np.einsum("nib,ib->ni", tc, ppca._C) + ppca._sigma ** 2  # ppca_model.rs:485-508
+        return self._cov_diag_dataset(ppca, None).numpy()
 
     def smoothed_covariances_diagonal(self, ppca: PPCAModel) -> Dataset:
-        return Dataset(self._smoothed_cov_diag(ppca))
+        return self._cov_diag_dataset(ppca, None)
 
     def extrapolated_covariances(self, ppca: PPCAModel, dataset: Dataset) -> List[np.ndarray]:
         x = dataset.numpy()
@@ -580,9 +591,7 @@ class InferredMasked:
         return out
 
     def extrapolated_covariances_diagonal(self, ppca: PPCAModel, dataset: Dataset) -> Dataset:
-        x = dataset.numpy()
-        diag = self._smoothed_cov_diag(ppca)
-        return Dataset(np.where(np.isfinite(x), 0.0, diag))  # ppca_model.rs:542-577
+        return self._cov_diag_dataset(ppca, dataset)  # ppca_model.rs:542-577
 
     def posterior_sampler(self) -> "PosteriorSampler":
         return PosteriorSampler(self._states, np.linalg.cholesky(self._covs))  # ppca_model.rs:581-592

@@ -440,6 +440,39 @@ def test_model_sample_on_device_has_the_model_distribution(pk):
     assert fitted.llk(fresh) > model.llk(fresh) - 0.01 * abs(model.llk(fresh))   # the fit explains the draw like the truth
 
 
+@pytest.mark.parametrize("n,d,k", [(3000, 37, 5), (2500, 200, 16), (700, 130, 48), (300, 20, 1)])
+def test_covariance_diagonals_on_device(pk, n, d, k):
+    """InferredMasked.smoothed_/extrapolated_covariances_diagonal (ppca_model.rs:485-508, 542-577) on the device
+    (ppca_b200_covariance_diagonal) against the defining formula diag(sigma^2 I + C Sigma_n C^T)."""
+    X, C0, mu0, s0 = _case(n, d, k, 0.3, seed=51)
+    X[3, :] = np.nan
+    model = pk.PPCAModel(0.4, C0, mu0)
+    ds = pk.Dataset(X)
+    inf = model.infer(ds)
+    covs = np.stack(inf.covariances())
+    want = np.einsum("ia,nab,ib->ni", C0, covs, C0) + 0.4 ** 2
+    got = inf.smoothed_covariances_diagonal(model)
+    assert isinstance(got, pk.Dataset) and got.empty_dimensions() == []
+    assert rel_err(got.numpy(), want) < 1e-12
+    ex = inf.extrapolated_covariances_diagonal(model, ds).numpy()
+    fin = np.isfinite(X)
+    assert np.all(ex[fin] == 0.0) and rel_err(ex[~fin], want[~fin]) < 1e-12
+    full = inf.smoothed_covariances(model)                      # the d x d matrices (host) share the diagonal
+    assert rel_err(np.diag(full[0]), want[0]) < 1e-12
+    # mixture: law of total variance over the components (mix.rs:445-458)
+    if k <= 16:
+        other = pk.PPCAModel(0.7, C0[:, ::-1].copy(), mu0 + 0.3)
+        mix = pk.PPCAMix([model, other], np.log([0.4, 0.6]))
+        im = mix.infer(ds)
+        post = im.posteriors()
+        means = [im._inf[j]._states @ m.transform.T + m.mean for j, m in enumerate([model, other])]
+        mean = sum(post[:, j:j + 1] * means[j] for j in range(2))
+        diags = [np.einsum("ia,nab,ib->ni", m.transform, np.stack(im._inf[j].covariances()), m.transform)
+                 + m.isotropic_noise ** 2 for j, m in enumerate([model, other])]
+        want_mix = sum(post[:, j:j + 1] * (diags[j] + (means[j] - mean) ** 2) for j in range(2))
+        assert rel_err(im.smoothed_covariances_diagonal(mix).numpy(), want_mix) < 1e-11
+
+
 # ---- full-size properties (BASELINE configs[1]: N=1M, d=200, k=16, 20% missing) ---------------------------
 def test_full_size_properties(pk):
     n, d, k = 1_000_000, 200, 16
