@@ -64,32 +64,38 @@ class ClockSampler:
         self.samples = []
         self._stop = threading.Event()
         self._t = threading.Thread(target=self._run, daemon=True)
+        # NVML is initialised here, outside the timed region (nvmlInit alone takes tens of ms - a 40 ms region would
+        # otherwise be over before the first sample)
+        self._nv = None
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            self._nv = nv
+            self._h = nv.nvmlDeviceGetHandleByIndex(index)
+            self._max = nv.nvmlDeviceGetMaxClockInfo(self._h, nv.NVML_CLOCK_SM)
+        except Exception:
+            self._nv = None
 
-    def _run_nvml(self):
-        """NVML in-process: ~2 ms per sample, so even a 50 ms timed region gets a few samples."""
-        import pynvml as nv
-        nv.nvmlInit()
-        h = nv.nvmlDeviceGetHandleByIndex(self.index)
-        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
-        bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else 0x8,
-                "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
-        while not self._stop.is_set():
-            sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
-            try:
-                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
-            except Exception:
-                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-            self.samples.append([str(sm), str(mx)] + ["Active" if (r & bits[k]) else "Not Active"
-                                                      for k in ("hw_slowdown", "hw_thermal_slowdown",
-                                                                "sw_thermal_slowdown", "sw_power_cap")])
-            self._stop.wait(0.005)
+    _BITS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
+
+    def _sample_nvml(self):
+        nv = self._nv
+        sm = nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)
+        try:
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+        except Exception:
+            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+        self.samples.append([str(sm), str(self._max)] + ["Active" if (r & bit) else "Not Active" for _, bit in self._BITS])
 
     def _run(self):
-        try:
-            self._run_nvml()
-            return
-        except Exception:
-            pass
+        if self._nv is not None:
+            try:
+                while not self._stop.is_set():
+                    self._sample_nvml()
+                    self._stop.wait(0.003)
+                return
+            except Exception:
+                pass
         while not self._stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
