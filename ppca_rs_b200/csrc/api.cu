@@ -1295,7 +1295,11 @@ int32_t ppca_b200_iterate(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int32
 int32_t ppca_b200_host_register(const void *p, uint64_t bytes) {
   return guarded([&] {
     REQUIRE(p != nullptr && bytes > 0, "null host range");
-    CUDA_CHECK(cudaHostRegister(const_cast<void *>(p), (size_t)bytes, cudaHostRegisterPortable));
+    const cudaError_t e = cudaHostRegister(const_cast<void *>(p), (size_t)bytes, cudaHostRegisterPortable);
+    if (e != cudaSuccess) {
+      cudaGetLastError();  // not sticky: clear it so the next launch check does not see a stale error
+      PPCA_THROW(PPCA_ERR_CUDA, "cudaHostRegister failed: %s (the range stays pageable)", cudaGetErrorString(e));
+    }
   });
 }
 
