@@ -279,3 +279,19 @@ def test_dataframe_adapter_unknown_dimensions_are_dropped():
     ad = DataFrameAdapter.from_pandas(df, keys=["k"], dimension_idx=idx, metric="v", dataset_factory=_FakeDataset)
     assert ad.dimensions == ["dim"]
     assert np.allclose(ad.dataset.numpy(), [[1.0, 2.0], [3.0, np.nan]], equal_nan=True)
+
+
+def test_rust_ffi_declarations_are_in_sync_with_the_header(tmp_path):
+    """bindings/rust/ppca_b200_sys.rs is generated from include/ppca_b200.h (tools/gen_rust_ffi.py): one `pub fn` per
+    exported symbol, regenerating reproduces the committed file."""
+    import re
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    committed = open(os.path.join(root, "bindings", "rust", "ppca_b200_sys.rs")).read()
+    header = open(os.path.join(root, "include", "ppca_b200.h")).read()
+    declared = set(re.findall(r"\b(ppca_b200_\w+)\s*\(", re.sub(r"/\*.*?\*/", "", header, flags=re.S)))
+    bound = set(re.findall(r"pub fn (ppca_b200_\w+)\(", committed))
+    assert declared == bound
+    subprocess.check_call([sys.executable, os.path.join(root, "tools", "gen_rust_ffi.py")], stdout=subprocess.DEVNULL)
+    assert open(os.path.join(root, "bindings", "rust", "ppca_b200_sys.rs")).read() == committed
