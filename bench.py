@@ -496,6 +496,12 @@ def run_ours(args, wl, rank, world, local_rank):
             entry.update(bound="tensor", achieved=ach, peak=pk_, unit=roofline["unit"], frac=ach / pk_)
         families[name] = entry
     roofline["families"] = families
+    # the family that takes the largest share of the step, with the roof that bounds it (the top-level entry above is the
+    # masked-Gram contraction the north star names; at small k the per-sample solve is the longer kernel)
+    timed = {kname: e for kname, e in families.items() if e.get("frac") is not None}
+    if timed:
+        top = max(timed, key=lambda kname: timed[kname]["ms_per_step"])
+        roofline["dominant_by_time"] = dict(timed[top], family=top)
 
     # ---- CPU baseline on a bounded sample of the same workload (rank 0, N=1 only) ----------------
     cpu = None
