@@ -473,6 +473,39 @@ def test_covariance_diagonals_on_device(pk, n, d, k):
         assert rel_err(im.smoothed_covariances_diagonal(mix).numpy(), want_mix) < 1e-11
 
 
+# ---- the reference's own smoke tests (ppca/src/lib.rs:47-105), same flow through this API, with assertions ----------
+def test_reference_toy_model_flow(pk):
+    """lib.rs:47-62 test_toy_model: sample 1000 draws (20 % masked) from the 3 x 2 toy model, init(2), 1600 iterations."""
+    real = pk.PPCAModel(0.1, np.array([[1.0, 1.0], [1.0, 0.0], [0.0, 1.0]]), np.array([[0.0], [1.0], [0.0]]))
+    sample = real.sample(1_000, 0.2, seed=7)
+    model = pk.PPCAModel.init(2, sample, seed=1)
+    aic = []
+    for _ in range(1600):
+        aic.append(2.0 * (model.n_parameters - model.llk(sample)) / len(sample))
+        model = model.iterate(sample)
+    assert all(b <= a + 1e-9 * abs(a) for a, b in zip(aic, aic[1:]))          # EM never increases the AIC
+    assert abs(model.isotropic_noise - 0.1) < 0.02
+    assert model.llk(sample) >= real.llk(sample) - 1e-6 * abs(real.llk(sample))   # the MLE beats the truth on its sample
+
+
+def test_reference_big_toy_model_flow(pk):
+    """lib.rs:82-101 test_big_toy_model: 200 x 16 Bernoulli(0.1) transform, sigma 0.1, 100 000 draws (20 % masked),
+    init(16), 24 iterations, to_canonical."""
+    rng = np.random.default_rng(0)
+    real = pk.PPCAModel(0.1, (rng.random((200, 16)) < 0.1).astype(np.float64), np.zeros(200))
+    sample = real.sample(100_000, 0.2, seed=3)
+    model = pk.PPCAModel.init(16, sample, seed=2)
+    aic = []
+    for _ in range(24):
+        aic.append(2.0 * (model.n_parameters - model.llk(sample)) / len(sample))
+        model = model.iterate(sample)
+    assert all(b <= a + 1e-9 * abs(a) for a, b in zip(aic, aic[1:]))
+    canon = model.to_canonical()
+    assert abs(canon.llk(sample) - model.llk(sample)) < 1e-9 * abs(model.llk(sample))
+    sv = canon.singular_values
+    assert np.all(np.diff(sv) <= 1e-12) and canon.isotropic_noise < 0.5
+
+
 # ---- full-size properties (BASELINE configs[1]: N=1M, d=200, k=16, 20% missing) ---------------------------
 def test_full_size_properties(pk):
     n, d, k = 1_000_000, 200, 16
