@@ -506,6 +506,25 @@ def test_reference_big_toy_model_flow(pk):
     assert np.all(np.diff(sv) <= 1e-12) and canon.isotropic_noise < 0.5
 
 
+@pytest.mark.parametrize("script", ["toy_model.py", "big_toy_model.py", "ppca_mixture.py",
+                                    "priors_pickling_empty_dimensions.py"])
+def test_examples_run_unmodified_ppca_rs_calls(script, capsys):
+    """examples/ use the reference's import lines (`from ppca_rs import ...`, `from ppca_rs.ppca_rs import ...`) through
+    ppca_rs_b200.compat.install_as_ppca_rs()."""
+    import os
+    import runpy
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "examples"))
+    try:
+        runpy.run_path(os.path.join(root, "examples", script), run_name="__main__")
+    finally:
+        sys.path.remove(os.path.join(root, "examples"))
+        for name in ("ppca_rs", "ppca_rs.ppca_rs", "_alias"):
+            sys.modules.pop(name, None)
+    assert capsys.readouterr().out.strip() != ""
+
+
 # ---- full-size properties (BASELINE configs[1]: N=1M, d=200, k=16, 20% missing) ---------------------------
 def test_full_size_properties(pk):
     n, d, k = 1_000_000, 200, 16
