@@ -192,8 +192,9 @@ def measured_hbm_peak():
         return 6650.0, "B200_PROFILING.md fallback (MEASURED_PEAKS.json absent)"
 
 
-def ctx_chunk(ctx, n, d, k, slices=6):
+def ctx_chunk(ctx, n, d, k, slices=None):
     """Samples per chunk the engine picks automatically (mirrors pick_chunk in csrc/api.cu)."""
+    slices = slices or int(os.environ.get("PPCA_B200_SLICES", "6"))
     kk = k * (k + 1) // 2
     kkp, kp = (kk + 7) // 8 * 8, (k + 7) // 8 * 8
     per_row = (kkp + 2 * kp + 4) * 8 + kkp * slices

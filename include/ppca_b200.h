@@ -77,7 +77,10 @@ int32_t ppca_b200_ctx_set_chunk(ppca_b200_ctx *ctx, int64_t chunk_samples);
  *            digit planes (int8) of the FP64 operand, int32 accumulation (exact), FP64 recombination.  slices in
  *            {6,7,8} keep every term to 46 / 54 / 62 bits below its column scale (6: below FP64 dot-product
  *            rounding; 7: every FP64 input exactly).  mma.sync IMMA.
- *   mode 2 = the same arithmetic on tcgen05.mma.kind::i8 with the accumulators in tensor memory.
+ *   mode 2 = the same arithmetic on tcgen05.mma.kind::i8 with the accumulators in tensor memory.  slices = 4 is
+ *            accepted in this mode only: the opt-in FP32-class FAST PATH (30 bits below each column scale, ~1e-9 per
+ *            term: iterates agree with the FP64 path to ~1e-6, inside the 1e-4 the FP32 path is allowed) at two
+ *            thirds of the tensor work and digit-plane bytes.
  * Default: mode 2 with 6 slices; the environment overrides it: PPCA_B200_GEMM=dmma|int8|tc, PPCA_B200_SLICES=6|7|8. */
 int32_t ppca_b200_ctx_set_gemm(ppca_b200_ctx *ctx, int32_t mode, int32_t slices);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */

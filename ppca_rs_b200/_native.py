@@ -185,7 +185,7 @@ class Context:
 
     def set_gemm(self, mode: str, slices: int = 6) -> None:
         """'dmma' (FP64 tensor cores), 'int8' (exact int8-sliced evaluation on mma.sync) or 'tc' (the same on
-        tcgen05 with TMEM accumulators); see include/ppca_b200.h."""
+        tcgen05 with TMEM accumulators); see include/ppca_b200.h.  slices=4 with 'tc' is the FP32-class fast path."""
         check(lib().ppca_b200_ctx_set_gemm(self._h, {"dmma": 0, "int8": 1, "tc": 2}[mode], int(slices)))
 
     def launch_count(self) -> int:

@@ -779,7 +779,7 @@ int32_t ppca_b200_ctx_create(int32_t device, void *cuda_stream, ppca_b200_ctx **
       ctx->gemm_mode = (strcmp(e, "int8") == 0) ? 1 : (strcmp(e, "dmma") == 0 ? 0 : 2);
     if (const char *e = getenv("PPCA_B200_SLICES")) {
       const int t = atoi(e);
-      if (t >= 6 && t <= 8) ctx->slices = t;
+      if ((t >= 6 && t <= 8) || (t == 4 && ctx->gemm_mode == 2)) ctx->slices = t;
     }
     if (cuda_stream) {
       ctx->stream = (cudaStream_t)cuda_stream;
@@ -835,7 +835,8 @@ int32_t ppca_b200_ctx_set_gemm(ppca_b200_ctx *ctx, int32_t mode, int32_t slices)
   return guarded([&] {
     REQUIRE(ctx != nullptr, "null context");
     REQUIRE(mode >= 0 && mode <= 2, "gemm mode must be 0 (dmma), 1 (int8 on mma.sync) or 2 (int8 on tcgen05)");
-    REQUIRE(slices >= 6 && slices <= 8, "slices must be 6, 7 or 8");
+    REQUIRE((slices >= 6 && slices <= 8) || (slices == 4 && mode == 2),
+            "slices must be 6, 7 or 8 (or 4, the FP32-class fast path, with the tcgen05 mode)");
     ctx->gemm_mode = mode;
     ctx->slices = slices;
   });

@@ -833,10 +833,11 @@ void launch_slice_tc(const Launcher &L, const double *Bmat, int64_t ldb, int K, 
     ++*L.launch_counter;
   }
   dim3 grid(qtiles, (kblocks32 + 3) / 4);
-  if (T == 6) slice_tc_kernel<6><<<grid, 128, 0, L.stream>>>(Bmat, ldb, K, Nq, kblocks32, cm, q, scale);
+  if (T == 4) slice_tc_kernel<4><<<grid, 128, 0, L.stream>>>(Bmat, ldb, K, Nq, kblocks32, cm, q, scale);
+  else if (T == 6) slice_tc_kernel<6><<<grid, 128, 0, L.stream>>>(Bmat, ldb, K, Nq, kblocks32, cm, q, scale);
   else if (T == 7) slice_tc_kernel<7><<<grid, 128, 0, L.stream>>>(Bmat, ldb, K, Nq, kblocks32, cm, q, scale);
   else if (T == 8) slice_tc_kernel<8><<<grid, 128, 0, L.stream>>>(Bmat, ldb, K, Nq, kblocks32, cm, q, scale);
-  else PPCA_THROW(PPCA_ERR_INVALID, "int8 path: T must be 6, 7 or 8 (got %d)", T);
+  else PPCA_THROW(PPCA_ERR_INVALID, "tcgen05 int8 path: T must be 4, 6, 7 or 8 (got %d)", T);
   CUDA_CHECK(cudaGetLastError());
   ++*L.launch_counter;
 }
@@ -915,7 +916,8 @@ void launch_tbitgemm(const Launcher &L, const uint32_t *bits, int64_t ldbits, in
   a.bits = bits; a.ldbits = ldbits; a.nwords = nwords; a.Bq = Bq; a.scale = scale; a.Out = Out; a.ldo = ldo;
   a.M = M; a.Nq = Nq; a.ksteps = ksteps; a.accumulate = accumulate; a.partials = partials; a.splitk = splitk;
   a.defer_reduce = defer_reduce;
-  if (T == 6) launch_tb<6>(L, a);
+  if (T == 4) launch_tb<4>(L, a);
+  else if (T == 6) launch_tb<6>(L, a);
   else if (T == 7) launch_tb<7>(L, a);
   else if (T == 8) launch_tb<8>(L, a);
   else PPCA_THROW(PPCA_ERR_INVALID, "int8 path: T must be 6, 7 or 8 (got %d)", T);

@@ -587,6 +587,30 @@ def test_int8_sliced_iterate(pk, orc, int8_ctx, mode, slices, n, d, k, p):
         C, mu, s = Cw, muw, sw
 
 
+@pytest.mark.parametrize("n,d,k,p", [(777, 37, 5, 0.3), (3000, 200, 16, 0.2), (1200, 150, 32, 0.25), (500, 260, 64, 0.3)])
+def test_fp32_class_fast_path(pk, orc, int8_ctx, n, d, k, p):
+    """The opt-in fast path (4 digit planes on tcgen05): BASELINE.json north_star allows 1e-4 relative for the FP32
+    path on per-iteration llk, C, mu, sigma^2; masks and observed slots of extrapolate stay bit-identical."""
+    X, C0, mu0, s0 = _case(n, d, k, p, seed=61)
+    int8_ctx.set_gemm("tc", 4)
+    ds = pk.Dataset(X)
+    C, mu, s = C0, mu0, s0
+    for _ in range(3):
+        new, llk = pk.PPCAModel(s, C, mu)._iterate(ds, None)
+        with orc.stable():
+            Cw, muw, sw = orc.iterate(X, None, C, mu, s)
+            llkw = orc.llk(X, None, C, mu, s)
+        assert abs(llk - llkw) < 1e-4 * abs(llkw)
+        assert rel_err(new.transform, Cw) < 1e-4 and rel_err(new.mean, muw) < 1e-4
+        assert abs(new.isotropic_noise ** 2 - sw ** 2) < 1e-4 * sw ** 2
+        C, mu, s = Cw, muw, sw
+    ex = pk.PPCAModel(s, C, mu).extrapolate(ds).numpy()
+    fin = np.isfinite(X)
+    assert np.array_equal(ex[fin], X[fin]) and np.isfinite(ex).all()
+    with pytest.raises(Exception):
+        int8_ctx.set_gemm("int8", 4)          # the fast path exists on the tcgen05 mode only
+
+
 def test_int8_sliced_matches_dmma_closely(pk, int8_ctx):
     """Same inputs through both arithmetic paths: the int8-sliced statistics agree with DMMA to ~1e-13."""
     n, d, k = 20000, 200, 16

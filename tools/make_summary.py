@@ -103,7 +103,8 @@ The engine now takes as many rows per chunk as 8 GiB of workspace holds (at most
   reciprocals per pivot with the register file limiting the samples in flight (4 per SM at k=64).
 * Cross-moment / residual pass: FP64 DMMA-bound at k >= 16 (4dk flop per 8d bytes), 31-53 % of the DMMA peak.
 * Contractions at the c3 shape: 43 % (E) / 53 % (M) of the int8 peak; stage round-trip latency (4 stages) and the
-  mask expansion issue rate bound the main loop.  Full-sector (256-bit) epilogue stores were worth 9-21 % of the E-step.
+  mask expansion issue rate bound the main loop: the 4-plane fast path (a third less MMA work, `r01_bench_*_fastpath_T4.json`)
+  is only 1-3 % faster.  Next: one expanded mask stage feeding two 32-column output tiles.  Full-sector (256-bit) epilogue stores were worth 9-21 % of the E-step.
 """
     with open(os.path.join(P, "r01_summary.md"), "w") as f:
         f.write(txt)
