@@ -723,6 +723,308 @@ __global__ void __launch_bounds__(tb::THREADS_ATM, 1) tbitgemm_atm_kernel(TBitGe
   }
 }
 
+// Two 32-column output tiles per expanded mask stage ("Q2", the default for long K loops; PPCA_B200_TC_Q2=0 disables).  The fast-path experiment showed
+// the main loop is bound by the mask expansion / stage round trip, not by the tensor pipe (a third less MMA work
+// changed nothing), so here one A stage in tensor memory feeds TWO N = 32 T MMA groups: tile = 128 rows x 64 columns,
+// accumulators 2 x 32 T columns single-buffered (384 + 4 x 32 A columns = the 512 TMEM columns), the two digit-plane
+// tiles of a K step are adjacent in memory and arrive with one bulk copy.  Same roles and barriers as above.
+template <int T, int NGRP, int NEPI>
+__global__ void __launch_bounds__(tb::THREADS_ATM, 1) tbitgemm_atm2_kernel(TBitGemmArgs a) {
+  static_assert(32 * (4 * NGRP + 2 + 4 * NEPI) == tb::THREADS_ATM, "role split must add up to the CTA size");
+  using namespace tb;
+  constexpr int N = T * NQ;
+  // the A tile never touches shared memory here: producers write it to tensor memory (tcgen05.st), the MMA
+  // reads it from there, so shared memory only carries the digit-plane tile (write once, read once per K step)
+  constexpr int NQT = 2;  // 32-column output tiles per tile (sharing every A stage)
+  constexpr uint32_t B_BYTES = N * BKB, STAGE_BYTES = NQT * B_BYTES;
+  constexpr int ACOL = NQT * MH * N;  // first TMEM column of the A stages (32 columns = 128 K-bytes each)
+  static_assert(ACOL + 32 * STAGES <= 512, "A stages + the two accumulator tiles must fit the 512 TMEM columns");
+  constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  static_assert(MH == 1 && (STAGES & (STAGES - 1)) == 0, "producer groups assume one 128-row half and 2^n stages");
+  extern __shared__ unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * STAGES + 4];
+  __shared__ uint32_t tmem_base_slot;
+
+  // warps 0-3 / 4-7: two producer groups (alternate jobs; warp w writes TMEM lane quarter w & 3), warp 8: MMA issuer,
+  // warps 9-12: epilogue (quarters 1,2,3,0), warp 13: digit-plane loader
+  constexpr int MMA_WARP = 4 * NGRP, EPI_WARP0 = MMA_WARP + 1, LOAD_WARP = EPI_WARP0 + 4 * NEPI;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int b) { return bar0 + 8u * (2 * STAGES + b); };
+  auto tempty_bar = [&](int b) { return bar0 + 8u * (2 * STAGES + 2 + b); };
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), PRODUCERS / 32 + 1);  // one elected lane per producer warp + the bulk-copy issue
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull_bar(b), 1);
+      mbar_init(tempty_bar(b), 128 * NEPI);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == MMA_WARP) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                 "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  const int mtiles = (a.M + BM - 1) / BM, qtiles = (a.Nq + NQ - 1) / NQ;
+  const int qgroups = (qtiles + NQT - 1) / NQT;  // pairs of q tiles
+  const int ntiles = mtiles * qgroups * a.splitk;
+  const int ks_per = (a.ksteps + a.splitk - 1) / a.splitk;
+
+  if (warp < 4 * NGRP) {
+    // ===================== producers =====================
+    // The (tile, K step) jobs of this CTA form one sequence; producer group g = warp / 4 takes jobs j = g (mod NGRP).
+    // Per job every thread of the group expands its mask row (row = 32 (warp & 3) + lane = TMEM lane) to int8
+    // {0,1} in registers and writes the 128 bytes to the stage's tensor-memory columns with one tcgen05.st;
+    // tcgen05.wait::st, fence, arrive.  The 16 bytes of mask a thread needs per job are fetched DEPTH own jobs
+    // ahead with cp.async into a private shared-memory ring (mask rows are strided: latency, not bandwidth).
+    constexpr int DEPTH = ATM_DEPTH, RING = ATM_RING;
+    const int grp = warp >> 2, gt = tid & 127;  // group, thread within the group = row of the tile
+    uint32_t *ring = reinterpret_cast<uint32_t *>(smem_raw + (smem_base - smem_u32(smem_raw)) + STAGES * STAGE_BYTES) +
+                     grp * (RING * 128 * 4);
+    struct Cursor {
+      int tiles_left, tile, ks, ks_end;
+      const uint32_t *wrow;
+      bool row_ok;
+    };
+    auto open_tile = [&](Cursor &c) {
+      const int z = c.tile / (mtiles * qgroups), rem = c.tile % (mtiles * qgroups);
+      const int mt = rem % mtiles;
+      c.ks = z * ks_per;
+      c.ks_end = min(a.ksteps, c.ks + ks_per);
+      const int row = mt * BM + gt;
+      c.row_ok = row < a.M;
+      c.wrow = a.bits + (int64_t)(c.row_ok ? row : 0) * a.ldbits;
+    };
+    auto settle = [&](Cursor &c) {
+      while (c.tiles_left > 0 && c.ks >= c.ks_end) {
+        c.tile += gridDim.x;
+        if (--c.tiles_left > 0) open_tile(c);
+      }
+    };
+    auto step1 = [&](Cursor &c) {  // to the next job of the sequence
+      if (c.tiles_left > 0) {
+        ++c.ks;
+        settle(c);
+      }
+    };
+    auto step = [&](Cursor &c) {  // to this group's next job
+#pragma unroll
+      for (int g = 0; g < NGRP; ++g) step1(c);
+    };
+    auto start = [&](Cursor &c) {
+      c.tiles_left = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+      c.tile = blockIdx.x;
+      c.ks = c.ks_end = 0;
+      c.wrow = a.bits;
+      c.row_ok = false;
+      if (c.tiles_left > 0) open_tile(c);
+      settle(c);
+      if (grp == 1) step1(c);  // group 1 starts at job 1
+    };
+    auto fetch_words = [&](const Cursor &c, int slot) {  // 4 x 4-byte cp.async (mask rows are only 4-byte aligned)
+      const uint32_t dst = smem_u32(ring + (slot * 128 + gt) * 4);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int wi = 4 * c.ks + j;
+        const bool ok = c.tiles_left > 0 && c.row_ok && wi < a.nwords;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + 4 * j), "l"(ok ? c.wrow + wi : a.bits),
+                     "r"(ok ? 4 : 0));
+      }
+      asm volatile("cp.async.commit_group;" ::);
+    };
+    Cursor cp, cf;  // processing cursor, fetch cursor (DEPTH own jobs ahead)
+    start(cp);
+    start(cf);
+    int nf = 0;
+    for (; nf < DEPTH; ++nf) {
+      fetch_words(cf, nf % RING);
+      step(cf);
+    }
+    int job = grp, own = 0;
+    while (cp.tiles_left > 0) {
+      fetch_words(cf, nf % RING);
+      ++nf;
+      step(cf);
+      const int stage = job & (STAGES - 1);
+      const uint32_t phase = (uint32_t)(job / STAGES) & 1u;
+      mbar_wait_warp(empty_bar(stage), phase ^ 1u);
+      tc_fence_after();
+      asm volatile("cp.async.wait_group %0;" ::"n"(DEPTH) : "memory");  // this job's own mask words have landed
+      const uint4 wq = *reinterpret_cast<const uint4 *>(ring + ((own % RING) * 128 + gt) * 4);
+      const uint32_t wc[4] = {wq.x, wq.y, wq.z, wq.w};
+      uint32_t v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = nib4(wc[j >> 3], 4 * (j & 7));
+      tc_st32(tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(ACOL + 32 * stage), v);
+      tc_wait_st();
+      tc_fence_before();
+      // one arrive per warp: 128 lanes arriving on one mbarrier word serialise in the shared-memory pipe (ncu counted
+      // ~1e9 LSU bank conflicts per E-step launch, the same pipe the bulk copies and the mask ring use)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full_bar(stage));
+      step(cp);
+      job += NGRP;
+      ++own;
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+  } else if (warp == LOAD_WARP) {
+    // ===================== digit-plane loader =====================
+    // one thread streams the pre-swizzled digit-plane tiles with cp.async.bulk as soon as a stage is free,
+    // independently of the mask expansion (completion counted in bytes on the stage's "full" mbarrier)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int z = tile / (mtiles * qgroups), rem = tile % (mtiles * qgroups);
+        const int qt = NQT * (rem / mtiles);
+        const int ks_begin = z * ks_per, ks_end = min(a.ksteps, ks_begin + ks_per);
+        for (int ks = ks_begin; ks < ks_end; ++ks) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sB = smem_base + stage * STAGE_BYTES;
+          const int8_t *src = a.Bq + ((int64_t)ks * qtiles + qt) * (int64_t)B_BYTES;
+          const uint32_t nbytes = (qt + 1 < qtiles ? 2u : 1u) * B_BYTES;  // tiles (ks, qt) and (ks, qt + 1) are adjacent
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full_bar(stage)), "r"(nbytes)
+                       : "memory");
+          asm volatile(
+              "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sB),
+              "l"(src), "r"(nbytes), "r"(full_bar(stage))
+              : "memory");
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == MMA_WARP) {
+    // ===================== MMA issuer =====================
+    int stage = 0, buf = 0;
+    uint32_t phase = 0, tphase = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int z = tile / (mtiles * qgroups), rem = tile % (mtiles * qgroups);
+      const int ngroups = (NQT * (rem / mtiles) + 1 < qtiles) ? 2 : 1;  // the last pair may hold one q tile only
+      const int ks_begin = z * ks_per, ks_end = min(a.ksteps, ks_begin + ks_per);
+      mbar_wait_warp(tempty_bar(buf), tphase ^ 1u);
+      tc_fence_after();
+      const uint32_t tmem_c = tmem_base;
+      if (ks_begin >= ks_end) {  // empty K slab (never produced by the host-side split): publish immediately
+        if (lane == 0) tc_commit(tfull_bar(buf));
+        __syncwarp();
+      }
+      for (int ks = ks_begin; ks < ks_end; ++ks) {
+        mbar_wait_warp(full_bar(stage), phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sB = smem_base + stage * STAGE_BYTES;
+          const uint32_t tmem_a = tmem_base + (uint32_t)(ACOL + 32 * stage);
+          for (int g = 0; g < ngroups; ++g) {
+            const uint64_t bd = smem_desc_sw128(sB + g * B_BYTES);
+#pragma unroll
+            for (int k = 0; k < BKB / 32; ++k)
+              tc_mma_i8_ts(tmem_c + (uint32_t)(g * N), tmem_a + (uint32_t)(8 * k), bd + (uint64_t)(2 * k), IDESC,
+                           (ks > ks_begin || k > 0) ? 1u : 0u);
+          }
+          tc_commit(empty_bar(stage));
+          if (ks == ks_end - 1) tc_commit(tfull_bar(buf));
+        }
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+      tphase ^= 1u;  // one accumulator buffer: every tile flips the phase
+    }
+  } else {
+    // ===================== epilogue =====================
+    int buf = 0;
+    uint32_t tphase = 0;
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access (hardware rule: warp id mod 4)
+    const int cset = (warp - EPI_WARP0) >> 2;  // which NQ / NEPI column set of the tile this warp drains
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int z = tile / (mtiles * qgroups), rem = tile % (mtiles * qgroups);
+      const int qt0 = NQT * (rem / mtiles), mt = rem % mtiles;
+      const bool empty_slab = z * ks_per >= min(a.ksteps, z * ks_per + ks_per);
+      double *out;
+      int64_t ldo;
+      bool accumulate;
+      if (a.splitk > 1) {
+        out = a.partials + (int64_t)z * a.M * a.Nq;
+        ldo = a.Nq;
+        accumulate = a.defer_reduce != 0;
+      } else {
+        out = a.Out;
+        ldo = a.ldo;
+        accumulate = a.accumulate != 0;
+      }
+      mbar_wait_warp(tfull_bar(buf), tphase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int h = 0; h < NQT; ++h) {  // the two q tiles of this tile
+        const int qt = qt0 + h;
+        if (qt >= qtiles) break;
+        const int row = mt * BM + quarter * 32 + lane;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(h * N);
+#pragma unroll 1
+        for (int qc = cset * (NQ / 8 / NEPI); qc < (cset + 1) * (NQ / 8 / NEPI); ++qc) {
+          int rg[T][8];
+#pragma unroll
+          for (int t = 0; t < T; ++t) tc_ld8(taddr + (uint32_t)(t * NQ + 8 * qc), rg[t]);
+          tc_wait_ld();
+          const int q = qt * NQ + 8 * qc;
+          if (row < a.M && q < a.Nq) {
+            double v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              int d[T];
+#pragma unroll
+              for (int t = 0; t < T; ++t) d[t] = rg[t][j];
+              v[j] = empty_slab ? 0.0 : combine_planes<T>(d) * (a.scale[q + j] * combine_scale<T>());
+            }
+            // 32-byte accesses: a lane's 8 outputs are two full L2 sectors (16-byte stores wrote every sector twice)
+            double *p = out + (int64_t)row * ldo + q;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              if (accumulate) {
+                double o0, o1, o2, o3;
+                ld_global_256(p + 4 * j, o0, o1, o2, o3);
+                v[4 * j] += o0;
+                v[4 * j + 1] += o1;
+                v[4 * j + 2] += o2;
+                v[4 * j + 3] += o3;
+              }
+              st_global_256(p + 4 * j, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(buf));
+      tphase ^= 1u;  // one accumulator buffer: every tile flips the phase
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+  }
+}
+
+
 // ---------------------------------------------------------------------------------------------
 // digit planes: [kstep][qtile] tiles, each the exact SWIZZLE_128B shared-memory image of (T NQ rows) x 128 bytes
 // ---------------------------------------------------------------------------------------------
@@ -881,6 +1183,32 @@ static void launch_tb(const Launcher &L, const TBitGemmArgs &a) {
       static const int force = getenv("PPCA_B200_TC_ROLES") ? atoi(getenv("PPCA_B200_TC_ROLES")) : 0;
       const int ks_per = (a.ksteps + a.splitk - 1) / a.splitk;
       const bool drain = force ? force == 2 : ks_per <= 4;  // short K loops: epilogue-bound
+      if constexpr (2 * T * tb::NQ + 32 * tb::STAGES <= 512) {
+        // long K loops: two 32-column output tiles per expanded mask stage (tbitgemm_atm2_kernel; measured -13 % / -15 %
+        // on the c3 E-/M-step contraction); PPCA_B200_TC_Q2=0 keeps the one-tile kernel
+        static const bool q2 = !(getenv("PPCA_B200_TC_Q2") && atoi(getenv("PPCA_B200_TC_Q2")) == 0);
+        // ... when the halved tile count still fills the persistent grid (c2's M-step has 6 x 29 = 174 paired tiles
+        // for 148 CTAs: 59 % of the second round would idle, measured 0.35 vs 0.24 ms)
+        const int64_t qg_ = (round_up(a.Nq, tb::NQ) / tb::NQ + 1) / 2;
+        const int64_t t2_ = round_up(a.M, tb::BM) / tb::BM * qg_ * a.splitk;
+        const bool balanced = (double)t2_ >= 0.85 * (double)(round_up(t2_, L.sms));
+        if (q2 && !drain && a.Nq > tb::NQ && balanced) {
+          constexpr size_t SMEM_Q2 = (size_t)tb::STAGES * 2 * (T * tb::NQ * tb::BKB) + 1024 + 2 * tb::ATM_RING * 128 * 16;
+          static bool configured_q2 = false;
+          if (!configured_q2) {
+            CUDA_CHECK(cudaFuncSetAttribute(tbitgemm_atm2_kernel<T, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)SMEM_Q2));
+            configured_q2 = true;
+          }
+          const int64_t qg = (round_up(a.Nq, tb::NQ) / tb::NQ + 1) / 2;
+          const int64_t tiles2 = round_up(a.M, tb::BM) / tb::BM * qg * a.splitk;
+          const int grid2 = (int)(tiles2 < L.sms ? tiles2 : L.sms);
+          tbitgemm_atm2_kernel<T, 2, 1><<<grid2, tb::THREADS_ATM, SMEM_Q2, L.stream>>>(a);
+          CUDA_CHECK(cudaGetLastError());
+          ++*L.launch_counter;
+          return;
+        }
+      }
       if (drain) tbitgemm_atm_kernel<T, 1, 2><<<grid, tb::THREADS_ATM, SMEM_ATM, L.stream>>>(a);
       else tbitgemm_atm_kernel<T, 2, 1><<<grid, tb::THREADS_ATM, SMEM_ATM, L.stream>>>(a);
       CUDA_CHECK(cudaGetLastError());

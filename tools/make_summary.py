@@ -102,9 +102,12 @@ The engine now takes as many rows per chunk as 8 GiB of workspace holds (at most
 * Per-sample solve: 30 % (c2) to 36 % (c3) of the step, ~25 % of the FP64 peak; latency-bound chain of dependent
   reciprocals per pivot with the register file limiting the samples in flight (4 per SM at k=64).
 * Cross-moment / residual pass: FP64 DMMA-bound at k >= 16 (4dk flop per 8d bytes), 31-53 % of the DMMA peak.
-* Contractions at the c3 shape: 43 % (E) / 53 % (M) of the int8 peak; stage round-trip latency (4 stages) and the
-  mask expansion issue rate bound the main loop: the 4-plane fast path (a third less MMA work, `r01_bench_*_fastpath_T4.json`)
-  is only 1-3 % faster.  Next: one expanded mask stage feeding two 32-column output tiles.  Full-sector (256-bit) epilogue stores were worth 9-21 % of the E-step.
+* Contractions at the c3 shape: the 4-plane fast path (a third less MMA work, `r01_bench_*_fastpath_T4.json`) was only
+  1-3 % faster, i.e. the main loop is bound by the mask expansion / stage round trip, not the tensor pipe.  Acting on
+  that, `tbitgemm_atm2_kernel` feeds TWO 32-column output tiles from each expanded mask stage (single-buffered
+  accumulators, one bulk copy for both digit-plane tiles): E-step 13.6 -> 11.6 ms, M-step 11.1 -> 9.2 ms at c3s
+  (49 % / 64 % of the int8 peak; the c3s line above is measured with it, the 4M-row c3, c4s and c5 lines predate it).
+  Next: the same reuse across a CTA pair (`cta_group::2`) and a deeper A-stage ring.  Full-sector (256-bit) epilogue stores were worth 9-21 % of the E-step.
 """
     with open(os.path.join(P, "r01_summary.md"), "w") as f:
         f.write(txt)
