@@ -71,7 +71,10 @@ hbm = 6551 GB/s):
 |---|---|---|---|---|---|---|
 | c2 | {roofrow(c2)} |
 | c3 (4M rows) | {roofrow(c3)} |
+| c3s (two output tiles per mask stage) | {roofrow(c3s)} |
 | c4s | {roofrow(c4)} |
+
+(slice at or above 100 % of HBM: part of W is still L2-resident when it is sliced.)
 
 ## Roofline of the masked-Gram contraction (`tbitgemm_atm_kernel<6>`, tcgen05.mma.kind::i8, E- and M-step launches)
 
@@ -79,12 +82,13 @@ hbm = 6551 GB/s):
 |---|---|---|---|---|
 | c2 | {r(c2)['achieved']:.0f} | {100*r(c2)['frac']:.1f} % | {r(c2)['fp64_equivalent_tflops']:.0f} | {r(c2)['fp64_equivalent_frac']:.2f}x |
 | c3 (4M rows) | {r(c3)['achieved']:.0f} | {100*r(c3)['frac']:.1f} % | {r(c3)['fp64_equivalent_tflops']:.0f} | {r(c3)['fp64_equivalent_frac']:.2f}x |
+| c3s (`tbitgemm_atm2_kernel`: two output tiles per mask stage) | {r(c3s)['achieved']:.0f} | {100*r(c3s)['frac']:.1f} % | {r(c3s)['fp64_equivalent_tflops']:.0f} | {r(c3s)['fp64_equivalent_frac']:.2f}x |
 | c4s | {r(c4)['achieved']:.0f} | {100*r(c4)['frac']:.1f} % | {r(c4)['fp64_equivalent_tflops']:.0f} | {r(c4)['fp64_equivalent_frac']:.2f}x |
 
 c2 (k=16, d=200) is not tensor-bound: a tile is two K steps and 136 output columns, so the contraction is bounded by
 the FP64 recombination epilogue and the G write (DESIGN.md §3.1); the tensor fraction is meaningful at c3 (north star:
 >= 50 % of the FP64 tensor roofline on the masked-Gram contraction — the FP64 DMMA path `bitgemm_kernel` measures 84 %
-DMMA-pipe active, `r01_bitgemm_c3s_ncu_details.txt`; the default int8-sliced path does {r(c3)['fp64_equivalent_frac']:.1f}x that roofline in
+DMMA-pipe active, `r01_bitgemm_c3s_ncu_details.txt`; the default int8-sliced path does {r(c3s)['fp64_equivalent_frac']:.1f}x that roofline in
 FP64-equivalent work).  Whole-step FP64-equivalent throughput (SURVEY §8d F_iter) against the DMMA peak:
 c2 {100*r(c2)['whole_step_fp64_equivalent_frac']:.0f} %, c3 {100*r(c3)['whole_step_fp64_equivalent_frac']:.0f} %, c4s {100*r(c4)['whole_step_fp64_equivalent_frac']:.0f} %.
 
