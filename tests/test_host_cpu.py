@@ -295,3 +295,31 @@ def test_rust_ffi_declarations_are_in_sync_with_the_header(tmp_path):
     assert declared == bound
     subprocess.check_call([sys.executable, os.path.join(root, "tools", "gen_rust_ffi.py")], stdout=subprocess.DEVNULL)
     assert open(os.path.join(root, "bindings", "rust", "ppca_b200_sys.rs")).read() == committed
+
+
+def test_compat_alias_exposes_the_reference_module_names():
+    """compat.install_as_ppca_rs(): `from ppca_rs import ...` and `from ppca_rs.ppca_rs import ...` resolve to this package
+    (names of python/ppca_rs/__init__.py and of the pyO3 module, src/python_bindings.rs:15-26)."""
+    import importlib
+    import sys
+    import ppca_rs_b200 as pk
+    import ppca_rs_b200.compat as compat
+    saved = {k: sys.modules.pop(k) for k in ("ppca_rs", "ppca_rs.ppca_rs") if k in sys.modules}
+    try:
+        compat.install_as_ppca_rs()
+        top = importlib.import_module("ppca_rs")
+        native = importlib.import_module("ppca_rs.ppca_rs")
+        for name in ("Dataset", "PPCAModel", "PPCAMix", "Prior", "PPCATrainer", "PPCAMixTrainer", "DataFrameAdapter",
+                     "DataFrameAdapterDescription", "InferredMasked", "InferredMaskedMix"):
+            assert getattr(top, name) is getattr(pk, name)
+        for name in ("Dataset", "Prior", "PPCAModel", "PPCAMix", "InferredMasked", "InferredMaskedMix"):
+            assert getattr(native, name) is getattr(pk, name)
+        compat.install_as_ppca_rs()                     # idempotent on its own alias
+        sys.modules["ppca_rs"] = type(sys)("ppca_rs")   # a "real" module already imported: refuse to shadow it
+        with pytest.raises(ImportError):
+            compat.install_as_ppca_rs()
+        compat.install_as_ppca_rs(force=True)
+    finally:
+        for k in ("ppca_rs", "ppca_rs.ppca_rs"):
+            sys.modules.pop(k, None)
+        sys.modules.update(saved)
