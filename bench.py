@@ -229,7 +229,9 @@ def host_sample(wl, rows, seed):
     return X
 
 
-def cpu_step_time(wl, X, steps, warmup):
+def cpu_step_time(wl, X, steps, warmup, keep=None):
+    """Times `steps` CPU steps (llk + iterate) of the restated reference algorithm.  `keep` (a dict) receives the
+    log-likelihood of the initial model and the model after the FIRST step, for the parity block of the bench line."""
     from oracle import oracle as orc  # bench.py's cpu_baseline / reference leg only
     # the reference fans out on rayon's global pool = every host core; torchrun exports OMP_NUM_THREADS=1, undo that
     orc.set_num_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
@@ -239,20 +241,67 @@ def cpu_step_time(wl, X, steps, warmup):
         C, mu, s = init_params(d, k, SEED + 1000)
         for it in range(warmup + steps):
             t0 = time.perf_counter()
-            orc.llk(X, None, C, mu, s)            # python/ppca_rs/__init__.py:51
+            llk = orc.llk(X, None, C, mu, s)            # python/ppca_rs/__init__.py:51
             C, mu, s = orc.iterate(X, None, C, mu, s)  # :61-65
             if it >= warmup:
                 times.append(time.perf_counter() - t0)
+            if it == 0 and keep is not None:
+                keep.update(llk=llk, C=C.copy(), mu=mu.copy(), sigma=s)
     else:
         models = [init_params(d, k, SEED + 1000 + j) for j in range(m)]
         logw = np.full(m, -np.log(m))
         for it in range(warmup + steps):
             t0 = time.perf_counter()
-            orc.mix_llk(X, None, models, logw)
+            llk = orc.mix_llk(X, None, models, logw)
             models, logw = orc.mix_iterate(X, None, models, logw)
             if it >= warmup:
                 times.append(time.perf_counter() - t0)
+            if it == 0 and keep is not None:
+                keep.update(llk=llk, models=[(Cj.copy(), muj.copy(), sj) for Cj, muj, sj in models], logw=logw.copy())
     return times, orc.num_threads()
+
+
+PARITY_TOL = 1e-9   # BASELINE.json north_star: per-iteration llk, C, mu, sigma^2 within 1e-9 relative (FP64 path)
+
+
+def parity_block(pk, ds, wl, rows, keep):
+    """The GPU step on the SAME rows and initial model the CPU leg just ran (oracle/ as the checker only)."""
+    from oracle import oracle as orc
+    d, k, m = wl["d"], wl["k"], wl["m"]
+    sub = ds._slice(0, rows)
+
+    def rel(a, b):
+        a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+        return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+    X = sub.numpy()
+    if m == 1:
+        C0, mu0, s0 = init_params(d, k, SEED + 1000)
+        new, llk = pk.PPCAModel(s0, C0, mu0)._iterate(sub, None)
+        with orc.stable():   # the cancellation-free form of the same algebra (see oracle/ppca_oracle.c header)
+            Cs, mus, ss = orc.iterate(X, None, C0, mu0, s0)
+        out = {"max_rel_C": rel(new.transform, Cs), "max_rel_mu": rel(new.mean, mus),
+               "rel_sigma2": abs(new.isotropic_noise ** 2 - ss ** 2) / ss ** 2,
+               "rel_llk": abs(llk - keep["llk"]) / abs(keep["llk"]),
+               "vs_reference_order": {"max_rel_C": rel(new.transform, keep["C"]), "max_rel_mu": rel(new.mean, keep["mu"]),
+                                      "rel_sigma2": abs(new.isotropic_noise ** 2 - keep["sigma"] ** 2) / keep["sigma"] ** 2}}
+    else:
+        models = [init_params(d, k, SEED + 1000 + j) for j in range(m)]
+        mix = pk.PPCAMix([pk.PPCAModel(sg, Cj, muj) for Cj, muj, sg in models], np.zeros(m))
+        new, llk = mix._iterate(sub, None)
+        with orc.stable():
+            st_models, st_logw = orc.mix_iterate(X, None, models, np.full(m, -np.log(m)))
+        out = {"max_rel_C": max(rel(g.transform, w[0]) for g, w in zip(new.models, st_models)),
+               "max_rel_mu": max(rel(g.mean, w[1]) for g, w in zip(new.models, st_models)),
+               "rel_sigma2": max(abs(g.isotropic_noise ** 2 - w[2] ** 2) / w[2] ** 2 for g, w in zip(new.models, st_models)),
+               "max_abs_log_weights": float(np.max(np.abs(new.log_weights - st_logw))),
+               "rel_llk": abs(llk - keep["llk"]) / abs(keep["llk"])}
+    worst = max(v for kname, v in out.items() if isinstance(v, float))
+    out.update(rows=rows, tolerance=PARITY_TOL, ok=bool(worst < PARITY_TOL),
+               against="oracle/ppca_oracle.c on the same rows and initial model: C, mu, sigma^2 vs its cancellation-free "
+                       "('stable') form, llk vs the reference operation order; vs_reference_order adds the reference's own "
+                       "rounding noise (eps (|G|/sigma^2)^2)")
+    return out
 
 
 def run_reference(args, wl, rank):
@@ -505,12 +554,14 @@ def run_ours(args, wl, rank, world, local_rank):
         roofline["dominant_by_time"] = dict(timed[top], family=top)
 
     # ---- CPU baseline on a bounded sample of the same workload (rank 0, N=1 only) ----------------
-    cpu = None
+    cpu, parity = None, None
     if world == 1 and not args.no_cpu:
         rows = min(cpu_sample_rows(wl), n)
         X = np.empty((rows, d))
         nat.check(nat.lib().ppca_b200_dataset_to_host(ctx.handle, ds._h, 0, rows, nat.dptr(X)))
-        times, cores = cpu_step_time(wl, X, 1, 0)
+        keep = {}
+        times, cores = cpu_step_time(wl, X, 1, 0, keep)
+        parity = parity_block(pk, ds, wl, rows, keep)
         cpu = {"value": rows / times[0], "unit": "samples*iters/s", "cores": cores, "kind": "port",
                "sample": f"first {rows} rows of the GPU workload, 1 step of llk + iterate with the CPU restatement "
                          "of the reference's algorithm (oracle/ppca_oracle.c, OpenMP); Rust crate not buildable here"}
@@ -540,13 +591,16 @@ def run_ours(args, wl, rank, world, local_rank):
         "config": {"workload": f"{args.workload}: {wl['desc']}", "rows_per_gpu": n, "d": d, "k": k,
                    "components": m, "parallelism": f"sample-sharded x{world}, one NCCL all-reduce of the statistics per step",
                    "l2": "inputs larger than L2 (resident X per GPU = %.2f GB)" % (n * d * 8 / 1e9)},
-        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "ingest": ingest, "gpu_launches": int(launches),
-        "clocks": clocks.summary(),
+        "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "e2e": e2e, "ingest": ingest,
+        "gpu_launches": int(launches), "clocks": clocks.summary(),
     }
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+    if parity is not None and not parity["ok"]:
+        print("bench.py: GPU step differs from the oracle by more than %.0e: %s" % (PARITY_TOL, parity), file=sys.stderr)
+        sys.exit(3)
 
 
 # ------------------------------------------------------------------------------------------------

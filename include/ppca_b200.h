@@ -44,7 +44,10 @@ enum {
   PPCA_ERR_CUDA = 2,      /* CUDA runtime error or no device */
   PPCA_ERR_EMPTY = 3,     /* empty dataset where the reference asserts (ppca_model.rs:52,358) */
   PPCA_ERR_NUMERIC = 4,   /* singular system where the reference `expect`s (output_covariance.rs:69, prior.rs:109) */
-  PPCA_ERR_WEIGHTS = 5    /* mixture iterate needs strictly positive weights (mix.rs:304-309,326) */
+  PPCA_ERR_WEIGHTS = 5,   /* mixture iterate needs strictly positive weights (mix.rs:304-309,326) */
+  PPCA_ERR_PRECISION = 6  /* ppca_b200_em_finish only: the precision guard of the int8-sliced contractions fired on the
+                             (reduced) statistics and the context has moved to a wider arithmetic; repeat
+                             em_stats (+ the all-reduce) and em_finish.  Single-call entry points retry internally. */
 };
 
 /* prior.rs:8-29 Prior.  mean_precision is the inverse of the prior mean covariance (prior.rs:36-41),
@@ -69,6 +72,10 @@ int32_t ppca_b200_device_count(int32_t *out);
 int32_t ppca_b200_ctx_create(int32_t device, void *cuda_stream, ppca_b200_ctx **out);
 int32_t ppca_b200_ctx_destroy(ppca_b200_ctx *ctx);
 int32_t ppca_b200_ctx_synchronize(ppca_b200_ctx *ctx);
+/* The cudaStream_t every call of this context is enqueued on (the one passed to ctx_create, or the context's own).
+ * Asynchronous entry points (ppca_b200_em_stats*, ppca_b200_mix_em_stats) return while their kernels run: foreign
+ * work that touches their buffers (an NCCL all-reduce of the statistics) must be enqueued on, or ordered with, it. */
+int32_t ppca_b200_ctx_stream(ppca_b200_ctx *ctx, void **out);
 /* Tuning knob: samples per E/M-step chunk (0 = automatic). */
 int32_t ppca_b200_ctx_set_chunk(ppca_b200_ctx *ctx, int64_t chunk_samples);
 /* Arithmetic path of the two masked-Gram contractions (E-step Gram matrices, M-step second moments):
@@ -83,8 +90,24 @@ int32_t ppca_b200_ctx_set_chunk(ppca_b200_ctx *ctx, int64_t chunk_samples);
  *            thirds of the tensor work and digit-plane bytes.
  * Default: mode 2 with 6 slices; the environment overrides it: PPCA_B200_GEMM=dmma|int8|tc, PPCA_B200_SLICES=6|7|8. */
 int32_t ppca_b200_ctx_set_gemm(ppca_b200_ctx *ctx, int32_t mode, int32_t slices);
+/* Precision guard of the int8-sliced modes (on by default; never active in mode 0 or with 4 slices).  Every term of
+ * those contractions is kept to 8 slices - 2 bits below the largest entry of its COLUMN, so a sample (E-step) or an output
+ * dimension (M-step) that only sees entries far below that maximum loses relative accuracy.  The engine bounds the loss
+ * against the diagonal of the matrix it perturbs - terms(d_n) s_aa 2^-(8 slices - 1) <= 2^-eps_bits (sigma^2 + G_n[a][a])
+ * per sample, the analogue with sum_n m_ni W_n[a][a] per output dimension - and, when any entry fails, repeats the whole
+ * pass one rung up the ladder: configured slices -> 8 slices -> mode 0 (FP64 DMMA, the reference's own arithmetic).  The
+ * rung that was needed is kept for the context's next 16 passes.  eps_bits = 0 keeps the current value (default 40).
+ * Counter 13 of ppca_b200_ctx_variant_counts counts the repeated passes. */
+int32_t ppca_b200_ctx_set_guard(ppca_b200_ctx *ctx, int32_t enabled, int32_t eps_bits);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 int32_t ppca_b200_ctx_launch_count(ppca_b200_ctx *ctx, int64_t *out);
+/* Launches so far per shape-dependent kernel variant, 16 counters (tests assert which code path a case ran):
+ *   0 tbitgemm_kernel (A tile in shared memory, T = 7, 8)   1 tbitgemm_atm_kernel<T,2,1>   2 tbitgemm_atm_kernel<T,1,2>
+ *   3 tbitgemm_atm2_kernel (two output tiles per mask stage)  4 ibitgemm_kernel (IMMA)      5 bitgemm_kernel (DMMA)
+ *   6-8 solve_reg_kernel<8|16|32>   9 solve_split64_kernel   10 solve_reg64_kernel   11 solve_blk_kernel
+ *   12 solve_kernel (generic)   13 passes repeated at a wider arithmetic by the precision guard
+ *   14 batched mixture contraction launches   15 reserved */
+int32_t ppca_b200_ctx_variant_counts(ppca_b200_ctx *ctx, int64_t *out16);
 /* Device time accumulated since profiling was enabled (ppca_b200_ctx_set_profiling(ctx, 1) resets it), broken
  * down per kernel family, in ms; reading it synchronises the stream once, the profiled calls never do:
  * out[0]=model staging (Ksym, digit planes) out[1]=gram (masked contraction, E-step) out[2]=proj out[3]=solve

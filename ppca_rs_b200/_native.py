@@ -35,6 +35,9 @@ class CPrior(C.Structure):
     ]
 
 
+ERR_PRECISION = 6  # PPCA_ERR_PRECISION (include/ppca_b200.h)
+
+
 class NativeError(RuntimeError):
     """Raised where the reference panics (pyO3 PanicException) or returns a PyException."""
 
@@ -51,9 +54,12 @@ _PROTOTYPES = {
     "ppca_b200_ctx_create": (C.c_int32, [C.c_int32, C.c_void_p, C.POINTER(c_ctx_p)]),
     "ppca_b200_ctx_destroy": (C.c_int32, [c_ctx_p]),
     "ppca_b200_ctx_synchronize": (C.c_int32, [c_ctx_p]),
+    "ppca_b200_ctx_stream": (C.c_int32, [c_ctx_p, C.POINTER(C.c_void_p)]),
     "ppca_b200_ctx_set_chunk": (C.c_int32, [c_ctx_p, C.c_int64]),
     "ppca_b200_ctx_set_gemm": (C.c_int32, [c_ctx_p, C.c_int32, C.c_int32]),
+    "ppca_b200_ctx_set_guard": (C.c_int32, [c_ctx_p, C.c_int32, C.c_int32]),
     "ppca_b200_ctx_launch_count": (C.c_int32, [c_ctx_p, C.POINTER(C.c_int64)]),
+    "ppca_b200_ctx_variant_counts": (C.c_int32, [c_ctx_p, C.POINTER(C.c_int64)]),
     "ppca_b200_ctx_set_profiling": (C.c_int32, [c_ctx_p, C.c_int32]),
     "ppca_b200_ctx_last_profile": (C.c_int32, [c_ctx_p, c_dp]),
     "ppca_b200_dataset_from_host": (C.c_int32, [c_ctx_p, c_dp, C.c_int64, C.c_int32, c_dp, C.POINTER(c_ds_p)]),
@@ -180,6 +186,12 @@ class Context:
     def synchronize(self) -> None:
         check(lib().ppca_b200_ctx_synchronize(self._h))
 
+    def stream_handle(self) -> int:
+        """The cudaStream_t the context launches on (to order foreign work, e.g. an NCCL all-reduce, with it)."""
+        out = C.c_void_p()
+        check(lib().ppca_b200_ctx_stream(self._h, C.byref(out)))
+        return int(out.value or 0)
+
     def set_chunk(self, chunk: int) -> None:
         check(lib().ppca_b200_ctx_set_chunk(self._h, int(chunk)))
 
@@ -188,10 +200,25 @@ class Context:
         tcgen05 with TMEM accumulators); see include/ppca_b200.h.  slices=4 with 'tc' is the FP32-class fast path."""
         check(lib().ppca_b200_ctx_set_gemm(self._h, {"dmma": 0, "int8": 1, "tc": 2}[mode], int(slices)))
 
+    def set_guard(self, enabled: bool = True, eps_bits: int = 0) -> None:
+        """Precision guard + ladder of the int8-sliced contractions (include/ppca_b200.h: ppca_b200_ctx_set_guard)."""
+        check(lib().ppca_b200_ctx_set_guard(self._h, int(bool(enabled)), int(eps_bits)))
+
     def launch_count(self) -> int:
         out = C.c_int64(0)
         check(lib().ppca_b200_ctx_launch_count(self._h, C.byref(out)))
         return out.value
+
+    VARIANTS = ("tc_smem_a", "tc_atm_feed", "tc_atm_drain", "tc_atm2", "imma", "dmma", "solve_reg8", "solve_reg16",
+                "solve_reg32", "solve_split64", "solve_pair64", "solve_blk", "solve_generic", "precision_retry",
+                "tc_mix", "reserved15")
+
+    def variant_counts(self) -> Dict[str, int]:
+        """Launches so far per shape-dependent kernel variant (ppca_b200_ctx_variant_counts): lets a test assert
+        which contraction / solve kernel a case really ran."""
+        out = (C.c_int64 * 16)()
+        check(lib().ppca_b200_ctx_variant_counts(self._h, out))
+        return dict(zip(self.VARIANTS, [int(v) for v in out]))
 
     def set_profiling(self, enabled: bool) -> None:
         check(lib().ppca_b200_ctx_set_profiling(self._h, int(bool(enabled))))

@@ -30,9 +30,20 @@ struct ppca_b200_ctx {
   bool own_stream = false;
   int sms = 148;
   int64_t launches = 0;
+  int64_t variants[V_COUNT] = {0};
   int64_t chunk = 0;  // 0 = automatic
-  int gemm_mode = 2;  // 0 = DMMA, 1 = int8-sliced on mma.sync (ibitgemm.cu), 2 = int8-sliced on tcgen05 (tbitgemm.cu)
+  // arithmetic of the two masked-Gram contractions IN USE by the current pass: 0 = DMMA, 1 = int8-sliced on mma.sync
+  // (ibitgemm.cu), 2 = int8-sliced on tcgen05 (tbitgemm.cu).  base_* is what the caller configured; a pass starts at
+  // rung `rung` of the precision ladder (base -> 8 digit planes -> DMMA) and climbs when the guard fires (run_guarded).
+  int gemm_mode = 2;
   int slices = 6;
+  int base_mode = 2, base_slices = 6;
+  bool guard = true;     // PPCA_B200_GUARD=0 disables the precision guard (and with it the ladder)
+  int guard_bits = 40;   // eps = 2^-guard_bits: accepted perturbation of M_n / A_i relative to their diagonals
+  int rung = 0, rung_ttl = 0;
+  int64_t em_rows = 0;   // samples accumulated since em_begin (term count of the M-step guard)
+  DevBuf<unsigned int> unsafe;   // [0] E-step guard violations (solve kernels), [1] spare
+  DevBuf<double> WScaleMax;      // running maximum over chunks of the W column scales
   DevBuf<int8_t> KsymQ, WQ;
   DevBuf<double> KsymScale, WScale;
   DevBuf<unsigned long long> colmax;
@@ -65,7 +76,7 @@ struct ppca_b200_ctx {
   std::vector<Span> spans;
   double last_profile[FAM_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0};
 
-  Launcher L() { return Launcher{stream, &launches, sms}; }
+  Launcher L() { return Launcher{stream, &launches, sms, variants}; }
   double *pin(size_t count) {
     if (count > pinned_count) {
       if (pinned) cudaFreeHost(pinned);
@@ -214,6 +225,69 @@ int64_t pick_stream_block(ppca_b200_ctx *ctx, int64_t n_pad, const Shape &s) {
   return blk;
 }
 
+// ---- precision guard and ladder -----------------------------------------------------------------------------------
+// The int8-sliced contractions keep every term to 8T-2 bits below the maximum of its COLUMN; a sample (dimension) whose
+// own terms are much smaller than that maximum loses relative accuracy.  The solve kernels (E-step) and
+// mstep_guard_kernel (M-step) bound that loss against the diagonal of the matrix it perturbs and count violations;
+// when any is counted the whole pass is repeated one rung up: T -> 8 digit planes -> FP64 DMMA (which has the
+// reference's own FP64 semantics).  The rung that was needed is remembered for the next 16 passes of the context.
+struct Rung {
+  int mode, slices;
+};
+int ladder(const ppca_b200_ctx *ctx, Rung out[3]) {
+  int n = 0;
+  out[n++] = Rung{ctx->base_mode, ctx->base_slices};
+  if (ctx->guard && ctx->base_mode != 0 && ctx->base_slices != 4) {  // 4 planes = the opt-in FP32-class fast path
+    if (ctx->base_slices < 8) out[n++] = Rung{ctx->base_mode, 8};
+    out[n++] = Rung{0, ctx->base_slices};
+  }
+  return n;
+}
+bool guard_on(const ppca_b200_ctx *ctx) { return ctx->guard && ctx->gemm_mode != 0 && ctx->slices != 4; }
+double guard_coef(const ppca_b200_ctx *ctx) { return std::ldexp(1.0, ctx->guard_bits + 1 - 8 * ctx->slices); }
+void guard_reset(ppca_b200_ctx *ctx) {
+  ctx->unsafe.reserve(2);
+  CUDA_CHECK(cudaMemsetAsync(ctx->unsafe.p, 0, 2 * sizeof(unsigned int), ctx->stream));
+}
+// selects the arithmetic of the next pass from the remembered rung
+void begin_pass(ppca_b200_ctx *ctx) {
+  Rung r[3];
+  const int n = ladder(ctx, r);
+  if (ctx->rung >= n) ctx->rung = n - 1;
+  ctx->gemm_mode = r[ctx->rung].mode;
+  ctx->slices = r[ctx->rung].slices;
+  guard_reset(ctx);
+}
+// after a pass: true = accept; false = the caller must repeat it (the context has moved one rung up)
+bool end_pass(ppca_b200_ctx *ctx, double violations) {
+  Rung r[3];
+  const int n = ladder(ctx, r);
+  if (violations > 0.0 && ctx->rung + 1 < n) {
+    ++ctx->rung;
+    ctx->rung_ttl = 16;
+    ++ctx->variants[V_PRECISION_RETRY];
+    return false;
+  }
+  if (ctx->rung > 0 && --ctx->rung_ttl <= 0) ctx->rung = 0;
+  return true;
+}
+// E-step guard violations counted so far in this pass (synchronises the stream)
+double read_unsafe(ppca_b200_ctx *ctx) {
+  if (!guard_on(ctx)) return 0.0;
+  unsigned int h[2] = {0u, 0u};
+  CUDA_CHECK(cudaMemcpyAsync(h, ctx->unsafe.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  return (double)h[0] + (double)h[1];
+}
+// body() runs one complete pass and returns its violation count
+template <class Body>
+void run_guarded(ppca_b200_ctx *ctx, Body &&body) {
+  for (;;) {
+    begin_pass(ctx);
+    if (end_pass(ctx, body())) return;
+  }
+}
+
 // uploads (C, mu) and builds the padded model + Ksym table on the device
 DevModel stage_model(ppca_b200_ctx *ctx, int d, int k, const double *C, const double *mu, double sigma,
                      bool need_ksym = true) {
@@ -335,6 +409,11 @@ void e_step_chunk(ppca_b200_ctx *ctx, const SampleStore &st, const double *w, in
   sa.part = solve_part;
   sa.mode = mode;
   sa.colmax = w_colmax;
+  if (guard_on(ctx)) {
+    sa.gscale = ctx->KsymScale.p;
+    sa.guard_coef = guard_coef(ctx);
+    sa.unsafe = ctx->unsafe.p;
+  }
   if (w_colmax) CUDA_CHECK(cudaMemsetAsync(w_colmax, 0, sizeof(unsigned long long) * m.s.kkp, ctx->stream));
   ctx->span_begin(FAM_SOLVE);
   launch_solve(L, sa);
@@ -372,6 +451,11 @@ EmPlan em_begin(ppca_b200_ctx *ctx, int64_t chunk, const DevModel &m, double *st
     ctx->WScale.reserve((size_t)m.s.kkp);
     ctx->colmax.reserve((size_t)m.s.kkp);
   }
+  ctx->em_rows = 0;
+  if (guard_on(ctx)) {
+    ctx->WScaleMax.reserve((size_t)m.s.kkp);
+    CUDA_CHECK(cudaMemsetAsync(ctx->WScaleMax.p, 0, sizeof(double) * m.s.kkp, ctx->stream));
+  }
   ctx->part_bg.reserve(p.bglen);
   p.slabs = cross_resid_slabs(m.s.d, m.s.k, (int)p.chunk, ctx->sms);
   p.crlen = cross_resid_partials_len(m.s.d, m.s.k, p.slabs);
@@ -406,6 +490,8 @@ void em_chunk(ppca_b200_ctx *ctx, const SampleStore &st, const double *w, int64_
     launch_slice(L, ctx->GW.p, m.s.kkp, rows, m.s.kkp, kblocks, ctx->slices, ctx->WQ.p, ctx->WScale.p, ctx->colmax.p);
     ctx->span_end();
   }
+  ctx->em_rows += rows;
+  if (guard_on(ctx)) launch_scale_max(L, ctx->WScale.p, m.s.kkp, ctx->WScaleMax.p);
   ctx->span_begin(FAM_MOMENT);
   if (ctx->gemm_mode == 2) {
     const int ksteps = (kblocks + 3) / 4;
@@ -473,6 +559,12 @@ void em_end(ppca_b200_ctx *ctx, const DevModel &m, double *stats_dev, const EmPl
   launch_cross_resid_finish(L, m.s.d, m.s.k, ctx->part_cr.p, p.slabs, stats_dev + lay.offB, stats_dev + lay.offTdev,
                             stats_dev + lay.offTotals, stats_dev + lay.offScalars);
   ctx->span_end();
+  if (guard_on(ctx)) {  // scalars 5, 6: guard violations of this shard's E- and M-step contractions
+    ctx->span_begin(FAM_FINISH);
+    launch_mstep_guard(L, m.s.d, m.s.k, stats_dev + lay.offA, stats_dev + lay.offTotals, ctx->WScaleMax.p,
+                       guard_terms((double)ctx->em_rows) * guard_coef(ctx), ctx->unsafe.p, stats_dev + lay.offScalars);
+    ctx->span_end();
+  }
 }
 
 // E-step + local M-step statistics of a whole (local, resident) dataset into stats_dev
@@ -529,9 +621,10 @@ bool host_qr_solve(std::vector<double> &A, int n, std::vector<double> &b) {
 }
 
 // M-step finish from (reduced) statistics
-void em_finish_impl(ppca_b200_ctx *ctx, int d, int k, const double *C, const double *mu, double sigma,
-                    const ppca_b200_prior *prior, const double *stats_dev, double *C_out, double *mu_out,
-                    double *sigma_out, double *llk_in, double *sumw_out) {
+// returns the precision-guard violations carried by the (reduced) statistics
+double em_finish_impl(ppca_b200_ctx *ctx, int d, int k, const double *C, const double *mu, double sigma,
+                      const ppca_b200_prior *prior, const double *stats_dev, double *C_out, double *mu_out,
+                      double *sigma_out, double *llk_in, double *sumw_out) {
   REQUIRE(C && mu && C_out && mu_out && sigma_out, "null model parameters");
   const Shape s(d, k);
   const StatsLayout lay(d, k);
@@ -593,6 +686,7 @@ void em_finish_impl(ppca_b200_ctx *ctx, int d, int k, const double *C, const dou
   *sigma_out = std::sqrt(noise_sq);  // :389
   if (llk_in) *llk_in = sc[SC_LLK];
   if (sumw_out) *sumw_out = sc[SC_SUMW];
+  return sc[SC_UNSAFE_E] + sc[SC_UNSAFE_M];
 }
 
 void check_ds(const ppca_b200_ctx *ctx, const ppca_b200_dataset *ds) {
@@ -781,6 +875,13 @@ int32_t ppca_b200_ctx_create(int32_t device, void *cuda_stream, ppca_b200_ctx **
       const int t = atoi(e);
       if ((t >= 6 && t <= 8) || (t == 4 && ctx->gemm_mode == 2)) ctx->slices = t;
     }
+    ctx->base_mode = ctx->gemm_mode;
+    ctx->base_slices = ctx->slices;
+    if (const char *e = getenv("PPCA_B200_GUARD")) ctx->guard = atoi(e) != 0;
+    if (const char *e = getenv("PPCA_B200_GUARD_BITS")) {
+      const int b = atoi(e);
+      if (b >= 8 && b <= 52) ctx->guard_bits = b;
+    }
     if (cuda_stream) {
       ctx->stream = (cudaStream_t)cuda_stream;
       ctx->own_stream = false;
@@ -823,6 +924,13 @@ int32_t ppca_b200_ctx_synchronize(ppca_b200_ctx *ctx) {
   });
 }
 
+int32_t ppca_b200_ctx_stream(ppca_b200_ctx *ctx, void **out) {
+  return guarded([&] {
+    REQUIRE(ctx != nullptr && out != nullptr, "null argument");
+    *out = (void *)ctx->stream;
+  });
+}
+
 int32_t ppca_b200_ctx_set_chunk(ppca_b200_ctx *ctx, int64_t chunk_samples) {
   return guarded([&] {
     REQUIRE(ctx != nullptr, "null context");
@@ -837,8 +945,19 @@ int32_t ppca_b200_ctx_set_gemm(ppca_b200_ctx *ctx, int32_t mode, int32_t slices)
     REQUIRE(mode >= 0 && mode <= 2, "gemm mode must be 0 (dmma), 1 (int8 on mma.sync) or 2 (int8 on tcgen05)");
     REQUIRE((slices >= 6 && slices <= 8) || (slices == 4 && mode == 2),
             "slices must be 6, 7 or 8 (or 4, the FP32-class fast path, with the tcgen05 mode)");
-    ctx->gemm_mode = mode;
-    ctx->slices = slices;
+    ctx->gemm_mode = ctx->base_mode = mode;
+    ctx->slices = ctx->base_slices = slices;
+    ctx->rung = ctx->rung_ttl = 0;
+  });
+}
+
+int32_t ppca_b200_ctx_set_guard(ppca_b200_ctx *ctx, int32_t enabled, int32_t eps_bits) {
+  return guarded([&] {
+    REQUIRE(ctx != nullptr, "null context");
+    REQUIRE(eps_bits == 0 || (eps_bits >= 8 && eps_bits <= 52), "eps_bits must be 0 (keep) or in [8, 52]");
+    ctx->guard = enabled != 0;
+    if (eps_bits) ctx->guard_bits = eps_bits;
+    ctx->rung = ctx->rung_ttl = 0;
   });
 }
 
@@ -846,6 +965,13 @@ int32_t ppca_b200_ctx_launch_count(ppca_b200_ctx *ctx, int64_t *out) {
   return guarded([&] {
     REQUIRE(ctx != nullptr && out != nullptr, "null argument");
     *out = ctx->launches;
+  });
+}
+
+int32_t ppca_b200_ctx_variant_counts(ppca_b200_ctx *ctx, int64_t *out16) {
+  return guarded([&] {
+    REQUIRE(ctx != nullptr && out16 != nullptr, "null argument");
+    for (int i = 0; i < V_COUNT; ++i) out16[i] = ctx->variants[i];
   });
 }
 
@@ -1090,8 +1216,16 @@ int32_t ppca_b200_dataset_slice(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds,
     std::unique_ptr<ppca_b200_dataset> nd(make_dataset(ctx, st, nullptr));
     if (nrows > 0)
       CUDA_CHECK(cudaMemcpyAsync(nd->w.p, ds->w.p + row0, sizeof(double) * nrows, cudaMemcpyDeviceToDevice, ctx->stream));
-    nd->min_w = ds->min_w;
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    // smallest weight OF THE SLICE (mixture EM rejects non-positive weights, mix.rs:304-309): the parent's minimum
+    // may sit outside this row range
+    double mn = std::numeric_limits<double>::infinity();
+    if (nrows > 0) {
+      std::vector<double> hw((size_t)nrows);
+      CUDA_CHECK(cudaMemcpy(hw.data(), ds->w.p + row0, sizeof(double) * nrows, cudaMemcpyDeviceToHost));
+      for (int64_t i = 0; i < nrows; ++i) mn = hw[i] < mn ? hw[i] : (hw[i] != hw[i] ? -1.0 : mn);
+    }
+    nd->min_w = mn;
     *out = nd.release();
   });
 }
@@ -1146,11 +1280,14 @@ int32_t ppca_b200_llks(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int32_t 
     if (st.n == 0) return;
     REQUIRE(out != nullptr, "null output");
     DeviceGuard g(ctx->device);
-    DevModel m = stage_model(ctx, st.d, k, C, mu, sigma);
-    ctx->rbuf.reserve((size_t)st.n_pad);
-    llks_impl(ctx, st, m, ctx->rbuf.p);
-    CUDA_CHECK(cudaMemcpyAsync(out, ctx->rbuf.p, sizeof(double) * st.n, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    run_guarded(ctx, [&] {
+      DevModel m = stage_model(ctx, st.d, k, C, mu, sigma);
+      ctx->rbuf.reserve((size_t)st.n_pad);
+      llks_impl(ctx, st, m, ctx->rbuf.p);
+      CUDA_CHECK(cudaMemcpyAsync(out, ctx->rbuf.p, sizeof(double) * st.n, cudaMemcpyDeviceToHost, ctx->stream));
+      CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+      return read_unsafe(ctx);
+    });
   });
 }
 
@@ -1165,22 +1302,25 @@ int32_t ppca_b200_llk(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int32_t k
       return;
     }
     DeviceGuard g(ctx->device);
-    DevModel m = stage_model(ctx, st.d, k, C, mu, sigma);
-    const int64_t chunk = pick_chunk(ctx, st.n_pad, m.s);
-    reserve_chunk_ws(ctx, chunk, m.s);
-    ctx->stats.reserve(8);
-    ctx->part_solve.reserve((size_t)SOLVE_SLOTS * 4);
-    CUDA_CHECK(cudaMemsetAsync(ctx->stats.p, 0, sizeof(double) * 8, ctx->stream));
-    CUDA_CHECK(cudaMemsetAsync(ctx->part_solve.p, 0, sizeof(double) * SOLVE_SLOTS * 4, ctx->stream));
-    for (int64_t row0 = 0; row0 < st.n; row0 += chunk) {
-      const int rows = (int)((st.n - row0) < chunk ? (st.n - row0) : chunk);
-      e_step_chunk(ctx, st, ds->w.p, row0, rows, m, 0, ctx->llk.p, nullptr, ctx->part_solve.p);
-    }
-    launch_solve_finish(ctx->L(), ctx->part_solve.p, ctx->stats.p);
-    double h[8];
-    CUDA_CHECK(cudaMemcpyAsync(h, ctx->stats.p, sizeof(double) * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-    *out = h[SC_LLK];
+    run_guarded(ctx, [&] {
+      DevModel m = stage_model(ctx, st.d, k, C, mu, sigma);
+      const int64_t chunk = pick_chunk(ctx, st.n_pad, m.s);
+      reserve_chunk_ws(ctx, chunk, m.s);
+      ctx->stats.reserve(8);
+      ctx->part_solve.reserve((size_t)SOLVE_SLOTS * 4);
+      CUDA_CHECK(cudaMemsetAsync(ctx->stats.p, 0, sizeof(double) * 8, ctx->stream));
+      CUDA_CHECK(cudaMemsetAsync(ctx->part_solve.p, 0, sizeof(double) * SOLVE_SLOTS * 4, ctx->stream));
+      for (int64_t row0 = 0; row0 < st.n; row0 += chunk) {
+        const int rows = (int)((st.n - row0) < chunk ? (st.n - row0) : chunk);
+        e_step_chunk(ctx, st, ds->w.p, row0, rows, m, 0, ctx->llk.p, nullptr, ctx->part_solve.p);
+      }
+      launch_solve_finish(ctx->L(), ctx->part_solve.p, ctx->stats.p);
+      double h[8];
+      CUDA_CHECK(cudaMemcpyAsync(h, ctx->stats.p, sizeof(double) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+      CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+      *out = h[SC_LLK];
+      return read_unsafe(ctx);
+    });
   });
 }
 
@@ -1192,6 +1332,7 @@ int32_t ppca_b200_infer(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int32_t
     if (st.n == 0) return;
     REQUIRE(states != nullptr, "null output");
     DeviceGuard g(ctx->device);
+    run_guarded(ctx, [&] {
     DevModel m = stage_model(ctx, st.d, k, C, mu, sigma);
     int64_t chunk = pick_chunk(ctx, st.n_pad, m.s);
     if (covariances) {  // bound the k x k covariance staging buffer to ~1 GiB
@@ -1216,6 +1357,8 @@ int32_t ppca_b200_infer(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int32_t
                                    cudaMemcpyDeviceToHost, ctx->stream));
       CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     }
+    return read_unsafe(ctx);
+    });
   });
 }
 
@@ -1228,8 +1371,11 @@ static int32_t smooth_or_extrapolate(ppca_b200_ctx *ctx, const ppca_b200_dataset
     DeviceGuard g(ctx->device);
     auto ost = make_store(ctx, st.n, st.d);
     if (st.n > 0) {
-      DevModel m = stage_model(ctx, st.d, k, C, mu, sigma);
-      reconstruct_impl(ctx, st, m, extrapolate, nullptr, 0, 0, *ost);
+      run_guarded(ctx, [&] {
+        DevModel m = stage_model(ctx, st.d, k, C, mu, sigma);
+        reconstruct_impl(ctx, st, m, extrapolate, nullptr, 0, 0, *ost);
+        return read_unsafe(ctx);
+      });
       finalize_full_store(ctx, *ost);
     }
     std::unique_ptr<ppca_b200_dataset> nd(make_dataset(ctx, ost, nullptr));
@@ -1261,6 +1407,7 @@ int32_t ppca_b200_em_stats(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int3
     check_ds(ctx, ds);
     REQUIRE(stats_dev != nullptr, "null statistics buffer");
     DeviceGuard g(ctx->device);
+    begin_pass(ctx);
     DevModel m = stage_model(ctx, ds->store->d, k, C, mu, sigma);
     em_stats_impl(ctx, *ds->store, ds->w.p, m, stats_dev);
   });
@@ -1273,7 +1420,12 @@ int32_t ppca_b200_em_finish(ppca_b200_ctx *ctx, int32_t d, int32_t k, const doub
     REQUIRE(ctx != nullptr && stats_dev != nullptr, "null argument");
     REQUIRE(d >= 1 && k >= 1, "bad shape");
     DeviceGuard g(ctx->device);
-    em_finish_impl(ctx, d, k, C, mu, sigma, prior, stats_dev, C_out, mu_out, sigma_out, llk_in, nullptr);
+    const double viol = em_finish_impl(ctx, d, k, C, mu, sigma, prior, stats_dev, C_out, mu_out, sigma_out, llk_in, nullptr);
+    if (!end_pass(ctx, viol))
+      PPCA_THROW(PPCA_ERR_PRECISION,
+                 "precision guard: %.0f entries of the int8-sliced contractions lost accuracy against their column "
+                 "scale; the context now uses a wider arithmetic - repeat em_stats, the all-reduce and em_finish",
+                 viol);
   });
 }
 
@@ -1285,10 +1437,12 @@ int32_t ppca_b200_iterate(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int32
     const SampleStore &st = *ds->store;
     if (st.n == 0) PPCA_THROW(PPCA_ERR_EMPTY, "non-empty dataset required (ppca_model.rs:358)");
     DeviceGuard g(ctx->device);
-    DevModel m = stage_model(ctx, st.d, k, C, mu, sigma);
-    ctx->stats.reserve((size_t)StatsLayout(st.d, k).len);
-    em_stats_impl(ctx, st, ds->w.p, m, ctx->stats.p);
-    em_finish_impl(ctx, st.d, k, C, mu, sigma, prior, ctx->stats.p, C_out, mu_out, sigma_out, llk_in, nullptr);
+    run_guarded(ctx, [&] {
+      DevModel m = stage_model(ctx, st.d, k, C, mu, sigma);
+      ctx->stats.reserve((size_t)StatsLayout(st.d, k).len);
+      em_stats_impl(ctx, st, ds->w.p, m, ctx->stats.p);
+      return em_finish_impl(ctx, st.d, k, C, mu, sigma, prior, ctx->stats.p, C_out, mu_out, sigma_out, llk_in, nullptr);
+    });
   });
 }
 
@@ -1382,6 +1536,7 @@ int32_t ppca_b200_em_stats_host(ppca_b200_ctx *ctx, const double *x, int64_t n, 
     REQUIRE(n >= 0 && d >= 1, "bad dataset shape %lld x %d", (long long)n, d);
     REQUIRE(n == 0 || x != nullptr, "null data");
     DeviceGuard g(ctx->device);
+    begin_pass(ctx);
     DevModel m = stage_model(ctx, d, k, C, mu, sigma);
     if (n == 0) {
       CUDA_CHECK(cudaMemsetAsync(stats_dev, 0, sizeof(double) * StatsLayout(d, k).len, ctx->stream));
@@ -1401,10 +1556,12 @@ int32_t ppca_b200_iterate_host(ppca_b200_ctx *ctx, const double *x, int64_t n, i
     if (n == 0) PPCA_THROW(PPCA_ERR_EMPTY, "non-empty dataset required (ppca_model.rs:358)");
     REQUIRE(x != nullptr, "null data");
     DeviceGuard g(ctx->device);
-    DevModel m = stage_model(ctx, d, k, C, mu, sigma);
-    ctx->stats.reserve((size_t)StatsLayout(d, k).len);
-    em_stats_host_impl(ctx, x, n, d, weights, m, ctx->stats.p);
-    em_finish_impl(ctx, d, k, C, mu, sigma, prior, ctx->stats.p, C_out, mu_out, sigma_out, llk_in, nullptr);
+    run_guarded(ctx, [&] {
+      DevModel m = stage_model(ctx, d, k, C, mu, sigma);
+      ctx->stats.reserve((size_t)StatsLayout(d, k).len);
+      em_stats_host_impl(ctx, x, n, d, weights, m, ctx->stats.p);
+      return em_finish_impl(ctx, d, k, C, mu, sigma, prior, ctx->stats.p, C_out, mu_out, sigma_out, llk_in, nullptr);
+    });
   });
 }
 
@@ -1433,6 +1590,7 @@ int32_t ppca_b200_reconstruct_host(ppca_b200_ctx *ctx, const double *x, int64_t 
         CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_outfree[b], cudaEventDisableTiming));
       }
     }
+    run_guarded(ctx, [&] {
     DevModel m = stage_model(ctx, d, k, C, mu, sigma);
     const int64_t blk = pick_stream_block(ctx, round_up(n, 256), m.s);
     reserve_chunk_ws(ctx, blk, m.s);
@@ -1478,6 +1636,8 @@ int32_t ppca_b200_reconstruct_host(ppca_b200_ctx *ctx, const double *x, int64_t 
     }
     CUDA_CHECK(cudaStreamSynchronize(ctx->out_stream));
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    return read_unsafe(ctx);
+    });
   });
 }
 
@@ -1558,9 +1718,12 @@ int32_t ppca_b200_mix_llks(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int3
     DevBuf<double> &LP = ctx->mixLP, &ml = ctx->mixLlk;
     LP.reserve((size_t)st.n * m);
     ml.reserve((size_t)st.n);
-    mix_posteriors_impl(ctx, ds, mv, LP.p, ml.p, nullptr, nullptr);
-    CUDA_CHECK(cudaMemcpyAsync(out, ml.p, sizeof(double) * st.n, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    run_guarded(ctx, [&] {
+      mix_posteriors_impl(ctx, ds, mv, LP.p, ml.p, nullptr, nullptr);
+      CUDA_CHECK(cudaMemcpyAsync(out, ml.p, sizeof(double) * st.n, cudaMemcpyDeviceToHost, ctx->stream));
+      CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+      return read_unsafe(ctx);
+    });
   });
 }
 
@@ -1582,9 +1745,12 @@ int32_t ppca_b200_mix_llk(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int32
     LP.reserve((size_t)st.n * m);
     ml.reserve((size_t)st.n);
     sum.reserve(1);
-    mix_posteriors_impl(ctx, ds, mv, LP.p, ml.p, nullptr, sum.p);
-    CUDA_CHECK(cudaMemcpyAsync(out, sum.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    run_guarded(ctx, [&] {
+      mix_posteriors_impl(ctx, ds, mv, LP.p, ml.p, nullptr, sum.p);
+      CUDA_CHECK(cudaMemcpyAsync(out, sum.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+      CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+      return read_unsafe(ctx);
+    });
   });
 }
 
@@ -1601,9 +1767,12 @@ int32_t ppca_b200_mix_infer_cluster(ppca_b200_ctx *ctx, const ppca_b200_dataset 
     DeviceGuard g(ctx->device);
     DevBuf<double> &LP = ctx->mixLP;
     LP.reserve((size_t)st.n * m);
-    mix_posteriors_impl(ctx, ds, mv, LP.p, nullptr, nullptr, nullptr);
-    CUDA_CHECK(cudaMemcpyAsync(out, LP.p, sizeof(double) * st.n * m, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    run_guarded(ctx, [&] {
+      mix_posteriors_impl(ctx, ds, mv, LP.p, nullptr, nullptr, nullptr);
+      CUDA_CHECK(cudaMemcpyAsync(out, LP.p, sizeof(double) * st.n * m, cudaMemcpyDeviceToHost, ctx->stream));
+      CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+      return read_unsafe(ctx);
+    });
   });
 }
 
@@ -1626,16 +1795,19 @@ static int32_t mix_smooth_or_extrapolate(ppca_b200_ctx *ctx, const ppca_b200_dat
     if (st.n > 0) {
       DevBuf<double> &LP = ctx->mixLP;
       LP.reserve((size_t)st.n * m);
-      mix_posteriors_impl(ctx, ds, mv, LP.p, nullptr, nullptr, nullptr);
-      const int64_t total = st.n * m;
-      const int blocks = (int)((total + 255) / 256 < (int64_t)ctx->sms * 8 ? (total + 255) / 256 : (int64_t)ctx->sms * 8);
-      exp_inplace_kernel<<<blocks, 256, 0, ctx->stream>>>(LP.p, total);  // posterior() (mix.rs:366-368)
-      CUDA_CHECK(cudaGetLastError());
-      ++ctx->launches;
-      for (int j = 0; j < m; ++j) {  // sum_j posterior_j * (smoothed | extrapolated)_j  (mix.rs:397-414)
-        DevModel dm = stage_model(ctx, st.d, ks[j], mv.C(j), mv.mu(j), sigmas[j]);
-        reconstruct_impl(ctx, st, dm, extrapolate, LP.p + j, m, j > 0 ? 1 : 0, *ost);
-      }
+      run_guarded(ctx, [&] {
+        mix_posteriors_impl(ctx, ds, mv, LP.p, nullptr, nullptr, nullptr);
+        const int64_t total = st.n * m;
+        const int blocks = (int)((total + 255) / 256 < (int64_t)ctx->sms * 8 ? (total + 255) / 256 : (int64_t)ctx->sms * 8);
+        exp_inplace_kernel<<<blocks, 256, 0, ctx->stream>>>(LP.p, total);  // posterior() (mix.rs:366-368)
+        CUDA_CHECK(cudaGetLastError());
+        ++ctx->launches;
+        for (int j = 0; j < m; ++j) {  // sum_j posterior_j * (smoothed | extrapolated)_j  (mix.rs:397-414)
+          DevModel dm = stage_model(ctx, st.d, ks[j], mv.C(j), mv.mu(j), sigmas[j]);
+          reconstruct_impl(ctx, st, dm, extrapolate, LP.p + j, m, j > 0 ? 1 : 0, *ost);
+        }
+        return read_unsafe(ctx);
+      });
       finalize_full_store(ctx, *ost);
     }
     *out = make_dataset(ctx, ost, nullptr);  // weights reset to 1 (mix.rs:245-265)
@@ -1669,13 +1841,16 @@ int32_t ppca_b200_mix_posteriors(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds
     ml.reserve((size_t)std::max<int64_t>(st.n, 1));
     cm.reserve((size_t)m);
     sum.reserve(1);
-    CUDA_CHECK(cudaMemsetAsync(sum.p, 0, sizeof(double), ctx->stream));
-    mix_posteriors_impl(ctx, ds, mv, logpost_dev, ml.p, cm.p, st.n > 0 ? sum.p : nullptr);
-    double h = 0.0;
-    CUDA_CHECK(cudaMemcpyAsync(comp_max, cm.p, sizeof(double) * m, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_CHECK(cudaMemcpyAsync(&h, sum.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-    if (llk_in) *llk_in = h;
+    run_guarded(ctx, [&] {
+      CUDA_CHECK(cudaMemsetAsync(sum.p, 0, sizeof(double), ctx->stream));
+      mix_posteriors_impl(ctx, ds, mv, logpost_dev, ml.p, cm.p, st.n > 0 ? sum.p : nullptr);
+      double h = 0.0;
+      CUDA_CHECK(cudaMemcpyAsync(comp_max, cm.p, sizeof(double) * m, cudaMemcpyDeviceToHost, ctx->stream));
+      CUDA_CHECK(cudaMemcpyAsync(&h, sum.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+      CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+      if (llk_in) *llk_in = h;
+      return read_unsafe(ctx);
+    });
   });
 }
 
@@ -1688,6 +1863,7 @@ int32_t ppca_b200_mix_em_stats(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, 
     REQUIRE(j >= 0 && j < m, "component index out of range");
     const SampleStore &st = *ds->store;
     DeviceGuard g(ctx->device);
+    begin_pass(ctx);
     ctx->rbuf.reserve((size_t)st.n_pad);
     CUDA_CHECK(cudaMemsetAsync(ctx->rbuf.p, 0, sizeof(double) * st.n_pad, ctx->stream));
     launch_responsibilities(ctx->L(), logpost_dev, st.n, m, j, ds->w.p, comp_max_j, ctx->rbuf.p);
@@ -1718,12 +1894,15 @@ int32_t ppca_b200_mix_iterate(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, i
       const int kj = ks[j];
       DevBuf<double> &stats = ctx->mixStats;
       stats.reserve((size_t)StatsLayout(st.d, kj).len);
-      rc = ppca_b200_mix_em_stats(ctx, ds, m, j, kj, mv.C(j), mv.mu(j), sigmas[j], LP.p, cmax[j], stats.p);
-      if (rc) throw Error{rc, g_last_error};
       double sumw = 0.0;
       const size_t off = (size_t)(mv.C(j) - Cs);
-      em_finish_impl(ctx, st.d, kj, mv.C(j), mv.mu(j), sigmas[j], prior, stats.p, Cs_out + off,
-                     mus_out + (size_t)j * st.d, sigmas_out + j, nullptr, &sumw);
+      for (;;) {  // one guarded pass per component (ppca_b200_mix_em_stats starts at the remembered rung)
+        rc = ppca_b200_mix_em_stats(ctx, ds, m, j, kj, mv.C(j), mv.mu(j), sigmas[j], LP.p, cmax[j], stats.p);
+        if (rc) throw Error{rc, g_last_error};
+        const double viol = em_finish_impl(ctx, st.d, kj, mv.C(j), mv.mu(j), sigmas[j], prior, stats.p, Cs_out + off,
+                                           mus_out + (size_t)j * st.d, sigmas_out + j, nullptr, &sumw);
+        if (end_pass(ctx, viol)) break;
+      }
       logsum[j] = std::log(sumw) + cmax[j];  // mix.rs:323-324
     }
     // robust_log_softmax (mix.rs:14-18, :335)

@@ -237,16 +237,16 @@ size_t bitgemm_partials_len(int M, int Nq, int splitk) { return splitk > 1 ? (si
 
 template <class Cfg>
 static void launch_cfg(const Launcher &L, const BitGemmArgs &a) {
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.need()) {
     CUDA_CHECK(cudaFuncSetAttribute(bitgemm_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-    configured = true;
   }
   dim3 grid((unsigned)(round_up(a.M, Cfg::BM) / Cfg::BM), (unsigned)(round_up(a.Nq, Cfg::BN) / Cfg::BN),
             (unsigned)a.splitk);
   bitgemm_kernel<Cfg><<<grid, Cfg::THREADS, Cfg::SMEM, L.stream>>>(a);
   CUDA_CHECK(cudaGetLastError());
   ++*L.launch_counter;
+  L.count(V_DMMA);
 }
 
 void launch_bitgemm(const Launcher &L, const BitGemmArgs &a) {

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <memory>
 #include <string>
 #include <vector>
@@ -74,7 +75,7 @@ struct StatsLayout {
     len = offScalars + 8;
   }
 };
-enum { SC_SQERR = 0, SC_DEV2 = 1, SC_LLK = 2, SC_SUMW = 3, SC_NONEMPTY = 4 };
+enum { SC_SQERR = 0, SC_DEV2 = 1, SC_LLK = 2, SC_SUMW = 3, SC_NONEMPTY = 4, SC_UNSAFE_E = 5, SC_UNSAFE_M = 6 };
 
 // ---------------------------------------------------------------------------------------------
 // device buffers
@@ -139,10 +140,48 @@ struct DevModel {
   const double *Ksym;  // d32 x kkp  (zero padded rows and columns)
 };
 
+// Kernel variants whose selection depends on the shape: counted per context so that tests can assert which code path
+// a case actually ran (ppca_b200_ctx_variant_counts).
+enum Variant {
+  V_TC_SMEM_A = 0,   // tbitgemm_kernel<T>            (A tile in shared memory; T = 7, 8)
+  V_TC_ATM_FEED,     // tbitgemm_atm_kernel<T, 2, 1>  (A tile in tensor memory, two producer groups)
+  V_TC_ATM_DRAIN,    // tbitgemm_atm_kernel<T, 1, 2>  (short K loops, two epilogue sets)
+  V_TC_ATM2,         // tbitgemm_atm2_kernel<T, 2, 1> (two output tiles per expanded mask stage)
+  V_IMMA,            // ibitgemm_kernel
+  V_DMMA,            // bitgemm_kernel
+  V_SOLVE_REG8,
+  V_SOLVE_REG16,
+  V_SOLVE_REG32,
+  V_SOLVE_SPLIT64,
+  V_SOLVE_PAIR64,
+  V_SOLVE_BLK,
+  V_SOLVE_GENERIC,
+  V_PRECISION_RETRY,  // passes repeated at a wider arithmetic after the precision guard fired
+  V_TC_MIX,           // batched mixture contraction launches
+  V_RESERVED15,
+  V_COUNT
+};
+
 struct Launcher {
   cudaStream_t stream;
   int64_t *launch_counter;
   int sms;
+  int64_t *variants = nullptr;  // V_COUNT counters (nullable)
+  void count(int v) const {
+    if (variants) ++variants[v];
+  }
+};
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-device attribute: the guarded block runs once per
+// (call site, device), so contexts on several GPUs of one process each opt their kernels in.
+struct PerDeviceOnce {
+  std::atomic<unsigned long long> done{0};
+  bool need() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    return (done.fetch_or(bit) & bit) == 0;
+  }
 };
 
 // ---- kernels (host launchers) ----------------------------------------------------------------
@@ -213,7 +252,23 @@ struct SolveArgs {
   int mode;            // 0 = llk only, 1 = infer (z, cov), 2 = EM (z, W, wz, t)
   unsigned long long *colmax;  // kkp (nullable, mode 2, k <= 64; zeroed by the caller): atomicMax of the bit patterns
                                // of max_n |W[n][q]| — the column scales of the M-step digit planes, fused here
+  // Precision guard of the int8-sliced E-step contraction (null gscale = FP64 contraction, no guard).  G_n arrives with
+  // an error of at most terms(d_n) s_q 2^-(8T-1) per entry (s_q = power-of-two column scale of Ksym); the sample is
+  // accepted when, for every a, that bound on the DIAGONAL entry is below eps (sigma^2 + G_aa), i.e. the perturbation
+  // of M_n = sigma^2 I + G_n is small in the diagonally scaled sense under which its inverse / determinant are
+  // well conditioned (off-diagonal scales obey s_ab <= 2 sqrt(s_aa s_bb)).  Violations are counted in unsafe[0]; the
+  // host then repeats the pass at a wider arithmetic (api.cu, run_guarded).
+  const double *gscale = nullptr;  // kkp column scales of the Ksym digit planes
+  double guard_coef = 0.0;         // 2^-(8T-1) / eps
+  unsigned int *unsafe = nullptr;
 };
+// How many maximal quantisation errors e = s_q 2^-(8T-1) a sum of n terms can carry: all of them for short sums;
+// for long ones 4 sqrt(n), a 7-sigma bound (independent round-to-nearest errors are uniform in [-e, e]: the sum has
+// standard deviation 0.58 sqrt(n) e).
+__host__ __device__ inline double guard_terms(double n) {
+  const double r = 4.0 * sqrt(n);
+  return n < r ? n : r;
+}
 enum { SOLVE_SLOTS = 128 };
 void launch_solve(const Launcher &L, const SolveArgs &a);
 // sums the partial slots (fixed order) into scalars[SC_SQERR, SC_LLK, SC_SUMW, SC_NONEMPTY]
@@ -232,6 +287,15 @@ size_t cross_resid_partials_len(int d, int k, int slabs_alloc);
 void launch_reconstruct(const Launcher &L, const SampleStore &st, int64_t row0, int rows, const DevModel &m,
                         const double *Z, int extrapolate, const double *scale, int64_t scale_ld, int accumulate,
                         double *outX, int64_t ldo);
+
+// finish.cu : precision guard of the int8-sliced M-step contraction.  A_i[a][a] (a sum of positive terms) is compared with
+// the bound terms(n) smax_aa 2^-(8T-1) on its quantisation error; dimensions nobody observed (totals == 0) are skipped.
+// One block; writes scalars[SC_UNSAFE_E] = unsafe[0] (E-step violations counted by the solve kernels) and
+// scalars[SC_UNSAFE_M] = violating (dimension, a) pairs.  smax == nullptr: only publishes the E-step counter.
+void launch_mstep_guard(const Launcher &L, int d, int k, const double *statA, const double *totals, const double *smax,
+                        double coef_terms, const unsigned int *unsafe, double *scalars);
+// smax[q] = max(smax[q], scale[q])
+void launch_scale_max(const Launcher &L, const double *scale, int n, double *smax);
 
 // finish.cu : per-dimension solves (A_i + tau I) c = B_i
 void launch_row_solve(const Launcher &L, int d, int k, const double *statA, const double *statB, double tau,

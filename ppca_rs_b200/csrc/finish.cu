@@ -69,6 +69,50 @@ __global__ void __launch_bounds__(128) row_solve_kernel(int d, int k, int kp, in
   }
 }
 
+__global__ void __launch_bounds__(1024) mstep_guard_kernel(int d, int k, int kkp, const double *__restrict__ A,
+                                                           const double *__restrict__ totals,
+                                                           const double *__restrict__ smax, double coef_terms,
+                                                           const unsigned int *__restrict__ unsafe, double *scalars) {
+  __shared__ unsigned int cnt;
+  if (threadIdx.x == 0) cnt = 0u;
+  __syncthreads();
+  if (smax) {
+    unsigned int mine = 0u;
+    for (int idx = threadIdx.x; idx < d * k; idx += blockDim.x) {
+      const int i = idx / k, a = idx % k;
+      if (!(totals[i] > 0.0)) continue;  // nobody (with weight) observed this dimension: the row is kept as is
+      const int q = tri_row_off(a, k);
+      if (coef_terms * smax[q] > A[(int64_t)i * kkp + q]) ++mine;
+    }
+    if (mine) atomicAdd(&cnt, mine);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    scalars[SC_UNSAFE_E] = unsafe ? (double)unsafe[0] : 0.0;
+    scalars[SC_UNSAFE_M] = (double)cnt;
+  }
+}
+
+void launch_mstep_guard(const Launcher &L, int d, int k, const double *statA, const double *totals, const double *smax,
+                        double coef_terms, const unsigned int *unsafe, double *scalars) {
+  Shape s(d, k);
+  mstep_guard_kernel<<<1, 1024, 0, L.stream>>>(d, k, s.kkp, statA, totals, smax, coef_terms, unsafe, scalars);
+  CUDA_CHECK(cudaGetLastError());
+  ++*L.launch_counter;
+}
+
+__global__ void scale_max_kernel(const double *__restrict__ scale, int n, double *smax) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < n) smax[q] = fmax(smax[q], scale[q]);
+}
+
+void launch_scale_max(const Launcher &L, const double *scale, int n, double *smax) {
+  if (n <= 0) return;
+  scale_max_kernel<<<(n + 255) / 256, 256, 0, L.stream>>>(scale, n, smax);
+  CUDA_CHECK(cudaGetLastError());
+  ++*L.launch_counter;
+}
+
 void launch_row_solve(const Launcher &L, int d, int k, const double *statA, const double *statB, double tau,
                       const double *Cold_pad, double *Cnew, int *flags) {
   if (d <= 0 || k <= 0) return;
@@ -78,10 +122,9 @@ void launch_row_solve(const Launcher &L, int d, int k, const double *statA, cons
   int warps = 4;
   while (warps > 1 && per_warp * warps > 200 * 1024) warps >>= 1;
   REQUIRE(per_warp * warps <= 227 * 1024, "state_size %d too large for the row-solve kernel", k);
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.need()) {
     CUDA_CHECK(cudaFuncSetAttribute(row_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = true;
   }
   const int blocks = (d + warps - 1) / warps;
   row_solve_kernel<<<blocks, warps * 32, per_warp * warps, L.stream>>>(d, k, s.kp, s.kkp, statA, statB, tau, Cold_pad,

@@ -300,16 +300,16 @@ int ibitgemm_pick_splitk(int M, int Nq, int kblocks, int sms) {
 
 template <class Cfg>
 static void launch_ib(const Launcher &L, const IBitGemmArgs &a) {
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.need()) {
     CUDA_CHECK(cudaFuncSetAttribute(ibitgemm_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-    configured = true;
   }
   dim3 grid((unsigned)(round_up(a.M, Cfg::BM) / Cfg::BM), (unsigned)(round_up(a.Nq, Cfg::NQ) / Cfg::NQ),
             (unsigned)a.splitk);
   ibitgemm_kernel<Cfg><<<grid, Cfg::THREADS, Cfg::SMEM, L.stream>>>(a);
   CUDA_CHECK(cudaGetLastError());
   ++*L.launch_counter;
+  L.count(V_IMMA);
 }
 
 void launch_ibitgemm(const Launcher &L, const IBitGemmArgs &a) {

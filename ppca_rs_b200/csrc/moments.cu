@@ -318,11 +318,10 @@ size_t cross_resid_partials_len(int d, int k, int slabs_alloc) {
 template <int KT, int BS>
 static void launch_cr(const Launcher &L, CrArgs a, int dblocks, int slabs) {
   using Cfg = CrCfg<KT, BS>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.need()) {
     CUDA_CHECK(cudaFuncSetAttribute(cross_resid_kernel<KT, BS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)Cfg::SMEM));
-    configured = true;
   }
   cross_resid_kernel<KT, BS><<<dim3(dblocks, slabs), 256, Cfg::SMEM, L.stream>>>(a);
   CUDA_CHECK(cudaGetLastError());
@@ -468,10 +467,9 @@ static void launch_rec(const Launcher &L, const RecArgs &a, dim3 grid) {
   constexpr int KPP = 8 * KT;
   constexpr int LDZ = KPP + ((20 - KPP % 16) % 16);
   constexpr size_t SMEM = (2 * 64 * LDZ > 64 * 66 ? 2 * 64 * LDZ : 64 * 66) * sizeof(double);
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.need()) {
     CUDA_CHECK(cudaFuncSetAttribute(reconstruct_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-    configured = true;
   }
   reconstruct_kernel<KT><<<grid, 256, SMEM, L.stream>>>(a);
 }

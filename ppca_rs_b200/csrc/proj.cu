@@ -134,10 +134,9 @@ template <int NI>
 static void launch_proj_ni(const Launcher &L, const SampleStore &st, int64_t row0, int rows, const DevModel &m,
                            double *Y, double *nx) {
   using Cfg = ProjCfg<NI>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.need()) {
     CUDA_CHECK(cudaFuncSetAttribute(proj_kernel<NI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-    configured = true;
   }
   dim3 grid((unsigned)((rows + Cfg::BM - 1) / Cfg::BM), (unsigned)((m.s.kp + Cfg::BN - 1) / Cfg::BN));
   proj_kernel<NI><<<grid, 256, Cfg::SMEM, L.stream>>>(st.X.p, st.ldx, st.mask.p, st.dw, row0, m.C, m.s.kp, m.mu,
@@ -164,10 +163,9 @@ template <int NI>
 static void launch_rowgemm_ni(const Launcher &L, const double *A, int lda, int rows_pad, int K, const double *Bt, int n8,
                               const uint32_t *ones, const double *zeros, double *Y, double *nx_scratch) {
   using Cfg = ProjCfg<NI>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.need()) {
     CUDA_CHECK(cudaFuncSetAttribute(proj_kernel<NI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-    configured = true;
   }
   dim3 grid((unsigned)(rows_pad / Cfg::BM), (unsigned)((n8 + Cfg::BN - 1) / Cfg::BN));
   proj_kernel<NI><<<grid, 256, Cfg::SMEM, L.stream>>>(A, lda, ones, 0, 0, Bt, n8, zeros, (K + 31) / 32, K, Y, nx_scratch);

@@ -84,6 +84,11 @@ __global__ void __launch_bounds__(256) solve_kernel(SolveArgs a) {
     }
     for (int q = lane; q < k; q += 32) M[k * ldk + q] = y[q];
     __syncwarp();
+    if (a.gscale) {  // precision guard of the int8-sliced Gram matrix (see SolveArgs)
+      const double terms = guard_terms((double)dn) * a.guard_coef;
+      for (int p = lane; p < k; p += 32)
+        if (terms * a.gscale[tri_row_off(p, k)] > M[p * ldk + p]) atomicAdd(a.unsafe, 1u);
+    }
 
     // 2. Cholesky of the augmented matrix: rows 0..k-1 -> L, row k -> u = L^{-1} y
     double logdet = 0.0;
@@ -240,6 +245,10 @@ __global__ void __launch_bounds__(256, MINB) solve_reg_kernel(SolveArgs a) {
       const double g = st[idx];
       const double unit = (j == li) ? 1.0 : 0.0;
       A[j] = use ? fma(unit, s2, g) : unit;
+    }
+    if (a.gscale && live) {  // precision guard of the int8-sliced Gram matrix (see SolveArgs); lane li checks M_ii
+      const int qd = up + li;
+      if (guard_terms((double)dn) * a.guard_coef * a.gscale[qd] > s2 + st[qd]) atomicAdd(a.unsafe, 1u);
     }
 
     double mypiv = 1.0, myinv = 1.0;
@@ -400,6 +409,10 @@ __global__ void __launch_bounds__(256, 1) solve_reg64_kernel(SolveArgs a) {
       const double unit = (j == li) ? 1.0 : 0.0;
       A[j] = use ? fma(unit, s2, g) : unit;
     }
+    if (a.gscale && live) {  // precision guard (see SolveArgs)
+      const int qd = up + li;
+      if (guard_terms((double)dn) * a.guard_coef * a.gscale[qd] > s2 + stage[qd]) atomicAdd(a.unsafe, 1u);
+    }
 
     double mypiv = 1.0, myinv = 1.0;
 #pragma unroll
@@ -555,6 +568,10 @@ __global__ void __launch_bounds__(256, 2) solve_split64_kernel(SolveArgs a) {
       const double g = stage[idx];
       const double unit = (j == li) ? 1.0 : 0.0;
       A[jj] = use ? fma(unit, s2, g) : unit;
+    }
+    if (a.gscale && live && h == 0) {  // precision guard (see SolveArgs)
+      const int qd = up + li;
+      if (guard_terms((double)dn) * a.guard_coef * a.gscale[qd] > s2 + stage[qd]) atomicAdd(a.unsafe, 1u);
     }
 
     double mypiv = 1.0, myinv = 1.0;
@@ -757,6 +774,10 @@ __global__ void __launch_bounds__(256, (NT == 8 ? 3 : 4)) solve_blk_kernel(Solve
         const double unit = (gr == gc) ? 1.0 : 0.0;
         x[j][s] = use ? fma(unit, s2, g) : unit;
       }
+    if (a.gscale && !empty && c == 0 && gr < k) {  // precision guard (see SolveArgs)
+      const int qd = tri_row_off(gr, k);
+      if (guard_terms((double)dn) * a.guard_coef * a.gscale[qd] > s2 + stage[qd]) atomicAdd(a.unsafe, 1u);
+    }
 
     double logdet = 0.0;
 #pragma unroll
@@ -907,10 +928,9 @@ template <int NT>
 static void launch_solve_blk(const Launcher &L, const SolveArgs &a) {
   using Cfg = BlkCfg<NT>;
   const size_t smem = (size_t)Cfg::SPC * Cfg::per_slot(a.s.kkp, a.colmax != nullptr) * sizeof(double);
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.need()) {
     CUDA_CHECK(cudaFuncSetAttribute(solve_blk_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    configured = true;
   }
   int64_t blocks = (a.rows_pad + Cfg::SPC - 1) / Cfg::SPC;
   const int64_t cap = (int64_t)L.sms * (NT == 8 ? 3 : 4);
@@ -918,34 +938,35 @@ static void launch_solve_blk(const Launcher &L, const SolveArgs &a) {
   solve_blk_kernel<NT><<<(unsigned)blocks, 256, smem, L.stream>>>(a);
   CUDA_CHECK(cudaGetLastError());
   ++*L.launch_counter;
+  L.count(V_SOLVE_BLK);
 }
 
 static void launch_solve_split64(const Launcher &L, const SolveArgs &a) {
   const size_t smem = (size_t)2 * (a.s.kkp + 2 * 128 + 64 + 128 + 16 + (a.colmax ? a.s.kkp : 0)) * sizeof(double);
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.need()) {
     CUDA_CHECK(cudaFuncSetAttribute(solve_split64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    configured = true;
   }
   int64_t blocks = (a.rows_pad + 1) / 2;
   if (blocks > 2 * (int64_t)L.sms) blocks = 2 * (int64_t)L.sms;
   solve_split64_kernel<<<(unsigned)blocks, 256, smem, L.stream>>>(a);
   CUDA_CHECK(cudaGetLastError());
   ++*L.launch_counter;
+  L.count(V_SOLVE_SPLIT64);
 }
 
 static void launch_solve_reg64(const Launcher &L, const SolveArgs &a) {
   const size_t smem = (size_t)4 * (a.s.kkp + 5 * 64 + (a.colmax ? a.s.kkp : 0)) * sizeof(double);
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.need()) {
     CUDA_CHECK(cudaFuncSetAttribute(solve_reg64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    configured = true;
   }
   int64_t blocks = (a.rows_pad + 3) / 4;
   if (blocks > L.sms) blocks = L.sms;
   solve_reg64_kernel<<<(unsigned)blocks, 256, smem, L.stream>>>(a);
   CUDA_CHECK(cudaGetLastError());
   ++*L.launch_counter;
+  L.count(V_SOLVE_PAIR64);
 }
 
 template <int KP, int MINB>
@@ -953,10 +974,9 @@ static void launch_solve_reg_b(const Launcher &L, const SolveArgs &a) {
   constexpr int SPW = 32 / KP;
   const int warps = 8;
   const size_t smem = (size_t)warps * (SPW * a.s.kkp + 128 + (a.colmax ? SPW * a.s.kkp : 0)) * sizeof(double);
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.need()) {
     CUDA_CHECK(cudaFuncSetAttribute(solve_reg_kernel<KP, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    configured = true;
   }
   const int groups = (a.rows_pad + SPW - 1) / SPW;
   int64_t blocks = (groups + warps - 1) / warps;
@@ -967,6 +987,7 @@ static void launch_solve_reg_b(const Launcher &L, const SolveArgs &a) {
   solve_reg_kernel<KP, MINB><<<(unsigned)blocks, warps * 32, smem, L.stream>>>(a);
   CUDA_CHECK(cudaGetLastError());
   ++*L.launch_counter;
+  L.count(KP == 8 ? V_SOLVE_REG8 : KP == 16 ? V_SOLVE_REG16 : V_SOLVE_REG32);
 }
 
 template <int KP>
@@ -1035,10 +1056,9 @@ static void launch_solve_generic(const Launcher &L, const SolveArgs &a) {
   while (warps > 1 && per_warp * warps > 200 * 1024) warps >>= 1;
   REQUIRE(per_warp * warps <= 227 * 1024, "state_size %d too large for the per-sample solve kernel", a.s.k);
   const size_t smem = per_warp * warps;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.need()) {
     CUDA_CHECK(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = true;
   }
   int ctas_per_sm = (int)((220 * 1024) / (smem + 1024));
   if (ctas_per_sm < 1) ctas_per_sm = 1;
@@ -1049,6 +1069,7 @@ static void launch_solve_generic(const Launcher &L, const SolveArgs &a) {
   solve_kernel<<<(unsigned)blocks, warps * 32, smem, L.stream>>>(a);
   CUDA_CHECK(cudaGetLastError());
   ++*L.launch_counter;
+  L.count(V_SOLVE_GENERIC);
 }
 
 void launch_solve(const Launcher &L, const SolveArgs &a) {

@@ -1174,11 +1174,10 @@ static void launch_tb(const Launcher &L, const TBitGemmArgs &a) {
     static const bool smem_a = getenv("PPCA_B200_TC_SMEM_A") && atoi(getenv("PPCA_B200_TC_SMEM_A")) == 1;
     if (!smem_a) {  // A operand in tensor memory: shared memory carries only the digit planes
       constexpr size_t SMEM_ATM = (size_t)tb::STAGES * (T * tb::NQ * tb::BKB) + 1024 + 2 * tb::ATM_RING * 128 * 16;
-      static bool configured_atm = false;
-      if (!configured_atm) {
+      static PerDeviceOnce configured_atm;
+      if (configured_atm.need()) {
         CUDA_CHECK(cudaFuncSetAttribute(tbitgemm_atm_kernel<T, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_ATM));
         CUDA_CHECK(cudaFuncSetAttribute(tbitgemm_atm_kernel<T, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_ATM));
-        configured_atm = true;
       }
       static const int force = getenv("PPCA_B200_TC_ROLES") ? atoi(getenv("PPCA_B200_TC_ROLES")) : 0;
       const int ks_per = (a.ksteps + a.splitk - 1) / a.splitk;
@@ -1194,11 +1193,10 @@ static void launch_tb(const Launcher &L, const TBitGemmArgs &a) {
         const bool balanced = (double)t2_ >= 0.85 * (double)(round_up(t2_, L.sms));
         if (q2 && !drain && a.Nq > tb::NQ && balanced) {
           constexpr size_t SMEM_Q2 = (size_t)tb::STAGES * 2 * (T * tb::NQ * tb::BKB) + 1024 + 2 * tb::ATM_RING * 128 * 16;
-          static bool configured_q2 = false;
-          if (!configured_q2) {
+          static PerDeviceOnce configured_q2;
+          if (configured_q2.need()) {
             CUDA_CHECK(cudaFuncSetAttribute(tbitgemm_atm2_kernel<T, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)SMEM_Q2));
-            configured_q2 = true;
           }
           const int64_t qg = (round_up(a.Nq, tb::NQ) / tb::NQ + 1) / 2;
           const int64_t tiles2 = round_up(a.M, tb::BM) / tb::BM * qg * a.splitk;
@@ -1206,6 +1204,7 @@ static void launch_tb(const Launcher &L, const TBitGemmArgs &a) {
           tbitgemm_atm2_kernel<T, 2, 1><<<grid2, tb::THREADS_ATM, SMEM_Q2, L.stream>>>(a);
           CUDA_CHECK(cudaGetLastError());
           ++*L.launch_counter;
+          L.count(V_TC_ATM2);
           return;
         }
       }
@@ -1213,18 +1212,19 @@ static void launch_tb(const Launcher &L, const TBitGemmArgs &a) {
       else tbitgemm_atm_kernel<T, 2, 1><<<grid, tb::THREADS_ATM, SMEM_ATM, L.stream>>>(a);
       CUDA_CHECK(cudaGetLastError());
       ++*L.launch_counter;
+      L.count(drain ? V_TC_ATM_DRAIN : V_TC_ATM_FEED);
       return;
     }
   }
   constexpr size_t SMEM = (size_t)tb::STAGES * (tb::BM * tb::BKB + T * tb::NQ * tb::BKB) + 1024;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.need()) {
     CUDA_CHECK(cudaFuncSetAttribute(tbitgemm_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-    configured = true;
   }
   tbitgemm_kernel<T><<<grid, tb::THREADS, SMEM, L.stream>>>(a);
   CUDA_CHECK(cudaGetLastError());
   ++*L.launch_counter;
+  L.count(V_TC_SMEM_A);
 }
 
 void launch_tbitgemm(const Launcher &L, const uint32_t *bits, int64_t ldbits, int nwords, const int8_t *Bq,

@@ -14,6 +14,7 @@ replicated finish) can be exercised with world_size-2 gloo tests on CPU tensors;
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 from typing import List, Optional, Sequence, Tuple
 
@@ -46,11 +47,19 @@ class CudaEngine:
         self.torch = torch
         self.ctx = ctx
         self.device = torch.device("cuda", ctx.device)
+        # Everything torch does for this engine (buffer initialisation, the NCCL all-reduce) is enqueued on the CONTEXT's
+        # stream, so it is ordered with the kernels of em_stats / em_finish without any host synchronisation
+        # (ppca_b200_em_stats returns while its kernels are still running).
+        self.stream = torch.cuda.ExternalStream(ctx.stream_handle(), device=self.device)
+
+    def stream_scope(self):
+        return self.torch.cuda.stream(self.stream)
 
     def new_stats(self, d: int, k: int):
         n = nat.lib().ppca_b200_em_stats_len(d, k)
         assert n == stats_len(d, k)
-        return self.torch.zeros(n, dtype=self.torch.float64, device=self.device)
+        with self.stream_scope():
+            return self.torch.zeros(n, dtype=self.torch.float64, device=self.device)
 
     def em_stats(self, ds, model: PPCAModel, stats) -> None:
         if isinstance(ds, HostDataset):  # this rank's rows stay in host memory and are streamed every step
@@ -77,7 +86,8 @@ class CudaEngine:
 
     # mixtures
     def new_logpost(self, n: int, m: int):
-        return self.torch.empty(max(n, 1) * m, dtype=self.torch.float64, device=self.device)
+        with self.stream_scope():
+            return self.torch.empty(max(n, 1) * m, dtype=self.torch.float64, device=self.device)
 
     def mix_posteriors(self, ds: Dataset, mix: PPCAMix, logpost) -> Tuple[np.ndarray, float]:
         ks, Cs, mus, sig, lw = mix._pack()
@@ -96,10 +106,17 @@ class CudaEngine:
                                                    C.c_void_p(stats.data_ptr())))
 
     def to_tensor(self, a: np.ndarray):
-        return self.torch.from_numpy(np.ascontiguousarray(a)).to(self.device)
+        with self.stream_scope():
+            return self.torch.from_numpy(np.ascontiguousarray(a)).to(self.device)
 
     def scalar_sumw(self, stats, d: int, k: int) -> float:
         return float(stats[stats_len(d, k) - 8 + 3].item())
+
+
+def _scope(engine):
+    """Stream scope of the engine's collectives (the product engine: the context's stream; CPU test engines: none)."""
+    fn = getattr(engine, "stream_scope", None)
+    return fn() if fn is not None else contextlib.nullcontext()
 
 
 class ShardedPPCA:
@@ -113,10 +130,18 @@ class ShardedPPCA:
 
     def step(self) -> float:
         """One EM iteration; returns the (global) log-likelihood of the model the step started from."""
-        self.engine.em_stats(self.dataset, self.model, self.stats)
-        if self.group is not None:
-            self.group.all_reduce(self.stats)  # SUM
-        self.model, self.last_llk = self.engine.em_finish(self.model, self.prior, self.stats)
+        for _ in range(3):  # at most two climbs of the precision ladder (include/ppca_b200.h, PPCA_ERR_PRECISION)
+            self.engine.em_stats(self.dataset, self.model, self.stats)
+            if self.group is not None:
+                with _scope(self.engine):
+                    self.group.all_reduce(self.stats)  # SUM, enqueued behind the statistics kernels
+            try:
+                self.model, self.last_llk = self.engine.em_finish(self.model, self.prior, self.stats)
+                break
+            except nat.NativeError as e:
+                # the guard counters ride in the reduced buffer, so every rank takes this branch together
+                if e.code != nat.ERR_PRECISION:
+                    raise
         return self.last_llk
 
 
@@ -136,20 +161,26 @@ class ShardedPPCAMix:
         m, d = len(mix._models), mix.output_size
         cmax, llk = eng.mix_posteriors(self.dataset, mix, self.logpost)
         if self.group is not None:
-            t = eng.to_tensor(np.concatenate([cmax, [llk]]))
-            tmax = t[:m].clone()
-            self.group.all_reduce(tmax, op=self.group.ReduceOp.MAX)
-            tsum = t[m:].clone()
-            self.group.all_reduce(tsum)
-            cmax, llk = tmax.cpu().numpy(), float(tsum.item())
-        for j in range(m):
-            eng.mix_em_stats(self.dataset, mix, j, self.logpost, float(cmax[j]), self.stats[j])
-        if self.group is not None:
-            for st in self.stats:
-                self.group.all_reduce(st)
+            with _scope(eng):
+                t = eng.to_tensor(np.concatenate([cmax, [llk]]))
+                tmax = t[:m].clone()
+                self.group.all_reduce(tmax, op=self.group.ReduceOp.MAX)
+                tsum = t[m:].clone()
+                self.group.all_reduce(tsum)
+                cmax, llk = tmax.cpu().numpy(), float(tsum.item())
         models, logsum = [], np.empty(m)
         for j, mj in enumerate(mix._models):
-            new, _ = eng.em_finish(mj, self.prior, self.stats[j])
+            for _ in range(3):  # precision ladder, as in ShardedPPCA.step
+                eng.mix_em_stats(self.dataset, mix, j, self.logpost, float(cmax[j]), self.stats[j])
+                if self.group is not None:
+                    with _scope(eng):
+                        self.group.all_reduce(self.stats[j])
+                try:
+                    new, _ = eng.em_finish(mj, self.prior, self.stats[j])
+                    break
+                except nat.NativeError as e:
+                    if e.code != nat.ERR_PRECISION:
+                        raise
             models.append(new)
             logsum[j] = np.log(eng.scalar_sumw(self.stats[j], d, mj.state_size)) + cmax[j]  # mix.rs:323-324
         new_mix = PPCAMix.__new__(PPCAMix)

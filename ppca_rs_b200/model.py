@@ -458,7 +458,7 @@ class PPCAModel:
         covs = np.empty((n, k, k))
         nat.check(nat.lib().ppca_b200_infer(dataset._ctx.handle, dataset._h, k, nat.dptr(self._C), nat.dptr(self._mu),
                                             self._sigma, nat.dptr(states), nat.dptr(covs)))
-        return InferredMasked(states, covs)
+        return InferredMasked(states, covs, self)
 
     def _recon(self, dataset: Dataset, fn) -> Dataset:
         self._check(dataset)
@@ -534,9 +534,10 @@ class PPCAModel:
 # Per-sample convenience algebra on the inferred posteriors.  Host numpy: SURVEY.md §8(f) rank 1 ("next").
 # =================================================================================================
 class InferredMasked:
-    def __init__(self, states: np.ndarray, covariances: np.ndarray):
+    def __init__(self, states: np.ndarray, covariances: np.ndarray, model: Optional["PPCAModel"] = None):
         self._states = states
         self._covs = covariances
+        self._model = model  # the reference struct keeps a clone of the model (ppca_model.rs:428-432)
 
     def __len__(self) -> int:
         return self._states.shape[0]
@@ -596,7 +597,7 @@ class InferredMasked:
         return self._cov_diag_dataset(ppca, dataset)  # ppca_model.rs:542-577
 
     def posterior_sampler(self) -> "PosteriorSampler":
-        return PosteriorSampler(self._states, np.linalg.cholesky(self._covs))  # ppca_model.rs:581-592
+        return PosteriorSampler(self._states, np.linalg.cholesky(self._covs), self._model)  # ppca_model.rs:581-592
 
 
 class PosteriorSampler:
@@ -735,7 +736,7 @@ class PPCAMix:
 
     def infer(self, dataset: Dataset) -> "InferredMaskedMix":
         log_post = self.infer_cluster(dataset)
-        return InferredMaskedMix(log_post, [m.infer(dataset) for m in self._models])
+        return InferredMaskedMix(log_post, [m.infer(dataset) for m in self._models], self)
 
     def smooth(self, dataset: Dataset) -> Dataset:
         h = nat.c_ds_p()
@@ -799,9 +800,10 @@ class PPCAMix:
 # InferredMaskedMix  (src/python_bindings.rs:713-905 ; mix.rs:357-532).  Host numpy ("next").
 # =================================================================================================
 class InferredMaskedMix:
-    def __init__(self, log_posteriors: np.ndarray, inferred: List[InferredMasked]):
+    def __init__(self, log_posteriors: np.ndarray, inferred: List[InferredMasked], mix: Optional["PPCAMix"] = None):
         self._lp = log_posteriors
         self._inf = inferred
+        self._mix = mix
 
     def __len__(self) -> int:
         return self._lp.shape[0]
@@ -889,16 +891,20 @@ class InferredMaskedMix:
         return Dataset(acc)
 
     def posterior_sampler(self) -> "PosteriorSamplerMix":
-        return PosteriorSamplerMix(np.exp(self._lp), [inf.posterior_sampler() for inf in self._inf])
+        return PosteriorSamplerMix(np.exp(self._lp), [inf.posterior_sampler() for inf in self._inf], self._mix)
 
 
 class PosteriorSamplerMix:
     """mix.rs:519-532."""
 
-    def __init__(self, posteriors: np.ndarray, samplers: List[PosteriorSampler]):
-        self._post, self._samplers = posteriors, samplers
+    def __init__(self, posteriors: np.ndarray, samplers: List[PosteriorSampler], mix: Optional[PPCAMix] = None):
+        self._post, self._samplers, self._mix = posteriors, samplers, mix
 
-    def sample(self, mix: PPCAMix) -> Dataset:
+    def sample(self, mix: Optional[PPCAMix] = None) -> Dataset:
+        """No arguments, as in the reference (src/python_bindings.rs:895): the samplers carry their models."""
+        mix = mix or self._mix
+        if mix is None:
+            raise ValueError("a PPCAMix is needed to sample outputs")
         rng = np.random.default_rng()
         n = self._post.shape[0]
         p = self._post / self._post.sum(axis=1, keepdims=True)

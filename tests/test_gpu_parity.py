@@ -644,3 +644,222 @@ def test_dmma_mixture_and_inference(pk, orc, int8_ctx):
     for got, (Cw, muw, sw), (Cs, mus, ss) in zip(new.models, want_models, st_models):
         assert_close(got.transform, Cw, Cs, "mix C")
         assert_close(got.isotropic_noise, sw, ss, "mix sigma")
+
+
+# ---- the c3 / c5 contraction kernel (tbitgemm_atm2_kernel: two output tiles per expanded mask stage) ---------------
+# It is the default whenever a tile is > 4 K steps and the paired tile count balances the persistent grid (d > 512 in
+# the E-step; the M-step when n / 128 > 4 K steps per slab and ceil(d/128) * ceil(qtiles/2) * splitk fills 148 CTAs).
+# The per-variant launch counters prove which kernel ran.
+@pytest.mark.parametrize("n,d,k,p,e_atm2,m_atm2", [
+    (4096, 2048, 64, 0.3, True, True),     # BASELINE configs[2] shape: both contractions on the two-tile kernel
+    (8192, 1024, 48, 0.3, True, False),    # BASELINE configs[4] shape: E-step two-tile, M-step one-tile feed kernel
+    (5500, 640, 40, 0.25, True, None),     # ragged: kk = 820 (last pair holds one q tile), partial last row tile
+])
+def test_two_tile_contraction_kernel_parity(pk, orc, n, d, k, p, e_atm2, m_atm2):
+    X, C0, mu0, s0 = _case(n, d, k, p, seed=21, empty_rows=(3,), empty_dims=(d - 2,))
+    w = np.random.default_rng(5).random(n) + 0.5
+    ds = pk.Dataset(X, w)
+    ctx = pk.get_context()
+    c0 = ctx.variant_counts()
+    model = pk.PPCAModel(0.6, C0, mu0)
+    got = model.llks(ds)
+    c1 = ctx.variant_counts()
+    assert (c1["tc_atm2"] - c0["tc_atm2"] >= 1) == e_atm2, (c0, c1)
+    want = orc.llks(X, C0, mu0, 0.6)
+    assert rel_err(got, want) < TOL
+    assert np.max(np.abs(got - want) / np.maximum(np.abs(want), 1.0)) < TOL       # element-wise, not only max-norm
+    (Z, COV), (Zs, COVs) = both(orc, orc.infer, X[:512], C0, mu0, 0.6)
+    inf = model.infer(ds._slice(0, 512))
+    assert_close(inf.states(), Z, Zs, "states")
+    assert_close(np.stack(inf.covariances()), COV, COVs, "covariances")
+    C, mu, s = C0, mu0, s0
+    for it in range(2):
+        c2 = ctx.variant_counts()
+        new, llk = pk.PPCAModel(s, C, mu)._iterate(ds, None)
+        c3 = ctx.variant_counts()
+        n_atm2 = c3["tc_atm2"] - c2["tc_atm2"]
+        if m_atm2 is not None:
+            assert n_atm2 == (1 if e_atm2 else 0) + (1 if m_atm2 else 0), (c2, c3)
+        (Cw, muw, sw), (Cs, mus, ss) = both(orc, orc.iterate, X, w, C, mu, s)
+        llkw = orc.llk(X, w, C, mu, s)
+        assert abs(llk - llkw) <= TOL * abs(llkw), f"llk iteration {it}"
+        assert_close(new.transform, Cw, Cs, f"C iteration {it}")
+        assert_close(new.mean, muw, mus, f"mu iteration {it}")
+        assert_close(new.isotropic_noise ** 2, sw ** 2, ss ** 2, f"sigma^2 iteration {it}")
+        assert np.array_equal(new.transform[d - 2], C[d - 2])                     # empty dimension keeps its row
+        C, mu, s = Cw, muw, sw
+    ex = pk.PPCAModel(s, C, mu).extrapolate(ds._slice(0, 1024)).numpy()
+    fin = np.isfinite(X[:1024])
+    assert np.array_equal(ex[fin], X[:1024][fin])
+    want_ex, want_ex_s = both(orc, orc.extrapolate, X[:1024], C, mu, s)
+    assert_close(ex, want_ex, want_ex_s, "extrapolate")
+
+
+def test_posterior_samplers_carry_their_models(pk):
+    """InferredMasked.posterior_sampler().sample() takes no arguments (src/python_bindings.rs:335-361, :875-901)."""
+    X, C0, mu0, s0 = _case(400, 12, 3, 0.2, seed=2)
+    ds = pk.Dataset(X)
+    model = pk.PPCAModel(0.5, C0, mu0)
+    smp = model.infer(ds).posterior_sampler().sample()
+    assert len(smp) == 400 and np.isfinite(smp.numpy()).all()
+    mix = pk.PPCAMix([model, pk.PPCAModel(0.7, C0 * 0.5, mu0 + 0.2)], np.log([0.4, 0.6]))
+    smp = mix.infer(ds).posterior_sampler().sample()
+    assert len(smp) == 400 and np.isfinite(smp.numpy()).all()
+
+
+def test_slice_recomputes_its_minimum_weight(pk):
+    """A chunk with only positive weights from a parent holding a zero weight elsewhere is accepted by mixture EM."""
+    X, C0, mu0, s0 = _case(600, 10, 2, 0.2, seed=4)
+    w = np.ones(600)
+    w[5] = 0.0
+    ds = pk.Dataset(X, w)
+    mix = pk.PPCAMix([pk.PPCAModel(1.0, C0, mu0), pk.PPCAModel(1.0, -C0, mu0 + 0.1)], np.log([0.5, 0.5]))
+    with pytest.raises(Exception):
+        mix.iterate(ds)                         # zero weight: mix.rs:304-309
+    tail = ds._slice(300, 300)
+    assert isinstance(mix.iterate(tail), pk.PPCAMix)
+    with pytest.raises(Exception):
+        mix.iterate(ds._slice(0, 300))
+
+
+def test_two_contexts_on_two_devices_in_one_process(pk):
+    """cudaFuncSetAttribute is per device: a second context on another GPU must opt its kernels in again."""
+    from ppca_rs_b200 import _native as nat
+    if nat.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    X, C0, mu0, s0 = _case(3000, 200, 16, 0.2)
+    outs = []
+    for dev in (0, 1):
+        ctx = nat.Context(dev)
+        ds = pk.Dataset(X, _ctx=ctx)
+        new, llk = pk.PPCAModel(s0, C0, mu0)._iterate(ds, None)
+        outs.append((new.transform, llk))
+    assert np.array_equal(outs[0][0], outs[1][0]) and outs[0][1] == outs[1][1]
+
+
+# ---- precision guard of the int8-sliced contractions: adversarial dynamic range -----------------------------------
+# The default arithmetic keeps every term to 46 bits below its COLUMN maximum.  These cases put the column maximum far
+# above what some samples / dimensions see; the guard must notice and the ladder (8 planes, then FP64 DMMA) must bring
+# the result back to the accuracy of an FP64 evaluation.  `floor` = what two FP64 evaluations of the same quantity
+# (the oracle and the independent dense restatement tests/dense_ref.py) disagree by on these ill-scaled inputs.
+def _elementwise(got, want):
+    got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
+    return float(np.max(np.abs(got - want) / np.maximum(np.abs(want), 1.0)))
+
+
+@pytest.fixture
+def guard_ctx(pk):
+    ctx = pk.get_context()
+    ctx.set_gemm("tc", 6)
+    ctx.set_guard(True, 40)
+    yield ctx
+    ctx.set_gemm("tc", 6)
+    ctx.set_guard(True, 40)
+
+
+@pytest.mark.parametrize("scale", [1e2, 1e3, 1e4])
+def test_precision_guard_one_feature_in_other_units(pk, orc, guard_ctx, scale):
+    import dense_ref
+    n, d, k = 1500, 40, 5
+    X, C0, mu0, s0 = _case(n, d, k, 0.3, seed=3)
+    X[:, 7] *= scale
+    C0 = C0.copy()
+    C0[7] *= scale
+    ds = pk.Dataset(X)
+    model = pk.PPCAModel(0.5, C0, mu0)
+    want = orc.llks(X, C0, mu0, 0.5)
+    dense = np.array([dense_ref.llk_one(X[i], C0, mu0, 0.5) for i in range(n)])
+    floor = _elementwise(dense, want)
+    guard_ctx.set_gemm("dmma")
+    fp64 = model.llks(ds)
+    guard_ctx.set_gemm("tc", 6)
+    before = guard_ctx.variant_counts()["precision_retry"]
+    got = model.llks(ds)
+    retried = guard_ctx.variant_counts()["precision_retry"] - before
+    guard_ctx.set_guard(False)
+    raw = model.llks(ds)                                  # what the unguarded 46-bit path would have returned
+    guard_ctx.set_guard(True)
+    print(f"scale {scale:g}: guarded {_elementwise(got, want):.2e} unguarded {_elementwise(raw, want):.2e} "
+          f"fp64 {_elementwise(fp64, want):.2e} floor {floor:.2e} retries {retried}")
+    assert retried >= 1
+    assert _elementwise(got, want) < TOL + 4.0 * floor
+    assert _elementwise(got, fp64) < TOL + 4.0 * floor
+    # one EM iteration from the ill-scaled model
+    guard_ctx.set_gemm("tc", 6)
+    new, llk = pk.PPCAModel(1.0, C0, mu0)._iterate(ds, None)
+    with orc.stable():
+        Cs, mus, ss = orc.iterate(X, None, C0, mu0, 1.0)
+    Cd, mud, sd = dense_ref.iterate(X[:400], np.ones(400), C0, mu0, 1.0)
+    with orc.stable():
+        Cs4, mus4, ss4 = orc.iterate(X[:400], None, C0, mu0, 1.0)
+    fl = max(rel_err(Cd, Cs4), rel_err(mud, mus4), abs(sd - ss4) / ss4)
+    assert rel_err(new.transform, Cs) < TOL + 4.0 * fl
+    assert rel_err(new.mean, mus) < TOL + 4.0 * fl
+    assert abs(new.isotropic_noise - ss) < (TOL + 4.0 * fl) * ss
+
+
+def test_precision_guard_stays_quiet_on_well_scaled_data(pk, orc, guard_ctx):
+    X, C0, mu0, s0 = _case(3000, 200, 16, 0.2)
+    ds = pk.Dataset(X)
+    before = guard_ctx.variant_counts()
+    model = pk.PPCAModel(s0, C0, mu0)
+    for _ in range(3):
+        model, _ = model._iterate(ds, None)
+    model.llks(ds)
+    model.extrapolate(ds)
+    after = guard_ctx.variant_counts()
+    assert after["precision_retry"] == before["precision_retry"]
+    assert after["dmma"] == before["dmma"] and after["tc_smem_a"] == before["tc_smem_a"]
+
+
+def test_precision_guard_weights_with_a_wide_dynamic_range(pk, orc, guard_ctx):
+    """A dimension observed only by samples of weight 1e-12: its second-moment matrix A_i is a sum of terms 1e-12
+    below the column scale of W (M-step guard)."""
+    n, d, k = 2000, 30, 4
+    X, C0, mu0, s0 = _case(n, d, k, 0.2, seed=8)
+    w = np.ones(n)
+    w[:200] = 1e-12
+    X[200:, 11] = np.nan                     # dimension 11 is seen by the 200 light samples only
+    X[:200, 11] = X[:200, 11] + 1.0
+    ds = pk.Dataset(X, w)
+    before = guard_ctx.variant_counts()["precision_retry"]
+    new, llk = pk.PPCAModel(s0, C0, mu0)._iterate(ds, None)
+    assert guard_ctx.variant_counts()["precision_retry"] > before
+    (Cw, muw, sw), (Cs, mus, ss) = both(orc, orc.iterate, X, w, C0, mu0, s0)
+    assert_close(new.transform, Cw, Cs, "C")
+    assert np.max(np.abs(new.transform[11] - Cs[11])) < TOL * np.max(np.abs(Cs[11]))   # the light row itself
+    assert_close(new.mean, muw, mus, "mu")
+    assert_close(new.isotropic_noise ** 2, sw ** 2, ss ** 2, "sigma^2")
+    guard_ctx.set_guard(False)
+    raw, _ = pk.PPCAModel(s0, C0, mu0)._iterate(ds, None)
+    print("unguarded row error", np.max(np.abs(raw.transform[11] - Cs[11])) / np.max(np.abs(Cs[11])))
+
+
+def test_precision_guard_mixture_responsibilities_spanning_1e30(pk, orc, guard_ctx):
+    """Two far-apart clusters: the responsibilities of a component for the other cluster's samples are ~1e-30 and one
+    dimension is observed by that other cluster only (mix.rs:304-326)."""
+    rng = np.random.default_rng(12)
+    n, d = 1600, 16
+    A = make_data(n // 2, d, 3, 0.2, seed=1, mean_scale=0.2)
+    B = make_data(n // 2, d, 3, 0.2, seed=2, mean_scale=0.2) + 1.5
+    A[:, 5] = np.nan                           # dimension 5: cluster B only
+    X = np.concatenate([A, B])
+    X = X[rng.permutation(n)]
+    models = []
+    for j, shift in enumerate((0.0, 1.5)):
+        C0, mu0, _ = init_model(d, 3, seed=50 + j)
+        models.append((0.3 * C0, mu0 + shift, 0.6))
+    logw = np.log([0.5, 0.5])
+    ds = pk.Dataset(X)
+    mix = pk.PPCAMix([pk.PPCAModel(s, C, mu) for C, mu, s in models], logw)
+    post = mix.infer_cluster(ds)
+    assert np.nanmin(post[np.isfinite(post)]) < np.log(1e-30)          # the case really spans > 30 orders of magnitude
+    new, llk = mix._iterate(ds, None)
+    (want_models, want_logw), (st_models, _) = both(orc, orc.mix_iterate, X, None, models, logw)
+    assert abs(llk - orc.mix_llk(X, None, models, logw)) < TOL * abs(llk)
+    assert np.max(np.abs(new.log_weights - want_logw)) < 1e-9
+    for got, (Cw, muw, sw), (Cs, mus, ss) in zip(new.models, want_models, st_models):
+        assert_close(got.transform, Cw, Cs, "mix C")
+        assert np.max(np.abs(got.transform[5] - Cs[5])) < TOL * max(np.max(np.abs(Cs[5])), 1e-300)
+        assert_close(got.mean, muw, mus, "mix mu")
+        assert_close(got.isotropic_noise, sw, ss, "mix sigma")

@@ -1,0 +1,60 @@
+"""One EM step + one extrapolate per shape-dependent kernel variant, small enough for compute-sanitizer.
+
+    compute-sanitizer --tool memcheck  python tools/sanitize_cases.py
+    compute-sanitizer --tool racecheck python tools/sanitize_cases.py
+
+Prints the per-variant launch counters at the end so the log shows which kernels the run covered.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import ppca_rs_b200 as pk  # noqa: E402
+from helpers import init_model, make_data  # noqa: E402
+
+CASES = [
+    # n, d, k, gemm, slices : what it exercises
+    (2048, 200, 16, "tc", 6),    # tbitgemm_atm_kernel<6,1,2> (drain), solve_reg16
+    (1024, 700, 7, "tc", 6),     # tbitgemm_atm_kernel<6,2,1> (feed: one q tile), solve_reg8
+    (2048, 1024, 32, "tc", 6),   # tbitgemm_atm2_kernel (E-step), solve_reg32
+    (1024, 260, 64, "tc", 6),    # solve_split64
+    (512, 150, 70, "tc", 6),     # solve_kernel (generic), colmax_kernel_tc
+    (1024, 200, 16, "tc", 7),    # tbitgemm_kernel<7> (A tile in shared memory)
+    (1024, 200, 16, "tc", 8),    # tbitgemm_kernel<8>
+    (1024, 200, 16, "int8", 6),  # ibitgemm
+    (1024, 200, 16, "dmma", 6),  # bitgemm
+]
+
+
+def main():
+    ctx = pk.get_context()
+    only = os.environ.get("SANITIZE_ONLY")
+    for i, (n, d, k, gemm, slices) in enumerate(CASES):
+        if only and str(i) not in only.split(","):
+            continue
+        ctx.set_gemm(gemm, slices)
+        X = make_data(n, d, min(k, 8), 0.25, seed=i, empty_rows=(1,))
+        C0, mu0, s0 = init_model(d, k)
+        ds = pk.Dataset(X)
+        model = pk.PPCAModel(s0, C0, mu0)
+        new, llk = model._iterate(ds, None)
+        ex = new.extrapolate(ds).numpy()
+        assert np.isfinite(ex).all() and np.isfinite(llk)
+        print("case", i, (n, d, k, gemm, slices), "llk", llk, flush=True)
+    ctx.set_gemm("tc", 6)
+    if os.environ.get("SANITIZE_MIX", "1") == "1" and not only:
+        X = make_data(1500, 64, 4, 0.2, seed=9)
+        mix = pk.PPCAMix([pk.PPCAModel(1.0, *init_model(64, kk, seed=j)[:2][::1]) for j, kk in enumerate((4, 6, 3))],
+                         np.zeros(3))
+        mix2 = mix.iterate(pk.Dataset(X))
+        print("mixture ok", mix2.log_weights, flush=True)
+    print("variant counts", {k: v for k, v in ctx.variant_counts().items() if v}, flush=True)
+
+
+if __name__ == "__main__":
+    main()
