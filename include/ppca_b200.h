@@ -270,6 +270,38 @@ int32_t ppca_b200_mix_em_stats(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, 
                                int32_t k, const double *C, const double *mu, double sigma,
                                const double *logpost_dev, double comp_max_j, double *stats_dev);
 
+/* ---- sample-sharded EM with the collective inside the library -------------------------------------------------------
+ * One process (or thread) per GPU, each with its own context and its own shard of the samples; the model is replicated.
+ * The reference has no counterpart (its only parallelism is rayon over samples, ppca_model.rs:281-358): these entry
+ * points are what a Rust `ppca` host binds to get the north star's "one NCCL all-reduce over NVLink per iteration".
+ * Rank 0 creates a unique id and ships its 128 bytes to the other ranks through any channel it has (file, socket,
+ * MPI, torch.distributed ...); every rank then calls ppca_b200_comm_init.  NCCL itself is bound at run time
+ * (dlopen libnccl.so.2; PPCA_B200_NCCL_LIB overrides the name). */
+#define PPCA_B200_UNIQUE_ID_BYTES 128
+int32_t ppca_b200_comm_unique_id(uint8_t *out /* PPCA_B200_UNIQUE_ID_BYTES */);
+int32_t ppca_b200_comm_init(ppca_b200_ctx *ctx, const uint8_t *unique_id, int32_t rank, int32_t world);
+int32_t ppca_b200_comm_destroy(ppca_b200_ctx *ctx);
+/* In-place all-reduce of `count` doubles (DEVICE memory) on the context's stream; op 0 = sum, 1 = max. */
+int32_t ppca_b200_comm_allreduce(ppca_b200_ctx *ctx, double *buf_dev, int64_t count, int32_t op);
+/* PPCAModel::iterate_with_prior (ppca_model.rs:277-393) over the union of all ranks' shards: local statistics, ONE
+ * all-reduce(sum) of [A | B | tdev | totals | 8 scalars], M-step finish replicated on every rank (identical outputs).
+ * A rank may hold an empty shard.  The precision ladder climbs on every rank together (the guard counters are part of
+ * the reduced buffer). */
+int32_t ppca_b200_iterate_sharded(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int32_t k, const double *C,
+                                  const double *mu, double sigma, const ppca_b200_prior *prior, double *C_out,
+                                  double *mu_out, double *sigma_out, double *llk_in);
+/* The same with this rank's samples in HOST memory, streamed every step (see ppca_b200_iterate_host). */
+int32_t ppca_b200_iterate_host_sharded(ppca_b200_ctx *ctx, const double *x, int64_t n, int32_t d, const double *weights,
+                                       int32_t k, const double *C, const double *mu, double sigma,
+                                       const ppca_b200_prior *prior, double *C_out, double *mu_out, double *sigma_out,
+                                       double *llk_in);
+/* PPCAMix::iterate_with_prior (mix.rs:281-337) over all ranks' shards: all-reduce(max) of the per-component
+ * responsibility maxima (mix.rs:312-318), all-reduce(sum) of the statistics of every component. */
+int32_t ppca_b200_mix_iterate_sharded(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int32_t m, const int32_t *ks,
+                                      const double *Cs, const double *mus, const double *sigmas,
+                                      const double *log_weights, const ppca_b200_prior *prior, double *Cs_out,
+                                      double *mus_out, double *sigmas_out, double *log_weights_out, double *llk_in);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

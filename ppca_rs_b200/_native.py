@@ -123,6 +123,23 @@ _PROTOTYPES = {
     ),
     "ppca_b200_mix_posteriors": (
         C.c_int32, [c_ctx_p, c_ds_p, C.c_int32, c_ip, c_dp, c_dp, c_dp, c_dp, C.c_void_p, c_dp, c_dp]),
+    "ppca_b200_comm_unique_id": (C.c_int32, [C.POINTER(C.c_uint8)]),
+    "ppca_b200_comm_init": (C.c_int32, [c_ctx_p, C.POINTER(C.c_uint8), C.c_int32, C.c_int32]),
+    "ppca_b200_comm_destroy": (C.c_int32, [c_ctx_p]),
+    "ppca_b200_comm_allreduce": (C.c_int32, [c_ctx_p, C.c_void_p, C.c_int64, C.c_int32]),
+    "ppca_b200_iterate_sharded": (
+        C.c_int32,
+        [c_ctx_p, c_ds_p, C.c_int32, c_dp, c_dp, C.c_double, C.POINTER(CPrior), c_dp, c_dp, c_dp, c_dp],
+    ),
+    "ppca_b200_iterate_host_sharded": (
+        C.c_int32,
+        [c_ctx_p, c_dp, C.c_int64, C.c_int32, c_dp, C.c_int32, c_dp, c_dp, C.c_double, C.POINTER(CPrior), c_dp, c_dp,
+         c_dp, c_dp],
+    ),
+    "ppca_b200_mix_iterate_sharded": (
+        C.c_int32,
+        [c_ctx_p, c_ds_p, C.c_int32, c_ip, c_dp, c_dp, c_dp, c_dp, C.POINTER(CPrior), c_dp, c_dp, c_dp, c_dp, c_dp],
+    ),
     "ppca_b200_mix_em_stats": (
         C.c_int32,
         [c_ctx_p, c_ds_p, C.c_int32, C.c_int32, C.c_int32, c_dp, c_dp, C.c_double, C.c_void_p, C.c_double, C.c_void_p],
@@ -191,6 +208,25 @@ class Context:
         out = C.c_void_p()
         check(lib().ppca_b200_ctx_stream(self._h, C.byref(out)))
         return int(out.value or 0)
+
+    # -- sample-sharded EM: the NCCL communicator lives inside the library (ppca_b200_comm_*) --------------------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = (C.c_uint8 * 128)()
+        check(lib().ppca_b200_comm_unique_id(buf))
+        return bytes(buf)
+
+    def comm_init(self, unique_id: bytes, rank: int, world: int) -> None:
+        assert len(unique_id) == 128
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        check(lib().ppca_b200_comm_init(self._h, buf, int(rank), int(world)))
+        self.comm_rank, self.comm_world = int(rank), int(world)
+
+    def comm_destroy(self) -> None:
+        check(lib().ppca_b200_comm_destroy(self._h))
+
+    def comm_allreduce(self, dev_ptr: int, count: int, op: str = "sum") -> None:
+        check(lib().ppca_b200_comm_allreduce(self._h, C.c_void_p(dev_ptr), int(count), {"sum": 0, "max": 1}[op]))
 
     def set_chunk(self, chunk: int) -> None:
         check(lib().ppca_b200_ctx_set_chunk(self._h, int(chunk)))

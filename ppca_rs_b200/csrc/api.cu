@@ -53,6 +53,9 @@ struct ppca_b200_ctx {
   DevBuf<double> GW, YZ, WZ, nx, llk, tn, part_bg, part_cr, part_solve, stats, Cnew, cov, rbuf;
   DevBuf<double> mixLP, mixLlk, mixMax, mixSum, mixStats;  // mixture workspaces (grow-only, no per-call cudaMalloc)
   DevBuf<int> flags;
+  // sample-sharded EM: NCCL communicator of this rank (ppca_b200_comm_init), null = single process
+  void *comm = nullptr;
+  int comm_rank = 0, comm_world = 1;
   // pinned staging
   double *pinned = nullptr;
   size_t pinned_count = 0;
@@ -899,6 +902,13 @@ int32_t ppca_b200_ctx_destroy(ppca_b200_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
+    if (ctx->comm) {
+      try {
+        comm_destroy(ctx->comm);
+      } catch (...) {
+      }
+      ctx->comm = nullptr;
+    }
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     for (int b = 0; b < 2; ++b)
       if (ctx->upload_pin[b]) cudaFreeHost(ctx->upload_pin[b]);
@@ -1872,46 +1882,161 @@ int32_t ppca_b200_mix_em_stats(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, 
   });
 }
 
+static void mix_iterate_impl(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int32_t m, const int32_t *ks,
+                             const double *Cs, const double *mus, const double *sigmas, const double *log_weights,
+                             const ppca_b200_prior *prior, double *Cs_out, double *mus_out, double *sigmas_out,
+                             double *log_weights_out, double *llk_in, bool sharded) {
+  check_ds(ctx, ds);
+  MixView mv{m, ks, Cs, mus, sigmas, log_weights, ds->store->d};
+  check_mix(mv);
+  REQUIRE(Cs_out && mus_out && sigmas_out && log_weights_out, "null output");
+  REQUIRE(!sharded || ctx->comm != nullptr, "no communicator: call ppca_b200_comm_init first");
+  const SampleStore &st = *ds->store;
+  if (st.n == 0 && !sharded) PPCA_THROW(PPCA_ERR_EMPTY, "dataset not empty (mix.rs:315)");
+  DeviceGuard g(ctx->device);
+  DevBuf<double> &LP = ctx->mixLP;
+  LP.reserve((size_t)std::max<int64_t>(st.n, 1) * m);
+  std::vector<double> cmax(m + 1);
+  double llk_local = 0.0;
+  int32_t rc = ppca_b200_mix_posteriors(ctx, ds, m, ks, Cs, mus, sigmas, log_weights, LP.p, cmax.data(), &llk_local);
+  if (rc) throw Error{rc, g_last_error};
+  if (sharded) {  // global per-component maxima (mix.rs:312-318) and the global log-likelihood
+    ctx->mixMax.reserve((size_t)m + 1);
+    cmax[m] = llk_local;
+    CUDA_CHECK(cudaMemcpyAsync(ctx->mixMax.p, cmax.data(), sizeof(double) * (m + 1), cudaMemcpyHostToDevice, ctx->stream));
+    comm_allreduce(ctx->comm, ctx->mixMax.p, m, 1, ctx->stream);
+    comm_allreduce(ctx->comm, ctx->mixMax.p + m, 1, 0, ctx->stream);
+    CUDA_CHECK(cudaMemcpyAsync(cmax.data(), ctx->mixMax.p, sizeof(double) * (m + 1), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    llk_local = cmax[m];
+  }
+  if (llk_in) *llk_in = llk_local;
+  std::vector<double> logsum(m);
+  for (int j = 0; j < m; ++j) {
+    const int kj = ks[j];
+    DevBuf<double> &stats = ctx->mixStats;
+    const int64_t slen = StatsLayout(st.d, kj).len;
+    stats.reserve((size_t)slen);
+    double sumw = 0.0;
+    const size_t off = (size_t)(mv.C(j) - Cs);
+    for (;;) {  // one guarded pass per component (ppca_b200_mix_em_stats starts at the remembered rung)
+      rc = ppca_b200_mix_em_stats(ctx, ds, m, j, kj, mv.C(j), mv.mu(j), sigmas[j], LP.p, cmax[j], stats.p);
+      if (rc) throw Error{rc, g_last_error};
+      if (sharded) comm_allreduce(ctx->comm, stats.p, slen, 0, ctx->stream);
+      const double viol = em_finish_impl(ctx, st.d, kj, mv.C(j), mv.mu(j), sigmas[j], prior, stats.p, Cs_out + off,
+                                         mus_out + (size_t)j * st.d, sigmas_out + j, nullptr, &sumw);
+      if (end_pass(ctx, viol)) break;
+    }
+    logsum[j] = std::log(sumw) + cmax[j];  // mix.rs:323-324
+  }
+  // robust_log_softmax (mix.rs:14-18, :335)
+  double mx = logsum[0];
+  for (int j = 1; j < m; ++j) mx = logsum[j] > mx ? logsum[j] : mx;
+  double s = 0.0;
+  for (int j = 0; j < m; ++j) s += std::exp(logsum[j] - mx);
+  const double ln = std::log(s);
+  for (int j = 0; j < m; ++j) log_weights_out[j] = logsum[j] - mx - ln;
+}
+
 int32_t ppca_b200_mix_iterate(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int32_t m, const int32_t *ks,
                               const double *Cs, const double *mus, const double *sigmas, const double *log_weights,
                               const ppca_b200_prior *prior, double *Cs_out, double *mus_out, double *sigmas_out,
                               double *log_weights_out, double *llk_in) {
   return guarded([&] {
-    check_ds(ctx, ds);
-    MixView mv{m, ks, Cs, mus, sigmas, log_weights, ds->store->d};
-    check_mix(mv);
-    REQUIRE(Cs_out && mus_out && sigmas_out && log_weights_out, "null output");
-    const SampleStore &st = *ds->store;
-    if (st.n == 0) PPCA_THROW(PPCA_ERR_EMPTY, "dataset not empty (mix.rs:315)");
+    mix_iterate_impl(ctx, ds, m, ks, Cs, mus, sigmas, log_weights, prior, Cs_out, mus_out, sigmas_out, log_weights_out,
+                     llk_in, false);
+  });
+}
+
+// ---- sample-sharded EM with the collective inside the library (one process per GPU) ----------------------------------
+int32_t ppca_b200_comm_unique_id(uint8_t *out) {
+  return guarded([&] {
+    REQUIRE(out != nullptr, "null output");
+    comm_unique_id(out);
+  });
+}
+
+int32_t ppca_b200_comm_init(ppca_b200_ctx *ctx, const uint8_t *unique_id, int32_t rank, int32_t world) {
+  return guarded([&] {
+    REQUIRE(ctx != nullptr && unique_id != nullptr, "null argument");
+    REQUIRE(world >= 1 && rank >= 0 && rank < world, "bad rank %d of %d", rank, world);
+    REQUIRE(ctx->comm == nullptr, "the context already has a communicator");
     DeviceGuard g(ctx->device);
-    DevBuf<double> &LP = ctx->mixLP;
-    LP.reserve((size_t)st.n * m);
-    std::vector<double> cmax(m);
-    int32_t rc = ppca_b200_mix_posteriors(ctx, ds, m, ks, Cs, mus, sigmas, log_weights, LP.p, cmax.data(), llk_in);
-    if (rc) throw Error{rc, g_last_error};
-    std::vector<double> logsum(m);
-    for (int j = 0; j < m; ++j) {
-      const int kj = ks[j];
-      DevBuf<double> &stats = ctx->mixStats;
-      stats.reserve((size_t)StatsLayout(st.d, kj).len);
-      double sumw = 0.0;
-      const size_t off = (size_t)(mv.C(j) - Cs);
-      for (;;) {  // one guarded pass per component (ppca_b200_mix_em_stats starts at the remembered rung)
-        rc = ppca_b200_mix_em_stats(ctx, ds, m, j, kj, mv.C(j), mv.mu(j), sigmas[j], LP.p, cmax[j], stats.p);
-        if (rc) throw Error{rc, g_last_error};
-        const double viol = em_finish_impl(ctx, st.d, kj, mv.C(j), mv.mu(j), sigmas[j], prior, stats.p, Cs_out + off,
-                                           mus_out + (size_t)j * st.d, sigmas_out + j, nullptr, &sumw);
-        if (end_pass(ctx, viol)) break;
-      }
-      logsum[j] = std::log(sumw) + cmax[j];  // mix.rs:323-324
-    }
-    // robust_log_softmax (mix.rs:14-18, :335)
-    double mx = logsum[0];
-    for (int j = 1; j < m; ++j) mx = logsum[j] > mx ? logsum[j] : mx;
-    double s = 0.0;
-    for (int j = 0; j < m; ++j) s += std::exp(logsum[j] - mx);
-    const double ln = std::log(s);
-    for (int j = 0; j < m; ++j) log_weights_out[j] = logsum[j] - mx - ln;
+    ctx->comm = comm_create(unique_id, rank, world);
+    ctx->comm_rank = rank;
+    ctx->comm_world = world;
+  });
+}
+
+int32_t ppca_b200_comm_destroy(ppca_b200_ctx *ctx) {
+  return guarded([&] {
+    REQUIRE(ctx != nullptr, "null context");
+    if (!ctx->comm) return;
+    DeviceGuard g(ctx->device);
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    comm_destroy(ctx->comm);
+    ctx->comm = nullptr;
+    ctx->comm_rank = 0;
+    ctx->comm_world = 1;
+  });
+}
+
+int32_t ppca_b200_comm_allreduce(ppca_b200_ctx *ctx, double *buf_dev, int64_t count, int32_t op) {
+  return guarded([&] {
+    REQUIRE(ctx != nullptr && ctx->comm != nullptr, "no communicator: call ppca_b200_comm_init first");
+    REQUIRE(buf_dev != nullptr && count >= 0 && (op == 0 || op == 1), "bad all-reduce arguments");
+    DeviceGuard g(ctx->device);
+    comm_allreduce(ctx->comm, buf_dev, count, op, ctx->stream);
+  });
+}
+
+int32_t ppca_b200_iterate_sharded(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int32_t k, const double *C,
+                                  const double *mu, double sigma, const ppca_b200_prior *prior, double *C_out,
+                                  double *mu_out, double *sigma_out, double *llk_in) {
+  return guarded([&] {
+    check_ds(ctx, ds);
+    REQUIRE(ctx->comm != nullptr, "no communicator: call ppca_b200_comm_init first");
+    const SampleStore &st = *ds->store;
+    DeviceGuard g(ctx->device);
+    const int64_t slen = StatsLayout(st.d, k).len;
+    run_guarded(ctx, [&] {  // the guard counters ride in the reduced buffer: every rank repeats (or accepts) together
+      DevModel m = stage_model(ctx, st.d, k, C, mu, sigma);
+      ctx->stats.reserve((size_t)slen);
+      em_stats_impl(ctx, st, ds->w.p, m, ctx->stats.p);
+      comm_allreduce(ctx->comm, ctx->stats.p, slen, 0, ctx->stream);
+      return em_finish_impl(ctx, st.d, k, C, mu, sigma, prior, ctx->stats.p, C_out, mu_out, sigma_out, llk_in, nullptr);
+    });
+  });
+}
+
+int32_t ppca_b200_iterate_host_sharded(ppca_b200_ctx *ctx, const double *x, int64_t n, int32_t d, const double *weights,
+                                       int32_t k, const double *C, const double *mu, double sigma,
+                                       const ppca_b200_prior *prior, double *C_out, double *mu_out, double *sigma_out,
+                                       double *llk_in) {
+  return guarded([&] {
+    REQUIRE(ctx != nullptr && ctx->comm != nullptr, "no communicator: call ppca_b200_comm_init first");
+    REQUIRE(n >= 0 && d >= 1, "bad dataset shape %lld x %d", (long long)n, d);
+    REQUIRE(n == 0 || x != nullptr, "null data");
+    DeviceGuard g(ctx->device);
+    const int64_t slen = StatsLayout(d, k).len;
+    run_guarded(ctx, [&] {
+      DevModel m = stage_model(ctx, d, k, C, mu, sigma);
+      ctx->stats.reserve((size_t)slen);
+      if (n == 0) CUDA_CHECK(cudaMemsetAsync(ctx->stats.p, 0, sizeof(double) * slen, ctx->stream));
+      else em_stats_host_impl(ctx, x, n, d, weights, m, ctx->stats.p);
+      comm_allreduce(ctx->comm, ctx->stats.p, slen, 0, ctx->stream);
+      return em_finish_impl(ctx, d, k, C, mu, sigma, prior, ctx->stats.p, C_out, mu_out, sigma_out, llk_in, nullptr);
+    });
+  });
+}
+
+int32_t ppca_b200_mix_iterate_sharded(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int32_t m, const int32_t *ks,
+                                      const double *Cs, const double *mus, const double *sigmas,
+                                      const double *log_weights, const ppca_b200_prior *prior, double *Cs_out,
+                                      double *mus_out, double *sigmas_out, double *log_weights_out, double *llk_in) {
+  return guarded([&] {
+    mix_iterate_impl(ctx, ds, m, ks, Cs, mus, sigmas, log_weights, prior, Cs_out, mus_out, sigmas_out, log_weights_out,
+                     llk_in, true);
   });
 }
 

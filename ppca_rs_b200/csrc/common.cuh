@@ -301,6 +301,13 @@ void launch_scale_max(const Launcher &L, const double *scale, int n, double *sma
 void launch_row_solve(const Launcher &L, int d, int k, const double *statA, const double *statB, double tau,
                       const double *Cold_pad, double *Cnew /* d x k dense */, int *flags);
 
+// comm.cu : NCCL bound at run time (see the file header)
+void comm_unique_id(uint8_t *out128);
+void *comm_create(const uint8_t *id128, int rank, int world);
+void comm_destroy(void *comm);
+void comm_allreduce(void *comm, double *buf_dev, int64_t count, int op /* 0 = sum, 1 = max */, cudaStream_t stream);
+int comm_version();
+
 // mix.cu
 void launch_log_softmax_rows(const Launcher &L, double *LP, int64_t n, int m, const double *logw_dev,
                              const double *w, double *mix_llk /* n, nullable */, double *comp_max /* m */,
