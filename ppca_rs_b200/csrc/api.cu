@@ -52,6 +52,8 @@ struct ppca_b200_ctx {
   // chunk workspaces
   DevBuf<double> GW, YZ, WZ, nx, llk, tn, part_bg, part_cr, part_solve, stats, Cnew, cov, rbuf;
   DevBuf<double> mixLP, mixLlk, mixMax, mixSum, mixStats;  // mixture workspaces (grow-only, no per-call cudaMalloc)
+  DevBuf<double> mixArena;                                 // single-pass mixture EM: per-component chunk buffers
+  DevBuf<int8_t> mixArenaQ;                                //   ... and their digit planes
   DevBuf<int> flags;
   // sample-sharded EM: NCCL communicator of this rank (ppca_b200_comm_init), null = single process
   void *comm = nullptr;
@@ -291,18 +293,15 @@ void run_guarded(ppca_b200_ctx *ctx, Body &&body) {
   }
 }
 
-// uploads (C, mu) and builds the padded model + Ksym table on the device
-DevModel stage_model(ppca_b200_ctx *ctx, int d, int k, const double *C, const double *mu, double sigma,
-                     bool need_ksym = true) {
+// uploads (C, mu) and builds the padded model + Ksym table (+ its digit planes) into the given device buffers
+DevModel stage_model_into(ppca_b200_ctx *ctx, int d, int k, const double *C, const double *mu, double sigma, double *Cpad,
+                          double *mupad, double *Ksym, int8_t *KsymQ, double *KsymScale, unsigned long long *colmax) {
   REQUIRE(k >= 1, "state_size must be >= 1 (got %d)", k);
   REQUIRE(C && mu, "null model parameters");
   REQUIRE(sigma > 0.0 && std::isfinite(sigma), "isotropic_noise must be positive and finite");
   Shape s(d, k);
   ctx->Cdense.reserve((size_t)d * k);
   ctx->mudense.reserve((size_t)d);
-  ctx->Cpad.reserve((size_t)s.d32 * s.kp);
-  ctx->mupad.reserve((size_t)s.d32);
-  ctx->Ksym.reserve((size_t)s.d32 * s.kkp);
   double *stage = ctx->pin((size_t)d * k + d);
   CUDA_CHECK(cudaStreamSynchronize(ctx->stream));  // staging buffer may still be in flight
   memcpy(stage, C, sizeof(double) * d * k);
@@ -311,30 +310,65 @@ DevModel stage_model(ppca_b200_ctx *ctx, int d, int k, const double *C, const do
   CUDA_CHECK(cudaMemcpyAsync(ctx->mudense.p, stage + (size_t)d * k, sizeof(double) * d, cudaMemcpyHostToDevice,
                              ctx->stream));
   ctx->span_begin(FAM_KSYM);
-  launch_prepare_model(ctx->L(), ctx->Cdense.p, ctx->mudense.p, d, k, ctx->Cpad.p, ctx->mupad.p, ctx->Ksym.p);
-  if (ctx->gemm_mode == 2) {
-    const int kblocks = s.d32 / 32;
-    ctx->KsymQ.reserve(sliced_tc_bytes(kblocks, s.kkp, ctx->slices));
-    ctx->KsymScale.reserve((size_t)s.kkp);
-    ctx->colmax.reserve((size_t)s.kkp);
-    launch_slice_tc(ctx->L(), ctx->Ksym.p, s.kkp, d, s.kkp, kblocks, ctx->slices, ctx->KsymQ.p, ctx->KsymScale.p,
-                    ctx->colmax.p);
-  } else if (ctx->gemm_mode == 1) {
-    const int kblocks = s.d32 / 32;
-    ctx->KsymQ.reserve(sliced_bytes(kblocks, s.kkp, ctx->slices));
-    ctx->KsymScale.reserve((size_t)s.kkp);
-    ctx->colmax.reserve((size_t)s.kkp);
-    launch_slice(ctx->L(), ctx->Ksym.p, s.kkp, d, s.kkp, kblocks, ctx->slices, ctx->KsymQ.p, ctx->KsymScale.p,
-                 ctx->colmax.p);
-  }
+  launch_prepare_model(ctx->L(), ctx->Cdense.p, ctx->mudense.p, d, k, Cpad, mupad, Ksym);
+  const int kblocks = s.d32 / 32;
+  if (ctx->gemm_mode == 2)
+    launch_slice_tc(ctx->L(), Ksym, s.kkp, d, s.kkp, kblocks, ctx->slices, KsymQ, KsymScale, colmax);
+  else if (ctx->gemm_mode == 1)
+    launch_slice(ctx->L(), Ksym, s.kkp, d, s.kkp, kblocks, ctx->slices, KsymQ, KsymScale, colmax);
   ctx->span_end();
   DevModel m;
   m.s = s;
   m.sigma = sigma;
-  m.C = ctx->Cpad.p;
-  m.mu = ctx->mupad.p;
-  m.Ksym = ctx->Ksym.p;
+  m.C = Cpad;
+  m.mu = mupad;
+  m.Ksym = Ksym;
   return m;
+}
+
+size_t ksym_planes_bytes(const ppca_b200_ctx *ctx, const Shape &s) {
+  const int kblocks = s.d32 / 32;
+  return ctx->gemm_mode == 2 ? sliced_tc_bytes(kblocks, s.kkp, ctx->slices)
+                             : (ctx->gemm_mode == 1 ? sliced_bytes(kblocks, s.kkp, ctx->slices) : 0);
+}
+
+// single model: into the context's own buffers
+DevModel stage_model(ppca_b200_ctx *ctx, int d, int k, const double *C, const double *mu, double sigma,
+                     bool need_ksym = true) {
+  REQUIRE(k >= 1, "state_size must be >= 1 (got %d)", k);
+  Shape s(d, k);
+  ctx->Cpad.reserve((size_t)s.d32 * s.kp);
+  ctx->mupad.reserve((size_t)s.d32);
+  ctx->Ksym.reserve((size_t)s.d32 * s.kkp);
+  if (ctx->gemm_mode != 0) {
+    ctx->KsymQ.reserve(ksym_planes_bytes(ctx, s));
+    ctx->KsymScale.reserve((size_t)s.kkp);
+    ctx->colmax.reserve((size_t)s.kkp);
+  }
+  return stage_model_into(ctx, d, k, C, mu, sigma, ctx->Cpad.p, ctx->mupad.p, ctx->Ksym.p, ctx->KsymQ.p,
+                          ctx->KsymScale.p, ctx->colmax.p);
+}
+
+// the buffers a model's chunk kernels work on: its own set (mixture pass) or the context's
+ModelWs resolve_ws(ppca_b200_ctx *ctx, const DevModel &m) {
+  if (m.ws) return *m.ws;
+  ModelWs w;
+  w.GW = ctx->GW.p;
+  w.YZ = ctx->YZ.p;
+  w.WZ = ctx->WZ.p;
+  w.nx = ctx->nx.p;
+  w.llk = ctx->llk.p;
+  w.tn = ctx->tn.p;
+  w.KsymQ = ctx->KsymQ.p;
+  w.KsymScale = ctx->KsymScale.p;
+  w.WQ = ctx->WQ.p;
+  w.WScale = ctx->WScale.p;
+  w.WScaleMax = ctx->WScaleMax.p;
+  w.colmax = ctx->colmax.p;
+  w.part_bg = ctx->part_bg.p;
+  w.part_cr = ctx->part_cr.p;
+  w.part_solve = ctx->part_solve.p;
+  return w;
 }
 
 void reserve_chunk_ws(ppca_b200_ctx *ctx, int64_t chunk, const Shape &s) {
@@ -351,19 +385,20 @@ void e_step_chunk(ppca_b200_ctx *ctx, const SampleStore &st, const double *w, in
                   const DevModel &m, int mode, double *llk_out, double *cov_out, double *solve_part,
                   unsigned long long *w_colmax = nullptr) {
   const Launcher L = ctx->L();
+  const ModelWs ws = resolve_ws(ctx, m);
   const int rows_pad = (int)round_up(rows, 256);
   ctx->span_begin(FAM_GRAM);
   if (ctx->gemm_mode == 2) {
-    launch_tbitgemm(L, st.mask.p + row0 * st.dw, st.dw, st.dw, ctx->KsymQ.p, ctx->KsymScale.p, ctx->slices, ctx->GW.p,
+    launch_tbitgemm(L, st.mask.p + row0 * st.dw, st.dw, st.dw, ws.KsymQ, ws.KsymScale, ctx->slices, ws.GW,
                     m.s.kkp, rows, m.s.kkp, (m.s.d32 / 32 + 3) / 4, 0, nullptr, 1, 0);
   } else if (ctx->gemm_mode == 1) {
     IBitGemmArgs g;
     g.bits = st.mask.p + row0 * st.dw;
     g.ldbits = st.dw;
-    g.Bq = ctx->KsymQ.p;
-    g.scale = ctx->KsymScale.p;
+    g.Bq = ws.KsymQ;
+    g.scale = ws.KsymScale;
     g.T = ctx->slices;
-    g.Out = ctx->GW.p;
+    g.Out = ws.GW;
     g.ldo = m.s.kkp;
     g.M = rows;
     g.Nq = m.s.kkp;
@@ -379,7 +414,7 @@ void e_step_chunk(ppca_b200_ctx *ctx, const SampleStore &st, const double *w, in
     g.ldbits = st.dw;
     g.Bmat = m.Ksym;
     g.ldb = m.s.kkp;
-    g.Out = ctx->GW.p;
+    g.Out = ws.GW;
     g.ldo = m.s.kkp;
     g.M = rows;
     g.Nq = m.s.kkp;
@@ -393,27 +428,27 @@ void e_step_chunk(ppca_b200_ctx *ctx, const SampleStore &st, const double *w, in
   }
   ctx->span_end();
   ctx->span_begin(FAM_PROJ);
-  launch_proj(L, st, row0, rows, m, ctx->YZ.p, ctx->nx.p);
+  launch_proj(L, st, row0, rows, m, ws.YZ, ws.nx);
   ctx->span_end();
   SolveArgs sa;
   sa.s = m.s;
   sa.sigma = m.sigma;
   sa.rows = rows;
   sa.rows_pad = rows_pad;
-  sa.GW = ctx->GW.p;
-  sa.YZ = ctx->YZ.p;
-  sa.WZ = mode == 2 ? ctx->WZ.p : nullptr;
-  sa.nx = ctx->nx.p;
+  sa.GW = ws.GW;
+  sa.YZ = ws.YZ;
+  sa.WZ = (mode == 2 && w) ? ws.WZ : nullptr;
+  sa.nx = ws.nx;
   sa.dn = st.dn.p + row0;
   sa.w = w ? w + row0 : nullptr;
   sa.llk = llk_out;
-  sa.tn = mode == 2 ? ctx->tn.p : nullptr;
+  sa.tn = mode == 2 ? ws.tn : nullptr;
   sa.cov = cov_out;
   sa.part = solve_part;
   sa.mode = mode;
   sa.colmax = w_colmax;
   if (guard_on(ctx)) {
-    sa.gscale = ctx->KsymScale.p;
+    sa.gscale = ws.KsymScale;
     sa.guard_coef = guard_coef(ctx);
     sa.unsafe = ctx->unsafe.p;
   }
@@ -434,67 +469,74 @@ struct EmPlan {
   int slabs = 1;
 };
 
-EmPlan em_begin(ppca_b200_ctx *ctx, int64_t chunk, const DevModel &m, double *stats_dev) {
-  const StatsLayout lay(m.s.d, m.s.k);
-  CUDA_CHECK(cudaMemsetAsync(stats_dev, 0, sizeof(double) * lay.len, ctx->stream));
+size_t wq_bytes(const ppca_b200_ctx *ctx, int64_t chunk, const Shape &s) {
+  const int kb_chunk = (int)(chunk / 32);
+  return ctx->gemm_mode == 2 ? sliced_tc_bytes(kb_chunk, s.kkp, ctx->slices)
+                             : (ctx->gemm_mode == 1 ? sliced_bytes(kb_chunk, s.kkp, ctx->slices) : 0);
+}
+
+// sizes of the split-K / slab partial slots for chunks of `chunk` rows
+EmPlan em_plan(const ppca_b200_ctx *ctx, int64_t chunk, const Shape &s) {
   EmPlan p;
   p.chunk = chunk;
-  reserve_chunk_ws(ctx, p.chunk, m.s);
   const int kb_chunk = (int)(p.chunk / 32);
-  p.splitk = ctx->gemm_mode == 2   ? tbitgemm_pick_splitk(m.s.d, m.s.kkp, kb_chunk / 4, ctx->sms)
-             : ctx->gemm_mode == 1 ? ibitgemm_pick_splitk(m.s.d, m.s.kkp, kb_chunk, ctx->sms)
-                                   : bitgemm_pick_splitk(m.s.d, m.s.kkp, kb_chunk, ctx->sms);
-  p.bglen = bitgemm_partials_len(m.s.d, m.s.kkp, p.splitk);
-  if (ctx->gemm_mode == 2) {
-    ctx->WQ.reserve(sliced_tc_bytes(kb_chunk, m.s.kkp, ctx->slices));
-    ctx->WScale.reserve((size_t)m.s.kkp);
-    ctx->colmax.reserve((size_t)m.s.kkp);
-  } else if (ctx->gemm_mode == 1) {
-    ctx->WQ.reserve(sliced_bytes(kb_chunk, m.s.kkp, ctx->slices));
+  p.splitk = ctx->gemm_mode == 2   ? tbitgemm_pick_splitk(s.d, s.kkp, kb_chunk / 4, ctx->sms)
+             : ctx->gemm_mode == 1 ? ibitgemm_pick_splitk(s.d, s.kkp, kb_chunk, ctx->sms)
+                                   : bitgemm_pick_splitk(s.d, s.kkp, kb_chunk, ctx->sms);
+  p.bglen = bitgemm_partials_len(s.d, s.kkp, p.splitk);
+  p.slabs = cross_resid_slabs(s.d, s.k, (int)p.chunk, ctx->sms);
+  p.crlen = cross_resid_partials_len(s.d, s.k, p.slabs);
+  return p;
+}
+
+// zeroes the statistics and the partial slots of one model
+void em_zero(ppca_b200_ctx *ctx, const ModelWs &ws, const EmPlan &p, const Shape &s, double *stats_dev) {
+  CUDA_CHECK(cudaMemsetAsync(stats_dev, 0, sizeof(double) * StatsLayout(s.d, s.k).len, ctx->stream));
+  if (guard_on(ctx)) CUDA_CHECK(cudaMemsetAsync(ws.WScaleMax, 0, sizeof(double) * s.kkp, ctx->stream));
+  if (p.bglen) CUDA_CHECK(cudaMemsetAsync(ws.part_bg, 0, sizeof(double) * p.bglen, ctx->stream));
+  CUDA_CHECK(cudaMemsetAsync(ws.part_cr, 0, sizeof(double) * p.crlen, ctx->stream));
+  CUDA_CHECK(cudaMemsetAsync(ws.part_solve, 0, sizeof(double) * SOLVE_SLOTS * 4, ctx->stream));
+}
+
+EmPlan em_begin(ppca_b200_ctx *ctx, int64_t chunk, const DevModel &m, double *stats_dev) {
+  const EmPlan p = em_plan(ctx, chunk, m.s);
+  reserve_chunk_ws(ctx, p.chunk, m.s);
+  if (ctx->gemm_mode != 0) {
+    ctx->WQ.reserve(wq_bytes(ctx, p.chunk, m.s));
     ctx->WScale.reserve((size_t)m.s.kkp);
     ctx->colmax.reserve((size_t)m.s.kkp);
   }
   ctx->em_rows = 0;
-  if (guard_on(ctx)) {
-    ctx->WScaleMax.reserve((size_t)m.s.kkp);
-    CUDA_CHECK(cudaMemsetAsync(ctx->WScaleMax.p, 0, sizeof(double) * m.s.kkp, ctx->stream));
-  }
+  if (guard_on(ctx)) ctx->WScaleMax.reserve((size_t)m.s.kkp);
   ctx->part_bg.reserve(p.bglen);
-  p.slabs = cross_resid_slabs(m.s.d, m.s.k, (int)p.chunk, ctx->sms);
-  p.crlen = cross_resid_partials_len(m.s.d, m.s.k, p.slabs);
   ctx->part_cr.reserve(p.crlen);
   ctx->part_solve.reserve((size_t)SOLVE_SLOTS * 4);
-  if (p.bglen) CUDA_CHECK(cudaMemsetAsync(ctx->part_bg.p, 0, sizeof(double) * p.bglen, ctx->stream));
-  CUDA_CHECK(cudaMemsetAsync(ctx->part_cr.p, 0, sizeof(double) * p.crlen, ctx->stream));
-  CUDA_CHECK(cudaMemsetAsync(ctx->part_solve.p, 0, sizeof(double) * SOLVE_SLOTS * 4, ctx->stream));
+  em_zero(ctx, resolve_ws(ctx, m), p, m.s, stats_dev);
   return p;
 }
 
-void em_chunk(ppca_b200_ctx *ctx, const SampleStore &st, const double *w, int64_t row0, int rows, const DevModel &m,
-              double *stats_dev, const EmPlan &p) {
+// M-step statistics of one chunk whose second moments W (ws.GW), states (ws.YZ) and weighted states (ws.WZ) are in place;
+// wloc = the chunk's weights (index 0 = row0); have_colmax: ws.colmax already holds max_n |W[n][q]|
+void m_step_chunk(ppca_b200_ctx *ctx, const SampleStore &st, const double *wloc, int64_t row0, int rows, const DevModel &m,
+                  double *stats_dev, const EmPlan &p, bool have_colmax) {
   const Launcher L = ctx->L();
+  const ModelWs ws = resolve_ws(ctx, m);
   const StatsLayout lay(m.s.d, m.s.k);
   const int splitk = p.splitk;
-  // the solve kernels (state_size <= 64) leave the column maxima of W behind for the tcgen05 digit planes
-  const bool fused_colmax = ctx->gemm_mode == 2 && m.s.k <= 64;
-  e_step_chunk(ctx, st, w, row0, rows, m, 2, ctx->llk.p, nullptr, ctx->part_solve.p,
-               fused_colmax ? ctx->colmax.p : nullptr);
   const int kblocks = (int)(round_up(rows, 32) / 32);
   int sk = splitk < kblocks ? splitk : (kblocks > 0 ? kblocks : 1);
   if (splitk > 1 && sk < 2) sk = 2 <= kblocks ? 2 : 1;
   const bool direct = splitk > 1 && sk == 1;  // degenerate last chunk: accumulate straight into the statistics
   if (ctx->gemm_mode == 2) {
     ctx->span_begin(FAM_SLICE);
-    launch_slice_tc(L, ctx->GW.p, m.s.kkp, rows, m.s.kkp, kblocks, ctx->slices, ctx->WQ.p, ctx->WScale.p,
-                    ctx->colmax.p, fused_colmax);
+    launch_slice_tc(L, ws.GW, m.s.kkp, rows, m.s.kkp, kblocks, ctx->slices, ws.WQ, ws.WScale, ws.colmax, have_colmax);
     ctx->span_end();
   } else if (ctx->gemm_mode == 1) {
     ctx->span_begin(FAM_SLICE);
-    launch_slice(L, ctx->GW.p, m.s.kkp, rows, m.s.kkp, kblocks, ctx->slices, ctx->WQ.p, ctx->WScale.p, ctx->colmax.p);
+    launch_slice(L, ws.GW, m.s.kkp, rows, m.s.kkp, kblocks, ctx->slices, ws.WQ, ws.WScale, ws.colmax);
     ctx->span_end();
   }
-  ctx->em_rows += rows;
-  if (guard_on(ctx)) launch_scale_max(L, ctx->WScale.p, m.s.kkp, ctx->WScaleMax.p);
+  if (guard_on(ctx)) launch_scale_max(L, ws.WScale, m.s.kkp, ws.WScaleMax);
   ctx->span_begin(FAM_MOMENT);
   if (ctx->gemm_mode == 2) {
     const int ksteps = (kblocks + 3) / 4;
@@ -505,15 +547,15 @@ void em_chunk(ppca_b200_ctx *ctx, const SampleStore &st, const double *w, int64_
       skt = (ksteps + per - 1) / per;
     }
     const bool to_partials = splitk > 1 && skt > 1;
-    launch_tbitgemm(L, st.maskT.p + row0 / 32, st.nwT, 4 * ksteps, ctx->WQ.p, ctx->WScale.p, ctx->slices,
-                    stats_dev + lay.offA, m.s.kkp, m.s.d, m.s.kkp, ksteps, 1, to_partials ? ctx->part_bg.p : nullptr,
+    launch_tbitgemm(L, st.maskT.p + row0 / 32, st.nwT, 4 * ksteps, ws.WQ, ws.WScale, ctx->slices,
+                    stats_dev + lay.offA, m.s.kkp, m.s.d, m.s.kkp, ksteps, 1, to_partials ? ws.part_bg : nullptr,
                     skt, to_partials ? 1 : 0);
   } else if (ctx->gemm_mode == 1) {
     IBitGemmArgs g;
     g.bits = st.maskT.p + row0 / 32;
     g.ldbits = st.nwT;
-    g.Bq = ctx->WQ.p;
-    g.scale = ctx->WScale.p;
+    g.Bq = ws.WQ;
+    g.scale = ws.WScale;
     g.T = ctx->slices;
     g.Out = stats_dev + lay.offA;
     g.ldo = m.s.kkp;
@@ -522,14 +564,14 @@ void em_chunk(ppca_b200_ctx *ctx, const SampleStore &st, const double *w, int64_
     g.kblocks = kblocks;
     g.accumulate = 1;
     g.splitk = sk;
-    g.partials = (splitk > 1 && !direct) ? ctx->part_bg.p : nullptr;
+    g.partials = (splitk > 1 && !direct) ? ws.part_bg : nullptr;
     g.defer_reduce = direct ? 0 : 1;
     launch_ibitgemm(L, g);
   } else {
     BitGemmArgs g;
     g.bits = st.maskT.p + row0 / 32;
     g.ldbits = st.nwT;
-    g.Bmat = ctx->GW.p;
+    g.Bmat = ws.GW;
     g.ldb = m.s.kkp;
     g.Out = stats_dev + lay.offA;
     g.ldo = m.s.kkp;
@@ -539,33 +581,45 @@ void em_chunk(ppca_b200_ctx *ctx, const SampleStore &st, const double *w, int64_
     g.kcols = 32 * kblocks;
     g.accumulate = 1;
     g.splitk = sk;
-    g.partials = (splitk > 1 && !direct) ? ctx->part_bg.p : nullptr;
+    g.partials = (splitk > 1 && !direct) ? ws.part_bg : nullptr;
     g.defer_reduce = direct ? 0 : 1;
     launch_bitgemm(L, g);
   }
   ctx->span_end();
   ctx->span_begin(FAM_CROSS);
-  launch_cross_resid(L, st, row0, rows, m, ctx->YZ.p, ctx->WZ.p, w + row0, ctx->part_cr.p, p.slabs);
+  launch_cross_resid(L, st, row0, rows, m, ws.YZ, ws.WZ, wloc, ws.part_cr, p.slabs);
   ctx->span_end();
 }
 
-void em_end(ppca_b200_ctx *ctx, const DevModel &m, double *stats_dev, const EmPlan &p) {
+void em_chunk(ppca_b200_ctx *ctx, const SampleStore &st, const double *w, int64_t row0, int rows, const DevModel &m,
+              double *stats_dev, const EmPlan &p) {
+  const ModelWs ws = resolve_ws(ctx, m);
+  // the solve kernels (state_size <= 64) leave the column maxima of W behind for the tcgen05 digit planes
+  const bool fused_colmax = ctx->gemm_mode == 2 && m.s.k <= 64;
+  e_step_chunk(ctx, st, w, row0, rows, m, 2, ws.llk, nullptr, ws.part_solve, fused_colmax ? ws.colmax : nullptr);
+  ctx->em_rows += rows;
+  m_step_chunk(ctx, st, w + row0, row0, rows, m, stats_dev, p, fused_colmax);
+}
+
+void em_end(ppca_b200_ctx *ctx, const DevModel &m, double *stats_dev, const EmPlan &p, int64_t rows_total = -1) {
   const Launcher L = ctx->L();
+  const ModelWs ws = resolve_ws(ctx, m);
   const StatsLayout lay(m.s.d, m.s.k);
+  if (rows_total < 0) rows_total = ctx->em_rows;
   ctx->span_begin(FAM_SOLVE);
-  launch_solve_finish(L, ctx->part_solve.p, stats_dev + lay.offScalars);
+  launch_solve_finish(L, ws.part_solve, stats_dev + lay.offScalars);
   ctx->span_end();
   ctx->span_begin(FAM_MOMENT);
-  launch_bitgemm_reduce(L, ctx->part_bg.p, p.splitk, m.s.d, m.s.kkp, stats_dev + lay.offA, m.s.kkp, 1);
+  launch_bitgemm_reduce(L, ws.part_bg, p.splitk, m.s.d, m.s.kkp, stats_dev + lay.offA, m.s.kkp, 1);
   ctx->span_end();
   ctx->span_begin(FAM_CROSS);
-  launch_cross_resid_finish(L, m.s.d, m.s.k, ctx->part_cr.p, p.slabs, stats_dev + lay.offB, stats_dev + lay.offTdev,
+  launch_cross_resid_finish(L, m.s.d, m.s.k, ws.part_cr, p.slabs, stats_dev + lay.offB, stats_dev + lay.offTdev,
                             stats_dev + lay.offTotals, stats_dev + lay.offScalars);
   ctx->span_end();
   if (guard_on(ctx)) {  // scalars 5, 6: guard violations of this shard's E- and M-step contractions
     ctx->span_begin(FAM_FINISH);
-    launch_mstep_guard(L, m.s.d, m.s.k, stats_dev + lay.offA, stats_dev + lay.offTotals, ctx->WScaleMax.p,
-                       guard_terms((double)ctx->em_rows) * guard_coef(ctx), ctx->unsafe.p, stats_dev + lay.offScalars);
+    launch_mstep_guard(L, m.s.d, m.s.k, stats_dev + lay.offA, stats_dev + lay.offTotals, ws.WScaleMax,
+                       guard_terms((double)rows_total) * guard_coef(ctx), ctx->unsafe.p, stats_dev + lay.offScalars);
     ctx->span_end();
   }
 }
@@ -1882,10 +1936,196 @@ int32_t ppca_b200_mix_em_stats(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, 
   });
 }
 
-static void mix_iterate_impl(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int32_t m, const int32_t *ks,
-                             const double *Cs, const double *mus, const double *sigmas, const double *log_weights,
-                             const ppca_b200_prior *prior, double *Cs_out, double *mus_out, double *sigmas_out,
-                             double *log_weights_out, double *llk_in, bool sharded) {
+}  // extern "C"
+
+namespace {
+
+// ---- single-pass mixture EM (mix.rs:281-337) ---------------------------------------------------------------------
+// The reference runs the E-step of every component twice per iteration: once for the posteriors (infer_cluster,
+// mix.rs:297-303) and once more inside each component's weighted iterate (:326).  Here ONE E-step per component and chunk
+// serves both: all components' unweighted second moments V = z z^T + Sigma, states and trace terms of a chunk stay on the
+// device while the chunk's log-posteriors are normalised, then each component weighs its V by its responsibilities and
+// runs its M-step contractions.  The responsibilities are scaled by exp(-max) of a RUNNING per-component maximum; the
+// accumulators of a component are rescaled when a later chunk raises it (see mix.cu), so the result is the reference's
+// exp(lp - max over the dataset) weighting up to rounding.
+struct MixComp {
+  DevModel m;
+  ModelWs ws;
+  EmPlan plan;
+  double *stats = nullptr;
+  int64_t stats_len = 0;
+};
+
+struct MixPass {
+  std::vector<MixComp> comps;
+  double *stats_all = nullptr;  // [stats_0 | ... | stats_{M-1} | llk_sum]   (one all-reduce)
+  int64_t stats_total = 0;      // doubles, including the trailing llk_sum
+  double *run_max = nullptr;    // M
+};
+
+struct Carver {
+  double *p;
+  size_t used = 0;
+  explicit Carver(double *base) : p(base) {}
+  double *take(size_t n) {
+    n = (n + 3) & ~(size_t)3;  // keep 32-byte alignment
+    double *r = p ? p + used : nullptr;
+    used += n;
+    return r;
+  }
+};
+
+void mix_em_pass(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, const MixView &mv, MixPass &out) {
+  const SampleStore &st = *ds->store;
+  const Launcher L = ctx->L();
+  const int M = mv.m, d = st.d;
+  std::vector<Shape> shp(M);
+  int kp_max = 8, kkp_max = 8;
+  int64_t per_row = 0, stats_total = 0;
+  for (int j = 0; j < M; ++j) {
+    REQUIRE(mv.ks[j] >= 1, "state_size must be >= 1 (got %d)", mv.ks[j]);
+    shp[j] = Shape(d, mv.ks[j]);
+    kp_max = std::max(kp_max, shp[j].kp);
+    kkp_max = std::max(kkp_max, shp[j].kkp);
+    per_row += (int64_t)(shp[j].kkp + shp[j].kp + 1) * 8;
+    stats_total += StatsLayout(d, mv.ks[j]).len;
+  }
+  per_row += (int64_t)(2 * M + kp_max + 4) * 8 + (int64_t)kkp_max * ctx->slices;
+  // rows per chunk: all components' V / Z / t of a chunk live together (at most 16 GiB), at least one wave of row tiles
+  int64_t chunk = ctx->chunk;
+  if (chunk <= 0) {
+    int64_t cap = ((int64_t)16 << 30) / per_row;
+    cap = std::min<int64_t>(cap, (int64_t)1 << 20);
+    cap = std::max<int64_t>(cap, (int64_t)ctx->sms * 128);
+    const int64_t nchunks = (st.n_pad + cap - 1) / cap;
+    chunk = (st.n_pad + nchunks - 1) / nchunks;
+  }
+  chunk = std::min<int64_t>(round_up(chunk, 256), st.n_pad);
+
+  // ---- carve the arenas (two passes: size, then pointers)
+  out.comps.assign(M, MixComp());
+  size_t need = 0, need_q = 0;
+  double *sh_nx = nullptr, *sh_llk = nullptr, *sh_WZ = nullptr, *sh_r = nullptr, *LPc = nullptr, *mixllk = nullptr,
+         *chunk_max = nullptr, *factor = nullptr;
+  int8_t *sh_WQ = nullptr;
+  for (int pass = 0; pass < 2; ++pass) {
+    if (pass == 1) {
+      ctx->mixArena.reserve(need);
+      ctx->mixArenaQ.reserve(need_q ? need_q : 1);
+      ctx->mixStats.reserve((size_t)stats_total + 1);
+    }
+    Carver cv(pass ? ctx->mixArena.p : nullptr);
+    size_t qoff = 0;
+    sh_nx = cv.take((size_t)chunk);
+    sh_llk = cv.take((size_t)chunk);
+    sh_WZ = cv.take((size_t)chunk * kp_max);
+    sh_r = cv.take((size_t)chunk);
+    LPc = cv.take((size_t)chunk * M);
+    mixllk = cv.take((size_t)chunk);
+    out.run_max = cv.take((size_t)M);
+    chunk_max = cv.take((size_t)M);
+    factor = cv.take((size_t)M);
+    sh_WQ = pass ? ctx->mixArenaQ.p + qoff : nullptr;
+    {
+      size_t wq = 0;
+      for (int j = 0; j < M; ++j) wq = std::max(wq, wq_bytes(ctx, chunk, shp[j]));
+      qoff += (wq + 1023) & ~(size_t)1023;
+    }
+    int64_t soff = 0;
+    for (int j = 0; j < M; ++j) {
+      MixComp &c = out.comps[j];
+      const Shape &s = shp[j];
+      c.plan = em_plan(ctx, chunk, s);
+      double *Cpad = cv.take((size_t)s.d32 * s.kp), *mupad = cv.take((size_t)s.d32), *Ksym = cv.take((size_t)s.d32 * s.kkp);
+      c.ws.KsymScale = cv.take((size_t)s.kkp);
+      c.ws.WScale = cv.take((size_t)s.kkp);
+      c.ws.WScaleMax = cv.take((size_t)s.kkp);
+      c.ws.colmax = reinterpret_cast<unsigned long long *>(cv.take((size_t)s.kkp));
+      c.ws.GW = cv.take((size_t)chunk * s.kkp);
+      c.ws.YZ = cv.take((size_t)chunk * s.kp);
+      c.ws.tn = cv.take((size_t)chunk);
+      c.ws.part_bg = cv.take(c.plan.bglen);
+      c.ws.part_cr = cv.take(c.plan.crlen);
+      c.ws.part_solve = cv.take((size_t)SOLVE_SLOTS * 4);
+      c.ws.nx = sh_nx;
+      c.ws.llk = sh_llk;
+      c.ws.WZ = sh_WZ;
+      c.ws.WQ = sh_WQ;
+      c.ws.KsymQ = pass ? ctx->mixArenaQ.p + qoff : nullptr;
+      qoff += (ksym_planes_bytes(ctx, s) + 1023) & ~(size_t)1023;
+      c.stats_len = StatsLayout(d, mv.ks[j]).len;
+      c.stats = pass ? ctx->mixStats.p + soff : nullptr;
+      soff += c.stats_len;
+      if (pass) {
+        c.m = stage_model_into(ctx, d, mv.ks[j], mv.C(j), mv.mu(j), mv.sigmas[j], Cpad, mupad, Ksym, c.ws.KsymQ,
+                               c.ws.KsymScale, c.ws.colmax);
+        c.m.ws = &c.ws;
+        em_zero(ctx, c.ws, c.plan, s, c.stats);
+      }
+    }
+    need = cv.used;
+    need_q = qoff;
+  }
+  out.stats_all = ctx->mixStats.p;
+  out.stats_total = stats_total + 1;
+  double *llk_sum = ctx->mixStats.p + stats_total;
+  CUDA_CHECK(cudaMemsetAsync(llk_sum, 0, sizeof(double), ctx->stream));
+  {
+    const double ninf = -std::numeric_limits<double>::infinity();
+    std::vector<double> init((size_t)M, ninf);
+    // small synchronous upload (M doubles) before any kernel of the pass reads it
+    CUDA_CHECK(cudaMemcpyAsync(out.run_max, init.data(), sizeof(double) * M, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  }
+  ctx->logw.reserve((size_t)M);
+  CUDA_CHECK(cudaMemcpyAsync(ctx->logw.p, mv.logw, sizeof(double) * M, cudaMemcpyHostToDevice, ctx->stream));
+
+  int64_t rows_total = 0;
+  for (int64_t row0 = 0; row0 < st.n; row0 += chunk) {
+    const int rows = (int)std::min<int64_t>(chunk, st.n - row0);
+    const int rows_pad = (int)round_up(rows, 256);
+    rows_total += rows;
+    // E-step of every component on this chunk (unweighted: W = V = z z^T + Sigma)
+    for (int j = 0; j < M; ++j) {
+      MixComp &c = out.comps[j];
+      e_step_chunk(ctx, st, nullptr, row0, rows, c.m, 2, sh_llk, nullptr, nullptr, nullptr);
+      const int blocks = (int)std::min<int64_t>((int64_t)ctx->sms * 8, (rows + 255) / 256);
+      strided_copy_kernel<<<blocks, 256, 0, ctx->stream>>>(sh_llk, rows, 1, 1, LPc + j, M);
+      CUDA_CHECK(cudaGetLastError());
+      ++ctx->launches;
+    }
+    // log-posteriors of the chunk (mix.rs:179-189), mixture log-likelihood (:162-174), chunk maxima of ln w + lp (:312-318)
+    launch_log_softmax_rows(L, LPc, rows, M, ctx->logw.p, ds->w.p + row0, mixllk, chunk_max, nullptr);
+    launch_weighted_sum(L, mixllk, ds->w.p + row0, rows, llk_sum, 1);
+    launch_mix_update_max(L, M, out.run_max, chunk_max, factor);
+    for (int j = 0; j < M; ++j) {
+      MixComp &c = out.comps[j];
+      const Shape &s = shp[j];
+      if (row0 > 0) {  // bring what this component has accumulated so far onto the new maximum
+        const StatsLayout lay(d, s.k);
+        launch_scale_by(L, c.stats, lay.offScalars, factor + j, 0);
+        launch_scale_by(L, c.ws.part_bg, (int64_t)c.plan.bglen, factor + j, 0);
+        launch_scale_by(L, c.ws.part_cr, (int64_t)c.plan.crlen, factor + j, 0);
+        launch_scale_by(L, c.ws.part_solve, (int64_t)SOLVE_SLOTS * 4, factor + j, 1);
+      }
+      // column maxima of W fused into the weighting kernel (its shared-memory scratch holds 8 rows of W)
+      const bool tc = ctx->gemm_mode == 2 && (size_t)8 * s.kkp * sizeof(double) <= 200 * 1024;
+      if (tc) CUDA_CHECK(cudaMemsetAsync(c.ws.colmax, 0, sizeof(unsigned long long) * s.kkp, ctx->stream));
+      ctx->span_begin(FAM_SOLVE);
+      launch_mix_weight(L, LPc, M, j, ds->w.p + row0, out.run_max, rows, rows_pad, s.kkp, s.kp, c.ws.GW, c.ws.YZ, sh_WZ,
+                        sh_r, tc ? c.ws.colmax : nullptr);
+      launch_solve_reduce(L, rows, nullptr, c.ws.tn, st.dn.p + row0, sh_r, c.ws.part_solve);
+      ctx->span_end();
+      m_step_chunk(ctx, st, sh_r, row0, rows, c.m, c.stats, c.plan, tc);
+    }
+  }
+  for (int j = 0; j < M; ++j) em_end(ctx, out.comps[j].m, out.comps[j].stats, out.comps[j].plan, rows_total);
+}
+
+void mix_iterate_impl(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int32_t m, const int32_t *ks, const double *Cs,
+                      const double *mus, const double *sigmas, const double *log_weights, const ppca_b200_prior *prior,
+                      double *Cs_out, double *mus_out, double *sigmas_out, double *log_weights_out, double *llk_in,
+                      bool sharded) {
   check_ds(ctx, ds);
   MixView mv{m, ks, Cs, mus, sigmas, log_weights, ds->store->d};
   check_mix(mv);
@@ -1893,50 +2133,53 @@ static void mix_iterate_impl(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, in
   REQUIRE(!sharded || ctx->comm != nullptr, "no communicator: call ppca_b200_comm_init first");
   const SampleStore &st = *ds->store;
   if (st.n == 0 && !sharded) PPCA_THROW(PPCA_ERR_EMPTY, "dataset not empty (mix.rs:315)");
+  if (st.n > 0 && !(ds->min_w > 0.0))
+    PPCA_THROW(PPCA_ERR_WEIGHTS, "mixture EM needs strictly positive weights (mix.rs:304-309,326)");
   DeviceGuard g(ctx->device);
-  DevBuf<double> &LP = ctx->mixLP;
-  LP.reserve((size_t)std::max<int64_t>(st.n, 1) * m);
-  std::vector<double> cmax(m + 1);
-  double llk_local = 0.0;
-  int32_t rc = ppca_b200_mix_posteriors(ctx, ds, m, ks, Cs, mus, sigmas, log_weights, LP.p, cmax.data(), &llk_local);
-  if (rc) throw Error{rc, g_last_error};
-  if (sharded) {  // global per-component maxima (mix.rs:312-318) and the global log-likelihood
-    ctx->mixMax.reserve((size_t)m + 1);
-    cmax[m] = llk_local;
-    CUDA_CHECK(cudaMemcpyAsync(ctx->mixMax.p, cmax.data(), sizeof(double) * (m + 1), cudaMemcpyHostToDevice, ctx->stream));
-    comm_allreduce(ctx->comm, ctx->mixMax.p, m, 1, ctx->stream);
-    comm_allreduce(ctx->comm, ctx->mixMax.p + m, 1, 0, ctx->stream);
-    CUDA_CHECK(cudaMemcpyAsync(cmax.data(), ctx->mixMax.p, sizeof(double) * (m + 1), cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-    llk_local = cmax[m];
-  }
-  if (llk_in) *llk_in = llk_local;
-  std::vector<double> logsum(m);
-  for (int j = 0; j < m; ++j) {
-    const int kj = ks[j];
-    DevBuf<double> &stats = ctx->mixStats;
-    const int64_t slen = StatsLayout(st.d, kj).len;
-    stats.reserve((size_t)slen);
-    double sumw = 0.0;
-    const size_t off = (size_t)(mv.C(j) - Cs);
-    for (;;) {  // one guarded pass per component (ppca_b200_mix_em_stats starts at the remembered rung)
-      rc = ppca_b200_mix_em_stats(ctx, ds, m, j, kj, mv.C(j), mv.mu(j), sigmas[j], LP.p, cmax[j], stats.p);
-      if (rc) throw Error{rc, g_last_error};
-      if (sharded) comm_allreduce(ctx->comm, stats.p, slen, 0, ctx->stream);
-      const double viol = em_finish_impl(ctx, st.d, kj, mv.C(j), mv.mu(j), sigmas[j], prior, stats.p, Cs_out + off,
-                                         mus_out + (size_t)j * st.d, sigmas_out + j, nullptr, &sumw);
-      if (end_pass(ctx, viol)) break;
+  std::vector<double> cmax(m), sumw(m);
+  double llk = 0.0;
+  run_guarded(ctx, [&] {
+    MixPass pass;
+    mix_em_pass(ctx, ds, mv, pass);
+    ctx->mixMax.reserve((size_t)2 * m);
+    double *gmax = ctx->mixMax.p;  // global maxima (= local ones in a single process)
+    CUDA_CHECK(cudaMemcpyAsync(gmax, pass.run_max, sizeof(double) * m, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (sharded) {
+      comm_allreduce(ctx->comm, gmax, m, 1, ctx->stream);
+      for (int j = 0; j < m; ++j) {
+        const StatsLayout lay(st.d, ks[j]);
+        launch_mix_rescale_stats(ctx->L(), pass.comps[j].stats, lay.offScalars, pass.comps[j].stats + lay.offScalars,
+                                 pass.run_max, gmax, j);
+      }
+      comm_allreduce(ctx->comm, pass.stats_all, pass.stats_total, 0, ctx->stream);  // every component + the llk at once
     }
-    logsum[j] = std::log(sumw) + cmax[j];  // mix.rs:323-324
-  }
+    CUDA_CHECK(cudaMemcpyAsync(cmax.data(), gmax, sizeof(double) * m, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaMemcpyAsync(&llk, pass.stats_all + pass.stats_total - 1, sizeof(double), cudaMemcpyDeviceToHost,
+                               ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    double viol = 0.0;
+    for (int j = 0; j < m; ++j) {
+      const size_t off = (size_t)(mv.C(j) - Cs);
+      viol += em_finish_impl(ctx, st.d, ks[j], mv.C(j), mv.mu(j), sigmas[j], prior, pass.comps[j].stats, Cs_out + off,
+                             mus_out + (size_t)j * st.d, sigmas_out + j, nullptr, &sumw[j]);
+    }
+    return viol;
+  });
+  if (llk_in) *llk_in = llk;
+  std::vector<double> logsum(m);
+  for (int j = 0; j < m; ++j) logsum[j] = std::log(sumw[j]) + cmax[j];  // mix.rs:323-324
   // robust_log_softmax (mix.rs:14-18, :335)
   double mx = logsum[0];
   for (int j = 1; j < m; ++j) mx = logsum[j] > mx ? logsum[j] : mx;
-  double s = 0.0;
-  for (int j = 0; j < m; ++j) s += std::exp(logsum[j] - mx);
-  const double ln = std::log(s);
+  double sm = 0.0;
+  for (int j = 0; j < m; ++j) sm += std::exp(logsum[j] - mx);
+  const double ln = std::log(sm);
   for (int j = 0; j < m; ++j) log_weights_out[j] = logsum[j] - mx - ln;
 }
+
+}  // namespace
+
+extern "C" {
 
 int32_t ppca_b200_mix_iterate(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int32_t m, const int32_t *ks,
                               const double *Cs, const double *mus, const double *sigmas, const double *log_weights,

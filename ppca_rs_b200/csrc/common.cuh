@@ -131,6 +131,18 @@ struct ppca_b200_dataset {
 
 namespace ppca {
 
+// Chunk workspaces and accumulators of one model.  A single model uses the context's own buffers; a mixture pass keeps
+// one set per component alive at the same time (api.cu, mix_em_pass).
+struct ModelWs {
+  double *GW = nullptr, *YZ = nullptr, *WZ = nullptr, *nx = nullptr, *llk = nullptr, *tn = nullptr;
+  int8_t *KsymQ = nullptr;
+  double *KsymScale = nullptr;
+  int8_t *WQ = nullptr;
+  double *WScale = nullptr, *WScaleMax = nullptr;
+  unsigned long long *colmax = nullptr;
+  double *part_bg = nullptr, *part_cr = nullptr, *part_solve = nullptr;
+};
+
 // per-iteration device model
 struct DevModel {
   Shape s;
@@ -138,6 +150,7 @@ struct DevModel {
   const double *C;     // d32 x kp   (zero padded)
   const double *mu;    // d32
   const double *Ksym;  // d32 x kkp  (zero padded rows and columns)
+  const ModelWs *ws = nullptr;  // null = the context's buffers
 };
 
 // Kernel variants whose selection depends on the shape: counted per context so that tests can assert which code path
@@ -271,6 +284,9 @@ __host__ __device__ inline double guard_terms(double n) {
 }
 enum { SOLVE_SLOTS = 128 };
 void launch_solve(const Launcher &L, const SolveArgs &a);
+// part[slot][0..3] += sum over the slot's rows of (w t, w llk, w, #non-empty) — what launch_solve does when a.part is set
+void launch_solve_reduce(const Launcher &L, int rows, const double *llk, const double *tn, const int *dn, const double *w,
+                         double *part);
 // sums the partial slots (fixed order) into scalars[SC_SQERR, SC_LLK, SC_SUMW, SC_NONEMPTY]
 void launch_solve_finish(const Launcher &L, const double *part, double *scalars);
 
@@ -314,6 +330,23 @@ void launch_log_softmax_rows(const Launcher &L, double *LP, int64_t n, int m, co
                              double *llk_sum /* 1, nullable */);
 void launch_responsibilities(const Launcher &L, const double *LP, int64_t n, int m, int j, const double *w,
                              double comp_max_j, double *r_out);
+// ---- single-pass mixture EM (api.cu, mix_em_pass) ----
+// accumulate != 0: llk_sum[0] += sum_n w_n mix_llk[n] (one block, fixed order), else overwrite
+void launch_weighted_sum(const Launcher &L, const double *v, const double *w, int64_t n, double *out, int accumulate);
+// run_max[j] <- max(run_max[j], chunk_max[j]) ; factor[j] = exp(old - new) (1 when unchanged, 0 on the first chunk)
+void launch_mix_update_max(const Launcher &L, int m, double *run_max, const double *chunk_max, double *factor);
+// buf[0, len) *= factor[0]; returns at once when the factor is exactly 1.  stride4 != 0: buf is [slots][4] and only the
+// first three entries of each slot are scaled (the fourth is a count).
+void launch_scale_by(const Launcher &L, double *buf, int64_t len, const double *factor, int stride4);
+// r[n] = w_n > 0 ? exp(ln w_n + LP[n][j] - run_max[j]) : 0 for n < rows (0 up to rows_pad) ;
+// W[n][q] = r_n V[n][q] in place (rows_pad x kkp) ; WZ[n][a] = r_n Z[n][a] ; colmax[q] = max_n |W[n][q]| (bit patterns)
+void launch_mix_weight(const Launcher &L, const double *LP, int m, int j, const double *w, const double *run_max, int rows,
+                       int rows_pad, int kkp, int kp, double *V, const double *Z, double *WZ, double *r,
+                       unsigned long long *colmax);
+// stats[..] *= exp(local_max[j] - global_max[j]) for the weight-linear entries (everything except the two counters and
+// the guard slots)
+void launch_mix_rescale_stats(const Launcher &L, double *stats, int64_t len_linear, double *scalars, const double *local_max,
+                              const double *global_max, int j);
 
 }  // namespace ppca
 

@@ -67,7 +67,7 @@ __global__ void fill_kernel(double *p, int64_t n, double v) {
 
 // fixed-order weighted sum: out[0] = sum_n w_n v_n  (single block)
 __global__ void __launch_bounds__(1024) weighted_sum_kernel(const double *__restrict__ v, const double *__restrict__ w,
-                                                            int64_t n, double *out) {
+                                                            int64_t n, double *out, int accumulate = 0) {
   __shared__ double sh[32];
   double s = 0.0;
   for (int64_t i = threadIdx.x; i < n; i += 1024) s = fma(w ? w[i] : 1.0, v[i], s);
@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(1024) weighted_sum_kernel(const double *__rest
   __syncthreads();
   if (threadIdx.x < 32) {
     s = warp_sum(sh[threadIdx.x]);
-    if (threadIdx.x == 0) out[0] = s;
+    if (threadIdx.x == 0) out[0] = accumulate ? out[0] + s : s;
   }
 }
 
@@ -116,6 +116,133 @@ void launch_responsibilities(const Launcher &L, const double *LP, int64_t n, int
   const int64_t want = (n + 255) / 256;
   const int blocks = (int)(want < (int64_t)L.sms * 8 ? want : (int64_t)L.sms * 8);
   responsibilities_kernel<<<blocks, 256, 0, L.stream>>>(LP, n, m, j, w, comp_max_j, r_out);
+  CUDA_CHECK(cudaGetLastError());
+  ++*L.launch_counter;
+}
+
+void launch_weighted_sum(const Launcher &L, const double *v, const double *w, int64_t n, double *out, int accumulate) {
+  weighted_sum_kernel<<<1, 1024, 0, L.stream>>>(v, w, n, out, accumulate);
+  CUDA_CHECK(cudaGetLastError());
+  ++*L.launch_counter;
+}
+
+// ---- single-pass mixture EM: running per-component maxima with rescaling of what has been accumulated so far --------
+// The reference scales the responsibilities of component j by exp(-max_n (ln w_n + lp_nj)) over the WHOLE dataset
+// (mix.rs:312-318).  One pass over the samples only knows the maximum so far, so every accumulator of component j is
+// kept relative to the running maximum and multiplied by exp(old - new) whenever a chunk raises it: the statistics are
+// linear in the weights, the result is the reference's up to rounding.
+__global__ void mix_update_max_kernel(int m, double *run_max, const double *__restrict__ chunk_max, double *factor) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= m) return;
+  const double old = run_max[j], c = chunk_max[j];
+  if (!(c > old)) {  // also when the chunk had no positive-weight sample (c = -inf)
+    factor[j] = 1.0;
+    return;
+  }
+  run_max[j] = c;
+  factor[j] = old == -INFINITY ? 0.0 : exp(old - c);
+}
+
+void launch_mix_update_max(const Launcher &L, int m, double *run_max, const double *chunk_max, double *factor) {
+  mix_update_max_kernel<<<(m + 63) / 64, 64, 0, L.stream>>>(m, run_max, chunk_max, factor);
+  CUDA_CHECK(cudaGetLastError());
+  ++*L.launch_counter;
+}
+
+__global__ void scale_by_kernel(double *buf, int64_t len, const double *__restrict__ factor, int stride4) {
+  const double f = factor[0];
+  if (f == 1.0) return;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x)
+    if (!stride4 || (i & 3) != 3) buf[i] = f == 0.0 ? 0.0 : buf[i] * f;
+}
+
+void launch_scale_by(const Launcher &L, double *buf, int64_t len, const double *factor, int stride4) {
+  if (len <= 0) return;
+  const int64_t want = (len + 255) / 256;
+  const int blocks = (int)(want < (int64_t)L.sms * 8 ? want : (int64_t)L.sms * 8);
+  scale_by_kernel<<<blocks, 256, 0, L.stream>>>(buf, len, factor, stride4);
+  CUDA_CHECK(cudaGetLastError());
+  ++*L.launch_counter;
+}
+
+// one warp per sample row: r, W = r V (in place), WZ = r Z, running column maxima of |W| per warp slot in shared memory
+__global__ void __launch_bounds__(256) mix_weight_kernel(const double *__restrict__ LP, int m, int j,
+                                                         const double *__restrict__ w, const double *__restrict__ run_max,
+                                                         int rows, int rows_pad, int kkp, int kp, double *V,
+                                                         const double *__restrict__ Z, double *WZ, double *r_out,
+                                                         unsigned long long *colmax) {
+  extern __shared__ double cm_sh[];  // [8 warps][kkp]
+  const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+  double *cm = cm_sh + (size_t)wi * kkp;
+  if (colmax)
+    for (int q = lane; q < kkp; q += 32) cm[q] = 0.0;
+  const double mx = run_max[j];
+  for (int row = blockIdx.x * 8 + wi; row < rows_pad; row += gridDim.x * 8) {
+    double r = 0.0;
+    if (row < rows) {
+      const double wn = w ? w[row] : 1.0;
+      r = wn > 0.0 ? exp(log(wn) + LP[(int64_t)row * m + j] - mx) : 0.0;
+    }
+    if (lane == 0) r_out[row] = r;
+    double *v = V + (int64_t)row * kkp;
+    for (int q = 2 * lane; q < kkp; q += 64) {
+      double2 x = *reinterpret_cast<double2 *>(v + q);
+      x.x *= r;
+      x.y *= r;
+      *reinterpret_cast<double2 *>(v + q) = x;
+      if (colmax) {
+        cm[q] = fmax(cm[q], fabs(x.x));
+        cm[q + 1] = fmax(cm[q + 1], fabs(x.y));
+      }
+    }
+    for (int a = lane; a < kp; a += 32) WZ[(int64_t)row * kp + a] = r * Z[(int64_t)row * kp + a];
+  }
+  if (colmax) {
+    __syncthreads();
+    for (int q = threadIdx.x; q < kkp; q += blockDim.x) {
+      double mq = 0.0;
+      for (int s = 0; s < 8; ++s) mq = fmax(mq, cm_sh[(size_t)s * kkp + q]);
+      if (mq > 0.0) atomicMax(colmax + q, (unsigned long long)__double_as_longlong(mq));
+    }
+  }
+}
+
+void launch_mix_weight(const Launcher &L, const double *LP, int m, int j, const double *w, const double *run_max, int rows,
+                       int rows_pad, int kkp, int kp, double *V, const double *Z, double *WZ, double *r,
+                       unsigned long long *colmax) {
+  if (rows_pad <= 0) return;
+  const size_t smem = colmax ? (size_t)8 * kkp * sizeof(double) : 0;
+  REQUIRE(smem <= 200 * 1024, "mixture EM: state_size too large for the fused column maxima");
+  static PerDeviceOnce configured;
+  if (configured.need())
+    CUDA_CHECK(cudaFuncSetAttribute(mix_weight_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  int64_t blocks = (rows_pad + 7) / 8;
+  const int64_t cap = (int64_t)L.sms * (smem > 96 * 1024 ? 1 : (smem > 48 * 1024 ? 2 : 4));
+  if (blocks > cap) blocks = cap;
+  mix_weight_kernel<<<(unsigned)blocks, 256, smem, L.stream>>>(LP, m, j, w, run_max, rows, rows_pad, kkp, kp, V, Z, WZ, r,
+                                                              colmax);
+  CUDA_CHECK(cudaGetLastError());
+  ++*L.launch_counter;
+}
+
+__global__ void mix_rescale_stats_kernel(double *stats, int64_t len_linear, double *scalars,
+                                         const double *__restrict__ local_max, const double *__restrict__ global_max,
+                                         int j) {
+  const double lm = local_max[j], gm = global_max[j];
+  if (lm == gm) return;
+  const double f = lm == -INFINITY ? 0.0 : exp(lm - gm);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < len_linear; i += (int64_t)gridDim.x * blockDim.x)
+    stats[i] = f == 0.0 ? 0.0 : stats[i] * f;
+  if (blockIdx.x == 0 && threadIdx.x < 4) {  // SC_SQERR, SC_DEV2, SC_LLK, SC_SUMW are linear in the weights
+    scalars[threadIdx.x] = f == 0.0 ? 0.0 : scalars[threadIdx.x] * f;
+  }
+}
+
+void launch_mix_rescale_stats(const Launcher &L, double *stats, int64_t len_linear, double *scalars, const double *local_max,
+                              const double *global_max, int j) {
+  const int64_t want = (len_linear + 255) / 256;
+  const int blocks = (int)(want < (int64_t)L.sms * 8 ? want : (int64_t)L.sms * 8);
+  mix_rescale_stats_kernel<<<blocks > 0 ? blocks : 1, 256, 0, L.stream>>>(stats, len_linear, scalars, local_max, global_max, j);
   CUDA_CHECK(cudaGetLastError());
   ++*L.launch_counter;
 }

@@ -192,12 +192,15 @@ __global__ void __launch_bounds__(256) solve_kernel(SolveArgs a) {
 
 // ---------------------------------------------------------------------------------------------
 // Register-resident variant for k <= 32: KP (8/16/32) lanes per sample, lane i owns row i of the symmetric
-// matrix in registers.  M_n is inverted by an in-place Gauss-Jordan elimination without row scaling:
-//   pivot p:  m_i = T[i][p] / d_p ;  T[i][j] -= m_i T[p][j] (j != p) ;  T[i][p] = -m_i ;  T[p][p] = 1
-// and a final row scaling by 1/d_i.  The pivot ROW is never broadcast from one lane: by symmetry of the
-// Schur complement T[p][j] = T[j][p] for unpivoted j and T[p][j] = -T[j][p] / d_j for pivoted j, so every
-// lane contributes its own element through one conflict-free shared-memory store per pivot.  The pivots are
-// the Cholesky pivots squared, so ln det M = sum ln d_p (no determinant overflow).
+// matrix in registers.  M_n is inverted by an in-place Gauss-Jordan elimination with deferred row scaling:
+//   pivot p:  m_i = T[i][p] / d_p ;  T[i][j] -= m_i T[p][j] (i, j != p) ;  T[i][p] = -m_i ;  T[p][p] = 1
+// and a final scaling of row i by 1/d_i.  The pivot ROW is published by the lane that owns it (one predicated burst of
+// 128-bit shared-memory stores) and read back by everybody as broadcast loads.  Round 1 rebuilt the pivot row from the
+// column entries by symmetry (T[p][j] = T[j][p] or -T[j][p] / d_j): algebraically the same, but the two triangles follow
+// different rounding paths, and on ill-conditioned M_n (one feature in other units: M = small + big v v^T) the
+// inconsistency cost four digits of y^T M^-1 y against an LU or Cholesky evaluation (profiles/r02_solve_accuracy.md).
+// With the real row the kernel is plain Gauss-Jordan on an SPD matrix and matches them.  The pivots are the Cholesky
+// pivots squared, so ln det M = sum ln d_p (no determinant overflow).
 // ---------------------------------------------------------------------------------------------
 template <int KP, int MINB>
 __global__ void __launch_bounds__(256, MINB) solve_reg_kernel(SolveArgs a) {
@@ -255,9 +258,12 @@ __global__ void __launch_bounds__(256, MINB) solve_reg_kernel(SolveArgs a) {
 #pragma unroll
     for (int p = 0; p < KP; ++p) {
       double *cb = col + (p & 1) * 32;
-      cb[lane] = (li < p) ? -A[p] * myinv : A[p];
+      double *cs = cb + sub * KP;
+      if (li == p) {  // the owner publishes the pivot row
+#pragma unroll
+        for (int j = 0; j < KP; j += 2) *reinterpret_cast<double2 *>(cs + j) = make_double2(A[j], A[j + 1]);
+      }
       __syncwarp();
-      const double *cs = cb + sub * KP;
       const double dpp = cs[p];
       const double inv = fast_rcp(dpp);
       if (li == p) {
@@ -418,7 +424,10 @@ __global__ void __launch_bounds__(256, 1) solve_reg64_kernel(SolveArgs a) {
 #pragma unroll
     for (int p = 0; p < KP; ++p) {
       double *cb = col + (p & 1) * 64;
-      cb[li] = (li < p) ? -A[p] * myinv : A[p];
+      if (li == p) {  // the owner publishes the pivot row (see solve_reg_kernel)
+#pragma unroll
+        for (int j = 0; j < KP; j += 2) *reinterpret_cast<double2 *>(cb + j) = make_double2(A[j], A[j + 1]);
+      }
       pair_sync(bar_id);
       const double dpp = cb[p];
       const double inv = fast_rcp(dpp);
@@ -577,11 +586,11 @@ __global__ void __launch_bounds__(256, 2) solve_split64_kernel(SolveArgs a) {
     double mypiv = 1.0, myinv = 1.0;
 #pragma unroll
     for (int p = 0; p < KP; ++p) {
-      double *cb = col + (p & 1) * 128;  // [0,64) transformed column, [64,128) raw column
-      if (h == (p >> 5)) {
-        const double v = A[p & 31];
-        cb[li] = (li < p) ? -v * myinv : v;
-        cb[64 + li] = v;
+      double *cb = col + (p & 1) * 128;  // [0,64) pivot row (published by its two owners), [64,128) raw column p
+      if (h == (p >> 5)) cb[64 + li] = A[p & 31];
+      if (li == p) {
+#pragma unroll
+        for (int jj = 0; jj < CW; jj += 2) *reinterpret_cast<double2 *>(cb + c0 + jj) = make_double2(A[jj], A[jj + 1]);
       }
       quad_sync(bar_id);
       const double dpp = cb[p];
@@ -1043,6 +1052,14 @@ __global__ void solve_finish_kernel(const double *__restrict__ part, double *sca
   }
 }
 
+void launch_solve_reduce(const Launcher &L, int rows, const double *llk, const double *tn, const int *dn, const double *w,
+                         double *part) {
+  if (rows <= 0) return;
+  solve_reduce_kernel<<<SOLVE_SLOTS, 256, 0, L.stream>>>(rows, llk, tn, dn, w, part);
+  CUDA_CHECK(cudaGetLastError());
+  ++*L.launch_counter;
+}
+
 void launch_solve_finish(const Launcher &L, const double *part, double *scalars) {
   solve_finish_kernel<<<1, 32, 0, L.stream>>>(part, scalars);
   CUDA_CHECK(cudaGetLastError());
@@ -1100,11 +1117,7 @@ void launch_solve(const Launcher &L, const SolveArgs &a) {
     REQUIRE(a.colmax == nullptr, "solve: the generic kernel (state_size > 64) does not produce column maxima");
     launch_solve_generic(L, a);
   }
-  if (a.part) {
-    solve_reduce_kernel<<<SOLVE_SLOTS, 256, 0, L.stream>>>(a.rows, a.llk, a.tn, a.dn, a.w, a.part);
-    CUDA_CHECK(cudaGetLastError());
-    ++*L.launch_counter;
-  }
+  if (a.part) launch_solve_reduce(L, a.rows, a.llk, a.tn, a.dn, a.w, a.part);
 }
 
 }  // namespace ppca
