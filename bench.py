@@ -261,6 +261,13 @@ def cpu_step_time(wl, X, steps, warmup, keep=None):
     return times, orc.num_threads()
 
 
+DTYPE_NOTE = {
+    "dmma": "f64",
+    "tc": "f64; the two masked-Gram contractions sum int8 digit planes exactly (x{T}, tcgen05 kind::i8, every term kept to "
+          "8*{T}-2 bits below its column maximum, guarded: repeats at 8 planes / FP64 DMMA when a sample or dimension sits "
+          "far below that maximum)",
+    "int8": "f64; masked-Gram contractions on int8 digit planes (x{T}, mma.sync IMMA), guarded",
+}
 PARITY_TOL = 1e-9   # BASELINE.json north_star: per-iteration llk, C, mu, sigma^2 within 1e-9 relative (FP64 path)
 
 
@@ -317,7 +324,9 @@ def run_reference(args, wl, rank):
         "impl": "reference", "metric": "EM samples*iters/sec", "value": value, "unit": "samples*iters/s",
         "n_gpus": args.gpus, "steps": len(times), "warmup": warmup, "ms_per_step": 1e3 * total / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {wl['desc']}", "sample_rows": rows},
+        "config": {"workload": f"{args.workload}: {wl['desc']}", "sample_rows": rows,
+                   "steps_note": f"--steps {args.steps} --warmup {args.warmup} requested; the CPU arm runs at most 3 timed "
+                                 "steps and 1 warm-up (one step takes seconds on the host cores)"},
         "cpu_baseline": {"value": value, "unit": "samples*iters/s", "cores": cores, "kind": "port",
                          "sample": f"{rows} rows of the workload, {len(times)} step(s) of llk + iterate "
                                    "(oracle/ppca_oracle.c, OpenMP, restatement of the reference's CPU algorithm; "
@@ -330,6 +339,136 @@ def run_reference(args, wl, rank):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
+def timed_steps(torch, ctx, stream, step_fn, steps, warmup, dist, local_rank, sample_clocks=True):
+    """W untimed + K timed calls of step_fn, CUDA events on the launching stream, barrier + synchronize on both sides,
+    max over ranks.  Returns (ms_total, per-family ms, launches, clocks summary)."""
+    def sync_all():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        step_fn()
+    ctx.set_profiling(True)
+    sync_all()
+    launches0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        e0.record(stream)
+        for _ in range(steps):
+            step_fn()
+        e1.record(stream)
+        sync_all()
+    fam = ctx.last_profile()
+    ms_total = e0.elapsed_time(e1)
+    launches = ctx.launch_count() - launches0
+    ctx.set_profiling(False)
+    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item()), fam, launches, clocks.summary()
+
+
+def family_rooflines(fam, ms_total, steps, n, d, k, m, slices, gemm, peak64, peak64_src, tensor_peak, tensor_unit):
+    """Every kernel family of the step against the roofline that bounds it (HBM bytes or FP64 / int8 tensor work)."""
+    hbm_peak, hbm_src = measured_hbm_peak()
+    kk = k * (k + 1) // 2
+    kkp, kp = (kk + 7) // 8 * 8, (k + 7) // 8 * 8
+    comps = max(1, m)
+    fam_bytes = {                                           # algorithmic bytes per sample (per component)
+        "proj": 8 * d + d / 8 + 8 * kp,                                   # read x + mask, write y
+        "solve": 8 * (2 * kkp + 3 * kp + 4),                              # read G, y; write W, z, w z, scalars
+        "slice": (8 + slices) * kkp if gemm != "dmma" else 0,             # read W once, write T digit planes
+        "cross_resid": 8 * d + d / 8 + 16 * kp,                           # read x + mask, z, w z
+    }
+    # FP64 flops per sample of the families that run on the FP64 pipes (DMMA for proj / cross_resid, DFMA for the solve):
+    # with 37 TFLOP/s of FP64 against 6.5 TB/s of HBM the ridge is ~5.7 flop/B, so at k >= 16 the X passes are FP64-bound
+    fam_flops = {"proj": 2 * d * k, "cross_resid": 4 * d * k, "solve": 2 * k ** 3}
+    families = {}
+    for name, ms in fam.items():
+        entry = {"ms_per_step": ms / steps, "share_of_step": ms / ms_total if ms_total else None}
+        if name in fam_bytes and ms > 0 and fam_bytes[name] > 0:
+            gbs = fam_bytes[name] * comps * n * steps / (ms * 1e-3) / 1e9
+            tfl = fam_flops.get(name, 0) * comps * n * steps / (ms * 1e-3) / 1e12
+            if tfl / peak64 > gbs / hbm_peak:   # the FP64 pipe, not HBM, is the nearer roof
+                entry.update(bound="tensor", achieved=tfl, peak=peak64, unit="TFLOP/s", frac=tfl / peak64,
+                             peak_source=peak64_src + " (FP64: DMMA rate = DFMA rate)", hbm_gbs=gbs, hbm_frac=gbs / hbm_peak)
+            else:
+                entry.update(bound="hbm", achieved=gbs, peak=hbm_peak, unit="GB/s", frac=gbs / hbm_peak,
+                             peak_source=hbm_src, fp64_tflops=tfl, fp64_frac=tfl / peak64)
+        elif name in ("gram", "moment") and ms > 0:
+            ops = comps * 2 * d * kk * n * steps * (slices if gemm != "dmma" else 1)
+            ach = ops / (ms * 1e-3) / 1e12
+            entry.update(bound="tensor", achieved=ach, peak=tensor_peak, unit=tensor_unit, frac=ach / tensor_peak)
+        families[name] = entry
+    return families
+
+
+def shard_block(torch, pk, pdist, ctx, stream, dist, rank, world, local_rank, args, name, rows, steps, warmup):
+    """A second, smaller measurement carried inside the default JSON line: `rows` per GPU of another BASELINE config
+    (c3: d=2048 k=64, the north-star shape; c4: PPCAMix M=32), same timing rules, plus the time of its all-reduce."""
+    wl = WORKLOADS[name]
+    d, k, m = wl["d"], wl["k"], wl["m"]
+    ds = pk.Dataset.synthetic(rows, d, wl["k_true"], 0.1, wl["p"], n_components=max(1, m), seed=SEED + 77 + rank, ctx=ctx)
+    if m == 1:
+        C, mu, s = init_params(d, k, SEED + 1000)
+        state = pdist.ShardedPPCA(ctx, ds, pk.PPCAModel(s, C, mu), group=dist)
+    else:
+        models = [pk.PPCAModel(sg, Cj, muj) for Cj, muj, sg in (init_params(d, k, SEED + 1000 + j) for j in range(m))]
+        state = pdist.ShardedPPCAMix(ctx, ds, pk.PPCAMix(models, np.zeros(m)), group=dist)
+    ms_total, fam, launches, clocks = timed_steps(torch, ctx, stream, state.step, steps, warmup, dist, local_rank)
+    block = {"workload": f"{name}: {wl['desc']}", "rows_per_gpu": rows, "d": d, "k": k, "components": m,
+             "steps": steps, "warmup": warmup, "ms_per_step": ms_total / steps,
+             "value": rows * world * steps / (ms_total * 1e-3), "unit": "samples*iters/s", "gpu_launches": int(launches),
+             "clocks": clocks}
+    # the statistics all-reduce of this shape, timed alone on the context's stream (NCCL over NVLink)
+    kk = k * (k + 1) // 2
+    stats_doubles = max(1, m) * (d * ((kk + 7) // 8 * 8) + d * ((k + 7) // 8 * 8) + 2 * d + 8)
+    block["allreduce_bytes"] = stats_doubles * 8
+    if dist is not None:
+        buf = torch.zeros(stats_doubles, dtype=torch.float64, device="cuda")
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        for _ in range(3):
+            ctx.comm_allreduce(buf.data_ptr(), stats_doubles)
+        torch.cuda.synchronize()
+        dist.barrier()
+        ev[0].record(stream)
+        for _ in range(10):
+            ctx.comm_allreduce(buf.data_ptr(), stats_doubles)
+        ev[1].record(stream)
+        torch.cuda.synchronize()
+        t = torch.tensor([ev[0].elapsed_time(ev[1]) / 10.0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        block["comm_ms_per_step"] = float(t.item())
+        block["comm_gb_per_s"] = stats_doubles * 8 / (block["comm_ms_per_step"] * 1e-3) / 1e9
+    else:
+        block["comm_ms_per_step"] = 0.0
+    if rank == 0:
+        peak64, _, peak64_src = fp64_peak()
+        if args.gemm == "tc":
+            tpeak, _ = int8_tc_peak()
+            tunit = "TOP/s"
+        elif args.gemm == "dmma":
+            tpeak, tunit = peak64, "TFLOP/s"
+        else:
+            with open(os.path.join(ROOT, "profiles", "r01_imma_peak.json")) as f:
+                tpeak, tunit = json.load(f)["imma_s8_tops"], "TOP/s"
+        fams = family_rooflines(fam, ms_total, steps, rows, d, k, m, args.slices, args.gemm, peak64, peak64_src, tpeak, tunit)
+        block["families"] = fams
+        bit_ms = fam.get("gram", 0.0) + fam.get("moment", 0.0)
+        if bit_ms > 0:
+            contractions = 2 * max(1, m)
+            ops = contractions * 2 * d * kk * rows * steps * (args.slices if args.gemm != "dmma" else 1)
+            ach = ops / (bit_ms * 1e-3) / 1e12
+            block["contraction"] = {"achieved": ach, "peak": tpeak, "unit": tunit, "frac": ach / tpeak,
+                                    "fp64_equivalent_tflops": contractions * 2 * d * kk * rows * steps / (bit_ms * 1e-3) / 1e12,
+                                    "fp64_dmma_peak_tflops": peak64, "share_of_step": bit_ms / ms_total}
+    del state, ds
+    torch.cuda.empty_cache()
+    return block
+
+
 def run_ours(args, wl, rank, world, local_rank):
     import torch
     import ppca_rs_b200 as pk
@@ -368,29 +507,34 @@ def run_ours(args, wl, rank, world, local_rank):
             dist.barrier()
             torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        state.step()
-    ctx.set_profiling(True)
-    fam = {}
-    sync_all()
-    launches0 = ctx.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clocks:
-        e0.record(stream)
-        for _ in range(args.steps):
-            state.step()
-        e1.record(stream)
-        sync_all()
-    fam = ctx.last_profile()  # CUDA-event spans recorded on the launching stream during the timed steps
-    ms_total = e0.elapsed_time(e1)
-    launches = ctx.launch_count() - launches0
-    ctx.set_profiling(False)
-    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
+    variants0 = ctx.variant_counts()
+    ms_total, fam, launches, clocks_summary = timed_steps(torch, ctx, stream, state.step, args.steps, args.warmup, dist,
+                                                          local_rank)
+    variants = {kname: v - variants0.get(kname, 0) for kname, v in ctx.variant_counts().items()
+                if v - variants0.get(kname, 0)}
     n_total = n * world
     value = n_total * args.steps / (ms_total * 1e-3)
+
+    # ---- strong scaling: the SAME total work (the N=1 row count) split over the ranks -----------------------------
+    strong = None
+    if m == 1 and not args.no_blocks:
+        n_strong = max(256, n // world)
+        ds_s = pk.Dataset.synthetic(n_strong, d, wl["k_true"], 0.1, wl["p"], seed=SEED + 500 + rank, ctx=ctx)
+        C, mu, s = init_params(d, k, SEED + 1000)
+        st_s = pdist.ShardedPPCA(ctx, ds_s, pk.PPCAModel(s, C, mu), group=dist)
+        ms_s, _, _, _ = timed_steps(torch, ctx, stream, st_s.step, args.steps, 3, dist, local_rank, sample_clocks=False)
+        strong = {"scaling": "strong", "total_rows": n_strong * world, "rows_per_gpu": n_strong,
+                  "ms_per_step": ms_s / args.steps, "value": n_strong * world * args.steps / (ms_s * 1e-3),
+                  "unit": "samples*iters/s"}
+        del st_s, ds_s
+
+    # ---- the other BASELINE shapes, small shards, inside the same line (same timing rules) -------------------------
+    blocks = {}
+    if not args.no_blocks and args.workload == "c2":
+        blocks["c3_shard"] = shard_block(torch, pk, pdist, ctx, stream, dist, rank, world, local_rank, args, "c3",
+                                         args.c3_rows, 5, 3)
+        blocks["c4_shard"] = shard_block(torch, pk, pdist, ctx, stream, dist, rank, world, local_rank, args, "c4",
+                                         args.c4_rows, 3, 3)
 
     # ---- end to end: HOST buffers in, host model out, every step -----------------------------------------------
     # The samples start in page-locked host memory and cross the bus inside the timed region on every step
@@ -469,8 +613,9 @@ def run_ours(args, wl, rank, world, local_rank):
     peak64, peak64_sustained, peak64_src = fp64_peak()
     kk = k * (k + 1) // 2
     bit_ms = fam.get("gram", 0.0) + fam.get("moment", 0.0)
-    # E-step runs twice per mixture component (posterior pass + weighted pass), M-step once
-    contractions = (3 if m > 1 else 2) * max(1, m)
+    # one E-step and one M-step contraction per model (the mixture pass shares the E-step between the posteriors and the
+    # weighted statistics)
+    contractions = 2 * max(1, m)
     flops_bit = contractions * (2 * d * kk) * n * args.steps          # algorithmic FP64 flops
     fp64_equiv = flops_bit / (bit_ms * 1e-3) / 1e12 if bit_ms > 0 else None
     launches_bit = contractions * args.steps * max(1, -(-n // max(1, ctx_chunk(ctx, n, d, k))))
@@ -479,8 +624,8 @@ def run_ours(args, wl, rank, world, local_rank):
     alg_bytes_launch = n_chunk * ((d + 31) // 32) * 4 + n_chunk * ((kk + 7) // 8 * 8) * (8 + args.slices) / 2.0
     common = {
         "bound": "tensor", "traffic": measured_traffic(args.workload, "tbitgemm_atm_kernel") if args.gemm == "tc" else None,
-        "traffic_note": "DRAM bytes per launch (E- and M-step launches averaged) from profiles/r01_traffic.json; below the "
-                        "algorithmic bytes because the 126 MB L2 absorbs most of the chunk's G / W round trip",
+        "traffic_note": "dram__bytes_read + dram__bytes_write per launch (E- and M-step launches averaged) from the committed "
+                        "ncu --set full capture (profiles/r01_traffic.json)",
         "algorithmic_bytes_per_launch": alg_bytes_launch,
         "share_of_step": bit_ms / ms_total if ms_total else None,
         "avg_launch_ms": bit_ms / launches_bit if launches_bit else None,
@@ -512,39 +657,8 @@ def run_ours(args, wl, rank, world, local_rank):
                              "int32 accumulation, FP64 recombination; achieved counts 2*rows*d*kk*slices int8 ops per launch")
 
     # ---- every kernel family of the step against the roofline that bounds it -----------------------------------
-    hbm_peak, hbm_src = measured_hbm_peak()
-    kkp, kp = (kk + 7) // 8 * 8, (k + 7) // 8 * 8
-    passes = (3 if m > 1 else 2) * max(1, m) / 2.0          # E-step passes relative to a single model
-    comps = max(1, m)
-    fam_bytes = {                                           # algorithmic bytes per sample (per component)
-        "proj": 8 * d + d / 8 + 8 * kp,                                   # read x + mask, write y
-        "solve": 8 * (2 * kkp + 3 * kp + 4),                              # read G, y; write W, z, w z, scalars
-        "slice": (8 + args.slices) * kkp if args.gemm != "dmma" else 0,      # read W once, write T digit planes
-        "cross_resid": 8 * d + d / 8 + 16 * kp,                           # read x + mask, z, w z
-    }
-    fam_mult = {"proj": passes, "solve": passes, "slice": comps, "cross_resid": comps}
-    # FP64 flops per sample of the families that run on the FP64 pipes (DMMA for proj / cross_resid, DFMA for the solve):
-    # with 37 TFLOP/s of FP64 against 6.5 TB/s of HBM the ridge is ~5.7 flop/B, so at k >= 16 the X passes are FP64-bound
-    fam_flops = {"proj": 2 * d * k, "cross_resid": 4 * d * k, "solve": 2 * k ** 3}
-    families = {}
-    for name, ms in fam.items():
-        entry = {"ms_per_step": ms / args.steps, "share_of_step": ms / ms_total if ms_total else None}
-        if name in fam_bytes and ms > 0 and fam_bytes[name] > 0:
-            gbs = fam_bytes[name] * fam_mult[name] * n * args.steps / (ms * 1e-3) / 1e9
-            tfl = fam_flops.get(name, 0) * fam_mult[name] * n * args.steps / (ms * 1e-3) / 1e12
-            if tfl / peak64 > gbs / hbm_peak:   # the FP64 pipe, not HBM, is the nearer roof
-                entry.update(bound="tensor", achieved=tfl, peak=peak64, unit="TFLOP/s", frac=tfl / peak64,
-                             peak_source=peak64_src + " (FP64: DMMA rate = DFMA rate)", hbm_gbs=gbs, hbm_frac=gbs / hbm_peak)
-            else:
-                entry.update(bound="hbm", achieved=gbs, peak=hbm_peak, unit="GB/s", frac=gbs / hbm_peak,
-                             peak_source=hbm_src, fp64_tflops=tfl, fp64_frac=tfl / peak64)
-        elif name in ("gram", "moment") and ms > 0:
-            share = (2 if name == "gram" and m > 1 else 1) * comps
-            ops = share * 2 * d * kk * n * args.steps * (args.slices if args.gemm != "dmma" else 1)
-            ach = ops / (ms * 1e-3) / 1e12
-            pk_ = roofline["peak"]
-            entry.update(bound="tensor", achieved=ach, peak=pk_, unit=roofline["unit"], frac=ach / pk_)
-        families[name] = entry
+    families = family_rooflines(fam, ms_total, args.steps, n, d, k, m, args.slices, args.gemm, peak64, peak64_src,
+                                roofline["peak"], roofline["unit"])
     roofline["families"] = families
     # the family that takes the largest share of the step, with the roof that bounds it (the top-level entry above is the
     # masked-Gram contraction the north star names; at small k the per-sample solve is the longer kernel)
@@ -587,12 +701,15 @@ def run_ours(args, wl, rank, world, local_rank):
     line = {
         "metric": "EM samples*iters/sec", "value": value, "unit": "samples*iters/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None, "dtype": DTYPE_NOTE.get(args.gemm, "f64").format(T=args.slices),
+        "data": "synthetic",
         "config": {"workload": f"{args.workload}: {wl['desc']}", "rows_per_gpu": n, "d": d, "k": k,
-                   "components": m, "parallelism": f"sample-sharded x{world}, one NCCL all-reduce of the statistics per step",
+                   "components": m, "parallelism": f"sample-sharded x{world}, one NCCL all-reduce of the statistics per step "
+                                                   "(ppca_b200_iterate_sharded: collective inside the C ABI)",
                    "l2": "inputs larger than L2 (resident X per GPU = %.2f GB)" % (n * d * 8 / 1e9)},
         "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "e2e": e2e, "ingest": ingest,
-        "gpu_launches": int(launches), "clocks": clocks.summary(),
+        "gpu_launches": int(launches), "kernel_variants": variants, "clocks": clocks_summary,
+        "strong_scaling": strong, "c3_shard": blocks.get("c3_shard"), "c4_shard": blocks.get("c4_shard"),
     }
     print(json.dumps(line), flush=True)
     if dist is not None:
@@ -742,6 +859,9 @@ def main():
     ap.add_argument("--rows", type=int, default=0, help="override rows per GPU")
     ap.add_argument("--chunk", type=int, default=0, help="samples per chunk (0 = automatic)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-blocks", action="store_true", help="skip the strong-scaling run and the c3/c4 shard blocks")
+    ap.add_argument("--c3-rows", type=int, default=524_288, help="rows per GPU of the c3_shard block")
+    ap.add_argument("--c4-rows", type=int, default=131_072, help="rows per GPU of the c4_shard block")
     ap.add_argument("--gemm", default=os.environ.get("PPCA_B200_GEMM", "tc"), choices=["dmma", "int8", "tc"],
                     help="arithmetic path of the masked-Gram contractions (see include/ppca_b200.h)")
     ap.add_argument("--slices", type=int, default=int(os.environ.get("PPCA_B200_SLICES", "6")))

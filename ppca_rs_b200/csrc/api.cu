@@ -1988,7 +1988,7 @@ void mix_em_pass(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, const MixView 
     kp_max = std::max(kp_max, shp[j].kp);
     kkp_max = std::max(kkp_max, shp[j].kkp);
     per_row += (int64_t)(shp[j].kkp + shp[j].kp + 1) * 8;
-    stats_total += StatsLayout(d, mv.ks[j]).len;
+    stats_total += round_up(StatsLayout(d, mv.ks[j]).len, 4);  // every component's buffer stays 32-byte aligned
   }
   per_row += (int64_t)(2 * M + kp_max + 4) * 8 + (int64_t)kkp_max * ctx->slices;
   // rows per chunk: all components' V / Z / t of a chunk live together (at most 16 GiB), at least one wave of row tiles
@@ -2055,7 +2055,7 @@ void mix_em_pass(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, const MixView 
       qoff += (ksym_planes_bytes(ctx, s) + 1023) & ~(size_t)1023;
       c.stats_len = StatsLayout(d, mv.ks[j]).len;
       c.stats = pass ? ctx->mixStats.p + soff : nullptr;
-      soff += c.stats_len;
+      soff += round_up(c.stats_len, 4);
       if (pass) {
         c.m = stage_model_into(ctx, d, mv.ks[j], mv.C(j), mv.mu(j), mv.sigmas[j], Cpad, mupad, Ksym, c.ws.KsymQ,
                                c.ws.KsymScale, c.ws.colmax);
@@ -2068,6 +2068,7 @@ void mix_em_pass(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, const MixView 
   }
   out.stats_all = ctx->mixStats.p;
   out.stats_total = stats_total + 1;
+  CUDA_CHECK(cudaMemsetAsync(ctx->mixStats.p, 0, sizeof(double) * (stats_total + 1), ctx->stream));  // alignment gaps too
   double *llk_sum = ctx->mixStats.p + stats_total;
   CUDA_CHECK(cudaMemsetAsync(llk_sum, 0, sizeof(double), ctx->stream));
   {

@@ -192,16 +192,26 @@ __global__ void __launch_bounds__(256) solve_kernel(SolveArgs a) {
 
 // ---------------------------------------------------------------------------------------------
 // Register-resident variant for k <= 32: KP (8/16/32) lanes per sample, lane i owns row i of the symmetric
-// matrix in registers.  M_n is inverted by an in-place Gauss-Jordan elimination with deferred row scaling:
-//   pivot p:  m_i = T[i][p] / d_p ;  T[i][j] -= m_i T[p][j] (i, j != p) ;  T[i][p] = -m_i ;  T[p][p] = 1
-// and a final scaling of row i by 1/d_i.  The pivot ROW is published by the lane that owns it (one predicated burst of
-// 128-bit shared-memory stores) and read back by everybody as broadcast loads.  Round 1 rebuilt the pivot row from the
-// column entries by symmetry (T[p][j] = T[j][p] or -T[j][p] / d_j): algebraically the same, but the two triangles follow
-// different rounding paths, and on ill-conditioned M_n (one feature in other units: M = small + big v v^T) the
-// inconsistency cost four digits of y^T M^-1 y against an LU or Cholesky evaluation (profiles/r02_solve_accuracy.md).
-// With the real row the kernel is plain Gauss-Jordan on an SPD matrix and matches them.  The pivots are the Cholesky
-// pivots squared, so ln det M = sum ln d_p (no determinant overflow).
+// matrix in registers.  M_n is inverted in place by the symmetric sweep operator in its square-root form:
+//   pivot p (d = T[p][p], r = 1/sqrt(d)):   s_i = T[i][p] r ;  T[i][j] -= s_i s_j (i, j != p) ;  T[i][p] = s_i r ;  T[p][p] = -1/d
+// after all pivots T = -M^-1.  The update product s_i s_j is commutative, so T[i][j] and T[j][i] stay BITWISE equal and
+// the pivot row never has to be broadcast: every lane contributes its own column-p entry s_i through one shared-memory
+// store per pivot and reads the k of them back (by symmetry that IS the pivot row).  The pivot row itself is left
+// unscaled (stored = d x true) and scaled once at the end; a pivoted lane publishes stored x 1/d.
+// Why this form: round 1 used the non-commutative product (T[i][p]/d) T[j][p]; the two triangles then follow different
+// rounding paths, and on ill-conditioned M_n (one feature in other units: M = small + big v v^T) rebuilding the row from
+// the column cost four digits of y^T M^-1 y against LU / Cholesky.  With the commutative product the elimination
+// matches them (tools/solve_accuracy.py, profiles/r02_solve_accuracy.md).  The pivots are the Cholesky pivots squared,
+// so ln det M = sum ln d_p (no determinant overflow, unlike determinant().ln() at output_covariance.rs:117).
 // ---------------------------------------------------------------------------------------------
+// 1 / sqrt(x) for a positive normal double: hardware seed (2^-22) and one third-order step (-> 2^-66, then rounding)
+__device__ __forceinline__ double fast_rsqrt(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double e = fma(-(x * y), y, 1.0);
+  return fma(y * e, fma(0.375, e, 0.5), y);
+}
+
 template <int KP, int MINB>
 __global__ void __launch_bounds__(256, MINB) solve_reg_kernel(SolveArgs a) {
   constexpr int SPW = 32 / KP;
@@ -213,7 +223,7 @@ __global__ void __launch_bounds__(256, MINB) solve_reg_kernel(SolveArgs a) {
   double *stage = smem_reg + (size_t)wi * per_warp;  // SPW packed rows
   double *col = stage + SPW * kkp;                   // [2][32] pivot-column exchange
   double *yb = col + 64;                             // [32]
-  double *zb = yb + 32;                              // [32]
+  double *zb = yb + 32;                              // [32]; zb[31 - ...] is never read beyond KP per sample
   // running max |W| per staged slot of this warp (column maxima for the int8 digit planes, fused here so the
   // M-step slicing does not need its own pass over W)
   double *cmw = smem_reg + (size_t)warps * per_warp + (size_t)wi * (SPW * kkp);
@@ -222,6 +232,13 @@ __global__ void __launch_bounds__(256, MINB) solve_reg_kernel(SolveArgs a) {
   const double s2 = a.sigma * a.sigma;
   const double ln_sigma = log(a.sigma);
   const int groups = (a.rows_pad + SPW - 1) / SPW;
+  // row li of the packed symmetric matrix: (li, j >= li) sits at up + j, (j < li, li) at j (2k - j - 1) / 2 + li.
+  // The gather offsets do not depend on the sample: computed once (padding lanes / columns: -1).
+  const int up = tri_row_off(li, k) - li;
+  int gi[KP];
+#pragma unroll
+  for (int j = 0; j < KP; ++j)
+    gi[j] = (li < k && j < k) ? ((j >= li) ? up + j : ((j * (2 * k - j - 1)) >> 1) + li) : -1;
 
   for (int g = blockIdx.x * warps + wi; g < groups; g += gridDim.x * warps) {
     const int row0 = g * SPW;
@@ -237,15 +254,11 @@ __global__ void __launch_bounds__(256, MINB) solve_reg_kernel(SolveArgs a) {
 
     const double *st = stage + sub * kkp;
     const bool live = li < k && !empty;
-    // row li of the packed symmetric matrix: (li, j >= li) sits at up + j, (j < li, li) at j (2k - j - 1) / 2 + li
-    const int up = tri_row_off(li, k) - li;
     double A[KP];
 #pragma unroll
-    for (int j = 0; j < KP; ++j) {  // branch-free: clamped index, unconditional load, select
-      int idx = (j >= li) ? up + j : ((j * (2 * k - j - 1)) >> 1) + li;
-      const bool use = live && j < k;
-      idx = use ? idx : 0;
-      const double g = st[idx];
+    for (int j = 0; j < KP; ++j) {  // M = sigma^2 I + G where live, the identity elsewhere
+      const bool use = !empty && gi[j] >= 0;
+      const double g = st[use ? gi[j] : 0];
       const double unit = (j == li) ? 1.0 : 0.0;
       A[j] = use ? fma(unit, s2, g) : unit;
     }
@@ -254,34 +267,32 @@ __global__ void __launch_bounds__(256, MINB) solve_reg_kernel(SolveArgs a) {
       if (guard_terms((double)dn) * a.guard_coef * a.gscale[qd] > s2 + st[qd]) atomicAdd(a.unsafe, 1u);
     }
 
-    double mypiv = 1.0, myinv = 1.0;
+    double mypiv = 1.0, sc = 1.0;  // d_i, and 1 / d_i once row li has been the pivot (1 before)
 #pragma unroll
     for (int p = 0; p < KP; ++p) {
+      const double dpp = __shfl_sync(0xffffffffu, A[p], sub * KP + p);  // current pivot, from the lane that owns row p
+      const double rinv = fast_rsqrt(dpp);
+      const double own = A[p] * rinv;  // s_i in this row's units
       double *cb = col + (p & 1) * 32;
-      double *cs = cb + sub * KP;
-      if (li == p) {  // the owner publishes the pivot row
-#pragma unroll
-        for (int j = 0; j < KP; j += 2) *reinterpret_cast<double2 *>(cs + j) = make_double2(A[j], A[j + 1]);
-      }
+      cb[lane] = own * sc;             // s_i in true units for everybody else
       __syncwarp();
-      const double dpp = cs[p];
-      const double inv = fast_rcp(dpp);
-      if (li == p) {
-        mypiv = dpp;
-        myinv = inv;
-      }
-      const double f = (li == p) ? 0.0 : A[p] * inv;
-      const double2 *cs2 = reinterpret_cast<const double2 *>(cs);
+      const bool isp = li == p;
+      const double f = isp ? 0.0 : own;  // the pivot row is left as it is (its 1/d is applied at the end)
+      const double2 *cs2 = reinterpret_cast<const double2 *>(cb + sub * KP);
 #pragma unroll
       for (int j = 0; j < KP; j += 2) {
         const double2 cv = cs2[j >> 1];
         if (j != p) A[j] = fma(-f, cv.x, A[j]);
         if (j + 1 != p) A[j + 1] = fma(-f, cv.y, A[j + 1]);
       }
-      A[p] = (li == p) ? 1.0 : -f;
+      A[p] = isp ? -1.0 : own * rinv;
+      if (isp) {
+        mypiv = dpp;
+        sc = rinv * rinv;
+      }
     }
-#pragma unroll
-    for (int j = 0; j < KP; ++j) A[j] *= myinv;  // A[j] = M^{-1}[li][j]
+    // M^-1[li][j] = -sc A[j]; the factor is folded into what follows instead of a pass over the row
+    const double nsc = -sc;
 
     // z = M^{-1} y ; quad = y^T z ; ln det
     double zi = 0.0;
@@ -290,7 +301,7 @@ __global__ void __launch_bounds__(256, MINB) solve_reg_kernel(SolveArgs a) {
 #pragma unroll
       for (int j = 0; j < KP; ++j) zi = fma(A[j], ys[j], zi);
     }
-    if (!live) zi = 0.0;
+    zi = live ? zi * nsc : 0.0;
     double quad = yb[lane] * zi;
     double logdet = live ? log(mypiv) : 0.0;
 #pragma unroll
@@ -316,9 +327,10 @@ __global__ void __launch_bounds__(256, MINB) solve_reg_kernel(SolveArgs a) {
     }
     if (a.cov && row < a.rows && li < k) {
       double *cv = a.cov + (int64_t)row * k * k + (int64_t)li * k;
+      const double cs = s2 * nsc;
 #pragma unroll
       for (int j = 0; j < KP; ++j)
-        if (j < k) cv[j] = empty ? (j == li ? 1.0 : 0.0) : s2 * A[j];
+        if (j < k) cv[j] = empty ? (j == li ? 1.0 : 0.0) : cs * A[j];
     }
     if (a.mode == 2) {
       // t = tr(Sigma G) = sigma^2 tr(M^{-1} (M - sigma^2 I)) = sigma^2 sum_i (1 - sigma^2 M^{-1}_ii)
@@ -328,7 +340,7 @@ __global__ void __launch_bounds__(256, MINB) solve_reg_kernel(SolveArgs a) {
 #pragma unroll
         for (int j = 0; j < KP; ++j)
           if (j == li) diag = A[j];
-        if (live) tpart = fma(-s2, diag, 1.0);
+        if (live) tpart = fma(-s2 * nsc, diag, 1.0);
       }
 #pragma unroll
       for (int o = KP / 2; o > 0; o >>= 1) tpart += __shfl_xor_sync(0xffffffffu, tpart, o);
@@ -338,7 +350,7 @@ __global__ void __launch_bounds__(256, MINB) solve_reg_kernel(SolveArgs a) {
       if (li < k) {
         double *so = stage + sub * kkp + up;
         const double *zs = zb + sub * KP;
-        const double ws2 = empty ? 0.0 : w * s2, wzi = empty ? 0.0 : w * zi;
+        const double ws2 = empty ? 0.0 : w * s2 * nsc, wzi = empty ? 0.0 : w * zi;
 #pragma unroll
         for (int j = 0; j < KP; ++j)
           if (j >= li && j < k) so[j] = fma(wzi, zs[j], ws2 * A[j]);
@@ -542,10 +554,10 @@ __global__ void __launch_bounds__(256, 2) solve_split64_kernel(SolveArgs a) {
   const int c0 = CW * h;
   const int bar_id = smp + 1;
   const int k = a.s.k, kkp = a.s.kkp, kp = a.s.kp;
-  const int per_smp = kkp + 2 * 128 + 64 + 128 + 16;
+  const int per_smp = kkp + 2 * 136 + 64 + 128 + 16;
   double *stage = smem_reg + (size_t)smp * per_smp;  // one packed row
-  double *col = stage + kkp;                         // [2][64 transformed | 64 raw]
-  double *yb = col + 256;                            // [64]
+  double *col = stage + kkp;                         // [2][64 true units | 64 own units | next diagonal, padded to 136]
+  double *yb = col + 272;                            // [64]
   double *zpart = yb + 64;                           // [2][64] partial z per column half
   double *red = zpart + 128;                         // [16]
   double *cmw = smem_reg + (size_t)2 * per_smp + (size_t)smp * kkp;  // running max |W| of this slot's samples
@@ -583,23 +595,32 @@ __global__ void __launch_bounds__(256, 2) solve_split64_kernel(SolveArgs a) {
       if (guard_terms((double)dn) * a.guard_coef * a.gscale[qd] > s2 + stage[qd]) atomicAdd(a.unsafe, 1u);
     }
 
-    double mypiv = 1.0, myinv = 1.0;
+    // Square-root form of the symmetric sweep (see solve_reg_kernel): commutative update products keep the two
+    // triangles bitwise equal, so the column-p entries every row owner publishes ARE the pivot row.  A thread of the
+    // half that does not hold column p takes its own s_i from its sibling through shared memory (slots 64..127).  The
+    // next pivot d_{p+1} = T[p+1][p+1] - s_{p+1}^2 is formed by EVERY thread from the published entry and the diagonal
+    // value its owner adds to the exchange (slot 128): one barrier per pivot, and 1/sqrt(d_{p+1}) overlaps the update.
+    double mypiv = 1.0, sc = 1.0;  // d_i, and 1 / d_i once row li has been the pivot (1 before)
+    double dcur = empty || k <= 0 ? 1.0 : s2 + stage[0];
 #pragma unroll
     for (int p = 0; p < KP; ++p) {
-      double *cb = col + (p & 1) * 128;  // [0,64) pivot row (published by its two owners), [64,128) raw column p
-      if (h == (p >> 5)) cb[64 + li] = A[p & 31];
-      if (li == p) {
-#pragma unroll
-        for (int jj = 0; jj < CW; jj += 2) *reinterpret_cast<double2 *>(cb + c0 + jj) = make_double2(A[jj], A[jj + 1]);
+      double *cb = col + (p & 1) * 136;  // [0,64) s in true units, [64,128) s in the row's own units, [128] next diagonal
+      const double dthis = dcur;
+      const double rinv = fast_rsqrt(dthis);
+      if (h == (p >> 5)) {
+        const double own = A[p & 31] * rinv;
+        cb[li] = own * sc;
+        cb[64 + li] = own;
       }
+      if (p + 1 < KP && li == p + 1 && h == ((p + 1) >> 5)) cb[128] = A[(p + 1) & 31];
       quad_sync(bar_id);
-      const double dpp = cb[p];
-      const double inv = fast_rcp(dpp);
-      if (li == p) {
-        mypiv = dpp;
-        myinv = inv;
+      const bool isp = li == p;
+      const double own = cb[64 + li];
+      const double f = isp ? 0.0 : own;  // the pivot row is left as it is (its 1/d is applied at the end)
+      if (p + 1 < KP) {
+        const double sn = cb[p + 1];
+        dcur = fma(-sn, sn, cb[128]);    // bitwise what the owner of row p + 1 computes below
       }
-      const double f = (li == p) ? 0.0 : cb[64 + li] * inv;
       const double2 *cb2 = reinterpret_cast<const double2 *>(cb + c0);
 #pragma unroll
       for (int jj = 0; jj < CW; jj += 2) {
@@ -607,10 +628,17 @@ __global__ void __launch_bounds__(256, 2) solve_split64_kernel(SolveArgs a) {
         A[jj] = fma(-f, cv.x, A[jj]);
         A[jj + 1] = fma(-f, cv.y, A[jj + 1]);
       }
-      if (h == (p >> 5)) A[p & 31] = (li == p) ? 1.0 : -f;
+      if (h == (p >> 5)) A[p & 31] = isp ? -1.0 : own * rinv;
+      if (isp) {
+        mypiv = dthis;
+        sc = rinv * rinv;
+      }
     }
+    {
+      const double nsc = -sc;
 #pragma unroll
-    for (int jj = 0; jj < CW; ++jj) A[jj] *= myinv;  // A[jj] = M^{-1}[li][c0 + jj]
+      for (int jj = 0; jj < CW; ++jj) A[jj] *= nsc;  // A[jj] = M^{-1}[li][c0 + jj]
+    }
 
     double zp = 0.0;
 #pragma unroll
@@ -951,7 +979,7 @@ static void launch_solve_blk(const Launcher &L, const SolveArgs &a) {
 }
 
 static void launch_solve_split64(const Launcher &L, const SolveArgs &a) {
-  const size_t smem = (size_t)2 * (a.s.kkp + 2 * 128 + 64 + 128 + 16 + (a.colmax ? a.s.kkp : 0)) * sizeof(double);
+  const size_t smem = (size_t)2 * (a.s.kkp + 2 * 136 + 64 + 128 + 16 + (a.colmax ? a.s.kkp : 0)) * sizeof(double);
   static PerDeviceOnce configured;
   if (configured.need()) {
     CUDA_CHECK(cudaFuncSetAttribute(solve_split64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));

@@ -119,17 +119,43 @@ def _scope(engine):
     return fn() if fn is not None else contextlib.nullcontext()
 
 
-class ShardedPPCA:
-    """EM for one PPCAModel over a dataset sharded across the ranks of `group` (None = single process)."""
+def native_comm_init(ctx: nat.Context, group) -> None:
+    """Gives `ctx` the library's own NCCL communicator (ppca_b200_comm_init) over the ranks of a torch.distributed
+    group: rank 0 creates the unique id, the group only ferries its 128 bytes."""
+    if getattr(ctx, "comm_world", 1) > 1:
+        return
+    rank, world = group.get_rank(), group.get_world_size()
+    box = [nat.Context.comm_unique_id() if rank == 0 else None]
+    group.broadcast_object_list(box, src=0)
+    ctx.comm_init(box[0], rank, world)
 
-    def __init__(self, ctx, dataset, model: PPCAModel, group=None, prior: Optional[Prior] = None, engine=None):
-        self.engine = engine or CudaEngine(ctx)
+
+class ShardedPPCA:
+    """EM for one PPCAModel over a dataset sharded across the ranks of `group` (None = single process).
+
+    collective="native" (the product default on GPUs): one call per step into ppca_b200_iterate_sharded /
+    ppca_b200_iterate_host_sharded; statistics, NCCL all-reduce and finish all run inside the library on the context's
+    stream.  collective="torch": the same protocol spelled out here (em_stats -> group.all_reduce -> em_finish), which is
+    what the CPU (gloo) tests exercise with a numpy engine."""
+
+    def __init__(self, ctx, dataset, model: PPCAModel, group=None, prior: Optional[Prior] = None, engine=None,
+                 collective: Optional[str] = None):
+        if collective is None:
+            collective = "native" if (engine is None and group is not None) else "torch"
+        self.native = collective == "native" and group is not None
         self.dataset, self.model, self.prior, self.group = dataset, model, prior, group
-        self.stats = self.engine.new_stats(model.output_size, model.state_size)
         self.last_llk = float("nan")
+        if self.native:
+            native_comm_init(ctx, group)
+            return
+        self.engine = engine or CudaEngine(ctx)
+        self.stats = self.engine.new_stats(model.output_size, model.state_size)
 
     def step(self) -> float:
         """One EM iteration; returns the (global) log-likelihood of the model the step started from."""
+        if self.native:
+            self.model, self.last_llk = self.model._iterate(self.dataset, self.prior, sharded=True)
+            return self.last_llk
         for _ in range(3):  # at most two climbs of the precision ladder (include/ppca_b200.h, PPCA_ERR_PRECISION)
             self.engine.em_stats(self.dataset, self.model, self.stats)
             if self.group is not None:
@@ -148,15 +174,28 @@ class ShardedPPCA:
 class ShardedPPCAMix:
     """EM for a PPCAMix over a sharded dataset (mix.rs:281-337)."""
 
-    def __init__(self, ctx, dataset, mix: PPCAMix, group=None, prior: Optional[Prior] = None, engine=None):
-        self.engine = engine or CudaEngine(ctx)
+    def __init__(self, ctx, dataset, mix: PPCAMix, group=None, prior: Optional[Prior] = None, engine=None,
+                 collective: Optional[str] = None):
+        if collective is None:
+            collective = "native" if engine is None else "torch"
+        # "native": single-pass mixture EM inside the library (ppca_b200_mix_iterate[_sharded]); "torch": the
+        # two-pass protocol below (posteriors, then one weighted pass per component), kept for the CPU (gloo) tests
+        self.native = collective == "native"
         self.dataset, self.mix, self.prior, self.group = dataset, mix, prior, group
+        self.last_llk = float("nan")
+        if self.native:
+            if group is not None:
+                native_comm_init(ctx, group)
+            return
+        self.engine = engine or CudaEngine(ctx)
         d = mix.output_size
         self.stats = [self.engine.new_stats(d, k) for k in mix.state_sizes]
         self.logpost = self.engine.new_logpost(len(dataset), len(mix._models))
-        self.last_llk = float("nan")
 
     def step(self) -> float:
+        if self.native:
+            self.mix, self.last_llk = self.mix._iterate(self.dataset, self.prior, sharded=self.group is not None)
+            return self.last_llk
         eng, mix = self.engine, self.mix
         m, d = len(mix._models), mix.output_size
         cmax, llk = eng.mix_posteriors(self.dataset, mix, self.logpost)

@@ -478,8 +478,11 @@ class PPCAModel:
     def extrapolate(self, dataset: Dataset) -> Dataset:
         return self._recon(dataset, nat.lib().ppca_b200_extrapolate)
 
-    def _iterate(self, dataset: Dataset, prior: Optional[Prior]):
-        """Returns (new model, llk of THIS model on dataset) — the E-step yields the latter for free."""
+    def _iterate(self, dataset: Dataset, prior: Optional[Prior], sharded: bool = False):
+        """Returns (new model, llk of THIS model on dataset) — the E-step yields the latter for free.
+        sharded=True: `dataset` is this rank's shard and the context carries a communicator (Context.comm_init): the
+        statistics are all-reduced inside the library (ppca_b200_iterate_sharded / _host_sharded), every rank returns
+        the same model and the GLOBAL log-likelihood."""
         self._check(dataset)
         d, k = self.output_size, self.state_size
         C_out = np.empty((d, k))
@@ -490,15 +493,16 @@ class PPCAModel:
         if prior is not None:
             pr, keep = prior._c(d)
             pr_ref = C.byref(pr)
+        lib = nat.lib()
         if isinstance(dataset, HostDataset):
-            nat.check(nat.lib().ppca_b200_iterate_host(dataset._ctx.handle, nat.dptr(dataset._x), len(dataset), d,
-                                                       nat.dptr(dataset._w), k, nat.dptr(self._C), nat.dptr(self._mu),
-                                                       self._sigma, pr_ref, nat.dptr(C_out), nat.dptr(mu_out),
-                                                       C.byref(s_out), C.byref(llk)))
+            fn = lib.ppca_b200_iterate_host_sharded if sharded else lib.ppca_b200_iterate_host
+            nat.check(fn(dataset._ctx.handle, nat.dptr(dataset._x), len(dataset), d, nat.dptr(dataset._w), k,
+                         nat.dptr(self._C), nat.dptr(self._mu), self._sigma, pr_ref, nat.dptr(C_out), nat.dptr(mu_out),
+                         C.byref(s_out), C.byref(llk)))
             return PPCAModel(s_out.value, C_out, mu_out), llk.value
-        nat.check(nat.lib().ppca_b200_iterate(dataset._ctx.handle, dataset._h, k, nat.dptr(self._C), nat.dptr(self._mu),
-                                              self._sigma, pr_ref, nat.dptr(C_out), nat.dptr(mu_out), C.byref(s_out),
-                                              C.byref(llk)))
+        fn = lib.ppca_b200_iterate_sharded if sharded else lib.ppca_b200_iterate
+        nat.check(fn(dataset._ctx.handle, dataset._h, k, nat.dptr(self._C), nat.dptr(self._mu), self._sigma, pr_ref,
+                     nat.dptr(C_out), nat.dptr(mu_out), C.byref(s_out), C.byref(llk)))
         return PPCAModel(s_out.value, C_out, mu_out), llk.value
 
     def iterate_with_prior(self, dataset: Dataset, prior: Prior) -> "PPCAModel":
@@ -750,7 +754,7 @@ class PPCAMix:
         self._call(nat.lib().ppca_b200_mix_extrapolate, dataset, C.byref(h))
         return Dataset._wrap(h, dataset._ctx)
 
-    def _iterate(self, dataset: Dataset, prior: Optional[Prior]):
+    def _iterate(self, dataset: Dataset, prior: Optional[Prior], sharded: bool = False):
         self._check(dataset)
         ks, Cs, mus, sig, lw = self._pack()
         Cs_o, mus_o, sig_o, lw_o = np.empty_like(Cs), np.empty_like(mus), np.empty_like(sig), np.empty_like(lw)
@@ -759,10 +763,10 @@ class PPCAMix:
         if prior is not None:
             pr, keep = prior._c(self.output_size)
             pr_ref = C.byref(pr)
-        nat.check(nat.lib().ppca_b200_mix_iterate(dataset._ctx.handle, dataset._h, len(self._models),
-                                                  ks.ctypes.data_as(nat.c_ip), nat.dptr(Cs), nat.dptr(mus),
-                                                  nat.dptr(sig), nat.dptr(lw), pr_ref, nat.dptr(Cs_o), nat.dptr(mus_o),
-                                                  nat.dptr(sig_o), nat.dptr(lw_o), C.byref(llk)))
+        fn = nat.lib().ppca_b200_mix_iterate_sharded if sharded else nat.lib().ppca_b200_mix_iterate
+        nat.check(fn(dataset._ctx.handle, dataset._h, len(self._models), ks.ctypes.data_as(nat.c_ip), nat.dptr(Cs),
+                     nat.dptr(mus), nat.dptr(sig), nat.dptr(lw), pr_ref, nat.dptr(Cs_o), nat.dptr(mus_o),
+                     nat.dptr(sig_o), nat.dptr(lw_o), C.byref(llk)))
         d = self.output_size
         models, off = [], 0
         for j, k in enumerate(ks):

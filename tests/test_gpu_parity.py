@@ -863,3 +863,109 @@ def test_precision_guard_mixture_responsibilities_spanning_1e30(pk, orc, guard_c
         assert np.max(np.abs(got.transform[5] - Cs[5])) < TOL * max(np.max(np.abs(Cs[5])), 1e-300)
         assert_close(got.mean, muw, mus, "mix mu")
         assert_close(got.isotropic_noise, sw, ss, "mix sigma")
+
+
+# ---- single-pass mixture EM: several chunks, the running per-component maximum is raised by later chunks -----------
+@pytest.mark.parametrize("chunk", [512, 1024, 0])
+def test_mixture_single_pass_rescales_across_chunks(pk, orc, chunk):
+    X, models, logw = _mix_case(pk, 2400, 24, (3, 5, 2, 8), seed=4)
+    n = X.shape[0]
+    w = np.random.default_rng(5).random(n) + 0.5
+    w[: n // 2] *= 1e-3                                   # light samples first: every later chunk raises ln w + lp
+    ds = pk.Dataset(X, w)
+    ctx = pk.get_context()
+    ctx.set_chunk(chunk)
+    try:
+        mix = pk.PPCAMix([pk.PPCAModel(s, C, mu) for C, mu, s in models], logw)
+        new, llk = mix._iterate(ds, None)
+    finally:
+        ctx.set_chunk(0)
+    (want_models, want_logw), (st_models, _) = both(orc, orc.mix_iterate, X, w, models, logw)
+    assert abs(llk - orc.mix_llk(X, w, models, logw)) < TOL * abs(llk)
+    assert np.max(np.abs(new.log_weights - want_logw)) < 1e-9
+    for got, (Cw, muw, sw), (Cs, mus, ss) in zip(new.models, want_models, st_models):
+        assert_close(got.transform, Cw, Cs, "mix C")
+        assert_close(got.mean, muw, mus, "mix mu")
+        assert_close(got.isotropic_noise, sw, ss, "mix sigma")
+
+
+# ---- the collective behind the C ABI (ppca_b200_comm_* and the *_sharded entry points) ----------------------------
+def test_sharded_entry_points_world_of_one(pk, orc):
+    """NCCL bound at run time, a communicator of one rank: the sharded calls must reproduce the plain ones bit for bit."""
+    from ppca_rs_b200 import _native as nat
+    ctx = nat.Context(0)
+    ctx.comm_init(nat.Context.comm_unique_id(), 0, 1)
+    X, C0, mu0, s0 = _case(3000, 60, 8, 0.2, seed=6)
+    w = np.random.default_rng(1).random(3000) + 0.5
+    ds = pk.Dataset(X, w, _ctx=ctx)
+    model = pk.PPCAModel(s0, C0, mu0)
+    a, llk_a = model._iterate(ds, None)
+    b, llk_b = model._iterate(ds, None, sharded=True)
+    assert np.array_equal(a.transform, b.transform) and np.array_equal(a.mean, b.mean)
+    assert a.isotropic_noise == b.isotropic_noise and llk_a == llk_b
+    host = pk.HostDataset(X, w, pin=False, ctx=ctx)
+    c, llk_c = model._iterate(host, None, sharded=True)
+    assert rel_err(c.transform, a.transform) < 1e-12 and abs(llk_c - llk_a) < 1e-12 * abs(llk_a)
+    Xm, models, logw = _mix_case(pk, 900, 24, (3, 5, 2))
+    dsm = pk.Dataset(Xm, _ctx=ctx)
+    mix = pk.PPCAMix([pk.PPCAModel(s, C, mu) for C, mu, s in models], logw)
+    m1, l1 = mix._iterate(dsm, None)
+    m2, l2 = mix._iterate(dsm, None, sharded=True)
+    assert l1 == l2 and np.array_equal(m1.log_weights, m2.log_weights)
+    for x, y in zip(m1.models, m2.models):
+        assert np.array_equal(x.transform, y.transform)
+    ctx.comm_destroy()
+
+
+def _two_gpu_rank(rank, uid, X, w, C0, mu0, s0, Xm, models, logw, out):
+    import ppca_rs_b200 as pk
+    from ppca_rs_b200 import _native as nat
+    from ppca_rs_b200.distributed import shard_bounds
+    ctx = nat.Context(rank)
+    ctx.comm_init(uid, rank, 2)
+    lo, hi = shard_bounds(X.shape[0], 2, rank)
+    ds = pk.Dataset(X[lo:hi], w[lo:hi], _ctx=ctx)
+    model = pk.PPCAModel(s0, C0, mu0)
+    llks = []
+    for _ in range(3):
+        model, llk = model._iterate(ds, None, sharded=True)
+        llks.append(llk)
+    lo, hi = shard_bounds(Xm.shape[0], 2, rank)
+    mix = pk.PPCAMix([pk.PPCAModel(s, C, mu) for C, mu, s in models], logw)
+    mix, mllk = mix._iterate(pk.Dataset(Xm[lo:hi], _ctx=ctx), None, sharded=True)
+    out[rank] = (model, llks, mix, mllk)
+    ctx.synchronize()
+
+
+def test_sharded_entry_points_two_gpus(pk, orc):
+    """Two ranks (threads, one GPU each) through ppca_b200_iterate_sharded / ppca_b200_mix_iterate_sharded against the
+    oracle on the whole dataset."""
+    import threading
+    from ppca_rs_b200 import _native as nat
+    if nat.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    n, d, k = 6000, 90, 12
+    X, C0, mu0, s0 = _case(n, d, k, 0.25, seed=21)
+    w = np.random.default_rng(2).random(n) + 0.5
+    Xm, models, logw = _mix_case(pk, 1800, 24, (3, 5, 2, 8), seed=3)
+    uid = nat.Context.comm_unique_id()
+    out = {}
+    th = [threading.Thread(target=_two_gpu_rank, args=(r, uid, X, w, C0, mu0, s0, Xm, models, logw, out)) for r in range(2)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(timeout=300)
+    assert set(out) == {0, 1}
+    (m0, l0, x0, ml0), (m1, l1, x1, ml1) = out[0], out[1]
+    assert np.array_equal(m0.transform, m1.transform) and l0 == l1 and ml0 == ml1     # replicated finish
+    C, mu, s = C0, mu0, s0
+    with orc.stable():
+        for it in range(3):
+            assert abs(l0[it] - orc.llk(X, w, C, mu, s)) < TOL * abs(l0[it])
+            C, mu, s = orc.iterate(X, w, C, mu, s)
+        want_models, want_logw = orc.mix_iterate(Xm, None, models, logw)
+    assert rel_err(m0.transform, C) < 1e-8 and rel_err(m0.mean, mu) < 1e-8 and abs(m0.isotropic_noise - s) < 1e-8 * s
+    assert abs(ml0 - orc.mix_llk(Xm, None, models, logw)) < TOL * abs(ml0)
+    assert np.max(np.abs(x0.log_weights - want_logw)) < 1e-9
+    for got, (Cw, muw, sw) in zip(x0.models, want_models):
+        assert rel_err(got.transform, Cw) < TOL and rel_err(got.mean, muw) < TOL and abs(got.isotropic_noise - sw) < TOL * sw
