@@ -104,7 +104,7 @@ int32_t ppca_b200_ctx_launch_count(ppca_b200_ctx *ctx, int64_t *out);
 /* Launches so far per shape-dependent kernel variant, 16 counters (tests assert which code path a case ran):
  *   0 tbitgemm_kernel (A tile in shared memory, T = 7, 8)   1 tbitgemm_atm_kernel<T,2,1>   2 tbitgemm_atm_kernel<T,1,2>
  *   3 tbitgemm_atm2_kernel (two output tiles per mask stage)  4 ibitgemm_kernel (IMMA)      5 bitgemm_kernel (DMMA)
- *   6-8 solve_reg_kernel<8|16|32>   9 solve_split64_kernel   10 solve_reg64_kernel   11 solve_blk_kernel
+ *   6-8 solve_reg_kernel<8|16|32>   9 solve_split64_kernel   10, 11 unused (kernels removed in round 2)
  *   12 solve_kernel (generic)   13 passes repeated at a wider arithmetic by the precision guard
  *   14 batched mixture contraction launches   15 reserved */
 int32_t ppca_b200_ctx_variant_counts(ppca_b200_ctx *ctx, int64_t *out16);
@@ -178,6 +178,14 @@ int32_t ppca_b200_smooth(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int32_
                          const double *mu, double sigma, ppca_b200_dataset **out);
 int32_t ppca_b200_extrapolate(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int32_t k, const double *C,
                               const double *mu, double sigma, ppca_b200_dataset **out);
+/* smooth (extrapolate = 0) / extrapolate (= 1) and, from the SAME E-step, PPCAModel::llks (ppca_model.rs:152-159) into
+ * `llks` (host, n entries, nullable).  `reuse` (nullable) is a dataset an earlier smooth / extrapolate / reconstruct call
+ * returned for an input of the same shape: its storage is overwritten in place (no allocation, no mask rebuild) and
+ * *out == reuse; with reuse == NULL a new dataset is created.  This is what a streaming inference loop calls per batch:
+ * the reference runs the per-sample algebra once for extrapolate and once more for llks. */
+int32_t ppca_b200_reconstruct(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int32_t k, const double *C,
+                              const double *mu, double sigma, int32_t extrapolate, ppca_b200_dataset *reuse,
+                              double *llks, ppca_b200_dataset **out);
 /* PPCAModel::iterate_with_prior (ppca_model.rs:277-393); prior may be NULL (= iterate, :267-269).
  * llk_in (nullable) receives the log-likelihood of the INPUT model on ds, which the E-step produces
  * for free (what PPCATrainer prints each iteration, python/ppca_rs/__init__.py:51). */
@@ -214,8 +222,10 @@ int32_t ppca_b200_host_unregister(const void *p);
 /* ---- sharded EM: one process per GPU, statistics all-reduced by the caller --------------------- */
 /* Length (in doubles) of the additive sufficient-statistics buffer for (d, k):
  *   [ A: d x kkp | B: d x kp | tdev: d | totals: d | 8 scalars ]   kkp = roundup8(k(k+1)/2), kp = roundup8(k)
- * scalars: 0 = sum w tr(C_o Sigma_n C_o^T) (square_error), 1 = sum w |dev|^2, 2 = sum w llk_n,
- *          3 = sum w (all samples), 4 = number of non-empty samples, 5..7 reserved. */
+ * scalars: 0 = sum w (tr(C_o Sigma_n C_o^T) + |dev_n|^2)  (square_error + deviations_square_sum, ppca_model.rs:345-346; the
+ *          residual norm is |x~|^2 - y^T z - sigma^2 |z|^2, never a pass over the residual itself), 1 = 0 (kept for
+ *          layout compatibility), 2 = sum w llk_n, 3 = sum w (all samples), 4 = number of non-empty samples,
+ *          5 = E-step and 6 = M-step precision-guard violations of this shard (see ppca_b200_ctx_set_guard), 7 reserved. */
 int64_t ppca_b200_em_stats_len(int32_t d, int32_t k);
 /* E-step + local M-step statistics of this shard (ppca_model.rs:278-358) into stats_dev (DEVICE memory,
  * overwritten).  Asynchronous on the context's stream. */

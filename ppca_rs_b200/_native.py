@@ -89,6 +89,10 @@ _PROTOTYPES = {
     ),
     "ppca_b200_smooth": (C.c_int32, [c_ctx_p, c_ds_p, C.c_int32, c_dp, c_dp, C.c_double, C.POINTER(c_ds_p)]),
     "ppca_b200_extrapolate": (C.c_int32, [c_ctx_p, c_ds_p, C.c_int32, c_dp, c_dp, C.c_double, C.POINTER(c_ds_p)]),
+    "ppca_b200_reconstruct": (
+        C.c_int32,
+        [c_ctx_p, c_ds_p, C.c_int32, c_dp, c_dp, C.c_double, C.c_int32, c_ds_p, c_dp, C.POINTER(c_ds_p)],
+    ),
     "ppca_b200_iterate": (
         C.c_int32,
         [c_ctx_p, c_ds_p, C.c_int32, c_dp, c_dp, C.c_double, C.POINTER(CPrior), c_dp, c_dp, c_dp, c_dp],
@@ -246,7 +250,7 @@ class Context:
         return out.value
 
     VARIANTS = ("tc_smem_a", "tc_atm_feed", "tc_atm_drain", "tc_atm2", "imma", "dmma", "solve_reg8", "solve_reg16",
-                "solve_reg32", "solve_split64", "solve_pair64", "solve_blk", "solve_generic", "precision_retry",
+                "solve_reg32", "solve_split64", "unused10", "unused11", "solve_generic", "precision_retry",
                 "tc_mix", "reserved15")
 
     def variant_counts(self) -> Dict[str, int]:

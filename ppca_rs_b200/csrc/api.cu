@@ -42,6 +42,12 @@ struct ppca_b200_ctx {
   int guard_bits = 40;   // eps = 2^-guard_bits: accepted perturbation of M_n / A_i relative to their diagonals
   int rung = 0, rung_ttl = 0;
   int64_t em_rows = 0;   // samples accumulated since em_begin (term count of the M-step guard)
+  DevBuf<int8_t> ZQ;             // digit planes of w Z (second M-step contraction, Mask^T (w Z))
+  DevBuf<double> ZScale, MZ, part_mz;
+  DevBuf<unsigned long long> zcolmax;
+  DevBuf<double> dv, part_rx;    // identity-form residual norms of a chunk; partial slots of the exact residual pass
+  DevBuf<int> rflag;
+  DevBuf<double> rscratch;       // block totals + completion counter of solve_reduce_kernel (zeroed at allocation)
   DevBuf<unsigned int> unsafe;   // [0] E-step guard violations (solve kernels), [1] spare
   DevBuf<double> WScaleMax;      // running maximum over chunks of the W column scales
   DevBuf<int8_t> KsymQ, WQ;
@@ -368,7 +374,22 @@ ModelWs resolve_ws(ppca_b200_ctx *ctx, const DevModel &m) {
   w.part_bg = ctx->part_bg.p;
   w.part_cr = ctx->part_cr.p;
   w.part_solve = ctx->part_solve.p;
+  w.ZQ = ctx->ZQ.p;
+  w.ZScale = ctx->ZScale.p;
+  w.MZ = ctx->MZ.p;
+  w.part_mz = ctx->part_mz.p;
+  w.zcolmax = ctx->zcolmax.p;
+  w.dv = ctx->dv.p;
+  w.rflag = ctx->rflag.p;
+  w.part_rx = ctx->part_rx.p;
+  w.rscratch = ctx->rscratch.p;
   return w;
+}
+
+void ensure_rscratch(ppca_b200_ctx *ctx) {
+  if (ctx->rscratch.p) return;
+  ctx->rscratch.alloc((size_t)SOLVE_SCRATCH);
+  CUDA_CHECK(cudaMemsetAsync(ctx->rscratch.p, 0, sizeof(double) * SOLVE_SCRATCH, ctx->stream));
 }
 
 void reserve_chunk_ws(ppca_b200_ctx *ctx, int64_t chunk, const Shape &s) {
@@ -378,6 +399,9 @@ void reserve_chunk_ws(ppca_b200_ctx *ctx, int64_t chunk, const Shape &s) {
   ctx->nx.reserve((size_t)chunk);
   ctx->llk.reserve((size_t)chunk);
   ctx->tn.reserve((size_t)chunk);
+  ctx->dv.reserve((size_t)chunk);
+  ctx->rflag.reserve(8);
+  ensure_rscratch(ctx);
 }
 
 // E-step of one chunk: Gram contraction, projection, per-sample solve
@@ -443,8 +467,10 @@ void e_step_chunk(ppca_b200_ctx *ctx, const SampleStore &st, const double *w, in
   sa.w = w ? w + row0 : nullptr;
   sa.llk = llk_out;
   sa.tn = mode == 2 ? ws.tn : nullptr;
+  sa.dv = mode == 2 ? ws.dv : nullptr;
   sa.cov = cov_out;
   sa.part = solve_part;
+  sa.rscratch = ws.rscratch;
   sa.mode = mode;
   sa.colmax = w_colmax;
   if (guard_on(ctx)) {
@@ -467,13 +493,18 @@ struct EmPlan {
   int splitk = 1;
   size_t bglen = 0, crlen = 0;
   int slabs = 1;
+  int splitk_mz = 1;  // split-K of the second contraction Mask^T (w Z) (d x kp)
+  size_t mzlen = 0;
+  size_t rxlen = 0;   // partial slots of the exact residual pass
 };
 
-size_t wq_bytes(const ppca_b200_ctx *ctx, int64_t chunk, const Shape &s) {
+size_t planes_bytes(const ppca_b200_ctx *ctx, int64_t chunk, int Nq) {
   const int kb_chunk = (int)(chunk / 32);
-  return ctx->gemm_mode == 2 ? sliced_tc_bytes(kb_chunk, s.kkp, ctx->slices)
-                             : (ctx->gemm_mode == 1 ? sliced_bytes(kb_chunk, s.kkp, ctx->slices) : 0);
+  return ctx->gemm_mode == 2 ? sliced_tc_bytes(kb_chunk, Nq, ctx->slices)
+                             : (ctx->gemm_mode == 1 ? sliced_bytes(kb_chunk, Nq, ctx->slices) : 0);
 }
+size_t wq_bytes(const ppca_b200_ctx *ctx, int64_t chunk, const Shape &s) { return planes_bytes(ctx, chunk, s.kkp); }
+size_t zq_bytes(const ppca_b200_ctx *ctx, int64_t chunk, const Shape &s) { return planes_bytes(ctx, chunk, s.kp); }
 
 // sizes of the split-K / slab partial slots for chunks of `chunk` rows
 EmPlan em_plan(const ppca_b200_ctx *ctx, int64_t chunk, const Shape &s) {
@@ -484,8 +515,13 @@ EmPlan em_plan(const ppca_b200_ctx *ctx, int64_t chunk, const Shape &s) {
              : ctx->gemm_mode == 1 ? ibitgemm_pick_splitk(s.d, s.kkp, kb_chunk, ctx->sms)
                                    : bitgemm_pick_splitk(s.d, s.kkp, kb_chunk, ctx->sms);
   p.bglen = bitgemm_partials_len(s.d, s.kkp, p.splitk);
+  p.splitk_mz = ctx->gemm_mode == 2   ? tbitgemm_pick_splitk(s.d, s.kp, kb_chunk / 4, ctx->sms)
+                : ctx->gemm_mode == 1 ? ibitgemm_pick_splitk(s.d, s.kp, kb_chunk, ctx->sms)
+                                      : bitgemm_pick_splitk(s.d, s.kp, kb_chunk, ctx->sms);
+  p.mzlen = bitgemm_partials_len(s.d, s.kp, p.splitk_mz);
   p.slabs = cross_resid_slabs(s.d, s.k, (int)p.chunk, ctx->sms);
   p.crlen = cross_resid_partials_len(s.d, s.k, p.slabs);
+  p.rxlen = resid_exact_partials_len(s.d, p.slabs);
   return p;
 }
 
@@ -496,6 +532,10 @@ void em_zero(ppca_b200_ctx *ctx, const ModelWs &ws, const EmPlan &p, const Shape
   if (p.bglen) CUDA_CHECK(cudaMemsetAsync(ws.part_bg, 0, sizeof(double) * p.bglen, ctx->stream));
   CUDA_CHECK(cudaMemsetAsync(ws.part_cr, 0, sizeof(double) * p.crlen, ctx->stream));
   CUDA_CHECK(cudaMemsetAsync(ws.part_solve, 0, sizeof(double) * SOLVE_SLOTS * 4, ctx->stream));
+  CUDA_CHECK(cudaMemsetAsync(ws.part_rx, 0, sizeof(double) * p.rxlen, ctx->stream));
+  CUDA_CHECK(cudaMemsetAsync(ws.rflag, 0, sizeof(int), ctx->stream));
+  CUDA_CHECK(cudaMemsetAsync(ws.MZ, 0, sizeof(double) * (size_t)s.d * s.kp, ctx->stream));
+  if (p.mzlen) CUDA_CHECK(cudaMemsetAsync(ws.part_mz, 0, sizeof(double) * p.mzlen, ctx->stream));
 }
 
 EmPlan em_begin(ppca_b200_ctx *ctx, int64_t chunk, const DevModel &m, double *stats_dev) {
@@ -511,6 +551,14 @@ EmPlan em_begin(ppca_b200_ctx *ctx, int64_t chunk, const DevModel &m, double *st
   ctx->part_bg.reserve(p.bglen);
   ctx->part_cr.reserve(p.crlen);
   ctx->part_solve.reserve((size_t)SOLVE_SLOTS * 4);
+  if (ctx->gemm_mode != 0) {
+    ctx->ZQ.reserve(zq_bytes(ctx, p.chunk, m.s));
+    ctx->ZScale.reserve((size_t)m.s.kp);
+    ctx->zcolmax.reserve((size_t)m.s.kp);
+  }
+  ctx->MZ.reserve((size_t)m.s.d * m.s.kp);
+  ctx->part_mz.reserve(p.mzlen);
+  ctx->part_rx.reserve(p.rxlen);
   em_zero(ctx, resolve_ws(ctx, m), p, m.s, stats_dev);
   return p;
 }
@@ -522,72 +570,81 @@ void m_step_chunk(ppca_b200_ctx *ctx, const SampleStore &st, const double *wloc,
   const Launcher L = ctx->L();
   const ModelWs ws = resolve_ws(ctx, m);
   const StatsLayout lay(m.s.d, m.s.k);
-  const int splitk = p.splitk;
   const int kblocks = (int)(round_up(rows, 32) / 32);
-  int sk = splitk < kblocks ? splitk : (kblocks > 0 ? kblocks : 1);
-  if (splitk > 1 && sk < 2) sk = 2 <= kblocks ? 2 : 1;
-  const bool direct = splitk > 1 && sk == 1;  // degenerate last chunk: accumulate straight into the statistics
-  if (ctx->gemm_mode == 2) {
-    ctx->span_begin(FAM_SLICE);
-    launch_slice_tc(L, ws.GW, m.s.kkp, rows, m.s.kkp, kblocks, ctx->slices, ws.WQ, ws.WScale, ws.colmax, have_colmax);
-    ctx->span_end();
-  } else if (ctx->gemm_mode == 1) {
-    ctx->span_begin(FAM_SLICE);
-    launch_slice(L, ws.GW, m.s.kkp, rows, m.s.kkp, kblocks, ctx->slices, ws.WQ, ws.WScale, ws.colmax);
-    ctx->span_end();
-  }
-  if (guard_on(ctx)) launch_scale_max(L, ws.WScale, m.s.kkp, ws.WScaleMax);
-  ctx->span_begin(FAM_MOMENT);
-  if (ctx->gemm_mode == 2) {
-    const int ksteps = (kblocks + 3) / 4;
-    int skt = splitk < ksteps ? splitk : ksteps;
-    if (skt < 1) skt = 1;
-    {  // no empty slabs
-      const int per = (ksteps + skt - 1) / skt;
-      skt = (ksteps + per - 1) / per;
+  // Out[d x Nq] += Mask^T[d x rows] * Bsrc[rows x Nq] on the configured arithmetic, split-K partials deferred to em_end
+  auto contract = [&](const double *Bsrc, int Nq, int8_t *Q, double *Scale, unsigned long long *cmax, bool have_cmax,
+                      double *Out, double *partials, int splitk, double *scale_max) {
+    int sk = splitk < kblocks ? splitk : (kblocks > 0 ? kblocks : 1);
+    if (splitk > 1 && sk < 2) sk = 2 <= kblocks ? 2 : 1;
+    const bool direct = splitk > 1 && sk == 1;  // degenerate last chunk: accumulate straight into the output
+    if (ctx->gemm_mode == 2) {
+      ctx->span_begin(FAM_SLICE);
+      launch_slice_tc(L, Bsrc, Nq, rows, Nq, kblocks, ctx->slices, Q, Scale, cmax, have_cmax);
+      ctx->span_end();
+    } else if (ctx->gemm_mode == 1) {
+      ctx->span_begin(FAM_SLICE);
+      launch_slice(L, Bsrc, Nq, rows, Nq, kblocks, ctx->slices, Q, Scale, cmax);
+      ctx->span_end();
     }
-    const bool to_partials = splitk > 1 && skt > 1;
-    launch_tbitgemm(L, st.maskT.p + row0 / 32, st.nwT, 4 * ksteps, ws.WQ, ws.WScale, ctx->slices,
-                    stats_dev + lay.offA, m.s.kkp, m.s.d, m.s.kkp, ksteps, 1, to_partials ? ws.part_bg : nullptr,
-                    skt, to_partials ? 1 : 0);
-  } else if (ctx->gemm_mode == 1) {
-    IBitGemmArgs g;
-    g.bits = st.maskT.p + row0 / 32;
-    g.ldbits = st.nwT;
-    g.Bq = ws.WQ;
-    g.scale = ws.WScale;
-    g.T = ctx->slices;
-    g.Out = stats_dev + lay.offA;
-    g.ldo = m.s.kkp;
-    g.M = m.s.d;
-    g.Nq = m.s.kkp;
-    g.kblocks = kblocks;
-    g.accumulate = 1;
-    g.splitk = sk;
-    g.partials = (splitk > 1 && !direct) ? ws.part_bg : nullptr;
-    g.defer_reduce = direct ? 0 : 1;
-    launch_ibitgemm(L, g);
-  } else {
-    BitGemmArgs g;
-    g.bits = st.maskT.p + row0 / 32;
-    g.ldbits = st.nwT;
-    g.Bmat = ws.GW;
-    g.ldb = m.s.kkp;
-    g.Out = stats_dev + lay.offA;
-    g.ldo = m.s.kkp;
-    g.M = m.s.d;
-    g.Nq = m.s.kkp;
-    g.kblocks = kblocks;
-    g.kcols = 32 * kblocks;
-    g.accumulate = 1;
-    g.splitk = sk;
-    g.partials = (splitk > 1 && !direct) ? ws.part_bg : nullptr;
-    g.defer_reduce = direct ? 0 : 1;
-    launch_bitgemm(L, g);
-  }
-  ctx->span_end();
+    if (scale_max && guard_on(ctx)) launch_scale_max(L, Scale, Nq, scale_max);
+    ctx->span_begin(FAM_MOMENT);
+    if (ctx->gemm_mode == 2) {
+      const int ksteps = (kblocks + 3) / 4;
+      int skt = splitk < ksteps ? splitk : ksteps;
+      if (skt < 1) skt = 1;
+      {  // no empty slabs
+        const int per = (ksteps + skt - 1) / skt;
+        skt = (ksteps + per - 1) / per;
+      }
+      const bool to_partials = splitk > 1 && skt > 1;
+      launch_tbitgemm(L, st.maskT.p + row0 / 32, st.nwT, 4 * ksteps, Q, Scale, ctx->slices, Out, Nq, m.s.d, Nq, ksteps, 1,
+                      to_partials ? partials : nullptr, skt, to_partials ? 1 : 0);
+    } else if (ctx->gemm_mode == 1) {
+      IBitGemmArgs g;
+      g.bits = st.maskT.p + row0 / 32;
+      g.ldbits = st.nwT;
+      g.Bq = Q;
+      g.scale = Scale;
+      g.T = ctx->slices;
+      g.Out = Out;
+      g.ldo = Nq;
+      g.M = m.s.d;
+      g.Nq = Nq;
+      g.kblocks = kblocks;
+      g.accumulate = 1;
+      g.splitk = sk;
+      g.partials = (splitk > 1 && !direct) ? partials : nullptr;
+      g.defer_reduce = direct ? 0 : 1;
+      launch_ibitgemm(L, g);
+    } else {
+      BitGemmArgs g;
+      g.bits = st.maskT.p + row0 / 32;
+      g.ldbits = st.nwT;
+      g.Bmat = Bsrc;
+      g.ldb = Nq;
+      g.Out = Out;
+      g.ldo = Nq;
+      g.M = m.s.d;
+      g.Nq = Nq;
+      g.kblocks = kblocks;
+      g.kcols = 32 * kblocks;
+      g.accumulate = 1;
+      g.splitk = sk;
+      g.partials = (splitk > 1 && !direct) ? partials : nullptr;
+      g.defer_reduce = direct ? 0 : 1;
+      launch_bitgemm(L, g);
+    }
+    ctx->span_end();
+  };
+  // A += Mask^T W   (second moments, ppca_model.rs:297-306)
+  contract(ws.GW, m.s.kkp, ws.WQ, ws.WScale, ws.colmax, have_colmax, stats_dev + lay.offA, ws.part_bg, p.splitk,
+           ws.WScaleMax);
+  // MZ += Mask^T (w Z)   (the part of total_deviation that needs the mask, ppca_model.rs:338-347)
+  contract(ws.WZ, m.s.kp, ws.ZQ, ws.ZScale, ws.zcolmax, false, ws.MZ, ws.part_mz, p.splitk_mz, nullptr);
   ctx->span_begin(FAM_CROSS);
-  launch_cross_resid(L, st, row0, rows, m, ws.YZ, ws.WZ, wloc, ws.part_cr, p.slabs);
+  launch_cross_resid(L, st, row0, rows, m, ws.WZ, wloc, ws.part_cr, p.slabs);
+  // exact residual norms for a chunk whose identity-form ones were flagged (returns at once otherwise)
+  launch_resid_exact(L, st, row0, rows, m, ws.YZ, wloc, ws.rflag, ws.part_rx, p.slabs);
   ctx->span_end();
 }
 
@@ -596,7 +653,11 @@ void em_chunk(ppca_b200_ctx *ctx, const SampleStore &st, const double *w, int64_
   const ModelWs ws = resolve_ws(ctx, m);
   // the solve kernels (state_size <= 64) leave the column maxima of W behind for the tcgen05 digit planes
   const bool fused_colmax = ctx->gemm_mode == 2 && m.s.k <= 64;
-  e_step_chunk(ctx, st, w, row0, rows, m, 2, ws.llk, nullptr, ws.part_solve, fused_colmax ? ws.colmax : nullptr);
+  e_step_chunk(ctx, st, w, row0, rows, m, 2, ws.llk, nullptr, nullptr, fused_colmax ? ws.colmax : nullptr);
+  ctx->span_begin(FAM_SOLVE);
+  launch_solve_reduce(ctx->L(), rows, ws.llk, ws.tn, ws.dv, ws.nx, st.dn.p + row0, w + row0, ws.part_solve, ws.rscratch,
+                      ws.rflag);
+  ctx->span_end();
   ctx->em_rows += rows;
   m_step_chunk(ctx, st, w + row0, row0, rows, m, stats_dev, p, fused_colmax);
 }
@@ -611,10 +672,12 @@ void em_end(ppca_b200_ctx *ctx, const DevModel &m, double *stats_dev, const EmPl
   ctx->span_end();
   ctx->span_begin(FAM_MOMENT);
   launch_bitgemm_reduce(L, ws.part_bg, p.splitk, m.s.d, m.s.kkp, stats_dev + lay.offA, m.s.kkp, 1);
+  launch_bitgemm_reduce(L, ws.part_mz, p.splitk_mz, m.s.d, m.s.kp, ws.MZ, m.s.kp, 1);
   ctx->span_end();
   ctx->span_begin(FAM_CROSS);
-  launch_cross_resid_finish(L, m.s.d, m.s.k, ws.part_cr, p.slabs, stats_dev + lay.offB, stats_dev + lay.offTdev,
-                            stats_dev + lay.offTotals, stats_dev + lay.offScalars);
+  launch_cross_resid_finish(L, m.s.d, m.s.k, ws.part_cr, p.slabs, m.C, ws.MZ, stats_dev + lay.offB,
+                            stats_dev + lay.offTdev, stats_dev + lay.offTotals);
+  launch_resid_exact_finish(L, m.s.d, ws.part_rx, p.slabs, stats_dev + lay.offScalars);
   ctx->span_end();
   if (guard_on(ctx)) {  // scalars 5, 6: guard violations of this shard's E- and M-step contractions
     ctx->span_begin(FAM_FINISH);
@@ -681,7 +744,7 @@ bool host_qr_solve(std::vector<double> &A, int n, std::vector<double> &b) {
 // returns the precision-guard violations carried by the (reduced) statistics
 double em_finish_impl(ppca_b200_ctx *ctx, int d, int k, const double *C, const double *mu, double sigma,
                       const ppca_b200_prior *prior, const double *stats_dev, double *C_out, double *mu_out,
-                      double *sigma_out, double *llk_in, double *sumw_out) {
+                      double *sigma_out, double *llk_in, double *sumw_out, double *viol_em = nullptr) {
   REQUIRE(C && mu && C_out && mu_out && sigma_out, "null model parameters");
   const Shape s(d, k);
   const StatsLayout lay(d, k);
@@ -743,6 +806,10 @@ double em_finish_impl(ppca_b200_ctx *ctx, int d, int k, const double *C, const d
   *sigma_out = std::sqrt(noise_sq);  // :389
   if (llk_in) *llk_in = sc[SC_LLK];
   if (sumw_out) *sumw_out = sc[SC_SUMW];
+  if (viol_em) {
+    viol_em[0] = sc[SC_UNSAFE_E];
+    viol_em[1] = sc[SC_UNSAFE_M];
+  }
   return sc[SC_UNSAFE_E] + sc[SC_UNSAFE_M];
 }
 
@@ -784,13 +851,15 @@ __global__ void strided_copy_kernel(const double *src, int64_t n, int cols, int6
 
 // smooth / extrapolate into a fresh all-observed store; scale/accumulate for mixtures
 void reconstruct_impl(ppca_b200_ctx *ctx, const SampleStore &st, const DevModel &m, int extrapolate,
-                      const double *scale, int64_t scale_ld, int accumulate, SampleStore &out) {
+                      const double *scale, int64_t scale_ld, int accumulate, SampleStore &out,
+                      double *llk_dev = nullptr) {
   if (st.n == 0) return;
   const int64_t chunk = pick_chunk(ctx, st.n_pad, m.s);
   reserve_chunk_ws(ctx, chunk, m.s);
   for (int64_t row0 = 0; row0 < st.n; row0 += chunk) {
     const int rows = (int)((st.n - row0) < chunk ? (st.n - row0) : chunk);
-    e_step_chunk(ctx, st, nullptr, row0, rows, m, 1, nullptr, nullptr, nullptr);
+    // the per-sample log-likelihoods are a by-product of the same E-step (llk_dev: n entries, nullable)
+    e_step_chunk(ctx, st, nullptr, row0, rows, m, 1, llk_dev ? llk_dev + row0 : nullptr, nullptr, nullptr);
     launch_reconstruct(ctx->L(), st, row0, rows, m, ctx->YZ.p, extrapolate, scale ? scale + row0 * scale_ld : nullptr,
                        scale_ld, accumulate, out.X.p + row0 * out.ldx, out.ldx);
   }
@@ -1442,12 +1511,48 @@ static int32_t smooth_or_extrapolate(ppca_b200_ctx *ctx, const ppca_b200_dataset
       });
       finalize_full_store(ctx, *ost);
     }
+    ost->full = true;
     std::unique_ptr<ppca_b200_dataset> nd(make_dataset(ctx, ost, nullptr));
     if (st.n > 0)  // weights are carried through (ppca_model.rs:242,259)
       CUDA_CHECK(cudaMemcpyAsync(nd->w.p, ds->w.p, sizeof(double) * st.n, cudaMemcpyDeviceToDevice, ctx->stream));
     nd->min_w = ds->min_w;
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     *out = nd.release();
+  });
+}
+
+int32_t ppca_b200_reconstruct(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int32_t k, const double *C,
+                              const double *mu, double sigma, int32_t extrapolate, ppca_b200_dataset *reuse,
+                              double *llks, ppca_b200_dataset **out) {
+  return guarded([&] {
+    check_ds(ctx, ds);
+    REQUIRE(out != nullptr, "null output");
+    const SampleStore &st = *ds->store;
+    if (reuse) {
+      check_ds(ctx, reuse);
+      REQUIRE(reuse != ds && reuse->store != ds->store, "the output dataset must not share samples with the input");
+      REQUIRE(reuse->store->n == st.n && reuse->store->d == st.d, "the reused output dataset has another shape");
+      REQUIRE(reuse->store->full, "the reused output must be a dataset produced by smooth / extrapolate (all observed)");
+    }
+    DeviceGuard g(ctx->device);
+    std::shared_ptr<SampleStore> ost = reuse ? reuse->store : make_store(ctx, st.n, st.d);
+    if (st.n > 0) {
+      if (llks) ctx->rbuf.reserve((size_t)st.n_pad);
+      run_guarded(ctx, [&] {
+        DevModel m = stage_model(ctx, st.d, k, C, mu, sigma);
+        reconstruct_impl(ctx, st, m, extrapolate, nullptr, 0, 0, *ost, llks ? ctx->rbuf.p : nullptr);
+        return read_unsafe(ctx);
+      });
+      if (!reuse) finalize_full_store(ctx, *ost);
+      if (llks) CUDA_CHECK(cudaMemcpyAsync(llks, ctx->rbuf.p, sizeof(double) * st.n, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    ost->full = true;
+    ppca_b200_dataset *nd = reuse ? reuse : make_dataset(ctx, ost, nullptr);
+    if (st.n > 0)  // weights are carried through (ppca_model.rs:242,259)
+      CUDA_CHECK(cudaMemcpyAsync(nd->w.p, ds->w.p, sizeof(double) * st.n, cudaMemcpyDeviceToDevice, ctx->stream));
+    nd->min_w = ds->min_w;
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    *out = nd;
   });
 }
 
@@ -1975,7 +2080,7 @@ struct Carver {
   }
 };
 
-void mix_em_pass(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, const MixView &mv, MixPass &out) {
+void mix_em_pass(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, const MixView &mv, MixPass &out, double *LP_full) {
   const SampleStore &st = *ds->store;
   const Launcher L = ctx->L();
   const int M = mv.m, d = st.d;
@@ -1987,7 +2092,7 @@ void mix_em_pass(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, const MixView 
     shp[j] = Shape(d, mv.ks[j]);
     kp_max = std::max(kp_max, shp[j].kp);
     kkp_max = std::max(kkp_max, shp[j].kkp);
-    per_row += (int64_t)(shp[j].kkp + shp[j].kp + 1) * 8;
+    per_row += (int64_t)(shp[j].kkp + shp[j].kp + 3) * 8;
     stats_total += round_up(StatsLayout(d, mv.ks[j]).len, 4);  // every component's buffer stays 32-byte aligned
   }
   per_row += (int64_t)(2 * M + kp_max + 4) * 8 + (int64_t)kkp_max * ctx->slices;
@@ -2002,12 +2107,13 @@ void mix_em_pass(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, const MixView 
   }
   chunk = std::min<int64_t>(round_up(chunk, 256), st.n_pad);
 
+  ensure_rscratch(ctx);
   // ---- carve the arenas (two passes: size, then pointers)
   out.comps.assign(M, MixComp());
   size_t need = 0, need_q = 0;
   double *sh_nx = nullptr, *sh_llk = nullptr, *sh_WZ = nullptr, *sh_r = nullptr, *LPc = nullptr, *mixllk = nullptr,
          *chunk_max = nullptr, *factor = nullptr;
-  int8_t *sh_WQ = nullptr;
+  int8_t *sh_WQ = nullptr, *sh_ZQ = nullptr;
   for (int pass = 0; pass < 2; ++pass) {
     if (pass == 1) {
       ctx->mixArena.reserve(need);
@@ -2031,6 +2137,12 @@ void mix_em_pass(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, const MixView 
       for (int j = 0; j < M; ++j) wq = std::max(wq, wq_bytes(ctx, chunk, shp[j]));
       qoff += (wq + 1023) & ~(size_t)1023;
     }
+    sh_ZQ = pass ? ctx->mixArenaQ.p + qoff : nullptr;
+    {
+      size_t zq = 0;
+      for (int j = 0; j < M; ++j) zq = std::max(zq, zq_bytes(ctx, chunk, shp[j]));
+      qoff += (zq + 1023) & ~(size_t)1023;
+    }
     int64_t soff = 0;
     for (int j = 0; j < M; ++j) {
       MixComp &c = out.comps[j];
@@ -2047,7 +2159,16 @@ void mix_em_pass(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, const MixView 
       c.ws.part_bg = cv.take(c.plan.bglen);
       c.ws.part_cr = cv.take(c.plan.crlen);
       c.ws.part_solve = cv.take((size_t)SOLVE_SLOTS * 4);
-      c.ws.nx = sh_nx;
+      c.ws.ZScale = cv.take((size_t)s.kp);
+      c.ws.zcolmax = reinterpret_cast<unsigned long long *>(cv.take((size_t)s.kp));
+      c.ws.MZ = cv.take((size_t)s.d * s.kp);
+      c.ws.part_mz = cv.take(c.plan.mzlen);
+      c.ws.ZQ = sh_ZQ;
+      c.ws.nx = cv.take((size_t)chunk);   // |x~|^2 depends on the component's mean
+      c.ws.dv = cv.take((size_t)chunk);
+      c.ws.part_rx = cv.take(c.plan.rxlen);
+      c.ws.rflag = reinterpret_cast<int *>(cv.take(4));
+      c.ws.rscratch = ctx->rscratch.p;
       c.ws.llk = sh_llk;
       c.ws.WZ = sh_WZ;
       c.ws.WQ = sh_WQ;
@@ -2098,6 +2219,9 @@ void mix_em_pass(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, const MixView 
     // log-posteriors of the chunk (mix.rs:179-189), mixture log-likelihood (:162-174), chunk maxima of ln w + lp (:312-318)
     launch_log_softmax_rows(L, LPc, rows, M, ctx->logw.p, ds->w.p + row0, mixllk, chunk_max, nullptr);
     launch_weighted_sum(L, mixllk, ds->w.p + row0, rows, llk_sum, 1);
+    if (LP_full)  // kept for the per-component repeats of the precision ladder
+      CUDA_CHECK(cudaMemcpyAsync(LP_full + row0 * M, LPc, sizeof(double) * (size_t)rows * M, cudaMemcpyDeviceToDevice,
+                                 ctx->stream));
     launch_mix_update_max(L, M, out.run_max, chunk_max, factor);
     for (int j = 0; j < M; ++j) {
       MixComp &c = out.comps[j];
@@ -2108,6 +2232,9 @@ void mix_em_pass(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, const MixView 
         launch_scale_by(L, c.ws.part_bg, (int64_t)c.plan.bglen, factor + j, 0);
         launch_scale_by(L, c.ws.part_cr, (int64_t)c.plan.crlen, factor + j, 0);
         launch_scale_by(L, c.ws.part_solve, (int64_t)SOLVE_SLOTS * 4, factor + j, 1);
+        launch_scale_by(L, c.ws.MZ, (int64_t)s.d * s.kp, factor + j, 0);
+        launch_scale_by(L, c.ws.part_mz, (int64_t)c.plan.mzlen, factor + j, 0);
+        launch_scale_by(L, c.ws.part_rx, (int64_t)c.plan.rxlen, factor + j, 0);
       }
       // column maxima of W fused into the weighting kernel (its shared-memory scratch holds 8 rows of W)
       const bool tc = ctx->gemm_mode == 2 && (size_t)8 * s.kkp * sizeof(double) <= 200 * 1024;
@@ -2115,7 +2242,8 @@ void mix_em_pass(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, const MixView 
       ctx->span_begin(FAM_SOLVE);
       launch_mix_weight(L, LPc, M, j, ds->w.p + row0, out.run_max, rows, rows_pad, s.kkp, s.kp, c.ws.GW, c.ws.YZ, sh_WZ,
                         sh_r, tc ? c.ws.colmax : nullptr);
-      launch_solve_reduce(L, rows, nullptr, c.ws.tn, st.dn.p + row0, sh_r, c.ws.part_solve);
+      launch_solve_reduce(L, rows, nullptr, c.ws.tn, c.ws.dv, c.ws.nx, st.dn.p + row0, sh_r, c.ws.part_solve, c.ws.rscratch,
+                          c.ws.rflag);
       ctx->span_end();
       m_step_chunk(ctx, st, sh_r, row0, rows, c.m, c.stats, c.plan, tc);
     }
@@ -2140,8 +2268,16 @@ void mix_iterate_impl(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int32_t m
   std::vector<double> cmax(m), sumw(m);
   double llk = 0.0;
   run_guarded(ctx, [&] {
+    Rung rungs[3];
+    const int nrungs = ladder(ctx, rungs);
+    const bool can_climb = guard_on(ctx) && ctx->rung + 1 < nrungs;
+    double *LP_full = nullptr;
+    if (can_climb) {
+      ctx->mixLP.reserve((size_t)std::max<int64_t>(st.n, 1) * m);
+      LP_full = ctx->mixLP.p;
+    }
     MixPass pass;
-    mix_em_pass(ctx, ds, mv, pass);
+    mix_em_pass(ctx, ds, mv, pass, LP_full);
     ctx->mixMax.reserve((size_t)2 * m);
     double *gmax = ctx->mixMax.p;  // global maxima (= local ones in a single process)
     CUDA_CHECK(cudaMemcpyAsync(gmax, pass.run_max, sizeof(double) * m, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -2158,13 +2294,51 @@ void mix_iterate_impl(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int32_t m
     CUDA_CHECK(cudaMemcpyAsync(&llk, pass.stats_all + pass.stats_total - 1, sizeof(double), cudaMemcpyDeviceToHost,
                                ctx->stream));
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-    double viol = 0.0;
+    double viol_e = 0.0, viol_m = 0.0;
+    std::vector<double> vm(m, 0.0);
     for (int j = 0; j < m; ++j) {
       const size_t off = (size_t)(mv.C(j) - Cs);
-      viol += em_finish_impl(ctx, st.d, ks[j], mv.C(j), mv.mu(j), sigmas[j], prior, pass.comps[j].stats, Cs_out + off,
-                             mus_out + (size_t)j * st.d, sigmas_out + j, nullptr, &sumw[j]);
+      double v2[2] = {0.0, 0.0};
+      em_finish_impl(ctx, st.d, ks[j], mv.C(j), mv.mu(j), sigmas[j], prior, pass.comps[j].stats, Cs_out + off,
+                     mus_out + (size_t)j * st.d, sigmas_out + j, nullptr, &sumw[j], v2);
+      viol_e = std::max(viol_e, v2[0]);  // one counter for the whole pass (the solve kernels of every component)
+      vm[j] = v2[1];
+      viol_m += v2[1];
     }
-    return viol;
+    if (getenv("PPCA_B200_DEBUG")) {
+      int nflag = 0;
+      for (int j = 0; j < m; ++j) nflag += vm[j] > 0.0;
+      fprintf(stderr, "[ppca_b200] mixture pass at rung %d: E-step violations %.0f, components with M-step violations %d/%d\n",
+              ctx->rung, viol_e, nflag, m);
+    }
+    if (viol_e > 0.0 || !can_climb) return viol_e + viol_m;  // the whole pass climbs (or nothing can)
+    // Only M-step violations: a component whose second moments sit far below their column scales (few effective samples).
+    // Repeat THAT component alone, as a weighted single-model pass from the kept log-posteriors, one rung up at a time.
+    const int base_mode = ctx->gemm_mode, base_slices = ctx->slices;
+    for (int j = 0; j < m; ++j) {
+      if (!(vm[j] > 0.0)) continue;
+      const size_t off = (size_t)(mv.C(j) - Cs);
+      const int64_t slen = StatsLayout(st.d, ks[j]).len;
+      for (int r = ctx->rung + 1; r < nrungs; ++r) {
+        ctx->gemm_mode = rungs[r].mode;
+        ctx->slices = rungs[r].slices;
+        guard_reset(ctx);
+        ++ctx->variants[V_PRECISION_RETRY];
+        ctx->rbuf.reserve((size_t)st.n_pad);
+        CUDA_CHECK(cudaMemsetAsync(ctx->rbuf.p, 0, sizeof(double) * st.n_pad, ctx->stream));
+        launch_responsibilities(ctx->L(), LP_full, st.n, m, j, ds->w.p, cmax[j], ctx->rbuf.p);
+        DevModel dm = stage_model(ctx, st.d, ks[j], mv.C(j), mv.mu(j), sigmas[j]);
+        ctx->stats.reserve((size_t)slen);
+        em_stats_impl(ctx, st, ctx->rbuf.p, dm, ctx->stats.p);
+        if (sharded) comm_allreduce(ctx->comm, ctx->stats.p, slen, 0, ctx->stream);
+        const double v = em_finish_impl(ctx, st.d, ks[j], mv.C(j), mv.mu(j), sigmas[j], prior, ctx->stats.p, Cs_out + off,
+                                        mus_out + (size_t)j * st.d, sigmas_out + j, nullptr, &sumw[j]);
+        if (!(v > 0.0)) break;
+      }
+    }
+    ctx->gemm_mode = base_mode;
+    ctx->slices = base_slices;
+    return 0.0;
   });
   if (llk_in) *llk_in = llk;
   std::vector<double> logsum(m);

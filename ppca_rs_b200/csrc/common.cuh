@@ -118,6 +118,7 @@ struct SampleStore {
   DevBuf<uint32_t> mask;   // n_pad x dw  ; bit b of word j <-> dimension 32 j + b (LSB first, like bit-vec)
   DevBuf<uint32_t> maskT;  // d_pad x nwT ; bit b of word j <-> sample 32 j + b
   DevBuf<int> dn;          // n_pad observed counts
+  bool full = false;       // every slot observed (an output of smooth / extrapolate): may be overwritten in place
 };
 
 }  // namespace ppca
@@ -141,6 +142,14 @@ struct ModelWs {
   double *WScale = nullptr, *WScaleMax = nullptr;
   unsigned long long *colmax = nullptr;
   double *part_bg = nullptr, *part_cr = nullptr, *part_solve = nullptr;
+  // Mask^T (w Z): the second M-step contraction (d x kp), its digit planes, scales and split-K partials
+  int8_t *ZQ = nullptr;
+  double *ZScale = nullptr, *MZ = nullptr, *part_mz = nullptr;
+  unsigned long long *zcolmax = nullptr;
+  double *dv = nullptr;       // per-sample |R_n|^2 of the chunk (identity form)
+  int *rflag = nullptr;       // chunk flag: take the residual norms from the exact pass instead
+  double *part_rx = nullptr;  // partial slots of the exact residual pass
+  double *rscratch = nullptr; // SOLVE_SCRATCH doubles (block totals + completion counter of solve_reduce_kernel)
 };
 
 // per-iteration device model
@@ -166,8 +175,8 @@ enum Variant {
   V_SOLVE_REG16,
   V_SOLVE_REG32,
   V_SOLVE_SPLIT64,
-  V_SOLVE_PAIR64,
-  V_SOLVE_BLK,
+  V_UNUSED10,
+  V_UNUSED11,
   V_SOLVE_GENERIC,
   V_PRECISION_RETRY,  // passes repeated at a wider arithmetic after the precision guard fired
   V_TC_MIX,           // batched mixture contraction launches
@@ -260,6 +269,8 @@ struct SolveArgs {
   const double *w;     // rows (nullable = 1)
   double *llk;         // rows : out per-sample log-likelihood (nullable)
   double *tn;          // rows : out per-sample tr(Sigma_n G_n) (nullable, mode 2)
+  double *dv = nullptr;  // rows : out per-sample |R_n|^2, R_n = m (x~ - C z) (nullable, mode 2).  The residual is never
+                         // formed: G z = y - sigma^2 z gives |R_n|^2 = nx - y^T z - sigma^2 |z|^2 (ppca_model.rs:338-346)
   double *cov;         // rows x k x k full covariances (nullable)
   double *part;        // SOLVE_SLOTS x 4 partial sums to accumulate into (nullable; needs llk): w t, w llk, w, #non-empty
   int mode;            // 0 = llk only, 1 = infer (z, cov), 2 = EM (z, W, wz, t)
@@ -271,6 +282,7 @@ struct SolveArgs {
   // of M_n = sigma^2 I + G_n is small in the diagonally scaled sense under which its inverse / determinant are
   // well conditioned (off-diagonal scales obey s_ab <= 2 sqrt(s_aa s_bb)).  Violations are counted in unsafe[0]; the
   // host then repeats the pass at a wider arithmetic (api.cu, run_guarded).
+  double *rscratch = nullptr;      // SOLVE_SCRATCH doubles for the reduction behind `part`
   const double *gscale = nullptr;  // kkp column scales of the Ksym digit planes
   double guard_coef = 0.0;         // 2^-(8T-1) / eps
   unsigned int *unsafe = nullptr;
@@ -282,21 +294,31 @@ __host__ __device__ inline double guard_terms(double n) {
   const double r = 4.0 * sqrt(n);
   return n < r ? n : r;
 }
-enum { SOLVE_SLOTS = 128 };
+enum { SOLVE_SLOTS = 128, SOLVE_SCRATCH = 128 * 6 + 2 };
 void launch_solve(const Launcher &L, const SolveArgs &a);
 // part[slot][0..3] += sum over the slot's rows of (w t, w llk, w, #non-empty) — what launch_solve does when a.part is set
-void launch_solve_reduce(const Launcher &L, int rows, const double *llk, const double *tn, const int *dn, const double *w,
-                         double *part);
+// dv (nullable) = identity-form residual norms, folded into slot 0 unless the chunk's cancellation check fails, in which
+// case *resid_flag = 1 and resid_exact_kernel supplies them; scratch = SOLVE_SCRATCH doubles (zeroed once at allocation)
+void launch_solve_reduce(const Launcher &L, int rows, const double *llk, const double *tn, const double *dv,
+                         const double *nx, const int *dn, const double *w, double *part, double *scratch, int *resid_flag);
 // sums the partial slots (fixed order) into scalars[SC_SQERR, SC_LLK, SC_SUMW, SC_NONEMPTY]
 void launch_solve_finish(const Launcher &L, const double *part, double *scalars);
 
-// moments.cu : B += Xc^T (w z) ; residual statistics ; reconstruction writers
+// moments.cu : B += Xc^T (w z), weighted column sums of Xc, totals ; reconstruction writers
 // accumulates into per-(slab, dimension block) partial slots (zeroed by the caller before the first chunk);
-// launch_cross_resid_finish reduces them once, in fixed order, into the statistics buffer
+// launch_cross_resid_finish reduces them once, in fixed order, into the statistics buffer and forms
+// tdev_i = Sx_i - sum_a C[i][a] MZ[i][a]  (MZ = Mask^T (w Z), d x kp, from the M-step contraction)
 void launch_cross_resid(const Launcher &L, const SampleStore &st, int64_t row0, int rows, const DevModel &m,
-                        const double *Z, const double *WZ, const double *w, double *partials, int slabs_alloc);
-void launch_cross_resid_finish(const Launcher &L, int d, int k, const double *partials, int slabs_alloc, double *statB,
-                               double *statTdev, double *statTotals, double *scalars);
+                        const double *WZ, const double *w, double *partials, int slabs_alloc);
+void launch_cross_resid_finish(const Launcher &L, int d, int k, const double *partials, int slabs_alloc,
+                               const double *Cpad, const double *MZ, double *statB, double *statTdev,
+                               double *statTotals);
+// exact sum_n w_n |m (x~ - C z)|^2 of a chunk into per-(slab, dimension block) slots pD — runs only when *flag != 0
+// (every CTA returns at once otherwise); launch_resid_exact_finish adds the slots to scalars[SC_DEV2]
+void launch_resid_exact(const Launcher &L, const SampleStore &st, int64_t row0, int rows, const DevModel &m, const double *Z,
+                        const double *w, const int *flag, double *pD, int slabs_alloc);
+void launch_resid_exact_finish(const Launcher &L, int d, const double *pD, int slabs_alloc, double *scalars);
+size_t resid_exact_partials_len(int d, int slabs_alloc);
 int cross_resid_slabs(int d, int k, int rows, int sms);
 size_t cross_resid_partials_len(int d, int k, int slabs_alloc);
 // out = extrapolate ? (m ? x : C z + mu) : C z + mu ; scale != null multiplies by scale[n*scale_ld] and accumulates

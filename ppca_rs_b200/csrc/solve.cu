@@ -70,6 +70,7 @@ __global__ void __launch_bounds__(256) solve_kernel(SolveArgs a) {
       if (row < a.rows) {
         if (a.llk && lane == 0) a.llk[row] = 0.0;
         if (a.tn && lane == 0) a.tn[row] = 0.0;
+        if (a.dv && lane == 0) a.dv[row] = 0.0;
         if (a.cov)
           for (int q = lane; q < k * k; q += 32) a.cov[(int64_t)row * k * k + q] = (q / k == q % k) ? 1.0 : 0.0;
       }
@@ -182,8 +183,12 @@ __global__ void __launch_bounds__(256) solve_kernel(SolveArgs a) {
       }
       if (a.mode == 2) {
         for (int q = kk + lane; q < kkp; q += 32) G[q] = 0.0;
+        double zz = 0.0;
+        for (int q = lane; q < k; q += 32) zz = fma(zv[q], zv[q], zz);
         tpart = warp_sum(tpart);
+        zz = warp_sum(zz);
         if (a.tn && lane == 0) a.tn[row] = s2 * tpart;
+        if (a.dv && lane == 0) a.dv[row] = (a.nx[row] - quad) - s2 * zz;  // |R_n|^2, see SolveArgs::dv
       }
     }
     __syncwarp();
@@ -342,9 +347,16 @@ __global__ void __launch_bounds__(256, MINB) solve_reg_kernel(SolveArgs a) {
           if (j == li) diag = A[j];
         if (live) tpart = fma(-s2 * nsc, diag, 1.0);
       }
+      double zz = zi * zi;
 #pragma unroll
-      for (int o = KP / 2; o > 0; o >>= 1) tpart += __shfl_xor_sync(0xffffffffu, tpart, o);
-      if (a.tn && li == 0 && row < a.rows) a.tn[row] = empty ? 0.0 : s2 * tpart;
+      for (int o = KP / 2; o > 0; o >>= 1) {
+        tpart += __shfl_xor_sync(0xffffffffu, tpart, o);
+        zz += __shfl_xor_sync(0xffffffffu, zz, o);
+      }
+      if (li == 0 && row < a.rows) {
+        if (a.tn) a.tn[row] = empty ? 0.0 : s2 * tpart;
+        if (a.dv) a.dv[row] = empty ? 0.0 : (a.nx[row] - quad) - s2 * zz;  // |R_n|^2, see SolveArgs::dv
+      }
       __syncwarp();  // everyone is done reading G and zb is visible
       // W = w (z z^T + sigma^2 M^{-1}), upper triangle of row li, packed in place
       if (li < k) {
@@ -381,162 +393,7 @@ __global__ void __launch_bounds__(256, MINB) solve_reg_kernel(SolveArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// 32 < k <= 64: the same elimination with 64 lanes (two warps) per sample; the pivot-column exchange and the
-// reductions go through shared memory with a 64-thread named barrier per sample.
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void pair_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
-
-__global__ void __launch_bounds__(256, 1) solve_reg64_kernel(SolveArgs a) {
-  constexpr int KP = 64;
-  extern __shared__ __align__(16) double smem_reg[];
-  const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
-  const int pair = wi >> 1, li = (wi & 1) * 32 + lane;
-  const int bar_id = pair + 1;
-  const int k = a.s.k, kkp = a.s.kkp, kp = a.s.kp;
-  const int per_pair = kkp + 5 * 64;
-  double *stage = smem_reg + (size_t)pair * per_pair;  // one packed row
-  double *col = stage + kkp;                           // [2][64]
-  double *yb = col + 128;                              // [64]
-  double *zb = yb + 64;                                // [64]
-  double *red = zb + 64;                               // [64] scratch for reductions
-  double *cmw = smem_reg + (size_t)4 * per_pair + (size_t)pair * kkp;  // running max |W| of this pair's samples
-  if (a.colmax)
-    for (int q = li; q < kkp; q += 64) cmw[q] = 0.0;
-  const double s2 = a.sigma * a.sigma;
-  const double ln_sigma = log(a.sigma);
-
-  for (int row = blockIdx.x * 4 + pair; row < a.rows_pad; row += gridDim.x * 4) {
-    double *gsrc = a.GW + (int64_t)row * kkp;
-    for (int q = li * 2; q < kkp; q += 128)
-      *reinterpret_cast<double2 *>(stage + q) = *reinterpret_cast<const double2 *>(gsrc + q);
-    yb[li] = (li < kp) ? a.YZ[(int64_t)row * kp + li] : 0.0;
-    const int dn = row < a.rows ? a.dn[row] : 0;
-    const bool empty = dn == 0;
-    const double w = (a.w && row < a.rows) ? a.w[row] : (row < a.rows ? 1.0 : 0.0);
-    pair_sync(bar_id);
-
-    const bool live = li < k && !empty;
-    const int up = tri_row_off(li, k) - li;
-    double A[KP];
-#pragma unroll
-    for (int j = 0; j < KP; ++j) {  // branch-free: clamped index, unconditional load, select
-      int idx = (j >= li) ? up + j : ((j * (2 * k - j - 1)) >> 1) + li;
-      const bool use = live && j < k;
-      idx = use ? idx : 0;
-      const double g = stage[idx];
-      const double unit = (j == li) ? 1.0 : 0.0;
-      A[j] = use ? fma(unit, s2, g) : unit;
-    }
-    if (a.gscale && live) {  // precision guard (see SolveArgs)
-      const int qd = up + li;
-      if (guard_terms((double)dn) * a.guard_coef * a.gscale[qd] > s2 + stage[qd]) atomicAdd(a.unsafe, 1u);
-    }
-
-    double mypiv = 1.0, myinv = 1.0;
-#pragma unroll
-    for (int p = 0; p < KP; ++p) {
-      double *cb = col + (p & 1) * 64;
-      if (li == p) {  // the owner publishes the pivot row (see solve_reg_kernel)
-#pragma unroll
-        for (int j = 0; j < KP; j += 2) *reinterpret_cast<double2 *>(cb + j) = make_double2(A[j], A[j + 1]);
-      }
-      pair_sync(bar_id);
-      const double dpp = cb[p];
-      const double inv = fast_rcp(dpp);
-      if (li == p) {
-        mypiv = dpp;
-        myinv = inv;
-      }
-      const double f = (li == p) ? 0.0 : A[p] * inv;
-      const double2 *cb2 = reinterpret_cast<const double2 *>(cb);
-#pragma unroll
-      for (int j = 0; j < KP; j += 2) {
-        const double2 cv = cb2[j >> 1];
-        if (j != p) A[j] = fma(-f, cv.x, A[j]);
-        if (j + 1 != p) A[j + 1] = fma(-f, cv.y, A[j + 1]);
-      }
-      A[p] = (li == p) ? 1.0 : -f;
-    }
-#pragma unroll
-    for (int j = 0; j < KP; ++j) A[j] *= myinv;
-
-    double zi = 0.0;
-#pragma unroll
-    for (int j = 0; j < KP; ++j) zi = fma(A[j], yb[j], zi);
-    if (!live) zi = 0.0;
-    double quad = warp_sum(yb[li] * zi);
-    double logdet = warp_sum(live ? log(mypiv) : 0.0);
-    if (lane == 0) {
-      red[(wi & 1) * 2] = quad;
-      red[(wi & 1) * 2 + 1] = logdet;
-    }
-    zb[li] = zi;
-    pair_sync(bar_id);
-    if (a.llk && li == 0 && row < a.rows) {
-      double llk = 0.0;
-      if (!empty)
-        llk = -0.5 * (a.nx[row] - (red[0] + red[2])) / s2 -
-              0.5 * ((red[1] + red[3]) + 2.0 * ln_sigma * (double)(dn - k)) - 0.5 * LN_2PI * (double)dn;
-      a.llk[row] = llk;
-    }
-    if (a.mode != 0) {
-      if (li < kp) {
-        a.YZ[(int64_t)row * kp + li] = zi;
-        if (a.WZ) a.WZ[(int64_t)row * kp + li] = w * zi;
-      }
-      if (a.cov && row < a.rows && li < k) {
-        double *cv = a.cov + (int64_t)row * k * k + (int64_t)li * k;
-#pragma unroll
-        for (int j = 0; j < KP; ++j)
-          if (j < k) cv[j] = empty ? (j == li ? 1.0 : 0.0) : s2 * A[j];
-      }
-    }
-    if (a.mode == 2) {
-      double tpart = 0.0;
-      {
-        double diag = 0.0;
-#pragma unroll
-        for (int j = 0; j < KP; ++j)
-          if (j == li) diag = A[j];
-        if (live) tpart = fma(-s2, diag, 1.0);
-      }
-      tpart = warp_sum(tpart);
-      if (lane == 0) red[4 + (wi & 1)] = tpart;
-      pair_sync(bar_id);  // all reads of G done, partial traces visible
-      if (a.tn && li == 0 && row < a.rows) a.tn[row] = empty ? 0.0 : s2 * (red[4] + red[5]);
-      if (li < k) {
-        double *so = stage + up;
-        const double ws2 = empty ? 0.0 : w * s2, wzi = empty ? 0.0 : w * zi;
-#pragma unroll
-        for (int j = 0; j < KP; ++j)
-          if (j >= li && j < k) so[j] = fma(wzi, zb[j], ws2 * A[j]);
-      }
-      pair_sync(bar_id);
-      for (int q = li * 2; q < kkp; q += 128) {
-        const double2 v = *reinterpret_cast<const double2 *>(stage + q);
-        *reinterpret_cast<double2 *>(gsrc + q) = v;
-        if (a.colmax) {
-          double2 m = *reinterpret_cast<const double2 *>(cmw + q);
-          m.x = fmax(m.x, fabs(v.x));
-          m.y = fmax(m.y, fabs(v.y));
-          *reinterpret_cast<double2 *>(cmw + q) = m;
-        }
-      }
-    }
-    pair_sync(bar_id);
-  }
-  if (a.colmax) {
-    __syncthreads();
-    const double *all = smem_reg + (size_t)4 * per_pair;
-    for (int c = threadIdx.x; c < kkp; c += blockDim.x) {
-      const double m = fmax(fmax(all[c], all[kkp + c]), fmax(all[2 * kkp + c], all[3 * kkp + c]));
-      if (m > 0.0) atomicMax(a.colmax + c, (unsigned long long)__double_as_longlong(m));
-    }
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// 32 < k <= 64, second variant: 128 threads per sample.  Thread (i, h) owns columns [32 h, 32 h + 32) of row i,
+// 32 < k <= 64: 128 threads per sample.  Thread (i, h) owns columns [32 h, 32 h + 32) of row i,
 // so the per-pivot dependent chain is 32 FMAs instead of 64, registers halve (two CTAs of two samples per SM)
 // and twice as many warps hide the exchange / reciprocal latency.  Same elimination as above; the column
 // exchange carries both the symmetric-transformed value (pivot row) and the raw value (this row's multiplier).
@@ -657,7 +514,11 @@ __global__ void __launch_bounds__(256, 2) solve_split64_kernel(SolveArgs a) {
       for (int jj = 0; jj < CW; ++jj)
         if (c0 + jj == li) diag = A[jj];
       tpart = warp_sum((live && h == (li >> 5)) ? fma(-s2, diag, 1.0) : 0.0);
-      if (lane == 0) red[8 + ws] = tpart;
+      const double zz = warp_sum(h == 0 ? zi * zi : 0.0);
+      if (lane == 0) {
+        red[8 + ws] = tpart;
+        red[12 + ws] = zz;
+      }
     }
     quad_sync(bar_id);
     if (ts == 0 && row < a.rows) {
@@ -669,6 +530,7 @@ __global__ void __launch_bounds__(256, 2) solve_split64_kernel(SolveArgs a) {
         a.llk[row] = llk;
       }
       if (a.mode == 2 && a.tn) a.tn[row] = empty ? 0.0 : s2 * (red[8] + red[9] + red[10] + red[11]);
+      if (a.mode == 2 && a.dv) a.dv[row] = empty ? 0.0 : (a.nx[row] - (red[4] + red[5])) - s2 * (red[12] + red[13]);
     }
     if (a.mode != 0) {
       if (h == 0 && li < kp) {
@@ -717,267 +579,6 @@ __global__ void __launch_bounds__(256, 2) solve_split64_kernel(SolveArgs a) {
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Blocked Gauss-Jordan on the FP64 tensor cores (k <= 64).  M_n is held as 8 x 8 tiles in the accumulator layout
-// of mma.sync.m8n8k4.f64: warp i of the sample owns block row i (NT tiles, 2 doubles per lane each).  Per pivot
-// block b (in place, no pivoting: every pivot block is an SPD Schur complement):
-//     A_bb <- P^-1 ;  A_bj <- P^-1 A_bj ;  A_ib <- -A_ib P^-1 ;  A_ij <- A_ij - (A_ib P^-1) A_bj
-// Warp b publishes its raw row block to shared memory, inverts the 8 x 8 pivot block in registers (scalar
-// Gauss-Jordan over warp shuffles: the only serial part) and publishes P^-1; after ONE barrier every warp updates its
-// block row with 2 NT DMMAs, taking the B operands (A_bj, P^-1) from shared memory and converting its own panel tile
-// from accumulator to A-operand layout with two shuffles per half.  Against the scalar kernels above this issues
-// k^3 / 256 DMMAs instead of k^3 / 32 DFMAs plus a 2 k-byte pivot-row broadcast per pivot, so the FP64 pipe, not the
-// issue slots and shared-memory latency, is what bounds it.  ln det M = sum_b ln det P_b.
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ double acc_to_aop(double x0, double x1, int h, int lane) {
-  // accumulator layout (r, 2c / 2c+1) -> A operand of K half h: lane (r, c) needs X[r][4h + c]
-  const int c = lane & 3, src = (lane & ~3) | (2 * h + (c >> 1));
-  const double t0 = __shfl_sync(0xffffffffu, x0, src), t1 = __shfl_sync(0xffffffffu, x1, src);
-  return (c & 1) ? t1 : t0;
-}
-
-__device__ __forceinline__ void inv8_acc(double &x0, double &x1, double &det, int lane) {
-  const int r = lane >> 2, c = lane & 3;
-  det = 1.0;
-#pragma unroll
-  for (int p = 0; p < 8; ++p) {
-    const double xs = (p & 1) ? x1 : x0;
-    const double d = __shfl_sync(0xffffffffu, xs, 4 * p + (p >> 1));            // P[p][p]
-    const double f = __shfl_sync(0xffffffffu, xs, (lane & ~3) + (p >> 1));      // P[r][p]
-    const double row0 = __shfl_sync(0xffffffffu, x0, 4 * p + c);                // P[p][2c]
-    const double row1 = __shfl_sync(0xffffffffu, x1, 4 * p + c);                // P[p][2c+1]
-    const double inv = fast_rcp(d);
-    det *= d;
-    const double n0 = row0 * inv, n1 = row1 * inv, fi = -f * inv;
-    const bool isp = r == p, c0p = 2 * c == p, c1p = 2 * c + 1 == p;
-    x0 = isp ? (c0p ? inv : n0) : (c0p ? fi : fma(-f, n0, x0));
-    x1 = isp ? (c1p ? inv : n1) : (c1p ? fi : fma(-f, n1, x1));
-  }
-}
-
-template <int NT>
-struct BlkCfg {
-  static constexpr int KP = 8 * NT, TPS = 32 * NT, SPC = 256 / TPS, LDR = KP + 8;
-  __host__ __device__ static int per_slot(int kkp, bool colmax) {
-    return kkp + 2 * 8 * LDR + 2 * 64 + 2 * KP + 32 + (colmax ? kkp : 0);
-  }
-};
-
-template <int NT>
-__global__ void __launch_bounds__(256, (NT == 8 ? 3 : 4)) solve_blk_kernel(SolveArgs a) {
-  using Cfg = BlkCfg<NT>;
-  constexpr int KP = Cfg::KP, TPS = Cfg::TPS, SPC = Cfg::SPC, LDR = Cfg::LDR;
-  extern __shared__ __align__(16) double smem_reg[];
-  const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
-  const int slot = wi / NT, wb = wi % NT, ts = threadIdx.x % TPS;
-  const int r = lane >> 2, c = lane & 3;
-  const int k = a.s.k, kk = a.s.kk, kkp = a.s.kkp, kp = a.s.kp;
-  const int per_slot = Cfg::per_slot(kkp, a.colmax != nullptr);
-  double *stage = smem_reg + (size_t)slot * per_slot;  // packed G in, packed W out
-  double *rowbuf = stage + kkp;                        // [2][8][LDR] raw pivot row block
-  double *pinv = rowbuf + 2 * 8 * LDR;                 // [2][8][8]
-  double *yb = pinv + 128;                             // [KP]
-  double *zb = yb + KP;                                // [KP]
-  double *red = zb + KP;                               // [32]: quad[0..8) logdet[8..16) trace[16..24)
-  double *cmw = red + 32;                              // [kkp] running max |W| (optional)
-  const int bar_id = slot + 1;
-  auto sample_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(TPS) : "memory"); };
-  if (a.colmax)
-    for (int q = ts; q < kkp; q += TPS) cmw[q] = 0.0;
-  const double s2 = a.sigma * a.sigma;
-  const double ln_sigma = log(a.sigma);
-  const int gr = 8 * wb + r;  // this lane's matrix row
-
-  for (int row = blockIdx.x * SPC + slot; row < a.rows_pad; row += gridDim.x * SPC) {
-    double *gsrc = a.GW + (int64_t)row * kkp;
-    for (int q = ts * 2; q < kkp; q += 2 * TPS)
-      *reinterpret_cast<double2 *>(stage + q) = *reinterpret_cast<const double2 *>(gsrc + q);
-    if (ts < KP) yb[ts] = (ts < kp) ? a.YZ[(int64_t)row * kp + ts] : 0.0;
-    const int dn = row < a.rows ? a.dn[row] : 0;
-    const bool empty = dn == 0;
-    const double w = (a.w && row < a.rows) ? a.w[row] : (row < a.rows ? 1.0 : 0.0);
-    sample_sync();
-
-    // block row wb of M = sigma^2 I + G (identity where padded or empty)
-    double x[NT][2];
-#pragma unroll
-    for (int j = 0; j < NT; ++j)
-#pragma unroll
-      for (int s = 0; s < 2; ++s) {
-        const int gc = 8 * j + 2 * c + s;
-        const bool use = !empty && gr < k && gc < k;
-        const int lo = min(gr, gc), hi = max(gr, gc);
-        const double g = stage[use ? tri_idx(lo, hi, k) : 0];
-        const double unit = (gr == gc) ? 1.0 : 0.0;
-        x[j][s] = use ? fma(unit, s2, g) : unit;
-      }
-    if (a.gscale && !empty && c == 0 && gr < k) {  // precision guard (see SolveArgs)
-      const int qd = tri_row_off(gr, k);
-      if (guard_terms((double)dn) * a.guard_coef * a.gscale[qd] > s2 + stage[qd]) atomicAdd(a.unsafe, 1u);
-    }
-
-    double logdet = 0.0;
-#pragma unroll
-    for (int b = 0; b < NT; ++b) {
-      double *rb = rowbuf + (b & 1) * (8 * LDR);
-      double *pb = pinv + (b & 1) * 64;
-      if (wb == b) {
-#pragma unroll
-        for (int j = 0; j < NT; ++j)
-          *reinterpret_cast<double2 *>(rb + r * LDR + 8 * j + 2 * c) = make_double2(x[j][0], x[j][1]);
-        double det;
-        inv8_acc(x[b][0], x[b][1], det, lane);
-        logdet += log(det);
-        *reinterpret_cast<double2 *>(pb + r * 8 + 2 * c) = make_double2(x[b][0], x[b][1]);
-      }
-      sample_sync();
-      if (wb == b) {
-        const double a0 = acc_to_aop(x[b][0], x[b][1], 0, lane), a1 = acc_to_aop(x[b][0], x[b][1], 1, lane);
-#pragma unroll
-        for (int j = 0; j < NT; ++j) {
-          if (j == b) continue;
-          double c0 = 0.0, c1 = 0.0;
-          dmma884(c0, c1, a0, rb[c * LDR + 8 * j + r]);
-          dmma884(c0, c1, a1, rb[(4 + c) * LDR + 8 * j + r]);
-          x[j][0] = c0;
-          x[j][1] = c1;
-        }
-      } else {
-        double l0 = 0.0, l1 = 0.0;  // L = A_ib P^-1
-        dmma884(l0, l1, acc_to_aop(x[b][0], x[b][1], 0, lane), pb[c * 8 + r]);
-        dmma884(l0, l1, acc_to_aop(x[b][0], x[b][1], 1, lane), pb[(4 + c) * 8 + r]);
-        l0 = -l0;
-        l1 = -l1;
-        const double a0 = acc_to_aop(l0, l1, 0, lane), a1 = acc_to_aop(l0, l1, 1, lane);
-#pragma unroll
-        for (int j = 0; j < NT; ++j) {
-          if (j == b) continue;
-          dmma884(x[j][0], x[j][1], a0, rb[c * LDR + 8 * j + r]);
-          dmma884(x[j][0], x[j][1], a1, rb[(4 + c) * LDR + 8 * j + r]);
-        }
-        x[b][0] = l0;
-        x[b][1] = l1;
-      }
-    }
-    // x = block row wb of M^-1
-
-    // z = M^-1 y, quad = y^T z, trace term
-    double zp = 0.0;
-#pragma unroll
-    for (int j = 0; j < NT; ++j) {
-      const double2 yv = *reinterpret_cast<const double2 *>(yb + 8 * j + 2 * c);
-      zp = fma(x[j][0], yv.x, zp);
-      zp = fma(x[j][1], yv.y, zp);
-    }
-    zp += __shfl_xor_sync(0xffffffffu, zp, 1);
-    zp += __shfl_xor_sync(0xffffffffu, zp, 2);
-    const bool live = !empty && gr < k;
-    const double zi = live ? zp : 0.0;
-    if (c == 0) zb[gr] = zi;
-    const double quad = warp_sum(c == 0 ? yb[gr] * zi : 0.0);
-    double tr = 0.0;
-    if (a.mode == 2) {  // t = sigma^2 sum_i (1 - sigma^2 M^-1_ii)
-      double diag = 0.0;
-#pragma unroll
-      for (int j = 0; j < NT; ++j)
-        if (j == wb) diag = (r & 1) ? x[j][1] : x[j][0];
-      tr = warp_sum((live && c == (r >> 1)) ? fma(-s2, diag, 1.0) : 0.0);
-    }
-    if (lane == 0) {
-      red[wb] = quad;
-      red[8 + wb] = empty ? 0.0 : logdet;
-      red[16 + wb] = tr;
-    }
-    sample_sync();
-    if (ts == 0 && row < a.rows) {
-      double sq = 0.0, sl = 0.0, st = 0.0;
-#pragma unroll
-      for (int i = 0; i < NT; ++i) {
-        sq += red[i];
-        sl += red[8 + i];
-        st += red[16 + i];
-      }
-      if (a.llk) {
-        double llk = 0.0;
-        if (!empty)
-          llk = -0.5 * (a.nx[row] - sq) / s2 - 0.5 * (sl + 2.0 * ln_sigma * (double)(dn - k)) -
-                0.5 * LN_2PI * (double)dn;
-        a.llk[row] = llk;
-      }
-      if (a.mode == 2 && a.tn) a.tn[row] = empty ? 0.0 : s2 * st;
-    }
-    if (a.mode != 0) {
-      if (ts < kp) {
-        const double zv = zb[ts];
-        a.YZ[(int64_t)row * kp + ts] = zv;
-        if (a.WZ) a.WZ[(int64_t)row * kp + ts] = w * zv;
-      }
-      if (a.cov && row < a.rows && gr < k) {
-        double *cv = a.cov + (int64_t)row * k * k + (int64_t)gr * k;
-#pragma unroll
-        for (int j = 0; j < NT; ++j)
-#pragma unroll
-          for (int s = 0; s < 2; ++s) {
-            const int gc = 8 * j + 2 * c + s;
-            if (gc < k) cv[gc] = empty ? (gc == gr ? 1.0 : 0.0) : s2 * x[j][s];
-          }
-      }
-    }
-    if (a.mode == 2) {
-      // W = w (z z^T + sigma^2 M^-1), packed upper, in place of G (all reads of G happened before the elimination)
-      const double ws2 = empty ? 0.0 : w * s2, wzi = empty ? 0.0 : w * zi;
-      if (gr < k) {
-#pragma unroll
-        for (int j = 0; j < NT; ++j)
-#pragma unroll
-          for (int s = 0; s < 2; ++s) {
-            const int gc = 8 * j + 2 * c + s;
-            if (gc >= gr && gc < k) stage[tri_idx(gr, gc, k)] = fma(wzi, zb[gc], ws2 * x[j][s]);
-          }
-      }
-      for (int q = kk + ts; q < kkp; q += TPS) stage[q] = 0.0;
-      sample_sync();
-      for (int q = ts * 2; q < kkp; q += 2 * TPS) {
-        const double2 v = *reinterpret_cast<const double2 *>(stage + q);
-        *reinterpret_cast<double2 *>(gsrc + q) = v;
-        if (a.colmax) {
-          double2 m = *reinterpret_cast<const double2 *>(cmw + q);
-          m.x = fmax(m.x, fabs(v.x));
-          m.y = fmax(m.y, fabs(v.y));
-          *reinterpret_cast<double2 *>(cmw + q) = m;
-        }
-      }
-    }
-    sample_sync();
-  }
-  if (a.colmax) {
-    __syncthreads();
-    for (int q = threadIdx.x; q < kkp; q += blockDim.x) {
-      double m = 0.0;
-#pragma unroll
-      for (int sl = 0; sl < SPC; ++sl) m = fmax(m, smem_reg[(size_t)sl * per_slot + (cmw - stage) + q]);
-      if (m > 0.0) atomicMax(a.colmax + q, (unsigned long long)__double_as_longlong(m));
-    }
-  }
-}
-
-template <int NT>
-static void launch_solve_blk(const Launcher &L, const SolveArgs &a) {
-  using Cfg = BlkCfg<NT>;
-  const size_t smem = (size_t)Cfg::SPC * Cfg::per_slot(a.s.kkp, a.colmax != nullptr) * sizeof(double);
-  static PerDeviceOnce configured;
-  if (configured.need()) {
-    CUDA_CHECK(cudaFuncSetAttribute(solve_blk_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-  }
-  int64_t blocks = (a.rows_pad + Cfg::SPC - 1) / Cfg::SPC;
-  const int64_t cap = (int64_t)L.sms * (NT == 8 ? 3 : 4);
-  if (blocks > cap) blocks = cap;
-  solve_blk_kernel<NT><<<(unsigned)blocks, 256, smem, L.stream>>>(a);
-  CUDA_CHECK(cudaGetLastError());
-  ++*L.launch_counter;
-  L.count(V_SOLVE_BLK);
-}
-
 static void launch_solve_split64(const Launcher &L, const SolveArgs &a) {
   const size_t smem = (size_t)2 * (a.s.kkp + 2 * 136 + 64 + 128 + 16 + (a.colmax ? a.s.kkp : 0)) * sizeof(double);
   static PerDeviceOnce configured;
@@ -990,20 +591,6 @@ static void launch_solve_split64(const Launcher &L, const SolveArgs &a) {
   CUDA_CHECK(cudaGetLastError());
   ++*L.launch_counter;
   L.count(V_SOLVE_SPLIT64);
-}
-
-static void launch_solve_reg64(const Launcher &L, const SolveArgs &a) {
-  const size_t smem = (size_t)4 * (a.s.kkp + 5 * 64 + (a.colmax ? a.s.kkp : 0)) * sizeof(double);
-  static PerDeviceOnce configured;
-  if (configured.need()) {
-    CUDA_CHECK(cudaFuncSetAttribute(solve_reg64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-  }
-  int64_t blocks = (a.rows_pad + 3) / 4;
-  if (blocks > L.sms) blocks = L.sms;
-  solve_reg64_kernel<<<(unsigned)blocks, 256, smem, L.stream>>>(a);
-  CUDA_CHECK(cudaGetLastError());
-  ++*L.launch_counter;
-  L.count(V_SOLVE_PAIR64);
 }
 
 template <int KP, int MINB>
@@ -1042,31 +629,73 @@ static void launch_solve_reg(const Launcher &L, const SolveArgs &a) {
 
 // Per-sample scalars of one chunk -> SOLVE_SLOTS partial slots (block b always owns slot b and rows
 // [b R, (b+1) R) of the chunk, so the summation order is fixed run to run); launch_solve_finish sums the slots.
+// Per-sample scalars of one chunk -> SOLVE_SLOTS partial slots (block b always owns slot b and rows [b R, (b+1) R) of the
+// chunk, so the summation order is fixed run to run); launch_solve_finish sums the slots.
+// The residual norms dv come from the identity |R_n|^2 = nx - y^T z - sigma^2 |z|^2, which subtracts numbers of size nx:
+// its absolute error is ~2 eps nx.  Every block also sums w nx and w (t + dv); the LAST block to finish adds the block
+// totals in fixed order, raises *resid_flag when 2 eps sum(w nx) could move the noise update by more than 1e-11 (the chunk
+// then takes its residual norms from resid_exact_kernel, moments.cu), and only then folds the block totals into `part`,
+// with dv left out when flagged.
 __global__ void __launch_bounds__(256) solve_reduce_kernel(int rows, const double *__restrict__ llk,
-                                                           const double *__restrict__ tn, const int *__restrict__ dn,
-                                                           const double *__restrict__ w, double *part) {
-  __shared__ double sh[4][8];
+                                                           const double *__restrict__ tn, const double *__restrict__ dv,
+                                                           const double *__restrict__ nx, const int *__restrict__ dn,
+                                                           const double *__restrict__ w, double *part, double *scratch,
+                                                           int *resid_flag) {
+  __shared__ double sh[6][8];
+  __shared__ int last_flag[2];
   const int per = (rows + gridDim.x - 1) / gridDim.x;
   const int lo = blockIdx.x * per, hi = min(rows, lo + per);
-  double v[4] = {0.0, 0.0, 0.0, 0.0};
+  double v[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};  // w t, w llk, w, #non-empty, w dv, w nx
   for (int i = lo + threadIdx.x; i < hi; i += 256) {
     const double wi = w ? w[i] : 1.0;
     if (tn) v[0] = fma(wi, tn[i], v[0]);
     if (llk) v[1] = fma(wi, llk[i], v[1]);
     v[2] += wi;
     v[3] += dn[i] > 0 ? 1.0 : 0.0;
+    if (dv) {
+      v[4] = fma(wi, dv[i], v[4]);
+      v[5] = fma(wi, nx[i], v[5]);
+    }
   }
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
+  for (int j = 0; j < 6; ++j) {
     v[j] = warp_sum(v[j]);
     if (lane == 0) sh[j][wid] = v[j];
   }
   __syncthreads();
-  if (threadIdx.x < 4) {
+  if (threadIdx.x < 6) {
     double s = 0.0;
     for (int i = 0; i < 8; ++i) s += sh[threadIdx.x][i];
-    part[blockIdx.x * 4 + threadIdx.x] += s;
+    scratch[blockIdx.x * 6 + threadIdx.x] = s;
+  }
+  __threadfence();
+  __syncthreads();
+  unsigned int *counter = reinterpret_cast<unsigned int *>(scratch + (size_t)gridDim.x * 6);
+  if (threadIdx.x == 0) last_flag[0] = atomicAdd(counter, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!last_flag[0]) return;
+  __threadfence();
+  if (threadIdx.x < 32) {
+    double e = 0.0, s = 0.0;
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += 32) {
+      e += scratch[b * 6 + 5];
+      s += scratch[b * 6 + 0] + scratch[b * 6 + 4];
+    }
+    e = warp_sum(e);
+    s = warp_sum(s);
+    if (threadIdx.x == 0) {
+      const int flag = (dv != nullptr && 4.5e-16 * e > 1e-11 * s) ? 1 : 0;
+      last_flag[1] = flag;
+      if (resid_flag) *resid_flag = flag;
+      *counter = 0u;  // ready for the next launch
+    }
+  }
+  __syncthreads();
+  const bool use_dv = dv != nullptr && !last_flag[1];
+  for (int idx = threadIdx.x; idx < (int)gridDim.x * 4; idx += 256) {
+    const int b = idx >> 2, j = idx & 3;
+    part[idx] += scratch[b * 6 + j] + ((j == 0 && use_dv) ? scratch[b * 6 + 4] : 0.0);
   }
 }
 
@@ -1080,10 +709,10 @@ __global__ void solve_finish_kernel(const double *__restrict__ part, double *sca
   }
 }
 
-void launch_solve_reduce(const Launcher &L, int rows, const double *llk, const double *tn, const int *dn, const double *w,
-                         double *part) {
+void launch_solve_reduce(const Launcher &L, int rows, const double *llk, const double *tn, const double *dv,
+                         const double *nx, const int *dn, const double *w, double *part, double *scratch, int *resid_flag) {
   if (rows <= 0) return;
-  solve_reduce_kernel<<<SOLVE_SLOTS, 256, 0, L.stream>>>(rows, llk, tn, dn, w, part);
+  solve_reduce_kernel<<<SOLVE_SLOTS, 256, 0, L.stream>>>(rows, llk, tn, dv, nx, dn, w, part, scratch, resid_flag);
   CUDA_CHECK(cudaGetLastError());
   ++*L.launch_counter;
 }
@@ -1120,32 +749,18 @@ static void launch_solve_generic(const Launcher &L, const SolveArgs &a) {
 void launch_solve(const Launcher &L, const SolveArgs &a) {
   if (a.rows_pad <= 0) return;
   REQUIRE(a.mode == 0 || a.GW != nullptr, "solve: missing Gram buffer");
-  // PPCA_B200_SOLVE: unset / "scalar" (default) = the register-resident scalar kernels; "blk" = the DMMA-blocked
-  // kernel for 16 < k <= 64, "blk16" = also for 8 < k <= 16.  Measured on B200 (profiles/r01_solve_blk_ncu.txt): the
-  // blocked kernel issues 3x fewer instructions but only 3 samples fit an SM and 7 of a sample's 8 warps wait at the
-  // barrier while the 8 x 8 pivot block is inverted (a chain of 8 dependent reciprocals), so it ties at k = 64
-  // (28.1 vs 27.7 ms per 0.5 M samples) and loses at k = 32 (16.8 vs 9.9 ms) and k = 16 (3.3 vs 1.6 ms).
-  static const int blk_mode = [] {
-    const char *e = getenv("PPCA_B200_SOLVE");
-    if (!e) return 0;
-    return strcmp(e, "blk") == 0 ? 1 : (strcmp(e, "blk16") == 0 ? 2 : 0);
-  }();
-  if (blk_mode >= 1 && a.s.k > 32 && a.s.k <= 64) launch_solve_blk<8>(L, a);
-  else if (blk_mode >= 1 && a.s.k > 16 && a.s.k <= 32) launch_solve_blk<4>(L, a);
-  else if (blk_mode == 2 && a.s.k > 8 && a.s.k <= 16) launch_solve_blk<2>(L, a);
-  else if (a.s.k <= 8) launch_solve_reg<8>(L, a);
+  // Round 1 also carried a DMMA-blocked 8 x 8 Gauss-Jordan kernel and a 64-lane variant; both were removed in round 2:
+  // the blocked elimination is not symmetric-consistent (tools/solve_accuracy.py: four digits worse on ill-conditioned
+  // M_n) and never beat the scalar kernels (profiles/r01_solve_blk_ncu.txt).
+  if (a.s.k <= 8) launch_solve_reg<8>(L, a);
   else if (a.s.k <= 16) launch_solve_reg<16>(L, a);
   else if (a.s.k <= 32) launch_solve_reg<32>(L, a);
-  else if (a.s.k <= 64) {
-    static const bool use_pair = getenv("PPCA_B200_SOLVE64") && atoi(getenv("PPCA_B200_SOLVE64")) == 1;
-    if (use_pair) launch_solve_reg64(L, a);
-    else launch_solve_split64(L, a);
-  }
+  else if (a.s.k <= 64) launch_solve_split64(L, a);
   else {
     REQUIRE(a.colmax == nullptr, "solve: the generic kernel (state_size > 64) does not produce column maxima");
     launch_solve_generic(L, a);
   }
-  if (a.part) launch_solve_reduce(L, a.rows, a.llk, a.tn, a.dn, a.w, a.part);
+  if (a.part) launch_solve_reduce(L, a.rows, a.llk, a.tn, nullptr, nullptr, a.dn, a.w, a.part, a.rscratch, nullptr);
 }
 
 }  // namespace ppca

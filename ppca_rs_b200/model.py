@@ -469,6 +469,24 @@ class PPCAModel:
                      self._sigma, C.byref(h)))
         return Dataset._wrap(h, dataset._ctx)
 
+    def reconstruct(self, dataset: Dataset, extrapolate: bool = True, out: Optional[Dataset] = None,
+                    with_llks: bool = False):
+        """smooth / extrapolate and (with_llks) the per-sample log-likelihoods from ONE E-step (ppca_b200_reconstruct).
+        `out` = a dataset an earlier smooth / extrapolate / reconstruct call returned for an input of the same shape: it
+        is overwritten in place and returned (no allocation).  Returns the dataset, or (dataset, llks).  Extension of the
+        reference API (it calls extrapolate and llks separately, ppca_model.rs:152-159,254-261)."""
+        self._check(dataset)
+        if isinstance(dataset, HostDataset):
+            res, llks = self._host_pass(dataset, extrapolate, with_llks)
+            return (res, llks) if with_llks else res
+        llks = np.empty(len(dataset)) if with_llks else None
+        h = nat.c_ds_p()
+        nat.check(nat.lib().ppca_b200_reconstruct(dataset._ctx.handle, dataset._h, self.state_size, nat.dptr(self._C),
+                                                  nat.dptr(self._mu), self._sigma, int(bool(extrapolate)),
+                                                  out._h if out is not None else None, nat.dptr(llks), C.byref(h)))
+        res = out if out is not None else Dataset._wrap(h, dataset._ctx)
+        return (res, llks) if with_llks else res
+
     def smooth(self, dataset: Dataset) -> Dataset:
         return self._recon(dataset, nat.lib().ppca_b200_smooth)
 

@@ -969,3 +969,27 @@ def test_sharded_entry_points_two_gpus(pk, orc):
     assert np.max(np.abs(x0.log_weights - want_logw)) < 1e-9
     for got, (Cw, muw, sw) in zip(x0.models, want_models):
         assert rel_err(got.transform, Cw) < TOL and rel_err(got.mean, muw) < TOL and abs(got.isotropic_noise - sw) < TOL * sw
+
+
+def test_reconstruct_one_pass_and_in_place_reuse(pk, orc):
+    """extrapolate / smooth + llks from one E-step (ppca_b200_reconstruct), output dataset overwritten in place."""
+    X, C0, mu0, s0 = _case(3000, 70, 10, 0.25, seed=13, empty_rows=(7,))
+    w = np.random.default_rng(4).random(3000) + 0.5
+    ds = pk.Dataset(X, w)
+    model = pk.PPCAModel(0.7, C0, mu0)
+    ex, ll = model.reconstruct(ds, True, with_llks=True)
+    assert np.array_equal(ex.numpy(), model.extrapolate(ds).numpy())
+    assert np.array_equal(ll, model.llks(ds)) and np.array_equal(ex.weights(), w)
+    assert rel_err(ll, orc.llks(X, C0, mu0, 0.7)) < TOL
+    # reuse: another model, another input of the same shape, same output handle
+    X2 = make_data(3000, 70, 10, 0.4, seed=99)
+    ds2 = pk.Dataset(X2)
+    model2 = pk.PPCAModel(0.3, 0.5 * C0, mu0 + 0.1)
+    again, ll2 = model2.reconstruct(ds2, False, out=ex, with_llks=True)
+    assert again is ex
+    assert np.array_equal(ex.numpy(), model2.smooth(ds2).numpy()) and np.array_equal(ll2, model2.llks(ds2))
+    assert np.array_equal(ex.weights(), np.ones(3000))
+    with pytest.raises(Exception):
+        model.reconstruct(ds, True, out=ds2)            # not an output dataset
+    with pytest.raises(Exception):
+        model.reconstruct(ds._slice(0, 100), True, out=ex)   # another shape
