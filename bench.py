@@ -171,9 +171,9 @@ def int8_tc_peak():
 
 def measured_traffic(workload, kernel):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed ncu --set full capture
-    of one chunk of this workload (profiles/r01_traffic.json); None when that workload was not captured."""
+    of one chunk of this workload (profiles/r02_traffic.json); None when that workload was not captured."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
             t = json.load(f)
         wl = {"c3": "c3s"}.get(workload, workload)
         for name, v in t[wl]["kernels"].items():
@@ -625,7 +625,7 @@ def run_ours(args, wl, rank, world, local_rank):
     common = {
         "bound": "tensor", "traffic": measured_traffic(args.workload, "tbitgemm_atm_kernel") if args.gemm == "tc" else None,
         "traffic_note": "dram__bytes_read + dram__bytes_write per launch (E- and M-step launches averaged) from the committed "
-                        "ncu --set full capture (profiles/r01_traffic.json)",
+                        "ncu --set full capture (profiles/r02_traffic.json)",
         "algorithmic_bytes_per_launch": alg_bytes_launch,
         "share_of_step": bit_ms / ms_total if ms_total else None,
         "avg_launch_ms": bit_ms / launches_bit if launches_bit else None,

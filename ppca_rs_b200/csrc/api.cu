@@ -61,6 +61,7 @@ struct ppca_b200_ctx {
   DevBuf<double> mixArena;                                 // single-pass mixture EM: per-component chunk buffers
   DevBuf<int8_t> mixArenaQ;                                //   ... and their digit planes
   DevBuf<int> flags;
+  DevBuf<double> priorP, priorV;  // mean prior: total precision (d x d) and [m0 | mu_hat | rhs]
   // sample-sharded EM: NCCL communicator of this rank (ppca_b200_comm_init), null = single process
   void *comm = nullptr;
   int comm_rank = 0, comm_world = 1;
@@ -789,19 +790,50 @@ double em_finish_impl(ppca_b200_ctx *ctx, int d, int k, const double *C, const d
   for (int i = 0; i < d; ++i) mu_out[i] = (totals[i] > 0.0 ? tdev[i] / totals[i] : 0.0) + mu[i];  // :373-377
   if (prior && prior->has_mean_prior) {  // :379-384 ; prior.rs:97-110
     REQUIRE(prior->mean && prior->mean_precision, "mean prior needs mean and mean_precision");
-    std::vector<double> P((size_t)d * d), num(d);
-    for (int i = 0; i < d; ++i) {
-      double acc = 0.0;
-      for (int j = 0; j < d; ++j) {
-        const double pm = prior->mean_precision[(size_t)i * d + j];
-        P[(size_t)i * d + j] = pm + (i == j ? totals[i] / noise_sq : 0.0);
-        acc += pm * prior->mean[j];
+    // device path: blocked Cholesky of the (SPD) total precision; see finish.cu
+    bool solved = false;
+    {
+      ctx->priorP.reserve((size_t)d * d);
+      ctx->priorV.reserve((size_t)3 * d);
+      ctx->flags.reserve((size_t)d + 1);
+      double *m0_dev = ctx->priorV.p, *muhat_dev = ctx->priorV.p + d, *rhs_dev = ctx->priorV.p + 2 * (size_t)d;
+      CUDA_CHECK(cudaMemcpyAsync(ctx->priorP.p, prior->mean_precision, sizeof(double) * (size_t)d * d,
+                                 cudaMemcpyHostToDevice, ctx->stream));
+      CUDA_CHECK(cudaMemcpyAsync(m0_dev, prior->mean, sizeof(double) * d, cudaMemcpyHostToDevice, ctx->stream));
+      CUDA_CHECK(cudaMemcpyAsync(muhat_dev, mu_out, sizeof(double) * d, cudaMemcpyHostToDevice, ctx->stream));
+      ctx->span_begin(FAM_FINISH);
+      launch_mean_prior_solve(ctx->L(), ctx->priorP.p, d, m0_dev, stats_dev + lay.offTotals, muhat_dev, noise_sq, rhs_dev,
+                              ctx->flags.p + d);
+      ctx->span_end();
+      std::vector<double> sol((size_t)d);
+      int fail = 0;
+      CUDA_CHECK(cudaMemcpyAsync(sol.data(), rhs_dev, sizeof(double) * d, cudaMemcpyDeviceToHost, ctx->stream));
+      CUDA_CHECK(cudaMemcpyAsync(&fail, ctx->flags.p + d, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+      CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+      if (!fail) {
+        bool finite = true;
+        for (int i = 0; i < d; ++i) finite = finite && std::isfinite(sol[i]);
+        if (finite) {
+          for (int i = 0; i < d; ++i) mu_out[i] = sol[i];
+          solved = true;
+        }
       }
-      num[i] = acc + (totals[i] / noise_sq) * mu_out[i];
     }
-    if (!host_qr_solve(P, d, num))
-      PPCA_THROW(PPCA_ERR_NUMERIC, "total precision matrix is always invertible (prior.rs:109)");
-    for (int i = 0; i < d; ++i) mu_out[i] = num[i];
+    if (!solved) {  // precision matrix not positive definite: the reference's QR route, on the host
+      std::vector<double> P((size_t)d * d), num(d);
+      for (int i = 0; i < d; ++i) {
+        double acc = 0.0;
+        for (int j = 0; j < d; ++j) {
+          const double pm = prior->mean_precision[(size_t)i * d + j];
+          P[(size_t)i * d + j] = pm + (i == j ? totals[i] / noise_sq : 0.0);
+          acc += pm * prior->mean[j];
+        }
+        num[i] = acc + (totals[i] / noise_sq) * mu_out[i];
+      }
+      if (!host_qr_solve(P, d, num))
+        PPCA_THROW(PPCA_ERR_NUMERIC, "total precision matrix is always invertible (prior.rs:109)");
+      for (int i = 0; i < d; ++i) mu_out[i] = num[i];
+    }
   }
   *sigma_out = std::sqrt(noise_sq);  // :389
   if (llk_in) *llk_in = sc[SC_LLK];

@@ -335,6 +335,11 @@ void launch_mstep_guard(const Launcher &L, int d, int k, const double *statA, co
 // smax[q] = max(smax[q], scale[q])
 void launch_scale_max(const Launcher &L, const double *scale, int n, double *smax);
 
+// finish.cu : mean prior (prior.rs:97-110).  P_dev (n x n, prior precision on entry) is overwritten by the Cholesky factor of
+// P + diag(totals / noise_sq); rhs_dev receives the solution.  *fail_dev != 0: not positive definite (caller falls back).
+void launch_mean_prior_solve(const Launcher &L, double *P_dev, int n, const double *m0_dev, const double *totals_dev,
+                             const double *mu_hat_dev, double noise_sq, double *rhs_dev, int *fail_dev);
+
 // finish.cu : per-dimension solves (A_i + tau I) c = B_i
 void launch_row_solve(const Launcher &L, int d, int k, const double *statA, const double *statB, double tau,
                       const double *Cold_pad, double *Cnew /* d x k dense */, int *flags);

@@ -10,6 +10,8 @@
 //
 // reconstruct_kernel: smoothed = C z + mu (ppca_model.rs:454-456); extrapolated = mask.choose(x, smoothed)
 // (:460-463, utils.rs:137-153) — observed slots are copied, never recomputed.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "mma.cuh"
 
@@ -53,8 +55,12 @@ struct CrArgs {
 // with x~ = m ? x - mu : 0 (OLD mu; select, never multiply).  The residual R = m (x~ - C z) of the reference is never
 // formed: sum_n w R_ni = Sx_i - c_i . (Mask^T (w Z))_i, whose second term rides on the M-step contraction, and |R_n|^2 is a
 // per-sample scalar of the solve kernel (see SolveArgs::tn).  Round 1 ran a second DMMA GEMM (Z C^T) in this kernel for them.
+// resident CTAs per SM: the kernel is a stream over X with two tiles in flight per CTA, so small states (few accumulator
+// registers, small tiles) run more CTAs to keep more loads in flight
+__host__ __device__ constexpr int cr_minb(int kt) { return kt <= 2 ? 4 : (kt <= 4 ? 3 : (kt <= 8 ? 2 : 1)); }
+
 template <int KT, int BS>
-__global__ void __launch_bounds__(256, 2) cross_moment_kernel(CrArgs a) {
+__global__ void __launch_bounds__(256, cr_minb(KT)) cross_moment_kernel(CrArgs a) {
   using Cfg = CrCfg<KT, BS>;
   constexpr int LDX = Cfg::LDX, LDZ = Cfg::LDZ, KPP = Cfg::KPP;
   extern __shared__ __align__(16) double smem[];
@@ -222,7 +228,10 @@ __global__ void cross_moment_reduce_kernel(int slabs, int d64, int d, int kp, co
 }
 
 static int cr_bs(int kp) { (void)kp; return 32; }
-static int cr_ctas_per_sm(int kp) { (void)kp; return 2; }
+static int cr_ctas_per_sm(int kp) {
+  static const int force = getenv("PPCA_B200_CROSS_MINB") ? atoi(getenv("PPCA_B200_CROSS_MINB")) : 0;
+  return force > 0 ? force : cr_minb(kp / 8);
+}
 
 int cross_resid_slabs(int d, int k, int rows, int sms) {
   Shape s(d, k);

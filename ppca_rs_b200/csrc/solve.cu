@@ -400,8 +400,12 @@ __global__ void __launch_bounds__(256, MINB) solve_reg_kernel(SolveArgs a) {
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void quad_sync(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 
-__global__ void __launch_bounds__(256, 2) solve_split64_kernel(SolveArgs a) {
-  constexpr int KP = 64, CW = 32;
+// KPIV = state_size rounded up to 8: rows / columns past it are identity padding whose pivots change nothing, so the
+// elimination stops there (k = 48: 48 of 64 pivots)
+template <int KPIV, int MINB>
+__global__ void __launch_bounds__(256, MINB) solve_split64_kernel(SolveArgs a) {
+  constexpr int KP = KPIV, CW = KPIV / 2;  // columns per thread: two halves of KPIV / 2 (k = 48: 24, not 32)
+  static_assert(CW % 2 == 0 && 2 * CW >= KPIV && CW <= 32, "column halves must be even and cover the state");
   extern __shared__ __align__(16) double smem_reg[];
   const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
   const int smp = wi >> 2;                       // sample slot in the CTA (0, 1)
@@ -464,12 +468,12 @@ __global__ void __launch_bounds__(256, 2) solve_split64_kernel(SolveArgs a) {
       double *cb = col + (p & 1) * 136;  // [0,64) s in true units, [64,128) s in the row's own units, [128] next diagonal
       const double dthis = dcur;
       const double rinv = fast_rsqrt(dthis);
-      if (h == (p >> 5)) {
-        const double own = A[p & 31] * rinv;
+      if (h == (p / CW)) {
+        const double own = A[p % CW] * rinv;
         cb[li] = own * sc;
         cb[64 + li] = own;
       }
-      if (p + 1 < KP && li == p + 1 && h == ((p + 1) >> 5)) cb[128] = A[(p + 1) & 31];
+      if (p + 1 < KP && li == p + 1 && h == ((p + 1) / CW)) cb[128] = A[(p + 1) % CW];
       quad_sync(bar_id);
       const bool isp = li == p;
       const double own = cb[64 + li];
@@ -485,7 +489,7 @@ __global__ void __launch_bounds__(256, 2) solve_split64_kernel(SolveArgs a) {
         A[jj] = fma(-f, cv.x, A[jj]);
         A[jj + 1] = fma(-f, cv.y, A[jj + 1]);
       }
-      if (h == (p >> 5)) A[p & 31] = isp ? -1.0 : own * rinv;
+      if (h == (p / CW)) A[p % CW] = isp ? -1.0 : own * rinv;
       if (isp) {
         mypiv = dthis;
         sc = rinv * rinv;
@@ -513,7 +517,7 @@ __global__ void __launch_bounds__(256, 2) solve_split64_kernel(SolveArgs a) {
 #pragma unroll
       for (int jj = 0; jj < CW; ++jj)
         if (c0 + jj == li) diag = A[jj];
-      tpart = warp_sum((live && h == (li >> 5)) ? fma(-s2, diag, 1.0) : 0.0);
+      tpart = warp_sum((live && h == (li / CW)) ? fma(-s2, diag, 1.0) : 0.0);
       const double zz = warp_sum(h == 0 ? zi * zi : 0.0);
       if (lane == 0) {
         red[8 + ws] = tpart;
@@ -579,18 +583,29 @@ __global__ void __launch_bounds__(256, 2) solve_split64_kernel(SolveArgs a) {
   }
 }
 
-static void launch_solve_split64(const Launcher &L, const SolveArgs &a) {
+template <int KPIV, int MINB>
+static void launch_solve_split64_b(const Launcher &L, const SolveArgs &a) {
   const size_t smem = (size_t)2 * (a.s.kkp + 2 * 136 + 64 + 128 + 16 + (a.colmax ? a.s.kkp : 0)) * sizeof(double);
   static PerDeviceOnce configured;
   if (configured.need()) {
-    CUDA_CHECK(cudaFuncSetAttribute(solve_split64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CUDA_CHECK(cudaFuncSetAttribute(solve_split64_kernel<KPIV, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
   }
   int64_t blocks = (a.rows_pad + 1) / 2;
-  if (blocks > 2 * (int64_t)L.sms) blocks = 2 * (int64_t)L.sms;
-  solve_split64_kernel<<<(unsigned)blocks, 256, smem, L.stream>>>(a);
+  if (blocks > MINB * (int64_t)L.sms) blocks = MINB * (int64_t)L.sms;
+  solve_split64_kernel<KPIV, MINB><<<(unsigned)blocks, 256, smem, L.stream>>>(a);
   CUDA_CHECK(cudaGetLastError());
   ++*L.launch_counter;
   L.count(V_SOLVE_SPLIT64);
+}
+
+// resident CTAs per SM: 2 (128 registers) by default; narrower states leave room for 3 (PPCA_B200_SOLVE64_MINB=3)
+template <int KPIV>
+static void launch_solve_split64(const Launcher &L, const SolveArgs &a) {
+  static const int minb = getenv("PPCA_B200_SOLVE64_MINB") ? atoi(getenv("PPCA_B200_SOLVE64_MINB")) : 2;
+  if constexpr (KPIV <= 48) {
+    if (minb == 3) return launch_solve_split64_b<KPIV, 3>(L, a);
+  }
+  launch_solve_split64_b<KPIV, 2>(L, a);
 }
 
 template <int KP, int MINB>
@@ -755,7 +770,10 @@ void launch_solve(const Launcher &L, const SolveArgs &a) {
   if (a.s.k <= 8) launch_solve_reg<8>(L, a);
   else if (a.s.k <= 16) launch_solve_reg<16>(L, a);
   else if (a.s.k <= 32) launch_solve_reg<32>(L, a);
-  else if (a.s.k <= 64) launch_solve_split64(L, a);
+  else if (a.s.k <= 40) launch_solve_split64<40>(L, a);
+  else if (a.s.k <= 48) launch_solve_split64<48>(L, a);
+  else if (a.s.k <= 56) launch_solve_split64<56>(L, a);
+  else if (a.s.k <= 64) launch_solve_split64<64>(L, a);
   else {
     REQUIRE(a.colmax == nullptr, "solve: the generic kernel (state_size > 64) does not produce column maxima");
     launch_solve_generic(L, a);

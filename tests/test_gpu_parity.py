@@ -993,3 +993,24 @@ def test_reconstruct_one_pass_and_in_place_reuse(pk, orc):
         model.reconstruct(ds, True, out=ds2)            # not an output dataset
     with pytest.raises(Exception):
         model.reconstruct(ds._slice(0, 100), True, out=ex)   # another shape
+
+
+def test_mean_prior_device_cholesky_matches_the_reference_qr(pk, orc):
+    """prior.rs:97-110 at a size where the blocked device Cholesky runs several panels (d = 150: 5 panels of 32)."""
+    n, d, k = 2500, 150, 6
+    X, C0, mu0, s0 = _case(n, d, k, 0.25, seed=31, empty_dims=(d - 1,))
+    ds = pk.Dataset(X)
+    rng = np.random.default_rng(7)
+    A = rng.standard_normal((d, d))
+    cov = A @ A.T / d + 0.5 * np.eye(d)
+    m0 = rng.standard_normal(d)
+    prior = pk.Prior().with_mean_prior(m0, cov).with_isotropic_noise_prior(2.0, 1.5).with_transformation_precision(0.1)
+    oprior = orc.Prior(mean=m0, mean_covariance=cov, isotropic_noise_alpha=2.0, isotropic_noise_beta=1.5,
+                       transformation_precision=0.1)
+    C, mu, s = C0, mu0, s0
+    for it in range(3):
+        new = pk.PPCAModel(s, C, mu).iterate_with_prior(ds, prior)
+        (C, mu, s), (Cs, mus, ss) = both(orc, orc.iterate, X, None, C, mu, s, oprior)
+        assert_close(new.transform, C, Cs, "C")
+        assert_close(new.mean, mu, mus, "mu")
+        assert_close(new.isotropic_noise, s, ss, "sigma")

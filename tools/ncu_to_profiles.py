@@ -1,8 +1,8 @@
 #!/usr/bin/env python
-"""Turns `ncu --page raw --csv` exports of one EM step (gpurun_out/<dir>/<wl>_full_raw.csv) into the committed
-profiles/r01_<wl>_step_ncu_full_summary.txt and profiles/r01_traffic.json.
+"""Turns `ncu --page raw --csv` exports of one EM step (gpurun_out/<dir>/<wl>_step_raw.csv) into the committed
+profiles/<round>_<wl>_step_ncu_full_summary.txt and profiles/<round>_traffic.json.
 
-    python tools/ncu_to_profiles.py gpurun_out/s18 c2:1000000 c3s:250112
+    python tools/ncu_to_profiles.py gpurun_out/r02g r02 c2:1000000 c3s:500000
 (the number after the colon is the rows per launch = the chunk size of that capture)."""
 import csv
 import json
@@ -36,11 +36,14 @@ def num(v, unit):
         return float("nan")
 
 
-def main(directory, specs):
+def main(directory, rnd, specs):
     traffic = {}
     for spec in specs:
         wl, rows_per_launch = spec.split(":")
-        rows = list(csv.reader(open(os.path.join(directory, f"{wl}_full_raw.csv"))))
+        path = os.path.join(directory, f"{wl}_step_raw.csv")
+        if not os.path.exists(path):
+            path = os.path.join(directory, f"{wl}_full_raw.csv")
+        rows = list(csv.reader(open(path)))
         hi = [i for i, r in enumerate(rows) if "Kernel Name" in r][0]
         hdr, units = rows[hi], rows[hi + 1]
         idx = {h: i for i, h in enumerate(hdr)}
@@ -64,21 +67,21 @@ def main(directory, specs):
             fam.setdefault(short, []).append((num(r[idx["dram__bytes_read.sum"]], units[idx["dram__bytes_read.sum"]]) * 1e6,
                                               num(r[idx["dram__bytes_write.sum"]], units[idx["dram__bytes_write.sum"]]) * 1e6,
                                               num(r[idx["gpu__time_duration.sum"]], units[idx["gpu__time_duration.sum"]])))
-        with open(os.path.join(ROOT, "profiles", f"r01_{wl}_step_ncu_full_summary.txt"), "w") as f:
+        with open(os.path.join(ROOT, "profiles", f"{rnd}_{wl}_step_ncu_full_summary.txt"), "w") as f:
             f.write(f"# ncu --set full --clock-control none, consecutive launches of one EM step of bench.py --workload {wl} "
                     f"({rows_per_launch} rows per launch)\n" + "\n".join(lines) + "\n")
         traffic[wl] = {"rows_per_launch": int(rows_per_launch),
                        "source": f"ncu --set full --clock-control none on bench.py --workload {wl}; summary in "
-                                 f"profiles/r01_{wl}_step_ncu_full_summary.txt",
+                                 f"profiles/{rnd}_{wl}_step_ncu_full_summary.txt",
                        "kernels": {n: {"launches": len(v), "dram_bytes_per_launch": sum(a + b for a, b, _ in v) / len(v),
                                        "dram_read_per_launch": sum(a for a, _, _ in v) / len(v),
                                        "dram_write_per_launch": sum(b for _, b, _ in v) / len(v),
                                        "time_us_under_ncu": sum(t for _, _, t in v) / len(v)} for n, v in fam.items()}}
         for n, v in traffic[wl]["kernels"].items():
             print(wl, n[:48], v["launches"], f"{v['dram_bytes_per_launch'] / 1e6:.1f} MB", f"{v['time_us_under_ncu']:.1f} us")
-    with open(os.path.join(ROOT, "profiles", "r01_traffic.json"), "w") as f:
+    with open(os.path.join(ROOT, "profiles", f"{rnd}_traffic.json"), "w") as f:
         json.dump(traffic, f, indent=1)
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], sys.argv[2:])
+    main(sys.argv[1], sys.argv[2], sys.argv[3:])
