@@ -380,11 +380,11 @@ def family_rooflines(fam, ms_total, steps, n, d, k, m, slices, gemm, peak64, pea
         "proj": 8 * d + d / 8 + 8 * kp,                                   # read x + mask, write y
         "solve": 8 * (2 * kkp + 3 * kp + 4),                              # read G, y; write W, z, w z, scalars
         "slice": (8 + slices) * kkp if gemm != "dmma" else 0,             # read W once, write T digit planes
-        "cross_resid": 8 * d + d / 8 + 16 * kp,                           # read x + mask, z, w z
+        "cross_resid": 8 * d + d / 8 + 8 * kp,                            # read x + mask, w z
     }
     # FP64 flops per sample of the families that run on the FP64 pipes (DMMA for proj / cross_resid, DFMA for the solve):
     # with 37 TFLOP/s of FP64 against 6.5 TB/s of HBM the ridge is ~5.7 flop/B, so at k >= 16 the X passes are FP64-bound
-    fam_flops = {"proj": 2 * d * k, "cross_resid": 4 * d * k, "solve": 2 * k ** 3}
+    fam_flops = {"proj": 2 * d * k, "cross_resid": 2 * d * k, "solve": 2 * k ** 3}
     families = {}
     for name, ms in fam.items():
         entry = {"ms_per_step": ms / steps, "share_of_step": ms / ms_total if ms_total else None}
@@ -398,7 +398,7 @@ def family_rooflines(fam, ms_total, steps, n, d, k, m, slices, gemm, peak64, pea
                 entry.update(bound="hbm", achieved=gbs, peak=hbm_peak, unit="GB/s", frac=gbs / hbm_peak,
                              peak_source=hbm_src, fp64_tflops=tfl, fp64_frac=tfl / peak64)
         elif name in ("gram", "moment") and ms > 0:
-            ops = comps * 2 * d * kk * n * steps * (slices if gemm != "dmma" else 1)
+            ops = comps * (2 * d * kk + (2 * d * k if name == "moment" else 0)) * n * steps * (slices if gemm != "dmma" else 1)
             ach = ops / (ms * 1e-3) / 1e12
             entry.update(bound="tensor", achieved=ach, peak=tensor_peak, unit=tensor_unit, frac=ach / tensor_peak)
         families[name] = entry
@@ -458,11 +458,11 @@ def shard_block(torch, pk, pdist, ctx, stream, dist, rank, world, local_rank, ar
         block["families"] = fams
         bit_ms = fam.get("gram", 0.0) + fam.get("moment", 0.0)
         if bit_ms > 0:
-            contractions = 2 * max(1, m)
-            ops = contractions * 2 * d * kk * rows * steps * (args.slices if args.gemm != "dmma" else 1)
+            fl = max(1, m) * (2 * (2 * d * kk) + 2 * d * k) * rows * steps   # Mask Ksym, Mask^T W, Mask^T (w Z)
+            ops = fl * (args.slices if args.gemm != "dmma" else 1)
             ach = ops / (bit_ms * 1e-3) / 1e12
             block["contraction"] = {"achieved": ach, "peak": tpeak, "unit": tunit, "frac": ach / tpeak,
-                                    "fp64_equivalent_tflops": contractions * 2 * d * kk * rows * steps / (bit_ms * 1e-3) / 1e12,
+                                    "fp64_equivalent_tflops": fl / (bit_ms * 1e-3) / 1e12,
                                     "fp64_dmma_peak_tflops": peak64, "share_of_step": bit_ms / ms_total}
     del state, ds
     torch.cuda.empty_cache()
@@ -546,13 +546,20 @@ def run_ours(args, wl, rank, world, local_rank):
     e2e_steps = max(1, min(args.steps, 10))
     if m == 1:
         C0, mu0, s0 = init_params(d, k, SEED + 1000)
-        host = pk.HostDataset(Xh, pin=True, ctx=ctx)
+        # compact host format (ppca_b200_pack_host, built once like the reference's own numpy -> Rust copy): only the
+        # observed values, the row offsets and the mask words cross the bus each step
+        host = pk.HostDataset(Xh, pin=True, ctx=ctx, packed=not args.e2e_plain)
         st8 = pdist.ShardedPPCA(ctx, host, pk.PPCAModel(s0, C0, mu0), group=dist)
-        h2d = n_e2e * d * 8 + (d * k + d) * 8
+        if host._packed is not None:
+            vals, rowptr, maskw = host._packed
+            h2d = int(rowptr[-1]) * 8 + rowptr.nbytes + maskw.nbytes + (d * k + d) * 8
+        else:
+            h2d = n_e2e * d * 8 + (d * k + d) * 8
         d2h = (d * k + 2 * d + 8) * 8
         step_fn = st8.step
-        call = ("PPCAModel.iterate(HostDataset) -> ppca_b200_iterate_host" if world == 1 else
-                "ShardedPPCA.step over HostDataset shards -> ppca_b200_em_stats_host + NCCL all-reduce + ppca_b200_em_finish")
+        fn = "ppca_b200_iterate_host" if args.e2e_plain else "ppca_b200_iterate_packed_host"
+        call = (f"PPCAModel.iterate(HostDataset) -> {fn}" if world == 1 else
+                f"ShardedPPCA.step over HostDataset shards -> {fn}_sharded (statistics, NCCL all-reduce, finish in one call)")
     else:
         mix0 = pk.PPCAMix([pk.PPCAModel(sg, Cj, muj) for Cj, muj, sg in (init_params(d, k, SEED + 1000 + j) for j in range(m))], np.zeros(m))
         host = pk.HostDataset(Xh, pin=True, ctx=ctx)            # page-locks Xh; Dataset(Xh) below DMAs from it directly
@@ -598,6 +605,7 @@ def run_ours(args, wl, rank, world, local_rank):
            "d2h_bytes_per_step": d2h, "steps": e2e_steps, "rows_per_gpu": n_e2e, "call": call,
            "h2d_gb_per_s": h2d * e2e_steps / e2e_s / 1e9,
            "resident_handle_value": resident,
+           "host_bytes_per_sample": h2d / n_e2e, "dense_bytes_per_sample": d * 8,
            "note": "samples in page-locked HOST memory cross the bus every step inside the timed region (wall clock, "
                    "barrier + synchronize on both sides, max over ranks); resident_handle_value = same public call with "
                    "the Dataset kept behind its device handle, as the reference API holds it (src/python_bindings.rs:28-30)"}
@@ -616,7 +624,8 @@ def run_ours(args, wl, rank, world, local_rank):
     # one E-step and one M-step contraction per model (the mixture pass shares the E-step between the posteriors and the
     # weighted statistics)
     contractions = 2 * max(1, m)
-    flops_bit = contractions * (2 * d * kk) * n * args.steps          # algorithmic FP64 flops
+    # algorithmic FP64 flops: Mask * Ksym (E-step), Mask^T * W and Mask^T * (w Z) (M-step), per model
+    flops_bit = max(1, m) * (2 * (2 * d * kk) + 2 * d * k) * n * args.steps
     fp64_equiv = flops_bit / (bit_ms * 1e-3) / 1e12 if bit_ms > 0 else None
     launches_bit = contractions * args.steps * max(1, -(-n // max(1, ctx_chunk(ctx, n, d, k))))
     n_chunk = min(ctx_chunk(ctx, n, d, k), n)
@@ -864,6 +873,8 @@ def main():
     ap.add_argument("--rows", type=int, default=0, help="override rows per GPU")
     ap.add_argument("--chunk", type=int, default=0, help="samples per chunk (0 = automatic)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--e2e-plain", action="store_true",
+                    help="end-to-end leg streams the full n x d matrix instead of the compact host format")
     ap.add_argument("--no-blocks", action="store_true", help="skip the strong-scaling run and the c3/c4 shard blocks")
     ap.add_argument("--c3-rows", type=int, default=524_288, help="rows per GPU of the c3_shard block")
     ap.add_argument("--c4-rows", type=int, default=131_072, help="rows per GPU of the c4_shard block")

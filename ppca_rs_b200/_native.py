@@ -102,6 +102,18 @@ _PROTOTYPES = {
         [c_ctx_p, c_dp, C.c_int64, C.c_int32, c_dp, C.c_int32, c_dp, c_dp, C.c_double, C.POINTER(CPrior), c_dp, c_dp,
          c_dp, c_dp],
     ),
+    "ppca_b200_pack_host": (
+        C.c_int32, [c_dp, C.c_int64, C.c_int32, c_dp, C.POINTER(C.c_int64), C.POINTER(C.c_uint32)]),
+    "ppca_b200_iterate_packed_host": (
+        C.c_int32,
+        [c_ctx_p, c_dp, C.POINTER(C.c_int64), C.POINTER(C.c_uint32), C.c_int64, C.c_int32, c_dp, C.c_int32, c_dp, c_dp,
+         C.c_double, C.POINTER(CPrior), c_dp, c_dp, c_dp, c_dp],
+    ),
+    "ppca_b200_iterate_packed_host_sharded": (
+        C.c_int32,
+        [c_ctx_p, c_dp, C.POINTER(C.c_int64), C.POINTER(C.c_uint32), C.c_int64, C.c_int32, c_dp, C.c_int32, c_dp, c_dp,
+         C.c_double, C.POINTER(CPrior), c_dp, c_dp, c_dp, c_dp],
+    ),
     "ppca_b200_em_stats_host": (
         C.c_int32, [c_ctx_p, c_dp, C.c_int64, C.c_int32, c_dp, C.c_int32, c_dp, c_dp, C.c_double, C.c_void_p]),
     "ppca_b200_reconstruct_host": (

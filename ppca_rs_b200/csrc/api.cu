@@ -75,6 +75,8 @@ struct ppca_b200_ctx {
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
   DevBuf<double> s_raw[2], s_wraw[2], s_w;
+  DevBuf<int64_t> s_rowptr[2];   // compact host format: row offsets and mask words of the block in flight
+  DevBuf<uint32_t> s_maskw[2];
   std::shared_ptr<SampleStore> s_store, s_tail;
   // out-of-core inference (ppca_b200_reconstruct_host): D2H stream and double-buffered outputs
   cudaStream_t out_stream = nullptr;
@@ -89,8 +91,22 @@ struct ppca_b200_ctx {
   double last_profile[FAM_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0};
 
   Launcher L() { return Launcher{stream, &launches, sms, variants}; }
+  // The pinned staging buffer is written by the host and read by asynchronous copies: instead of draining the whole stream
+  // before reusing it, an event marks the last copy that read it (pin_mark) and the next writer waits for that alone.
+  cudaEvent_t pin_ev = nullptr;
+  bool pin_pending = false;
+  void pin_wait() {
+    if (pin_pending) CUDA_CHECK(cudaEventSynchronize(pin_ev));
+    pin_pending = false;
+  }
+  void pin_mark() {
+    if (!pin_ev) CUDA_CHECK(cudaEventCreateWithFlags(&pin_ev, cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventRecord(pin_ev, stream));
+    pin_pending = true;
+  }
   double *pin(size_t count) {
     if (count > pinned_count) {
+      pin_wait();
       if (pinned) cudaFreeHost(pinned);
       pinned = nullptr;
       pinned_count = 0;
@@ -310,12 +326,13 @@ DevModel stage_model_into(ppca_b200_ctx *ctx, int d, int k, const double *C, con
   ctx->Cdense.reserve((size_t)d * k);
   ctx->mudense.reserve((size_t)d);
   double *stage = ctx->pin((size_t)d * k + d);
-  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));  // staging buffer may still be in flight
+  ctx->pin_wait();  // the staging buffer may still be the source of an earlier copy
   memcpy(stage, C, sizeof(double) * d * k);
   memcpy(stage + (size_t)d * k, mu, sizeof(double) * d);
   CUDA_CHECK(cudaMemcpyAsync(ctx->Cdense.p, stage, sizeof(double) * d * k, cudaMemcpyHostToDevice, ctx->stream));
   CUDA_CHECK(cudaMemcpyAsync(ctx->mudense.p, stage + (size_t)d * k, sizeof(double) * d, cudaMemcpyHostToDevice,
                              ctx->stream));
+  ctx->pin_mark();
   ctx->span_begin(FAM_KSYM);
   launch_prepare_model(ctx->L(), ctx->Cdense.p, ctx->mudense.p, d, k, Cpad, mupad, Ksym);
   const int kblocks = s.d32 / 32;
@@ -759,7 +776,7 @@ double em_finish_impl(ppca_b200_ctx *ctx, int d, int k, const double *C, const d
   ctx->flags.reserve((size_t)d);
   const size_t tail = (size_t)2 * d + 8;
   double *stage = ctx->pin((size_t)d * k + tail + (size_t)d * k);
-  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  ctx->pin_wait();  // no stream drain here: everything below is enqueued behind the statistics kernels still running
   memcpy(stage, C, sizeof(double) * d * k);
   CUDA_CHECK(cudaMemcpyAsync(ctx->Cdense.p, stage, sizeof(double) * d * k, cudaMemcpyHostToDevice, ctx->stream));
   // only the padded old transform is needed on the device here (fallback rows); mu stays on the host
@@ -775,7 +792,8 @@ double em_finish_impl(ppca_b200_ctx *ctx, int d, int k, const double *C, const d
   CUDA_CHECK(cudaMemcpyAsync(h_tail, stats_dev + lay.offTdev, sizeof(double) * tail, cudaMemcpyDeviceToHost,
                              ctx->stream));
   CUDA_CHECK(cudaMemcpyAsync(h_C, ctx->Cnew.p, sizeof(double) * d * k, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));  // the one synchronisation of an EM step
+  ctx->pin_pending = false;
   const double *tdev = h_tail, *totals = h_tail + d, *sc = h_tail + 2 * d;
   if (!(sc[SC_NONEMPTY] > 0.0)) PPCA_THROW(PPCA_ERR_EMPTY, "non-empty dataset required (ppca_model.rs:358)");
   memcpy(C_out, h_C, sizeof(double) * d * k);
@@ -1065,6 +1083,7 @@ int32_t ppca_b200_ctx_destroy(ppca_b200_ctx *ctx) {
       ctx->comm = nullptr;
     }
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->pin_ev) cudaEventDestroy(ctx->pin_ev);
     for (int b = 0; b < 2; ++b)
       if (ctx->upload_pin[b]) cudaFreeHost(ctx->upload_pin[b]);
     for (int b = 0; b < 2; ++b) {
@@ -1278,7 +1297,7 @@ int32_t ppca_b200_model_sample(ppca_b200_ctx *ctx, int64_t n, int32_t d, int32_t
       ctx->Cdense.reserve((size_t)d * k);
       ctx->mudense.reserve((size_t)d);
       double *stage = ctx->pin((size_t)d * k + d);
-      CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+      ctx->pin_wait();
       memcpy(stage, C, sizeof(double) * d * k);
       memcpy(stage + (size_t)d * k, mu, sizeof(double) * d);
       CUDA_CHECK(cudaMemcpyAsync(ctx->Cdense.p, stage, sizeof(double) * d * k, cudaMemcpyHostToDevice, ctx->stream));
@@ -1670,8 +1689,15 @@ int32_t ppca_b200_host_unregister(const void *p) {
 
 namespace {
 // streams x (host) through the device block by block and accumulates the statistics into stats_dev
+// compact host format of a shard (see ppca_b200_iterate_packed_host); null = the plain n x d matrix `x`
+struct PackedHost {
+  const double *vals = nullptr;
+  const int64_t *rowptr = nullptr;
+  const uint32_t *maskw = nullptr;
+};
+
 void em_stats_host_impl(ppca_b200_ctx *ctx, const double *x, int64_t n, int d, const double *weights, const DevModel &m,
-                        double *stats_dev) {
+                        double *stats_dev, const PackedHost *pk = nullptr) {
   if (!ctx->copy_stream) {
     CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     for (int b = 0; b < 2; ++b) {
@@ -1685,8 +1711,21 @@ void em_stats_host_impl(ppca_b200_ctx *ctx, const double *x, int64_t n, int d, c
   if (n >= blk && (!ctx->s_store || ctx->s_store->n != blk || ctx->s_store->d != d)) ctx->s_store = make_store(ctx, blk, d);
   if (tail && (!ctx->s_tail || ctx->s_tail->n != tail || ctx->s_tail->d != d)) ctx->s_tail = make_store(ctx, tail, d);
   const int64_t brows = n < blk ? n : blk;
+  const int dw = (d + 31) / 32;
+  size_t max_nnz = 0;  // most observed values of any block (packed source)
+  if (pk)
+    for (int64_t r0 = 0; r0 < n; r0 += blk) {
+      const int64_t r1 = std::min<int64_t>(n, r0 + blk);
+      max_nnz = std::max(max_nnz, (size_t)(pk->rowptr[r1] - pk->rowptr[r0]));
+    }
   for (int b = 0; b < 2; ++b) {
-    ctx->s_raw[b].reserve((size_t)brows * d);
+    if (pk) {
+      ctx->s_raw[b].reserve(max_nnz ? max_nnz : 1);
+      ctx->s_rowptr[b].reserve((size_t)brows + 1);
+      ctx->s_maskw[b].reserve((size_t)brows * dw);
+    } else {
+      ctx->s_raw[b].reserve((size_t)brows * d);
+    }
     if (weights) ctx->s_wraw[b].reserve((size_t)brows);
   }
   ctx->s_w.reserve((size_t)round_up(brows, 256));
@@ -1701,14 +1740,26 @@ void em_stats_host_impl(ppca_b200_ctx *ctx, const double *x, int64_t n, int d, c
     SampleStore &st = rows == blk ? *ctx->s_store : *ctx->s_tail;
     // H2D of block i on the copy stream, overlapped with the kernels of block i-1 on the compute stream
     if (i >= 2) CUDA_CHECK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_free[b], 0));
-    CUDA_CHECK(cudaMemcpyAsync(ctx->s_raw[b].p, x + r0 * d, sizeof(double) * rows * d, cudaMemcpyHostToDevice,
-                               ctx->copy_stream));
+    if (pk) {
+      const int64_t nnz = pk->rowptr[r0 + rows] - pk->rowptr[r0];
+      if (nnz > 0)
+        CUDA_CHECK(cudaMemcpyAsync(ctx->s_raw[b].p, pk->vals + pk->rowptr[r0], sizeof(double) * nnz, cudaMemcpyHostToDevice,
+                                   ctx->copy_stream));
+      CUDA_CHECK(cudaMemcpyAsync(ctx->s_rowptr[b].p, pk->rowptr + r0, sizeof(int64_t) * (rows + 1), cudaMemcpyHostToDevice,
+                                 ctx->copy_stream));
+      CUDA_CHECK(cudaMemcpyAsync(ctx->s_maskw[b].p, pk->maskw + r0 * dw, sizeof(uint32_t) * rows * dw,
+                                 cudaMemcpyHostToDevice, ctx->copy_stream));
+    } else {
+      CUDA_CHECK(cudaMemcpyAsync(ctx->s_raw[b].p, x + r0 * d, sizeof(double) * rows * d, cudaMemcpyHostToDevice,
+                                 ctx->copy_stream));
+    }
     if (weights)
       CUDA_CHECK(cudaMemcpyAsync(ctx->s_wraw[b].p, weights + r0, sizeof(double) * rows, cudaMemcpyHostToDevice,
                                  ctx->copy_stream));
     CUDA_CHECK(cudaEventRecord(ctx->ev_copied[b], ctx->copy_stream));
     CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[b], 0));
-    launch_ingest(L, ctx->s_raw[b].p, rows, d, 0, st);
+    if (pk) launch_unpack(L, ctx->s_raw[b].p, ctx->s_rowptr[b].p, ctx->s_maskw[b].p, rows, d, 0, st);
+    else launch_ingest(L, ctx->s_raw[b].p, rows, d, 0, st);
     CUDA_CHECK(cudaMemsetAsync(ctx->s_w.p, 0, sizeof(double) * st.n_pad, ctx->stream));
     if (weights) {
       CUDA_CHECK(cudaMemcpyAsync(ctx->s_w.p, ctx->s_wraw[b].p, sizeof(double) * rows, cudaMemcpyDeviceToDevice,
@@ -2478,6 +2529,101 @@ int32_t ppca_b200_iterate_host_sharded(ppca_b200_ctx *ctx, const double *x, int6
       return em_finish_impl(ctx, d, k, C, mu, sigma, prior, ctx->stats.p, C_out, mu_out, sigma_out, llk_in, nullptr);
     });
   });
+}
+
+int32_t ppca_b200_pack_host(const double *x, int64_t n, int32_t d, double *vals, int64_t *rowptr, uint32_t *maskw) {
+  return guarded([&] {
+    REQUIRE(n >= 0 && d >= 1 && rowptr != nullptr && (n == 0 || x != nullptr), "bad arguments");
+    const int dw = (d + 31) / 32;
+    // pass 1: per-row counts (threads over row ranges), pass 2: exclusive scan, pass 3: scatter (vals / maskw nullable)
+    const int nthr = (int)std::max<int64_t>(1, std::min<int64_t>(16, n / 4096));
+    rowptr[0] = 0;
+    auto rows_of = [&](int t, int64_t &lo, int64_t &hi) {
+      lo = n * t / nthr;
+      hi = n * (t + 1) / nthr;
+    };
+    {
+      std::vector<std::thread> th;
+      for (int t = 0; t < nthr; ++t)
+        th.emplace_back([&, t] {
+          int64_t lo, hi;
+          rows_of(t, lo, hi);
+          for (int64_t r = lo; r < hi; ++r) {
+            int64_t c = 0;
+            const double *row = x + r * d;
+            for (int i = 0; i < d; ++i) c += std::isfinite(row[i]) ? 1 : 0;
+            rowptr[r + 1] = c;
+          }
+        });
+      for (auto &t : th) t.join();
+    }
+    for (int64_t r = 0; r < n; ++r) rowptr[r + 1] += rowptr[r];
+    if (!vals || !maskw) return;  // counting call: rowptr[n] = number of observed values
+    {
+      std::vector<std::thread> th;
+      for (int t = 0; t < nthr; ++t)
+        th.emplace_back([&, t] {
+          int64_t lo, hi;
+          rows_of(t, lo, hi);
+          for (int64_t r = lo; r < hi; ++r) {
+            const double *row = x + r * d;
+            double *out = vals + rowptr[r];
+            uint32_t *mw = maskw + r * dw;
+            for (int j = 0; j < dw; ++j) mw[j] = 0u;
+            for (int i = 0; i < d; ++i)
+              if (std::isfinite(row[i])) {
+                *out++ = row[i];
+                mw[i >> 5] |= 1u << (i & 31);
+              }
+          }
+        });
+      for (auto &t : th) t.join();
+    }
+  });
+}
+
+static int32_t iterate_packed_host(ppca_b200_ctx *ctx, const double *vals, const int64_t *rowptr, const uint32_t *maskw,
+                                   int64_t n, int32_t d, const double *weights, int32_t k, const double *C,
+                                   const double *mu, double sigma, const ppca_b200_prior *prior, double *C_out,
+                                   double *mu_out, double *sigma_out, double *llk_in, bool sharded) {
+  return guarded([&] {
+    REQUIRE(ctx != nullptr, "null context");
+    REQUIRE(n >= 0 && d >= 1, "bad dataset shape %lld x %d", (long long)n, d);
+    REQUIRE(!sharded || ctx->comm != nullptr, "no communicator: call ppca_b200_comm_init first");
+    if (n == 0 && !sharded) PPCA_THROW(PPCA_ERR_EMPTY, "non-empty dataset required (ppca_model.rs:358)");
+    REQUIRE(n == 0 || (rowptr != nullptr && maskw != nullptr && (vals != nullptr || rowptr[n] == 0)), "null data");
+    DeviceGuard g(ctx->device);
+    const int64_t slen = StatsLayout(d, k).len;
+    PackedHost pk;
+    pk.vals = vals;
+    pk.rowptr = rowptr;
+    pk.maskw = maskw;
+    run_guarded(ctx, [&] {
+      DevModel m = stage_model(ctx, d, k, C, mu, sigma);
+      ctx->stats.reserve((size_t)slen);
+      if (n == 0) CUDA_CHECK(cudaMemsetAsync(ctx->stats.p, 0, sizeof(double) * slen, ctx->stream));
+      else em_stats_host_impl(ctx, nullptr, n, d, weights, m, ctx->stats.p, &pk);
+      if (sharded) comm_allreduce(ctx->comm, ctx->stats.p, slen, 0, ctx->stream);
+      return em_finish_impl(ctx, d, k, C, mu, sigma, prior, ctx->stats.p, C_out, mu_out, sigma_out, llk_in, nullptr);
+    });
+  });
+}
+
+int32_t ppca_b200_iterate_packed_host(ppca_b200_ctx *ctx, const double *vals, const int64_t *rowptr,
+                                      const uint32_t *maskw, int64_t n, int32_t d, const double *weights, int32_t k,
+                                      const double *C, const double *mu, double sigma, const ppca_b200_prior *prior,
+                                      double *C_out, double *mu_out, double *sigma_out, double *llk_in) {
+  return iterate_packed_host(ctx, vals, rowptr, maskw, n, d, weights, k, C, mu, sigma, prior, C_out, mu_out, sigma_out,
+                             llk_in, false);
+}
+
+int32_t ppca_b200_iterate_packed_host_sharded(ppca_b200_ctx *ctx, const double *vals, const int64_t *rowptr,
+                                              const uint32_t *maskw, int64_t n, int32_t d, const double *weights,
+                                              int32_t k, const double *C, const double *mu, double sigma,
+                                              const ppca_b200_prior *prior, double *C_out, double *mu_out,
+                                              double *sigma_out, double *llk_in) {
+  return iterate_packed_host(ctx, vals, rowptr, maskw, n, d, weights, k, C, mu, sigma, prior, C_out, mu_out, sigma_out,
+                             llk_in, true);
 }
 
 int32_t ppca_b200_mix_iterate_sharded(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int32_t m, const int32_t *ks,

@@ -209,6 +209,9 @@ struct PerDeviceOnce {
 // ---- kernels (host launchers) ----------------------------------------------------------------
 // ingest.cu
 void launch_ingest(const Launcher &L, const double *raw, int64_t nrows, int d, int64_t row0, SampleStore &st);
+// compact host format (observed values + row offsets + mask words), see ppca_b200_iterate_packed_host
+void launch_unpack(const Launcher &L, const double *vals, const int64_t *rowptr, const uint32_t *maskw, int64_t nrows, int d,
+                   int64_t row0, SampleStore &st);
 void launch_transpose_mask(const Launcher &L, SampleStore &st);
 void launch_export(const Launcher &L, const SampleStore &st, int64_t row0, int64_t nrows, double *out_dev);
 void launch_empty_dims(const Launcher &L, const SampleStore &st, uint8_t *out_dev);

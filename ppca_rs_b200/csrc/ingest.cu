@@ -40,6 +40,41 @@ void launch_ingest(const Launcher &L, const double *raw, int64_t nrows, int d, i
   ++*L.launch_counter;
 }
 
+// The compact host format of the out-of-core path: only the OBSERVED values cross the bus.  One warp per sample row
+// scatters vals[rowptr[row] - rowptr[0] + rank of the bit] into X, zeros elsewhere; the mask words are copied as they are.
+__global__ void unpack_kernel(const double *__restrict__ vals, const int64_t *__restrict__ rowptr,
+                              const uint32_t *__restrict__ maskw, int64_t nrows, int d, int64_t row0, double *X, int ldx,
+                              uint32_t *mask, int dw, int *dn) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (row >= nrows) return;
+  const double *src = vals + (rowptr[row] - rowptr[0]);
+  double *dst = X + (row0 + row) * ldx;
+  int count = 0;
+  for (int j = 0; j < dw; ++j) {
+    const int i = 32 * j + lane;
+    uint32_t word = maskw[row * dw + j];
+    if (32 * j + 32 > d) word &= (d - 32 * j >= 32) ? 0xffffffffu : ((1u << (d - 32 * j)) - 1u);  // bits past d never count
+    const bool obs = (word >> lane) & 1u;
+    const int pos = count + __popc(word & ((1u << lane) - 1u));
+    if (i < ldx) dst[i] = obs ? src[pos] : 0.0;
+    if (lane == 0) mask[(row0 + row) * dw + j] = word;
+    count += __popc(word);
+  }
+  if (lane == 0) dn[row0 + row] = count;
+}
+
+void launch_unpack(const Launcher &L, const double *vals, const int64_t *rowptr, const uint32_t *maskw, int64_t nrows, int d,
+                   int64_t row0, SampleStore &st) {
+  if (nrows <= 0) return;
+  const int threads = 256;
+  const int64_t blocks = (nrows * 32 + threads - 1) / threads;
+  unpack_kernel<<<(unsigned)blocks, threads, 0, L.stream>>>(vals, rowptr, maskw, nrows, d, row0, st.X.p, st.ldx, st.mask.p,
+                                                            st.dw, st.dn.p);
+  CUDA_CHECK(cudaGetLastError());
+  ++*L.launch_counter;
+}
+
 // maskT[32 j + b][bs] bit l  =  mask[32 bs + l][j] bit b.   One warp per 32x32 bit block; 32 warps per CTA
 // cover 32 consecutive sample blocks so the transposed words leave as 128-byte rows.
 __global__ void __launch_bounds__(1024) transpose_mask_kernel(const uint32_t *__restrict__ mask, int dw, int64_t n_pad,

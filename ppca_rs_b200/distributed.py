@@ -141,20 +141,21 @@ class ShardedPPCA:
     def __init__(self, ctx, dataset, model: PPCAModel, group=None, prior: Optional[Prior] = None, engine=None,
                  collective: Optional[str] = None):
         if collective is None:
-            collective = "native" if (engine is None and group is not None) else "torch"
-        self.native = collective == "native" and group is not None
+            collective = "native" if engine is None else "torch"
+        self.native = collective == "native"
         self.dataset, self.model, self.prior, self.group = dataset, model, prior, group
         self.last_llk = float("nan")
         if self.native:
-            native_comm_init(ctx, group)
+            if group is not None:
+                native_comm_init(ctx, group)
             return
         self.engine = engine or CudaEngine(ctx)
         self.stats = self.engine.new_stats(model.output_size, model.state_size)
 
     def step(self) -> float:
         """One EM iteration; returns the (global) log-likelihood of the model the step started from."""
-        if self.native:
-            self.model, self.last_llk = self.model._iterate(self.dataset, self.prior, sharded=True)
+        if self.native:  # one call into the library: iterate / iterate_host / iterate_packed_host (+ _sharded with a group)
+            self.model, self.last_llk = self.model._iterate(self.dataset, self.prior, sharded=self.group is not None)
             return self.last_llk
         for _ in range(3):  # at most two climbs of the precision ladder (include/ppca_b200.h, PPCA_ERR_PRECISION)
             self.engine.em_stats(self.dataset, self.model, self.stats)

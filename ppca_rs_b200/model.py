@@ -184,7 +184,11 @@ class HostDataset:
     previous one.  For data that does not fit the device (BASELINE config 3 is 1.64 TB) or is visited once.
     Accepted by `PPCAModel.iterate / iterate_with_prior` and `PPCATrainer`; same numbers as `Dataset`."""
 
-    def __init__(self, ndarray, weights=None, *, pin: bool = True, ctx: Optional[nat.Context] = None):
+    def __init__(self, ndarray, weights=None, *, pin: bool = True, ctx: Optional[nat.Context] = None,
+                 packed: bool = False):
+        """packed=True keeps a compact copy of the samples in page-locked memory - only the OBSERVED values, row
+        offsets and the mask words (ppca_b200_pack_host) - and streams that instead of the full matrix: the bytes that
+        cross PCIe per EM step drop by the missing fraction (same results, bit for bit)."""
         self._ctx = ctx or nat.get_context()
         self._x = _as_matrix(ndarray, "ndarray")
         n, d = self._x.shape
@@ -196,8 +200,21 @@ class HostDataset:
             if self._w.shape[0] != n:  # dataset.rs:163
                 raise ValueError(f"weights has {self._w.shape[0]} entries for {n} samples")
         self._pinned = []
+        self._packed = None
+        if packed and n > 0:
+            dw = (d + 31) // 32
+            rowptr = np.empty(n + 1, dtype=np.int64)
+            lib = nat.lib()
+            nat.check(lib.ppca_b200_pack_host(nat.dptr(self._x), n, d, None, rowptr.ctypes.data_as(C.POINTER(C.c_int64)), None))
+            vals = np.empty(max(int(rowptr[n]), 1))
+            maskw = np.empty((n, dw), dtype=np.uint32)
+            nat.check(lib.ppca_b200_pack_host(nat.dptr(self._x), n, d, nat.dptr(vals),
+                                              rowptr.ctypes.data_as(C.POINTER(C.c_int64)),
+                                              maskw.ctypes.data_as(C.POINTER(C.c_uint32))))
+            self._packed = (vals, rowptr, maskw)
         if pin and n > 0:
-            for a in (self._x, self._w):
+            to_pin = (self._w,) + self._packed if self._packed is not None else (self._x, self._w)
+            for a in to_pin:
                 if a is not None and a.nbytes > 0:
                     # page-locking can be refused (RLIMIT_MEMLOCK, already-registered ranges): the data then streams
                     # from pageable memory - same results, lower PCIe rate
@@ -512,6 +529,14 @@ class PPCAModel:
             pr, keep = prior._c(d)
             pr_ref = C.byref(pr)
         lib = nat.lib()
+        if isinstance(dataset, HostDataset) and dataset._packed is not None:
+            vals, rowptr, maskw = dataset._packed
+            fn = lib.ppca_b200_iterate_packed_host_sharded if sharded else lib.ppca_b200_iterate_packed_host
+            nat.check(fn(dataset._ctx.handle, nat.dptr(vals), rowptr.ctypes.data_as(C.POINTER(C.c_int64)),
+                         maskw.ctypes.data_as(C.POINTER(C.c_uint32)), len(dataset), d, nat.dptr(dataset._w), k,
+                         nat.dptr(self._C), nat.dptr(self._mu), self._sigma, pr_ref, nat.dptr(C_out), nat.dptr(mu_out),
+                         C.byref(s_out), C.byref(llk)))
+            return PPCAModel(s_out.value, C_out, mu_out), llk.value
         if isinstance(dataset, HostDataset):
             fn = lib.ppca_b200_iterate_host_sharded if sharded else lib.ppca_b200_iterate_host
             nat.check(fn(dataset._ctx.handle, nat.dptr(dataset._x), len(dataset), d, nat.dptr(dataset._w), k,

@@ -1014,3 +1014,23 @@ def test_mean_prior_device_cholesky_matches_the_reference_qr(pk, orc):
         assert_close(new.transform, C, Cs, "C")
         assert_close(new.mean, mu, mus, "mu")
         assert_close(new.isotropic_noise, s, ss, "sigma")
+
+
+@pytest.mark.parametrize("n,d,k,chunk", [(5000, 90, 12, 1024), (3000, 200, 16, 0), (2048, 33, 7, 512)])
+def test_packed_host_streaming_equals_plain_host_streaming(pk, orc, n, d, k, chunk):
+    """The compact host format (observed values + offsets + mask words) must give the plain out-of-core path's bits."""
+    X, C0, mu0, s0 = _case(n, d, k, 0.3, seed=17, empty_rows=(3,), empty_dims=(d - 1,))
+    w = np.random.default_rng(2).random(n) + 0.5
+    ctx = pk.get_context()
+    ctx.set_chunk(chunk)
+    try:
+        model = pk.PPCAModel(s0, C0, mu0)
+        a, llk_a = model._iterate(pk.HostDataset(X, w, pin=False), None)
+        b, llk_b = model._iterate(pk.HostDataset(X, w, pin=True, packed=True), None)
+    finally:
+        ctx.set_chunk(0)
+    assert np.array_equal(a.transform, b.transform) and np.array_equal(a.mean, b.mean)
+    assert a.isotropic_noise == b.isotropic_noise and llk_a == llk_b
+    (Cw, muw, sw), (Cs, mus, ss) = both(orc, orc.iterate, X, w, C0, mu0, s0)
+    assert_close(b.transform, Cw, Cs, "C")
+    assert_close(b.mean, muw, mus, "mu")

@@ -323,3 +323,63 @@ def test_compat_alias_exposes_the_reference_module_names():
         for k in ("ppca_rs", "ppca_rs.ppca_rs"):
             sys.modules.pop(k, None)
         sys.modules.update(saved)
+
+
+def test_posterior_samplers_carry_the_model_without_a_gpu():
+    """InferredMasked / InferredMaskedMix keep the model they came from (ppca_model.rs:428-432, mix.rs:357-362), so
+    posterior_sampler().sample() needs no argument; checked here on the host objects alone."""
+    from ppca_rs_b200.model import InferredMasked, InferredMaskedMix, PPCAMix, PPCAModel
+    rng = np.random.default_rng(0)
+    model = PPCAModel(0.5, rng.standard_normal((6, 2)), np.zeros(6))
+    inf = InferredMasked(rng.standard_normal((5, 2)), np.stack([np.eye(2)] * 5), model)
+    smp = inf.posterior_sampler()
+    assert smp._model is model
+    mix = PPCAMix([model, model], np.log([0.5, 0.5]))
+    infm = InferredMaskedMix(np.log(np.full((5, 2), 0.5)), [inf, inf], mix)
+    assert infm.posterior_sampler()._mix is mix
+    import inspect
+    from ppca_rs_b200.model import PosteriorSampler, PosteriorSamplerMix
+    for cls in (PosteriorSampler, PosteriorSamplerMix):
+        params = list(inspect.signature(cls.sample).parameters.values())[1:]
+        assert all(p.default is not inspect.Parameter.empty for p in params)   # callable with no arguments
+
+
+def test_sharded_front_end_picks_the_native_collective_only_with_a_group():
+    """ShardedPPCA: engine given (CPU tests) -> spelled-out torch protocol; no group -> single process."""
+    from numpy_engine import HostShard, NumpyEngine
+    from ppca_rs_b200.distributed import ShardedPPCA
+    from ppca_rs_b200.model import PPCAModel
+    X = make_data(50, 6, 2, 0.2, seed=1)
+    C0, mu0, s0 = init_model(6, 2)
+    st = ShardedPPCA(None, HostShard(X, np.ones(50)), PPCAModel(s0, C0, mu0), group=None, engine=NumpyEngine())
+    assert st.native is False
+    assert ShardedPPCA(None, HostShard(X, np.ones(50)), PPCAModel(s0, C0, mu0), group=None).native is True
+    llk = st.step()
+    assert np.isfinite(llk)
+
+
+def test_pack_host_builds_the_compact_format_without_a_gpu():
+    """ppca_b200_pack_host (host-only): observed values row-major, row offsets, bit-vec style mask words."""
+    import ctypes as C
+    from ppca_rs_b200 import _native as nat
+    rng = np.random.default_rng(3)
+    n, d = 5000, 70
+    X = rng.standard_normal((n, d))
+    X[rng.random((n, d)) < 0.3] = np.nan
+    X[7] = np.nan
+    X[11, 3] = np.inf
+    dw = (d + 31) // 32
+    rowptr = np.empty(n + 1, dtype=np.int64)
+    p64, p32 = C.POINTER(C.c_int64), C.POINTER(C.c_uint32)
+    nat.check(nat.lib().ppca_b200_pack_host(nat.dptr(X), n, d, None, rowptr.ctypes.data_as(p64), None))
+    fin = np.isfinite(X)
+    assert rowptr[0] == 0 and np.array_equal(np.diff(rowptr), fin.sum(axis=1))
+    vals = np.empty(int(rowptr[n]))
+    maskw = np.empty((n, dw), dtype=np.uint32)
+    nat.check(nat.lib().ppca_b200_pack_host(nat.dptr(X), n, d, nat.dptr(vals), rowptr.ctypes.data_as(p64),
+                                            maskw.ctypes.data_as(p32)))
+    assert np.array_equal(vals, X[fin])
+    bits = np.zeros((n, dw * 32), dtype=bool)
+    bits[:, :d] = fin
+    want = np.packbits(bits, axis=1, bitorder="little").view(np.uint32).reshape(n, dw)
+    assert np.array_equal(maskw, want)

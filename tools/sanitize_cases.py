@@ -51,12 +51,46 @@ def main():
         assert np.isfinite(ex).all() and np.isfinite(llk)
         print("case", i, (n, d, k, gemm, slices), "llk", llk, flush=True)
     ctx.set_gemm("tc", 6)
+    if os.environ.get("SANITIZE_EXTRA", "1") == "1" and (not only or "x" in only.split(",")):
+        # one feature in other units: precision ladder (8 planes, DMMA) and the exact-residual pass
+        X = make_data(1024, 40, 5, 0.3, seed=3)
+        C0, mu0, s0 = init_model(40, 5)
+        X[:, 7] *= 1e3
+        C0 = C0.copy()
+        C0[7] *= 1e3
+        new, llk = pk.PPCAModel(1.0, C0, mu0)._iterate(pk.Dataset(X), None)
+        print("ill-scaled ok", llk, flush=True)
+        # k = 48 (24-column halves of the 128-thread solve), k = 32
+        for kk in (48, 32, 40):
+            X = make_data(768, 130, 8, 0.25, seed=kk)
+            C0, mu0, s0 = init_model(130, kk)
+            new, llk = pk.PPCAModel(s0, C0, mu0)._iterate(pk.Dataset(X), None)
+            print("k", kk, "ok", llk, flush=True)
+        # mean prior through the device Cholesky (3 panels), packed host streaming, one-pass reconstruct with reuse
+        rng = np.random.default_rng(1)
+        d = 70
+        X = make_data(1024, d, 6, 0.25, seed=11)
+        C0, mu0, s0 = init_model(d, 6)
+        A = rng.standard_normal((d, d))
+        prior = pk.Prior().with_mean_prior(rng.standard_normal(d), A @ A.T / d + np.eye(d)).with_isotropic_noise_prior(2.0, 1.0)
+        model = pk.PPCAModel(s0, C0, mu0).iterate_with_prior(pk.Dataset(X), prior)
+        ctx.set_chunk(512)
+        model = model.iterate(pk.HostDataset(X, pin=True, packed=True))
+        ctx.set_chunk(0)
+        ds = pk.Dataset(X)
+        ex, ll = model.reconstruct(ds, True, with_llks=True)
+        ex, ll = model.reconstruct(ds, False, out=ex, with_llks=True)
+        assert np.isfinite(ex.numpy()).all() and np.isfinite(ll).all()
+        print("prior / packed host / reconstruct ok", flush=True)
     if os.environ.get("SANITIZE_MIX", "1") == "1" and not only:
         X = make_data(1500, 64, 4, 0.2, seed=9)
         mix = pk.PPCAMix([pk.PPCAModel(1.0, *init_model(64, kk, seed=j)[:2][::1]) for j, kk in enumerate((4, 6, 3))],
                          np.zeros(3))
         mix2 = mix.iterate(pk.Dataset(X))
-        print("mixture ok", mix2.log_weights, flush=True)
+        ctx.set_chunk(512)                      # several chunks: running maxima and rescaling
+        mix3 = mix2.iterate(pk.Dataset(X))
+        ctx.set_chunk(0)
+        print("mixture ok", mix3.log_weights, flush=True)
     print("variant counts", {k: v for k, v in ctx.variant_counts().items() if v}, flush=True)
 
 
