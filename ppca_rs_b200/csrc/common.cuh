@@ -175,7 +175,7 @@ enum Variant {
   V_SOLVE_REG16,
   V_SOLVE_REG32,
   V_SOLVE_SPLIT64,
-  V_UNUSED10,
+  V_SOLVE_TILE,      // solve_tile_kernel<32 | 48 | 64> (register-tiled sweep, 16 < k <= 64)
   V_UNUSED11,
   V_SOLVE_GENERIC,
   V_PRECISION_RETRY,  // passes repeated at a wider arithmetic after the precision guard fired

@@ -583,6 +583,340 @@ __global__ void __launch_bounds__(256, MINB) solve_split64_kernel(SolveArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Register-tiled variant (16 < k <= 64, the default): thread (tr, tc) owns the TR x TC tile rows [TR tr, TR tr + TR),
+// columns [TC tc, TC tc + TC) of the symmetric matrix.  Same elimination as above (square-root symmetric sweep, swept
+// rows left in their own units), but every exchanged multiplier a thread reads from shared memory now feeds TR (column
+// operands) or TC (row operands) FMAs instead of one: (TR + TC) 8-byte operands per TR TC FMAs (4 x 8: 0.375 per FMA,
+// 6 x 6: 0.33) against 1.03 for the lane-owns-a-row layout.  ncu on the row layout (profiles/r02_c3s_step_ncu_details.txt)
+// shows why that matters: shared-memory return bandwidth (128 B/clk/SM = 16 doubles) is a quarter of the FP64 FMA rate
+// (64/clk/SM), so a kernel that fetches one operand per FMA cannot pass 25 % of the FP64 roof (L1/TEX 72 % busy,
+// FP64 pipe 35 %).
+//   KD = 32: 4 x 8 tiles,  32 threads per sample (one warp, __syncwarp between pivots)
+//   KD = 48: 6 x 6 tiles,  64 threads per sample
+//   KD = 64: 4 x 8 tiles, 128 threads per sample
+// Per pivot p the threads of the column block that holds column p ("publishers", NTR consecutive threads) publish
+// s_i = T[i][p] / sqrt(d_p) for their rows, in true units (column operands for everybody) and in the row's own units
+// (row operands); the owner of (p+1, p+1) adds that diagonal entry, from which EVERY thread forms
+// d_{p+1} = T[p+1][p+1] - s_{p+1}^2 right after the barrier, so 1/sqrt(d_{p+1}) overlaps the update: one barrier per pivot.
+// Every thread tracks 1/d_i of its own rows in registers (swept rows stay in their own units, d_i x true).
+// ---------------------------------------------------------------------------------------------
+template <int N>
+__device__ __forceinline__ void sample_sync(int id) {
+  if constexpr (N == 32) __syncwarp();
+  else asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(N) : "memory");
+}
+
+template <int KD, int TR, int TC>
+struct TileLayout {
+  static constexpr int NTR = KD / TR, NTC = KD / TC, TPS = NTR * NTC, SPC = 256 / TPS, WPS = TPS / 32;
+  static constexpr int SR = 6;  // pitch (doubles) of one thread's row group in the own-units exchange: 2 x odd keeps the
+                                // 128-bit reads of eight consecutive row groups on disjoint banks
+  static constexpr int EX = KD + NTR * SR + 2;  // true units | own units | next diagonal (+ pad)
+  // per sample: stage[kkp] | exch[2][EX] | yb[KD] | zb[KD] | zpart[NTC][KD] | piv[KD] | red[4 * 4]
+  static constexpr int FIXED = 2 * EX + 3 * KD + NTC * KD + 16;
+  static_assert(KD % TR == 0 && KD % TC == 0 && TR % 2 == 0 && TC % 2 == 0 && TR <= SR, "tile shape");
+  static_assert(TPS % 32 == 0 && 256 % TPS == 0 && TPS >= KD && NTR >= 8, "thread layout");
+};
+
+template <int KD, int TR, int TC, int MINB>
+__global__ void __launch_bounds__(256, MINB) solve_tile_kernel(SolveArgs a) {
+  using LY = TileLayout<KD, TR, TC>;
+  constexpr int NTR = LY::NTR, NTC = LY::NTC, TPS = LY::TPS, SPC = LY::SPC, WPS = LY::WPS, SR = LY::SR, EX = LY::EX;
+  extern __shared__ __align__(16) double smem_reg[];
+  const int smp = threadIdx.x / TPS, t = threadIdx.x % TPS;
+  const int tr = t % NTR, tc = t / NTR;
+  const int r0 = TR * tr, c0 = TC * tc;
+  const int lane = threadIdx.x & 31, wis = t >> 5;  // warp within the sample
+  const int bar_id = smp + 1;
+  const int k = a.s.k, kkp = a.s.kkp, kp = a.s.kp;
+  // rows / columns past k are identity padding whose pivots change nothing: whole pivot blocks past k are skipped
+  constexpr int PBLK = TR > TC ? TR : TC;
+  const int nblk = (k + PBLK - 1) / PBLK;
+  const int kpiv = nblk * PBLK;
+  const int per_smp = kkp + LY::FIXED;
+  double *stage = smem_reg + (size_t)smp * per_smp;  // one packed row: G in, W out
+  double *exch = stage + kkp;
+  double *yb = exch + 2 * EX;
+  double *zb = yb + KD;
+  double *zpart = zb + KD;
+  double *piv = zpart + NTC * KD;
+  double *red = piv + KD;
+  double *cmw = smem_reg + (size_t)SPC * per_smp + (size_t)smp * kkp;  // running max |W| of this slot's samples
+  if (a.colmax)
+    for (int q = t; q < kkp; q += TPS) cmw[q] = 0.0;
+  const double s2 = a.sigma * a.sigma;
+  const double ln_sigma = log(a.sigma);
+
+  for (int row = blockIdx.x * SPC + smp; row < a.rows_pad; row += gridDim.x * SPC) {
+    double *gsrc = a.GW + (int64_t)row * kkp;
+    for (int q = t * 2; q < kkp; q += 2 * TPS)
+      *reinterpret_cast<double2 *>(stage + q) = *reinterpret_cast<const double2 *>(gsrc + q);
+    if (t < KD) yb[t] = (t < kp) ? a.YZ[(int64_t)row * kp + t] : 0.0;
+    const int dn = row < a.rows ? a.dn[row] : 0;
+    const bool empty = dn == 0;
+    const double w = (a.w && row < a.rows) ? a.w[row] : (row < a.rows ? 1.0 : 0.0);
+    sample_sync<TPS>(bar_id);
+
+    double A[TR][TC];
+#pragma unroll
+    for (int ia = 0; ia < TR; ++ia) {
+      const int i = r0 + ia;
+      const int upi = tri_row_off(i, k) - i;
+#pragma unroll
+      for (int jb = 0; jb < TC; ++jb) {
+        const int j = c0 + jb;
+        const bool use = !empty && i < k && j < k;
+        int idx = (j >= i) ? upi + j : ((j * (2 * k - j - 1)) >> 1) + i;
+        idx = use ? idx : 0;
+        const double g = stage[idx];
+        const double unit = (i == j) ? 1.0 : 0.0;
+        A[ia][jb] = use ? fma(unit, s2, g) : unit;
+      }
+    }
+    if (a.gscale && t < k && !empty) {  // precision guard (see SolveArgs): thread t checks M_tt
+      const int qd = tri_row_off(t, k);
+      if (guard_terms((double)dn) * a.guard_coef * a.gscale[qd] > s2 + stage[qd]) atomicAdd(a.unsafe, 1u);
+    }
+
+    // The pivot loop is unrolled over one block of PB pivots only (static register indices need p % TR, p % TC and the
+    // exchange-buffer parity at compile time, all periodic in PB); the blocks run in a real loop: fully unrolled, the 64
+    // pivot bodies were 140 KB of SASS, four times the instruction cache.  The body is BRANCH-FREE: every thread runs
+    // the publishers' arithmetic (1/sqrt(d), its column-p entries scaled) and only the stores are predicated.  With a
+    // branch around the publishers' section the serial chain  d -> 1/sqrt(d) -> s -> store -> barrier  sat behind the
+    // thread's own 32 FMAs and took half of every pivot (ncu source view: 350 of 730 cycles); in one basic block the
+    // compiler schedules the chain of pivot p + 1 (started right after the barrier of pivot p) under the FMAs of pivot p.
+    double dcur = (empty || k <= 0) ? 1.0 : s2 + stage[0];
+    double rinv = fast_rsqrt(dcur);
+    double sc[TR];  // 1/d_i once row i has been swept (1 before): swept rows stay in their own units (d_i x true)
+#pragma unroll
+    for (int ia = 0; ia < TR; ++ia) sc[ia] = 1.0;
+    constexpr int PB = PBLK;
+    static_assert(PB % TR == 0 && PB % TC == 0 && PB % 2 == 0 && KD % PB == 0, "pivot block");
+    constexpr int ND = KD + NTR * SR;  // slot of the next diagonal entry
+    for (int pb = 0; pb < nblk; ++pb) {
+#pragma unroll
+      for (int pp = 0; pp < PB; ++pp) {
+        const int p = pb * PB + pp;
+        double *ex = exch + (pp & 1) * EX;  // [0, KD) s true units | [KD, ND) s own units, padded | [ND] next diagonal
+        const bool pub = tc == pb * (PB / TC) + pp / TC;    // this thread holds column p
+        const bool prow = tr == pb * (PB / TR) + pp / TR;   // this thread holds row p
+        {
+          double mine[TR], tv[TR];
+#pragma unroll
+          for (int ia = 0; ia < TR; ++ia) {
+            mine[ia] = A[ia][pp % TC] * rinv;
+            tv[ia] = mine[ia] * sc[ia];
+          }
+          if (pub) {
+#pragma unroll
+            for (int ia = 0; ia < TR; ia += 2) {
+              *reinterpret_cast<double2 *>(ex + r0 + ia) = make_double2(tv[ia], tv[ia + 1]);
+              *reinterpret_cast<double2 *>(ex + KD + tr * SR + ia) = make_double2(mine[ia], mine[ia + 1]);
+            }
+          }
+          if (pub && prow) piv[p] = dcur;
+        }
+        // owner of (p + 1, p + 1) adds that diagonal entry (after the last pivot of the matrix there is none)
+        if (tr == pb * (PB / TR) + (pp + 1) / TR && tc == pb * (PB / TC) + (pp + 1) / TC)
+          ex[ND] = A[(pp + 1) % TR][(pp + 1) % TC];
+        sample_sync<TPS>(bar_id);
+        // d_{p+1} = T[p+1][p+1] - s_{p+1}^2, bitwise what the owner of (p + 1, p + 1) computes below (row p + 1 is not
+        // swept yet: its own units are the true units).  After the last pivot this reads padding and is not used.
+        const double sn = ex[p + 1];
+        dcur = fma(-sn, sn, ex[ND]);
+        const double rnext = fast_rsqrt(dcur);
+        double f[TR], cv[TC];
+#pragma unroll
+        for (int ia = 0; ia < TR; ia += 2) {
+          const double2 v = *reinterpret_cast<const double2 *>(ex + KD + tr * SR + ia);
+          f[ia] = v.x;
+          f[ia + 1] = v.y;
+        }
+#pragma unroll
+        for (int jb = 0; jb < TC; jb += 2) {
+          const double2 v = *reinterpret_cast<const double2 *>(ex + c0 + jb);
+          cv[jb] = v.x;
+          cv[jb + 1] = v.y;
+        }
+        const double fp = f[pp % TR];
+        f[pp % TR] = prow ? 0.0 : fp;  // the pivot row is left as it is (its 1/d is applied at the end)
+#pragma unroll
+        for (int ia = 0; ia < TR; ++ia)
+#pragma unroll
+          for (int jb = 0; jb < TC; ++jb) A[ia][jb] = fma(-f[ia], cv[jb], A[ia][jb]);
+        f[pp % TR] = fp;
+#pragma unroll
+        for (int ia = 0; ia < TR; ++ia) {
+          const double cnew = f[ia] * rinv;  // T[i][p] = s_i / sqrt(d)
+          A[ia][pp % TC] = pub ? cnew : A[ia][pp % TC];
+        }
+        A[pp % TR][pp % TC] = (pub && prow) ? -1.0 : A[pp % TR][pp % TC];
+        sc[pp % TR] = prow ? rinv * rinv : sc[pp % TR];
+        rinv = rnext;
+      }
+    }
+
+    // M^{-1}[i][j] = -(1/d_i) A[i][j]
+    bool rlive[TR];
+#pragma unroll
+    for (int ia = 0; ia < TR; ++ia) {
+      const int i = r0 + ia;
+      rlive[ia] = i < k && !empty;
+      const double nsc = -sc[ia];
+#pragma unroll
+      for (int jb = 0; jb < TC; ++jb) A[ia][jb] *= nsc;
+    }
+    {
+      double yv[TC];
+#pragma unroll
+      for (int jb = 0; jb < TC; jb += 2) {
+        const double2 v = *reinterpret_cast<const double2 *>(yb + c0 + jb);
+        yv[jb] = v.x;
+        yv[jb + 1] = v.y;
+      }
+#pragma unroll
+      for (int ia = 0; ia < TR; ++ia) {
+        double zp = 0.0;
+#pragma unroll
+        for (int jb = 0; jb < TC; ++jb) zp = fma(A[ia][jb], yv[jb], zp);
+        zpart[tc * KD + r0 + ia] = rlive[ia] ? zp : 0.0;
+      }
+    }
+    sample_sync<TPS>(bar_id);
+    double zi = 0.0;
+    double r_ld = 0.0, r_quad = 0.0, r_zz = 0.0, r_tp = 0.0;
+    if (t < KD) {
+#pragma unroll
+      for (int c = 0; c < NTC; ++c) zi += zpart[c * KD + t];
+      zb[t] = zi;
+      r_quad = yb[t] * zi;
+      r_zz = zi * zi;
+      if (t < kpiv) r_ld = log(piv[t]);
+    }
+    if (a.mode == 2) {  // t = sigma^2 sum_i (1 - sigma^2 M^{-1}_ii): the diagonal entries this tile holds
+#pragma unroll
+      for (int ia = 0; ia < TR; ++ia)
+#pragma unroll
+        for (int jb = 0; jb < TC; ++jb)
+          if (r0 + ia == c0 + jb && rlive[ia]) r_tp += fma(-s2, A[ia][jb], 1.0);
+    }
+    r_ld = warp_sum(r_ld);
+    r_quad = warp_sum(r_quad);
+    if (a.mode == 2) {
+      r_zz = warp_sum(r_zz);
+      r_tp = warp_sum(r_tp);
+    }
+    if (lane == 0) {
+      red[wis * 4 + 0] = r_ld;
+      red[wis * 4 + 1] = r_quad;
+      red[wis * 4 + 2] = r_zz;
+      red[wis * 4 + 3] = r_tp;
+    }
+    sample_sync<TPS>(bar_id);
+    if (t == 0 && row < a.rows) {
+      double ld = 0.0, quad = 0.0, zz = 0.0, tp = 0.0;
+#pragma unroll
+      for (int u = 0; u < WPS; ++u) {
+        ld += red[u * 4 + 0];
+        quad += red[u * 4 + 1];
+        zz += red[u * 4 + 2];
+        tp += red[u * 4 + 3];
+      }
+      if (a.llk) {
+        double llk = 0.0;
+        if (!empty)
+          llk = -0.5 * (a.nx[row] - quad) / s2 - 0.5 * (ld + 2.0 * ln_sigma * (double)(dn - k)) - 0.5 * LN_2PI * (double)dn;
+        a.llk[row] = llk;
+      }
+      if (a.mode == 2 && a.tn) a.tn[row] = empty ? 0.0 : s2 * tp;
+      if (a.mode == 2 && a.dv) a.dv[row] = empty ? 0.0 : (a.nx[row] - quad) - s2 * zz;  // |R_n|^2, see SolveArgs::dv
+    }
+    if (a.mode != 0) {
+      if (t < kp) {
+        a.YZ[(int64_t)row * kp + t] = zi;
+        if (a.WZ) a.WZ[(int64_t)row * kp + t] = w * zi;
+      }
+      if (a.cov && row < a.rows) {
+#pragma unroll
+        for (int ia = 0; ia < TR; ++ia) {
+          const int i = r0 + ia;
+          if (i < k) {
+            double *cvp = a.cov + (int64_t)row * k * k + (int64_t)i * k;
+#pragma unroll
+            for (int jb = 0; jb < TC; ++jb)
+              if (c0 + jb < k) cvp[c0 + jb] = empty ? (c0 + jb == i ? 1.0 : 0.0) : s2 * A[ia][jb];
+          }
+        }
+      }
+    }
+    if (a.mode == 2) {
+      // all reads of G happened before the elimination barriers; W overwrites it in place (upper triangle, packed)
+      double zc[TC];
+#pragma unroll
+      for (int jb = 0; jb < TC; jb += 2) {
+        const double2 v = *reinterpret_cast<const double2 *>(zb + c0 + jb);
+        zc[jb] = v.x;
+        zc[jb + 1] = v.y;
+      }
+      const double ws2 = empty ? 0.0 : w * s2;
+#pragma unroll
+      for (int ia = 0; ia < TR; ++ia) {
+        const int i = r0 + ia;
+        if (i < k) {
+          double *so = stage + (tri_row_off(i, k) - i);
+          const double wzi = empty ? 0.0 : w * zb[i];
+#pragma unroll
+          for (int jb = 0; jb < TC; ++jb) {
+            const int j = c0 + jb;
+            if (j >= i && j < k) so[j] = fma(wzi, zc[jb], ws2 * A[ia][jb]);
+          }
+        }
+      }
+      sample_sync<TPS>(bar_id);
+      for (int q = t * 2; q < kkp; q += 2 * TPS) {
+        const double2 v = *reinterpret_cast<const double2 *>(stage + q);
+        *reinterpret_cast<double2 *>(gsrc + q) = v;
+        if (a.colmax) {
+          double2 m = *reinterpret_cast<const double2 *>(cmw + q);
+          m.x = fmax(m.x, fabs(v.x));
+          m.y = fmax(m.y, fabs(v.y));
+          *reinterpret_cast<double2 *>(cmw + q) = m;
+        }
+      }
+    }
+    sample_sync<TPS>(bar_id);
+  }
+  if (a.colmax) {
+    __syncthreads();
+    const double *all = smem_reg + (size_t)SPC * per_smp;
+    for (int c = threadIdx.x; c < kkp; c += blockDim.x) {
+      double m = 0.0;
+#pragma unroll
+      for (int j = 0; j < SPC; ++j) m = fmax(m, all[(size_t)j * kkp + c]);
+      if (m > 0.0) atomicMax(a.colmax + c, (unsigned long long)__double_as_longlong(m));
+    }
+  }
+}
+
+template <int KD, int TR, int TC, int MINB>
+static void launch_solve_tile(const Launcher &L, const SolveArgs &a) {
+  using LY = TileLayout<KD, TR, TC>;
+  const size_t smem = (size_t)LY::SPC * (a.s.kkp + LY::FIXED + (a.colmax ? a.s.kkp : 0)) * sizeof(double);
+  static PerDeviceOnce configured;
+  if (configured.need()) {
+    CUDA_CHECK(cudaFuncSetAttribute(solve_tile_kernel<KD, TR, TC, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    110 * 1024));
+  }
+  REQUIRE(smem <= 110 * 1024, "solve_tile: shared memory %zu", smem);
+  int64_t blocks = (a.rows_pad + LY::SPC - 1) / LY::SPC;
+  if (blocks > MINB * (int64_t)L.sms) blocks = MINB * (int64_t)L.sms;
+  solve_tile_kernel<KD, TR, TC, MINB><<<(unsigned)blocks, 256, smem, L.stream>>>(a);
+  CUDA_CHECK(cudaGetLastError());
+  ++*L.launch_counter;
+  L.count(V_SOLVE_TILE);
+}
+
 template <int KPIV, int MINB>
 static void launch_solve_split64_b(const Launcher &L, const SolveArgs &a) {
   const size_t smem = (size_t)2 * (a.s.kkp + 2 * 136 + 64 + 128 + 16 + (a.colmax ? a.s.kkp : 0)) * sizeof(double);
@@ -767,8 +1101,17 @@ void launch_solve(const Launcher &L, const SolveArgs &a) {
   // Round 1 also carried a DMMA-blocked 8 x 8 Gauss-Jordan kernel and a 64-lane variant; both were removed in round 2:
   // the blocked elimination is not symmetric-consistent (tools/solve_accuracy.py: four digits worse on ill-conditioned
   // M_n) and never beat the scalar kernels (profiles/r01_solve_blk_ncu.txt).
+  // Default: lane-owns-a-row kernels up to k = 32, register-tiled sweep for 32 < k <= 64 (measured, profiles/r02_solve_tile.md:
+  // k = 48 -15 %, k = 64 -6 %, k = 32 +8 %).  PPCA_B200_SOLVE=rows / tile forces one family for 16 < k <= 64.
+  static const bool rows_layout = getenv("PPCA_B200_SOLVE") && !strcmp(getenv("PPCA_B200_SOLVE"), "rows");
+  static const bool tile32 = getenv("PPCA_B200_SOLVE") && !strcmp(getenv("PPCA_B200_SOLVE"), "tile");
   if (a.s.k <= 8) launch_solve_reg<8>(L, a);
   else if (a.s.k <= 16) launch_solve_reg<16>(L, a);
+  else if (a.s.k <= 64 && !rows_layout && (a.s.k > 32 || tile32)) {
+    if (a.s.k <= 32) launch_solve_tile<32, 4, 8, 2>(L, a);
+    else if (a.s.k <= 48) launch_solve_tile<48, 6, 6, 2>(L, a);
+    else launch_solve_tile<64, 4, 8, 2>(L, a);
+  }
   else if (a.s.k <= 32) launch_solve_reg<32>(L, a);
   else if (a.s.k <= 40) launch_solve_split64<40>(L, a);
   else if (a.s.k <= 48) launch_solve_split64<48>(L, a);

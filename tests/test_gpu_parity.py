@@ -1034,3 +1034,54 @@ def test_packed_host_streaming_equals_plain_host_streaming(pk, orc, n, d, k, chu
     (Cw, muw, sw), (Cs, mus, ss) = both(orc, orc.iterate, X, w, C0, mu0, s0)
     assert_close(b.transform, Cw, Cs, "C")
     assert_close(b.mean, muw, mus, "mu")
+
+
+# Every per-sample solve kernel and its padding rules: k <= 8 / <= 16 / <= 32 (lane owns a row), 33..48 / 49..64
+# (register-tiled sweep, state padded to 48 / 64 with whole pivot blocks past k skipped), > 64 (generic).
+@pytest.mark.parametrize("k", [3, 8, 9, 16, 17, 20, 24, 25, 31, 32, 33, 40, 41, 47, 48, 49, 55, 56, 57, 63, 64, 65, 70])
+def test_state_size_sweep(pk, orc, k):
+    n, d = 260, 96
+    X, C0, mu0, s0 = _case(n, d, k, 0.3, seed=k, empty_rows=(3,))
+    w = np.random.default_rng(k).random(n) + 0.5
+    ds = pk.Dataset(X, w)
+    ctx = pk.get_context()
+    before = ctx.variant_counts()
+    model = pk.PPCAModel(0.6, C0, mu0)
+    assert rel_err(model.llks(ds), orc.llks(X, C0, mu0, 0.6)) < TOL
+    inf = model.infer(ds)
+    (Z, COV), (Zs, COVs) = both(orc, orc.infer, X, C0, mu0, 0.6)
+    assert_close(inf.states(), Z, Zs, "states")
+    assert_close(np.stack(inf.covariances()), COV, COVs, "covariances")
+    assert np.array_equal(inf.covariances()[3], np.eye(k))
+    new, llk = model._iterate(ds, None)
+    (Cw, muw, sw), (Cs, mus, ss) = both(orc, orc.iterate, X, w, C0, mu0, 0.6)
+    assert abs(llk - orc.llk(X, w, C0, mu0, 0.6)) <= TOL * abs(llk)
+    assert_close(new.transform, Cw, Cs, "C")
+    assert_close(new.mean, muw, mus, "mu")
+    assert_close(new.isotropic_noise ** 2, sw ** 2, ss ** 2, "sigma^2")
+    after = ctx.variant_counts()
+    ran = {name for name, v in after.items() if name.startswith("solve") and v > before.get(name, 0)}
+    want = ("solve_reg8" if k <= 8 else "solve_reg16" if k <= 16 else "solve_reg32" if k <= 32 else
+            "solve_tile" if k <= 64 else "solve_generic")
+    assert ran == {want}, (ran, want)
+
+
+@pytest.mark.parametrize("k", [24, 48, 64])
+def test_tiled_solve_on_ill_conditioned_systems(pk, orc, guard_ctx, k):
+    """One feature in other units makes M_n = small + big v v^T: the register-tiled sweep has to keep the accuracy of an
+    LU / Cholesky evaluation there (tools/solve_accuracy.py), on the FP64 contraction so only the solve is under test."""
+    import dense_ref
+    n, d = 400, 60
+    X, C0, mu0, s0 = _case(n, d, k, 0.3, seed=100 + k)
+    X[:, 7] *= 1e3
+    C0 = C0.copy()
+    C0[7] *= 1e3
+    ds = pk.Dataset(X)
+    guard_ctx.set_gemm("dmma")
+    model = pk.PPCAModel(0.5, C0, mu0)
+    got = model.llks(ds)
+    want = orc.llks(X, C0, mu0, 0.5)
+    dense = np.array([dense_ref.llk_one(X[i], C0, mu0, 0.5) for i in range(n)])
+    floor = _elementwise(dense, want)
+    print(f"k {k}: tiled solve {_elementwise(got, want):.2e} floor {floor:.2e}")
+    assert _elementwise(got, want) < TOL + 4.0 * floor
