@@ -121,6 +121,30 @@ int32_t ppca_b200_ctx_last_profile(ppca_b200_ctx *ctx, double *out8);
 /* Dataset::new / new_with_weights from a host matrix (src/python_bindings.rs:32-64). weights may be NULL (all 1). */
 int32_t ppca_b200_dataset_from_host(ppca_b200_ctx *ctx, const double *x, int64_t n, int32_t d,
                                     const double *weights, ppca_b200_dataset **out);
+/* PPCAMix::sample (mix.rs:124-134): every draw picks a component from exp(log_weights) (WeightedIndex) and samples that
+ * model (sample_one, ppca_model.rs:164-191), on the device.  Cs = the d x k_j transforms back to back, mus = m x d. */
+int32_t ppca_b200_mix_sample(ppca_b200_ctx *ctx, int64_t n, int32_t d, int32_t m, const int32_t *ks, const double *Cs,
+                             const double *mus, const double *sigmas, const double *log_weights, double mask_prob,
+                             uint64_t seed, ppca_b200_dataset **out);
+/* PosteriorSampler / PosteriorSamplerMix (ppca_model.rs:581-626, mix.rs:505-532): one draw per inferred sample,
+ * x = C_j (state + L xi) + mu_j + sigma_j eps with L L^T = covariance (Cholesky on the device; PPCA_ERR_NUMERIC where the
+ * reference's `expect("Cholesky decomposition failed")` fires), component j drawn from the row's posterior probabilities
+ * (m > 1; posteriors is n x m, unnormalised weights are accepted as by WeightedIndex).  states[j]: n x k_j,
+ * covariances[j]: n x k_j x k_j, host arrays as returned by ppca_b200_infer.  Output samples are fully observed. */
+int32_t ppca_b200_posterior_sample(ppca_b200_ctx *ctx, int64_t n, int32_t d, int32_t m, const int32_t *ks, const double *Cs,
+                                   const double *mus, const double *sigmas, const double *posteriors,
+                                   const double *const *states, const double *const *covariances, uint64_t seed,
+                                   ppca_b200_dataset **out);
+/* Dataset::new from a matrix that is ALREADY ON THE DEVICE (DLPack / __cuda_array_interface__ producers): no host round
+ * trip; replaces the element-by-element numpy -> Rust copy of src/python_bindings.rs:41-54 for device-resident callers.
+ * x: row-major, row_stride doubles between rows (>= d); weights: device pointer or NULL; producer_stream: the
+ * cudaStream_t (as void*) the caller last wrote x / weights on, the ingest is ordered after it (NULL = default stream).
+ * The dataset keeps its own packed copy: x may be freed when the call returns. */
+int32_t ppca_b200_dataset_from_device(ppca_b200_ctx *ctx, const double *x, int64_t n, int32_t d, int64_t row_stride,
+                                      const double *weights, void *producer_stream, ppca_b200_dataset **out);
+/* Dataset::numpy (dataset.rs:64-72) into caller-provided device memory: nrows x d doubles, NaN at the masked slots. */
+int32_t ppca_b200_dataset_to_device(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int64_t row0, int64_t nrows,
+                                    double *out_dev);
 /* Synthetic data generated on the device with the reference's sampler semantics
  * (ppca_model.rs:164-191 sample_one): x = C_true xi + sigma_true eps, each entry masked with prob mask_prob.
  * C_true[i,a] ~ Bernoulli(0.1) as in examples/big_toy_model.py:6; n_components > 1 draws each sample
@@ -173,6 +197,12 @@ int32_t ppca_b200_infer(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int32_t
 int32_t ppca_b200_covariance_diagonal(ppca_b200_ctx *ctx, int64_t n, int32_t d, int32_t k, const double *C, double sigma,
                                       const double *covariances, const ppca_b200_dataset *masked_by,
                                       ppca_b200_dataset **out);
+/* InferredMasked::smoothed_covariance (masked_by NULL) / extrapolated_covariance (ppca_model.rs:471-477, 517-534): the full
+ * d x d matrices sigma^2 I + C Sigma_n C^T, computed on the device into out (host, n x d x d); with masked_by the rows and
+ * columns of the dimensions sample n observed are zero (all zeros when nothing is missing).  The reference warns about the
+ * size (:466-470): n d^2 doubles — prefer ppca_b200_covariance_diagonal for anything large. */
+int32_t ppca_b200_covariance_full(ppca_b200_ctx *ctx, int64_t n, int32_t d, int32_t k, const double *C, double sigma,
+                                  const double *covariances, const ppca_b200_dataset *masked_by, double *out);
 /* PPCAModel::smooth (ppca_model.rs:237-244) / ::extrapolate (:254-261): new all-observed dataset,
  * weights carried through. */
 int32_t ppca_b200_smooth(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int32_t k, const double *C,

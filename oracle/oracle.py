@@ -273,3 +273,51 @@ def mix_iterate(X, w, models, logw, prior: Optional[Prior] = None):
         out.append((Cs_o[off:off + d * k].reshape(d, k).copy(), mus_o[j].copy(), float(sig_o[j])))
         off += d * k
     return out, lw_o
+
+
+# ---- per-sample output covariances, restated in numpy in the reference's operation order -----------------
+def smoothed_covariance(Cm, sigma, cov) -> np.ndarray:
+    """InferredMasked::smoothed_covariance (ppca_model.rs:471-477): I sigma^2 + C Sigma C^T."""
+    Cm, cov = _f64(Cm), _f64(cov)
+    d = Cm.shape[0]
+    return np.eye(d) * sigma ** 2 + Cm @ cov @ Cm.T
+
+
+def smoothed_covariance_diagonal(Cm, sigma, cov) -> np.ndarray:
+    """ppca_model.rs:485-508: row-wise dot of (C Sigma) with C, plus sigma^2."""
+    Cm, cov = _f64(Cm), _f64(cov)
+    return np.einsum("ia,ia->i", Cm @ cov, Cm) + sigma ** 2
+
+
+def extrapolated_covariance(Cm, sigma, cov, x) -> np.ndarray:
+    """ppca_model.rs:517-534: the smoothed covariance of the MISSING dimensions expanded back to d x d (zeros on the rows and
+    columns of observed dimensions; all zeros when nothing is missing)."""
+    Cm, cov, x = _f64(Cm), _f64(cov), np.asarray(x, dtype=np.float64)
+    d = Cm.shape[0]
+    neg = ~np.isfinite(x)
+    out = np.zeros((d, d))
+    if not neg.any():
+        return out
+    sub = Cm[neg]
+    out[np.ix_(neg, neg)] = np.eye(sub.shape[0]) * sigma ** 2 + sub @ cov @ sub.T
+    return out
+
+
+def extrapolated_covariance_diagonal(Cm, sigma, cov, x) -> np.ndarray:
+    """ppca_model.rs:542-577."""
+    Cm, cov, x = _f64(Cm), _f64(cov), np.asarray(x, dtype=np.float64)
+    neg = ~np.isfinite(x)
+    out = np.zeros(Cm.shape[0])
+    if neg.any():
+        sub = Cm[neg]
+        out[neg] = np.einsum("ia,ia->i", sub @ cov, sub) + sigma ** 2
+    return out
+
+
+def mix_covariance(post, means, covs) -> np.ndarray:
+    """InferredMaskedMix::smoothed_covariance / extrapolated_covariance (mix.rs:422-437, 466-481) for ONE sample:
+    sum_j p_j (cov_j + (m_j - mean)(m_j - mean)^T), mean = sum_j p_j m_j; `covs` are the components' SMOOTHED covariances in
+    both forms (mix.rs:474), `means` their smoothed (or extrapolated) outputs."""
+    post = np.asarray(post, dtype=np.float64)
+    mean = sum(p * m for p, m in zip(post, means))
+    return sum(p * (c + np.outer(m - mean, m - mean)) for p, m, c in zip(post, means, covs))

@@ -63,6 +63,15 @@ _PROTOTYPES = {
     "ppca_b200_ctx_set_profiling": (C.c_int32, [c_ctx_p, C.c_int32]),
     "ppca_b200_ctx_last_profile": (C.c_int32, [c_ctx_p, c_dp]),
     "ppca_b200_dataset_from_host": (C.c_int32, [c_ctx_p, c_dp, C.c_int64, C.c_int32, c_dp, C.POINTER(c_ds_p)]),
+    "ppca_b200_mix_sample": (
+        C.c_int32, [c_ctx_p, C.c_int64, C.c_int32, C.c_int32, c_ip, c_dp, c_dp, c_dp, c_dp, C.c_double, C.c_uint64,
+                    C.POINTER(c_ds_p)]),
+    "ppca_b200_posterior_sample": (
+        C.c_int32, [c_ctx_p, C.c_int64, C.c_int32, C.c_int32, c_ip, c_dp, c_dp, c_dp, c_dp, C.POINTER(c_dp),
+                    C.POINTER(c_dp), C.c_uint64, C.POINTER(c_ds_p)]),
+    "ppca_b200_dataset_from_device": (
+        C.c_int32, [c_ctx_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.POINTER(c_ds_p)]),
+    "ppca_b200_dataset_to_device": (C.c_int32, [c_ctx_p, c_ds_p, C.c_int64, C.c_int64, C.c_void_p]),
     "ppca_b200_dataset_synthetic": (
         C.c_int32,
         [c_ctx_p, C.c_int64, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_uint64, C.POINTER(c_ds_p)],
@@ -83,6 +92,7 @@ _PROTOTYPES = {
     "ppca_b200_llks": (C.c_int32, [c_ctx_p, c_ds_p, C.c_int32, c_dp, c_dp, C.c_double, c_dp]),
     "ppca_b200_llk": (C.c_int32, [c_ctx_p, c_ds_p, C.c_int32, c_dp, c_dp, C.c_double, c_dp]),
     "ppca_b200_infer": (C.c_int32, [c_ctx_p, c_ds_p, C.c_int32, c_dp, c_dp, C.c_double, c_dp, c_dp]),
+    "ppca_b200_covariance_full": (C.c_int32, [c_ctx_p, C.c_int64, C.c_int32, C.c_int32, c_dp, C.c_double, c_dp, c_ds_p, c_dp]),
     "ppca_b200_covariance_diagonal": (
         C.c_int32,
         [c_ctx_p, C.c_int64, C.c_int32, C.c_int32, c_dp, C.c_double, c_dp, c_ds_p, C.POINTER(c_ds_p)],

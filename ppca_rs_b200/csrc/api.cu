@@ -1269,6 +1269,117 @@ int32_t ppca_b200_dataset_from_host(ppca_b200_ctx *ctx, const double *x, int64_t
   });
 }
 
+// smallest weight of a device array, NaN -> -1 (mixture EM rejects non-positive weights, mix.rs:304-309)
+__global__ void min_weight_kernel(const double *__restrict__ w, int64_t n, unsigned long long *out) {
+  double mn = __longlong_as_double(0x7ff0000000000000LL);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double v = w[i];
+    mn = (v != v) ? -1.0 : fmin(mn, v);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+  // order-preserving map of a double onto an unsigned integer so atomicMin works for negative values too
+  if ((threadIdx.x & 31) == 0) {
+    long long b = __double_as_longlong(mn);
+    unsigned long long key = b < 0 ? ~(unsigned long long)b : ((unsigned long long)b | 0x8000000000000000ULL);
+    atomicMin(out, key);
+  }
+}
+
+static double device_min_weight(ppca_b200_ctx *ctx, const double *w_dev, int64_t n) {
+  if (n <= 0) return std::numeric_limits<double>::infinity();
+  DevBuf<unsigned long long> key;
+  key.alloc(1);
+  CUDA_CHECK(cudaMemsetAsync(key.p, 0xff, sizeof(unsigned long long), ctx->stream));
+  const int64_t want = (n + 255) / 256;
+  const int blocks = (int)std::min<int64_t>(want, (int64_t)ctx->sms * 8);
+  min_weight_kernel<<<blocks, 256, 0, ctx->stream>>>(w_dev, n, key.p);
+  CUDA_CHECK(cudaGetLastError());
+  ++ctx->launches;
+  unsigned long long h = 0;
+  CUDA_CHECK(cudaMemcpyAsync(&h, key.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  const unsigned long long bits = (h & 0x8000000000000000ULL) ? (h & 0x7fffffffffffffffULL) : ~h;
+  double v;
+  memcpy(&v, &bits, sizeof(v));
+  return v;
+}
+
+// Dataset::new from a matrix that already lives on the device (zero-copy ingestion for DLPack / __cuda_array_interface__
+// producers; the reference copies numpy -> Rust element by element, src/python_bindings.rs:41-54).  `x` is row-major with
+// `row_stride` doubles between rows; `producer_stream` is the stream the caller last wrote x / weights on (the ingest is
+// ordered after it by an event; 0 = legacy default stream).
+int32_t ppca_b200_dataset_from_device(ppca_b200_ctx *ctx, const double *x, int64_t n, int32_t d, int64_t row_stride,
+                                      const double *weights, void *producer_stream, ppca_b200_dataset **out) {
+  return guarded([&] {
+    REQUIRE(ctx != nullptr && out != nullptr, "null argument");
+    REQUIRE(n >= 0 && d >= 1, "bad dataset shape %lld x %d", (long long)n, d);
+    REQUIRE(n == 0 || x != nullptr, "null data");
+    REQUIRE(row_stride >= d, "row stride %lld is shorter than a row of %d values", (long long)row_stride, d);
+    DeviceGuard g(ctx->device);
+    auto on_device = [&](const void *p, const char *what) {
+      cudaPointerAttributes pa;
+      const cudaError_t e = cudaPointerGetAttributes(&pa, p);
+      if (e != cudaSuccess) cudaGetLastError();
+      REQUIRE(e == cudaSuccess && (pa.type == cudaMemoryTypeDevice || pa.type == cudaMemoryTypeManaged),
+              "%s is not a device pointer", what);
+      REQUIRE(pa.type == cudaMemoryTypeManaged || pa.device == ctx->device, "%s lives on device %d, the context on %d", what,
+              pa.device, ctx->device);
+    };
+    if (n > 0) on_device(x, "data");
+    if (n > 0 && weights) on_device(weights, "weights");
+    {  // order the ingest after the producer's work
+      cudaEvent_t ev;
+      CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      cudaError_t e = cudaEventRecord(ev, (cudaStream_t)producer_stream);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ev, 0);
+      cudaEventDestroy(ev);
+      CUDA_CHECK(e);
+    }
+    auto st = make_store(ctx, n, d);
+    if (n > 0) {
+      if (row_stride == d) {
+        launch_ingest(ctx->L(), x, n, d, 0, *st);
+      } else {  // strided rows: compact block by block, then ingest
+        const int64_t rows_per = std::max<int64_t>(1, ((int64_t)64 << 20) / ((int64_t)d * 8));
+        DevBuf<double> buf;
+        buf.alloc((size_t)std::min<int64_t>(rows_per, n) * d);
+        for (int64_t r0 = 0; r0 < n; r0 += rows_per) {
+          const int64_t rows = std::min<int64_t>(rows_per, n - r0);
+          CUDA_CHECK(cudaMemcpy2DAsync(buf.p, sizeof(double) * d, x + r0 * row_stride, sizeof(double) * row_stride,
+                                       sizeof(double) * d, (size_t)rows, cudaMemcpyDeviceToDevice, ctx->stream));
+          launch_ingest(ctx->L(), buf.p, rows, d, r0, *st);
+        }
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));  // buf is released at the end of this scope
+      }
+      launch_transpose_mask(ctx->L(), *st);
+    }
+    std::unique_ptr<ppca_b200_dataset> nd(make_dataset(ctx, st, nullptr));
+    if (n > 0 && weights) {
+      CUDA_CHECK(cudaMemcpyAsync(nd->w.p, weights, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+      nd->min_w = device_min_weight(ctx, nd->w.p, n);
+    }
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    *out = nd.release();
+  });
+}
+
+// Dataset::numpy into caller-provided DEVICE memory (n x d doubles, row-major, NaN at the masked slots): the export side of
+// the zero-copy path.  Ordered on the context's stream; returns after the copy has completed.
+int32_t ppca_b200_dataset_to_device(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int64_t row0, int64_t nrows,
+                                    double *out_dev) {
+  return guarded([&] {
+    check_ds(ctx, ds);
+    const SampleStore &st = *ds->store;
+    REQUIRE(row0 >= 0 && nrows >= 0 && row0 + nrows <= st.n, "row range out of bounds");
+    if (nrows == 0) return;
+    REQUIRE(out_dev != nullptr, "null output");
+    DeviceGuard g(ctx->device);
+    launch_export(ctx->L(), st, row0, nrows, out_dev);
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  });
+}
+
 int32_t ppca_b200_dataset_synthetic(ppca_b200_ctx *ctx, int64_t n, int32_t d, int32_t k_true, double sigma_true,
                                     double mask_prob, int32_t n_components, uint64_t seed, ppca_b200_dataset **out) {
   return guarded([&] {
@@ -1308,6 +1419,122 @@ int32_t ppca_b200_model_sample(ppca_b200_ctx *ctx, int64_t n, int32_t d, int32_t
     }
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     *out = make_dataset(ctx, st, nullptr);
+  });
+}
+
+// Shared body of ppca_b200_mix_sample / ppca_b200_posterior_sample: stage the models, run sample_general_kernel.
+static void sample_general_impl(ppca_b200_ctx *ctx, int64_t n, int32_t d, int32_t m, const int32_t *ks, const double *Cs,
+                                const double *mus, const double *sigmas, const double *cdf_host, const double *post_host,
+                                const double *const *states_host, const double *const *covs_host, double mask_prob,
+                                uint64_t seed, ppca_b200_dataset **out) {
+  REQUIRE(ctx != nullptr && out != nullptr && ks && Cs && mus && sigmas, "null argument");
+  REQUIRE(n >= 0 && d >= 1 && m >= 1, "bad sample shape");
+  REQUIRE(mask_prob >= 0.0 && mask_prob <= 1.0, "invalid mask probability");  // ppca_model.rs:165
+  int kmax = 1;
+  std::vector<int64_t> coff((size_t)m);
+  int64_t ctot = 0;
+  for (int j = 0; j < m; ++j) {
+    REQUIRE(ks[j] >= 1, "state_size must be >= 1 (got %d)", ks[j]);
+    REQUIRE(sigmas[j] >= 0.0 && std::isfinite(sigmas[j]), "isotropic_noise must be finite and non-negative");
+    kmax = std::max(kmax, (int)ks[j]);
+    coff[j] = ctot;
+    ctot += (int64_t)d * ks[j];
+  }
+  const bool post_mode = states_host != nullptr;
+  REQUIRE(!post_mode || covs_host != nullptr, "posterior sampling needs states and covariances");
+  DeviceGuard g(ctx->device);
+  auto st = make_store(ctx, n, d);
+  if (n > 0) {
+    DevBuf<double> dC, dmu, dsig, dcdf, dpost;
+    DevBuf<int> dks, dfail;
+    DevBuf<int64_t> dcoff;
+    DevBuf<const double *> dstates, dcovs;
+    std::vector<std::unique_ptr<DevBuf<double>>> sbuf, cbuf;
+    auto up = [&](auto &buf, const auto *src, size_t count) {
+      buf.alloc(count);
+      CUDA_CHECK(cudaMemcpyAsync(buf.p, src, sizeof(*src) * count, cudaMemcpyHostToDevice, ctx->stream));
+    };
+    up(dC, Cs, (size_t)ctot);
+    up(dmu, mus, (size_t)m * d);
+    up(dsig, sigmas, (size_t)m);
+    up(dks, ks, (size_t)m);
+    up(dcoff, coff.data(), (size_t)m);
+    if (cdf_host) up(dcdf, cdf_host, (size_t)m);
+    if (post_host) up(dpost, post_host, (size_t)n * m);
+    std::vector<const double *> sp((size_t)m, nullptr), cp((size_t)m, nullptr);
+    if (post_mode) {
+      for (int j = 0; j < m; ++j) {
+        REQUIRE(states_host[j] && covs_host[j], "null states / covariances of component %d", j);
+        sbuf.emplace_back(new DevBuf<double>());
+        cbuf.emplace_back(new DevBuf<double>());
+        up(*sbuf[j], states_host[j], (size_t)n * ks[j]);
+        up(*cbuf[j], covs_host[j], (size_t)n * ks[j] * ks[j]);
+        sp[j] = sbuf[j]->p;
+        cp[j] = cbuf[j]->p;
+      }
+      up(dstates, sp.data(), (size_t)m);
+      up(dcovs, cp.data(), (size_t)m);
+    }
+    dfail.alloc(1);
+    CUDA_CHECK(cudaMemsetAsync(dfail.p, 0, sizeof(int), ctx->stream));
+    SamplerArgs a;
+    a.n = n;
+    a.d = d;
+    a.m = m;
+    a.kmax = kmax;
+    a.ks = dks.p;
+    a.coff = dcoff.p;
+    a.Cs = dC.p;
+    a.mus = dmu.p;
+    a.sigmas = dsig.p;
+    a.cdf = cdf_host ? dcdf.p : nullptr;
+    a.post = post_host ? dpost.p : nullptr;
+    a.post_mode = post_mode ? 1 : 0;
+    a.states = post_mode ? dstates.p : nullptr;
+    a.covs = post_mode ? dcovs.p : nullptr;
+    a.mask_prob = mask_prob;
+    a.seed = seed;
+    a.fail = dfail.p;
+    launch_sample_general(ctx->L(), *st, a);
+    launch_transpose_mask(ctx->L(), *st);
+    int fail = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&fail, dfail.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));  // the staging buffers above are released on return
+    if (fail) PPCA_THROW(PPCA_ERR_NUMERIC, "Cholesky decomposition failed (ppca_model.rs:582-586)");
+  }
+  *out = make_dataset(ctx, st, nullptr);
+}
+
+int32_t ppca_b200_mix_sample(ppca_b200_ctx *ctx, int64_t n, int32_t d, int32_t m, const int32_t *ks, const double *Cs,
+                             const double *mus, const double *sigmas, const double *log_weights, double mask_prob,
+                             uint64_t seed, ppca_b200_dataset **out) {
+  return guarded([&] {
+    REQUIRE(log_weights != nullptr && m >= 1, "null mixture parameters");
+    // WeightedIndex over exp(log_weights) (mix.rs:124-126): cumulative distribution, last entry exactly 1
+    std::vector<double> cdf((size_t)m);
+    double mx = log_weights[0], tot = 0.0;
+    for (int j = 1; j < m; ++j) mx = std::max(mx, log_weights[j]);
+    for (int j = 0; j < m; ++j) tot += std::exp(log_weights[j] - mx);
+    REQUIRE(tot > 0.0 && std::isfinite(tot), "can create WeightedIndex from distribution (mix.rs:125)");
+    double acc = 0.0;
+    for (int j = 0; j < m; ++j) {
+      acc += std::exp(log_weights[j] - mx) / tot;
+      cdf[j] = acc;
+    }
+    cdf[(size_t)m - 1] = 1.0;
+    sample_general_impl(ctx, n, d, m, ks, Cs, mus, sigmas, cdf.data(), nullptr, nullptr, nullptr, mask_prob, seed, out);
+  });
+}
+
+int32_t ppca_b200_posterior_sample(ppca_b200_ctx *ctx, int64_t n, int32_t d, int32_t m, const int32_t *ks, const double *Cs,
+                                   const double *mus, const double *sigmas, const double *posteriors,
+                                   const double *const *states, const double *const *covariances, uint64_t seed,
+                                   ppca_b200_dataset **out) {
+  return guarded([&] {
+    REQUIRE(states != nullptr && covariances != nullptr, "null states / covariances");
+    REQUIRE(m == 1 || posteriors != nullptr, "a mixture posterior sampler needs the posterior probabilities");
+    sample_general_impl(ctx, n, d, m, ks, Cs, mus, sigmas, nullptr, m > 1 ? posteriors : nullptr, states, covariances, 0.0,
+                        seed, out);
   });
 }
 
@@ -1894,6 +2121,100 @@ int32_t ppca_b200_reconstruct_host(ppca_b200_ctx *ctx, const double *x, int64_t 
 }
 
 // ---- covariance diagonals ------------------------------------------------------------------------------------------
+// InferredMasked::smoothed_covariance / extrapolated_covariance (ppca_model.rs:471-477, 517-534): per sample the full
+// d x d matrix  sigma^2 I + C Sigma_n C^T, with the rows and columns of the dimensions the sample observed zeroed when a
+// dataset is given (negative.expand_matrix; all zeros when nothing is missing).  One CTA per (sample, 32 x 32 output tile):
+// T = C_tile Sigma_n (32 x k) and the column tile of C sit in shared memory with an odd pitch.
+__global__ void __launch_bounds__(256) cov_full_kernel(const double *__restrict__ C, int d, int k, double s2,
+                                                       const double *__restrict__ covs, int64_t rows,
+                                                       const uint32_t *__restrict__ mask, int dw, int64_t mask_row0,
+                                                       double *__restrict__ out) {
+  extern __shared__ double sm_cov[];
+  const int pitch = k | 1;
+  double *T = sm_cov;               // 32 x pitch
+  double *Cj = T + 32 * pitch;      // 32 x pitch
+  double *Sg = Cj + 32 * pitch;     // k x k
+  const int tid = threadIdx.x, lane = tid & 31, wi = tid >> 5;
+  const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+  for (int64_t row = blockIdx.z; row < rows; row += gridDim.z) {
+    const double *S = covs + row * (int64_t)k * k;
+    for (int q = tid; q < k * k; q += 256) Sg[q] = S[q];
+    for (int q = tid; q < 32 * k; q += 256) {
+      const int r = q / k, a = q % k;
+      Cj[r * pitch + a] = (j0 + r < d) ? C[(int64_t)(j0 + r) * k + a] : 0.0;
+    }
+    __syncthreads();
+    for (int q = tid; q < 32 * k; q += 256) {  // T[r][b] = sum_a C[i0 + r][a] Sigma[a][b]
+      const int r = q / k, b = q % k;
+      double acc = 0.0;
+      if (i0 + r < d) {
+        const double *ci = C + (int64_t)(i0 + r) * k;
+        for (int a = 0; a < k; ++a) acc = fma(ci[a], Sg[a * k + b], acc);
+      }
+      T[r * pitch + b] = acc;
+    }
+    __syncthreads();
+    const int j = j0 + lane;
+    bool obs_j = false;
+    if (mask && j < d) obs_j = (mask[(mask_row0 + row) * dw + (j >> 5)] >> (j & 31)) & 1u;
+    for (int r = wi; r < 32; r += 8) {
+      const int i = i0 + r;
+      if (i >= d || j >= d) continue;
+      double acc = (i == j) ? s2 : 0.0;
+      for (int a = 0; a < k; ++a) acc = fma(T[r * pitch + a], Cj[lane * pitch + a], acc);
+      if (mask) {
+        const bool obs_i = (mask[(mask_row0 + row) * dw + (i >> 5)] >> (i & 31)) & 1u;
+        if (obs_i || obs_j) acc = 0.0;
+      }
+      out[(row * d + i) * (int64_t)d + j] = acc;
+    }
+    __syncthreads();
+  }
+}
+
+int32_t ppca_b200_covariance_full(ppca_b200_ctx *ctx, int64_t n, int32_t d, int32_t k, const double *C, double sigma,
+                                  const double *covariances, const ppca_b200_dataset *masked_by, double *out) {
+  return guarded([&] {
+    REQUIRE(ctx != nullptr && C != nullptr, "null argument");
+    REQUIRE(n >= 0 && d >= 1 && k >= 1, "bad shape");
+    REQUIRE(n == 0 || (covariances != nullptr && out != nullptr), "null covariances / output");
+    if (masked_by) {
+      check_ds(ctx, masked_by);
+      REQUIRE(masked_by->store->n == n && masked_by->store->d == d, "dataset shape does not match the inferred batch");
+    }
+    if (n == 0) return;
+    DeviceGuard g(ctx->device);
+    const size_t smem = sizeof(double) * ((size_t)64 * (k | 1) + (size_t)k * k);
+    REQUIRE(smem <= 200 * 1024, "state_size %d too large for the full-covariance kernel", k);
+    static PerDeviceOnce configured;
+    if (configured.need())
+      CUDA_CHECK(cudaFuncSetAttribute(cov_full_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    DevBuf<double> Cd, covd, outd;
+    Cd.alloc((size_t)d * k);
+    CUDA_CHECK(cudaMemcpyAsync(Cd.p, C, sizeof(double) * d * k, cudaMemcpyHostToDevice, ctx->stream));
+    // rows per pass: result staging <= 512 MiB
+    int64_t rows_per = std::max<int64_t>(1, ((int64_t)512 << 20) / ((int64_t)d * d * 8));
+    rows_per = std::min<int64_t>(rows_per, n);
+    covd.alloc((size_t)rows_per * k * k);
+    outd.alloc((size_t)rows_per * d * d);
+    const int tiles = (d + 31) / 32;
+    for (int64_t r0 = 0; r0 < n; r0 += rows_per) {
+      const int64_t rows = std::min<int64_t>(rows_per, n - r0);
+      CUDA_CHECK(cudaMemcpyAsync(covd.p, covariances + r0 * k * k, sizeof(double) * rows * k * k, cudaMemcpyHostToDevice,
+                                 ctx->stream));
+      dim3 grid((unsigned)tiles, (unsigned)tiles, (unsigned)std::min<int64_t>(rows, 32768));
+      cov_full_kernel<<<grid, 256, smem, ctx->stream>>>(Cd.p, d, k, sigma * sigma, covd.p, rows,
+                                                        masked_by ? masked_by->store->mask.p : nullptr,
+                                                        masked_by ? masked_by->store->dw : 0, r0, outd.p);
+      CUDA_CHECK(cudaGetLastError());
+      ++ctx->launches;
+      CUDA_CHECK(cudaMemcpyAsync(out + r0 * d * d, outd.p, sizeof(double) * rows * d * d, cudaMemcpyDeviceToHost,
+                                 ctx->stream));
+      CUDA_CHECK(cudaStreamSynchronize(ctx->stream));  // covd / outd are reused by the next pass
+    }
+  });
+}
+
 int32_t ppca_b200_covariance_diagonal(ppca_b200_ctx *ctx, int64_t n, int32_t d, int32_t k, const double *C, double sigma,
                                       const double *covariances, const ppca_b200_dataset *masked_by,
                                       ppca_b200_dataset **out) {

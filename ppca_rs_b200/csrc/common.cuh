@@ -217,6 +217,23 @@ void launch_export(const Launcher &L, const SampleStore &st, int64_t row0, int64
 void launch_empty_dims(const Launcher &L, const SampleStore &st, uint8_t *out_dev);
 void launch_synthetic(const Launcher &L, SampleStore &st, int k_true, double sigma_true, double mask_prob,
                       int n_components, uint64_t seed);
+// mixture / posterior sampling (sample_general_kernel, ingest.cu); every pointer is a device pointer
+struct SamplerArgs {
+  int64_t n;
+  int d, m, kmax;
+  const int *ks;            // m
+  const int64_t *coff;      // m : offset of C_j in Cs
+  const double *Cs, *mus, *sigmas;
+  const double *cdf;        // m cumulative mixture weights (prior sampling of a mixture), or null
+  const double *post;       // n x m posterior probabilities (posterior sampling of a mixture), or null
+  int post_mode;            // 0: z ~ N(0, I)   1: z ~ N(state_n, covariance_n)
+  const double *const *states;  // m device pointers, n x k_j   (post_mode)
+  const double *const *covs;    // m device pointers, n x k_j x k_j
+  double mask_prob;
+  uint64_t seed;
+  int *fail;                // set to 1 when a covariance is not positive definite
+};
+void launch_sample_general(const Launcher &L, SampleStore &st, const SamplerArgs &a);
 void launch_model_sample(const Launcher &L, SampleStore &st, int k, const double *C_dev, const double *mu_dev,
                          double sigma, double mask_prob, uint64_t seed);
 void launch_copy_rows(const Launcher &L, const SampleStore &src, int64_t src_row0, int64_t nrows, SampleStore &dst,

@@ -261,4 +261,124 @@ void launch_model_sample(const Launcher &L, SampleStore &st, int k, const double
   ++*L.launch_counter;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Mixture / posterior sampling (mix.rs:124-134 PPCAMix::sample; ppca_model.rs:581-626 PosteriorSampler;
+// mix.rs:505-532 PosteriorSamplerMix).  One warp per output sample:
+//   1. component j: inverse-CDF draw from the mixture weights (cdf, shared by all rows) or from this row's
+//      posterior probabilities (post, n x m; normalised here, WeightedIndex semantics); m == 1 -> 0
+//   2. state: xi ~ N(0, I_k) (prior sampling) or z = state_n + L_n xi with L_n L_n^T = covariance_n, the Cholesky
+//      factor formed here in shared memory (posterior sampling)
+//   3. x = C_j z + mu_j + sigma_j eps, each entry masked with probability mask_prob
+// A non-positive Cholesky pivot raises *fail (the reference `expect`s "Cholesky decomposition failed").
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sample_general_kernel(SamplerArgs a, double *X, int ldx, uint32_t *mask, int dw,
+                                                             int *dn) {
+  extern __shared__ double smem_sampler[];
+  const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+  const int64_t row = blockIdx.x * (int64_t)(blockDim.x >> 5) + wi;
+  if (row >= a.n) return;
+  const int kmax = a.kmax;
+  double *z = smem_sampler + (size_t)wi * (kmax + (a.post_mode ? kmax * kmax + kmax : 0));
+  double *xi = z + kmax;         // posterior mode only
+  double *Lm = xi + kmax;        // kmax x kmax, posterior mode only
+  // 1. component
+  int comp = 0;
+  if (a.m > 1) {
+    const double u = rng_uniform(a.seed, 4, (uint64_t)row);
+    if (a.post) {
+      const double *pr = a.post + row * a.m;
+      double tot = 0.0;
+      for (int j = 0; j < a.m; ++j) tot += pr[j];
+      double acc = 0.0;
+      comp = a.m - 1;
+      for (int j = 0; j < a.m; ++j) {
+        acc += pr[j];
+        if (u * tot < acc) {
+          comp = j;
+          break;
+        }
+      }
+    } else {
+      comp = a.m - 1;
+      for (int j = 0; j < a.m; ++j)
+        if (u < a.cdf[j]) {
+          comp = j;
+          break;
+        }
+    }
+  }
+  const int k = a.ks[comp];
+  const double *Cj = a.Cs + a.coff[comp];
+  const double *mj = a.mus + (int64_t)comp * a.d;
+  const double sigma = a.sigmas[comp];
+  // 2. state
+  if (!a.post_mode) {
+    for (int q = lane; q < k; q += 32) z[q] = rng_normal(a.seed, 3, (uint64_t)row * kmax + q);
+  } else {
+    const double *cov = a.covs[comp] + row * (int64_t)k * k;
+    const double *stt = a.states[comp] + row * (int64_t)k;
+    for (int q = lane; q < k * k; q += 32) Lm[q] = cov[q];
+    for (int q = lane; q < k; q += 32) xi[q] = rng_normal(a.seed, 3, (uint64_t)row * kmax + q);
+    __syncwarp();
+    for (int p = 0; p < k; ++p) {  // right-looking Cholesky, lower triangle in place
+      const double dpp = Lm[p * k + p];
+      if (!(dpp > 0.0)) {
+        if (lane == 0) atomicExch(a.fail, 1);
+        break;
+      }
+      const double inv = 1.0 / sqrt(dpp);
+      __syncwarp();
+      for (int r = p + lane; r < k; r += 32) Lm[r * k + p] *= inv;  // the diagonal becomes sqrt(d)
+      __syncwarp();
+      for (int c = p + 1; c < k; ++c) {
+        const double lcp = Lm[c * k + p];
+        for (int r = c + lane; r < k; r += 32) Lm[r * k + c] = fma(-Lm[r * k + p], lcp, Lm[r * k + c]);
+      }
+      __syncwarp();
+    }
+    for (int q = lane; q < k; q += 32) {
+      double acc = stt[q];
+      for (int c = 0; c <= q; ++c) acc = fma(Lm[q * k + c], xi[c], acc);
+      z[q] = acc;
+    }
+  }
+  __syncwarp();
+  // 3. outputs
+  int count = 0;
+  for (int j = 0; j < dw; ++j) {
+    const int i = 32 * j + lane;
+    double x = 0.0;
+    bool obs = false;
+    if (i < a.d) {
+      const double *crow = Cj + (int64_t)i * k;
+      double acc = mj[i];
+      for (int q = 0; q < k; ++q) acc = fma(crow[q], z[q], acc);
+      x = acc + sigma * rng_normal(a.seed, 5, (uint64_t)row * a.d + i);
+      obs = !(rng_uniform(a.seed, 6, (uint64_t)row * a.d + i) < a.mask_prob);
+    }
+    const uint32_t word = __ballot_sync(0xffffffffu, obs);
+    if (i < ldx) X[row * ldx + i] = obs ? x : 0.0;
+    if (lane == 0) mask[row * dw + j] = word;
+    count += __popc(word);
+  }
+  if (lane == 0) dn[row] = count;
+}
+
+void launch_sample_general(const Launcher &L, SampleStore &st, const SamplerArgs &a) {
+  if (st.n <= 0) return;
+  const size_t per_warp = sizeof(double) * (a.kmax + (a.post_mode ? (size_t)a.kmax * a.kmax + a.kmax : 0));
+  int warps = 8;
+  while (warps > 1 && per_warp * warps > 96 * 1024) warps >>= 1;
+  REQUIRE(per_warp * warps <= 200 * 1024, "state_size %d too large for the sampler kernel", a.kmax);
+  const size_t smem = per_warp * warps;
+  static PerDeviceOnce configured;
+  if (configured.need())
+    CUDA_CHECK(cudaFuncSetAttribute(sample_general_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  const int64_t blocks = (st.n + warps - 1) / warps;
+  sample_general_kernel<<<(unsigned)blocks, warps * 32, smem, L.stream>>>(a, st.X.p, st.ldx, st.mask.p, st.dw, st.dn.p);
+  CUDA_CHECK(cudaGetLastError());
+  ++*L.launch_counter;
+}
+
 }  // namespace ppca

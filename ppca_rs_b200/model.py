@@ -38,6 +38,52 @@ def _as_matrix(x, what: str) -> np.ndarray:
 # =================================================================================================
 # Dataset  (src/python_bindings.rs:28-166 ; ppca/src/dataset.rs)
 # =================================================================================================
+def _device_view(obj, ndim: int, what: str):
+    """(pointer, shape, strides in elements, keep-alive) of a float64 device array given through
+    `__cuda_array_interface__` (torch, CuPy, Numba) or, failing that, `__dlpack__` (imported with torch)."""
+    cai = getattr(obj, "__cuda_array_interface__", None)
+    keep = obj
+    if cai is None:
+        if not hasattr(obj, "__dlpack__"):
+            raise TypeError(f"{what} exposes neither __cuda_array_interface__ nor __dlpack__")
+        import torch
+        keep = torch.from_dlpack(obj)
+        if not keep.is_cuda:
+            raise ValueError(f"{what} is not on a CUDA device")
+        cai = keep.__cuda_array_interface__
+    if cai["typestr"] not in ("<f8", "=f8", "|f8"):
+        raise TypeError(f"{what} must be float64 (got typestr {cai['typestr']})")
+    shape = tuple(int(v) for v in cai["shape"])
+    if len(shape) != ndim:
+        raise ValueError(f"{what} must have {ndim} dimension(s), got shape {shape}")
+    strides = cai.get("strides")
+    if strides is None:
+        strides, acc = [], 1
+        for v in reversed(shape):
+            strides.append(acc)
+            acc *= max(v, 1)
+        strides = tuple(reversed(strides))
+    else:
+        if any(int(v) % 8 for v in strides):
+            raise ValueError(f"{what} has strides that are not multiples of 8 bytes")
+        strides = tuple(int(v) // 8 for v in strides)
+    ptr = int(cai["data"][0]) if cai["data"][0] is not None else 0
+    return C.c_void_p(ptr), shape, strides, keep
+
+
+def _producer_stream():
+    """The CUDA stream the caller's framework is currently enqueueing on (torch's current stream when torch is loaded and
+    CUDA is up; the legacy default stream otherwise): device ingestion is ordered after it."""
+    import sys
+    torch = sys.modules.get("torch")
+    try:
+        if torch is not None and torch.cuda.is_available() and torch.cuda.is_initialized():
+            return C.c_void_p(int(torch.cuda.current_stream().cuda_stream))
+    except Exception:
+        pass
+    return C.c_void_p(0)
+
+
 class Dataset:
     """A dataset of samples with potentially missing values, resident on the GPU.
 
@@ -77,6 +123,54 @@ class Dataset:
         nat.check(nat.lib().ppca_b200_dataset_synthetic(ctx.handle, int(n), int(d), int(k_true), float(sigma_true),
                                                         float(mask_prob), int(n_components), int(seed), C.byref(h)))
         return cls._wrap(h, ctx)
+
+    @classmethod
+    def from_device(cls, array, weights=None, ctx: Optional[nat.Context] = None) -> "Dataset":
+        """Zero-copy ingestion of a matrix that already lives on the GPU (ppca_b200_dataset_from_device): `array` (and
+        `weights`) is anything exposing `__cuda_array_interface__` or `__dlpack__` — a torch.Tensor, a CuPy / Numba array —
+        of dtype float64 and shape (n_samples, n_features), rows contiguous (any row stride).  Non-finite entries are the
+        missing values, exactly as in `Dataset(ndarray)`; nothing crosses the PCIe bus.  The reference has no such path
+        (it copies numpy -> Rust element by element, src/python_bindings.rs:41-54)."""
+        ctx = ctx or nat.get_context()
+        ptr, shape, strides, keep = _device_view(array, 2, "array")
+        n, d = shape
+        if strides[1] != 1 and n * d > 0:
+            raise ValueError("array rows must be contiguous (unit stride along the feature axis)")
+        if d < 1:
+            raise ValueError("dataset needs at least one output dimension")
+        row_stride = strides[0] if n > 1 else max(d, strides[0])
+        if row_stride < d:
+            raise ValueError("array rows overlap (row stride shorter than a row)")
+        wptr = None
+        if weights is not None:
+            wptr, wshape, wstrides, wkeep = _device_view(weights, 1, "weights")
+            if wshape[0] != n:  # dataset.rs:163
+                raise ValueError(f"weights has {wshape[0]} entries for {n} samples")
+            if wstrides[0] != 1 and n > 1:
+                raise ValueError("weights must be contiguous")
+            keep = (keep, wkeep)
+        h = nat.c_ds_p()
+        nat.check(nat.lib().ppca_b200_dataset_from_device(ctx.handle, ptr, n, d, row_stride, wptr, _producer_stream(),
+                                                          C.byref(h)))
+        del keep
+        return cls._wrap(h, ctx)
+
+    def to_torch(self):
+        """`numpy()` without leaving the GPU: a (n, d) float64 torch.Tensor on the dataset's device, NaN at the masked
+        slots (ppca_b200_dataset_to_device)."""
+        import torch
+        n, d = len(self), self._output_size()
+        out = torch.empty((n, d), dtype=torch.float64, device=f"cuda:{self._ctx.device}")
+        if n:
+            torch.cuda.current_stream(out.device).synchronize()  # the allocation may reuse memory with pending work
+            nat.check(nat.lib().ppca_b200_dataset_to_device(self._ctx.handle, self._h, 0, n, out.data_ptr()))
+        return out
+
+    def __dlpack__(self, stream=None):
+        return self.to_torch().__dlpack__(stream=stream)
+
+    def __dlpack_device__(self):
+        return (2, self._ctx.device)  # kDLCUDA
 
     def __del__(self):  # pragma: no cover
         try:
@@ -605,10 +699,21 @@ class InferredMasked:
         sm = self._states @ ppca._C.T + ppca._mu
         return Dataset(np.where(np.isfinite(x), x, sm))  # ppca_model.rs:460-463
 
+    def _cov_full(self, ppca: PPCAModel, dataset: Optional[Dataset]) -> np.ndarray:
+        """sigma^2 I + C Sigma_n C^T for every sample as one (n, d, d) array, on the device (ppca_b200_covariance_full);
+        rows / columns of the dimensions `dataset` observed are zero when it is given (ppca_model.rs:471-477, 517-534)."""
+        n, k, d = self._states.shape[0], ppca.state_size, ppca.output_size
+        out = np.empty((n, d, d), dtype=np.float64)
+        if n == 0:
+            return out
+        ctx = dataset._ctx if dataset is not None else nat.get_context()
+        covs = nat.f64(self._covs)
+        nat.check(nat.lib().ppca_b200_covariance_full(ctx.handle, n, d, k, nat.dptr(ppca._C), ppca._sigma, nat.dptr(covs),
+                                                      dataset._h if dataset is not None else None, nat.dptr(out)))
+        return out
+
     def smoothed_covariances(self, ppca: PPCAModel) -> List[np.ndarray]:
-        d = ppca.output_size
-        eye = np.eye(d) * ppca._sigma ** 2
-        return [eye + ppca._C @ c @ ppca._C.T for c in self._covs]  # ppca_model.rs:471-477
+        return list(self._cov_full(ppca, None))  # ppca_model.rs:471-477
 
     def _cov_diag_dataset(self, ppca: PPCAModel, dataset: Optional[Dataset]) -> Dataset:
         """sigma^2 + c_i^T Sigma_n c_i for every (sample, dimension), on the device (ppca_b200_covariance_diagonal);
@@ -629,39 +734,59 @@ class InferredMasked:
         return self._cov_diag_dataset(ppca, None)
 
     def extrapolated_covariances(self, ppca: PPCAModel, dataset: Dataset) -> List[np.ndarray]:
-        x = dataset.numpy()
-        out = []
-        full = self.smoothed_covariances(ppca)
-        for i in range(len(self)):
-            neg = ~np.isfinite(x[i])  # ppca_model.rs:517-534
-            m = np.zeros_like(full[i])
-            if neg.any():
-                m[np.ix_(neg, neg)] = full[i][np.ix_(neg, neg)]
-            out.append(m)
-        return out
+        if len(dataset) != len(self):
+            raise ValueError("dataset length does not match the inferred batch")
+        return list(self._cov_full(ppca, dataset))  # ppca_model.rs:517-534
 
     def extrapolated_covariances_diagonal(self, ppca: PPCAModel, dataset: Dataset) -> Dataset:
         return self._cov_diag_dataset(ppca, dataset)  # ppca_model.rs:542-577
 
     def posterior_sampler(self) -> "PosteriorSampler":
-        return PosteriorSampler(self._states, np.linalg.cholesky(self._covs), self._model)  # ppca_model.rs:581-592
+        return PosteriorSampler(self._states, self._covs, self._model)  # ppca_model.rs:581-592
+
+
+def _fresh_seed(seed: Optional[int]) -> int:
+    return int(np.random.default_rng().integers(0, 2 ** 63)) if seed is None else int(seed)
+
+
+def _posterior_sample(models: Sequence["PPCAModel"], posteriors: Optional[np.ndarray], states: Sequence[np.ndarray],
+                      covs: Sequence[np.ndarray], seed: Optional[int]) -> Dataset:
+    """One posterior draw per inferred sample on the device (ppca_b200_posterior_sample)."""
+    ctx = nat.get_context()
+    m = len(models)
+    n = int(states[0].shape[0])
+    d = models[0].output_size
+    ks = np.array([mm.state_size for mm in models], dtype=np.int32)
+    Cs = nat.f64(np.concatenate([mm._C.reshape(-1) for mm in models]))
+    mus = nat.f64(np.concatenate([mm._mu.reshape(-1) for mm in models]))
+    sig = nat.f64(np.array([mm._sigma for mm in models], dtype=np.float64))
+    st = [nat.f64(np.asarray(v, dtype=np.float64).reshape(n, -1)) for v in states]
+    cv = [nat.f64(np.asarray(v, dtype=np.float64).reshape(n, -1)) for v in covs]
+    sp = (nat.c_dp * m)(*[nat.dptr(v) for v in st])
+    cp = (nat.c_dp * m)(*[nat.dptr(v) for v in cv])
+    post = nat.f64(np.asarray(posteriors, dtype=np.float64).reshape(n, m)) if m > 1 else None
+    h = nat.c_ds_p()
+    nat.check(nat.lib().ppca_b200_posterior_sample(ctx.handle, n, d, m, ks.ctypes.data_as(nat.c_ip), nat.dptr(Cs),
+                                                   nat.dptr(mus), nat.dptr(sig), nat.dptr(post), sp, cp,
+                                                   _fresh_seed(seed), C.byref(h)))
+    return Dataset._wrap(h, ctx)
 
 
 class PosteriorSampler:
-    """ppca_model.rs:595-626; needs the model to map states to outputs, as in the reference struct."""
+    """ppca_model.rs:595-626: x = noise + mean + C (state + L standard), L L^T = covariance.  Drawn on the device; the
+    Cholesky factors are formed there too (a covariance that is not positive definite raises, as the reference's
+    `expect("Cholesky decomposition failed")`, ppca_model.rs:582-586)."""
 
-    def __init__(self, states: np.ndarray, chol: np.ndarray, model: Optional[PPCAModel] = None):
-        self._states, self._chol, self._model = states, chol, model
+    def __init__(self, states: np.ndarray, covs: np.ndarray, model: Optional["PPCAModel"] = None):
+        self._states, self._covs, self._model = states, covs, model
 
-    def sample(self, model: Optional[PPCAModel] = None) -> Dataset:
+    def sample(self, model: Optional["PPCAModel"] = None, seed: Optional[int] = None) -> Dataset:
+        """No arguments, as in the reference (src/python_bindings.rs:335-365); `seed` is an extension (the reference
+        draws from thread_rng)."""
         model = model or self._model
         if model is None:
             raise ValueError("a PPCAModel is needed to sample outputs")
-        rng = np.random.default_rng()
-        n, k = self._states.shape
-        z = self._states + np.einsum("nab,nb->na", self._chol, rng.standard_normal((n, k)))
-        noise = model._sigma * rng.standard_normal((n, model.output_size))
-        return Dataset(noise + model._mu + z @ model._C.T)
+        return _posterior_sample([model], None, [self._states], [self._covs], seed)
 
 
 # =================================================================================================
@@ -762,19 +887,18 @@ class PPCAMix:
         self._call(nat.lib().ppca_b200_mix_llk, dataset, C.byref(out))
         return out.value
 
-    def sample(self, dataset_size: int, mask_probability: float) -> Dataset:
-        """mix.rs:124-134 (unseeded)."""
-        rng = np.random.default_rng()
-        comp = rng.choice(len(self._models), size=int(dataset_size), p=self.weights / self.weights.sum())
-        d = self.output_size
-        x = np.empty((int(dataset_size), d))
-        for j, m in enumerate(self._models):
-            idx = np.nonzero(comp == j)[0]
-            if idx.size:
-                x[idx] = (rng.standard_normal((idx.size, m.state_size)) @ m._C.T + m._mu
-                          + m._sigma * rng.standard_normal((idx.size, d)))
-        x[rng.random(x.shape) < mask_probability] = np.nan
-        return Dataset(x)
+    def sample(self, dataset_size: int, mask_probability: float, seed: Optional[int] = None) -> Dataset:
+        """mix.rs:124-134 on the device (ppca_b200_mix_sample): component from exp(log_weights), then that model's
+        sample_one.  Unseeded like the reference unless `seed` is given (extension)."""
+        if not 0.0 <= mask_probability <= 1.0:
+            raise ValueError("invalid mask probability")
+        ctx = nat.get_context()
+        ks, Cs, mus, sig, lw = self._pack()
+        h = nat.c_ds_p()
+        nat.check(nat.lib().ppca_b200_mix_sample(ctx.handle, int(dataset_size), self.output_size, len(self._models),
+                                                 ks.ctypes.data_as(nat.c_ip), nat.dptr(Cs), nat.dptr(mus), nat.dptr(sig),
+                                                 nat.dptr(lw), float(mask_probability), _fresh_seed(seed), C.byref(h)))
+        return Dataset._wrap(h, ctx)
 
     def infer_cluster(self, dataset: Dataset) -> np.ndarray:
         out = np.empty((len(dataset), len(self._models)))
@@ -893,18 +1017,21 @@ class InferredMaskedMix:
         post, parts = self._parts(mix, dataset)
         return Dataset(sum(post[:, j:j + 1] * p for j, p in enumerate(parts)))  # mix.rs:407-414
 
-    def smoothed_covariances(self, mix: PPCAMix) -> List[np.ndarray]:
-        post, parts = self._parts(mix, None)
+    def _mix_cov_full(self, mix: PPCAMix, dataset: Optional[Dataset]) -> List[np.ndarray]:
+        """sum_j p_nj (cov_nj + (m_nj - mean_n)(m_nj - mean_n)^T) (mix.rs:422-437, 466-481): the component matrices come
+        from the device (ppca_b200_covariance_full); both the smoothed and the extrapolated form use the SMOOTHED
+        component covariance, as the reference does (mix.rs:474)."""
+        post, parts = self._parts(mix, dataset)
         mean = sum(post[:, j:j + 1] * p for j, p in enumerate(parts))
-        out = []
-        covs = [inf.smoothed_covariances(m) for inf, m in zip(self._inf, mix._models)]
-        for n in range(len(self)):  # mix.rs:422-437
-            acc = 0.0
-            for j in range(len(self._inf)):
-                dlt = parts[j][n] - mean[n]
-                acc = acc + post[n, j] * (covs[j][n] + np.outer(dlt, dlt))
-            out.append(acc)
-        return out
+        acc = None
+        for j, (inf, m) in enumerate(zip(self._inf, mix._models)):
+            dlt = parts[j] - mean
+            term = post[:, j, None, None] * (inf._cov_full(m, None) + dlt[:, :, None] * dlt[:, None, :])
+            acc = term if acc is None else acc + term
+        return list(acc)
+
+    def smoothed_covariances(self, mix: PPCAMix) -> List[np.ndarray]:
+        return self._mix_cov_full(mix, None)
 
     def smoothed_covariances_diagonal(self, mix: PPCAMix) -> Dataset:
         post, parts = self._parts(mix, None)
@@ -915,17 +1042,7 @@ class InferredMaskedMix:
         return Dataset(acc)
 
     def extrapolated_covariances(self, mix: PPCAMix, dataset: Dataset) -> List[np.ndarray]:
-        post, parts = self._parts(mix, dataset)
-        mean = sum(post[:, j:j + 1] * p for j, p in enumerate(parts))
-        covs = [inf.smoothed_covariances(m) for inf, m in zip(self._inf, mix._models)]  # mix.rs:474 (smoothed!)
-        out = []
-        for n in range(len(self)):
-            acc = 0.0
-            for j in range(len(self._inf)):
-                dlt = parts[j][n] - mean[n]
-                acc = acc + post[n, j] * (covs[j][n] + np.outer(dlt, dlt))
-            out.append(acc)
-        return out
+        return self._mix_cov_full(mix, dataset)
 
     def extrapolated_covariances_diagonal(self, mix: PPCAMix, dataset: Dataset) -> Dataset:
         post, parts = self._parts(mix, dataset)
@@ -947,14 +1064,12 @@ class PosteriorSamplerMix:
     def __init__(self, posteriors: np.ndarray, samplers: List[PosteriorSampler], mix: Optional[PPCAMix] = None):
         self._post, self._samplers, self._mix = posteriors, samplers, mix
 
-    def sample(self, mix: Optional[PPCAMix] = None) -> Dataset:
-        """No arguments, as in the reference (src/python_bindings.rs:895): the samplers carry their models."""
+    def sample(self, mix: Optional[PPCAMix] = None, seed: Optional[int] = None) -> Dataset:
+        """No arguments, as in the reference (src/python_bindings.rs:895): the samplers carry their models.  Component
+        drawn from each row's posterior (WeightedIndex, mix.rs:505-509), then that component's posterior sampler
+        (mix.rs:524-531), on the device."""
         mix = mix or self._mix
         if mix is None:
             raise ValueError("a PPCAMix is needed to sample outputs")
-        rng = np.random.default_rng()
-        n = self._post.shape[0]
-        p = self._post / self._post.sum(axis=1, keepdims=True)
-        choice = np.array([rng.choice(p.shape[1], p=p[i]) for i in range(n)])
-        outs = [s.sample(m).numpy() for s, m in zip(self._samplers, mix._models)]
-        return Dataset(np.stack([outs[choice[i]][i] for i in range(n)]))
+        return _posterior_sample(mix._models, self._post, [s_._states for s_ in self._samplers],
+                                 [s_._covs for s_ in self._samplers], seed)

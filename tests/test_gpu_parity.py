@@ -1085,3 +1085,164 @@ def test_tiled_solve_on_ill_conditioned_systems(pk, orc, guard_ctx, k):
     floor = _elementwise(dense, want)
     print(f"k {k}: tiled solve {_elementwise(got, want):.2e} floor {floor:.2e}")
     assert _elementwise(got, want) < TOL + 4.0 * floor
+
+
+def test_dataset_from_device_is_the_host_dataset(pk, orc):
+    """zero-copy ingestion (ppca_b200_dataset_from_device) of a torch tensor through
+    __cuda_array_interface__ / DLPack gives the same masks, values, weights and EM step as Dataset(ndarray)."""
+    import torch
+    n, d, k = 3000, 70, 10
+    X, C0, mu0, s0 = _case(n, d, k, 0.25, seed=21, empty_rows=(5,))
+    X[17, 3] = np.inf
+    X[18, 4] = -np.inf                                   # +-inf are missing values too (dataset.rs:19-22)
+    w = np.random.default_rng(5).random(n) + 0.5
+    ref = pk.Dataset(X, w)
+    t = torch.from_numpy(X).cuda()
+    tw = torch.from_numpy(w).cuda()
+    ds = pk.Dataset.from_device(t, tw)
+    want = ref.numpy()
+    assert np.array_equal(np.isnan(ds.numpy()), np.isnan(want))
+    assert np.array_equal(np.nan_to_num(ds.numpy()), np.nan_to_num(want))
+    assert np.array_equal(ds.weights(), w)
+    assert ds.empty_dimensions() == ref.empty_dimensions()
+    # strided rows (a column slice of a wider tensor) and a DLPack-only producer
+    wide = torch.full((n, d + 9), float("nan"), dtype=torch.float64, device="cuda")
+    wide[:, 4:4 + d] = t
+    ds2 = pk.Dataset.from_device(wide[:, 4:4 + d])
+    assert np.array_equal(np.nan_to_num(ds2.numpy()), np.nan_to_num(want))
+
+    class OnlyDLPack:
+        def __init__(self, t):
+            self.t = t
+
+        def __dlpack__(self, stream=None):
+            return self.t.__dlpack__()
+
+        def __dlpack_device__(self):
+            return self.t.__dlpack_device__()
+
+    ds3 = pk.Dataset.from_device(OnlyDLPack(t))
+    assert np.array_equal(np.nan_to_num(ds3.numpy()), np.nan_to_num(want))
+    # the export side: numpy() without leaving the device
+    back = ds.to_torch()
+    assert back.is_cuda and back.dtype == torch.float64
+    assert np.array_equal(np.nan_to_num(back.cpu().numpy()), np.nan_to_num(want))
+    assert np.array_equal(np.isnan(back.cpu().numpy()), np.isnan(want))
+    # and the EM step is the host dataset's, bit for bit
+    model = pk.PPCAModel(s0, C0, mu0)
+    a, la = model._iterate(ref, None)
+    b, lb = model._iterate(ds, None)
+    assert la == lb and np.array_equal(a.transform, b.transform) and a.isotropic_noise == b.isotropic_noise
+    (Cw, muw, sw), (Cs, mus, ss) = both(orc, orc.iterate, X, w, C0, mu0, s0)
+    assert_close(b.transform, Cw, Cs, "C")
+    # errors: wrong dtype, host tensor, non-positive weights reach mixture EM as in the host path
+    with pytest.raises(TypeError):
+        pk.Dataset.from_device(t.float())
+    with pytest.raises(Exception):
+        pk.Dataset.from_device(torch.from_numpy(X))
+    bad = tw.clone()
+    bad[7] = 0.0
+    mix = pk.PPCAMix([pk.PPCAModel(1.0, C0, mu0), pk.PPCAModel(1.0, C0[:, ::-1].copy(), mu0)], np.zeros(2))
+    with pytest.raises(Exception):
+        mix.iterate(pk.Dataset.from_device(t, bad))
+
+
+def test_mixture_and_posterior_samplers_on_device_have_the_reference_distributions(pk):
+    """SURVEY §8(f3).  PPCAMix.sample (mix.rs:124-134): component ~ exp(log_weights), x | j ~ N(mu_j, C_j C_j^T + s_j^2 I),
+    entries masked i.i.d.  PosteriorSampler (ppca_model.rs:595-626): x ~ N(C z + mu, C Sigma C^T + sigma^2 I).
+    PosteriorSamplerMix (mix.rs:505-532): component ~ posterior of the row.  The reference is unseeded, so parity is
+    distributional; a seed reproduces (counter-based RNG)."""
+    rng = np.random.default_rng(9)
+    d, n = 10, 300_000
+    ks = (2, 4, 3)
+    models = [pk.PPCAModel(0.3 + 0.2 * j, rng.standard_normal((d, k)), 4.0 * j + rng.standard_normal(d))
+              for j, k in enumerate(ks)]
+    wts = np.array([0.2, 0.5, 0.3])
+    mix = pk.PPCAMix(models, np.log(wts))
+    a = mix.sample(n, 0.25, seed=3).numpy()
+    fin = np.isfinite(a)
+    assert a.shape == (n, d) and abs(fin.mean() - 0.75) < 5e-3
+    # the mixture mean and second moment of the draw
+    mean_true = sum(w * m.mean.reshape(-1) for w, m in zip(wts, models))
+    mean = np.nanmean(a, axis=0)
+    sec_true = sum(w * (m.transform @ m.transform.T + m.isotropic_noise ** 2 * np.eye(d)
+                        + np.outer(m.mean.reshape(-1), m.mean.reshape(-1))) for w, m in zip(wts, models))
+    x0 = np.where(fin, a, 0.0)
+    pair = fin.astype(np.float64).T @ fin.astype(np.float64)
+    sec = (x0.T @ x0) / pair
+    assert np.max(np.abs(mean - mean_true)) < 0.05
+    assert np.max(np.abs(sec - sec_true)) < 0.02 * np.max(np.abs(sec_true))
+    # component frequencies through the posterior of the fully observed draws (means are 4 apart: well separated)
+    full = mix.sample(50_000, 0.0, seed=4)
+    freq = np.bincount(np.argmax(mix.infer_cluster(full), axis=1), minlength=3) / 50_000
+    assert np.max(np.abs(freq - wts)) < 0.01
+    assert np.array_equal(mix.sample(500, 0.25, seed=3).numpy(), a[:500], equal_nan=True)
+    assert len(mix.sample(0, 0.1)) == 0
+    with pytest.raises(ValueError):
+        mix.sample(10, 1.5)
+
+    # posterior sampler of one model: many draws of the same inferred sample
+    model = models[1]
+    x = model.sample(1, 0.4, seed=8).numpy()
+    reps = 200_000
+    inf = model.infer(pk.Dataset(np.repeat(x, reps, axis=0)))
+    z, S = inf.states()[0], inf.covariances()[0]
+    draw = inf.posterior_sampler().sample(seed=5).numpy()
+    assert draw.shape == (reps, d) and np.isfinite(draw).all()          # posterior samples are fully observed
+    Cm, mu, s = model.transform, model.mean.reshape(-1), model.isotropic_noise
+    assert np.max(np.abs(draw.mean(axis=0) - (Cm @ z + mu))) < 6 * np.sqrt(np.max(np.diag(Cm @ S @ Cm.T) + s * s) / reps)
+    cov_true = Cm @ S @ Cm.T + s * s * np.eye(d)
+    assert np.max(np.abs(np.cov(draw.T) - cov_true)) < 0.03 * np.max(np.abs(cov_true))
+    # mixture posterior sampler: rows whose posterior is concentrated on one component are drawn from that component
+    data = mix.sample(20_000, 0.3, seed=6)
+    infm = mix.infer(data)
+    post = infm.posteriors()
+    dm = infm.posterior_sampler().sample(seed=7).numpy()
+    assert dm.shape == (20_000, d) and np.isfinite(dm).all()
+    sm = mix.smooth(data).numpy()
+    sure = post.max(axis=1) > 0.999
+    assert sure.mean() > 0.9
+    resid = dm[sure] - sm[sure]                       # draw = smoothed + C L xi + sigma eps around the same component
+    assert abs(resid.mean()) < 0.02
+    assert np.array_equal(infm.posterior_sampler().sample(seed=7).numpy(), dm)
+    # a covariance that is not positive definite raises, as the reference's expect() (ppca_model.rs:582-586)
+    bad = pk.InferredMasked(np.zeros((4, 2)), np.stack([np.array([[1.0, 2.0], [2.0, 1.0]])] * 4), models[0])
+    with pytest.raises(Exception):
+        bad.posterior_sampler().sample()
+
+
+@pytest.mark.parametrize("n,d,k", [(60, 37, 5), (40, 100, 16), (9, 70, 33)])
+def test_full_covariances_on_device(pk, orc, n, d, k):
+    """InferredMasked.smoothed_covariances / extrapolated_covariances (ppca_model.rs:471-477, 517-534) and the
+    mixture forms (mix.rs:422-437, 466-481): d x d matrices made on the device (ppca_b200_covariance_full) against the
+    oracle's restatement."""
+    X, C0, mu0, s0 = _case(n, d, k, 0.3, seed=61)
+    X[3, :] = np.nan                       # nothing observed
+    X[4, :] = 1.5                          # nothing missing: the extrapolated covariance is all zeros (:520-522)
+    model = pk.PPCAModel(0.4, C0, mu0)
+    ds = pk.Dataset(X)
+    inf = model.infer(ds)
+    covs = inf.covariances()
+    sm = inf.smoothed_covariances(model)
+    ex = inf.extrapolated_covariances(model, ds)
+    assert len(sm) == n and sm[0].shape == (d, d)
+    for i in range(n):
+        assert rel_err(sm[i], orc.smoothed_covariance(C0, 0.4, covs[i])) < 1e-12
+        want = orc.extrapolated_covariance(C0, 0.4, covs[i], X[i])
+        assert np.array_equal(ex[i] == 0.0, want == 0.0) or rel_err(ex[i], want) < 1e-12
+        assert np.max(np.abs(ex[i] - want)) <= 1e-12 * max(np.max(np.abs(want)), 1.0)
+    assert not ex[4].any() and np.array_equal(ex[3], sm[3])
+    assert rel_err(np.stack([np.diag(m) for m in sm]), inf.smoothed_covariances_diagonal(model).numpy()) < 1e-12
+    other = pk.PPCAModel(0.7, C0[:, ::-1].copy(), mu0 + 0.3)
+    mix = pk.PPCAMix([model, other], np.log([0.4, 0.6]))
+    im = mix.infer(ds)
+    post = im.posteriors()
+    msm = im.smoothed_covariances(mix)
+    mex = im.extrapolated_covariances(mix, ds)
+    comps = [model, other]
+    for i in range(0, n, 7):
+        cj = [orc.smoothed_covariance(m.transform, m.isotropic_noise, im._inf[j].covariances()[i]) for j, m in enumerate(comps)]
+        smj = [im._inf[j].states()[i] @ m.transform.T + m.mean.reshape(-1) for j, m in enumerate(comps)]
+        exj = [np.where(np.isfinite(X[i]), X[i], v) for v in smj]
+        assert rel_err(msm[i], orc.mix_covariance(post[i], smj, cj)) < 1e-11
+        assert rel_err(mex[i], orc.mix_covariance(post[i], exj, cj)) < 1e-11

@@ -160,3 +160,34 @@ def test_reference_noise_floor_is_documented():
     assert errs[1.0][0] < 1e-11 and errs[1.0][1] < 1e-13
     assert errs[0.01][0] > 1e-9          # the reference's own noise floor is above the parity tolerance here
     assert errs[0.01][1] < 1e-13         # the cancellation-free form is not
+
+
+def test_covariance_family_restatement_is_consistent():
+    """oracle.smoothed_/extrapolated_covariance(_diagonal) and mix_covariance (ppca_model.rs:471-577, mix.rs:422-501):
+    diagonal forms are the diagonals of the full forms, expansion zeroes the observed rows / columns, and the mixture
+    form is the law of total covariance."""
+    from oracle import oracle as orc
+    rng = np.random.default_rng(5)
+    d, k = 9, 3
+    Cm = rng.standard_normal((d, k))
+    A = rng.standard_normal((k, k))
+    cov = A @ A.T + np.eye(k)
+    x = rng.standard_normal(d)
+    x[[1, 4, 5]] = np.nan
+    full = orc.smoothed_covariance(Cm, 0.3, cov)
+    assert np.allclose(np.diag(full), orc.smoothed_covariance_diagonal(Cm, 0.3, cov), rtol=1e-14)
+    ex = orc.extrapolated_covariance(Cm, 0.3, cov, x)
+    neg = np.isnan(x)
+    assert np.array_equal(ex[np.ix_(neg, neg)], np.eye(3) * 0.09 + Cm[neg] @ cov @ Cm[neg].T)
+    assert not ex[~neg].any() and not ex[:, ~neg].any()
+    assert np.allclose(np.diag(ex), orc.extrapolated_covariance_diagonal(Cm, 0.3, cov, x), rtol=1e-14)
+    assert not orc.extrapolated_covariance(Cm, 0.3, cov, np.ones(d)).any()
+    # law of total covariance against a Monte-Carlo draw of the two-component Gaussian mixture
+    means = [rng.standard_normal(d), rng.standard_normal(d) + 2.0]
+    covs = [full, orc.smoothed_covariance(Cm[:, ::-1], 0.5, cov)]
+    post = np.array([0.3, 0.7])
+    want = orc.mix_covariance(post, means, covs)
+    n = 400_000
+    comp = rng.random(n) < post[1]
+    draws = np.where(comp[:, None], rng.multivariate_normal(means[1], covs[1], n), rng.multivariate_normal(means[0], covs[0], n))
+    assert np.max(np.abs(np.cov(draws.T) - want)) < 0.03 * np.max(np.abs(want))
