@@ -107,7 +107,7 @@ int32_t ppca_b200_ctx_launch_count(ppca_b200_ctx *ctx, int64_t *out);
  *   6-8 solve_reg_kernel<8|16|32>   9 solve_split64_kernel   10 solve_tile_kernel (register-tiled, 16 < k <= 64)
  *   11 unused
  *   12 solve_kernel (generic)   13 passes repeated at a wider arithmetic by the precision guard
- *   14 batched mixture contraction launches   15 reserved */
+ *   14 batched mixture contraction launches   15 mixture chunk loops replayed from a captured CUDA graph */
 int32_t ppca_b200_ctx_variant_counts(ppca_b200_ctx *ctx, int64_t *out16);
 /* Device time accumulated since profiling was enabled (ppca_b200_ctx_set_profiling(ctx, 1) resets it), broken
  * down per kernel family, in ms; reading it synchronises the stream once, the profiled calls never do:
@@ -344,6 +344,15 @@ int32_t ppca_b200_comm_allreduce(ppca_b200_ctx *ctx, double *buf_dev, int64_t co
 int32_t ppca_b200_iterate_sharded(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int32_t k, const double *C,
                                   const double *mu, double sigma, const ppca_b200_prior *prior, double *C_out,
                                   double *mu_out, double *sigma_out, double *llk_in);
+/* One EM step (ppca_model.rs:277-393) over rows [row_begin, row_begin + nrows) of the synthetic dataset that
+ * ppca_b200_dataset_synthetic(n >= row_begin + nrows, d, k_true, sigma_true, mask_prob, n_components = 1, seed) would hold,
+ * WITHOUT storing them: every chunk is regenerated on the device and consumed (the out-of-core form of BASELINE
+ * configs[2], N = 100 M x 2048 = 1.6 TB, which fits no set of 8 GPUs).  sharded != 0: the statistics are all-reduced over
+ * the context's communicator before the finish (every rank passes its own row range and gets the same model). */
+int32_t ppca_b200_iterate_generated(ppca_b200_ctx *ctx, int64_t row_begin, int64_t nrows, int32_t d, int32_t k_true,
+                                    double sigma_true, double mask_prob, uint64_t seed, int32_t k, const double *C,
+                                    const double *mu, double sigma, const ppca_b200_prior *prior, int32_t sharded,
+                                    double *C_out, double *mu_out, double *sigma_out, double *llk_in);
 /* The same with this rank's samples in HOST memory, streamed every step (see ppca_b200_iterate_host). */
 int32_t ppca_b200_iterate_host_sharded(ppca_b200_ctx *ctx, const double *x, int64_t n, int32_t d, const double *weights,
                                        int32_t k, const double *C, const double *mu, double sigma,

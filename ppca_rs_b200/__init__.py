@@ -16,6 +16,7 @@ from .adapter import DataFrameAdapter, DataFrameAdapterDescription
 from .model import (
     Dataset,
     DatasetChunks,
+    GeneratedDataset,
     HostDataset,
     InferredMasked,
     InferredMaskedMix,
@@ -29,7 +30,7 @@ from .model import (
 __version__ = "0.1.0"
 
 __all__ = [
-    "Dataset", "DatasetChunks", "HostDataset", "InferredMasked", "InferredMaskedMix", "PosteriorSampler", "PosteriorSamplerMix",
+    "Dataset", "DatasetChunks", "GeneratedDataset", "HostDataset", "InferredMasked", "InferredMaskedMix", "PosteriorSampler", "PosteriorSamplerMix",
     "PPCAMix", "PPCAModel", "Prior", "PPCATrainer", "PPCAMixTrainer", "TrainMetrics", "DataFrameAdapter",
     "DataFrameAdapterDescription", "Context", "NativeError",
     "device_count", "get_context", "set_context",

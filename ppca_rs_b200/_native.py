@@ -157,6 +157,11 @@ _PROTOTYPES = {
         C.c_int32,
         [c_ctx_p, c_ds_p, C.c_int32, c_dp, c_dp, C.c_double, C.POINTER(CPrior), c_dp, c_dp, c_dp, c_dp],
     ),
+    "ppca_b200_iterate_generated": (
+        C.c_int32,
+        [c_ctx_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_uint64, C.c_int32, c_dp, c_dp,
+         C.c_double, C.POINTER(CPrior), C.c_int32, c_dp, c_dp, c_dp, c_dp],
+    ),
     "ppca_b200_iterate_host_sharded": (
         C.c_int32,
         [c_ctx_p, c_dp, C.c_int64, C.c_int32, c_dp, C.c_int32, c_dp, c_dp, C.c_double, C.POINTER(CPrior), c_dp, c_dp,
@@ -273,7 +278,7 @@ class Context:
 
     VARIANTS = ("tc_smem_a", "tc_atm_feed", "tc_atm_drain", "tc_atm2", "imma", "dmma", "solve_reg8", "solve_reg16",
                 "solve_reg32", "solve_split64", "solve_tile", "unused11", "solve_generic", "precision_retry",
-                "tc_mix", "reserved15")
+                "tc_mix", "graph_replays")
 
     def variant_counts(self) -> Dict[str, int]:
         """Launches so far per shape-dependent kernel variant (ppca_b200_ctx_variant_counts): lets a test assert

@@ -82,6 +82,19 @@ struct ppca_b200_ctx {
   cudaStream_t out_stream = nullptr;
   cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_outfree[2] = {nullptr, nullptr};
   DevBuf<double> s_out[2], s_llk[2];
+  // CUDA graphs of the mixture chunk loop (mix_em_pass): the loop is ~30 small launches per component and chunk — at
+  // M = 32 the HOST launch rate, not the GPU, bounded the step on slow hosts (measured 106 ... 336 ms for the same work).
+  // A pass with a key seen before (same dataset, shapes, arithmetic, buffers) is captured once and replayed.
+  struct MixGraph {
+    std::vector<uint64_t> key;
+    cudaGraphExec_t exec = nullptr;
+    int64_t launches = 0;
+    int64_t variants[V_COUNT] = {0};
+  };
+  std::vector<MixGraph> mix_graphs;
+  std::vector<std::vector<uint64_t>> mix_seen;
+  bool use_graphs = true;  // PPCA_B200_GRAPHS=0 disables
+  int64_t graph_replays = 0;
   // profiling
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;
@@ -475,6 +488,7 @@ void e_step_chunk(ppca_b200_ctx *ctx, const SampleStore &st, const double *w, in
   SolveArgs sa;
   sa.s = m.s;
   sa.sigma = m.sigma;
+  sa.sigma_dev = m.sigma_dev;
   sa.rows = rows;
   sa.rows_pad = rows_pad;
   sa.GW = ws.GW;
@@ -1075,6 +1089,8 @@ int32_t ppca_b200_ctx_destroy(ppca_b200_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
+    for (auto &g : ctx->mix_graphs)
+      if (g.exec) cudaGraphExecDestroy(g.exec);
     if (ctx->comm) {
       try {
         comm_destroy(ctx->comm);
@@ -2516,7 +2532,7 @@ void mix_em_pass(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, const MixView 
   out.comps.assign(M, MixComp());
   size_t need = 0, need_q = 0;
   double *sh_nx = nullptr, *sh_llk = nullptr, *sh_WZ = nullptr, *sh_r = nullptr, *LPc = nullptr, *mixllk = nullptr,
-         *chunk_max = nullptr, *factor = nullptr;
+         *chunk_max = nullptr, *factor = nullptr, *sigmas_dev = nullptr;
   int8_t *sh_WQ = nullptr, *sh_ZQ = nullptr;
   for (int pass = 0; pass < 2; ++pass) {
     if (pass == 1) {
@@ -2535,6 +2551,7 @@ void mix_em_pass(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, const MixView 
     out.run_max = cv.take((size_t)M);
     chunk_max = cv.take((size_t)M);
     factor = cv.take((size_t)M);
+    sigmas_dev = cv.take((size_t)M);
     sh_WQ = pass ? ctx->mixArenaQ.p + qoff : nullptr;
     {
       size_t wq = 0;
@@ -2585,6 +2602,7 @@ void mix_em_pass(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, const MixView 
         c.m = stage_model_into(ctx, d, mv.ks[j], mv.C(j), mv.mu(j), mv.sigmas[j], Cpad, mupad, Ksym, c.ws.KsymQ,
                                c.ws.KsymScale, c.ws.colmax);
         c.m.ws = &c.ws;
+        c.m.sigma_dev = sigmas_dev + j;
         em_zero(ctx, c.ws, c.plan, s, c.stats);
       }
     }
@@ -2601,58 +2619,133 @@ void mix_em_pass(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, const MixView 
     std::vector<double> init((size_t)M, ninf);
     // small synchronous upload (M doubles) before any kernel of the pass reads it
     CUDA_CHECK(cudaMemcpyAsync(out.run_max, init.data(), sizeof(double) * M, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_CHECK(cudaMemcpyAsync(sigmas_dev, mv.sigmas, sizeof(double) * M, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
   }
   ctx->logw.reserve((size_t)M);
   CUDA_CHECK(cudaMemcpyAsync(ctx->logw.p, mv.logw, sizeof(double) * M, cudaMemcpyHostToDevice, ctx->stream));
 
-  int64_t rows_total = 0;
-  for (int64_t row0 = 0; row0 < st.n; row0 += chunk) {
-    const int rows = (int)std::min<int64_t>(chunk, st.n - row0);
-    const int rows_pad = (int)round_up(rows, 256);
-    rows_total += rows;
-    // E-step of every component on this chunk (unweighted: W = V = z z^T + Sigma)
-    for (int j = 0; j < M; ++j) {
-      MixComp &c = out.comps[j];
-      e_step_chunk(ctx, st, nullptr, row0, rows, c.m, 2, sh_llk, nullptr, nullptr, nullptr);
-      const int blocks = (int)std::min<int64_t>((int64_t)ctx->sms * 8, (rows + 255) / 256);
-      strided_copy_kernel<<<blocks, 256, 0, ctx->stream>>>(sh_llk, rows, 1, 1, LPc + j, M);
-      CUDA_CHECK(cudaGetLastError());
-      ++ctx->launches;
-    }
-    // log-posteriors of the chunk (mix.rs:179-189), mixture log-likelihood (:162-174), chunk maxima of ln w + lp (:312-318)
-    launch_log_softmax_rows(L, LPc, rows, M, ctx->logw.p, ds->w.p + row0, mixllk, chunk_max, nullptr);
-    launch_weighted_sum(L, mixllk, ds->w.p + row0, rows, llk_sum, 1);
-    if (LP_full)  // kept for the per-component repeats of the precision ladder
-      CUDA_CHECK(cudaMemcpyAsync(LP_full + row0 * M, LPc, sizeof(double) * (size_t)rows * M, cudaMemcpyDeviceToDevice,
-                                 ctx->stream));
-    launch_mix_update_max(L, M, out.run_max, chunk_max, factor);
-    for (int j = 0; j < M; ++j) {
-      MixComp &c = out.comps[j];
-      const Shape &s = shp[j];
-      if (row0 > 0) {  // bring what this component has accumulated so far onto the new maximum
-        const StatsLayout lay(d, s.k);
-        launch_scale_by(L, c.stats, lay.offScalars, factor + j, 0);
-        launch_scale_by(L, c.ws.part_bg, (int64_t)c.plan.bglen, factor + j, 0);
-        launch_scale_by(L, c.ws.part_cr, (int64_t)c.plan.crlen, factor + j, 0);
-        launch_scale_by(L, c.ws.part_solve, (int64_t)SOLVE_SLOTS * 4, factor + j, 1);
-        launch_scale_by(L, c.ws.MZ, (int64_t)s.d * s.kp, factor + j, 0);
-        launch_scale_by(L, c.ws.part_mz, (int64_t)c.plan.mzlen, factor + j, 0);
-        launch_scale_by(L, c.ws.part_rx, (int64_t)c.plan.rxlen, factor + j, 0);
+  // ---- the chunk loop: everything below runs on the context's stream from device-resident inputs only, with launch
+  // parameters that depend on shapes alone (the models' sigma is read from sigmas_dev), so it can be replayed from a graph
+  auto run_loop = [&] {
+    int64_t rows_total = 0;
+    for (int64_t row0 = 0; row0 < st.n; row0 += chunk) {
+      const int rows = (int)std::min<int64_t>(chunk, st.n - row0);
+      const int rows_pad = (int)round_up(rows, 256);
+      rows_total += rows;
+      // E-step of every component on this chunk (unweighted: W = V = z z^T + Sigma)
+      for (int j = 0; j < M; ++j) {
+        MixComp &c = out.comps[j];
+        e_step_chunk(ctx, st, nullptr, row0, rows, c.m, 2, sh_llk, nullptr, nullptr, nullptr);
+        const int blocks = (int)std::min<int64_t>((int64_t)ctx->sms * 8, (rows + 255) / 256);
+        strided_copy_kernel<<<blocks, 256, 0, ctx->stream>>>(sh_llk, rows, 1, 1, LPc + j, M);
+        CUDA_CHECK(cudaGetLastError());
+        ++ctx->launches;
       }
-      // column maxima of W fused into the weighting kernel (its shared-memory scratch holds 8 rows of W)
-      const bool tc = ctx->gemm_mode == 2 && (size_t)8 * s.kkp * sizeof(double) <= 200 * 1024;
-      if (tc) CUDA_CHECK(cudaMemsetAsync(c.ws.colmax, 0, sizeof(unsigned long long) * s.kkp, ctx->stream));
-      ctx->span_begin(FAM_SOLVE);
-      launch_mix_weight(L, LPc, M, j, ds->w.p + row0, out.run_max, rows, rows_pad, s.kkp, s.kp, c.ws.GW, c.ws.YZ, sh_WZ,
-                        sh_r, tc ? c.ws.colmax : nullptr);
-      launch_solve_reduce(L, rows, nullptr, c.ws.tn, c.ws.dv, c.ws.nx, st.dn.p + row0, sh_r, c.ws.part_solve, c.ws.rscratch,
-                          c.ws.rflag);
-      ctx->span_end();
-      m_step_chunk(ctx, st, sh_r, row0, rows, c.m, c.stats, c.plan, tc);
+      // log-posteriors of the chunk (mix.rs:179-189), mixture log-likelihood (:162-174), chunk maxima of ln w + lp (:312-318)
+      launch_log_softmax_rows(L, LPc, rows, M, ctx->logw.p, ds->w.p + row0, mixllk, chunk_max, nullptr);
+      launch_weighted_sum(L, mixllk, ds->w.p + row0, rows, llk_sum, 1);
+      if (LP_full)  // kept for the per-component repeats of the precision ladder
+        CUDA_CHECK(cudaMemcpyAsync(LP_full + row0 * M, LPc, sizeof(double) * (size_t)rows * M, cudaMemcpyDeviceToDevice,
+                                   ctx->stream));
+      launch_mix_update_max(L, M, out.run_max, chunk_max, factor);
+      for (int j = 0; j < M; ++j) {
+        MixComp &c = out.comps[j];
+        const Shape &s = shp[j];
+        if (row0 > 0) {  // bring what this component has accumulated so far onto the new maximum
+          const StatsLayout lay(d, s.k);
+          launch_scale_by(L, c.stats, lay.offScalars, factor + j, 0);
+          launch_scale_by(L, c.ws.part_bg, (int64_t)c.plan.bglen, factor + j, 0);
+          launch_scale_by(L, c.ws.part_cr, (int64_t)c.plan.crlen, factor + j, 0);
+          launch_scale_by(L, c.ws.part_solve, (int64_t)SOLVE_SLOTS * 4, factor + j, 1);
+          launch_scale_by(L, c.ws.MZ, (int64_t)s.d * s.kp, factor + j, 0);
+          launch_scale_by(L, c.ws.part_mz, (int64_t)c.plan.mzlen, factor + j, 0);
+          launch_scale_by(L, c.ws.part_rx, (int64_t)c.plan.rxlen, factor + j, 0);
+        }
+        // column maxima of W fused into the weighting kernel (its shared-memory scratch holds 8 rows of W)
+        const bool tc = ctx->gemm_mode == 2 && (size_t)8 * s.kkp * sizeof(double) <= 200 * 1024;
+        if (tc) CUDA_CHECK(cudaMemsetAsync(c.ws.colmax, 0, sizeof(unsigned long long) * s.kkp, ctx->stream));
+        ctx->span_begin(FAM_SOLVE);
+        launch_mix_weight(L, LPc, M, j, ds->w.p + row0, out.run_max, rows, rows_pad, s.kkp, s.kp, c.ws.GW, c.ws.YZ, sh_WZ,
+                          sh_r, tc ? c.ws.colmax : nullptr);
+        launch_solve_reduce(L, rows, nullptr, c.ws.tn, c.ws.dv, c.ws.nx, st.dn.p + row0, sh_r, c.ws.part_solve, c.ws.rscratch,
+                            c.ws.rflag);
+        ctx->span_end();
+        m_step_chunk(ctx, st, sh_r, row0, rows, c.m, c.stats, c.plan, tc);
+      }
     }
+    for (int j = 0; j < M; ++j) em_end(ctx, out.comps[j].m, out.comps[j].stats, out.comps[j].plan, rows_total);
+  };
+  static const bool graphs_env = !(getenv("PPCA_B200_GRAPHS") && !strcmp(getenv("PPCA_B200_GRAPHS"), "0"));
+  const bool graphable = graphs_env && ctx->use_graphs && !ctx->profiling;
+  if (!graphable) {
+    run_loop();
+    return;
   }
-  for (int j = 0; j < M; ++j) em_end(ctx, out.comps[j].m, out.comps[j].stats, out.comps[j].plan, rows_total);
+  // key: every pointer and scalar the captured launches bake in
+  std::vector<uint64_t> key;
+  auto kp = [&](const void *p) { key.push_back((uint64_t)(uintptr_t)p); };
+  auto kv = [&](int64_t v) { key.push_back((uint64_t)v); };
+  kp(st.X.p); kp(st.mask.p); kp(st.maskT.p); kp(st.dn.p); kp(ds->w.p); kp(ctx->mixArena.p); kp(ctx->mixArenaQ.p);
+  kp(ctx->mixStats.p); kp(LP_full); kp(ctx->logw.p); kp(ctx->unsafe.p); kp(ctx->rscratch.p); kp(ctx->stream);
+  kv(st.n); kv(st.d); kv(M); kv(chunk); kv(ctx->gemm_mode); kv(ctx->slices); kv(guard_on(ctx) ? ctx->guard_bits : -1);
+  kv((int64_t)need); kv((int64_t)need_q);
+  for (int j = 0; j < M; ++j) kv(mv.ks[j]);
+  for (auto &g : ctx->mix_graphs)
+    if (g.key == key) {
+      CUDA_CHECK(cudaGraphLaunch(g.exec, ctx->stream));
+      ctx->launches += g.launches;
+      for (int v = 0; v < V_COUNT; ++v) ctx->variants[v] += g.variants[v];
+      ++ctx->graph_replays;
+      ++ctx->variants[V_GRAPH_REPLAYS];
+      return;
+    }
+  bool seen = false;
+  for (auto &k2 : ctx->mix_seen) seen = seen || k2 == key;
+  if (!seen) {  // first pass with this key runs eagerly (one-time kernel attributes, buffer growth), the next one is captured
+    if (ctx->mix_seen.size() >= 8) ctx->mix_seen.erase(ctx->mix_seen.begin());
+    ctx->mix_seen.push_back(key);
+    run_loop();
+    return;
+  }
+  const int64_t launches0 = ctx->launches;
+  int64_t variants0[V_COUNT];
+  for (int v = 0; v < V_COUNT; ++v) variants0[v] = ctx->variants[v];
+  cudaGraph_t graph = nullptr;
+  ppca_b200_ctx::MixGraph g;
+  g.key = key;
+  bool captured = false;
+  if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
+    try {
+      run_loop();
+      captured = true;
+    } catch (...) {
+    }
+    const cudaError_t ee = cudaStreamEndCapture(ctx->stream, &graph);
+    captured = captured && ee == cudaSuccess && graph != nullptr;
+    if (captured) captured = cudaGraphInstantiate(&g.exec, graph, 0) == cudaSuccess;
+    if (graph) cudaGraphDestroy(graph);
+  }
+  if (!captured) {  // something in the loop is not capturable on this driver: run it the ordinary way from now on
+    cudaGetLastError();
+    ctx->launches = launches0;
+    for (int v = 0; v < V_COUNT; ++v) ctx->variants[v] = variants0[v];
+    ctx->use_graphs = false;
+    run_loop();
+    return;
+  }
+  g.launches = ctx->launches - launches0;
+  for (int v = 0; v < V_COUNT; ++v) g.variants[v] = ctx->variants[v] - variants0[v];
+  CUDA_CHECK(cudaGraphLaunch(g.exec, ctx->stream));
+  ++ctx->graph_replays;
+  ++ctx->variants[V_GRAPH_REPLAYS];
+  if (ctx->mix_graphs.size() >= 4) {
+    // the oldest graph may still be executing on the stream: drain before destroying it
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    cudaGraphExecDestroy(ctx->mix_graphs.front().exec);
+    ctx->mix_graphs.erase(ctx->mix_graphs.begin());
+  }
+  ctx->mix_graphs.push_back(std::move(g));
 }
 
 void mix_iterate_impl(ppca_b200_ctx *ctx, const ppca_b200_dataset *ds, int32_t m, const int32_t *ks, const double *Cs,
@@ -2849,6 +2942,65 @@ int32_t ppca_b200_iterate_host_sharded(ppca_b200_ctx *ctx, const double *x, int6
       comm_allreduce(ctx->comm, ctx->stats.p, slen, 0, ctx->stream);
       return em_finish_impl(ctx, d, k, C, mu, sigma, prior, ctx->stats.p, C_out, mu_out, sigma_out, llk_in, nullptr);
     });
+  });
+}
+
+// EM step over rows [row_begin, row_begin + nrows) of the synthetic dataset (ppca_b200_dataset_synthetic with the same
+// d, k_true, sigma_true, mask_prob, seed and a single component) WITHOUT storing them: every chunk is regenerated on the
+// device (counter-based RNG keyed by the global row), ingested into a chunk-sized store and consumed.  This is how a job
+// larger than HBM (BASELINE configs[2]: N = 100 M x d = 2048 = 1.6 TB) runs at kernel speed on any number of GPUs:
+// `sharded` != 0 all-reduces the statistics over the context's communicator before the finish, as
+// ppca_b200_iterate_sharded does.  The result equals ppca_b200_iterate on the stored rows up to summation order.
+int32_t ppca_b200_iterate_generated(ppca_b200_ctx *ctx, int64_t row_begin, int64_t nrows, int32_t d, int32_t k_true,
+                                    double sigma_true, double mask_prob, uint64_t seed, int32_t k, const double *C,
+                                    const double *mu, double sigma, const ppca_b200_prior *prior, int32_t sharded,
+                                    double *C_out, double *mu_out, double *sigma_out, double *llk_in) {
+  return guarded([&] {
+    REQUIRE(ctx != nullptr, "null context");
+    REQUIRE(row_begin >= 0 && nrows >= 0 && d >= 1 && k_true >= 1, "bad synthetic shape");
+    REQUIRE(mask_prob >= 0.0 && mask_prob <= 1.0, "invalid mask probability");
+    REQUIRE(!sharded || ctx->comm != nullptr, "no communicator: call ppca_b200_comm_init first");
+    if (nrows == 0 && !sharded) PPCA_THROW(PPCA_ERR_EMPTY, "non-empty dataset required (ppca_model.rs:358)");
+    DeviceGuard g(ctx->device);
+    const int64_t slen = StatsLayout(d, k).len;
+    DevBuf<double> Ct, mut;
+    Ct.alloc((size_t)d * k_true);
+    mut.alloc((size_t)d);
+    launch_synth_truth(ctx->L(), d, k_true, 1, seed, Ct.p, mut.p);
+    run_guarded(ctx, [&] {
+      DevModel m = stage_model(ctx, d, k, C, mu, sigma);
+      ctx->stats.reserve((size_t)slen);
+      if (nrows == 0) {
+        CUDA_CHECK(cudaMemsetAsync(ctx->stats.p, 0, sizeof(double) * slen, ctx->stream));
+      } else {
+        const EmPlan p = em_begin(ctx, pick_chunk(ctx, round_up(nrows, 256), m.s), m, ctx->stats.p);
+        const int64_t blk = p.chunk, tail = nrows % blk;
+        if (nrows >= blk && (!ctx->s_store || ctx->s_store->n != blk || ctx->s_store->d != d)) ctx->s_store = make_store(ctx, blk, d);
+        if (tail && (!ctx->s_tail || ctx->s_tail->n != tail || ctx->s_tail->d != d)) ctx->s_tail = make_store(ctx, tail, d);
+        ctx->s_w.reserve((size_t)round_up(std::min(nrows, blk), 256));
+        DevBuf<double> gws;
+        gws.alloc(synth_ws_doubles(std::min(nrows, blk), d, k_true));
+        const Launcher L = ctx->L();
+        for (int64_t r0 = 0; r0 < nrows; r0 += blk) {
+          const int64_t rows = std::min<int64_t>(blk, nrows - r0);
+          SampleStore &st = rows == blk ? *ctx->s_store : *ctx->s_tail;
+          launch_generate_block(L, st, rows, row_begin + r0, k_true, Ct.p, mut.p, sigma_true, mask_prob, seed, gws.p);
+          launch_transpose_mask(L, st);
+          CUDA_CHECK(cudaMemsetAsync(ctx->s_w.p, 0, sizeof(double) * st.n_pad, ctx->stream));
+          const int64_t want = (rows + 255) / 256;
+          const int blocks = (int)(want < (int64_t)ctx->sms * 8 ? want : (int64_t)ctx->sms * 8);
+          fill_value_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->s_w.p, rows, 1.0);
+          CUDA_CHECK(cudaGetLastError());
+          ++ctx->launches;
+          em_chunk(ctx, st, ctx->s_w.p, 0, (int)rows, m, ctx->stats.p, p);
+        }
+        em_end(ctx, m, ctx->stats.p, p);
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));  // the generator workspace is released here
+      }
+      if (sharded) comm_allreduce(ctx->comm, ctx->stats.p, slen, 0, ctx->stream);
+      return em_finish_impl(ctx, d, k, C, mu, sigma, prior, ctx->stats.p, C_out, mu_out, sigma_out, llk_in, nullptr);
+    });
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));  // the truth tables are released on return
   });
 }
 

@@ -160,6 +160,7 @@ struct DevModel {
   const double *mu;    // d32
   const double *Ksym;  // d32 x kkp  (zero padded rows and columns)
   const ModelWs *ws = nullptr;  // null = the context's buffers
+  const double *sigma_dev = nullptr;  // device copy of sigma (mixture passes: lets the chunk loop replay from a CUDA graph)
 };
 
 // Kernel variants whose selection depends on the shape: counted per context so that tests can assert which code path
@@ -180,7 +181,7 @@ enum Variant {
   V_SOLVE_GENERIC,
   V_PRECISION_RETRY,  // passes repeated at a wider arithmetic after the precision guard fired
   V_TC_MIX,           // batched mixture contraction launches
-  V_RESERVED15,
+  V_GRAPH_REPLAYS,    // mixture chunk loops replayed from a captured CUDA graph instead of launched one by one
   V_COUNT
 };
 
@@ -217,6 +218,12 @@ void launch_export(const Launcher &L, const SampleStore &st, int64_t row0, int64
 void launch_empty_dims(const Launcher &L, const SampleStore &st, uint8_t *out_dev);
 void launch_synthetic(const Launcher &L, SampleStore &st, int k_true, double sigma_true, double mask_prob,
                       int n_components, uint64_t seed);
+void launch_synth_truth(const Launcher &L, int d, int k_true, int n_components, uint64_t seed, double *Ct_dev, double *mut_dev);
+// fast single-model generator (Xi -> DMMA row GEMM -> noise + mask): rows [row_offset, row_offset + rows) of the dataset into
+// local rows [0, rows) of st; ws = synth_ws_doubles(rows, d, k) doubles of workspace
+size_t synth_ws_doubles(int64_t rows, int d, int k);
+void launch_generate_block(const Launcher &L, SampleStore &st, int64_t rows, int64_t row_offset, int k, const double *C_dev,
+                           const double *mu_dev, double sigma, double mask_prob, uint64_t seed, double *ws);
 // mixture / posterior sampling (sample_general_kernel, ingest.cu); every pointer is a device pointer
 struct SamplerArgs {
   int64_t n;
@@ -279,6 +286,7 @@ void launch_rowgemm(const Launcher &L, const double *A, int lda, int rows_pad, i
 struct SolveArgs {
   Shape s;
   double sigma;
+  const double *sigma_dev = nullptr;  // when set the kernels read sigma from here (graph replays see the current model)
   int rows;            // valid samples in the chunk
   int rows_pad;        // rows of GW / YZ to (zero) fill, multiple of 32
   double *GW;          // rows_pad x kkp : in G (packed upper), out W = w (z z^T + Sigma)  [mode EM]

@@ -194,14 +194,20 @@ __global__ void synth_truth_kernel(int d, int k_true, int n_components, uint64_t
 }
 
 // one warp per sample
+// row_offset: the block's first row in the dataset the counters are keyed on (a chunk regenerated on its own is the
+// same rows a resident dataset of the whole job would hold); rows are written from local row 0
 __global__ void __launch_bounds__(256) synth_kernel(int64_t n, int d, int k_true, int n_components, double sigma_true,
                                                     double mask_prob, uint64_t seed, const double *__restrict__ Ct,
                                                     const double *__restrict__ mut, double *X, int ldx, uint32_t *mask,
-                                                    int dw, int *dn) {
+                                                    int dw, int *dn, int64_t row_offset) {
   extern __shared__ double xi_all[];  // warps x k_true
   const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
-  const int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-  if (row >= n) return;
+  const int64_t lrow = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (lrow >= n) return;
+  const int64_t row = lrow + row_offset;
+  X += (lrow - row) * (int64_t)ldx;  // outputs are indexed by the local row
+  mask += (lrow - row) * (int64_t)dw;
+  dn += (lrow - row);
   double *xi = xi_all + wi * k_true;
   for (int a = lane; a < k_true; a += 32) xi[a] = rng_normal(seed, 3, (uint64_t)row * k_true + a);
   __syncwarp();
@@ -228,6 +234,26 @@ __global__ void __launch_bounds__(256) synth_kernel(int64_t n, int d, int k_true
   if (lane == 0) dn[row] = count;
 }
 
+void launch_generate_rows(const Launcher &L, int d, double *X, int ldx, uint32_t *mask, int dw, int *dn, int64_t rows,
+                          int64_t row_offset, int k, const double *C_dev, const double *mu_dev, double sigma, double mask_prob,
+                          uint64_t seed, double *ws);
+size_t synth_ws_doubles(int64_t rows, int d, int k);
+
+// rows of a resident dataset through the fast generator, block by block (the GEMM workspace is rows x d doubles)
+static void generate_resident(const Launcher &L, SampleStore &st, int k, const double *C_dev, const double *mu_dev, double sigma,
+                              double mask_prob, uint64_t seed) {
+  const int64_t blk = std::max<int64_t>(128, std::min<int64_t>(((int64_t)1 << 30) / ((int64_t)st.d * 8) / 128 * 128, 1 << 18));
+  DevBuf<double> ws;
+  if (st.n <= 0) return;
+  ws.alloc(synth_ws_doubles(std::min<int64_t>(blk, st.n), st.d, k));
+  for (int64_t r0 = 0; r0 < st.n; r0 += blk) {
+    const int64_t rows = std::min<int64_t>(blk, st.n - r0);
+    launch_generate_rows(L, st.d, st.X.p + r0 * st.ldx, st.ldx, st.mask.p + r0 * st.dw, st.dw, st.dn.p + r0, rows, r0, k, C_dev,
+                         mu_dev, sigma, mask_prob, seed, ws.p);
+  }
+  CUDA_CHECK(cudaStreamSynchronize(L.stream));  // ws is freed on return
+}
+
 void launch_synthetic(const Launcher &L, SampleStore &st, int k_true, double sigma_true, double mask_prob,
                       int n_components, uint64_t seed) {
   DevBuf<double> Ct, mut;
@@ -236,29 +262,141 @@ void launch_synthetic(const Launcher &L, SampleStore &st, int k_true, double sig
   synth_truth_kernel<<<L.sms * 4, 256, 0, L.stream>>>(st.d, k_true, n_components, seed, Ct.p, mut.p);
   CUDA_CHECK(cudaGetLastError());
   ++*L.launch_counter;
+  if (n_components == 1) {
+    generate_resident(L, st, k_true, Ct.p, mut.p, sigma_true, mask_prob, seed);
+    return;
+  }
   const int threads = 256;
   const int64_t blocks = (st.n * 32 + threads - 1) / threads;
   const size_t smem = sizeof(double) * (threads / 32) * k_true;
   synth_kernel<<<(unsigned)blocks, threads, smem, L.stream>>>(st.n, st.d, k_true, n_components, sigma_true, mask_prob,
                                                               seed, Ct.p, mut.p, st.X.p, st.ldx, st.mask.p, st.dw,
-                                                              st.dn.p);
+                                                              st.dn.p, 0);
   CUDA_CHECK(cudaGetLastError());
   ++*L.launch_counter;
   CUDA_CHECK(cudaStreamSynchronize(L.stream));  // Ct / mut are freed on return
 }
 
 
+// ---------------------------------------------------------------------------------------------
+// Fast single-model generator: x = C xi + mu + sigma eps as a dense FP64 row GEMM (DMMA, launch_rowgemm) between two
+// streaming kernels, for any block of rows of the dataset — every counter is keyed by the GLOBAL row, so a block
+// regenerated on its own is bit-identical to the same rows of a resident dataset.  Used by Dataset.synthetic (one
+// component), PPCAModel.sample and the out-of-core path that regenerates every chunk (ppca_b200_iterate_generated).
+// The one-warp-per-sample synth_kernel above (k loads + k FMAs per element) stays for mixtures of truths.
+// ---------------------------------------------------------------------------------------------
+__global__ void synth_xi_kernel(int64_t rows, int64_t rows_pad, int k, int kpad, uint64_t seed, int64_t row_offset,
+                                double *__restrict__ Xi) {
+  const int64_t total = rows_pad * kpad;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = idx / kpad;
+    const int a = (int)(idx % kpad);
+    Xi[idx] = (r < rows && a < k) ? rng_normal(seed, 3, (uint64_t)(row_offset + r) * k + a) : 0.0;
+  }
+}
+
+// Bt[a][i] = C[i][a], zero padded to kpad x n8 (the right operand layout of launch_rowgemm)
+__global__ void synth_bt_kernel(const double *__restrict__ C, int d, int k, int kpad, int n8, double *__restrict__ Bt) {
+  const int64_t total = (int64_t)kpad * n8;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int a = (int)(idx / n8), i = (int)(idx % n8);
+    Bt[idx] = (a < k && i < d) ? C[(int64_t)i * k + a] : 0.0;
+  }
+}
+
+// one warp per sample: x = Y + mu + sigma eps, mask bit ~ Bernoulli(1 - mask_prob).  One Box-Muller pair serves the two
+// elements 32 j + lane and 32 (j + 1) + lane of a pair of mask words.
+__global__ void __launch_bounds__(256) synth_finish_kernel(int64_t rows, int d, int n8, const double *__restrict__ Y,
+                                                           const double *__restrict__ mu, double sigma, double mask_prob,
+                                                           uint64_t seed, int64_t row_offset, double *X, int ldx,
+                                                           uint32_t *mask, int dw, int *dn) {
+  const int lane = threadIdx.x & 31;
+  const int64_t lrow = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (lrow >= rows) return;
+  const uint64_t grow = (uint64_t)(row_offset + lrow);
+  const int pairs = (dw + 1) / 2;
+  const double *y = Y + lrow * (int64_t)n8;
+  double *xo = X + lrow * (int64_t)ldx;
+  int count = 0;
+  for (int jp = 0; jp < pairs; ++jp) {
+    const uint64_t c = (grow * pairs + jp) * 32 + lane;
+    const double u1 = rng_uniform(seed, 5, 2 * c), u2 = rng_uniform(seed, 5, 2 * c + 1);
+    const double r = sigma * sqrt(-2.0 * log(u1));
+    double sn, cs;
+    sincospi(2.0 * u2, &sn, &cs);
+    const double eps[2] = {r * cs, r * sn};
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int j = 2 * jp + h;
+      if (j >= dw) break;
+      const int i = 32 * j + lane;
+      double x = 0.0;
+      bool obs = false;
+      if (i < d) {
+        x = (y[i] + mu[i]) + eps[h];
+        obs = !(rng_uniform(seed, 6, grow * d + i) < mask_prob);
+      }
+      const uint32_t word = __ballot_sync(0xffffffffu, obs);
+      if (i < ldx) xo[i] = obs ? x : 0.0;
+      if (lane == 0) mask[lrow * dw + j] = word;
+      count += __popc(word);
+    }
+  }
+  if (lane == 0) dn[lrow] = count;
+}
+
+size_t synth_ws_doubles(int64_t rows, int d, int k) {  // workspace of one block: Xi | Y | Bt | zeros | ones (as doubles)
+  const int64_t rows_pad = (rows + 127) / 128 * 128;
+  const int kpad = (k + 31) / 32 * 32, n8 = (d + 7) / 8 * 8;
+  return (size_t)rows_pad * kpad + (size_t)rows_pad * n8 + (size_t)kpad * n8 + (size_t)kpad + (size_t)kpad / 32 + 8 +
+         (size_t)rows_pad;
+}
+
+// rows [row_offset, row_offset + rows) of the dataset into local rows [0, rows) of st; C_dev: d x k dense, mu_dev: d
+void launch_generate_rows(const Launcher &L, int d, double *X, int ldx, uint32_t *mask, int dw, int *dn, int64_t rows,
+                          int64_t row_offset, int k, const double *C_dev, const double *mu_dev, double sigma, double mask_prob,
+                          uint64_t seed, double *ws) {
+  if (rows <= 0) return;
+  const int64_t rows_pad = (rows + 127) / 128 * 128;
+  const int kpad = (k + 31) / 32 * 32, n8 = (d + 7) / 8 * 8;
+  double *Xi = ws, *Y = Xi + rows_pad * kpad, *Bt = Y + rows_pad * n8, *zeros = Bt + (size_t)kpad * n8;
+  uint32_t *ones = reinterpret_cast<uint32_t *>(zeros + kpad);
+  double *nxs = zeros + kpad + kpad / 32 + 8;
+  CUDA_CHECK(cudaMemsetAsync(zeros, 0, sizeof(double) * kpad, L.stream));
+  CUDA_CHECK(cudaMemsetAsync(ones, 0xff, sizeof(uint32_t) * (kpad / 32), L.stream));
+  const int gb = (int)std::min<int64_t>((int64_t)L.sms * 16, (rows_pad * kpad + 255) / 256);
+  synth_xi_kernel<<<gb, 256, 0, L.stream>>>(rows, rows_pad, k, kpad, seed, row_offset, Xi);
+  CUDA_CHECK(cudaGetLastError());
+  const int bb = (int)std::min<int64_t>((int64_t)L.sms * 16, ((int64_t)kpad * n8 + 255) / 256);
+  synth_bt_kernel<<<bb, 256, 0, L.stream>>>(C_dev, d, k, kpad, n8, Bt);
+  CUDA_CHECK(cudaGetLastError());
+  *L.launch_counter += 2;
+  launch_rowgemm(L, Xi, kpad, (int)rows_pad, kpad, Bt, n8, ones, zeros, Y, nxs);
+  const int64_t fb = (rows * 32 + 255) / 256;
+  synth_finish_kernel<<<(unsigned)fb, 256, 0, L.stream>>>(rows, d, n8, Y, mu_dev, sigma, mask_prob, seed, row_offset, X, ldx,
+                                                          mask, dw, dn);
+  CUDA_CHECK(cudaGetLastError());
+  ++*L.launch_counter;
+}
+
+void launch_generate_block(const Launcher &L, SampleStore &st, int64_t rows, int64_t row_offset, int k, const double *C_dev,
+                           const double *mu_dev, double sigma, double mask_prob, uint64_t seed, double *ws) {
+  launch_generate_rows(L, st.d, st.X.p, st.ldx, st.mask.p, st.dw, st.dn.p, rows, row_offset, k, C_dev, mu_dev, sigma, mask_prob,
+                       seed, ws);
+}
+
+// Truth tables of the synthetic generator (Ct d x k_true, mut d per component), kept by the caller
+void launch_synth_truth(const Launcher &L, int d, int k_true, int n_components, uint64_t seed, double *Ct_dev, double *mut_dev) {
+  synth_truth_kernel<<<L.sms * 4, 256, 0, L.stream>>>(d, k_true, n_components, seed, Ct_dev, mut_dev);
+  CUDA_CHECK(cudaGetLastError());
+  ++*L.launch_counter;
+}
+
 // PPCAModel::sample (ppca_model.rs:164-191) with a caller-supplied model: x = C xi + mu + sigma eps, masked with
 // probability mask_prob; C_dev is the dense d x k transform, mu_dev the mean (both on the device).
 void launch_model_sample(const Launcher &L, SampleStore &st, int k, const double *C_dev, const double *mu_dev,
                          double sigma, double mask_prob, uint64_t seed) {
-  const int threads = 256;
-  const int64_t blocks = (st.n * 32 + threads - 1) / threads;
-  const size_t smem = sizeof(double) * (threads / 32) * k;
-  synth_kernel<<<(unsigned)blocks, threads, smem, L.stream>>>(st.n, st.d, k, 1, sigma, mask_prob, seed, C_dev, mu_dev,
-                                                              st.X.p, st.ldx, st.mask.p, st.dw, st.dn.p);
-  CUDA_CHECK(cudaGetLastError());
-  ++*L.launch_counter;
+  generate_resident(L, st, k, C_dev, mu_dev, sigma, mask_prob, seed);
 }
 
 

@@ -53,8 +53,9 @@ __global__ void __launch_bounds__(256) solve_kernel(SolveArgs a) {
   double *M = smem_solve + (size_t)wi * lay.per_warp;  // (k+1) x ldk ; row k = y^T
   double *dinv = M + (k + 1) * ldk;                    // 1 / L_pp
   double *zv = dinv + k;
-  const double s2 = a.sigma * a.sigma;
-  const double ln_sigma = log(a.sigma);
+  const double sigma = a.sigma_dev ? *a.sigma_dev : a.sigma;  // device copy: the launch can be replayed from a CUDA graph
+  const double s2 = sigma * sigma;
+  const double ln_sigma = log(sigma);
 
   for (int row = blockIdx.x * warps + wi; row < a.rows_pad; row += gridDim.x * warps) {
     double *G = a.GW ? a.GW + (int64_t)row * kkp : nullptr;
@@ -234,8 +235,9 @@ __global__ void __launch_bounds__(256, MINB) solve_reg_kernel(SolveArgs a) {
   double *cmw = smem_reg + (size_t)warps * per_warp + (size_t)wi * (SPW * kkp);
   if (a.colmax)
     for (int q = lane; q < SPW * kkp; q += 32) cmw[q] = 0.0;
-  const double s2 = a.sigma * a.sigma;
-  const double ln_sigma = log(a.sigma);
+  const double sigma = a.sigma_dev ? *a.sigma_dev : a.sigma;  // device copy: the launch can be replayed from a CUDA graph
+  const double s2 = sigma * sigma;
+  const double ln_sigma = log(sigma);
   const int groups = (a.rows_pad + SPW - 1) / SPW;
   // row li of the packed symmetric matrix: (li, j >= li) sits at up + j, (j < li, li) at j (2k - j - 1) / 2 + li.
   // The gather offsets do not depend on the sample: computed once (padding lanes / columns: -1).
@@ -424,8 +426,9 @@ __global__ void __launch_bounds__(256, MINB) solve_split64_kernel(SolveArgs a) {
   double *cmw = smem_reg + (size_t)2 * per_smp + (size_t)smp * kkp;  // running max |W| of this slot's samples
   if (a.colmax)
     for (int q = ws * 32 + lane; q < kkp; q += 128) cmw[q] = 0.0;
-  const double s2 = a.sigma * a.sigma;
-  const double ln_sigma = log(a.sigma);
+  const double sigma = a.sigma_dev ? *a.sigma_dev : a.sigma;  // device copy: the launch can be replayed from a CUDA graph
+  const double s2 = sigma * sigma;
+  const double ln_sigma = log(sigma);
 
   for (int row = blockIdx.x * 2 + smp; row < a.rows_pad; row += gridDim.x * 2) {
     double *gsrc = a.GW + (int64_t)row * kkp;
@@ -645,8 +648,9 @@ __global__ void __launch_bounds__(256, MINB) solve_tile_kernel(SolveArgs a) {
   double *cmw = smem_reg + (size_t)SPC * per_smp + (size_t)smp * kkp;  // running max |W| of this slot's samples
   if (a.colmax)
     for (int q = t; q < kkp; q += TPS) cmw[q] = 0.0;
-  const double s2 = a.sigma * a.sigma;
-  const double ln_sigma = log(a.sigma);
+  const double sigma = a.sigma_dev ? *a.sigma_dev : a.sigma;  // device copy: the launch can be replayed from a CUDA graph
+  const double s2 = sigma * sigma;
+  const double ln_sigma = log(sigma);
 
   for (int row = blockIdx.x * SPC + smp; row < a.rows_pad; row += gridDim.x * SPC) {
     double *gsrc = a.GW + (int64_t)row * kkp;

@@ -272,6 +272,38 @@ def _load_dataset(data: bytes) -> Dataset:
     return Dataset.load(data)
 
 
+class GeneratedDataset:
+    """Out-of-core SYNTHETIC dataset: rows [row_begin, row_begin + n) of what `Dataset.synthetic(N, d, k_true, sigma_true,
+    mask_prob, seed=seed)` would hold, never stored — every EM step regenerates each chunk on the device from the
+    counter-based RNG and consumes it (`ppca_b200_iterate_generated`).  This is how BASELINE configs[2] (N = 100 M,
+    d = 2048: 1.6 TB) runs at kernel speed on 1 ... 8 GPUs; a rank of a sharded job passes its own row range.
+    Accepted by `PPCAModel.iterate / iterate_with_prior / _iterate`."""
+
+    def __init__(self, n: int, d: int, k_true: int, sigma_true: float = 0.1, mask_prob: float = 0.2,
+                 seed: int = 20240531, row_begin: int = 0, ctx: Optional[nat.Context] = None):
+        if n < 0 or d < 1 or k_true < 1 or row_begin < 0:
+            raise ValueError("bad synthetic shape")
+        self._ctx = ctx or nat.get_context()
+        self.n, self.d, self.k_true = int(n), int(d), int(k_true)
+        self.sigma_true, self.mask_prob, self.seed, self.row_begin = float(sigma_true), float(mask_prob), int(seed), int(row_begin)
+
+    def __len__(self) -> int:
+        return self.n
+
+    def _output_size(self) -> int:
+        return self.d
+
+    def output_size(self) -> int:
+        return self.d
+
+    def materialize(self) -> "Dataset":
+        """The same rows as a resident Dataset (for tests / small sizes)."""
+        if self.row_begin == 0:
+            return Dataset.synthetic(self.n, self.d, self.k_true, self.sigma_true, self.mask_prob, 1, self.seed, self._ctx)
+        return Dataset.synthetic(self.row_begin + self.n, self.d, self.k_true, self.sigma_true, self.mask_prob, 1,
+                                 self.seed, self._ctx)._slice(self.row_begin, self.n)
+
+
 class HostDataset:
     """Out-of-core dataset: the samples stay in (page-locked) HOST memory and are streamed through the GPU block by
     block on every EM step (`ppca_b200_iterate_host`), the H2D copy of one block overlapping the kernels of the
@@ -623,6 +655,12 @@ class PPCAModel:
             pr, keep = prior._c(d)
             pr_ref = C.byref(pr)
         lib = nat.lib()
+        if isinstance(dataset, GeneratedDataset):
+            nat.check(lib.ppca_b200_iterate_generated(
+                dataset._ctx.handle, dataset.row_begin, dataset.n, d, dataset.k_true, dataset.sigma_true, dataset.mask_prob,
+                dataset.seed, k, nat.dptr(self._C), nat.dptr(self._mu), self._sigma, pr_ref, 1 if sharded else 0,
+                nat.dptr(C_out), nat.dptr(mu_out), C.byref(s_out), C.byref(llk)))
+            return PPCAModel(s_out.value, C_out, mu_out), llk.value
         if isinstance(dataset, HostDataset) and dataset._packed is not None:
             vals, rowptr, maskw = dataset._packed
             fn = lib.ppca_b200_iterate_packed_host_sharded if sharded else lib.ppca_b200_iterate_packed_host

@@ -1246,3 +1246,73 @@ def test_full_covariances_on_device(pk, orc, n, d, k):
         exj = [np.where(np.isfinite(X[i]), X[i], v) for v in smj]
         assert rel_err(msm[i], orc.mix_covariance(post[i], smj, cj)) < 1e-11
         assert rel_err(mex[i], orc.mix_covariance(post[i], exj, cj)) < 1e-11
+
+
+@pytest.mark.parametrize("chunk", [0, 1024])
+def test_generated_dataset_equals_the_stored_rows(pk, orc, chunk):
+    """ppca_b200_iterate_generated (chunks regenerated on the device, never stored: the out-of-core form of BASELINE
+    configs[2]) gives the EM step of the same rows held as a resident Dataset, for a row range that starts past row 0."""
+    n, d, k_true, k = 5000, 70, 6, 5
+    ctx = pk.get_context()
+    gen = pk.GeneratedDataset(n, d, k_true, 0.1, 0.3, seed=99, row_begin=1234)
+    stored = gen.materialize()
+    assert len(stored) == n
+    whole = pk.Dataset.synthetic(1234 + n, d, k_true, 0.1, 0.3, seed=99).numpy()
+    assert np.array_equal(stored.numpy(), whole[1234:], equal_nan=True)
+    _, C0, mu0, s0 = _case(50, d, k, 0.2, seed=3)
+    model = pk.PPCAModel(s0, C0, mu0)
+    ctx.set_chunk(chunk)
+    try:
+        a, la = model._iterate(gen, None)
+    finally:
+        ctx.set_chunk(0)
+    b, lb = model._iterate(stored, None)
+    assert abs(la - lb) <= 1e-12 * abs(lb)
+    assert rel_err(a.transform, b.transform) < 1e-11 and rel_err(a.mean, b.mean) < 1e-11
+    assert abs(a.isotropic_noise - b.isotropic_noise) < 1e-12 * b.isotropic_noise
+    X = stored.numpy()
+    (Cw, muw, sw), (Cs, mus, ss) = both(orc, orc.iterate, X, None, C0, mu0, s0)
+    assert_close(a.transform, Cw, Cs, "C")
+    assert_close(a.isotropic_noise ** 2, sw ** 2, ss ** 2, "sigma^2")
+    assert a.iterate(gen).llk(stored) > model.llk(stored)
+
+
+def test_mixture_chunk_loop_replays_from_a_cuda_graph(pk, orc):
+    """The mixture EM chunk loop (~30 launches per component and chunk) is captured into a CUDA graph the second time a
+    (dataset, shapes, buffers) key is seen and replayed afterwards; the replays must give the eager pass's numbers bit for
+    bit, follow a CHANGED model (sigma is read from device memory, not baked into the launches), and match the oracle."""
+    n, d = 3000, 24
+    X, base, logw = _mix_case(pk, n, d, (3, 5, 2))
+    w = np.random.default_rng(1).random(X.shape[0]) + 0.5
+    ds = pk.Dataset(X, w)
+
+    def make(scale):
+        return pk.PPCAMix([pk.PPCAModel(scale * s, C * (2.0 - scale) if scale != 1.0 else C, mu) for C, mu, s in base], logw)
+
+    ctx = pk.get_context()
+    ctx.set_chunk(1024)                       # three chunks: the running-maximum rescaling is inside the graph too
+    try:
+        mixA, mixB = make(1.0), make(1.7)
+        before = ctx.variant_counts()["graph_replays"]
+        outs = [mixA._iterate(ds, None) for _ in range(4)]          # eager, captured, replayed, replayed
+        replays = ctx.variant_counts()["graph_replays"] - before
+        assert replays >= 2, replays
+        for o, l in outs[1:]:
+            assert l == outs[0][1]
+            for a, b in zip(o.models, outs[0][0].models):
+                assert np.array_equal(a.transform, b.transform) and np.array_equal(a.mean, b.mean)
+                assert a.isotropic_noise == b.isotropic_noise
+            assert np.array_equal(o.log_weights, outs[0][0].log_weights)
+        got, llk = mixB._iterate(ds, None)                          # same key, different model: replayed again
+        assert ctx.variant_counts()["graph_replays"] - before == replays + 1
+    finally:
+        ctx.set_chunk(0)
+    models = [(m.transform, m.mean.reshape(-1), m.isotropic_noise) for m in mixB.models]
+    with orc.stable():
+        new_models, new_lw = orc.mix_iterate(X, w, models, mixB.log_weights)
+    assert abs(llk - orc.mix_llk(X, w, models, mixB.log_weights)) <= TOL * abs(llk)
+    for j, (Cw, muw, sw) in enumerate(new_models):
+        assert rel_err(got.models[j].transform, Cw) < TOL
+        assert rel_err(got.models[j].mean.reshape(-1), muw) < TOL
+        assert abs(got.models[j].isotropic_noise - sw) < TOL * sw
+    assert rel_err(got.log_weights, new_lw) < TOL
