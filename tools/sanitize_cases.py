@@ -91,6 +91,39 @@ def main():
         mix3 = mix2.iterate(pk.Dataset(X))
         ctx.set_chunk(0)
         print("mixture ok", mix3.log_weights, flush=True)
+    if os.environ.get("SANITIZE_R2B", "1") == "1" and not only:
+        # later round-2 kernels: register-tiled solve (k = 40 / 48 / 64 run above and in CASES), device samplers with the
+        # in-kernel Cholesky, full covariances, the fast generator and the regenerated-chunk EM, device ingestion, and the
+        # CUDA-graph replay of the mixture chunk loop
+        import torch
+        rng = np.random.default_rng(4)
+        d = 40
+        models = [pk.PPCAModel(0.4 + 0.1 * j, rng.standard_normal((d, kk)), rng.standard_normal(d)) for j, kk in enumerate((3, 5))]
+        mix = pk.PPCAMix(models, np.log([0.3, 0.7]))
+        data = mix.sample(700, 0.3, seed=2)
+        infm = mix.infer(data)
+        draw = infm.posterior_sampler().sample(seed=3)
+        one = models[1].infer(data)
+        draw1 = one.posterior_sampler().sample(seed=4)
+        cov = one.extrapolated_covariances(models[1], data)
+        assert np.isfinite(draw.numpy()).all() and np.isfinite(draw1.numpy()).all() and len(cov) == 700
+        print("samplers / full covariances ok", flush=True)
+        gen = pk.GeneratedDataset(1500, 70, 6, 0.1, 0.3, seed=5, row_begin=100)
+        C0, mu0, s0 = init_model(70, 5)
+        ctx.set_chunk(512)
+        m2, llk = pk.PPCAModel(s0, C0, mu0)._iterate(gen, None)
+        ctx.set_chunk(0)
+        t = torch.from_numpy(gen.materialize().numpy()).cuda()
+        ds = pk.Dataset.from_device(t[:, 3:60], torch.rand(1500, dtype=torch.float64, device="cuda") + 0.5)
+        back = ds.to_torch()
+        assert back.shape == (1500, 57) and np.isfinite(llk)
+        print("generated / device ingestion ok", flush=True)
+        X = make_data(1500, 64, 4, 0.2, seed=9)
+        mixg = pk.PPCAMix([pk.PPCAModel(1.0, *init_model(64, kk, seed=j)[:2][::1]) for j, kk in enumerate((4, 6, 3))], np.zeros(3))
+        dsg = pk.Dataset(X)
+        for _ in range(3):                      # eager, captured, replayed
+            mixg2 = mixg.iterate(dsg)
+        print("graph replays", ctx.variant_counts()["graph_replays"], flush=True)
     print("variant counts", {k: v for k, v in ctx.variant_counts().items() if v}, flush=True)
 
 
