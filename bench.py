@@ -491,6 +491,9 @@ def full_job_block(torch, pk, ctx, stream, dist, rank, world, local_rank, args, 
     wl = WORKLOADS["c3"]
     d, k = wl["d"], wl["k"]
     ds = pk.GeneratedDataset(rows, d, wl["k_true"], 0.1, wl["p"], seed=SEED + 501, row_begin=rank * rows, ctx=ctx)
+    if dist is not None:
+        from ppca_rs_b200 import distributed as pdist
+        pdist.native_comm_init(ctx, dist)          # no-op when an earlier block already built the communicator
     C, mu, s = init_params(d, k, SEED + 1000)
     state = {"model": pk.PPCAModel(s, C, mu), "llk": None}
 

@@ -58,6 +58,7 @@ struct ppca_b200_ctx {
   // chunk workspaces
   DevBuf<double> GW, YZ, WZ, nx, llk, tn, part_bg, part_cr, part_solve, stats, Cnew, cov, rbuf;
   DevBuf<double> mixLP, mixLlk, mixMax, mixSum, mixStats;  // mixture workspaces (grow-only, no per-call cudaMalloc)
+  DevBuf<double> gen_ws, gen_Ct, gen_mut;                  // regenerated-chunk EM: generator workspace and truth tables (grow-only)
   DevBuf<double> mixArena;                                 // single-pass mixture EM: per-component chunk buffers
   DevBuf<int8_t> mixArenaQ;                                //   ... and their digit planes
   DevBuf<int> flags;
@@ -2963,9 +2964,9 @@ int32_t ppca_b200_iterate_generated(ppca_b200_ctx *ctx, int64_t row_begin, int64
     if (nrows == 0 && !sharded) PPCA_THROW(PPCA_ERR_EMPTY, "non-empty dataset required (ppca_model.rs:358)");
     DeviceGuard g(ctx->device);
     const int64_t slen = StatsLayout(d, k).len;
-    DevBuf<double> Ct, mut;
-    Ct.alloc((size_t)d * k_true);
-    mut.alloc((size_t)d);
+    DevBuf<double> &Ct = ctx->gen_Ct, &mut = ctx->gen_mut;
+    Ct.reserve((size_t)d * k_true);
+    mut.reserve((size_t)d);
     launch_synth_truth(ctx->L(), d, k_true, 1, seed, Ct.p, mut.p);
     run_guarded(ctx, [&] {
       DevModel m = stage_model(ctx, d, k, C, mu, sigma);
@@ -2978,8 +2979,8 @@ int32_t ppca_b200_iterate_generated(ppca_b200_ctx *ctx, int64_t row_begin, int64
         if (nrows >= blk && (!ctx->s_store || ctx->s_store->n != blk || ctx->s_store->d != d)) ctx->s_store = make_store(ctx, blk, d);
         if (tail && (!ctx->s_tail || ctx->s_tail->n != tail || ctx->s_tail->d != d)) ctx->s_tail = make_store(ctx, tail, d);
         ctx->s_w.reserve((size_t)round_up(std::min(nrows, blk), 256));
-        DevBuf<double> gws;
-        gws.alloc(synth_ws_doubles(std::min(nrows, blk), d, k_true));
+        DevBuf<double> &gws = ctx->gen_ws;
+        gws.reserve(synth_ws_doubles(std::min(nrows, blk), d, k_true));
         const Launcher L = ctx->L();
         for (int64_t r0 = 0; r0 < nrows; r0 += blk) {
           const int64_t rows = std::min<int64_t>(blk, nrows - r0);
@@ -2995,12 +2996,10 @@ int32_t ppca_b200_iterate_generated(ppca_b200_ctx *ctx, int64_t row_begin, int64
           em_chunk(ctx, st, ctx->s_w.p, 0, (int)rows, m, ctx->stats.p, p);
         }
         em_end(ctx, m, ctx->stats.p, p);
-        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));  // the generator workspace is released here
       }
       if (sharded) comm_allreduce(ctx->comm, ctx->stats.p, slen, 0, ctx->stream);
       return em_finish_impl(ctx, d, k, C, mu, sigma, prior, ctx->stats.p, C_out, mu_out, sigma_out, llk_in, nullptr);
     });
-    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));  // the truth tables are released on return
   });
 }
 

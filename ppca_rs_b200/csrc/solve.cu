@@ -615,17 +615,25 @@ struct TileLayout {
   static constexpr int NTR = KD / TR, NTC = KD / TC, TPS = NTR * NTC, SPC = 256 / TPS, WPS = TPS / 32;
   static constexpr int SR = 6;  // pitch (doubles) of one thread's row group in the own-units exchange: 2 x odd keeps the
                                 // 128-bit reads of eight consecutive row groups on disjoint banks
-  static constexpr int EX = KD + NTR * SR + 2;  // true units | own units | next diagonal (+ pad)
-  // per sample: stage[kkp] | exch[2][EX] | yb[KD] | zb[KD] | zpart[NTC][KD] | piv[KD] | red[4 * 4]
-  static constexpr int FIXED = 2 * EX + 3 * KD + NTC * KD + 16;
+  // PW pivots per exchange (a "panel"): the rows and the columns of a panel each sit inside one thread tile
+  static constexpr int PW = (TR % 4 == 0 && TC % 4 == 0) ? 4 : 3;
+  static constexpr int PB = TR > TC ? TR : TC;          // pivots per unrolled block: static indices repeat with this period
+  // one exchange buffer: PW x (true units [KD] | own units, padded [NTR SR]) | PW 1/d | pad
+  static constexpr int EXQ = KD + NTR * SR;
+  static constexpr int EX = PW * EXQ + 4;
+  // per sample: stage[kkp] | exch[2][EX] (reused for the partial z sums after the elimination) | yb[KD] | zb[KD] | piv[KD] | red[16]
+  static constexpr int FIXED = 2 * EX + 3 * KD + 16;
   static_assert(KD % TR == 0 && KD % TC == 0 && TR % 2 == 0 && TC % 2 == 0 && TR <= SR, "tile shape");
-  static_assert(TPS % 32 == 0 && 256 % TPS == 0 && TPS >= KD && NTR >= 8, "thread layout");
+  static_assert(TPS % 32 == 0 && 256 % TPS == 0 && TPS >= KD && NTR >= 8 && 32 % NTR == 0, "thread layout");
+  static_assert(TR % PW == 0 && TC % PW == 0 && PB % TR == 0 && PB % TC == 0 && (PB / PW) % 2 == 0 && KD % PB == 0, "panels");
+  static_assert(2 * EX >= NTC * KD, "the partial z sums reuse the exchange buffers");
 };
 
 template <int KD, int TR, int TC, int MINB>
 __global__ void __launch_bounds__(256, MINB) solve_tile_kernel(SolveArgs a) {
   using LY = TileLayout<KD, TR, TC>;
   constexpr int NTR = LY::NTR, NTC = LY::NTC, TPS = LY::TPS, SPC = LY::SPC, WPS = LY::WPS, SR = LY::SR, EX = LY::EX;
+  constexpr int PW = LY::PW, PB = LY::PB, EXQ = LY::EXQ;
   extern __shared__ __align__(16) double smem_reg[];
   const int smp = threadIdx.x / TPS, t = threadIdx.x % TPS;
   const int tr = t % NTR, tc = t / NTR;
@@ -634,17 +642,16 @@ __global__ void __launch_bounds__(256, MINB) solve_tile_kernel(SolveArgs a) {
   const int bar_id = smp + 1;
   const int k = a.s.k, kkp = a.s.kkp, kp = a.s.kp;
   // rows / columns past k are identity padding whose pivots change nothing: whole pivot blocks past k are skipped
-  constexpr int PBLK = TR > TC ? TR : TC;
-  const int nblk = (k + PBLK - 1) / PBLK;
-  const int kpiv = nblk * PBLK;
+  const int nblk = (k + PB - 1) / PB;
+  const int kpiv = nblk * PB;
   const int per_smp = kkp + LY::FIXED;
   double *stage = smem_reg + (size_t)smp * per_smp;  // one packed row: G in, W out
   double *exch = stage + kkp;
   double *yb = exch + 2 * EX;
   double *zb = yb + KD;
-  double *zpart = zb + KD;
-  double *piv = zpart + NTC * KD;
+  double *piv = zb + KD;
   double *red = piv + KD;
+  double *zpart = exch;  // [NTC][KD], after the elimination
   double *cmw = smem_reg + (size_t)SPC * per_smp + (size_t)smp * kkp;  // running max |W| of this slot's samples
   if (a.colmax)
     for (int q = t; q < kkp; q += TPS) cmw[q] = 0.0;
@@ -683,83 +690,112 @@ __global__ void __launch_bounds__(256, MINB) solve_tile_kernel(SolveArgs a) {
       if (guard_terms((double)dn) * a.guard_coef * a.gscale[qd] > s2 + stage[qd]) atomicAdd(a.unsafe, 1u);
     }
 
-    // The pivot loop is unrolled over one block of PB pivots only (static register indices need p % TR, p % TC and the
-    // exchange-buffer parity at compile time, all periodic in PB); the blocks run in a real loop: fully unrolled, the 64
-    // pivot bodies were 140 KB of SASS, four times the instruction cache.  The body is BRANCH-FREE: every thread runs
-    // the publishers' arithmetic (1/sqrt(d), its column-p entries scaled) and only the stores are predicated.  With a
-    // branch around the publishers' section the serial chain  d -> 1/sqrt(d) -> s -> store -> barrier  sat behind the
-    // thread's own 32 FMAs and took half of every pivot (ncu source view: 350 of 730 cycles); in one basic block the
-    // compiler schedules the chain of pivot p + 1 (started right after the barrier of pivot p) under the FMAs of pivot p.
-    double dcur = (empty || k <= 0) ? 1.0 : s2 + stage[0];
-    double rinv = fast_rsqrt(dcur);
+    // PANEL-BLOCKED elimination: PW pivots per exchange.  The threads that hold the panel's columns ("publishers", one
+    // column block = NTR consecutive lanes) run the PW pivots of the panel among themselves — pivot values and the
+    // multipliers of the panel's own rows travel by warp shuffle from the lane that holds the panel's diagonal block —
+    // and publish all PW multiplier vectors at once; after ONE barrier every thread applies the PW rank-1 updates to its
+    // tile.  The arithmetic per element is the pivot-by-pivot sweep's, FMA for FMA (same order), so the results are bitwise
+    // those of the unblocked loop; what changes is the serial chain per sample: one (barrier, shared-memory round trip)
+    // per PW pivots instead of per pivot.  The loop is unrolled over one block of PB pivots (static register indices need
+    // p % TR, p % TC and the buffer parity at compile time, all periodic in PB; fully unrolled, 64 pivot bodies were 140 KB
+    // of SASS against a 32 KB instruction cache).  Measured history and the ncu analysis: profiles/r02_solve_tile.md — the
+    // kernel is bound by the publishers' serial chain (~400 cycles per pivot: shuffle, 1/sqrt, two multiplies, shuffle,
+    // FMA) with four samples resident per SM; a look-ahead variant (next panel's chain before the publishers' own
+    // remaining updates) was slower, because the publishers' warp stays the critical path and only gets more to do.
     double sc[TR];  // 1/d_i once row i has been swept (1 before): swept rows stay in their own units (d_i x true)
 #pragma unroll
     for (int ia = 0; ia < TR; ++ia) sc[ia] = 1.0;
-    constexpr int PB = PBLK;
-    static_assert(PB % TR == 0 && PB % TC == 0 && PB % 2 == 0 && KD % PB == 0, "pivot block");
-    constexpr int ND = KD + NTR * SR;  // slot of the next diagonal entry
+    const int gbase = (tc * NTR) & 31;  // first lane of this thread's column block within its warp
+    const unsigned gmask = NTR == 32 ? 0xffffffffu : (((1u << NTR) - 1u) << gbase);
     for (int pb = 0; pb < nblk; ++pb) {
 #pragma unroll
-      for (int pp = 0; pp < PB; ++pp) {
-        const int p = pb * PB + pp;
-        double *ex = exch + (pp & 1) * EX;  // [0, KD) s true units | [KD, ND) s own units, padded | [ND] next diagonal
-        const bool pub = tc == pb * (PB / TC) + pp / TC;    // this thread holds column p
-        const bool prow = tr == pb * (PB / TR) + pp / TR;   // this thread holds row p
-        {
-          double mine[TR], tv[TR];
+      for (int ps = 0; ps < PB / PW; ++ps) {
+        const int pp0 = ps * PW;             // first pivot of the panel within the block (compile time after unrolling)
+        const int p0 = pb * PB + pp0;
+        const int a0 = pp0 % TR, cl0 = pp0 % TC;  // the panel's rows / columns inside the tile that holds them
+        double *ex = exch + (ps & 1) * EX;
+        const bool pub = tc == pb * (PB / TC) + pp0 / TC;   // this thread holds the panel's columns
+        const bool prow = tr == pb * (PB / TR) + pp0 / TR;  // this thread holds the panel's rows
+        if (pub) {
+          const int dlane = gbase + pb * (PB / TR) + pp0 / TR;  // lane of the thread with the panel's diagonal block
+          double dq = __shfl_sync(gmask, A[a0][cl0], dlane);
 #pragma unroll
-          for (int ia = 0; ia < TR; ++ia) {
-            mine[ia] = A[ia][pp % TC] * rinv;
-            tv[ia] = mine[ia] * sc[ia];
-          }
-          if (pub) {
+          for (int q = 0; q < PW; ++q) {
+            const double dthis = dq;
+            const double rinv = fast_rsqrt(dthis);
+            double own[TR], tv[TR];
+#pragma unroll
+            for (int ia = 0; ia < TR; ++ia) own[ia] = A[ia][cl0 + q] * rinv;
+            if (q + 1 < PW) {
+              // next pivot d' = T[p+1][p+1] - s_{p+1}^2 straight from the diagonal lane (row p + 1 is not swept yet: its
+              // own units are the true units), ahead of the panel's other updates: bitwise what the loop below leaves there
+              const int n = q + 1 < PW ? q + 1 : q;
+              const double dn = fma(-own[a0 + n], own[a0 + n], A[a0 + n][cl0 + n]);
+              dq = __shfl_sync(gmask, dn, dlane);
+            }
+#pragma unroll
+            for (int ia = 0; ia < TR; ++ia) tv[ia] = own[ia] * sc[ia];
 #pragma unroll
             for (int ia = 0; ia < TR; ia += 2) {
-              *reinterpret_cast<double2 *>(ex + r0 + ia) = make_double2(tv[ia], tv[ia + 1]);
-              *reinterpret_cast<double2 *>(ex + KD + tr * SR + ia) = make_double2(mine[ia], mine[ia + 1]);
+              *reinterpret_cast<double2 *>(ex + q * EXQ + r0 + ia) = make_double2(tv[ia], tv[ia + 1]);
+              *reinterpret_cast<double2 *>(ex + q * EXQ + KD + tr * SR + ia) = make_double2(own[ia], own[ia + 1]);
+            }
+            if (prow) {
+              piv[p0 + q] = dthis;
+              ex[PW * EXQ + q] = rinv * rinv;
+            }
+            // the other columns of the panel (swept or not) take this pivot's update now: their column operands are the
+            // true-unit multipliers of the panel's own rows, which the diagonal lane holds
+#pragma unroll
+            for (int q2 = 0; q2 < PW; ++q2) {
+              if (q2 == q) continue;
+              const double sq = __shfl_sync(gmask, tv[a0 + q2], dlane);
+#pragma unroll
+              for (int ia = 0; ia < TR; ++ia) {
+                const double f = (prow && ia == a0 + q) ? 0.0 : own[ia];  // the pivot row is left as it is
+                A[ia][cl0 + q2] = fma(-f, sq, A[ia][cl0 + q2]);
+              }
+            }
+#pragma unroll
+            for (int ia = 0; ia < TR; ++ia) A[ia][cl0 + q] = own[ia] * rinv;  // T[i][p] = s_i / sqrt(d)
+            if (prow) {
+              A[a0 + q][cl0 + q] = -1.0;
+              sc[a0 + q] = rinv * rinv;
             }
           }
-          if (pub && prow) piv[p] = dcur;
         }
-        // owner of (p + 1, p + 1) adds that diagonal entry (after the last pivot of the matrix there is none)
-        if (tr == pb * (PB / TR) + (pp + 1) / TR && tc == pb * (PB / TC) + (pp + 1) / TC)
-          ex[ND] = A[(pp + 1) % TR][(pp + 1) % TC];
         sample_sync<TPS>(bar_id);
-        // d_{p+1} = T[p+1][p+1] - s_{p+1}^2, bitwise what the owner of (p + 1, p + 1) computes below (row p + 1 is not
-        // swept yet: its own units are the true units).  After the last pivot this reads padding and is not used.
-        const double sn = ex[p + 1];
-        dcur = fma(-sn, sn, ex[ND]);
-        const double rnext = fast_rsqrt(dcur);
-        double f[TR], cv[TC];
 #pragma unroll
-        for (int ia = 0; ia < TR; ia += 2) {
-          const double2 v = *reinterpret_cast<const double2 *>(ex + KD + tr * SR + ia);
-          f[ia] = v.x;
-          f[ia + 1] = v.y;
+        for (int q = 0; q < PW; ++q) {
+          double f[TR], cv[TC];
+#pragma unroll
+          for (int ia = 0; ia < TR; ia += 2) {
+            const double2 v = *reinterpret_cast<const double2 *>(ex + q * EXQ + KD + tr * SR + ia);
+            f[ia] = v.x;
+            f[ia + 1] = v.y;
+          }
+#pragma unroll
+          for (int jb = 0; jb < TC; jb += 2) {
+            const double2 v = *reinterpret_cast<const double2 *>(ex + q * EXQ + c0 + jb);
+            cv[jb] = v.x;
+            cv[jb + 1] = v.y;
+          }
+          f[a0 + q] = prow ? 0.0 : f[a0 + q];  // the pivot row is left as it is (its 1/d is applied at the end)
+#pragma unroll
+          for (int jq = 0; jq < PW; ++jq) cv[cl0 + jq] = pub ? 0.0 : cv[cl0 + jq];  // the publishers' panel columns are done
+#pragma unroll
+          for (int ia = 0; ia < TR; ++ia)
+#pragma unroll
+            for (int jb = 0; jb < TC; ++jb) A[ia][jb] = fma(-f[ia], cv[jb], A[ia][jb]);
         }
+        if (prow && !pub) {
 #pragma unroll
-        for (int jb = 0; jb < TC; jb += 2) {
-          const double2 v = *reinterpret_cast<const double2 *>(ex + c0 + jb);
-          cv[jb] = v.x;
-          cv[jb + 1] = v.y;
+          for (int q = 0; q < PW; ++q) sc[a0 + q] = ex[PW * EXQ + q];
         }
-        const double fp = f[pp % TR];
-        f[pp % TR] = prow ? 0.0 : fp;  // the pivot row is left as it is (its 1/d is applied at the end)
-#pragma unroll
-        for (int ia = 0; ia < TR; ++ia)
-#pragma unroll
-          for (int jb = 0; jb < TC; ++jb) A[ia][jb] = fma(-f[ia], cv[jb], A[ia][jb]);
-        f[pp % TR] = fp;
-#pragma unroll
-        for (int ia = 0; ia < TR; ++ia) {
-          const double cnew = f[ia] * rinv;  // T[i][p] = s_i / sqrt(d)
-          A[ia][pp % TC] = pub ? cnew : A[ia][pp % TC];
-        }
-        A[pp % TR][pp % TC] = (pub && prow) ? -1.0 : A[pp % TR][pp % TC];
-        sc[pp % TR] = prow ? rinv * rinv : sc[pp % TR];
-        rinv = rnext;
       }
     }
+
+    sample_sync<TPS>(bar_id);  // the partial z sums below reuse the exchange buffers
 
     // M^{-1}[i][j] = -(1/d_i) A[i][j]
     bool rlive[TR];
@@ -1099,6 +1135,11 @@ static void launch_solve_generic(const Launcher &L, const SolveArgs &a) {
   L.count(V_SOLVE_GENERIC);
 }
 
+static bool tile32_fits(const SolveArgs &a) {  // eight samples per CTA: the widest states with column maxima do not fit
+  using LY = TileLayout<32, 4, 8>;
+  return (size_t)LY::SPC * (a.s.kkp + LY::FIXED + (a.colmax ? a.s.kkp : 0)) * sizeof(double) <= 110 * 1024;
+}
+
 void launch_solve(const Launcher &L, const SolveArgs &a) {
   if (a.rows_pad <= 0) return;
   REQUIRE(a.mode == 0 || a.GW != nullptr, "solve: missing Gram buffer");
@@ -1111,7 +1152,7 @@ void launch_solve(const Launcher &L, const SolveArgs &a) {
   static const bool tile32 = getenv("PPCA_B200_SOLVE") && !strcmp(getenv("PPCA_B200_SOLVE"), "tile");
   if (a.s.k <= 8) launch_solve_reg<8>(L, a);
   else if (a.s.k <= 16) launch_solve_reg<16>(L, a);
-  else if (a.s.k <= 64 && !rows_layout && (a.s.k > 32 || tile32)) {
+  else if (a.s.k <= 64 && !rows_layout && (a.s.k > 32 || (tile32 && tile32_fits(a)))) {
     if (a.s.k <= 32) launch_solve_tile<32, 4, 8, 2>(L, a);
     else if (a.s.k <= 48) launch_solve_tile<48, 6, 6, 2>(L, a);
     else launch_solve_tile<64, 4, 8, 2>(L, a);
