@@ -507,7 +507,7 @@ def test_reference_big_toy_model_flow(pk):
 
 
 @pytest.mark.parametrize("script", ["toy_model.py", "big_toy_model.py", "ppca_mixture.py",
-                                    "priors_pickling_empty_dimensions.py"])
+                                    "priors_pickling_empty_dimensions.py", "device_resident_and_out_of_core.py"])
 def test_examples_run_unmodified_ppca_rs_calls(script, capsys):
     """examples/ use the reference's import lines (`from ppca_rs import ...`, `from ppca_rs.ppca_rs import ...`) through
     ppca_rs_b200.compat.install_as_ppca_rs()."""

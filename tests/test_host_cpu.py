@@ -383,3 +383,37 @@ def test_pack_host_builds_the_compact_format_without_a_gpu():
     bits[:, :d] = fin
     want = np.packbits(bits, axis=1, bitorder="little").view(np.uint32).reshape(n, dw)
     assert np.array_equal(maskw, want)
+
+
+def test_device_ingestion_front_end_validates_its_inputs():
+    """Dataset.from_device (ppca_b200_dataset_from_device): the host-side checks of the __cuda_array_interface__ /
+    DLPack view — dtype, rank, strides — run without a GPU."""
+    from ppca_rs_b200 import model as M
+
+    class Fake:
+        def __init__(self, shape, typestr="<f8", strides=None, ptr=4096):
+            self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "strides": strides,
+                                             "data": (ptr, False), "version": 3}
+
+    ptr, shape, strides, keep = M._device_view(Fake((5, 3)), 2, "array")
+    assert shape == (5, 3) and strides == (3, 1) and ptr.value == 4096
+    _, _, strides, _ = M._device_view(Fake((5, 3), strides=(80, 8)), 2, "array")
+    assert strides == (10, 1)                                     # bytes -> elements, padded rows
+    with pytest.raises(TypeError):
+        M._device_view(Fake((5, 3), typestr="<f4"), 2, "array")
+    with pytest.raises(ValueError):
+        M._device_view(Fake((5,)), 2, "array")
+    with pytest.raises(ValueError):
+        M._device_view(Fake((5, 3), strides=(20, 4)), 2, "array")
+    with pytest.raises(TypeError):
+        M._device_view(object(), 2, "array")
+
+
+def test_generated_dataset_describes_a_row_range():
+    import ppca_rs_b200 as pk
+    if pk.device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(pk.NativeError):                           # no context without a device: never a CPU path
+        pk.GeneratedDataset(10, 4, 2)
+    with pytest.raises(ValueError):
+        pk.GeneratedDataset(-1, 4, 2, ctx=object())

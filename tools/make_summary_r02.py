@@ -60,6 +60,11 @@ def main():
     lines.append(f"| c4 shard inside the default line (`c4_shard`): PPCAMix M=32 d=512 k=32 | {b4['rows_per_gpu']:,} | — | {b4['ms_per_step']:.1f} | "
                  f"{b4['value']/1e6:.2f} M samples·iters/s = {32 * b4['value']/1e6:.1f} M component-samples/s "
                  f"(round 1, M=4: 35.6 M component-samples/s with two E-steps per component) | — |")
+    bf = c2.get("c3_full")
+    if bf:
+        lines.append(f"| c3 AS SPECIFIED (`c3_full`): N = 100 M x 2048, k = 64, out of core, chunks regenerated on the device inside the step | "
+                     f"{bf['rows_per_gpu']:,} (= N/8) | — | {bf['ms_per_step']:.0f} | {bf['value']/1e6:.2f} M/s per GPU "
+                     f"(generator + ingest {bf['generator_and_ingest_ms_per_step']:.0f} ms of the step) | — |")
     if c4:
         n4 = c4["config"]["rows_per_gpu"]
         lines.append(f"| c4: PPCAMix M=32 d=512 k=32 25 % missing | {n4:,} | — | {c4['ms_per_step']:.0f} | {c4['value']/1e6:.2f} M samples·iters/s = "
@@ -81,7 +86,19 @@ def main():
                   f"{c2x2['e2e']['value']/1e6:.1f} M/s; c3 shard {c2x2['c3_shard']['value']/1e6:.2f} M/s with its 35 MB all-reduce at "
                   f"{c2x2['c3_shard']['comm_ms_per_step']:.3f} ms ({c2x2['c3_shard'].get('comm_gb_per_s', 0):.0f} GB/s); c4 shard all-reduce "
                   f"({c2x2['c4_shard']['allreduce_bytes']/1e6:.0f} MB, all 32 components at once) {c2x2['c4_shard']['comm_ms_per_step']:.3f} ms.", ""]
-    lines += ["## Kernel families, ms per step (CUDA events on the launching stream, inside the timed region)", "",
+    lines += ["## Second half of round 2", "",
+              "* Per-sample solve, 32 < k <= 64: register-tiled, panel-blocked sweep (`solve_tile_kernel`): c5 solve 60.2 -> 46.9 ms, c3s 29.7 -> 26.4 ms;",
+              "  seven measured variants and the ncu analysis (latency-bound serial chain per pivot, four samples resident per SM) in",
+              "  `r02_solve_tile.md`; `tools/rank1_probe.cu`: the rank-1 update pattern alone runs at 87 % of the FP64 peak.",
+              "* Mixture EM: the chunk loop (4 500 launches per step at M = 32) replays from a captured CUDA graph: c4 shard 223 -> 99 ms on a",
+              "  host whose launch rate bounded the step (`r02_launches_c4.csv`: 49 ms of kernels per 65 536 rows); on fast hosts 106 -> 99 ms.",
+              "  With more ranks the c4 block is data dependent: a rank whose random start leaves components with next to no",
+              "  responsibility mass repeats those components one rung up the precision ladder (2-GPU run: 120 repeats, 239 ms).",
+              "* Out-of-core EM over regenerated chunks (`ppca_b200_iterate_generated`): BASELINE configs[2] as specified; the generator",
+              "  (xi -> DMMA row GEMM -> noise + mask) went from 5.9 s to 0.31 s per 12.5 M rows.",
+              "* Widened into SURVEY §8(f): device ingestion (`__cuda_array_interface__` / DLPack), every sampler and the full covariances on the device.",
+              "* compute-sanitizer over all of it: memcheck 0 errors, racecheck 0 hazards (`r02_sanitizer_*.log`); 170 GPU tests (`r02_pytest_gpu.log`).", "",
+              "## Kernel families, ms per step (CUDA events on the launching stream, inside the timed region)", "",
               "| workload | gram (E) | proj | solve | slice | moment (M) | cross | finish |", "|---|---|---|---|---|---|---|---|",
               f"| c2 round 1 | {famrow(r1c2['roofline']['families'])} |",
               f"| c2 | {famrow(c2['roofline']['families'])} |",
