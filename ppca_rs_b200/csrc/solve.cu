@@ -606,13 +606,13 @@ __global__ void __launch_bounds__(256, MINB) solve_split64_kernel(SolveArgs a) {
 // ---------------------------------------------------------------------------------------------
 template <int N>
 __device__ __forceinline__ void sample_sync(int id) {
-  if constexpr (N == 32) __syncwarp();
+  if constexpr (N <= 32) __syncwarp();
   else asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(N) : "memory");
 }
 
 template <int KD, int TR, int TC>
 struct TileLayout {
-  static constexpr int NTR = KD / TR, NTC = KD / TC, TPS = NTR * NTC, SPC = 256 / TPS, WPS = TPS / 32;
+  static constexpr int NTR = KD / TR, NTC = KD / TC, TPS = NTR * NTC, SPC = 256 / TPS, WPS = TPS >= 32 ? TPS / 32 : 1;
   static constexpr int SR = 6;  // pitch (doubles) of one thread's row group in the own-units exchange: 2 x odd keeps the
                                 // 128-bit reads of eight consecutive row groups on disjoint banks
   // PW pivots per exchange (a "panel"): the rows and the columns of a panel each sit inside one thread tile
@@ -621,13 +621,29 @@ struct TileLayout {
   // one exchange buffer: PW x (true units [KD] | own units, padded [NTR SR]) | PW 1/d | pad
   static constexpr int EXQ = KD + NTR * SR;
   static constexpr int EX = PW * EXQ + 4;
-  // per sample: stage[kkp] | exch[2][EX] (reused for the partial z sums after the elimination) | yb[KD] | zb[KD] | piv[KD] | red[16]
-  static constexpr int FIXED = 2 * EX + 3 * KD + 16;
+  // Samples narrower than a warp (KD = 16: 8 threads, four samples per warp) synchronise with __syncwarp, which costs
+  // next to nothing: ONE exchange buffer and a second sync after the reads instead of two buffers; and one array of column
+  // maxima per CTA (shared-memory atomicMax) instead of one per sample slot — 32 samples per CTA have to fit.
+  static constexpr bool SUBWARP = TPS < 32;
+  static constexpr int NBUF = SUBWARP ? 1 : 2;
+  // per sample: stage[kkp] | exch[NBUF][EX] (reused for the partial z sums after the elimination) | yb[KD] | zb[KD] | piv[KD] | red[16]
+  static constexpr int FIXED = NBUF * EX + 3 * KD + 16;
   static_assert(KD % TR == 0 && KD % TC == 0 && TR % 2 == 0 && TC % 2 == 0 && TR <= SR, "tile shape");
-  static_assert(TPS % 32 == 0 && 256 % TPS == 0 && TPS >= KD && NTR >= 8 && 32 % NTR == 0, "thread layout");
+  static_assert((TPS % 32 == 0 || 32 % TPS == 0) && 256 % TPS == 0 && 32 % NTR == 0, "thread layout");
   static_assert(TR % PW == 0 && TC % PW == 0 && PB % TR == 0 && PB % TC == 0 && (PB / PW) % 2 == 0 && KD % PB == 0, "panels");
-  static_assert(2 * EX >= NTC * KD, "the partial z sums reuse the exchange buffers");
+  static_assert(NBUF * EX >= NTC * KD, "the partial z sums reuse the exchange buffers");
+  static size_t smem_doubles(int kkp, bool colmax) {
+    return (size_t)SPC * (kkp + FIXED) + (colmax ? (size_t)(SUBWARP ? 1 : SPC) * kkp : 0);
+  }
 };
+
+// sum over the TPS lanes of one sample (TPS <= 32: inside the warp segment; every lane of the segment gets the sum)
+template <int TPS>
+__device__ __forceinline__ double sample_seg_sum(double v) {
+#pragma unroll
+  for (int o = (TPS < 32 ? TPS : 32) / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
 
 template <int KD, int TR, int TC, int MINB>
 __global__ void __launch_bounds__(256, MINB) solve_tile_kernel(SolveArgs a) {
@@ -647,14 +663,21 @@ __global__ void __launch_bounds__(256, MINB) solve_tile_kernel(SolveArgs a) {
   const int per_smp = kkp + LY::FIXED;
   double *stage = smem_reg + (size_t)smp * per_smp;  // one packed row: G in, W out
   double *exch = stage + kkp;
-  double *yb = exch + 2 * EX;
+  double *yb = exch + LY::NBUF * EX;
   double *zb = yb + KD;
   double *piv = zb + KD;
   double *red = piv + KD;
   double *zpart = exch;  // [NTC][KD], after the elimination
-  double *cmw = smem_reg + (size_t)SPC * per_smp + (size_t)smp * kkp;  // running max |W| of this slot's samples
-  if (a.colmax)
-    for (int q = t; q < kkp; q += TPS) cmw[q] = 0.0;
+  // running max |W|: per sample slot, or (sub-warp samples) one array per CTA updated with shared-memory atomics
+  double *cmw = smem_reg + (size_t)SPC * per_smp + (LY::SUBWARP ? 0 : (size_t)smp * kkp);
+  if (a.colmax) {
+    if constexpr (LY::SUBWARP) {
+      for (int q = threadIdx.x; q < kkp; q += blockDim.x) cmw[q] = 0.0;
+      __syncthreads();
+    } else {
+      for (int q = t; q < kkp; q += TPS) cmw[q] = 0.0;
+    }
+  }
   const double sigma = a.sigma_dev ? *a.sigma_dev : a.sigma;  // device copy: the launch can be replayed from a CUDA graph
   const double s2 = sigma * sigma;
   const double ln_sigma = log(sigma);
@@ -663,7 +686,7 @@ __global__ void __launch_bounds__(256, MINB) solve_tile_kernel(SolveArgs a) {
     double *gsrc = a.GW + (int64_t)row * kkp;
     for (int q = t * 2; q < kkp; q += 2 * TPS)
       *reinterpret_cast<double2 *>(stage + q) = *reinterpret_cast<const double2 *>(gsrc + q);
-    if (t < KD) yb[t] = (t < kp) ? a.YZ[(int64_t)row * kp + t] : 0.0;
+    for (int r = t; r < KD; r += TPS) yb[r] = (r < kp) ? a.YZ[(int64_t)row * kp + r] : 0.0;
     const int dn = row < a.rows ? a.dn[row] : 0;
     const bool empty = dn == 0;
     const double w = (a.w && row < a.rows) ? a.w[row] : (row < a.rows ? 1.0 : 0.0);
@@ -685,9 +708,11 @@ __global__ void __launch_bounds__(256, MINB) solve_tile_kernel(SolveArgs a) {
         A[ia][jb] = use ? fma(unit, s2, g) : unit;
       }
     }
-    if (a.gscale && t < k && !empty) {  // precision guard (see SolveArgs): thread t checks M_tt
-      const int qd = tri_row_off(t, k);
-      if (guard_terms((double)dn) * a.guard_coef * a.gscale[qd] > s2 + stage[qd]) atomicAdd(a.unsafe, 1u);
+    if (a.gscale && !empty) {  // precision guard (see SolveArgs): M_rr for the rows r = t, t + TPS, ...
+      for (int r = t; r < k; r += TPS) {
+        const int qd = tri_row_off(r, k);
+        if (guard_terms((double)dn) * a.guard_coef * a.gscale[qd] > s2 + stage[qd]) atomicAdd(a.unsafe, 1u);
+      }
     }
 
     // PANEL-BLOCKED elimination: PW pivots per exchange.  The threads that hold the panel's columns ("publishers", one
@@ -705,7 +730,7 @@ __global__ void __launch_bounds__(256, MINB) solve_tile_kernel(SolveArgs a) {
     double sc[TR];  // 1/d_i once row i has been swept (1 before): swept rows stay in their own units (d_i x true)
 #pragma unroll
     for (int ia = 0; ia < TR; ++ia) sc[ia] = 1.0;
-    const int gbase = (tc * NTR) & 31;  // first lane of this thread's column block within its warp
+    const int gbase = lane - tr;  // first lane of this thread's column block within its warp
     const unsigned gmask = NTR == 32 ? 0xffffffffu : (((1u << NTR) - 1u) << gbase);
     for (int pb = 0; pb < nblk; ++pb) {
 #pragma unroll
@@ -713,7 +738,7 @@ __global__ void __launch_bounds__(256, MINB) solve_tile_kernel(SolveArgs a) {
         const int pp0 = ps * PW;             // first pivot of the panel within the block (compile time after unrolling)
         const int p0 = pb * PB + pp0;
         const int a0 = pp0 % TR, cl0 = pp0 % TC;  // the panel's rows / columns inside the tile that holds them
-        double *ex = exch + (ps & 1) * EX;
+        double *ex = exch + ((ps & 1) % LY::NBUF) * EX;
         const bool pub = tc == pb * (PB / TC) + pp0 / TC;   // this thread holds the panel's columns
         const bool prow = tr == pb * (PB / TR) + pp0 / TR;  // this thread holds the panel's rows
         if (pub) {
@@ -792,6 +817,7 @@ __global__ void __launch_bounds__(256, MINB) solve_tile_kernel(SolveArgs a) {
 #pragma unroll
           for (int q = 0; q < PW; ++q) sc[a0 + q] = ex[PW * EXQ + q];
         }
+        if constexpr (LY::NBUF == 1) sample_sync<TPS>(bar_id);  // single exchange buffer: reads done before the next panel
       }
     }
 
@@ -824,15 +850,15 @@ __global__ void __launch_bounds__(256, MINB) solve_tile_kernel(SolveArgs a) {
       }
     }
     sample_sync<TPS>(bar_id);
-    double zi = 0.0;
     double r_ld = 0.0, r_quad = 0.0, r_zz = 0.0, r_tp = 0.0;
-    if (t < KD) {
+    for (int r = t; r < KD; r += TPS) {  // row r of z: sum of the column blocks' partial products
+      double zi = 0.0;
 #pragma unroll
-      for (int c = 0; c < NTC; ++c) zi += zpart[c * KD + t];
-      zb[t] = zi;
-      r_quad = yb[t] * zi;
-      r_zz = zi * zi;
-      if (t < kpiv) r_ld = log(piv[t]);
+      for (int c = 0; c < NTC; ++c) zi += zpart[c * KD + r];
+      zb[r] = zi;
+      r_quad = fma(yb[r], zi, r_quad);
+      r_zz = fma(zi, zi, r_zz);
+      if (r < kpiv) r_ld += log(piv[r]);
     }
     if (a.mode == 2) {  // t = sigma^2 sum_i (1 - sigma^2 M^{-1}_ii): the diagonal entries this tile holds
 #pragma unroll
@@ -841,13 +867,13 @@ __global__ void __launch_bounds__(256, MINB) solve_tile_kernel(SolveArgs a) {
         for (int jb = 0; jb < TC; ++jb)
           if (r0 + ia == c0 + jb && rlive[ia]) r_tp += fma(-s2, A[ia][jb], 1.0);
     }
-    r_ld = warp_sum(r_ld);
-    r_quad = warp_sum(r_quad);
+    r_ld = sample_seg_sum<TPS>(r_ld);
+    r_quad = sample_seg_sum<TPS>(r_quad);
     if (a.mode == 2) {
-      r_zz = warp_sum(r_zz);
-      r_tp = warp_sum(r_tp);
+      r_zz = sample_seg_sum<TPS>(r_zz);
+      r_tp = sample_seg_sum<TPS>(r_tp);
     }
-    if (lane == 0) {
+    if ((t & 31) == 0) {
       red[wis * 4 + 0] = r_ld;
       red[wis * 4 + 1] = r_quad;
       red[wis * 4 + 2] = r_zz;
@@ -873,9 +899,10 @@ __global__ void __launch_bounds__(256, MINB) solve_tile_kernel(SolveArgs a) {
       if (a.mode == 2 && a.dv) a.dv[row] = empty ? 0.0 : (a.nx[row] - quad) - s2 * zz;  // |R_n|^2, see SolveArgs::dv
     }
     if (a.mode != 0) {
-      if (t < kp) {
-        a.YZ[(int64_t)row * kp + t] = zi;
-        if (a.WZ) a.WZ[(int64_t)row * kp + t] = w * zi;
+      for (int r = t; r < kp; r += TPS) {
+        const double zi = r < KD ? zb[r] : 0.0;
+        a.YZ[(int64_t)row * kp + r] = zi;
+        if (a.WZ) a.WZ[(int64_t)row * kp + r] = w * zi;
       }
       if (a.cov && row < a.rows) {
 #pragma unroll
@@ -918,10 +945,18 @@ __global__ void __launch_bounds__(256, MINB) solve_tile_kernel(SolveArgs a) {
         const double2 v = *reinterpret_cast<const double2 *>(stage + q);
         *reinterpret_cast<double2 *>(gsrc + q) = v;
         if (a.colmax) {
-          double2 m = *reinterpret_cast<const double2 *>(cmw + q);
-          m.x = fmax(m.x, fabs(v.x));
-          m.y = fmax(m.y, fabs(v.y));
-          *reinterpret_cast<double2 *>(cmw + q) = m;
+          if constexpr (LY::SUBWARP) {  // one array per CTA: non-negative doubles order like their bit patterns
+            unsigned long long *cm = reinterpret_cast<unsigned long long *>(cmw + q);
+            const unsigned long long bx = (unsigned long long)__double_as_longlong(fabs(v.x));
+            const unsigned long long by = (unsigned long long)__double_as_longlong(fabs(v.y));
+            if (bx > cm[0]) atomicMax(cm, bx);
+            if (by > cm[1]) atomicMax(cm + 1, by);
+          } else {
+            double2 m = *reinterpret_cast<const double2 *>(cmw + q);
+            m.x = fmax(m.x, fabs(v.x));
+            m.y = fmax(m.y, fabs(v.y));
+            *reinterpret_cast<double2 *>(cmw + q) = m;
+          }
         }
       }
     }
@@ -933,7 +968,7 @@ __global__ void __launch_bounds__(256, MINB) solve_tile_kernel(SolveArgs a) {
     for (int c = threadIdx.x; c < kkp; c += blockDim.x) {
       double m = 0.0;
 #pragma unroll
-      for (int j = 0; j < SPC; ++j) m = fmax(m, all[(size_t)j * kkp + c]);
+      for (int j = 0; j < (LY::SUBWARP ? 1 : SPC); ++j) m = fmax(m, all[(size_t)j * kkp + c]);
       if (m > 0.0) atomicMax(a.colmax + c, (unsigned long long)__double_as_longlong(m));
     }
   }
@@ -942,7 +977,7 @@ __global__ void __launch_bounds__(256, MINB) solve_tile_kernel(SolveArgs a) {
 template <int KD, int TR, int TC, int MINB>
 static void launch_solve_tile(const Launcher &L, const SolveArgs &a) {
   using LY = TileLayout<KD, TR, TC>;
-  const size_t smem = (size_t)LY::SPC * (a.s.kkp + LY::FIXED + (a.colmax ? a.s.kkp : 0)) * sizeof(double);
+  const size_t smem = LY::smem_doubles(a.s.kkp, a.colmax != nullptr) * sizeof(double);
   static PerDeviceOnce configured;
   if (configured.need()) {
     CUDA_CHECK(cudaFuncSetAttribute(solve_tile_kernel<KD, TR, TC, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1137,7 +1172,7 @@ static void launch_solve_generic(const Launcher &L, const SolveArgs &a) {
 
 static bool tile32_fits(const SolveArgs &a) {  // eight samples per CTA: the widest states with column maxima do not fit
   using LY = TileLayout<32, 4, 8>;
-  return (size_t)LY::SPC * (a.s.kkp + LY::FIXED + (a.colmax ? a.s.kkp : 0)) * sizeof(double) <= 110 * 1024;
+  return LY::smem_doubles(a.s.kkp, a.colmax != nullptr) * sizeof(double) <= 110 * 1024;
 }
 
 void launch_solve(const Launcher &L, const SolveArgs &a) {
@@ -1150,7 +1185,9 @@ void launch_solve(const Launcher &L, const SolveArgs &a) {
   // k = 48 -15 %, k = 64 -6 %, k = 32 +8 %).  PPCA_B200_SOLVE=rows / tile forces one family for 16 < k <= 64.
   static const bool rows_layout = getenv("PPCA_B200_SOLVE") && !strcmp(getenv("PPCA_B200_SOLVE"), "rows");
   static const bool tile32 = getenv("PPCA_B200_SOLVE") && !strcmp(getenv("PPCA_B200_SOLVE"), "tile");
+  static const bool tile16 = getenv("PPCA_B200_SOLVE16") && !strcmp(getenv("PPCA_B200_SOLVE16"), "tile");
   if (a.s.k <= 8) launch_solve_reg<8>(L, a);
+  else if (a.s.k <= 16 && tile16) launch_solve_tile<16, 4, 8, 2>(L, a);
   else if (a.s.k <= 16) launch_solve_reg<16>(L, a);
   else if (a.s.k <= 64 && !rows_layout && (a.s.k > 32 || (tile32 && tile32_fits(a)))) {
     if (a.s.k <= 32) launch_solve_tile<32, 4, 8, 2>(L, a);
