@@ -104,7 +104,7 @@ int32_t ppca_b200_ctx_launch_count(ppca_b200_ctx *ctx, int64_t *out);
 /* Launches so far per shape-dependent kernel variant, 16 counters (tests assert which code path a case ran):
  *   0 tbitgemm_kernel (A tile in shared memory, T = 7, 8)   1 tbitgemm_atm_kernel<T,2,1>   2 tbitgemm_atm_kernel<T,1,2>
  *   3 tbitgemm_atm2_kernel (two output tiles per mask stage)  4 ibitgemm_kernel (IMMA)      5 bitgemm_kernel (DMMA)
- *   6-8 solve_reg_kernel<8|16|32>   9 solve_split64_kernel   10 solve_tile_kernel (register-tiled, 16 < k <= 64)
+ *   6-8 solve_reg_kernel<8|16|32>   9 unused (kernel removed)   10 solve_tile_kernel (register-tiled, 32 < k <= 64)
  *   11 unused
  *   12 solve_kernel (generic)   13 passes repeated at a wider arithmetic by the precision guard
  *   14 batched mixture contraction launches   15 mixture chunk loops replayed from a captured CUDA graph */

@@ -277,7 +277,7 @@ class Context:
         return out.value
 
     VARIANTS = ("tc_smem_a", "tc_atm_feed", "tc_atm_drain", "tc_atm2", "imma", "dmma", "solve_reg8", "solve_reg16",
-                "solve_reg32", "solve_split64", "solve_tile", "unused11", "solve_generic", "precision_retry",
+                "solve_reg32", "unused9", "solve_tile", "unused11", "solve_generic", "precision_retry",
                 "tc_mix", "graph_replays")
 
     def variant_counts(self) -> Dict[str, int]:

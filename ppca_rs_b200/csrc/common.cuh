@@ -175,7 +175,7 @@ enum Variant {
   V_SOLVE_REG8,
   V_SOLVE_REG16,
   V_SOLVE_REG32,
-  V_SOLVE_SPLIT64,
+  V_UNUSED9,         // (solve_split64_kernel, removed: superseded by solve_tile_kernel)
   V_SOLVE_TILE,      // solve_tile_kernel<32 | 48 | 64> (register-tiled sweep, 16 < k <= 64)
   V_UNUSED11,
   V_SOLVE_GENERIC,

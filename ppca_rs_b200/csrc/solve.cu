@@ -395,198 +395,6 @@ __global__ void __launch_bounds__(256, MINB) solve_reg_kernel(SolveArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// 32 < k <= 64: 128 threads per sample.  Thread (i, h) owns columns [32 h, 32 h + 32) of row i,
-// so the per-pivot dependent chain is 32 FMAs instead of 64, registers halve (two CTAs of two samples per SM)
-// and twice as many warps hide the exchange / reciprocal latency.  Same elimination as above; the column
-// exchange carries both the symmetric-transformed value (pivot row) and the raw value (this row's multiplier).
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void quad_sync(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
-
-// KPIV = state_size rounded up to 8: rows / columns past it are identity padding whose pivots change nothing, so the
-// elimination stops there (k = 48: 48 of 64 pivots)
-template <int KPIV, int MINB>
-__global__ void __launch_bounds__(256, MINB) solve_split64_kernel(SolveArgs a) {
-  constexpr int KP = KPIV, CW = KPIV / 2;  // columns per thread: two halves of KPIV / 2 (k = 48: 24, not 32)
-  static_assert(CW % 2 == 0 && 2 * CW >= KPIV && CW <= 32, "column halves must be even and cover the state");
-  extern __shared__ __align__(16) double smem_reg[];
-  const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
-  const int smp = wi >> 2;                       // sample slot in the CTA (0, 1)
-  const int ws = wi & 3;                         // warp within the sample
-  const int li = (ws & 1) * 32 + lane;           // row
-  const int h = ws >> 1;                         // column half
-  const int c0 = CW * h;
-  const int bar_id = smp + 1;
-  const int k = a.s.k, kkp = a.s.kkp, kp = a.s.kp;
-  const int per_smp = kkp + 2 * 136 + 64 + 128 + 16;
-  double *stage = smem_reg + (size_t)smp * per_smp;  // one packed row
-  double *col = stage + kkp;                         // [2][64 true units | 64 own units | next diagonal, padded to 136]
-  double *yb = col + 272;                            // [64]
-  double *zpart = yb + 64;                           // [2][64] partial z per column half
-  double *red = zpart + 128;                         // [16]
-  double *cmw = smem_reg + (size_t)2 * per_smp + (size_t)smp * kkp;  // running max |W| of this slot's samples
-  if (a.colmax)
-    for (int q = ws * 32 + lane; q < kkp; q += 128) cmw[q] = 0.0;
-  const double sigma = a.sigma_dev ? *a.sigma_dev : a.sigma;  // device copy: the launch can be replayed from a CUDA graph
-  const double s2 = sigma * sigma;
-  const double ln_sigma = log(sigma);
-
-  for (int row = blockIdx.x * 2 + smp; row < a.rows_pad; row += gridDim.x * 2) {
-    double *gsrc = a.GW + (int64_t)row * kkp;
-    const int ts = ws * 32 + lane;  // 0..127
-    for (int q = ts * 2; q < kkp; q += 256)
-      *reinterpret_cast<double2 *>(stage + q) = *reinterpret_cast<const double2 *>(gsrc + q);
-    if (h == 0) yb[li] = (li < kp) ? a.YZ[(int64_t)row * kp + li] : 0.0;
-    const int dn = row < a.rows ? a.dn[row] : 0;
-    const bool empty = dn == 0;
-    const double w = (a.w && row < a.rows) ? a.w[row] : (row < a.rows ? 1.0 : 0.0);
-    quad_sync(bar_id);
-
-    const bool live = li < k && !empty;
-    const int up = tri_row_off(li, k) - li;
-    double A[CW];
-#pragma unroll
-    for (int jj = 0; jj < CW; ++jj) {
-      const int j = c0 + jj;
-      int idx = (j >= li) ? up + j : ((j * (2 * k - j - 1)) >> 1) + li;
-      const bool use = live && j < k;
-      idx = use ? idx : 0;
-      const double g = stage[idx];
-      const double unit = (j == li) ? 1.0 : 0.0;
-      A[jj] = use ? fma(unit, s2, g) : unit;
-    }
-    if (a.gscale && live && h == 0) {  // precision guard (see SolveArgs)
-      const int qd = up + li;
-      if (guard_terms((double)dn) * a.guard_coef * a.gscale[qd] > s2 + stage[qd]) atomicAdd(a.unsafe, 1u);
-    }
-
-    // Square-root form of the symmetric sweep (see solve_reg_kernel): commutative update products keep the two
-    // triangles bitwise equal, so the column-p entries every row owner publishes ARE the pivot row.  A thread of the
-    // half that does not hold column p takes its own s_i from its sibling through shared memory (slots 64..127).  The
-    // next pivot d_{p+1} = T[p+1][p+1] - s_{p+1}^2 is formed by EVERY thread from the published entry and the diagonal
-    // value its owner adds to the exchange (slot 128): one barrier per pivot, and 1/sqrt(d_{p+1}) overlaps the update.
-    double mypiv = 1.0, sc = 1.0;  // d_i, and 1 / d_i once row li has been the pivot (1 before)
-    double dcur = empty || k <= 0 ? 1.0 : s2 + stage[0];
-#pragma unroll
-    for (int p = 0; p < KP; ++p) {
-      double *cb = col + (p & 1) * 136;  // [0,64) s in true units, [64,128) s in the row's own units, [128] next diagonal
-      const double dthis = dcur;
-      const double rinv = fast_rsqrt(dthis);
-      if (h == (p / CW)) {
-        const double own = A[p % CW] * rinv;
-        cb[li] = own * sc;
-        cb[64 + li] = own;
-      }
-      if (p + 1 < KP && li == p + 1 && h == ((p + 1) / CW)) cb[128] = A[(p + 1) % CW];
-      quad_sync(bar_id);
-      const bool isp = li == p;
-      const double own = cb[64 + li];
-      const double f = isp ? 0.0 : own;  // the pivot row is left as it is (its 1/d is applied at the end)
-      if (p + 1 < KP) {
-        const double sn = cb[p + 1];
-        dcur = fma(-sn, sn, cb[128]);    // bitwise what the owner of row p + 1 computes below
-      }
-      const double2 *cb2 = reinterpret_cast<const double2 *>(cb + c0);
-#pragma unroll
-      for (int jj = 0; jj < CW; jj += 2) {
-        const double2 cv = cb2[jj >> 1];
-        A[jj] = fma(-f, cv.x, A[jj]);
-        A[jj + 1] = fma(-f, cv.y, A[jj + 1]);
-      }
-      if (h == (p / CW)) A[p % CW] = isp ? -1.0 : own * rinv;
-      if (isp) {
-        mypiv = dthis;
-        sc = rinv * rinv;
-      }
-    }
-    {
-      const double nsc = -sc;
-#pragma unroll
-      for (int jj = 0; jj < CW; ++jj) A[jj] *= nsc;  // A[jj] = M^{-1}[li][c0 + jj]
-    }
-
-    double zp = 0.0;
-#pragma unroll
-    for (int jj = 0; jj < CW; ++jj) zp = fma(A[jj], yb[c0 + jj], zp);
-    zpart[h * 64 + li] = live ? zp : 0.0;
-    double ld = warp_sum((live && h == 0) ? log(mypiv) : 0.0);
-    if (lane == 0) red[ws] = ld;
-    quad_sync(bar_id);
-    const double zi = zpart[li] + zpart[64 + li];
-    double quad = warp_sum(h == 0 ? yb[li] * zi : 0.0);
-    if (lane == 0) red[4 + ws] = quad;
-    double tpart = 0.0;
-    if (a.mode == 2) {  // t = sigma^2 sum_i (1 - sigma^2 M^{-1}_ii): the diagonal lives in half h = i / 32
-      double diag = 0.0;
-#pragma unroll
-      for (int jj = 0; jj < CW; ++jj)
-        if (c0 + jj == li) diag = A[jj];
-      tpart = warp_sum((live && h == (li / CW)) ? fma(-s2, diag, 1.0) : 0.0);
-      const double zz = warp_sum(h == 0 ? zi * zi : 0.0);
-      if (lane == 0) {
-        red[8 + ws] = tpart;
-        red[12 + ws] = zz;
-      }
-    }
-    quad_sync(bar_id);
-    if (ts == 0 && row < a.rows) {
-      if (a.llk) {
-        double llk = 0.0;
-        if (!empty)
-          llk = -0.5 * (a.nx[row] - (red[4] + red[5])) / s2 -
-                0.5 * ((red[0] + red[1]) + 2.0 * ln_sigma * (double)(dn - k)) - 0.5 * LN_2PI * (double)dn;
-        a.llk[row] = llk;
-      }
-      if (a.mode == 2 && a.tn) a.tn[row] = empty ? 0.0 : s2 * (red[8] + red[9] + red[10] + red[11]);
-      if (a.mode == 2 && a.dv) a.dv[row] = empty ? 0.0 : (a.nx[row] - (red[4] + red[5])) - s2 * (red[12] + red[13]);
-    }
-    if (a.mode != 0) {
-      if (h == 0 && li < kp) {
-        a.YZ[(int64_t)row * kp + li] = zi;
-        if (a.WZ) a.WZ[(int64_t)row * kp + li] = w * zi;
-      }
-      if (a.cov && row < a.rows && li < k) {
-        double *cv = a.cov + (int64_t)row * k * k + (int64_t)li * k;
-#pragma unroll
-        for (int jj = 0; jj < CW; ++jj)
-          if (c0 + jj < k) cv[c0 + jj] = empty ? (c0 + jj == li ? 1.0 : 0.0) : s2 * A[jj];
-      }
-    }
-    if (a.mode == 2) {
-      // all reads of G are done (gather happened before the elimination barriers); W overwrites it in place
-      if (li < k) {
-        double *so = stage + up;
-        const double ws2 = empty ? 0.0 : w * s2, wzi = empty ? 0.0 : w * zi;
-#pragma unroll
-        for (int jj = 0; jj < CW; ++jj) {
-          const int j = c0 + jj;
-          if (j >= li && j < k) so[j] = fma(wzi, zpart[j] + zpart[64 + j], ws2 * A[jj]);
-        }
-      }
-      quad_sync(bar_id);
-      for (int q = ts * 2; q < kkp; q += 256) {
-        const double2 v = *reinterpret_cast<const double2 *>(stage + q);
-        *reinterpret_cast<double2 *>(gsrc + q) = v;
-        if (a.colmax) {
-          double2 m = *reinterpret_cast<const double2 *>(cmw + q);
-          m.x = fmax(m.x, fabs(v.x));
-          m.y = fmax(m.y, fabs(v.y));
-          *reinterpret_cast<double2 *>(cmw + q) = m;
-        }
-      }
-    }
-    quad_sync(bar_id);
-  }
-  if (a.colmax) {
-    __syncthreads();
-    const double *all = smem_reg + (size_t)2 * per_smp;
-    for (int c = threadIdx.x; c < kkp; c += blockDim.x) {
-      const double m = fmax(all[c], all[kkp + c]);
-      if (m > 0.0) atomicMax(a.colmax + c, (unsigned long long)__double_as_longlong(m));
-    }
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
 // Register-tiled variant (16 < k <= 64, the default): thread (tr, tc) owns the TR x TC tile rows [TR tr, TR tr + TR),
 // columns [TC tc, TC tc + TC) of the symmetric matrix.  Same elimination as above (square-root symmetric sweep, swept
 // rows left in their own units), but every exchanged multiplier a thread reads from shared memory now feeds TR (column
@@ -992,31 +800,6 @@ static void launch_solve_tile(const Launcher &L, const SolveArgs &a) {
   L.count(V_SOLVE_TILE);
 }
 
-template <int KPIV, int MINB>
-static void launch_solve_split64_b(const Launcher &L, const SolveArgs &a) {
-  const size_t smem = (size_t)2 * (a.s.kkp + 2 * 136 + 64 + 128 + 16 + (a.colmax ? a.s.kkp : 0)) * sizeof(double);
-  static PerDeviceOnce configured;
-  if (configured.need()) {
-    CUDA_CHECK(cudaFuncSetAttribute(solve_split64_kernel<KPIV, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-  }
-  int64_t blocks = (a.rows_pad + 1) / 2;
-  if (blocks > MINB * (int64_t)L.sms) blocks = MINB * (int64_t)L.sms;
-  solve_split64_kernel<KPIV, MINB><<<(unsigned)blocks, 256, smem, L.stream>>>(a);
-  CUDA_CHECK(cudaGetLastError());
-  ++*L.launch_counter;
-  L.count(V_SOLVE_SPLIT64);
-}
-
-// resident CTAs per SM: 2 (128 registers) by default; narrower states leave room for 3 (PPCA_B200_SOLVE64_MINB=3)
-template <int KPIV>
-static void launch_solve_split64(const Launcher &L, const SolveArgs &a) {
-  static const int minb = getenv("PPCA_B200_SOLVE64_MINB") ? atoi(getenv("PPCA_B200_SOLVE64_MINB")) : 2;
-  if constexpr (KPIV <= 48) {
-    if (minb == 3) return launch_solve_split64_b<KPIV, 3>(L, a);
-  }
-  launch_solve_split64_b<KPIV, 2>(L, a);
-}
-
 template <int KP, int MINB>
 static void launch_solve_reg_b(const Launcher &L, const SolveArgs &a) {
   constexpr int SPW = 32 / KP;
@@ -1178,27 +961,21 @@ static bool tile32_fits(const SolveArgs &a) {  // eight samples per CTA: the wid
 void launch_solve(const Launcher &L, const SolveArgs &a) {
   if (a.rows_pad <= 0) return;
   REQUIRE(a.mode == 0 || a.GW != nullptr, "solve: missing Gram buffer");
-  // Round 1 also carried a DMMA-blocked 8 x 8 Gauss-Jordan kernel and a 64-lane variant; both were removed in round 2:
-  // the blocked elimination is not symmetric-consistent (tools/solve_accuracy.py: four digits worse on ill-conditioned
-  // M_n) and never beat the scalar kernels (profiles/r01_solve_blk_ncu.txt).
-  // Default: lane-owns-a-row kernels up to k = 32, register-tiled sweep for 32 < k <= 64 (measured, profiles/r02_solve_tile.md:
-  // k = 48 -15 %, k = 64 -6 %, k = 32 +8 %).  PPCA_B200_SOLVE=rows / tile forces one family for 16 < k <= 64.
-  static const bool rows_layout = getenv("PPCA_B200_SOLVE") && !strcmp(getenv("PPCA_B200_SOLVE"), "rows");
+  // Removed in round 2: a DMMA-blocked 8 x 8 Gauss-Jordan kernel and a 64-lane variant (the blocked elimination was not
+  // symmetric-consistent — tools/solve_accuracy.py: four digits worse on ill-conditioned M_n — and never beat the scalar
+  // kernels, profiles/r01_solve_blk_ncu.txt) and the 128-thread row kernel for 32 < k <= 64 (superseded by the tiled one).
+  // k <= 32: lane-owns-a-row kernels; 32 < k <= 64: register-tiled, panel-blocked sweep (measured against the round-1/2
+  // 128-thread row kernel it replaced: k = 48 -22 %, k = 64 -11 %; profiles/r02_solve_tile.md).  The tiled kernel also runs
+  // k <= 32 (PPCA_B200_SOLVE=tile: k = 32 +16 %) and k <= 16 (PPCA_B200_SOLVE16=tile: +36 %): slower there, kept as switches.
   static const bool tile32 = getenv("PPCA_B200_SOLVE") && !strcmp(getenv("PPCA_B200_SOLVE"), "tile");
   static const bool tile16 = getenv("PPCA_B200_SOLVE16") && !strcmp(getenv("PPCA_B200_SOLVE16"), "tile");
   if (a.s.k <= 8) launch_solve_reg<8>(L, a);
   else if (a.s.k <= 16 && tile16) launch_solve_tile<16, 4, 8, 2>(L, a);
   else if (a.s.k <= 16) launch_solve_reg<16>(L, a);
-  else if (a.s.k <= 64 && !rows_layout && (a.s.k > 32 || (tile32 && tile32_fits(a)))) {
-    if (a.s.k <= 32) launch_solve_tile<32, 4, 8, 2>(L, a);
-    else if (a.s.k <= 48) launch_solve_tile<48, 6, 6, 2>(L, a);
-    else launch_solve_tile<64, 4, 8, 2>(L, a);
-  }
+  else if (a.s.k <= 32 && tile32 && tile32_fits(a)) launch_solve_tile<32, 4, 8, 2>(L, a);
   else if (a.s.k <= 32) launch_solve_reg<32>(L, a);
-  else if (a.s.k <= 40) launch_solve_split64<40>(L, a);
-  else if (a.s.k <= 48) launch_solve_split64<48>(L, a);
-  else if (a.s.k <= 56) launch_solve_split64<56>(L, a);
-  else if (a.s.k <= 64) launch_solve_split64<64>(L, a);
+  else if (a.s.k <= 48) launch_solve_tile<48, 6, 6, 2>(L, a);
+  else if (a.s.k <= 64) launch_solve_tile<64, 4, 8, 2>(L, a);
   else {
     REQUIRE(a.colmax == nullptr, "solve: the generic kernel (state_size > 64) does not produce column maxima");
     launch_solve_generic(L, a);

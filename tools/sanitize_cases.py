@@ -22,7 +22,7 @@ CASES = [
     (2048, 200, 16, "tc", 6),    # tbitgemm_atm_kernel<6,1,2> (drain), solve_reg16
     (1024, 700, 7, "tc", 6),     # tbitgemm_atm_kernel<6,2,1> (feed: one q tile), solve_reg8
     (2048, 1024, 32, "tc", 6),   # tbitgemm_atm2_kernel (E-step), solve_reg32
-    (1024, 260, 64, "tc", 6),    # solve_split64
+    (1024, 260, 64, "tc", 6),    # solve_tile_kernel<64>
     (512, 150, 66, "tc", 6),     # solve_kernel (generic), colmax_kernel_tc; E-step only under the sanitizer (the M-step's
                                  # cross_resid tile at k > 64 asks for more shared memory than the tool leaves available)
     (1024, 200, 16, "tc", 7),    # tbitgemm_kernel<7> (A tile in shared memory)
