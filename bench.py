@@ -324,9 +324,13 @@ def run_reference(args, wl, rank):
         "impl": "reference", "metric": "EM samples*iters/sec", "value": value, "unit": "samples*iters/s",
         "n_gpus": args.gpus, "steps": len(times), "warmup": warmup, "ms_per_step": 1e3 * total / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {wl['desc']}", "sample_rows": rows,
-                   "steps_note": f"--steps {args.steps} --warmup {args.warmup} requested; the CPU arm runs at most 3 timed "
-                                 "steps and 1 warm-up (one step takes seconds on the host cores)"},
+        # same keys as our arm's config (the workload is the same rows of the same synthetic data set)
+        "config": {"workload": f"{args.workload}: {wl['desc']}", "rows_per_gpu": rows, "d": wl["d"], "k": wl["k"],
+                   "components": wl["m"],
+                   "parallelism": f"OpenMP over samples / dimensions, {cores} host threads (the reference uses rayon the same way)",
+                   "l2": "host memory"},
+        "steps_note": f"--steps {args.steps} --warmup {args.warmup} requested; the CPU arm runs at most 3 timed "
+                      "steps and 1 warm-up (one step takes seconds on the host cores)",
         "cpu_baseline": {"value": value, "unit": "samples*iters/s", "cores": cores, "kind": "port",
                          "sample": f"{rows} rows of the workload, {len(times)} step(s) of llk + iterate "
                                    "(oracle/ppca_oracle.c, OpenMP, restatement of the reference's CPU algorithm; "
