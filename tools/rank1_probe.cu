@@ -84,6 +84,32 @@ __global__ void __launch_bounds__(WARPS * 32, 2) rank4_dmma_kernel(double *out, 
   out[blockIdx.x * blockDim.x + threadIdx.x] = s2;
 }
 
+// The serial chain of one pivot inside a panel, alone on an SM sub-partition: broadcast the pivot from the diagonal lane,
+// 1/sqrt (MUFU + third-order step), scale the lane's column entries, form the next pivot on the diagonal lane.
+// One warp per CTA, one CTA per SM: cycles per pivot = the latency floor of the elimination for one sample.
+__device__ __forceinline__ double probe_rsqrt(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double e = fma(-(x * y), y, 1.0);
+  return fma(y * e, fma(0.375, e, 0.5), y);
+}
+__global__ void chain_kernel(double *out, long long *cycles, int iters) {
+  const int lane = threadIdx.x & 31;
+  double a0 = 2.0 + lane * 1e-3, a1 = 3.0 + lane * 1e-3, d = 1.5;
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+    const double dq = __shfl_sync(0xffffu, d, it & 15);
+    const double rinv = probe_rsqrt(dq);
+    const double own0 = a0 * rinv, own1 = a1 * rinv;
+    d = fma(-own1, own1, a1 + 4.0);   // next pivot (kept positive)
+    a0 = fma(-own0, own1, a0) + 1e-3;
+    a1 = own1 * rinv + 2.5;
+  }
+  const long long t1 = clock64();
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + d;
+  if (threadIdx.x == 0 && blockIdx.x == 0) *cycles = t1 - t0;
+}
+
 template <class F> static float time_ms(F f) {
   cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   f(); CK(cudaDeviceSynchronize());
@@ -100,6 +126,12 @@ int main() {
   float b = time_ms([&] { rank1_kernel<8><<<sms * 2, 256>>>(out, iters, 1); });
   const double fl4 = 2.0 * 16 * 256 * iters * 8.0 * 2 * sms;  // rank-4 DMMA: 16 x 256 FMA per warp per step
   float c = time_ms([&] { rank4_dmma_kernel<8><<<sms * 2, 256>>>(out, iters); });
+  long long *cyc; CK(cudaMalloc(&cyc, sizeof(long long)));
+  const int chain_iters = 100000;
+  chain_kernel<<<sms, 32>>>(out, cyc, chain_iters); CK(cudaDeviceSynchronize());
+  chain_kernel<<<sms, 32>>>(out, cyc, chain_iters); CK(cudaDeviceSynchronize());
+  long long hc = 0; CK(cudaMemcpy(&hc, cyc, sizeof(hc), cudaMemcpyDeviceToHost));
+  printf("{\"pivot_chain_cycles_alone\": %.1f}\n", (double)hc / chain_iters);
   printf("{\"rank1_regs_tflops\": %.2f, \"rank1_smem_operands_tflops\": %.2f, \"rank4_dmma_smem_operands_tflops\": %.2f, \"warps_per_sm\": 16}\n",
          fl1 / a / 1e9, fl1 / b / 1e9, fl4 / c / 1e9);
   return 0;
