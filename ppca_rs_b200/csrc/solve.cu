@@ -412,6 +412,20 @@ __global__ void __launch_bounds__(256, MINB) solve_reg_kernel(SolveArgs a) {
 // d_{p+1} = T[p+1][p+1] - s_{p+1}^2 right after the barrier, so 1/sqrt(d_{p+1}) overlaps the update: one barrier per pivot.
 // Every thread tracks 1/d_i of its own rows in registers (swept rows stay in their own units, d_i x true).
 // ---------------------------------------------------------------------------------------------
+// Phase timing of solve_tile_kernel (development builds only: make NVCC_EXTRA=-DPPCA_SOLVE_TIMING): cycles per warp spent
+// in [0] load + gather, [1] the publishers' panel section, [2] waiting at the panel barrier, [3] the rank-1 updates,
+// [4] everything after the elimination; [5] = warp-samples counted.  Read with ppca_b200_debug_solve_timing (not in the ABI).
+#ifdef PPCA_SOLVE_TIMING
+__device__ unsigned long long g_solve_timing[8];
+#define PT_DECL long long pt_last = clock64(), pt_acc[5] = {0, 0, 0, 0, 0}
+#define PT_MARK(slot) { const long long pt_now = clock64(); pt_acc[slot] += pt_now - pt_last; pt_last = pt_now; }
+#define PT_FLUSH if ((threadIdx.x & 31) == 0) { for (int pt_i = 0; pt_i < 5; ++pt_i) atomicAdd(&g_solve_timing[pt_i], (unsigned long long)pt_acc[pt_i]); atomicAdd(&g_solve_timing[5], 1ull); }
+#else
+#define PT_DECL
+#define PT_MARK(slot)
+#define PT_FLUSH
+#endif
+
 template <int N>
 __device__ __forceinline__ void sample_sync(int id) {
   if constexpr (N <= 32) __syncwarp();
@@ -421,10 +435,11 @@ __device__ __forceinline__ void sample_sync(int id) {
 template <int KD, int TR, int TC>
 struct TileLayout {
   static constexpr int NTR = KD / TR, NTC = KD / TC, TPS = NTR * NTC, SPC = 256 / TPS, WPS = TPS >= 32 ? TPS / 32 : 1;
-  static constexpr int SR = 6;  // pitch (doubles) of one thread's row group in the own-units exchange: 2 x odd keeps the
-                                // 128-bit reads of eight consecutive row groups on disjoint banks
-  // PW pivots per exchange (a "panel"): the rows and the columns of a panel each sit inside one thread tile
-  static constexpr int PW = (TR % 4 == 0 && TC % 4 == 0) ? 4 : 3;
+  static constexpr int SR = TR == 2 ? 2 : 6;  // pitch (doubles) of one thread's row group in the own-units exchange: 2 x odd
+                                // keeps the 128-bit reads of eight consecutive row groups on disjoint banks (TR = 2: contiguous)
+  // PW pivots per exchange (a "panel"): its columns sit inside one thread tile, its rows in one thread (TR >= PW) or in
+  // PW / TR consecutive threads of the column block (TR = 2)
+  static constexpr int PW = (TC % 4 == 0 && (TR % 4 == 0 || 4 % TR == 0)) ? 4 : 3;
   static constexpr int PB = TR > TC ? TR : TC;          // pivots per unrolled block: static indices repeat with this period
   // one exchange buffer: PW x (true units [KD] | own units, padded [NTR SR]) | PW 1/d | pad
   static constexpr int EXQ = KD + NTR * SR;
@@ -438,7 +453,7 @@ struct TileLayout {
   static constexpr int FIXED = NBUF * EX + 3 * KD + 16;
   static_assert(KD % TR == 0 && KD % TC == 0 && TR % 2 == 0 && TC % 2 == 0 && TR <= SR, "tile shape");
   static_assert((TPS % 32 == 0 || 32 % TPS == 0) && 256 % TPS == 0 && 32 % NTR == 0, "thread layout");
-  static_assert(TR % PW == 0 && TC % PW == 0 && PB % TR == 0 && PB % TC == 0 && (PB / PW) % 2 == 0 && KD % PB == 0, "panels");
+  static_assert((TR % PW == 0 || PW % TR == 0) && TC % PW == 0 && PB % TR == 0 && PB % TC == 0 && (PB / PW) % 2 == 0 && KD % PB == 0, "panels");
   static_assert(NBUF * EX >= NTC * KD, "the partial z sums reuse the exchange buffers");
   static size_t smem_doubles(int kkp, bool colmax) {
     return (size_t)SPC * (kkp + FIXED) + (colmax ? (size_t)(SUBWARP ? 1 : SPC) * kkp : 0);
@@ -491,6 +506,7 @@ __global__ void __launch_bounds__(256, MINB) solve_tile_kernel(SolveArgs a) {
   const double ln_sigma = log(sigma);
 
   for (int row = blockIdx.x * SPC + smp; row < a.rows_pad; row += gridDim.x * SPC) {
+    PT_DECL;
     double *gsrc = a.GW + (int64_t)row * kkp;
     for (int q = t * 2; q < kkp; q += 2 * TPS)
       *reinterpret_cast<double2 *>(stage + q) = *reinterpret_cast<const double2 *>(gsrc + q);
@@ -545,26 +561,31 @@ __global__ void __launch_bounds__(256, MINB) solve_tile_kernel(SolveArgs a) {
       for (int ps = 0; ps < PB / PW; ++ps) {
         const int pp0 = ps * PW;             // first pivot of the panel within the block (compile time after unrolling)
         const int p0 = pb * PB + pp0;
-        const int a0 = pp0 % TR, cl0 = pp0 % TC;  // the panel's rows / columns inside the tile that holds them
+        const int cl0 = pp0 % TC;            // the panel's columns inside the tile that holds them
+        // row p0 + q of the panel: register row RA(q) of the thread with tr == trp + RT(q) (TR >= PW: one thread holds them all)
+#define RA(q) ((pp0 + (q)) % TR)
+#define RT(q) ((pp0 % TR + (q)) / TR)
+        const int trp = pb * (PB / TR) + pp0 / TR;
         double *ex = exch + ((ps & 1) % LY::NBUF) * EX;
         const bool pub = tc == pb * (PB / TC) + pp0 / TC;   // this thread holds the panel's columns
-        const bool prow = tr == pb * (PB / TR) + pp0 / TR;  // this thread holds the panel's rows
+        PT_MARK(ps == 0 && pb == 0 ? 0 : 3);
         if (pub) {
-          const int dlane = gbase + pb * (PB / TR) + pp0 / TR;  // lane of the thread with the panel's diagonal block
-          double dq = __shfl_sync(gmask, A[a0][cl0], dlane);
+          const int dlane = gbase + trp;  // lane of the thread with the panel's first diagonal entry
+          double dq = __shfl_sync(gmask, A[RA(0)][cl0], dlane);
 #pragma unroll
           for (int q = 0; q < PW; ++q) {
+            const bool prow = tr == trp + RT(q);  // this thread holds row p0 + q
             const double dthis = dq;
             const double rinv = fast_rsqrt(dthis);
             double own[TR], tv[TR];
 #pragma unroll
             for (int ia = 0; ia < TR; ++ia) own[ia] = A[ia][cl0 + q] * rinv;
             if (q + 1 < PW) {
-              // next pivot d' = T[p+1][p+1] - s_{p+1}^2 straight from the diagonal lane (row p + 1 is not swept yet: its
-              // own units are the true units), ahead of the panel's other updates: bitwise what the loop below leaves there
+              // next pivot d' = T[p+1][p+1] - s_{p+1}^2 straight from the lane that holds it (row p + 1 is not swept yet:
+              // its own units are the true units), ahead of the panel's other updates: bitwise what the loop below leaves
               const int n = q + 1 < PW ? q + 1 : q;
-              const double dn = fma(-own[a0 + n], own[a0 + n], A[a0 + n][cl0 + n]);
-              dq = __shfl_sync(gmask, dn, dlane);
+              const double dn = fma(-own[RA(n)], own[RA(n)], A[RA(n)][cl0 + n]);
+              dq = __shfl_sync(gmask, dn, dlane + RT(n));
             }
 #pragma unroll
             for (int ia = 0; ia < TR; ++ia) tv[ia] = own[ia] * sc[ia];
@@ -578,28 +599,31 @@ __global__ void __launch_bounds__(256, MINB) solve_tile_kernel(SolveArgs a) {
               ex[PW * EXQ + q] = rinv * rinv;
             }
             // the other columns of the panel (swept or not) take this pivot's update now: their column operands are the
-            // true-unit multipliers of the panel's own rows, which the diagonal lane holds
+            // true-unit multipliers of the panel's own rows, which the diagonal lanes hold
 #pragma unroll
             for (int q2 = 0; q2 < PW; ++q2) {
               if (q2 == q) continue;
-              const double sq = __shfl_sync(gmask, tv[a0 + q2], dlane);
+              const double sq = __shfl_sync(gmask, tv[RA(q2)], dlane + RT(q2));
 #pragma unroll
               for (int ia = 0; ia < TR; ++ia) {
-                const double f = (prow && ia == a0 + q) ? 0.0 : own[ia];  // the pivot row is left as it is
+                const double f = (prow && ia == RA(q)) ? 0.0 : own[ia];  // the pivot row is left as it is
                 A[ia][cl0 + q2] = fma(-f, sq, A[ia][cl0 + q2]);
               }
             }
 #pragma unroll
             for (int ia = 0; ia < TR; ++ia) A[ia][cl0 + q] = own[ia] * rinv;  // T[i][p] = s_i / sqrt(d)
             if (prow) {
-              A[a0 + q][cl0 + q] = -1.0;
-              sc[a0 + q] = rinv * rinv;
+              A[RA(q)][cl0 + q] = -1.0;
+              sc[RA(q)] = rinv * rinv;
             }
           }
         }
+        PT_MARK(1);
         sample_sync<TPS>(bar_id);
+        PT_MARK(2);
 #pragma unroll
         for (int q = 0; q < PW; ++q) {
+          const bool prow = tr == trp + RT(q);
           double f[TR], cv[TC];
 #pragma unroll
           for (int ia = 0; ia < TR; ia += 2) {
@@ -613,22 +637,22 @@ __global__ void __launch_bounds__(256, MINB) solve_tile_kernel(SolveArgs a) {
             cv[jb] = v.x;
             cv[jb + 1] = v.y;
           }
-          f[a0 + q] = prow ? 0.0 : f[a0 + q];  // the pivot row is left as it is (its 1/d is applied at the end)
+          f[RA(q)] = prow ? 0.0 : f[RA(q)];  // the pivot row is left as it is (its 1/d is applied at the end)
 #pragma unroll
           for (int jq = 0; jq < PW; ++jq) cv[cl0 + jq] = pub ? 0.0 : cv[cl0 + jq];  // the publishers' panel columns are done
 #pragma unroll
           for (int ia = 0; ia < TR; ++ia)
 #pragma unroll
             for (int jb = 0; jb < TC; ++jb) A[ia][jb] = fma(-f[ia], cv[jb], A[ia][jb]);
+          if (prow && !pub) sc[RA(q)] = ex[PW * EXQ + q];
         }
-        if (prow && !pub) {
-#pragma unroll
-          for (int q = 0; q < PW; ++q) sc[a0 + q] = ex[PW * EXQ + q];
-        }
+#undef RA
+#undef RT
         if constexpr (LY::NBUF == 1) sample_sync<TPS>(bar_id);  // single exchange buffer: reads done before the next panel
       }
     }
 
+    PT_MARK(3);
     sample_sync<TPS>(bar_id);  // the partial z sums below reuse the exchange buffers
 
     // M^{-1}[i][j] = -(1/d_i) A[i][j]
@@ -769,6 +793,8 @@ __global__ void __launch_bounds__(256, MINB) solve_tile_kernel(SolveArgs a) {
       }
     }
     sample_sync<TPS>(bar_id);
+    PT_MARK(4);
+    PT_FLUSH;
   }
   if (a.colmax) {
     __syncthreads();
@@ -958,6 +984,20 @@ static bool tile32_fits(const SolveArgs &a) {  // eight samples per CTA: the wid
   return LY::smem_doubles(a.s.kkp, a.colmax != nullptr) * sizeof(double) <= 110 * 1024;
 }
 
+#ifdef PPCA_SOLVE_TIMING
+}  // namespace ppca
+extern "C" __attribute__((visibility("default"))) int ppca_b200_debug_solve_timing(unsigned long long *out8, int reset) {
+  cudaDeviceSynchronize();
+  if (cudaMemcpyFromSymbol(out8, ppca::g_solve_timing, sizeof(unsigned long long) * 8) != cudaSuccess) return 1;
+  if (reset) {
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    cudaMemcpyToSymbol(ppca::g_solve_timing, z, sizeof(z));
+  }
+  return 0;
+}
+namespace ppca {
+#endif
+
 void launch_solve(const Launcher &L, const SolveArgs &a) {
   if (a.rows_pad <= 0) return;
   REQUIRE(a.mode == 0 || a.GW != nullptr, "solve: missing Gram buffer");
@@ -975,7 +1015,11 @@ void launch_solve(const Launcher &L, const SolveArgs &a) {
   else if (a.s.k <= 32 && tile32 && tile32_fits(a)) launch_solve_tile<32, 4, 8, 2>(L, a);
   else if (a.s.k <= 32) launch_solve_reg<32>(L, a);
   else if (a.s.k <= 48) launch_solve_tile<48, 6, 6, 2>(L, a);
-  else if (a.s.k <= 64) launch_solve_tile<64, 4, 8, 2>(L, a);
+  else if (a.s.k <= 64) {
+    static const bool wide = getenv("PPCA_B200_SOLVE64") && !strcmp(getenv("PPCA_B200_SOLVE64"), "2x16");
+    if (wide) launch_solve_tile<64, 2, 16, 2>(L, a);
+    else launch_solve_tile<64, 4, 8, 2>(L, a);
+  }
   else {
     REQUIRE(a.colmax == nullptr, "solve: the generic kernel (state_size > 64) does not produce column maxima");
     launch_solve_generic(L, a);
