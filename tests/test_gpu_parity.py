@@ -209,9 +209,9 @@ def _mix_case(pk, n, d, ks, seed=0):
     return X, models, logw
 
 
-@pytest.mark.parametrize("ks", [(2, 2), (4, 4, 4), (3, 5, 2, 8)])
+@pytest.mark.parametrize("ks", [(2, 2), (4, 4, 4), (3, 5, 2, 8), (34, 12, 48)])
 def test_mixture(pk, orc, ks):
-    n, d = 900, 24
+    n, d = (900, 24) if max(ks) <= 8 else (1200, 72)   # the last case runs the register-tiled solve inside the mixture pass
     X, models, logw = _mix_case(pk, n, d, ks)
     w = np.random.default_rng(5).random(X.shape[0]) + 0.5
     ds = pk.Dataset(X, w)
