@@ -423,7 +423,8 @@ def shard_block(torch, pk, pdist, ctx, stream, dist, rank, world, local_rank, ar
     (c3: d=2048 k=64, the north-star shape; c4: PPCAMix M=32), same timing rules, plus the time of its all-reduce."""
     wl = WORKLOADS[name]
     d, k, m = wl["d"], wl["k"], wl["m"]
-    ds = pk.Dataset.synthetic(rows, d, wl["k_true"], 0.1, wl["p"], n_components=max(1, m), seed=SEED + 77 + rank, ctx=ctx)
+    ds = pk.Dataset.synthetic(rows, d, wl["k_true"], 0.1, wl["p"], n_components=max(1, m), seed=SEED + 77, ctx=ctx,
+                              row_begin=rank * rows)   # every rank holds its own rows of ONE dataset
     if m == 1:
         C, mu, s = init_params(d, k, SEED + 1000)
         state = pdist.ShardedPPCA(ctx, ds, pk.PPCAModel(s, C, mu), group=dist)
@@ -538,7 +539,7 @@ def run_ours(args, wl, rank, world, local_rank):
     n, d, k, m = wl["n"], wl["d"], wl["k"], wl["m"]
     if args.rows:
         n = args.rows
-    ds = pk.Dataset.synthetic(n, d, wl["k_true"], 0.1, wl["p"], n_components=max(1, m), seed=SEED + rank, ctx=ctx)
+    ds = pk.Dataset.synthetic(n, d, wl["k_true"], 0.1, wl["p"], n_components=max(1, m), seed=SEED, ctx=ctx, row_begin=rank * n)
 
     if m == 1:
         C, mu, s = init_params(d, k, SEED + 1000)
@@ -565,7 +566,7 @@ def run_ours(args, wl, rank, world, local_rank):
     strong = None
     if m == 1 and not args.no_blocks:
         n_strong = max(256, n // world)
-        ds_s = pk.Dataset.synthetic(n_strong, d, wl["k_true"], 0.1, wl["p"], seed=SEED + 500 + rank, ctx=ctx)
+        ds_s = pk.Dataset.synthetic(n_strong, d, wl["k_true"], 0.1, wl["p"], seed=SEED + 500, ctx=ctx, row_begin=rank * n_strong)
         C, mu, s = init_params(d, k, SEED + 1000)
         st_s = pdist.ShardedPPCA(ctx, ds_s, pk.PPCAModel(s, C, mu), group=dist)
         ms_s, _, _, _ = timed_steps(torch, ctx, stream, st_s.step, args.steps, 3, dist, local_rank, sample_clocks=False)
@@ -800,7 +801,7 @@ def run_inference(args, wl, rank, world, local_rank):
     pk.set_context(ctx)
     ctx.set_gemm(args.gemm, args.slices)
     n, d, k = (args.rows or wl["n"]), wl["d"], wl["k"]
-    ds = pk.Dataset.synthetic(n, d, wl["k_true"], 0.1, wl["p"], seed=SEED + rank, ctx=ctx)
+    ds = pk.Dataset.synthetic(n, d, wl["k_true"], 0.1, wl["p"], seed=SEED, ctx=ctx, row_begin=rank * n)
     # "a trained model": 10 EM iterations on a subsample, same on every rank
     sub = pk.Dataset.synthetic(min(n, 262_144), d, wl["k_true"], 0.1, wl["p"], seed=SEED, ctx=ctx)
     C0, mu0, s0 = init_params(d, k, SEED + 1000)

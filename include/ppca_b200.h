@@ -152,6 +152,11 @@ int32_t ppca_b200_dataset_to_device(ppca_b200_ctx *ctx, const ppca_b200_dataset 
 int32_t ppca_b200_dataset_synthetic(ppca_b200_ctx *ctx, int64_t n, int32_t d, int32_t k_true,
                                     double sigma_true, double mask_prob, int32_t n_components,
                                     uint64_t seed, ppca_b200_dataset **out);
+/* Rows [row_begin, row_begin + n) of the same synthetic dataset (the generator's counters are keyed by the global row):
+ * the ranks of a sharded job pass one seed and their own row range and hold disjoint parts of ONE dataset. */
+int32_t ppca_b200_dataset_synthetic_rows(ppca_b200_ctx *ctx, int64_t row_begin, int64_t n, int32_t d, int32_t k_true,
+                                         double sigma_true, double mask_prob, int32_t n_components,
+                                         uint64_t seed, ppca_b200_dataset **out);
 /* PPCAModel::sample (ppca_model.rs:164-191): n draws x = C xi + mu + sigma eps from the given model, each entry masked
  * with probability mask_prob, generated on the device with a counter-based RNG keyed by `seed` (the reference is
  * unseeded: only the distribution can agree). */

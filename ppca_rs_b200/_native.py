@@ -76,6 +76,11 @@ _PROTOTYPES = {
         C.c_int32,
         [c_ctx_p, C.c_int64, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_uint64, C.POINTER(c_ds_p)],
     ),
+    "ppca_b200_dataset_synthetic_rows": (
+        C.c_int32,
+        [c_ctx_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_uint64,
+         C.POINTER(c_ds_p)],
+    ),
     "ppca_b200_model_sample": (
         C.c_int32,
         [c_ctx_p, C.c_int64, C.c_int32, C.c_int32, c_dp, c_dp, C.c_double, C.c_double, C.c_uint64, C.POINTER(c_ds_p)],

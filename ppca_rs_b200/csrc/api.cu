@@ -1397,19 +1397,31 @@ int32_t ppca_b200_dataset_to_device(ppca_b200_ctx *ctx, const ppca_b200_dataset 
   });
 }
 
+static void dataset_synthetic_impl(ppca_b200_ctx *ctx, int64_t row_begin, int64_t n, int32_t d, int32_t k_true,
+                                   double sigma_true, double mask_prob, int32_t n_components, uint64_t seed,
+                                   ppca_b200_dataset **out) {
+  REQUIRE(ctx != nullptr && out != nullptr, "null argument");
+  REQUIRE(n >= 1 && d >= 1 && k_true >= 1 && n_components >= 1 && row_begin >= 0, "bad synthetic shape");
+  REQUIRE(mask_prob >= 0.0 && mask_prob <= 1.0, "invalid mask probability");
+  DeviceGuard g(ctx->device);
+  auto st = make_store(ctx, n, d);
+  launch_synthetic(ctx->L(), *st, k_true, sigma_true, mask_prob, n_components, seed, row_begin);
+  launch_transpose_mask(ctx->L(), *st);
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  *out = make_dataset(ctx, st, nullptr);
+}
+
 int32_t ppca_b200_dataset_synthetic(ppca_b200_ctx *ctx, int64_t n, int32_t d, int32_t k_true, double sigma_true,
                                     double mask_prob, int32_t n_components, uint64_t seed, ppca_b200_dataset **out) {
-  return guarded([&] {
-    REQUIRE(ctx != nullptr && out != nullptr, "null argument");
-    REQUIRE(n >= 1 && d >= 1 && k_true >= 1 && n_components >= 1, "bad synthetic shape");
-    REQUIRE(mask_prob >= 0.0 && mask_prob <= 1.0, "invalid mask probability");
-    DeviceGuard g(ctx->device);
-    auto st = make_store(ctx, n, d);
-    launch_synthetic(ctx->L(), *st, k_true, sigma_true, mask_prob, n_components, seed);
-    launch_transpose_mask(ctx->L(), *st);
-    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-    *out = make_dataset(ctx, st, nullptr);
-  });
+  return guarded([&] { dataset_synthetic_impl(ctx, 0, n, d, k_true, sigma_true, mask_prob, n_components, seed, out); });
+}
+
+// rows [row_begin, row_begin + n) of the synthetic dataset: every counter of the generator is keyed by the global row, so
+// the ranks of a sharded job hold disjoint row ranges of ONE dataset (same truth) when they pass the same seed
+int32_t ppca_b200_dataset_synthetic_rows(ppca_b200_ctx *ctx, int64_t row_begin, int64_t n, int32_t d, int32_t k_true,
+                                         double sigma_true, double mask_prob, int32_t n_components, uint64_t seed,
+                                         ppca_b200_dataset **out) {
+  return guarded([&] { dataset_synthetic_impl(ctx, row_begin, n, d, k_true, sigma_true, mask_prob, n_components, seed, out); });
 }
 
 int32_t ppca_b200_model_sample(ppca_b200_ctx *ctx, int64_t n, int32_t d, int32_t k, const double *C, const double *mu,

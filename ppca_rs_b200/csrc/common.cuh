@@ -217,7 +217,7 @@ void launch_transpose_mask(const Launcher &L, SampleStore &st);
 void launch_export(const Launcher &L, const SampleStore &st, int64_t row0, int64_t nrows, double *out_dev);
 void launch_empty_dims(const Launcher &L, const SampleStore &st, uint8_t *out_dev);
 void launch_synthetic(const Launcher &L, SampleStore &st, int k_true, double sigma_true, double mask_prob,
-                      int n_components, uint64_t seed);
+                      int n_components, uint64_t seed, int64_t row_begin = 0);
 void launch_synth_truth(const Launcher &L, int d, int k_true, int n_components, uint64_t seed, double *Ct_dev, double *mut_dev);
 // fast single-model generator (Xi -> DMMA row GEMM -> noise + mask): rows [row_offset, row_offset + rows) of the dataset into
 // local rows [0, rows) of st; ws = synth_ws_doubles(rows, d, k) doubles of workspace

@@ -241,21 +241,21 @@ size_t synth_ws_doubles(int64_t rows, int d, int k);
 
 // rows of a resident dataset through the fast generator, block by block (the GEMM workspace is rows x d doubles)
 static void generate_resident(const Launcher &L, SampleStore &st, int k, const double *C_dev, const double *mu_dev, double sigma,
-                              double mask_prob, uint64_t seed) {
+                              double mask_prob, uint64_t seed, int64_t row_begin = 0) {
   const int64_t blk = std::max<int64_t>(128, std::min<int64_t>(((int64_t)1 << 30) / ((int64_t)st.d * 8) / 128 * 128, 1 << 18));
   DevBuf<double> ws;
   if (st.n <= 0) return;
   ws.alloc(synth_ws_doubles(std::min<int64_t>(blk, st.n), st.d, k));
   for (int64_t r0 = 0; r0 < st.n; r0 += blk) {
     const int64_t rows = std::min<int64_t>(blk, st.n - r0);
-    launch_generate_rows(L, st.d, st.X.p + r0 * st.ldx, st.ldx, st.mask.p + r0 * st.dw, st.dw, st.dn.p + r0, rows, r0, k, C_dev,
-                         mu_dev, sigma, mask_prob, seed, ws.p);
+    launch_generate_rows(L, st.d, st.X.p + r0 * st.ldx, st.ldx, st.mask.p + r0 * st.dw, st.dw, st.dn.p + r0, rows, row_begin + r0,
+                         k, C_dev, mu_dev, sigma, mask_prob, seed, ws.p);
   }
   CUDA_CHECK(cudaStreamSynchronize(L.stream));  // ws is freed on return
 }
 
 void launch_synthetic(const Launcher &L, SampleStore &st, int k_true, double sigma_true, double mask_prob,
-                      int n_components, uint64_t seed) {
+                      int n_components, uint64_t seed, int64_t row_begin) {
   DevBuf<double> Ct, mut;
   Ct.alloc((size_t)n_components * st.d * k_true);
   mut.alloc((size_t)n_components * st.d);
@@ -263,7 +263,7 @@ void launch_synthetic(const Launcher &L, SampleStore &st, int k_true, double sig
   CUDA_CHECK(cudaGetLastError());
   ++*L.launch_counter;
   if (n_components == 1) {
-    generate_resident(L, st, k_true, Ct.p, mut.p, sigma_true, mask_prob, seed);
+    generate_resident(L, st, k_true, Ct.p, mut.p, sigma_true, mask_prob, seed, row_begin);
     return;
   }
   const int threads = 256;
@@ -271,7 +271,7 @@ void launch_synthetic(const Launcher &L, SampleStore &st, int k_true, double sig
   const size_t smem = sizeof(double) * (threads / 32) * k_true;
   synth_kernel<<<(unsigned)blocks, threads, smem, L.stream>>>(st.n, st.d, k_true, n_components, sigma_true, mask_prob,
                                                               seed, Ct.p, mut.p, st.X.p, st.ldx, st.mask.p, st.dw,
-                                                              st.dn.p, 0);
+                                                              st.dn.p, row_begin);
   CUDA_CHECK(cudaGetLastError());
   ++*L.launch_counter;
   CUDA_CHECK(cudaStreamSynchronize(L.stream));  // Ct / mut are freed on return

@@ -116,12 +116,15 @@ class Dataset:
 
     @classmethod
     def synthetic(cls, n: int, d: int, k_true: int, sigma_true: float = 0.1, mask_prob: float = 0.2,
-                  n_components: int = 1, seed: int = 20240531, ctx: Optional[nat.Context] = None) -> "Dataset":
-        """Device-generated data with the reference sampler's semantics (ppca_model.rs:164-191)."""
+                  n_components: int = 1, seed: int = 20240531, ctx: Optional[nat.Context] = None,
+                  row_begin: int = 0) -> "Dataset":
+        """Device-generated data with the reference sampler's semantics (ppca_model.rs:164-191).  `row_begin`: rows
+        [row_begin, row_begin + n) of the dataset — the ranks of a sharded job pass one seed and their own row range."""
         ctx = ctx or nat.get_context()
         h = nat.c_ds_p()
-        nat.check(nat.lib().ppca_b200_dataset_synthetic(ctx.handle, int(n), int(d), int(k_true), float(sigma_true),
-                                                        float(mask_prob), int(n_components), int(seed), C.byref(h)))
+        nat.check(nat.lib().ppca_b200_dataset_synthetic_rows(ctx.handle, int(row_begin), int(n), int(d), int(k_true),
+                                                             float(sigma_true), float(mask_prob), int(n_components),
+                                                             int(seed), C.byref(h)))
         return cls._wrap(h, ctx)
 
     @classmethod
@@ -298,10 +301,8 @@ class GeneratedDataset:
 
     def materialize(self) -> "Dataset":
         """The same rows as a resident Dataset (for tests / small sizes)."""
-        if self.row_begin == 0:
-            return Dataset.synthetic(self.n, self.d, self.k_true, self.sigma_true, self.mask_prob, 1, self.seed, self._ctx)
-        return Dataset.synthetic(self.row_begin + self.n, self.d, self.k_true, self.sigma_true, self.mask_prob, 1,
-                                 self.seed, self._ctx)._slice(self.row_begin, self.n)
+        return Dataset.synthetic(self.n, self.d, self.k_true, self.sigma_true, self.mask_prob, 1, self.seed, self._ctx,
+                                 row_begin=self.row_begin)
 
 
 class HostDataset:

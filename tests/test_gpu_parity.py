@@ -1259,6 +1259,9 @@ def test_generated_dataset_equals_the_stored_rows(pk, orc, chunk):
     assert len(stored) == n
     whole = pk.Dataset.synthetic(1234 + n, d, k_true, 0.1, 0.3, seed=99).numpy()
     assert np.array_equal(stored.numpy(), whole[1234:], equal_nan=True)
+    mixed = pk.Dataset.synthetic(1234 + 700, d, k_true, 0.1, 0.3, n_components=3, seed=98).numpy()
+    part = pk.Dataset.synthetic(700, d, k_true, 0.1, 0.3, n_components=3, seed=98, row_begin=1234).numpy()
+    assert np.array_equal(part, mixed[1234:], equal_nan=True)     # row ranges of ONE dataset, mixtures of truths too
     _, C0, mu0, s0 = _case(50, d, k, 0.2, seed=3)
     model = pk.PPCAModel(s0, C0, mu0)
     ctx.set_chunk(chunk)

@@ -84,16 +84,18 @@ def main():
         lines += [f"2 GPUs (`gpurun --gpus 2`, torchrun, NCCL inside the library): c2 weak {c2x2['value']/1e6:.0f} M/s "
                   f"({c2x2['value']/c2['value']:.2f}× of one GPU), strong (1 M rows total) {s2['value']/1e6:.0f} M/s, e2e "
                   f"{c2x2['e2e']['value']/1e6:.1f} M/s; c3 shard {c2x2['c3_shard']['value']/1e6:.2f} M/s with its 35 MB all-reduce at "
-                  f"{c2x2['c3_shard']['comm_ms_per_step']:.3f} ms ({c2x2['c3_shard'].get('comm_gb_per_s', 0):.0f} GB/s); c4 shard all-reduce "
-                  f"({c2x2['c4_shard']['allreduce_bytes']/1e6:.0f} MB, all 32 components at once) {c2x2['c4_shard']['comm_ms_per_step']:.3f} ms.", ""]
+                  f"{c2x2['c3_shard']['comm_ms_per_step']:.3f} ms ({c2x2['c3_shard'].get('comm_gb_per_s', 0):.0f} GB/s); c4 shard {c2x2['c4_shard']['value']/1e6:.2f} M/s "
+                  f"({c2x2['c4_shard']['ms_per_step']:.0f} ms; all-reduce of {c2x2['c4_shard']['allreduce_bytes']/1e6:.0f} MB, all 32 components at once, "
+                  f"{c2x2['c4_shard']['comm_ms_per_step']:.3f} ms); c3 as specified {c2x2['c3_full']['value']/1e6:.1f} M/s.", ""]
     lines += ["## Second half of round 2", "",
               "* Per-sample solve, 32 < k <= 64: register-tiled, panel-blocked sweep (`solve_tile_kernel`): c5 solve 60.2 -> 46.9 ms, c3s 29.7 -> 26.4 ms;",
               "  seven measured variants and the ncu analysis (latency-bound serial chain per pivot, four samples resident per SM) in",
               "  `r02_solve_tile.md`; `tools/rank1_probe.cu`: the rank-1 update pattern alone runs at 87 % of the FP64 peak.",
               "* Mixture EM: the chunk loop (4 500 launches per step at M = 32) replays from a captured CUDA graph: c4 shard 223 -> 99 ms on a",
               "  host whose launch rate bounded the step (`r02_launches_c4.csv`: 49 ms of kernels per 65 536 rows); on fast hosts 106 -> 99 ms.",
-              "  With more ranks the c4 block is data dependent: a rank whose random start leaves components with next to no",
-              "  responsibility mass repeats those components one rung up the precision ladder (2-GPU run: 120 repeats, 239 ms).",
+              "  The ranks of the bench hold row ranges of ONE synthetic dataset (`Dataset.synthetic(..., row_begin=rank * rows)`); when every",
+              "  rank drew its own truth (earlier runs), a rank whose random start left components with next to no responsibility mass",
+              "  repeated those components up the precision ladder every step (2 GPUs: 120 repeats, 201-239 ms instead of 103).",
               "* Out-of-core EM over regenerated chunks (`ppca_b200_iterate_generated`): BASELINE configs[2] as specified; the generator",
               "  (xi -> DMMA row GEMM -> noise + mask) went from 5.9 s to 0.31 s per 12.5 M rows.",
               "* Widened into SURVEY §8(f): device ingestion (`__cuda_array_interface__` / DLPack), every sampler and the full covariances on the device.",
