@@ -87,6 +87,14 @@ def main():
                   f"{c2x2['c3_shard']['comm_ms_per_step']:.3f} ms ({c2x2['c3_shard'].get('comm_gb_per_s', 0):.0f} GB/s); c4 shard {c2x2['c4_shard']['value']/1e6:.2f} M/s "
                   f"({c2x2['c4_shard']['ms_per_step']:.0f} ms; all-reduce of {c2x2['c4_shard']['allreduce_bytes']/1e6:.0f} MB, all 32 components at once, "
                   f"{c2x2['c4_shard']['comm_ms_per_step']:.3f} ms); c3 as specified {c2x2['c3_full']['value']/1e6:.1f} M/s.", ""]
+    c8 = L("r02_bench_c2_8gpu.json")
+    if c8:
+        lines += [f"8 GPUs (`gpurun --gpus 8`, the driver's command `bench.py --gpus 8 --steps 20 --warmup 5`): c2 weak {c8['value']/1e6:.0f} M/s "
+                  f"({c8['value']/c2['value']:.2f}x of one GPU, {c8['ms_per_step']:.2f} ms per step), strong (1 M rows total) {c8['strong_scaling']['value']/1e6:.0f} M/s, "
+                  f"e2e {c8['e2e']['value']/1e6:.0f} M/s ({c8['e2e']['h2d_gb_per_s']:.1f} GB/s of H2D per GPU: the host, not the engine, is the limit); "
+                  f"c3 shard {c8['c3_shard']['value']/1e6:.1f} M/s (35 MB all-reduce {c8['c3_shard']['comm_ms_per_step']:.3f} ms); "
+                  f"c4 shard {c8['c4_shard']['value']/1e6:.2f} M/s; **c3 as specified, all N = 100 M rows: {c8['c3_full']['value']/1e6:.1f} M samples·iters/s, "
+                  f"{c8['c3_full']['ms_per_step']/1e3:.2f} s per EM iteration**.", ""]
     lines += ["## Second half of round 2", "",
               "* Per-sample solve, 32 < k <= 64: register-tiled, panel-blocked sweep (`solve_tile_kernel`): c5 solve 60.2 -> 46.9 ms, c3s 29.7 -> 26.4 ms;",
               "  seven measured variants and the ncu analysis (latency-bound serial chain per pivot, four samples resident per SM) in",
