@@ -95,6 +95,17 @@ def main():
                   f"c3 shard {c8['c3_shard']['value']/1e6:.1f} M/s (35 MB all-reduce {c8['c3_shard']['comm_ms_per_step']:.3f} ms); "
                   f"c4 shard {c8['c4_shard']['value']/1e6:.2f} M/s; **c3 as specified, all N = 100 M rows: {c8['c3_full']['value']/1e6:.1f} M samples·iters/s, "
                   f"{c8['c3_full']['ms_per_step']/1e3:.2f} s per EM iteration**.", ""]
+    c4g = L("r02_bench_c2_4gpu.json")
+    if c8 and c4g and c2x2:
+        rows_ = [(1, c2), (2, c2x2), (4, c4g), (8, c8)]
+        lines += ["### Scaling on one box (every line: `bench.py --gpus N` under torchrun, NCCL inside the library)", "",
+                  "| GPUs | c2 weak (M/s) | eff. | c2 strong, 1 M rows total (M/s) | c2 e2e (M/s) | H2D per GPU (GB/s) | c3 shard (M/s) | c4 shard (M/s) | c3 as specified (M/s) |",
+                  "|---|---|---|---|---|---|---|---|---|"]
+        for n_, j_ in rows_:
+            ss = j_.get("strong_scaling") or {}
+            lines.append(f"| {n_} | {j_['value']/1e6:.0f} | {j_['value']/c2['value']/n_:.3f} | {ss.get('value', 0)/1e6:.0f} | {j_['e2e']['value']/1e6:.1f} | "
+                         f"{j_['e2e']['h2d_gb_per_s']:.1f} | {j_['c3_shard']['value']/1e6:.1f} | {j_['c4_shard']['value']/1e6:.2f} | {j_['c3_full']['value']/1e6:.1f} |")
+        lines.append("")
     lines += ["## Second half of round 2", "",
               "* Per-sample solve, 32 < k <= 64: register-tiled, panel-blocked sweep (`solve_tile_kernel`): c5 solve 60.2 -> 46.9 ms, c3s 29.7 -> 26.4 ms;",
               "  seven measured variants and the ncu analysis (latency-bound serial chain per pivot, four samples resident per SM) in",
