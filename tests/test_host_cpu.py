@@ -417,3 +417,24 @@ def test_generated_dataset_describes_a_row_range():
         pk.GeneratedDataset(10, 4, 2)
     with pytest.raises(ValueError):
         pk.GeneratedDataset(-1, 4, 2, ctx=object())
+
+
+def test_bench_reference_arm_emits_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours): ONE JSON line with the contract's keys,
+    `impl`, a `cpu_baseline` describing the run and an `e2e` block that repeats the line's own value (no device copies)."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "c1",
+                          "--steps", "2", "--warmup", "1"], capture_output=True, text=True, timeout=600, check=True).stdout
+    lines = [ln for ln in out.strip().splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    j = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in j, key
+    assert j["impl"] == "reference" and j["higher_is_better"] is True and j["vs_baseline"] is None
+    assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1 and j["cpu_baseline"]["value"] == j["value"]
+    assert j["e2e"] == {"value": j["value"], "unit": j["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert set(j["config"]) >= {"workload", "rows_per_gpu", "d", "k", "components"}
