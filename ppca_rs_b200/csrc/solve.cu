@@ -218,16 +218,19 @@ __device__ __forceinline__ double fast_rsqrt(double x) {
   return fma(y * e, fma(0.375, e, 0.5), y);
 }
 
-template <int KP, int MINB>
+// PF: the packed rows of the NEXT group of samples are fetched with cp.async into a second staging buffer while this group
+// is eliminated (ncu: long_scoreboard 2.0 of 10.9 stall cycles per instruction = the warp waiting for its own G loads).
+template <int KP, int MINB, bool PF>
 __global__ void __launch_bounds__(256, MINB) solve_reg_kernel(SolveArgs a) {
   constexpr int SPW = 32 / KP;
+  constexpr int NST = PF ? 2 : 1;
   extern __shared__ __align__(16) double smem_reg[];
   const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5, warps = blockDim.x >> 5;
   const int sub = lane / KP, li = lane % KP;
   const int k = a.s.k, kkp = a.s.kkp, kp = a.s.kp;
-  const int per_warp = SPW * kkp + 128;
-  double *stage = smem_reg + (size_t)wi * per_warp;  // SPW packed rows
-  double *col = stage + SPW * kkp;                   // [2][32] pivot-column exchange
+  const int per_warp = NST * SPW * kkp + 128;
+  double *stage0 = smem_reg + (size_t)wi * per_warp;  // NST x SPW packed rows
+  double *col = stage0 + NST * SPW * kkp;             // [2][32] pivot-column exchange
   double *yb = col + 64;                             // [32]
   double *zb = yb + 32;                              // [32]; zb[31 - ...] is never read beyond KP per sample
   // running max |W| per staged slot of this warp (column maxima for the int8 digit planes, fused here so the
@@ -247,16 +250,32 @@ __global__ void __launch_bounds__(256, MINB) solve_reg_kernel(SolveArgs a) {
   for (int j = 0; j < KP; ++j)
     gi[j] = (li < k && j < k) ? ((j >= li) ? up + j : ((j * (2 * k - j - 1)) >> 1) + li) : -1;
 
-  for (int g = blockIdx.x * warps + wi; g < groups; g += gridDim.x * warps) {
+  const int gstride = gridDim.x * warps;
+  auto fetch = [&](int g2, double *dst) {  // 16-byte asynchronous copies of one group's packed rows (PF only)
+    if (g2 < groups) {
+      const double *src = a.GW + (int64_t)g2 * SPW * kkp;
+      for (int q = lane * 2; q < SPW * kkp; q += 64) cp_async16(dst + q, src + q, 16);
+    }
+    cp_async_commit();
+  };
+  int it = 0;
+  if constexpr (PF) fetch(blockIdx.x * warps + wi, stage0);
+  for (int g = blockIdx.x * warps + wi; g < groups; g += gstride, ++it) {
     const int row0 = g * SPW;
     const int row = row0 + sub;
     double *gsrc = a.GW + (int64_t)row0 * kkp;
-    for (int q = lane * 2; q < SPW * kkp; q += 64)
-      *reinterpret_cast<double2 *>(stage + q) = *reinterpret_cast<const double2 *>(gsrc + q);
+    double *stage = stage0 + (PF ? (it & 1) * SPW * kkp : 0);
+    if constexpr (PF) {
+      fetch(g + gstride, stage0 + ((it + 1) & 1) * SPW * kkp);  // the other buffer's last reader finished before the warp sync that ended the previous iteration
+    } else {
+      for (int q = lane * 2; q < SPW * kkp; q += 64)
+        *reinterpret_cast<double2 *>(stage + q) = *reinterpret_cast<const double2 *>(gsrc + q);
+    }
     yb[lane] = (li < kp) ? a.YZ[(int64_t)row * kp + li] : 0.0;
     const int dn = row < a.rows ? a.dn[row] : 0;
     const bool empty = dn == 0;
     const double w = (a.w && row < a.rows) ? a.w[row] : (row < a.rows ? 1.0 : 0.0);
+    if constexpr (PF) cp_async_wait<1>();
     __syncwarp();
 
     const double *st = stage + sub * kkp;
@@ -383,6 +402,7 @@ __global__ void __launch_bounds__(256, MINB) solve_reg_kernel(SolveArgs a) {
     }
     __syncwarp();
   }
+  if constexpr (PF) cp_async_wait<0>();
   if (a.colmax) {
     __syncthreads();
     const double *all = smem_reg + (size_t)warps * per_warp;
@@ -826,14 +846,14 @@ static void launch_solve_tile(const Launcher &L, const SolveArgs &a) {
   L.count(V_SOLVE_TILE);
 }
 
-template <int KP, int MINB>
-static void launch_solve_reg_b(const Launcher &L, const SolveArgs &a) {
+template <int KP, int MINB, bool PF>
+static void launch_solve_reg_pf(const Launcher &L, const SolveArgs &a) {
   constexpr int SPW = 32 / KP;
   const int warps = 8;
-  const size_t smem = (size_t)warps * (SPW * a.s.kkp + 128 + (a.colmax ? SPW * a.s.kkp : 0)) * sizeof(double);
+  const size_t smem = (size_t)warps * ((PF ? 2 : 1) * SPW * a.s.kkp + 128 + (a.colmax ? SPW * a.s.kkp : 0)) * sizeof(double);
   static PerDeviceOnce configured;
   if (configured.need()) {
-    CUDA_CHECK(cudaFuncSetAttribute(solve_reg_kernel<KP, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CUDA_CHECK(cudaFuncSetAttribute(solve_reg_kernel<KP, MINB, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
   }
   const int groups = (a.rows_pad + SPW - 1) / SPW;
   int64_t blocks = (groups + warps - 1) / warps;
@@ -841,10 +861,19 @@ static void launch_solve_reg_b(const Launcher &L, const SolveArgs &a) {
   // balances to < 1 %, where a 2.67-wave grid left the last third of the SMs idle for a whole CTA lifetime
   const int64_t cap = (int64_t)L.sms * MINB;
   if (blocks > cap) blocks = cap;
-  solve_reg_kernel<KP, MINB><<<(unsigned)blocks, warps * 32, smem, L.stream>>>(a);
+  solve_reg_kernel<KP, MINB, PF><<<(unsigned)blocks, warps * 32, smem, L.stream>>>(a);
   CUDA_CHECK(cudaGetLastError());
   ++*L.launch_counter;
   L.count(KP == 8 ? V_SOLVE_REG8 : KP == 16 ? V_SOLVE_REG16 : V_SOLVE_REG32);
+}
+
+template <int KP, int MINB>
+static void launch_solve_reg_b(const Launcher &L, const SolveArgs &a) {
+  // measured (tools/gpu_r2ac.sh): k = 32 (c4) 45.8 -> 43.0 ms with the prefetch, k = 16 (c2) 1.53 -> 1.63 ms: on for KP = 32 only
+  static const char *env = getenv("PPCA_B200_SOLVE_PREFETCH");
+  const bool prefetch = env ? strcmp(env, "0") != 0 : KP == 32;
+  if (prefetch) launch_solve_reg_pf<KP, MINB, true>(L, a);
+  else launch_solve_reg_pf<KP, MINB, false>(L, a);
 }
 
 template <int KP>
