@@ -13,7 +13,7 @@ from typing import Dict, Optional
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libppca_b200.so")
+LIB_PATH = os.environ.get("PPCA_B200_LIB") or os.path.join(_HERE, "libppca_b200.so")  # override: A/B runs of two builds
 
 c_ctx_p = C.c_void_p
 c_ds_p = C.c_void_p

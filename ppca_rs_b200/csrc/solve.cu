@@ -465,10 +465,13 @@ struct TileLayout {
   static constexpr int EXQ = KD + NTR * SR;
   static constexpr int EX = PW * EXQ + 4;
   // Samples narrower than a warp (KD = 16: 8 threads, four samples per warp) synchronise with __syncwarp, which costs
-  // next to nothing: ONE exchange buffer and a second sync after the reads instead of two buffers; and one array of column
-  // maxima per CTA (shared-memory atomicMax) instead of one per sample slot — 32 samples per CTA have to fit.
+  // next to nothing: ONE exchange buffer and a second sync after the reads instead of two buffers (32 samples per CTA have to fit).
   static constexpr bool SUBWARP = TPS < 32;
   static constexpr int NBUF = SUBWARP ? 1 : 2;
+  // two staging buffers per sample: the next sample's packed G arrives by cp.async during this sample's elimination.  Same-box
+  // A/B (tools/gpu_r2ae.sh): k = 48 solve 47.5 -> 45.0 ms, k = 64 27.15 -> 27.54 ms: on for KD = 48 only.  One array of column
+  // maxima per CTA (shared-memory atomicMax) instead of one per sample slot pays for the second buffer.
+  static constexpr int NSTAGE = KD == 48 ? 2 : 1;
   // per sample: stage[kkp] | exch[NBUF][EX] (reused for the partial z sums after the elimination) | yb[KD] | zb[KD] | piv[KD] | red[16]
   static constexpr int FIXED = NBUF * EX + 3 * KD + 16;
   static_assert(KD % TR == 0 && KD % TC == 0 && TR % 2 == 0 && TC % 2 == 0 && TR <= SR, "tile shape");
@@ -476,7 +479,7 @@ struct TileLayout {
   static_assert((TR % PW == 0 || PW % TR == 0) && TC % PW == 0 && PB % TR == 0 && PB % TC == 0 && (PB / PW) % 2 == 0 && KD % PB == 0, "panels");
   static_assert(NBUF * EX >= NTC * KD, "the partial z sums reuse the exchange buffers");
   static size_t smem_doubles(int kkp, bool colmax) {
-    return (size_t)SPC * (kkp + FIXED) + (colmax ? (size_t)(SUBWARP ? 1 : SPC) * kkp : 0);
+    return (size_t)SPC * (NSTAGE * kkp + FIXED) + (colmax ? (size_t)kkp : 0);
   }
 };
 
@@ -503,33 +506,45 @@ __global__ void __launch_bounds__(256, MINB) solve_tile_kernel(SolveArgs a) {
   // rows / columns past k are identity padding whose pivots change nothing: whole pivot blocks past k are skipped
   const int nblk = (k + PB - 1) / PB;
   const int kpiv = nblk * PB;
-  const int per_smp = kkp + LY::FIXED;
-  double *stage = smem_reg + (size_t)smp * per_smp;  // one packed row: G in, W out
-  double *exch = stage + kkp;
+  const int per_smp = LY::NSTAGE * kkp + LY::FIXED;
+  double *stage0 = smem_reg + (size_t)smp * per_smp;  // NSTAGE packed rows: G in, W out
+  double *exch = stage0 + LY::NSTAGE * kkp;
   double *yb = exch + LY::NBUF * EX;
   double *zb = yb + KD;
   double *piv = zb + KD;
   double *red = piv + KD;
   double *zpart = exch;  // [NTC][KD], after the elimination
-  // running max |W|: per sample slot, or (sub-warp samples) one array per CTA updated with shared-memory atomics
-  double *cmw = smem_reg + (size_t)SPC * per_smp + (LY::SUBWARP ? 0 : (size_t)smp * kkp);
+  // running max |W|: one array per CTA, updated with shared-memory atomics during the write-back
+  double *cmw = smem_reg + (size_t)SPC * per_smp;
   if (a.colmax) {
-    if constexpr (LY::SUBWARP) {
-      for (int q = threadIdx.x; q < kkp; q += blockDim.x) cmw[q] = 0.0;
-      __syncthreads();
-    } else {
-      for (int q = t; q < kkp; q += TPS) cmw[q] = 0.0;
-    }
+    for (int q = threadIdx.x; q < kkp; q += blockDim.x) cmw[q] = 0.0;
+    __syncthreads();
   }
   const double sigma = a.sigma_dev ? *a.sigma_dev : a.sigma;  // device copy: the launch can be replayed from a CUDA graph
   const double s2 = sigma * sigma;
   const double ln_sigma = log(sigma);
 
-  for (int row = blockIdx.x * SPC + smp; row < a.rows_pad; row += gridDim.x * SPC) {
+  auto fetch = [&](int row2, double *dst) {  // asynchronous 16-byte copies of one sample's packed G (NSTAGE == 2)
+    if (row2 < a.rows_pad) {
+      const double *src = a.GW + (int64_t)row2 * kkp;
+      for (int q = t * 2; q < kkp; q += 2 * TPS) cp_async16(dst + q, src + q, 16);
+    }
+    cp_async_commit();
+  };
+  const int rstride = gridDim.x * SPC;
+  int it = 0;
+  if constexpr (LY::NSTAGE == 2) fetch(blockIdx.x * SPC + smp, stage0);
+  for (int row = blockIdx.x * SPC + smp; row < a.rows_pad; row += rstride, ++it) {
     PT_DECL;
     double *gsrc = a.GW + (int64_t)row * kkp;
-    for (int q = t * 2; q < kkp; q += 2 * TPS)
-      *reinterpret_cast<double2 *>(stage + q) = *reinterpret_cast<const double2 *>(gsrc + q);
+    double *stage = stage0 + (LY::NSTAGE == 2 ? (it & 1) * kkp : 0);
+    if constexpr (LY::NSTAGE == 2) {
+      fetch(row + rstride, stage0 + ((it + 1) & 1) * kkp);  // its last reader (the previous sample's write-back) is behind a barrier
+      cp_async_wait<1>();
+    } else {
+      for (int q = t * 2; q < kkp; q += 2 * TPS)
+        *reinterpret_cast<double2 *>(stage + q) = *reinterpret_cast<const double2 *>(gsrc + q);
+    }
     for (int r = t; r < KD; r += TPS) yb[r] = (r < kp) ? a.YZ[(int64_t)row * kp + r] : 0.0;
     const int dn = row < a.rows ? a.dn[row] : 0;
     const bool empty = dn == 0;
@@ -796,19 +811,12 @@ __global__ void __launch_bounds__(256, MINB) solve_tile_kernel(SolveArgs a) {
       for (int q = t * 2; q < kkp; q += 2 * TPS) {
         const double2 v = *reinterpret_cast<const double2 *>(stage + q);
         *reinterpret_cast<double2 *>(gsrc + q) = v;
-        if (a.colmax) {
-          if constexpr (LY::SUBWARP) {  // one array per CTA: non-negative doubles order like their bit patterns
-            unsigned long long *cm = reinterpret_cast<unsigned long long *>(cmw + q);
-            const unsigned long long bx = (unsigned long long)__double_as_longlong(fabs(v.x));
-            const unsigned long long by = (unsigned long long)__double_as_longlong(fabs(v.y));
-            if (bx > cm[0]) atomicMax(cm, bx);
-            if (by > cm[1]) atomicMax(cm + 1, by);
-          } else {
-            double2 m = *reinterpret_cast<const double2 *>(cmw + q);
-            m.x = fmax(m.x, fabs(v.x));
-            m.y = fmax(m.y, fabs(v.y));
-            *reinterpret_cast<double2 *>(cmw + q) = m;
-          }
+        if (a.colmax) {  // one array per CTA: non-negative doubles order like their bit patterns
+          unsigned long long *cm = reinterpret_cast<unsigned long long *>(cmw + q);
+          const unsigned long long bx = (unsigned long long)__double_as_longlong(fabs(v.x));
+          const unsigned long long by = (unsigned long long)__double_as_longlong(fabs(v.y));
+          if (bx > cm[0]) atomicMax(cm, bx);
+          if (by > cm[1]) atomicMax(cm + 1, by);
         }
       }
     }
@@ -816,13 +824,11 @@ __global__ void __launch_bounds__(256, MINB) solve_tile_kernel(SolveArgs a) {
     PT_MARK(4);
     PT_FLUSH;
   }
+  if constexpr (LY::NSTAGE == 2) cp_async_wait<0>();
   if (a.colmax) {
     __syncthreads();
-    const double *all = smem_reg + (size_t)SPC * per_smp;
     for (int c = threadIdx.x; c < kkp; c += blockDim.x) {
-      double m = 0.0;
-#pragma unroll
-      for (int j = 0; j < (LY::SUBWARP ? 1 : SPC); ++j) m = fmax(m, all[(size_t)j * kkp + c]);
+      const double m = cmw[c];
       if (m > 0.0) atomicMax(a.colmax + c, (unsigned long long)__double_as_longlong(m));
     }
   }
